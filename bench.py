@@ -1,0 +1,309 @@
+#!/usr/bin/env python
+"""bench.py — Gibbs allocation sweeps of the multiview Pitman-Yor sampler on B200.
+
+    python bench.py --gpus N --steps K --warmup W           (N > 1: launched under torchrun)
+    python bench.py --impl reference --gpus N --steps K --warmup W
+
+Workload (BASELINE.json configs[2], SURVEY.md §8d "C3"): synthetic 3-view Gaussian mixture,
+N = 1M customers, D = 64 per view, cap K = 64 tables/dishes, FP32, seed 1999.  A "step" is ONE sweep
+of the hot path: likelihood + draw for every customer, birth/death bookkeeping, sufficient-statistics
+rebuild and the hyperparameter step.  metric = obs x view x K updates per second (whole job).
+With N GPUs the customers are row-sharded (total work fixed: strong scaling) and the per-table
+statistics are exchanged by one NCCL all-gather per sweep.
+
+The timed `value` has the data resident in HBM (inputs 768 MB >> 126 MB L2, so every sweep streams
+from HBM; no extra L2 flush).  `e2e` is the same metric through the reference-facing call with HOST
+buffers: upload of the views from pinned memory, state set, K sweeps, read-back of table_of.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+from pathlib import Path
+
+import numpy as np
+
+ROOT = Path(__file__).resolve().parent
+for p in (ROOT, ROOT / "multiview-clustering_b200"):
+    if str(p) not in sys.path:
+        sys.path.insert(0, str(p))
+
+N_ROWS = 1_000_000
+DIMS = [64, 64, 64]
+CAP = 64
+SEED = 1999
+METRIC = "obs_x_view_x_K_updates_per_s"
+UNIT = "updates/s"
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=30)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--rows", type=int, default=N_ROWS, help="total customers (default: the named config)")
+    ap.add_argument("--engine", type=int, default=0, help="0 auto, 1 CUDA-core, 2 tcgen05")
+    ap.add_argument("--no-hyper", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--cpu-rows", type=int, default=0, help="rows of the CPU sample (0: sized for ~15 s)")
+    return ap.parse_args()
+
+
+# ---------------------------------------------------------------------------------------------
+# synthetic workload: z ~ U{0..63}, mu_vk ~ N(0, 2^2 I), x = mu + N(0, I)
+# ---------------------------------------------------------------------------------------------
+def planted_means(rng):
+    return [rng.normal(0.0, 2.0, (CAP, d)).astype(np.float32) for d in DIMS]
+
+
+def make_rows_numpy(lo, hi, mus, seed=SEED):
+    """Rows [lo, hi) of the global data set, reproducible per 65536-row block (shard-invariant)."""
+    B = 65536
+    views = [np.empty((hi - lo, d), np.float32) for d in DIMS]
+    z = np.empty(hi - lo, np.int32)
+    b = lo // B
+    while b * B < hi:
+        rng = np.random.default_rng([seed, b])
+        zb = rng.integers(0, CAP, B).astype(np.int32)
+        nb = [rng.standard_normal((B, d), dtype=np.float32) for d in DIMS]
+        s, e = max(lo, b * B), min(hi, (b + 1) * B)
+        z[s - lo:e - lo] = zb[s - b * B:e - b * B]
+        for v in range(len(DIMS)):
+            views[v][s - lo:e - lo] = mus[v][zb[s - b * B:e - b * B]] + nb[v][s - b * B:e - b * B]
+        b += 1
+    return views, z
+
+
+def initial_state(z):
+    dish = np.tile(np.arange(CAP, dtype=np.int32), (len(DIMS), 1))      # dish_of[v][t] = t
+    hyp = dict(alpha_v=[1.0] * len(DIMS), sigma_v=[0.5] * len(DIMS), tau_v=[1.0] * len(DIMS), alpha_g=1.0, sigma_g=0.6)
+    return z.astype(np.int32), dish, hyp
+
+
+# ---------------------------------------------------------------------------------------------
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        super().__init__(daemon=True)
+        self.gpu, self.rows, self.stop_flag = gpu_index, [], False
+
+    def run(self):
+        while not self.stop_flag:
+            try:
+                out = subprocess.run(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-i",
+                                      str(self.gpu)], capture_output=True, text=True, timeout=5).stdout.strip()
+                if out:
+                    self.rows.append([x.strip() for x in out.split(",")])
+            except Exception:
+                pass
+            time.sleep(0.1)
+
+    def summary(self):
+        sm = [float(r[1]) for r in self.rows if len(r) > 8 and r[1].replace(".", "").isdigit()]
+        mx = [float(r[2]) for r in self.rows if len(r) > 8 and r[2].replace(".", "").isdigit()]
+        reasons = set()
+        for r in self.rows:
+            if len(r) > 8:
+                for name, val in zip(["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"], r[5:9]):
+                    if val.lower().startswith("active"):
+                        reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def measured_peak():
+    f = ROOT / "MEASURED_PEAKS.json"
+    if f.exists():
+        return float(json.loads(f.read_text())["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+def cpu_port_throughput(rows, threads):
+    """The FP64 CPU restatement of the sweep (oracle/mv_oracle.c) on a bounded sample of the workload."""
+    sys.path.insert(0, str(ROOT / "oracle"))
+    import pyoracle as po
+    mus = planted_means(np.random.default_rng(SEED))
+    views, z = make_rows_numpy(0, rows, mus)
+    tab, dish, hyp = initial_state(z)
+    o = po.OracleState(views, CAP, seed=SEED)
+    o.alpha_v[:] = hyp["alpha_v"]; o.sigma_v[:] = hyp["sigma_v"]; o.tau_v[:] = hyp["tau_v"]
+    o.set_assignment(tab, dish)
+    t0 = time.perf_counter()
+    o.sweep_n(1, threads=threads, do_hyper=True)
+    dt = time.perf_counter() - t0
+    return rows * len(DIMS) * CAP / dt, dt
+
+
+def run_reference(args):
+    """--impl reference: the reference's CPU implementation of the path on the host cores.  The
+    reference sampler itself has no D > 1 likelihood, so on this configuration the
+    CPU arm is the restated port of its arithmetic (oracle/mv_oracle.c, kind "port"), all host threads."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    threads = os.cpu_count() or 1
+    rows = args.cpu_rows or 16384
+    for _ in range(min(args.warmup, 1)):
+        cpu_port_throughput(min(rows, 2048), threads)
+    vals, dts = [], []
+    for _ in range(max(1, min(args.steps, 5))):
+        v, dt = cpu_port_throughput(rows, threads)
+        vals.append(v); dts.append(dt)
+    value = float(np.mean(vals))
+    sample = f"one FP64 sweep over the first {rows} customers of the C3 workload per step, {threads} OpenMP threads"
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+            "steps": len(vals), "warmup": min(args.warmup, 1), "ms_per_step": 1e3 * float(np.mean(dts)),
+            "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": "C3: 3-view Gaussian mixture N=1M D=64 K=64 (bounded CPU sample)", "rows_sampled": rows},
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
+            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line))
+
+
+def main():
+    args = parse()
+    if args.impl == "reference":
+        return run_reference(args)
+
+    import torch
+    import mvc_b200
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the sweep has no CPU path")
+    torch.cuda.set_device(local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    n_total = args.rows
+    lo, hi = rank * n_total // world, (rank + 1) * n_total // world
+    n_local = hi - lo
+    mus = planted_means(np.random.default_rng(SEED))
+    views_np, z = make_rows_numpy(lo, hi, mus)
+    tab, dish, hyp = initial_state(z)
+    views_pinned = [torch.from_numpy(v).pin_memory() for v in views_np]
+    views_dev = [v.cuda(non_blocking=True) for v in views_pinned]
+    torch.cuda.synchronize()
+
+    def make_sampler(attach):
+        s = mvc_b200.Sampler(n_local, DIMS, cap=CAP, seed=SEED, device=local_rank, engine=args.engine, rank=rank,
+                             world=world, row_offset=lo, n_rows_global=n_total)
+        if world > 1:
+            uid = [mvc_b200.Sampler.nccl_unique_id() if rank == 0 else None]
+            dist.broadcast_object_list(uid, src=0)
+            s.comm_init_rank(uid[0])
+        if attach:
+            for v in range(len(DIMS)):
+                s.attach_view_device(v, views_dev[v])
+        return s
+
+    do_hyper = not args.no_hyper
+    s = make_sampler(attach=True)
+    s.set_state(tab, dish, hyp["alpha_v"], hyp["sigma_v"], hyp["tau_v"], hyp["alpha_g"], hyp["sigma_g"])
+    s.sweep(args.warmup, do_hyper)
+    s.sync()
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    clocks = ClockSampler(local_rank)
+    barrier()
+    clocks.start()
+    l0 = s.launch_count()
+    t_wall = time.perf_counter()
+    s.sweep(args.steps, do_hyper)           # K sweeps, CUDA events around them on the library's stream
+    s.sync()
+    barrier()
+    wall_ms = 1e3 * (time.perf_counter() - t_wall)
+    clocks.stop_flag = True
+    dev_ms = s.last_sweep_ms()
+    launches = s.launch_count() - l0
+    t = torch.tensor([dev_ms], device="cuda")
+    if dist is not None:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    dev_ms = float(t.item())
+    ms_per_step = dev_ms / args.steps
+    updates = n_total * len(DIMS) * CAP
+    value = updates * args.steps / (dev_ms * 1e-3)
+
+    # per-kernel device times of a few extra sweeps (CUDA events between the launches)
+    prof = [s.profile_sweep(do_hyper) for _ in range(5)]
+    kern = {k: float(np.median([p[k] for p in prof])) for k in prof[0]}
+    peak, peak_src = measured_peak()
+    alg_bytes = n_local * (sum(DIMS) * 4 + 8)
+    achieved = alg_bytes / (kern["draw"] * 1e-3) / 1e9
+    roofline = {"bound": "hbm", "kernel": "likelihood+draw", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                "algorithmic_bytes_per_launch": alg_bytes, "kernel_ms": kern}
+    final = s.get_state(with_rows=False)
+    s.close()
+
+    # e2e: the reference-facing call with host buffers (upload + state + K sweeps + read-back), every rank
+    e2e = None
+    if not args.no_e2e:
+        k_e2e = args.steps
+        barrier()
+        t0 = time.perf_counter()
+        s2 = make_sampler(attach=False)
+        for v in range(len(DIMS)):
+            s2.upload_view(v, views_pinned[v].numpy())
+        s2.set_state(tab, dish, hyp["alpha_v"], hyp["sigma_v"], hyp["tau_v"], hyp["alpha_g"], hyp["sigma_g"])
+        s2.sweep(k_e2e, do_hyper)
+        out = s2.get_state(with_rows=True)
+        barrier()
+        dt = time.perf_counter() - t0
+        tt = torch.tensor([dt], device="cuda")
+        if dist is not None:
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        dt = float(tt.item())
+        h2d = n_local * (sum(DIMS) * 4 + 4)
+        d2h = n_local * 4
+        e2e = {"value": updates * k_e2e / dt, "unit": UNIT, "h2d_bytes_per_step": h2d / k_e2e,
+               "d2h_bytes_per_step": d2h / k_e2e, "sweeps": k_e2e, "seconds": dt,
+               "note": "one call = H2D of all views + table_of, K sweeps, D2H of table_of; wall clock incl. allocation"}
+        assert int(out["n_t"].sum()) == n_total
+        s2.close()
+
+    cpu = None
+    if rank == 0 and not args.no_cpu_baseline:
+        rows = args.cpu_rows or 4096
+        v1, dt1 = cpu_port_throughput(rows, 1)
+        cpu = {"value": v1, "unit": UNIT, "cores": 1, "kind": "port",
+               "sample": f"one FP64 sweep of oracle/mv_oracle.c over the first {rows} customers of the same workload, "
+                         f"1 thread ({dt1:.2f} s); the reference sampler itself has no D>1 path (SURVEY.md §0)"}
+
+    if rank == 0:
+        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+                "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+                "dtype": "f32", "data": "synthetic",
+                "config": {"workload": "C3: synthetic 3-view Gaussian mixture, N=%d, D=64/view, K(cap)=64, row-sharded" % n_total,
+                           "rows_per_gpu": n_local, "hyper_step": do_hyper, "engine": args.engine,
+                           "l2": "inputs (768 MB per sweep) larger than L2; no flush"},
+                "sweeps_per_s": args.steps / (dev_ms * 1e-3), "wall_ms_per_step": wall_ms / args.steps,
+                "clocks": clocks.summary(), "gpu_launches": int(launches),
+                "roofline": roofline, "e2e": e2e, "cpu_baseline": cpu,
+                "state_check": {"tables_live": int((final["n_t"] > 0).sum()), "customers": int(final["n_t"].sum())}}
+        print(json.dumps(line))
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

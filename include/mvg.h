@@ -1,0 +1,182 @@
+/* include/mvg.h — the C ABI of the B200-native allocation sweep (libmvg_b200.so).
+ *
+ * This is the drop-in boundary: the host-side C++ that keeps the reference's headers
+ * (multiview-clustering_b200/host/multiview_{gibbs,state,hyper,utils,rng}.h) and any foreign
+ * binding (Rcpp, ctypes — see INTEGRATION.md) reach CUDA only through these entry points.
+ * extern "C", plain pointers and sizes, int status codes, no C++/torch/Rcpp types.
+ *
+ * Reference interface each entry point replaces (paths under /root/reference/Multiview):
+ *
+ *   mvg_create / mvg_destroy        the process-global chain state, multiview_state.h:21-45 and
+ *                                   multiview_state.cpp:4-27 (one handle = one chain on one GPU)
+ *   mvg_upload_view_*               the copy-in of run_gibbs_cpp, multiview_gibbs.cpp:109-115
+ *   mvg_init_state_reference        initialize_state_from_data, multiview_gibbs.cpp:12-103
+ *   mvg_set_state / mvg_get_state   direct reads/writes of table_of, dish_of, views[v].* and the
+ *                                   hyperparameters (multiview_state.h:7-33)
+ *   mvg_sweep                       the loop body of gibbs_sampler, multiview_gibbs.cpp:157-202:
+ *                                   remove / score / draw / insert for every customer
+ *                                   (multiview_utils.cpp:71-289, :307-350) followed by
+ *                                   update_hyperparameters (multiview_hyper.cpp:233-292)
+ *   mvg_hyper_step                  update_hyperparameters alone, multiview_hyper.h:18
+ *   mvg_run                         gibbs_sampler(M, burn_in, thin) + save_state,
+ *                                   multiview_gibbs.cpp:134-212, multiview_utils.cpp:291-303
+ *   mvg_philox_*                    uniform01 / rnorm_scalar, multiview_utils.cpp:305-306 and the
+ *                                   unused multiview_rng.h:9-24 (host mirror of the device stream)
+ *
+ * Semantics that differ from the reference BY DESIGN:
+ *   - the sweep is synchronous: every customer is scored against the sweep-start statistics with
+ *     only its own contribution removed, instead of seeing the moves of customers 0..i-1;
+ *   - table and dish slots have a fixed capacity `cap`; a new table can only open in a slot that
+ *     was free at sweep start, births are seated in global row order and the overflow stays put;
+ *   - the random stream is Philox4x32-10 addressed by (seed, chain, sweep, row, slot) instead of
+ *     R's call-ordered generator.
+ *
+ * Threading: a handle is not re-entrant; calls on one handle must be serialised by the caller.
+ * Every call returns MVG_OK (0) or a negative MVG_E*; mvg_last_error gives the message.
+ */
+#ifndef MVG_H
+#define MVG_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MVG_ABI_VERSION 1
+
+enum {
+  MVG_OK = 0,
+  MVG_EINVAL = -1,      /* bad argument or state that violates an invariant */
+  MVG_ECUDA = -2,       /* a CUDA runtime call failed (message has the CUDA error string) */
+  MVG_ENOMEM = -3,
+  MVG_ESTATE = -4,      /* call out of order (e.g. sweep before all views are uploaded) */
+  MVG_ENCCL = -5,
+  MVG_EUNSUPPORTED = -6 /* shape outside what the kernels were built for */
+};
+
+enum { MVG_ENGINE_AUTO = 0, MVG_ENGINE_SIMT = 1, MVG_ENGINE_TCGEN05 = 2 };
+enum { MVG_VIEW_DENSE = 0, MVG_VIEW_CSR = 1 };
+
+#define MVG_NEW_TABLE (-1)
+#define MVG_MAX_VIEWS 16
+
+typedef struct mvg_handle mvg_handle;   /* opaque */
+
+typedef struct mvg_config {
+  int32_t abi_version;     /* MVG_ABI_VERSION */
+  int32_t device;          /* CUDA device ordinal */
+  int64_t n_rows;          /* rows (customers) held by THIS handle (its shard) */
+  int64_t n_rows_global;   /* customers over all shards; == n_rows on one GPU */
+  int64_t row_offset;      /* global index of this shard's row 0 (Philox addressing, birth order) */
+  int32_t n_views;         /* d in the reference */
+  int32_t cap;             /* capacity of table slots and of dish slots per view (32 or 64) */
+  uint64_t seed;           /* Philox key (echo of set.seed(1999), New_Simulation.R:12) */
+  uint32_t chain;          /* chain id, folded into the Philox key */
+  int32_t engine;          /* MVG_ENGINE_* : which likelihood+draw kernel */
+  int32_t debug_export;    /* !=0: keep the per-row dot products of the last sweep for mvg_get_debug_* */
+  int32_t rank;            /* shard index 0..world-1 (0 on one GPU) */
+  int32_t world;           /* number of shards (1 on one GPU) */
+  int32_t reserved[5];
+} mvg_config;
+
+/* Host-side view of the chain state.  All pointers are HOST buffers owned by the caller; a NULL
+ * pointer skips that field.  Sizes: V = n_views, cap, D_v = dim of view v, Dsum = sum of D_v. */
+typedef struct mvg_state_host {
+  int32_t* table_of;   /* [n_rows]   table slot of each local row                       (table_of) */
+  int32_t* n_t;        /* [cap]      customers per table slot, 0 = free                 (n_t) */
+  int32_t* dish_of;    /* [V*cap]    dish slot of table t in view v, -1 = free table    (dish_of[v][t]) */
+  int32_t* n_vk;       /* [V*cap]    customers per dish slot                            (ViewState::n_vk) */
+  int32_t* l_vk;       /* [V*cap]    tables per dish slot                               (ViewState::l_vk) */
+  double* sum_y;       /* [cap*Dsum] per view v a [cap][D_v] block, views concatenated  (ViewState::sum_y) */
+  double* sum_y2;      /* [V*cap]    sum of squared norms per dish slot                 (ViewState::sum_y2) */
+  double* alpha_v;     /* [V] */
+  double* sigma_v;     /* [V] */
+  double* tau_v;       /* [V] */
+  double* alpha_sigma_global;  /* [2] = {alpha_global, sigma_global} */
+  uint32_t* sweep;     /* [1] index of the next sweep */
+} mvg_state_host;
+
+/* ---- lifetime ------------------------------------------------------------------------ */
+int mvg_abi_version(void);
+int mvg_create(const mvg_config* cfg, mvg_handle** out);
+int mvg_destroy(mvg_handle* h);
+const char* mvg_last_error(const mvg_handle* h);   /* h may be NULL: error of the last failed create */
+
+/* ---- data ------------------------------------------------------------------------------ */
+/* Dense view v, row-major [n_rows][dim] in HOST memory (pageable or pinned); copied to the GPU. */
+int mvg_upload_view_f32(mvg_handle* h, int32_t v, const float* x_host, int32_t dim);
+/* Same from doubles, the type of the reference's y[v] (multiview_state.h:22); rounded to FP32. */
+int mvg_upload_view_f64(mvg_handle* h, int32_t v, const double* y_host, int32_t dim);
+/* Use a DEVICE buffer in place (row-major [n_rows][dim], 16-byte aligned); the caller keeps ownership. */
+int mvg_attach_view_device_f32(mvg_handle* h, int32_t v, const float* x_dev, int32_t dim);
+
+/* ---- state ----------------------------------------------------------------------------- */
+int mvg_init_state_reference(mvg_handle* h);
+/* Needs table_of, dish_of, alpha_v, sigma_v, tau_v, alpha_sigma_global (sweep optional); the
+ * sufficient statistics are rebuilt on the device. */
+int mvg_set_state(mvg_handle* h, const mvg_state_host* s);
+int mvg_get_state(mvg_handle* h, const mvg_state_host* out);
+
+/* ---- the hot path ---------------------------------------------------------------------- */
+/* n_sweeps synchronous allocation sweeps, each followed by the hyper step when do_hyper != 0.
+ * Asynchronous on the handle's stream; any mvg_get_* / mvg_sync observes the result. */
+int mvg_sweep(mvg_handle* h, int32_t n_sweeps, int32_t do_hyper);
+int mvg_hyper_step(mvg_handle* h);
+int mvg_sync(mvg_handle* h);
+/* gibbs_sampler(M, burn_in, thin): M sweeps; after sweep `iter` with iter >= burn_in and
+ * (iter - burn_in) % thin == 0 the state is appended to the caller's trace buffers
+ * (save rule of multiview_gibbs.cpp:205).  Buffers hold n_saved_max entries each:
+ * table_of [S][n_rows], dish_of [S][V*cap], hypers [S][3V+2] = alpha_v, sigma_v, tau_v, alpha_g, sigma_g.
+ * Returns the number of saved states in *n_saved. */
+int mvg_run(mvg_handle* h, int32_t M, int32_t burn_in, int32_t thin, int32_t n_saved_max,
+            int32_t* saved_table_of, int32_t* saved_dish_of, double* saved_hypers, int32_t* n_saved);
+
+/* ---- multi-GPU (row-sharded) -------------------------------------------------------------- */
+/* Attach an initialised NCCL communicator (ncclComm_t passed as void*) whose rank/size match the
+ * config.  Without one, world must be 1.  The library issues one all-gather per sweep on it. */
+int mvg_comm_attach(mvg_handle* h, void* nccl_comm);
+/* Convenience for callers without their own NCCL: unique_id is the 128-byte ncclUniqueId made by
+ * mvg_comm_unique_id on rank 0 and distributed by the caller (e.g. over torch.distributed/gloo). */
+int mvg_comm_unique_id(void* unique_id_128);
+int mvg_comm_init_rank(mvg_handle* h, const void* unique_id_128);
+
+/* ---- inspection (tests, profiling) ----------------------------------------------------- */
+/* The FP32 parameter block of the NEXT sweep, as the likelihood kernel will read it; pointers
+ * are host buffers, NULL skips.  Layouts are those of oracle/mv_oracle.h:mvo_params_f32. */
+typedef struct mvg_params_host {
+  int32_t* dish; float* A; float* C; float* A1; float* C1; float* W; float* W1; int32_t* lone;
+  float* AN; float* CN; float* WN; float* LD; float* LM; float* LM1; int32_t* single; float* LMN;
+  float* m;     /* [cap*Dsum]: per view a [cap][D_v] block of per-table means, views concatenated */
+} mvg_params_host;
+int mvg_get_params(mvg_handle* h, const mvg_params_host* out);
+/* With debug_export: per-row stage-A outputs of the LAST sweep: acc [n_rows][V][cap] dot products
+ * x.m and xx [n_rows][V] squared norms, plus the raw draw (before births are seated) [n_rows]. */
+int mvg_get_debug_rows(mvg_handle* h, float* acc, float* xx, int32_t* choice);
+/* Births of the LAST sweep: rows (global index) seated at new tables in order, and the
+ * V*(cap+1) max-normalised dish weights each saw.  rows holds cap entries, w cap*V*(cap+1). */
+int mvg_get_debug_births(mvg_handle* h, int32_t* n_seated, int64_t* rows, double* w);
+/* Device time of the last mvg_sweep call's kernels, by CUDA events on the handle's stream (ms). */
+int mvg_last_sweep_ms(mvg_handle* h, float* ms_total);
+/* Number of kernel launches the library issued since the handle was created. */
+int64_t mvg_launch_count(const mvg_handle* h);
+/* Per-kernel device time of the most recent sweep measured with CUDA events (ms):
+ * [0] likelihood+draw, [1] pack, [2] stats, [3] reduce, [4] finalize, [5] collective. */
+int mvg_profile_sweep(mvg_handle* h, int32_t do_hyper, float ms_out[6]);
+/* The CUDA stream (cudaStream_t as void*) all work of this handle is issued on. */
+void* mvg_stream(mvg_handle* h);
+
+/* ---- Philox host mirror (multiview_rng.h surface) ---------------------------------------- */
+void mvg_philox4x32_10(const uint32_t ctr[4], const uint32_t key[2], uint32_t out[4]);
+float mvg_philox_uniform_f32(uint64_t seed, uint32_t chain, uint32_t domain, uint32_t slot,
+                             uint32_t sweep, uint64_t index);
+double mvg_philox_uniform_f64(uint64_t seed, uint32_t chain, uint32_t domain, uint32_t slot,
+                              uint32_t sweep, uint64_t index);
+double mvg_philox_normal(uint64_t seed, uint32_t chain, uint32_t domain, uint32_t slot,
+                         uint32_t sweep, uint64_t index);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MVG_H */

@@ -1,0 +1,625 @@
+// mv_capi.cu — the C ABI of include/mvg.h: handle lifetime, HBM allocation, H2D/D2H, kernel
+// sequencing of one sweep, NCCL attachment.  Host code only; every number the sampler produces
+// comes from the kernels in mv_draw_*.cu and mv_state_kernels.cu.  There is no CPU fallback:
+// if CUDA is unavailable mvg_create fails with MVG_ECUDA.
+#include <cuda_runtime.h>
+#include <dlfcn.h>
+
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+#include <new>
+#include <string>
+#include <vector>
+
+#include "../../include/mvg.h"
+#include "mv_ctx.h"
+
+namespace {
+
+using namespace mv;
+
+// ---- minimal NCCL surface, resolved at run time so that one-GPU use needs no NCCL at all -------
+struct UidByValue { char internal[128]; };   // ncclUniqueId is passed by value
+struct NcclApi {
+  void* lib = nullptr;
+  int (*GetUniqueId)(void*) = nullptr;
+  int (*CommInitRank)(void**, int, UidByValue, int) = nullptr;
+  int (*AllGather)(const void*, void*, size_t, int, void*, cudaStream_t) = nullptr;
+  int (*CommDestroy)(void*) = nullptr;
+  const char* (*GetErrorString)(int) = nullptr;
+};
+NcclApi g_nccl;
+std::mutex g_nccl_mu;
+
+bool load_nccl(std::string& err) {
+  std::lock_guard<std::mutex> lk(g_nccl_mu);
+  if (g_nccl.lib) return true;
+  const char* names[] = {"libnccl.so.2", "libnccl.so"};
+  void* lib = nullptr;
+  for (const char* n : names) {
+    lib = dlopen(n, RTLD_NOW | RTLD_GLOBAL);
+    if (lib) break;
+  }
+  if (!lib) { err = "NCCL not found (dlopen libnccl.so.2)"; return false; }
+  g_nccl.GetUniqueId = reinterpret_cast<int (*)(void*)>(dlsym(lib, "ncclGetUniqueId"));
+  g_nccl.CommInitRank = reinterpret_cast<int (*)(void**, int, UidByValue, int)>(dlsym(lib, "ncclCommInitRank"));
+  g_nccl.AllGather = reinterpret_cast<int (*)(const void*, void*, size_t, int, void*, cudaStream_t)>(dlsym(lib, "ncclAllGather"));
+  g_nccl.CommDestroy = reinterpret_cast<int (*)(void*)>(dlsym(lib, "ncclCommDestroy"));
+  g_nccl.GetErrorString = reinterpret_cast<const char* (*)(int)>(dlsym(lib, "ncclGetErrorString"));
+  if (!g_nccl.GetUniqueId || !g_nccl.CommInitRank || !g_nccl.AllGather || !g_nccl.CommDestroy) {
+    err = "NCCL symbols missing";
+    return false;
+  }
+  g_nccl.lib = lib;
+  return true;
+}
+
+thread_local std::string g_create_error;
+
+}  // namespace
+
+struct mvg_handle {
+  mvg_config cfg{};
+  Ctx c{};
+  cudaStream_t stream = nullptr;
+  cudaEvent_t ev[8]{};
+  std::string err;
+  std::vector<void*> owned;          // device allocations to free
+  void* view_owned[kMaxViews]{};     // uploaded views (owned); attached views are not
+  bool layout_done = false;
+  bool state_ready = false;
+  int engine = MVG_ENGINE_SIMT;
+  void* comm = nullptr;
+  bool comm_owned = false;
+  int64_t launches = 0;
+  float last_ms = 0.f;
+  int sms = 148;
+};
+
+namespace {
+
+int fail(mvg_handle* h, int code, const std::string& msg) {
+  if (h) h->err = msg; else g_create_error = msg;
+  return code;
+}
+#define MVG_CUDA(h, expr)                                                                    \
+  do {                                                                                       \
+    cudaError_t e__ = (expr);                                                                \
+    if (e__ != cudaSuccess)                                                                  \
+      return fail(h, MVG_ECUDA, std::string(#expr) + ": " + cudaGetErrorString(e__));         \
+  } while (0)
+
+template <class T>
+int dev_alloc(mvg_handle* h, T** p, size_t count) {
+  void* q = nullptr;
+  size_t bytes = sizeof(T) * (count ? count : 1);
+  cudaError_t e = cudaMalloc(&q, bytes);
+  if (e != cudaSuccess) return fail(h, MVG_ENOMEM, std::string("cudaMalloc: ") + cudaGetErrorString(e));
+  e = cudaMemsetAsync(q, 0, bytes, h->stream);
+  if (e != cudaSuccess) return fail(h, MVG_ECUDA, std::string("cudaMemset: ") + cudaGetErrorString(e));
+  h->owned.push_back(q);
+  *p = static_cast<T*>(q);
+  return MVG_OK;
+}
+
+int align16(int x) { return (x + 15) & ~15; }
+
+// Allocate everything that depends on the dims of all views; called once they are all known.
+int ensure_layout(mvg_handle* h) {
+  if (h->layout_done) return MVG_OK;
+  Ctx& c = h->c;
+  int dsum = 0;
+  for (int v = 0; v < c.V; ++v) {
+    if (!c.x[v] || c.D[v] <= 0) return fail(h, MVG_ESTATE, "view " + std::to_string(v) + " has no data yet");
+    c.doff[v] = dsum;
+    dsum += c.D[v];
+  }
+  c.Dsum = dsum;
+  const size_t N = (size_t)c.n_rows, cap = (size_t)c.cap, V = (size_t)c.V;
+  int rc;
+#define A(ptr, count) if ((rc = dev_alloc(h, &(ptr), (count))) != MVG_OK) return rc
+  A(c.table_cur, N); A(c.choice, N); A(c.birthmask, (size_t)c.n_chunks); A(c.chunk_prefix, (size_t)c.n_chunks);
+  A(c.n_t, cap); A(c.dish_of, V * cap); A(c.n_vk, V * cap); A(c.l_vk, V * cap);
+  A(c.S1t, cap * dsum); A(c.S2t, V * cap); A(c.S1k, cap * dsum); A(c.S2k, V * cap);
+  A(c.hyp, 3 * V + 2); A(c.sweep, 1); A(c.status, 4);
+  A(c.tparam, V * cap); A(c.vparam, V); A(c.tmass, cap); A(c.gparam, 1);
+  A(c.mean, cap * dsum); A(c.mean_hi, cap * dsum); A(c.mean_lo, cap * dsum);
+  A(c.partial_f, (size_t)c.stat_ctas * (cap * dsum + V * cap)); A(c.partial_n, (size_t)c.stat_ctas * cap);
+  A(c.birth_lf, cap * V * (cap + 1));
+  A(c.dbg_birth_rows, cap); A(c.dbg_birth_w, cap * V * (cap + 1)); A(c.dbg_nseated, 1);
+  PacketLayout& p = c.pkt;
+  int off = 0;
+  p.off_hdr = off; off += 32;
+  p.off_cnt = off; off += align16(4 * c.cap);
+  p.off_cand_row = off; off += align16(4 * c.cap);
+  p.off_cand_t0 = off; off += align16(4 * c.cap);
+  p.off_s2t = off; off += align16(8 * c.V * c.cap);
+  p.off_s1t = off; off += align16(8 * c.cap * dsum);
+  p.off_cand_x = off; off += align16(4 * c.cap * dsum);
+  p.bytes = off;
+  A(c.packet, (size_t)c.world * p.bytes);
+  if (c.debug_export) { A(c.dbg_acc, N * V * cap); A(c.dbg_xx, N * V); A(c.dbg_choice, N); }
+#undef A
+  h->layout_done = true;
+  // engine choice
+  h->engine = MVG_ENGINE_SIMT;
+  if (h->cfg.engine == MVG_ENGINE_TCGEN05) {
+    if (!draw_tc_supported(c)) return fail(h, MVG_EUNSUPPORTED, "tcgen05 engine needs cap = 64 and every dim = 64");
+    h->engine = MVG_ENGINE_TCGEN05;
+  } else if (h->cfg.engine == MVG_ENGINE_AUTO && draw_tc_supported(c)) {
+    h->engine = MVG_ENGINE_TCGEN05;
+  }
+  return MVG_OK;
+}
+
+int exchange(mvg_handle* h) {
+  if (h->c.world == 1) return MVG_OK;
+  if (!h->comm) return fail(h, MVG_ESTATE, "world > 1 but no NCCL communicator attached");
+  unsigned char* base = h->c.packet;
+  int r = g_nccl.AllGather(base + (size_t)h->c.rank * h->c.pkt.bytes, base, (size_t)h->c.pkt.bytes, /*ncclChar*/ 0,
+                           h->comm, h->stream);
+  if (r != 0) return fail(h, MVG_ENCCL, std::string("ncclAllGather: ") + (g_nccl.GetErrorString ? g_nccl.GetErrorString(r) : "?"));
+  return MVG_OK;
+}
+
+// stats -> reduce -> exchange -> finalize: shared by sweeps, set_state and init
+int rebuild_pipeline(mvg_handle* h, int32_t flags, cudaEvent_t* marks /* 4 events or null */) {
+  MVG_CUDA(h, launch_stats(h->c, h->stream));
+  if (marks) MVG_CUDA(h, cudaEventRecord(marks[0], h->stream));
+  MVG_CUDA(h, launch_reduce(h->c, h->stream));
+  if (marks) MVG_CUDA(h, cudaEventRecord(marks[1], h->stream));
+  int rc = exchange(h);
+  if (rc != MVG_OK) return rc;
+  if (marks) MVG_CUDA(h, cudaEventRecord(marks[2], h->stream));
+  MVG_CUDA(h, launch_finalize(h->c, flags, h->stream));
+  if (marks) MVG_CUDA(h, cudaEventRecord(marks[3], h->stream));
+  h->launches += 3;
+  return MVG_OK;
+}
+
+int launch_draw(mvg_handle* h) {
+  if (h->engine == MVG_ENGINE_TCGEN05) MVG_CUDA(h, launch_draw_tc(h->c, h->stream));
+  else MVG_CUDA(h, launch_draw_simt(h->c, h->stream));
+  h->launches += 1;
+  return MVG_OK;
+}
+
+int check_status(mvg_handle* h) {
+  int32_t st[4] = {0, 0, 0, 0};
+  MVG_CUDA(h, cudaMemcpyAsync(st, h->c.status, sizeof(st), cudaMemcpyDeviceToHost, h->stream));
+  MVG_CUDA(h, cudaStreamSynchronize(h->stream));
+  if (st[0] != 0) {
+    MVG_CUDA(h, cudaMemsetAsync(h->c.status, 0, sizeof(st), h->stream));
+    return fail(h, MVG_EINVAL, "device-side invariant violated, flags=" + std::to_string(st[0]) +
+                                   " (1: no free dish slot for a birth, 2: live table without a dish)");
+  }
+  return MVG_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int mvg_abi_version(void) { return MVG_ABI_VERSION; }
+
+const char* mvg_last_error(const mvg_handle* h) { return h ? h->err.c_str() : g_create_error.c_str(); }
+
+int mvg_create(const mvg_config* cfg, mvg_handle** out) {
+  if (!cfg || !out) return fail(nullptr, MVG_EINVAL, "null argument");
+  *out = nullptr;
+  if (cfg->abi_version != MVG_ABI_VERSION) return fail(nullptr, MVG_EINVAL, "abi_version mismatch");
+  if (cfg->n_rows <= 0 || cfg->n_rows > 0x7fffffffLL) return fail(nullptr, MVG_EINVAL, "n_rows out of range");
+  if (cfg->n_views <= 0 || cfg->n_views > kMaxViews) return fail(nullptr, MVG_EINVAL, "n_views out of range");
+  if (cfg->cap != 32 && cfg->cap != 64) return fail(nullptr, MVG_EUNSUPPORTED, "cap must be 32 or 64");
+  if (cfg->world < 1 || cfg->world > 16 || cfg->rank < 0 || cfg->rank >= cfg->world)
+    return fail(nullptr, MVG_EINVAL, "rank/world out of range");
+  if (cfg->n_rows_global < cfg->n_rows || cfg->row_offset < 0 || cfg->row_offset + cfg->n_rows > cfg->n_rows_global)
+    return fail(nullptr, MVG_EINVAL, "row_offset / n_rows_global inconsistent");
+  int ndev = 0;
+  cudaError_t e = cudaGetDeviceCount(&ndev);
+  if (e != cudaSuccess || ndev == 0)
+    return fail(nullptr, MVG_ECUDA, std::string("no CUDA device: ") + cudaGetErrorString(e) +
+                                        " (this library has no CPU path)");
+  if (cfg->device < 0 || cfg->device >= ndev) return fail(nullptr, MVG_EINVAL, "device ordinal out of range");
+  mvg_handle* h = new (std::nothrow) mvg_handle();
+  if (!h) return fail(nullptr, MVG_ENOMEM, "host allocation failed");
+  h->cfg = *cfg;
+  if ((e = cudaSetDevice(cfg->device)) != cudaSuccess ||
+      (e = cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking)) != cudaSuccess) {
+    std::string m = std::string("cuda init: ") + cudaGetErrorString(e);
+    delete h;
+    return fail(nullptr, MVG_ECUDA, m);
+  }
+  for (auto& ev : h->ev) cudaEventCreate(&ev);
+  cudaDeviceGetAttribute(&h->sms, cudaDevAttrMultiProcessorCount, cfg->device);
+  Ctx& c = h->c;
+  c.n_rows = (int32_t)cfg->n_rows;
+  c.V = cfg->n_views;
+  c.cap = cfg->cap;
+  c.row_offset = cfg->row_offset;
+  c.n_global = cfg->n_rows_global;
+  c.seed = cfg->seed;
+  c.chain = cfg->chain;
+  c.rank = cfg->rank;
+  c.world = cfg->world;
+  c.n_chunks = (c.n_rows + 31) / 32;
+  c.stat_ctas = c.n_chunks < h->sms ? c.n_chunks : h->sms;
+  c.debug_export = cfg->debug_export;
+  *out = h;
+  return MVG_OK;
+}
+
+int mvg_destroy(mvg_handle* h) {
+  if (!h) return MVG_OK;
+  cudaSetDevice(h->cfg.device);
+  if (h->stream) cudaStreamSynchronize(h->stream);
+  if (h->comm && h->comm_owned && g_nccl.CommDestroy) g_nccl.CommDestroy(h->comm);
+  for (void* p : h->owned) cudaFree(p);
+  for (void* p : h->view_owned) if (p) cudaFree(p);
+  for (auto& ev : h->ev) if (ev) cudaEventDestroy(ev);
+  if (h->stream) cudaStreamDestroy(h->stream);
+  delete h;
+  return MVG_OK;
+}
+
+static int set_view(mvg_handle* h, int32_t v, int32_t dim) {
+  if (!h) return MVG_EINVAL;
+  if (v < 0 || v >= h->c.V) return fail(h, MVG_EINVAL, "view index out of range");
+  if (dim <= 0) return fail(h, MVG_EINVAL, "dim must be positive");
+  if (h->layout_done && h->c.D[v] != dim) return fail(h, MVG_ESTATE, "view dims are frozen after the first state call");
+  MVG_CUDA(h, cudaSetDevice(h->cfg.device));
+  return MVG_OK;
+}
+
+int mvg_upload_view_f32(mvg_handle* h, int32_t v, const float* x_host, int32_t dim) {
+  int rc = set_view(h, v, dim);
+  if (rc != MVG_OK) return rc;
+  if (!x_host) return fail(h, MVG_EINVAL, "null data");
+  const size_t bytes = sizeof(float) * (size_t)h->c.n_rows * dim;
+  if (!h->view_owned[v] || h->c.D[v] != dim) {
+    if (h->view_owned[v]) cudaFree(h->view_owned[v]);
+    h->view_owned[v] = nullptr;
+    MVG_CUDA(h, cudaMalloc(&h->view_owned[v], bytes));
+  }
+  MVG_CUDA(h, cudaMemcpyAsync(h->view_owned[v], x_host, bytes, cudaMemcpyHostToDevice, h->stream));
+  h->c.x[v] = static_cast<const float*>(h->view_owned[v]);
+  h->c.D[v] = dim;
+  return MVG_OK;
+}
+
+int mvg_upload_view_f64(mvg_handle* h, int32_t v, const double* y_host, int32_t dim) {
+  int rc = set_view(h, v, dim);
+  if (rc != MVG_OK) return rc;
+  if (!y_host) return fail(h, MVG_EINVAL, "null data");
+  const size_t count = (size_t)h->c.n_rows * dim;
+  if (!h->view_owned[v] || h->c.D[v] != dim) {
+    if (h->view_owned[v]) cudaFree(h->view_owned[v]);
+    h->view_owned[v] = nullptr;
+    MVG_CUDA(h, cudaMalloc(&h->view_owned[v], sizeof(float) * count));
+  }
+  double* tmp = nullptr;
+  MVG_CUDA(h, cudaMalloc(&tmp, sizeof(double) * count));
+  cudaError_t e = cudaMemcpyAsync(tmp, y_host, sizeof(double) * count, cudaMemcpyHostToDevice, h->stream);
+  if (e == cudaSuccess) e = launch_f64_to_f32(tmp, static_cast<float*>(h->view_owned[v]), (int64_t)count, h->stream);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
+  cudaFree(tmp);
+  if (e != cudaSuccess) return fail(h, MVG_ECUDA, std::string("upload f64: ") + cudaGetErrorString(e));
+  h->launches += 1;
+  h->c.x[v] = static_cast<const float*>(h->view_owned[v]);
+  h->c.D[v] = dim;
+  return MVG_OK;
+}
+
+int mvg_attach_view_device_f32(mvg_handle* h, int32_t v, const float* x_dev, int32_t dim) {
+  int rc = set_view(h, v, dim);
+  if (rc != MVG_OK) return rc;
+  if (!x_dev || (reinterpret_cast<uintptr_t>(x_dev) & 15)) return fail(h, MVG_EINVAL, "device pointer null or not 16-byte aligned");
+  if (h->view_owned[v]) { cudaFree(h->view_owned[v]); h->view_owned[v] = nullptr; }
+  h->c.x[v] = x_dev;
+  h->c.D[v] = dim;
+  return MVG_OK;
+}
+
+int mvg_init_state_reference(mvg_handle* h) {
+  if (!h) return MVG_EINVAL;
+  MVG_CUDA(h, cudaSetDevice(h->cfg.device));
+  int rc = ensure_layout(h);
+  if (rc != MVG_OK) return rc;
+  if (h->c.cap < 4) return fail(h, MVG_EINVAL, "reference initialisation needs cap >= 4");
+  const uint32_t zero = 0;
+  MVG_CUDA(h, cudaMemcpyAsync(h->c.sweep, &zero, sizeof(zero), cudaMemcpyHostToDevice, h->stream));
+  MVG_CUDA(h, launch_init_tables(h->c, 0, h->stream));
+  if ((rc = rebuild_pipeline(h, kFinTauInit, nullptr)) != MVG_OK) return rc;
+  MVG_CUDA(h, launch_init_tables(h->c, 1, h->stream));
+  if ((rc = rebuild_pipeline(h, 0, nullptr)) != MVG_OK) return rc;
+  h->launches += 2;
+  h->state_ready = true;
+  return check_status(h);
+}
+
+int mvg_set_state(mvg_handle* h, const mvg_state_host* s) {
+  if (!h || !s) return MVG_EINVAL;
+  MVG_CUDA(h, cudaSetDevice(h->cfg.device));
+  int rc = ensure_layout(h);
+  if (rc != MVG_OK) return rc;
+  const Ctx& c = h->c;
+  if (!s->table_of || !s->dish_of || !s->alpha_v || !s->sigma_v || !s->tau_v || !s->alpha_sigma_global)
+    return fail(h, MVG_EINVAL, "set_state needs table_of, dish_of, alpha_v, sigma_v, tau_v, alpha_sigma_global");
+  for (int64_t i = 0; i < c.n_rows; ++i)
+    if (s->table_of[i] < 0 || s->table_of[i] >= c.cap) return fail(h, MVG_EINVAL, "table_of entry outside [0,cap)");
+  for (int i = 0; i < c.V * c.cap; ++i)
+    if (s->dish_of[i] < -1 || s->dish_of[i] >= c.cap) return fail(h, MVG_EINVAL, "dish_of entry outside [-1,cap)");
+  for (int v = 0; v < c.V; ++v)
+    if (!(s->tau_v[v] > 0.0) || !(s->alpha_v[v] > 0.0) || !(s->sigma_v[v] > 0.0 && s->sigma_v[v] < 1.0))
+      return fail(h, MVG_EINVAL, "hyperparameters out of range (tau>0, alpha>0, 0<sigma<1)");
+  if (!(s->alpha_sigma_global[0] > 0.0) || !(s->alpha_sigma_global[1] > 0.0 && s->alpha_sigma_global[1] < 1.0))
+    return fail(h, MVG_EINVAL, "global hyperparameters out of range");
+  std::vector<double> hyp(3 * c.V + 2);
+  for (int v = 0; v < c.V; ++v) {
+    hyp[v] = s->alpha_v[v];
+    hyp[c.V + v] = s->sigma_v[v];
+    hyp[2 * c.V + v] = s->tau_v[v];
+  }
+  hyp[3 * c.V] = s->alpha_sigma_global[0];
+  hyp[3 * c.V + 1] = s->alpha_sigma_global[1];
+  const uint32_t sweep = s->sweep ? *s->sweep : 0u;
+  MVG_CUDA(h, cudaMemcpyAsync(c.choice, s->table_of, sizeof(int32_t) * (size_t)c.n_rows, cudaMemcpyHostToDevice, h->stream));
+  MVG_CUDA(h, cudaMemcpyAsync(c.dish_of, s->dish_of, sizeof(int32_t) * (size_t)c.V * c.cap, cudaMemcpyHostToDevice, h->stream));
+  MVG_CUDA(h, cudaMemcpyAsync(c.hyp, hyp.data(), sizeof(double) * hyp.size(), cudaMemcpyHostToDevice, h->stream));
+  MVG_CUDA(h, cudaMemcpyAsync(c.sweep, &sweep, sizeof(sweep), cudaMemcpyHostToDevice, h->stream));
+  MVG_CUDA(h, cudaMemsetAsync(c.birthmask, 0, sizeof(uint32_t) * (size_t)c.n_chunks, h->stream));
+  MVG_CUDA(h, cudaStreamSynchronize(h->stream));   // hyp/sweep are stack/vector temporaries
+  if ((rc = rebuild_pipeline(h, 0, nullptr)) != MVG_OK) return rc;
+  h->state_ready = true;
+  return check_status(h);
+}
+
+int mvg_get_state(mvg_handle* h, const mvg_state_host* o) {
+  if (!h || !o) return MVG_EINVAL;
+  if (!h->state_ready) return fail(h, MVG_ESTATE, "no state yet: call mvg_set_state or mvg_init_state_reference");
+  MVG_CUDA(h, cudaSetDevice(h->cfg.device));
+  const Ctx& c = h->c;
+  const size_t vc = (size_t)c.V * c.cap;
+  std::vector<double> hyp(3 * c.V + 2);
+#define D2H(dst, src, bytes) if (dst) MVG_CUDA(h, cudaMemcpyAsync((dst), (src), (bytes), cudaMemcpyDeviceToHost, h->stream))
+  D2H(o->table_of, c.table_cur, sizeof(int32_t) * (size_t)c.n_rows);
+  D2H(o->n_t, c.n_t, sizeof(int32_t) * (size_t)c.cap);
+  D2H(o->dish_of, c.dish_of, sizeof(int32_t) * vc);
+  D2H(o->n_vk, c.n_vk, sizeof(int32_t) * vc);
+  D2H(o->l_vk, c.l_vk, sizeof(int32_t) * vc);
+  D2H(o->sum_y, c.S1k, sizeof(double) * (size_t)c.cap * c.Dsum);
+  D2H(o->sum_y2, c.S2k, sizeof(double) * vc);
+  D2H(o->sweep, c.sweep, sizeof(uint32_t));
+  D2H(hyp.data(), c.hyp, sizeof(double) * hyp.size());
+#undef D2H
+  int rc = check_status(h);   // synchronises
+  if (rc != MVG_OK) return rc;
+  for (int v = 0; v < c.V; ++v) {
+    if (o->alpha_v) o->alpha_v[v] = hyp[v];
+    if (o->sigma_v) o->sigma_v[v] = hyp[c.V + v];
+    if (o->tau_v) o->tau_v[v] = hyp[2 * c.V + v];
+  }
+  if (o->alpha_sigma_global) { o->alpha_sigma_global[0] = hyp[3 * c.V]; o->alpha_sigma_global[1] = hyp[3 * c.V + 1]; }
+  return MVG_OK;
+}
+
+int mvg_sweep(mvg_handle* h, int32_t n_sweeps, int32_t do_hyper) {
+  if (!h) return MVG_EINVAL;
+  if (!h->state_ready) return fail(h, MVG_ESTATE, "no state yet: call mvg_set_state or mvg_init_state_reference");
+  if (n_sweeps < 0) return fail(h, MVG_EINVAL, "n_sweeps < 0");
+  MVG_CUDA(h, cudaSetDevice(h->cfg.device));
+  const int32_t flags = kFinReseat | kFinAdvance | (do_hyper ? kFinHyper : 0);
+  MVG_CUDA(h, cudaEventRecord(h->ev[0], h->stream));
+  for (int it = 0; it < n_sweeps; ++it) {
+    int rc = launch_draw(h);
+    if (rc != MVG_OK) return rc;
+    MVG_CUDA(h, launch_pack(h->c, h->stream));
+    h->launches += 1;
+    if ((rc = rebuild_pipeline(h, flags, nullptr)) != MVG_OK) return rc;
+  }
+  MVG_CUDA(h, cudaEventRecord(h->ev[1], h->stream));
+  return MVG_OK;
+}
+
+int mvg_hyper_step(mvg_handle* h) {
+  if (!h) return MVG_EINVAL;
+  if (!h->state_ready) return fail(h, MVG_ESTATE, "no state yet");
+  MVG_CUDA(h, cudaSetDevice(h->cfg.device));
+  // rebuild the statistics of the current assignment, then one hyper step (no draw, no reseat)
+  MVG_CUDA(h, cudaMemcpyAsync(h->c.choice, h->c.table_cur, sizeof(int32_t) * (size_t)h->c.n_rows,
+                              cudaMemcpyDeviceToDevice, h->stream));
+  return rebuild_pipeline(h, kFinHyper, nullptr);
+}
+
+int mvg_sync(mvg_handle* h) {
+  if (!h) return MVG_EINVAL;
+  MVG_CUDA(h, cudaSetDevice(h->cfg.device));
+  MVG_CUDA(h, cudaStreamSynchronize(h->stream));
+  return MVG_OK;
+}
+
+int mvg_run(mvg_handle* h, int32_t M, int32_t burn_in, int32_t thin, int32_t n_saved_max,
+            int32_t* saved_table_of, int32_t* saved_dish_of, double* saved_hypers, int32_t* n_saved) {
+  if (!h) return MVG_EINVAL;
+  if (M < 0 || thin <= 0) return fail(h, MVG_EINVAL, "M >= 0 and thin >= 1 required");
+  const Ctx& c = h->c;
+  int saved = 0;
+  for (int iter = 0; iter < M; ++iter) {
+    int rc = mvg_sweep(h, 1, 1);
+    if (rc != MVG_OK) return rc;
+    if (iter >= burn_in && ((iter - burn_in) % thin == 0)) {      // multiview_gibbs.cpp:205
+      if (saved >= n_saved_max) return fail(h, MVG_EINVAL, "trace buffers too small");
+      if (saved_table_of)
+        MVG_CUDA(h, cudaMemcpyAsync(saved_table_of + (size_t)saved * c.n_rows, c.table_cur,
+                                    sizeof(int32_t) * (size_t)c.n_rows, cudaMemcpyDeviceToHost, h->stream));
+      if (saved_dish_of)
+        MVG_CUDA(h, cudaMemcpyAsync(saved_dish_of + (size_t)saved * c.V * c.cap, c.dish_of,
+                                    sizeof(int32_t) * (size_t)c.V * c.cap, cudaMemcpyDeviceToHost, h->stream));
+      if (saved_hypers)
+        MVG_CUDA(h, cudaMemcpyAsync(saved_hypers + (size_t)saved * (3 * c.V + 2), c.hyp,
+                                    sizeof(double) * (size_t)(3 * c.V + 2), cudaMemcpyDeviceToHost, h->stream));
+      ++saved;
+    }
+  }
+  if (n_saved) *n_saved = saved;
+  return check_status(h);
+}
+
+int mvg_comm_attach(mvg_handle* h, void* nccl_comm) {
+  if (!h || !nccl_comm) return MVG_EINVAL;
+  std::string err;
+  if (!load_nccl(err)) return fail(h, MVG_ENCCL, err);
+  h->comm = nccl_comm;
+  h->comm_owned = false;
+  return MVG_OK;
+}
+
+int mvg_comm_unique_id(void* unique_id_128) {
+  std::string err;
+  if (!unique_id_128) return MVG_EINVAL;
+  if (!load_nccl(err)) return fail(nullptr, MVG_ENCCL, err);
+  int r = g_nccl.GetUniqueId(unique_id_128);
+  return r == 0 ? MVG_OK : fail(nullptr, MVG_ENCCL, "ncclGetUniqueId failed");
+}
+
+int mvg_comm_init_rank(mvg_handle* h, const void* unique_id_128) {
+  if (!h || !unique_id_128) return MVG_EINVAL;
+  std::string err;
+  if (!load_nccl(err)) return fail(h, MVG_ENCCL, err);
+  MVG_CUDA(h, cudaSetDevice(h->cfg.device));
+  UidByValue uid;
+  std::memcpy(uid.internal, unique_id_128, 128);
+  void* comm = nullptr;
+  int r = g_nccl.CommInitRank(&comm, h->c.world, uid, h->c.rank);
+  if (r != 0) return fail(h, MVG_ENCCL, std::string("ncclCommInitRank: ") + (g_nccl.GetErrorString ? g_nccl.GetErrorString(r) : "?"));
+  h->comm = comm;
+  h->comm_owned = true;
+  return MVG_OK;
+}
+
+int mvg_get_params(mvg_handle* h, const mvg_params_host* o) {
+  if (!h || !o) return MVG_EINVAL;
+  if (!h->state_ready) return fail(h, MVG_ESTATE, "no state yet");
+  MVG_CUDA(h, cudaSetDevice(h->cfg.device));
+  const Ctx& c = h->c;
+  const size_t vc = (size_t)c.V * c.cap;
+  std::vector<TableParam> tp(vc);
+  std::vector<ViewParam> vp(c.V);
+  std::vector<TableMass> tm(c.cap);
+  GlobalParam g;
+  MVG_CUDA(h, cudaMemcpyAsync(tp.data(), c.tparam, sizeof(TableParam) * vc, cudaMemcpyDeviceToHost, h->stream));
+  MVG_CUDA(h, cudaMemcpyAsync(vp.data(), c.vparam, sizeof(ViewParam) * c.V, cudaMemcpyDeviceToHost, h->stream));
+  MVG_CUDA(h, cudaMemcpyAsync(tm.data(), c.tmass, sizeof(TableMass) * c.cap, cudaMemcpyDeviceToHost, h->stream));
+  MVG_CUDA(h, cudaMemcpyAsync(&g, c.gparam, sizeof(g), cudaMemcpyDeviceToHost, h->stream));
+  if (o->m) MVG_CUDA(h, cudaMemcpyAsync(o->m, c.mean, sizeof(float) * (size_t)c.cap * c.Dsum, cudaMemcpyDeviceToHost, h->stream));
+  MVG_CUDA(h, cudaStreamSynchronize(h->stream));
+  for (size_t i = 0; i < vc; ++i) {
+    if (o->dish) o->dish[i] = tp[i].dish;
+    if (o->A) o->A[i] = tp[i].A;
+    if (o->C) o->C[i] = tp[i].C;
+    if (o->A1) o->A1[i] = tp[i].A1;
+    if (o->C1) o->C1[i] = tp[i].C1;
+    if (o->W) o->W[i] = tp[i].W;
+    if (o->W1) o->W1[i] = tp[i].W1;
+    if (o->lone) o->lone[i] = tp[i].lone;
+  }
+  for (int v = 0; v < c.V; ++v) {
+    if (o->AN) o->AN[v] = vp[v].AN;
+    if (o->CN) o->CN[v] = vp[v].CN;
+    if (o->WN) { o->WN[2 * v] = vp[v].WN0; o->WN[2 * v + 1] = vp[v].WN1; }
+    if (o->LD) { o->LD[2 * v] = vp[v].LD0; o->LD[2 * v + 1] = vp[v].LD1; }
+  }
+  for (int t = 0; t < c.cap; ++t) {
+    if (o->LM) o->LM[t] = tm[t].LM;
+    if (o->LM1) o->LM1[t] = tm[t].LM1;
+    if (o->single) o->single[t] = tm[t].single;
+  }
+  if (o->LMN) { o->LMN[0] = g.LMN0; o->LMN[1] = g.LMN1; }
+  return MVG_OK;
+}
+
+int mvg_get_debug_rows(mvg_handle* h, float* acc, float* xx, int32_t* choice) {
+  if (!h) return MVG_EINVAL;
+  const Ctx& c = h->c;
+  if (!c.debug_export || !c.dbg_acc) return fail(h, MVG_ESTATE, "handle was not created with debug_export");
+  MVG_CUDA(h, cudaSetDevice(h->cfg.device));
+  const size_t N = (size_t)c.n_rows;
+  if (acc) MVG_CUDA(h, cudaMemcpyAsync(acc, c.dbg_acc, sizeof(float) * N * c.V * c.cap, cudaMemcpyDeviceToHost, h->stream));
+  if (xx) MVG_CUDA(h, cudaMemcpyAsync(xx, c.dbg_xx, sizeof(float) * N * c.V, cudaMemcpyDeviceToHost, h->stream));
+  if (choice) MVG_CUDA(h, cudaMemcpyAsync(choice, c.dbg_choice, sizeof(int32_t) * N, cudaMemcpyDeviceToHost, h->stream));
+  MVG_CUDA(h, cudaStreamSynchronize(h->stream));
+  return MVG_OK;
+}
+
+int mvg_get_debug_births(mvg_handle* h, int32_t* n_seated, int64_t* rows, double* w) {
+  if (!h) return MVG_EINVAL;
+  const Ctx& c = h->c;
+  if (!c.debug_export) return fail(h, MVG_ESTATE, "handle was not created with debug_export");
+  MVG_CUDA(h, cudaSetDevice(h->cfg.device));
+  if (n_seated) MVG_CUDA(h, cudaMemcpyAsync(n_seated, c.dbg_nseated, sizeof(int32_t), cudaMemcpyDeviceToHost, h->stream));
+  if (rows) MVG_CUDA(h, cudaMemcpyAsync(rows, c.dbg_birth_rows, sizeof(int64_t) * (size_t)c.cap, cudaMemcpyDeviceToHost, h->stream));
+  if (w) MVG_CUDA(h, cudaMemcpyAsync(w, c.dbg_birth_w, sizeof(double) * (size_t)c.cap * c.V * (c.cap + 1), cudaMemcpyDeviceToHost, h->stream));
+  MVG_CUDA(h, cudaStreamSynchronize(h->stream));
+  return MVG_OK;
+}
+
+int mvg_last_sweep_ms(mvg_handle* h, float* ms_total) {
+  if (!h || !ms_total) return MVG_EINVAL;
+  MVG_CUDA(h, cudaSetDevice(h->cfg.device));
+  MVG_CUDA(h, cudaEventSynchronize(h->ev[1]));
+  MVG_CUDA(h, cudaEventElapsedTime(ms_total, h->ev[0], h->ev[1]));
+  return MVG_OK;
+}
+
+int64_t mvg_launch_count(const mvg_handle* h) { return h ? h->launches : 0; }
+
+int mvg_profile_sweep(mvg_handle* h, int32_t do_hyper, float ms_out[6]) {
+  if (!h || !ms_out) return MVG_EINVAL;
+  if (!h->state_ready) return fail(h, MVG_ESTATE, "no state yet");
+  MVG_CUDA(h, cudaSetDevice(h->cfg.device));
+  const int32_t flags = kFinReseat | kFinAdvance | (do_hyper ? kFinHyper : 0);
+  MVG_CUDA(h, cudaEventRecord(h->ev[2], h->stream));
+  int rc = launch_draw(h);
+  if (rc != MVG_OK) return rc;
+  MVG_CUDA(h, cudaEventRecord(h->ev[3], h->stream));
+  MVG_CUDA(h, launch_pack(h->c, h->stream));
+  h->launches += 1;
+  MVG_CUDA(h, cudaEventRecord(h->ev[4], h->stream));
+  cudaEvent_t marks[4];
+  for (auto& m : marks) MVG_CUDA(h, cudaEventCreate(&m));
+  rc = rebuild_pipeline(h, flags, marks);
+  if (rc == MVG_OK) {
+    MVG_CUDA(h, cudaStreamSynchronize(h->stream));
+    cudaEventElapsedTime(&ms_out[0], h->ev[2], h->ev[3]);
+    cudaEventElapsedTime(&ms_out[1], h->ev[3], h->ev[4]);
+    cudaEventElapsedTime(&ms_out[2], h->ev[4], marks[0]);
+    cudaEventElapsedTime(&ms_out[3], marks[0], marks[1]);
+    cudaEventElapsedTime(&ms_out[5], marks[1], marks[2]);
+    cudaEventElapsedTime(&ms_out[4], marks[2], marks[3]);
+  }
+  for (auto& m : marks) cudaEventDestroy(m);
+  return rc;
+}
+
+void* mvg_stream(mvg_handle* h) { return h ? static_cast<void*>(h->stream) : nullptr; }
+
+void mvg_philox4x32_10(const uint32_t ctr[4], const uint32_t key[2], uint32_t out[4]) {
+  U4 c{ctr[0], ctr[1], ctr[2], ctr[3]};
+  const U4 r = philox4x32_10(c, key[0], key[1]);
+  out[0] = r.x; out[1] = r.y; out[2] = r.z; out[3] = r.w;
+}
+float mvg_philox_uniform_f32(uint64_t seed, uint32_t chain, uint32_t domain, uint32_t slot, uint32_t sweep, uint64_t index) {
+  return uniform_f32_from(stream_block(seed, chain, domain, slot, sweep, index).x);
+}
+double mvg_philox_uniform_f64(uint64_t seed, uint32_t chain, uint32_t domain, uint32_t slot, uint32_t sweep, uint64_t index) {
+  const U4 r = stream_block(seed, chain, domain, slot, sweep, index);
+  return uniform_f64_from(r.x, r.y);
+}
+double mvg_philox_normal(uint64_t seed, uint32_t chain, uint32_t domain, uint32_t slot, uint32_t sweep, uint64_t index) {
+  const U4 r = stream_block(seed, chain, domain, slot, sweep, index);
+  const double u1 = uniform_f64_from(r.x, r.y), u2 = uniform_f64_from(r.z, r.w);
+  return sqrt(-2.0 * log(u1)) * cos(6.283185307179586476925286766559 * u2);
+}
+
+}  // extern "C"

@@ -1,0 +1,111 @@
+// mv_ctx.h — the POD kernel context: every device pointer and size one chain shard needs.
+// Passed by value to the kernels (well under the 4 KB parameter limit).
+//
+// HBM layout.  N = rows of this shard, V views, cap slots, D_v dims,
+// Dsum = sum D_v, doff[v] = sum_{u<v} D_u:
+//   x[v]            float  [N][D_v]        row-major features of view v            (y[v][i], multiview_state.h:22)
+//   table_cur       int32  [N]             table slot of each row                  (table_of)
+//   choice          int32  [N]             raw draw of the current sweep, -1 = new table
+//   birthmask       uint32 [ceil(N/32)]    bit r of word c: row 32c+r drew a new table
+//   chunk_prefix    int32  [ceil(N/32)]    births in rows before chunk c (this shard)
+//   n_t             int32  [cap]           customers per table                     (n_t)
+//   dish_of         int32  [V][cap]        dish of table t in view v, -1 = free    (dish_of)
+//   n_vk, l_vk      int32  [V][cap]        customers / tables per dish             (ViewState::n_vk, l_vk)
+//   S1t, S1k        double [cap*Dsum]      per view a [cap][D_v] block: sums of rows per TABLE / per DISH
+//   S2t, S2k        double [V][cap]        sums of squared norms per table / dish  (ViewState::sum_y2)
+//   hyp             double [3V+2]          alpha_v[V], sigma_v[V], tau_v[V], alpha_g, sigma_g
+//   tparam..gparam  FP32 parameter block of the next sweep (mv_device.cuh)
+//   mean            float  [cap*Dsum]      per view [cap][D_v] per-TABLE posterior means m
+//   partial         float  [stat_ctas][cap*Dsum + V*cap] + int32 [stat_ctas][cap]   per-CTA statistics
+//   packet          bytes  [world][pkt_bytes]   what the shards exchange once per sweep
+#pragma once
+#include <stdint.h>
+
+#include "mv_device.cuh"
+
+namespace mv {
+
+struct PacketLayout {       // byte offsets inside one shard's packet
+  int32_t off_hdr;          // int32[8]: ncand, nbirth_local, rank, 0, row_offset (int64 in words 4-5), 0, 0
+  int32_t off_cnt;          // int32[cap]      rows per table among non-candidate rows
+  int32_t off_cand_row;     // int32[cap]      local row index of each candidate birth
+  int32_t off_cand_t0;      // int32[cap]      its current table
+  int32_t off_s2t;          // double[V*cap]
+  int32_t off_s1t;          // double[cap*Dsum]
+  int32_t off_cand_x;       // float[cap][Dsum] features of the candidate rows, views concatenated
+  int32_t bytes;            // total, multiple of 16
+};
+
+struct Ctx {
+  int32_t n_rows, V, cap, Dsum;
+  int64_t row_offset, n_global;
+  uint64_t seed;
+  uint32_t chain;
+  int32_t rank, world;
+  int32_t n_chunks;         // ceil(n_rows/32)
+  int32_t stat_ctas;        // CTAs of the statistics kernel (fixes the summation tree)
+  int32_t debug_export;
+  int32_t D[kMaxViews];
+  int32_t doff[kMaxViews];
+  const float* x[kMaxViews];
+
+  int32_t* table_cur;
+  int32_t* choice;
+  uint32_t* birthmask;
+  int32_t* chunk_prefix;
+
+  int32_t* n_t;
+  int32_t* dish_of;
+  int32_t* n_vk;
+  int32_t* l_vk;
+  double* S1t;
+  double* S2t;
+  double* S1k;
+  double* S2k;
+  double* hyp;
+  uint32_t* sweep;          // [1] index of the next sweep
+  int32_t* status;          // [4] device-side error flags
+
+  TableParam* tparam;       // [V][cap]
+  ViewParam* vparam;        // [V]
+  TableMass* tmass;         // [cap]
+  GlobalParam* gparam;      // [1]
+  float* mean;              // [cap*Dsum]
+  float* mean_hi;           // tensor-core engine: TF32-representable part of mean
+  float* mean_lo;           //   and the remainder
+
+  float* partial_f;         // [stat_ctas][cap*Dsum + V*cap]
+  int32_t* partial_n;       // [stat_ctas][cap]
+  unsigned char* packet;    // [world][pkt.bytes]; this shard writes slot `rank`
+  PacketLayout pkt;
+
+  double* birth_lf;         // [cap][V][cap+1] scratch: log f of each seated birth under each dish
+  // debug exports
+  float* dbg_acc;           // [N][V][cap]
+  float* dbg_xx;            // [N][V]
+  int32_t* dbg_choice;      // [N]
+  int64_t* dbg_birth_rows;  // [cap]
+  double* dbg_birth_w;      // [cap][V][cap+1]
+  int32_t* dbg_nseated;     // [1]
+};
+
+enum FinalizeFlags : int32_t {
+  kFinReseat = 1,      // seat births / resolve candidates (after a draw)
+  kFinHyper = 2,       // run the hyperparameter step
+  kFinAdvance = 4,     // sweep += 1
+  kFinTauInit = 8      // derive tau_v from pooled variance (reference init), alpha/sigma literals
+};
+
+// launchers (definitions in the .cu files)
+cudaError_t launch_draw_simt(const Ctx& c, cudaStream_t s);
+cudaError_t launch_draw_tc(const Ctx& c, cudaStream_t s);
+bool draw_tc_supported(const Ctx& c);
+cudaError_t launch_pack(const Ctx& c, cudaStream_t s);
+cudaError_t launch_stats(const Ctx& c, cudaStream_t s);
+cudaError_t launch_reduce(const Ctx& c, cudaStream_t s);
+cudaError_t launch_finalize(const Ctx& c, int32_t flags, cudaStream_t s);
+cudaError_t launch_init_tables(const Ctx& c, int32_t mode, cudaStream_t s);
+cudaError_t launch_f64_to_f32(const double* src, float* dst, int64_t n, cudaStream_t s);
+int stats_smem_bytes(const Ctx& c);
+
+}  // namespace mv

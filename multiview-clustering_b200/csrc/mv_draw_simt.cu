@@ -1,0 +1,144 @@
+// mv_draw_simt.cu — likelihood + draw on FP32 CUDA cores (engine MVG_ENGINE_SIMT).
+//
+// One thread owns one customer.  For every view it forms the dot products x.m_t against the
+// per-table posterior means (staged in shared memory, broadcast reads) as ONE ascending fmaf chain
+// per table — the order oracle/mv_oracle.c:mvo_stageA_f32 restates — and hands them to
+// RowEpilogue (mv_device.cuh).  Any dim, any number of views; used for the reference's scalar
+// views (D = 1, New_Simulation.R) and wherever the tcgen05 engine's shape constraints do not hold.
+//
+// Replaces, per customer: remove_customer + compute_table_probs_with_cache + the inverse-CDF draw
+// (/root/reference/Multiview/multiview_utils.cpp:71-192, multiview_gibbs.cpp:157-199).
+#include "mv_ctx.h"
+
+namespace mv {
+
+constexpr int kSimtThreads = 128;
+constexpr int kSimtDChunk = 128;   // columns of m staged per pass
+
+template <int CAP, bool VEC4>
+__global__ void __launch_bounds__(kSimtThreads, 2) k_draw_simt(const Ctx c) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  float* s_m = reinterpret_cast<float*>(smem_raw);                       // [CAP][dch]
+  const int dch_max = (c.Dsum < kSimtDChunk) ? c.Dsum : kSimtDChunk;     // upper bound on any view's chunk
+  TableParam* s_tp = reinterpret_cast<TableParam*>(smem_raw + sizeof(float) * (size_t)CAP * (size_t)dch_max);
+  __shared__ TableMass s_tm[CAP];
+  __shared__ GlobalParam s_g;
+  __shared__ ViewParam s_vp;
+
+  const int tid = threadIdx.x;
+  for (int t = tid; t < CAP; t += kSimtThreads) s_tm[t] = c.tmass[t];
+  if (tid == 0) s_g = *c.gparam;
+  __syncthreads();
+  const uint32_t sweep = s_g.sweep;
+
+  const int n_tiles = (c.n_rows + kSimtThreads - 1) / kSimtThreads;
+  for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+    const int row = tile * kSimtThreads + tid;
+    const bool live = row < c.n_rows;
+    const int rowc = live ? row : (c.n_rows - 1);
+    RowEpilogue<CAP> epi;
+    epi.begin(s_tm, s_g, c.table_cur[rowc]);
+
+    for (int v = 0; v < c.V; ++v) {
+      const int D = c.D[v];
+      const float* __restrict__ xrow = c.x[v] + (size_t)rowc * D;
+      const float* __restrict__ mean_v = c.mean + (size_t)c.cap * c.doff[v];
+      float acc[CAP];
+#pragma unroll
+      for (int t = 0; t < CAP; ++t) acc[t] = 0.0f;
+      float xx = 0.0f;
+
+      for (int d0 = 0; d0 < D; d0 += kSimtDChunk) {
+        const int dch = (D - d0 < kSimtDChunk) ? (D - d0) : kSimtDChunk;
+        __syncthreads();   // previous users of s_m / s_tp are done
+        for (int idx = tid; idx < CAP * dch; idx += kSimtThreads) {
+          const int t = idx / dch, dd = idx - t * dch;
+          s_m[t * dch + dd] = mean_v[(size_t)t * D + d0 + dd];
+        }
+        if (d0 == 0) {
+          for (int t = tid; t < CAP; t += kSimtThreads) s_tp[t] = c.tparam[v * CAP + t];
+          if (tid == 0) s_vp = c.vparam[v];
+        }
+        __syncthreads();
+        if (VEC4) {
+          for (int dd = 0; dd < dch; dd += 4) {
+            const float4 xv = __ldg(reinterpret_cast<const float4*>(xrow + d0 + dd));
+            xx = __fmaf_rn(xv.x, xv.x, xx);
+            xx = __fmaf_rn(xv.y, xv.y, xx);
+            xx = __fmaf_rn(xv.z, xv.z, xx);
+            xx = __fmaf_rn(xv.w, xv.w, xx);
+#pragma unroll
+            for (int t = 0; t < CAP; ++t) {
+              const float4 mv4 = *reinterpret_cast<const float4*>(s_m + t * dch + dd);
+              float a = acc[t];
+              a = __fmaf_rn(xv.x, mv4.x, a);
+              a = __fmaf_rn(xv.y, mv4.y, a);
+              a = __fmaf_rn(xv.z, mv4.z, a);
+              a = __fmaf_rn(xv.w, mv4.w, a);
+              acc[t] = a;
+            }
+          }
+        } else {
+          for (int dd = 0; dd < dch; ++dd) {
+            const float xs = __ldg(xrow + d0 + dd);
+            xx = __fmaf_rn(xs, xs, xx);
+#pragma unroll
+            for (int t = 0; t < CAP; ++t) acc[t] = __fmaf_rn(xs, s_m[t * dch + dd], acc[t]);
+          }
+        }
+      }
+      if (c.debug_export && live) {
+        float* da = c.dbg_acc + ((size_t)row * c.V + v) * CAP;
+#pragma unroll
+        for (int t = 0; t < CAP; ++t) da[t] = acc[t];
+        c.dbg_xx[(size_t)row * c.V + v] = xx;
+      }
+      epi.view(s_tp, s_vp, acc, xx, v == 0);
+    }
+
+    const U4 rnd = stream_block(c.seed, c.chain, kDomTable, 0, sweep, (uint64_t)(c.row_offset + rowc));
+    int choice = epi.finish(s_tm, uniform_f32_from(rnd.x));
+    if (live) {
+      c.choice[row] = choice;
+      if (c.debug_export) c.dbg_choice[row] = choice;
+    }
+    const unsigned births = __ballot_sync(0xffffffffu, live && choice == kNewTable);
+    if ((tid & 31) == 0 && (row >> 5) < c.n_chunks) c.birthmask[row >> 5] = births;
+  }
+}
+
+template <int CAP>
+static cudaError_t launch_simt_cap(const Ctx& c, cudaStream_t s) {
+  bool vec4 = true;
+  for (int v = 0; v < c.V; ++v)
+    if ((c.D[v] & 3) != 0 || (reinterpret_cast<uintptr_t>(c.x[v]) & 15) != 0) vec4 = false;
+  const int dch = (c.Dsum < kSimtDChunk) ? c.Dsum : kSimtDChunk;
+  const size_t smem = sizeof(float) * (size_t)CAP * dch + sizeof(TableParam) * CAP;
+  const int n_tiles = (c.n_rows + kSimtThreads - 1) / kSimtThreads;
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  const int grid = n_tiles < 2 * sms ? n_tiles : 2 * sms;
+  cudaError_t e;
+  if (vec4) {
+    e = cudaFuncSetAttribute(k_draw_simt<CAP, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    k_draw_simt<CAP, true><<<grid, kSimtThreads, smem, s>>>(c);
+  } else {
+    e = cudaFuncSetAttribute(k_draw_simt<CAP, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    k_draw_simt<CAP, false><<<grid, kSimtThreads, smem, s>>>(c);
+  }
+  return cudaGetLastError();
+}
+
+cudaError_t launch_draw_simt(const Ctx& c, cudaStream_t s) {
+  if (c.n_rows <= 0) return cudaSuccess;
+  switch (c.cap) {
+    case 32: return launch_simt_cap<32>(c, s);
+    case 64: return launch_simt_cap<64>(c, s);
+    default: return cudaErrorInvalidValue;
+  }
+}
+
+}  // namespace mv

@@ -1,0 +1,854 @@
+// mv_state_kernels.cu — everything of a sweep that is not the likelihood+draw kernel:
+//
+//   k_pack      ordered compaction of the rows that drew "new table" (first `nfree` in row order
+//               become candidates; their features go into the exchange packet)
+//   k_stats     segmented reduction of the rows into per-TABLE sufficient statistics
+//               (fixed row->CTA->warp mapping, per-warp private accumulators: a fixed-order tree)
+//   k_reduce    fixed-order FP64 sum of the per-CTA partials into this shard's packet
+//   k_finalize  one CTA: rank-ordered sum of the shards' packets, births (dish sampling) and
+//               deaths, per-dish statistics, the Metropolis-Hastings hyperparameter step, and the
+//               FP32 parameter block of the next sweep
+//
+// Reference code being replaced (paths under /root/reference/Multiview):
+//   sufficient statistics      multiview_gibbs.cpp:64-73 (rebuild), multiview_utils.cpp:151-163,199-206
+//   births                     create_empty_table / assign_dishes_new_table / sample_dish_for_new_table,
+//                              multiview_utils.cpp:209-289
+//   deaths                     remove_customer's empty-table branch, multiview_utils.cpp:168-191
+//   hyper step                 update_hyperparameters and helpers, multiview_hyper.cpp:53-128,166-360
+#include "mv_ctx.h"
+
+namespace mv {
+
+constexpr double kEps = 1e-6;            // multiview_hyper.cpp:13
+constexpr double kLog2e = 1.4426950408889634074;
+constexpr double kPi = 3.14159265358979323846;
+
+__device__ __forceinline__ int32_t* pkt_i32(const Ctx& c, int g, int off) {
+  return reinterpret_cast<int32_t*>(c.packet + (size_t)g * c.pkt.bytes + off);
+}
+__device__ __forceinline__ double* pkt_f64(const Ctx& c, int g, int off) {
+  return reinterpret_cast<double*>(c.packet + (size_t)g * c.pkt.bytes + off);
+}
+__device__ __forceinline__ float* pkt_f32(const Ctx& c, int g, int off) {
+  return reinterpret_cast<float*>(c.packet + (size_t)g * c.pkt.bytes + off);
+}
+
+// =============================================================================================
+// k_pack
+// =============================================================================================
+constexpr int kPackThreads = 1024;
+
+__global__ void __launch_bounds__(kPackThreads, 1) k_pack(const Ctx c) {
+  __shared__ int s_warp[32];
+  __shared__ int s_total;
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  const int nfree = c.gparam->nfree;
+  int32_t* cand_row = pkt_i32(c, c.rank, c.pkt.off_cand_row);
+  int32_t* cand_t0 = pkt_i32(c, c.rank, c.pkt.off_cand_t0);
+  const int per = (c.n_chunks + kPackThreads - 1) / kPackThreads;
+  const int lo = min(tid * per, c.n_chunks), hi = min(lo + per, c.n_chunks);
+  int cnt = 0;
+  for (int ch = lo; ch < hi; ++ch) cnt += __popc(c.birthmask[ch]);
+  // block exclusive scan of cnt
+  int incl = cnt;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const int y = __shfl_up_sync(0xffffffffu, incl, o);
+    if (lane >= o) incl += y;
+  }
+  if (lane == 31) s_warp[wid] = incl;
+  __syncthreads();
+  if (wid == 0) {
+    int w = s_warp[lane];
+    int wi = w;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int y = __shfl_up_sync(0xffffffffu, wi, o);
+      if (lane >= o) wi += y;
+    }
+    s_warp[lane] = wi - w;            // exclusive prefix of the warp totals
+    if (lane == 31) s_total = wi;
+  }
+  __syncthreads();
+  int running = s_warp[wid] + incl - cnt;
+  for (int ch = lo; ch < hi; ++ch) {
+    c.chunk_prefix[ch] = running;
+    unsigned m = c.birthmask[ch];
+    while (m) {
+      const int b = __ffs(m) - 1;
+      m &= m - 1;
+      if (running < nfree) cand_row[running] = ch * 32 + b;
+      ++running;
+    }
+  }
+  __syncthreads();
+  const int total = s_total;
+  const int ncand = total < nfree ? total : nfree;
+  if (tid == 0) {
+    int32_t* hdr = pkt_i32(c, c.rank, c.pkt.off_hdr);
+    hdr[0] = ncand; hdr[1] = total; hdr[2] = c.rank; hdr[3] = 0;
+    *reinterpret_cast<int64_t*>(hdr + 4) = c.row_offset;
+    hdr[6] = 0; hdr[7] = 0;
+  }
+  __threadfence_block();
+  __syncthreads();
+  float* cx = pkt_f32(c, c.rank, c.pkt.off_cand_x);
+  for (int j = wid; j < ncand; j += kPackThreads / 32) {
+    const int row = cand_row[j];
+    if (lane == 0) cand_t0[j] = c.table_cur[row];
+    for (int v = 0; v < c.V; ++v) {
+      const int D = c.D[v];
+      const float* src = c.x[v] + (size_t)row * D;
+      float* dst = cx + (size_t)j * c.Dsum + c.doff[v];
+      for (int dd = lane; dd < D; dd += 32) dst[dd] = src[dd];
+    }
+  }
+}
+
+cudaError_t launch_pack(const Ctx& c, cudaStream_t s) {
+  k_pack<<<1, kPackThreads, 0, s>>>(c);
+  return cudaGetLastError();
+}
+
+// =============================================================================================
+// k_stats
+// =============================================================================================
+constexpr int kStatWarps = 8;
+constexpr int kStatThreads = kStatWarps * 32;
+constexpr int kStatCols = 64;     // feature columns per pass: lane handles columns lane and lane+32
+constexpr int kStatPrefetch = 8;  // rows whose loads are issued before their accumulation
+
+int stats_smem_bytes(const Ctx& c) {
+  return kStatWarps * c.cap * (kStatCols + 32) * (int)sizeof(float) + kStatWarps * c.cap * (int)sizeof(int32_t);
+}
+
+__global__ void __launch_bounds__(kStatThreads, 1) k_stats(const Ctx c) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int cap = c.cap;
+  float* s_acc = reinterpret_cast<float*>(smem_raw);                     // [warps][cap][64]
+  float* s_q = s_acc + (size_t)kStatWarps * cap * kStatCols;             // [warps][cap][32]
+  int32_t* s_cnt = reinterpret_cast<int32_t*>(s_q + (size_t)kStatWarps * cap * 32);   // [warps][cap]
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  float* acc = s_acc + (size_t)wid * cap * kStatCols;
+  float* accq = s_q + (size_t)wid * cap * 32;
+  int32_t* cntw = s_cnt + wid * cap;
+
+  // fixed mapping rows -> CTA -> warp, in whole 32-row chunks
+  const int chunks_per_cta = (c.n_chunks + gridDim.x - 1) / gridDim.x;
+  const int cta_lo = min((int)blockIdx.x * chunks_per_cta, c.n_chunks);
+  const int cta_hi = min(cta_lo + chunks_per_cta, c.n_chunks);
+  const int chunks_per_warp = (cta_hi - cta_lo + kStatWarps - 1) / kStatWarps;
+  const int w_lo = min(cta_lo + wid * chunks_per_warp, cta_hi);
+  const int w_hi = min(w_lo + chunks_per_warp, cta_hi);
+  const int nfree = c.gparam->nfree;
+
+  const size_t part_stride = (size_t)cap * c.Dsum + (size_t)c.V * cap;
+  float* part = c.partial_f + (size_t)blockIdx.x * part_stride;
+  float* part_s2 = part + (size_t)cap * c.Dsum;
+
+  bool first_pass = true;
+  for (int v = 0; v < c.V; ++v) {
+    const int D = c.D[v];
+    const float* __restrict__ xv = c.x[v];
+    for (int dc = 0; dc < D; dc += kStatCols) {
+      for (int i = lane; i < cap * kStatCols; i += 32) acc[i] = 0.0f;
+      for (int i = lane; i < cap * 32; i += 32) accq[i] = 0.0f;
+      if (first_pass) for (int i = lane; i < cap; i += 32) cntw[i] = 0;
+      __syncwarp();
+      const int col0 = dc + lane, col1 = dc + lane + 32;
+      const bool has0 = col0 < D, has1 = col1 < D;
+
+      for (int ch = w_lo; ch < w_hi; ++ch) {
+        const int row = ch * 32 + lane;
+        int tj = -3;                                   // beyond the end
+        if (row < c.n_rows) {
+          tj = c.choice[row];
+          if (first_pass) {
+            if (tj == kNewTable) {
+              const unsigned m = c.birthmask[ch];
+              const int rank = c.chunk_prefix[ch] + __popc(m & ((1u << lane) - 1u));
+              tj = (rank < nfree) ? -2 : c.table_cur[row];   // candidate : overflow stays put
+              c.choice[row] = tj;
+            }
+            if (tj >= 0) c.table_cur[row] = tj;
+          }
+        }
+        for (int j0 = 0; j0 < 32; j0 += kStatPrefetch) {
+          float x0[kStatPrefetch], x1[kStatPrefetch];
+          int tt[kStatPrefetch];
+#pragma unroll
+          for (int u = 0; u < kStatPrefetch; ++u) {
+            tt[u] = __shfl_sync(0xffffffffu, tj, j0 + u);
+            const size_t base = (size_t)(ch * 32 + j0 + u) * D;
+            x0[u] = (tt[u] >= 0 && has0) ? __ldg(xv + base + col0) : 0.0f;
+            x1[u] = (tt[u] >= 0 && has1) ? __ldg(xv + base + col1) : 0.0f;
+          }
+#pragma unroll
+          for (int u = 0; u < kStatPrefetch; ++u) {
+            const int t = tt[u];
+            if (t < 0) continue;                        // warp-uniform
+            float* a = acc + t * kStatCols;
+            a[lane] = __fadd_rn(a[lane], x0[u]);
+            a[lane + 32] = __fadd_rn(a[lane + 32], x1[u]);
+            float* q = accq + t * 32;
+            q[lane] = __fadd_rn(q[lane], __fmaf_rn(x1[u], x1[u], __fmul_rn(x0[u], x0[u])));
+            if (first_pass && lane == 0) cntw[t] += 1;
+          }
+        }
+      }
+      __syncthreads();
+      // fixed-order sum over the warps of this CTA
+      for (int i = tid; i < cap * kStatCols; i += kStatThreads) {
+        const int t = i / kStatCols, col = i - t * kStatCols;
+        if (dc + col < D) {
+          float sum = 0.0f;
+#pragma unroll
+          for (int w = 0; w < kStatWarps; ++w) sum = __fadd_rn(sum, s_acc[((size_t)w * cap + t) * kStatCols + col]);
+          part[(size_t)cap * c.doff[v] + (size_t)t * D + dc + col] = sum;
+        }
+      }
+      for (int t = tid; t < cap; t += kStatThreads) {
+        float sum = 0.0f;
+        for (int w = 0; w < kStatWarps; ++w)
+          for (int l = 0; l < 32; ++l) sum = __fadd_rn(sum, s_q[((size_t)w * cap + t) * 32 + l]);
+        if (dc == 0) part_s2[v * cap + t] = sum;
+        else part_s2[v * cap + t] = __fadd_rn(part_s2[v * cap + t], sum);
+        if (first_pass) {
+          int n = 0;
+          for (int w = 0; w < kStatWarps; ++w) n += s_cnt[w * cap + t];
+          c.partial_n[(size_t)blockIdx.x * cap + t] = n;
+        }
+      }
+      __syncthreads();
+      first_pass = false;
+    }
+  }
+}
+
+cudaError_t launch_stats(const Ctx& c, cudaStream_t s) {
+  const int smem = stats_smem_bytes(c);
+  cudaError_t e = cudaFuncSetAttribute(k_stats, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+  if (e != cudaSuccess) return e;
+  k_stats<<<c.stat_ctas, kStatThreads, smem, s>>>(c);
+  return cudaGetLastError();
+}
+
+// =============================================================================================
+// k_reduce
+// =============================================================================================
+__global__ void __launch_bounds__(256) k_reduce(const Ctx c) {
+  const int n_s1 = c.cap * c.Dsum, n_s2 = c.V * c.cap;
+  const size_t part_stride = (size_t)n_s1 + n_s2;
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n_s1 + n_s2) {
+    double sum = 0.0;
+    for (int b = 0; b < c.stat_ctas; ++b) sum += (double)c.partial_f[(size_t)b * part_stride + i];
+    if (i < n_s1) pkt_f64(c, c.rank, c.pkt.off_s1t)[i] = sum;
+    else pkt_f64(c, c.rank, c.pkt.off_s2t)[i - n_s1] = sum;
+  } else if (i < n_s1 + n_s2 + c.cap) {
+    const int t = i - n_s1 - n_s2;
+    int n = 0;
+    for (int b = 0; b < c.stat_ctas; ++b) n += c.partial_n[(size_t)b * c.cap + t];
+    pkt_i32(c, c.rank, c.pkt.off_cnt)[t] = n;
+  }
+}
+
+cudaError_t launch_reduce(const Ctx& c, cudaStream_t s) {
+  const int total = c.cap * c.Dsum + c.V * c.cap + c.cap;
+  k_reduce<<<(total + 255) / 256, 256, 0, s>>>(c);
+  return cudaGetLastError();
+}
+
+// =============================================================================================
+// k_finalize
+// =============================================================================================
+constexpr int kFinThreads = 512;
+constexpr int kMaxCap = 64;
+constexpr int kMaxWorld = 16;
+
+struct FinShared {
+  int32_t n_new[kMaxCap];                 // customers per table after this sweep
+  int32_t alive_start[kMaxCap];           // n_t > 0 at sweep start
+  int32_t free_slots[kMaxCap];
+  int32_t dish[kMaxViews][kMaxCap];       // working copy of dish_of
+  int32_t l_live[kMaxViews][kMaxCap];     // tables per dish (live-updated by births, then recomputed)
+  int32_t n_vk[kMaxViews][kMaxCap];       // customers per dish at sweep start, later the new ones
+  int32_t cand_g[kMaxWorld * kMaxCap];    // candidates in global row order: shard, index in shard
+  int32_t cand_j[kMaxWorld * kMaxCap];
+  int32_t cand_final[kMaxWorld * kMaxCap];
+  int32_t ncand_total, nseat, nfree, err;
+  double s1sq[kMaxViews][kMaxCap];        // |S1k|^2
+  double termA[2][kMaxCap + 1];           // scratch of the EPPF evaluations (two parameter sets)
+  double termB[2][kMaxCap + 1];
+  double wbuf[kMaxCap + 1];
+  double result[4];
+  double prop[2];
+  double hyp[3 * kMaxViews + 2];
+};
+
+__device__ __forceinline__ double dev_normal(const Ctx& c, uint32_t sweep, int idx) {
+  const U4 r = stream_block(c.seed, c.chain, kDomHyperNormal, 0, sweep, (uint64_t)idx);
+  const double u1 = uniform_f64_from(r.x, r.y), u2 = uniform_f64_from(r.z, r.w);
+  return sqrt(-2.0 * log(u1)) * cos(6.283185307179586476925286766559 * u2);
+}
+__device__ __forceinline__ double dev_unif(const Ctx& c, uint32_t sweep, int idx) {
+  const U4 r = stream_block(c.seed, c.chain, kDomHyperUnif, 0, sweep, (uint64_t)idx);
+  return uniform_f64_from(r.x, r.y);
+}
+
+__device__ __forceinline__ double log_prior_alpha(double a) {       // multiview_hyper.cpp:344-351
+  return (a <= 0.0) ? -INFINITY : (4.0 - 1.0) * log(a) - 3.0 * a;
+}
+__device__ __forceinline__ double log_prior_sigma(double s) {       // :353-360
+  return (s <= 0.0 || s >= 1.0) ? -INFINITY : (1.0 - 1.0) * log(s) + (5.0 - 1.0) * log(1.0 - s);
+}
+__device__ __forceinline__ double reflect_unit(double value) {      // :110-122
+  double p = value;
+  while (p <= kEps || p >= 1.0 - kEps) {
+    if (p <= kEps) p = 2.0 * kEps - p;
+    if (p >= 1.0 - kEps) p = 2.0 * (1.0 - kEps) - p;
+  }
+  return fmin(fmax(p, kEps), 1.0 - kEps);
+}
+
+// log EPPF of a partition with cluster sizes counts[0..n) (zeros = absent) of `total` items, for
+// two parameter sets at once (multiview_hyper.cpp:53-83 and :295-342; the two inner loops in closed
+// form: sum_{i=1}^{M-1} log(alpha+i) = lgamma(alpha+M) - lgamma(alpha+1) and
+// sum_{m=1}^{c-1} log(m-sigma) = lgamma(c-sigma) - lgamma(1-sigma)).  The terms are evaluated by
+// the block in parallel; threads 0/1 add them in ascending cluster order.  Block-uniform call.
+__device__ void eppf_pair(FinShared& S, const int32_t* counts, int n, long long total,
+                          double a0, double s0, double a1, double s1, double out[2]) {
+  const int tid = threadIdx.x;
+  __syncthreads();
+  if (tid < 2 * n) {
+    const int p = tid / n, i = tid - p * n;
+    const double alpha = p ? a1 : a0, sigma = p ? s1 : s0;
+    const int cnt = counts[i];
+    S.termB[p][i] = (cnt > 1) ? lgamma((double)cnt - sigma) - lgamma(1.0 - sigma) : 0.0;
+    int j = 0;                                    // rank of cluster i among the live ones
+    for (int q = 0; q < i; ++q) j += (counts[q] > 0);
+    const double term = alpha + (double)j * sigma;
+    S.termA[p][i] = (cnt > 0) ? ((term <= 0.0) ? -INFINITY : log(term)) : 0.0;
+  }
+  __syncthreads();
+  if (tid < 2) {
+    const int p = tid;
+    const double alpha = p ? a1 : a0, sigma = p ? s1 : s0;
+    double logp;
+    if (!(sigma > kEps && sigma < 1.0 - kEps) || alpha <= -sigma) {
+      logp = -INFINITY;
+    } else if (total <= 0) {
+      logp = 0.0;
+    } else {
+      logp = 0.0;
+      for (int i = 0; i < n; ++i) if (counts[i] > 0) logp += S.termA[p][i];
+      if (total > 1) logp -= lgamma(alpha + (double)total) - lgamma(alpha + 1.0);
+      for (int i = 0; i < n; ++i) if (counts[i] > 1) logp += S.termB[p][i];
+    }
+    S.result[p] = logp;
+  }
+  __syncthreads();
+  out[0] = S.result[0];
+  out[1] = S.result[1];
+  __syncthreads();
+}
+
+__device__ double log_posterior_tau(const Ctx& c, const FinShared& S, int v, double tau) {  // :176-209
+  if (tau <= 0.0) return -INFINITY;
+  const int D = c.D[v];
+  double loglik = 0.0;
+  for (int k = 0; k < c.cap; ++k) {
+    const int n_k = S.n_vk[v][k];
+    if (n_k == 0) continue;
+    double sse = c.S2k[v * c.cap + k] - S.s1sq[v][k] / (double)n_k;       // :191
+    if (sse < 0.0) sse = 0.0;
+    loglik += -0.5 * (double)n_k * (double)D * log(2.0 * kPi * tau) - 0.5 * (sse / tau);
+  }
+  const double a_tau = 2.0, b_tau = 1.0;                                   // :133-134
+  return loglik + (a_tau * log(b_tau) - lgamma(a_tau) - (a_tau + 1.0) * log(tau) - b_tau / tau);
+}
+
+// log predictive density of x (views concatenated, FP32) under dish k of view v, optionally with
+// x removed from the dish first (multiview_utils.cpp:307-338 in closed form, per coordinate).
+__device__ double log_f_dish(const Ctx& c, const FinShared& S, int v, int k, const float* x, bool loo,
+                             double tau) {
+  const int D = c.D[v];
+  const double* S1 = c.S1k + (size_t)c.cap * c.doff[v] + (size_t)k * D;
+  const double n = (double)S.n_vk[v][k] - (loo ? 1.0 : 0.0);
+  const double var = tau * (tau + n + 1.0) / (tau + n);
+  double dist = 0.0;
+  for (int dd = 0; dd < D; ++dd) {
+    const double xv = (double)x[c.doff[v] + dd];
+    const double s1 = S1[dd] - (loo ? xv : 0.0);
+    const double diff = xv - s1 / (tau + n);
+    dist += diff * diff;
+  }
+  return -0.5 * (double)D * log(2.0 * kPi * var) - 0.5 * dist / var;
+}
+
+__global__ void __launch_bounds__(kFinThreads, 1) k_finalize(const Ctx c, const int32_t flags) {
+  extern __shared__ __align__(16) unsigned char fin_smem[];
+  FinShared& S = *reinterpret_cast<FinShared*>(fin_smem);
+  const int tid = threadIdx.x;
+  const int cap = c.cap, V = c.V;
+  const uint32_t sweep = *c.sweep;
+  double* alpha_v = S.hyp;
+  double* sigma_v = S.hyp + V;
+  double* tau_v = S.hyp + 2 * V;
+  double& alpha_g = S.hyp[3 * V];
+  double& sigma_g = S.hyp[3 * V + 1];
+
+  if (tid == 0) { S.err = 0; S.ncand_total = 0; S.nseat = 0; S.nfree = 0; }
+  for (int i = tid; i < 3 * V + 2; i += kFinThreads) S.hyp[i] = c.hyp[i];
+  // ---- A. rank-ordered sums of the shards' packets ------------------------------------------
+  for (int t = tid; t < cap; t += kFinThreads) {
+    int n = 0;
+    for (int g = 0; g < c.world; ++g) n += pkt_i32(c, g, c.pkt.off_cnt)[t];
+    S.n_new[t] = n;
+    S.alive_start[t] = c.n_t[t] > 0;
+  }
+  for (int i = tid; i < cap * c.Dsum; i += kFinThreads) {
+    double sum = 0.0;
+    for (int g = 0; g < c.world; ++g) sum += pkt_f64(c, g, c.pkt.off_s1t)[i];
+    c.S1t[i] = sum;
+  }
+  for (int i = tid; i < V * cap; i += kFinThreads) {
+    double sum = 0.0;
+    for (int g = 0; g < c.world; ++g) sum += pkt_f64(c, g, c.pkt.off_s2t)[i];
+    c.S2t[i] = sum;
+    const int v = i / cap, t = i - v * cap;
+    S.dish[v][t] = c.dish_of[i];
+    S.l_live[v][t] = c.l_vk[i];
+    S.n_vk[v][t] = c.n_vk[i];
+  }
+  __syncthreads();
+
+  // ---- B. births: candidates in global row order, the first nfree are seated -----------------
+  if (flags & kFinReseat) {
+    if (tid == 0) {
+      int nf = 0;
+      for (int t = 0; t < cap; ++t) if (!S.alive_start[t]) S.free_slots[nf++] = t;
+      S.nfree = nf;
+      int n = 0;
+      for (int g = 0; g < c.world; ++g) {
+        const int nc = pkt_i32(c, g, c.pkt.off_hdr)[0];
+        for (int j = 0; j < nc && n < kMaxWorld * kMaxCap; ++j) { S.cand_g[n] = g; S.cand_j[n] = j; ++n; }
+      }
+      S.ncand_total = n;
+      S.nseat = n < nf ? n : nf;
+      if (c.debug_export) *c.dbg_nseated = S.nseat;
+    }
+    __syncthreads();
+    const int nseat = S.nseat, ncand = S.ncand_total;
+    // B1. log f of every seated candidate under every dish slot (and a new dish), in parallel
+    for (int idx = tid; idx < nseat * V * (cap + 1); idx += kFinThreads) {
+      const int b = idx / (V * (cap + 1));
+      const int rem = idx - b * V * (cap + 1);
+      const int v = rem / (cap + 1), k = rem - v * (cap + 1);
+      const float* x = pkt_f32(c, S.cand_g[b], c.pkt.off_cand_x) + (size_t)S.cand_j[b] * c.Dsum;
+      double val;
+      if (k == cap) {   // new dish: N(x; 0, tau)   (multiview_utils.cpp:340-350)
+        const int D = c.D[v];
+        double q = 0.0;
+        for (int dd = 0; dd < D; ++dd) q += (double)x[c.doff[v] + dd] * (double)x[c.doff[v] + dd];
+        val = -0.5 * (double)D * log(2.0 * kPi * tau_v[v]) - 0.5 * q / tau_v[v];
+      } else {
+        const int t0 = pkt_i32(c, S.cand_g[b], c.pkt.off_cand_t0)[S.cand_j[b]];
+        val = log_f_dish(c, S, v, k, x, (k == S.dish[v][t0]) && S.n_vk[v][k] > 0, tau_v[v]);
+      }
+      c.birth_lf[idx] = val;
+    }
+    __syncthreads();
+    // B2. seating in order; sample_dish_for_new_table (multiview_utils.cpp:224-276) per view
+    for (int b = 0; b < nseat; ++b) {
+      const int g = S.cand_g[b], j = S.cand_j[b];
+      const int t0 = pkt_i32(c, g, c.pkt.off_cand_t0)[j];
+      const int64_t grow = *reinterpret_cast<const int64_t*>(pkt_i32(c, g, c.pkt.off_hdr) + 4) +
+                           (int64_t)pkt_i32(c, g, c.pkt.off_cand_row)[j];
+      const int tn = S.free_slots[b];
+      const bool single = (c.n_t[t0] == 1);
+      for (int v = 0; v < V; ++v) {
+        const int k0 = S.dish[v][t0];
+        const double* lf = c.birth_lf + ((size_t)b * V + v) * (cap + 1);
+        if (tid <= cap) {
+          double lw = -INFINITY;
+          if (tid < cap) {
+            const int l = S.l_live[v][tid] - ((single && tid == k0) ? 1 : 0);
+            const double w = (double)l - sigma_v[v];                       // :232-233
+            if (l > 0 && w > 0.0) lw = log(w) + lf[tid];
+          } else {
+            int K_act = 0;
+            for (int k = 0; k < cap; ++k) K_act += (S.l_live[v][k] - ((single && k == k0) ? 1 : 0)) > 0;
+            const double wn = alpha_v[v] + sigma_v[v] * (double)K_act;     // :241-243
+            if (wn > 0.0) lw = log(wn) + lf[cap];
+          }
+          S.wbuf[tid] = lw;
+        }
+        __syncthreads();
+        if (tid == 0) {
+          double M = -INFINITY;
+          for (int k = 0; k <= cap; ++k) M = fmax(M, S.wbuf[k]);
+          S.result[0] = M;
+        }
+        __syncthreads();
+        if (tid <= cap) {
+          const double M = S.result[0], lw = S.wbuf[tid];
+          const double w = (M > -INFINITY && lw > -INFINITY) ? exp(lw - M) : 0.0;
+          S.termA[0][tid] = w;
+          if (c.debug_export) c.dbg_birth_w[((size_t)b * V + v) * (cap + 1) + tid] = w;
+        }
+        __syncthreads();
+        if (tid == 0) {
+          int pick = -1;
+          if (S.result[0] > -INFINITY) {
+            double total = 0.0;
+            for (int k = 0; k <= cap; ++k) total += S.termA[0][k];         // :247-248
+            const U4 r = stream_block(c.seed, c.chain, kDomDish, (uint32_t)v, sweep, (uint64_t)grow);
+            const double u = uniform_f64_from(r.x, r.y) * total;           // :261
+            double cum = 0.0;
+            for (int k = 0; k < cap; ++k) {
+              if (!(S.wbuf[k] > -INFINITY)) continue;
+              cum += S.termA[0][k];
+              if (u < cum) { pick = k; break; }
+            }
+          }
+          if (pick < 0) {                                                   // new dish: lowest free slot
+            for (int k = 0; k < cap; ++k) if (S.l_live[v][k] == 0) { pick = k; break; }
+          }
+          if (pick < 0) { S.err |= 1; pick = 0; }
+          S.dish[v][tn] = pick;
+          S.l_live[v][pick] += 1;                                           // :283
+        }
+        __syncthreads();
+      }
+      if (tid == 0) {
+        S.cand_final[b] = tn;
+        if (c.debug_export) c.dbg_birth_rows[b] = grow;
+      }
+    }
+    for (int b = nseat + tid; b < ncand; b += kFinThreads)
+      S.cand_final[b] = pkt_i32(c, S.cand_g[b], c.pkt.off_cand_t0)[S.cand_j[b]];   // overflow: stay put
+    __syncthreads();
+    // B3. candidates join the statistics of their final table, in global row order
+    if (tid == 0) for (int b = 0; b < ncand; ++b) S.n_new[S.cand_final[b]] += 1;
+    if (tid == 32) {
+      for (int b = 0; b < ncand; ++b)
+        if (S.cand_g[b] == c.rank)
+          c.table_cur[pkt_i32(c, c.rank, c.pkt.off_cand_row)[S.cand_j[b]]] = S.cand_final[b];
+    }
+    if (tid >= 64 && tid < 64 + V) {
+      const int v = tid - 64;
+      for (int b = 0; b < ncand; ++b) {
+        const float* x = pkt_f32(c, S.cand_g[b], c.pkt.off_cand_x) + (size_t)S.cand_j[b] * c.Dsum + c.doff[v];
+        double q = 0.0;
+        for (int dd = 0; dd < c.D[v]; ++dd) q += (double)x[dd] * (double)x[dd];
+        c.S2t[v * cap + S.cand_final[b]] += q;
+      }
+    }
+    for (int e = tid; e < c.Dsum; e += kFinThreads) {
+      int v = 0;
+      while (v + 1 < V && e >= c.doff[v + 1]) ++v;
+      const int dd = e - c.doff[v];
+      for (int b = 0; b < ncand; ++b) {
+        const float xv = pkt_f32(c, S.cand_g[b], c.pkt.off_cand_x)[(size_t)S.cand_j[b] * c.Dsum + e];
+        c.S1t[(size_t)cap * c.doff[v] + (size_t)S.cand_final[b] * c.D[v] + dd] += (double)xv;
+      }
+    }
+    __syncthreads();
+  }
+
+  // ---- C. deaths and per-dish statistics -------------------------------------------------------
+  for (int i = tid; i < V * cap; i += kFinThreads) {
+    const int v = i / cap, t = i - v * cap;
+    if (S.n_new[t] == 0) S.dish[v][t] = -1;                  // multiview_utils.cpp:168-191
+    else if (S.dish[v][t] < 0 || S.dish[v][t] >= cap) { S.err |= 2; S.dish[v][t] = 0; }
+  }
+  __syncthreads();
+  for (int i = tid; i < V * cap; i += kFinThreads) {
+    const int v = i / cap, k = i - v * cap;
+    int l = 0, n = 0;
+    double s2 = 0.0;
+    for (int t = 0; t < cap; ++t)
+      if (S.dish[v][t] == k) { l += 1; n += S.n_new[t]; s2 += c.S2t[v * cap + t]; }
+    S.l_live[v][k] = l;
+    S.n_vk[v][k] = n;
+    c.S2k[i] = s2;
+    c.l_vk[i] = l;
+    c.n_vk[i] = n;
+    c.dish_of[i] = S.dish[v][k];                             // (index reuse: i = v*cap + slot)
+  }
+  for (int t = tid; t < cap; t += kFinThreads) c.n_t[t] = S.n_new[t];
+  for (int i = tid; i < cap * c.Dsum; i += kFinThreads) {
+    int v = 0;
+    while (v + 1 < V && i >= cap * c.doff[v + 1]) ++v;
+    const int D = c.D[v];
+    const int local = i - cap * c.doff[v];
+    const int k = local / D, dd = local - k * D;
+    double sum = 0.0;
+    for (int t = 0; t < cap; ++t)
+      if (S.dish[v][t] == k) sum += c.S1t[(size_t)cap * c.doff[v] + (size_t)t * D + dd];
+    c.S1k[i] = sum;
+  }
+  __syncthreads();
+  for (int i = tid; i < V * cap; i += kFinThreads) {
+    const int v = i / cap, k = i - v * cap;
+    const int D = c.D[v];
+    const double* S1 = c.S1k + (size_t)cap * c.doff[v] + (size_t)k * D;
+    double q = 0.0;
+    for (int dd = 0; dd < D; ++dd) q += S1[dd] * S1[dd];
+    S.s1sq[v][k] = q;
+  }
+  __syncthreads();
+
+  // ---- reference initialisation of the hyperparameters (multiview_gibbs.cpp:75-98) ------------
+  if (flags & kFinTauInit) {
+    if (tid < V) {
+      const int v = tid;
+      // all customers sit at table 0 / dish 0 during this call: pooled variance over coordinates
+      const double n = (double)c.n_global;
+      double var = 1.0;
+      if (c.n_global > 1) var = (c.S2k[v * cap] - S.s1sq[v][0] / n) / ((n - 1.0) * (double)c.D[v]);
+      if (!(var > 0.0)) var = 1.0;
+      tau_v[v] = var * 0.25 * 0.01;
+      alpha_v[v] = 1.0;
+      sigma_v[v] = 0.5;
+    }
+    if (tid == 0) { alpha_g = 1.0; sigma_g = 0.6; }
+    __syncthreads();
+  }
+
+  // ---- D. hyperparameter step (multiview_hyper.cpp:233-292) -------------------------------------
+  if (flags & kFinHyper) {
+    if (tid == 0) {                                           // update_tau_v_MH, :211-231
+      for (int v = 0; v < V; ++v) {
+        double tau_old = tau_v[v];
+        if (tau_old <= 0.0) tau_old = kEps;
+        const double log_old = log_posterior_tau(c, S, v, tau_old);
+        const double tau_prop = exp(log(tau_old) + 0.0 + 0.3 * dev_normal(c, sweep, v));   // :166-174
+        const double log_new = log_posterior_tau(c, S, v, tau_prop);
+        const double log_acc = (log_new - log_old) + (log(tau_prop) - log(tau_old));
+        if (log(dev_unif(c, sweep, v)) < log_acc) tau_v[v] = tau_prop;
+      }
+    }
+    __syncthreads();
+    for (int v = 0; v < V; ++v) {
+      long long total = 0;
+      for (int k = 0; k < cap; ++k) total += S.l_live[v][k];
+      double lp[2];
+      // alpha_v: log-normal random walk, :242-255
+      double a_old = alpha_v[v];
+      if (a_old <= 0.0) a_old = kEps;
+      if (tid == 0) {
+        const double cand = exp(log(a_old > kEps ? a_old : kEps) + 0.0 + 0.1 * dev_normal(c, sweep, V + 2 * v));
+        S.prop[0] = cand > kEps ? cand : kEps;
+      }
+      __syncthreads();
+      const double a_prop = S.prop[0];
+      eppf_pair(S, S.l_live[v], cap, total, a_old, sigma_v[v], a_prop, sigma_v[v], lp);
+      if (tid == 0) {
+        const double lo = lp[0] + log_prior_alpha(a_old), ln = lp[1] + log_prior_alpha(a_prop);
+        const double log_acc = (ln - lo) + (log(a_prop) - log(a_old));
+        if (log(dev_unif(c, sweep, V + 2 * v)) < log_acc) alpha_v[v] = a_prop;
+        S.prop[1] = reflect_unit(sigma_v[v] + 0.0 + 0.05 * dev_normal(c, sweep, V + 2 * v + 1));   // :124-128
+      }
+      __syncthreads();
+      // sigma_v: reflected random walk, :257-265
+      const double s_old = sigma_v[v], s_prop = S.prop[1], a_cur = alpha_v[v];
+      eppf_pair(S, S.l_live[v], cap, total, a_cur, s_old, a_cur, s_prop, lp);
+      if (tid == 0) {
+        const double lpo = (s_old <= kEps || s_old >= 1.0 - kEps) ? -INFINITY : lp[0] + log_prior_sigma(s_old);
+        const double lpn = (s_prop <= kEps || s_prop >= 1.0 - kEps) ? -INFINITY : lp[1] + log_prior_sigma(s_prop);
+        if (log(dev_unif(c, sweep, V + 2 * v + 1)) < lpn - lpo) sigma_v[v] = s_prop;
+      }
+      __syncthreads();
+    }
+    {                                                          // global level, :268-291
+      double lp[2];
+      double a_old = alpha_g;
+      if (a_old <= 0.0) a_old = kEps;
+      if (tid == 0) {
+        const double cand = exp(log(a_old > kEps ? a_old : kEps) + 0.0 + 0.1 * dev_normal(c, sweep, 3 * V));
+        S.prop[0] = cand > kEps ? cand : kEps;
+      }
+      __syncthreads();
+      const double a_prop = S.prop[0];
+      eppf_pair(S, S.n_new, cap, (long long)c.n_global, a_old, sigma_g, a_prop, sigma_g, lp);
+      if (tid == 0) {
+        const double lo = lp[0] + log_prior_alpha(a_old), ln = lp[1] + log_prior_alpha(a_prop);
+        const double log_acc = (ln - lo) + (log(a_prop) - log(a_old));
+        if (log(dev_unif(c, sweep, 3 * V)) < log_acc) alpha_g = a_prop;
+        S.prop[1] = reflect_unit(sigma_g + 0.0 + 0.05 * dev_normal(c, sweep, 3 * V + 1));
+      }
+      __syncthreads();
+      const double s_old = sigma_g, s_prop = S.prop[1], a_cur = alpha_g;
+      eppf_pair(S, S.n_new, cap, (long long)c.n_global, a_cur, s_old, a_cur, s_prop, lp);
+      if (tid == 0) {
+        const double lpo = (s_old <= kEps || s_old >= 1.0 - kEps) ? -INFINITY : lp[0] + log_prior_sigma(s_old);
+        const double lpn = (s_prop <= kEps || s_prop >= 1.0 - kEps) ? -INFINITY : lp[1] + log_prior_sigma(s_prop);
+        if (log(dev_unif(c, sweep, 3 * V + 1)) < lpn - lpo) sigma_g = s_prop;
+      }
+      __syncthreads();
+    }
+  }
+  for (int i = tid; i < 3 * V + 2; i += kFinThreads) c.hyp[i] = S.hyp[i];
+
+  // ---- E. FP32 parameter block of the next sweep (oracle/mv_oracle.c:mvo_make_params) ----------
+  for (int i = tid; i < V * cap; i += kFinThreads) {
+    const int v = i / cap, t = i - v * cap;
+    const int D = c.D[v];
+    const int k = S.dish[v][t];
+    float* mt = c.mean + (size_t)cap * c.doff[v] + (size_t)t * D;
+    float* mh = c.mean_hi ? c.mean_hi + (size_t)cap * c.doff[v] + (size_t)t * D : nullptr;
+    float* ml = c.mean_lo ? c.mean_lo + (size_t)cap * c.doff[v] + (size_t)t * D : nullptr;
+    TableParam q;
+    if (k < 0) {
+      q.A = 0.f; q.C = kMasked; q.A1 = 0.f; q.C1 = kMasked; q.W = kMasked; q.W1 = kMasked; q.dish = -1; q.lone = 0;
+      for (int dd = 0; dd < D; ++dd) { mt[dd] = 0.f; if (mh) { mh[dd] = 0.f; ml[dd] = 0.f; } }
+    } else {
+      const double tau = tau_v[v], n = (double)S.n_vk[v][k];
+      const double* S1 = c.S1k + (size_t)cap * c.doff[v] + (size_t)k * D;
+      double mm = 0.0;
+      for (int dd = 0; dd < D; ++dd) {
+        const float m = (float)(S1[dd] / (tau + n));
+        mt[dd] = m;
+        if (mh) {
+          const float hi = __uint_as_float(__float_as_uint(m) & 0xFFFFE000u);   // TF32-exact part
+          mh[dd] = hi;
+          ml[dd] = __fadd_rn(m, -hi);
+        }
+        mm += (double)m * (double)m;
+      }
+      const double a = (tau + n) / (2.0 * tau * (tau + n + 1.0));
+      const double cc = -0.5 * log(2.0 * kPi * tau * (tau + n + 1.0) / (tau + n));
+      q.A = (float)(kLog2e * a);
+      q.C = (float)(kLog2e * ((double)D * cc - a * mm));
+      if (n >= 2.0) {
+        const double a1 = (tau + n) / (2.0 * tau * (tau + n - 1.0));
+        const double c1 = -0.5 * log(2.0 * kPi * tau * (tau + n) / (tau + n - 1.0));
+        q.A1 = (float)(kLog2e * a1);
+        q.C1 = (float)(kLog2e * ((double)D * c1 - a1 * mm));
+      } else {
+        q.A1 = 0.f; q.C1 = kMasked;
+      }
+      bool rep = true;
+      for (int t2 = 0; t2 < t; ++t2) if (S.dish[v][t2] == k) { rep = false; break; }
+      const double w = (double)S.l_live[v][k] - sigma_v[v], w1 = w - 1.0;
+      q.W = (rep && w > 0.0) ? (float)log2(w) : kMasked;
+      q.W1 = (rep && w1 > 0.0) ? (float)log2(w1) : kMasked;
+      q.dish = k;
+      q.lone = (S.l_live[v][k] == 1);
+    }
+    c.tparam[i] = q;
+  }
+  if (tid < V) {
+    const int v = tid;
+    const double tau = tau_v[v];
+    int K_act = 0;
+    long long sum_l = 0;
+    for (int k = 0; k < cap; ++k) if (S.l_live[v][k] > 0) { K_act++; sum_l += S.l_live[v][k]; }
+    ViewParam p;
+    p.AN = (float)(kLog2e / (2.0 * tau));
+    p.CN = (float)(kLog2e * (-0.5 * (double)c.D[v] * log(2.0 * kPi * tau)));
+    const double wn0 = alpha_v[v] + (double)K_act * sigma_v[v], wn1 = alpha_v[v] + (double)(K_act - 1) * sigma_v[v];
+    p.WN0 = wn0 > 0.0 ? (float)log2(wn0) : kMasked;
+    p.WN1 = wn1 > 0.0 ? (float)log2(wn1) : kMasked;
+    const double d0 = alpha_v[v] + (double)sum_l, d1 = alpha_v[v] + (double)(sum_l - 1);
+    p.LD0 = d0 > 0.0 ? (float)log2(d0) : 0.f;
+    p.LD1 = d1 > 0.0 ? (float)log2(d1) : 0.f;
+    p.pad0 = p.pad1 = 0.f;
+    c.vparam[v] = p;
+  }
+  for (int t = tid; t < cap; t += kFinThreads) {
+    const double mass = (double)S.n_new[t] - sigma_g, mass1 = mass - 1.0;
+    TableMass tm;
+    tm.LM = (S.n_new[t] > 0 && mass > 0.0) ? (float)log2(mass) : kMasked;
+    tm.LM1 = (S.n_new[t] > 1 && mass1 > 0.0) ? (float)log2(mass1) : kMasked;
+    tm.single = (S.n_new[t] == 1);
+    tm.pad = 0;
+    c.tmass[t] = tm;
+  }
+  if (tid == 0) {
+    int T_ne = 0;
+    for (int t = 0; t < cap; ++t) T_ne += S.n_new[t] > 0;
+    const int F = cap - T_ne;
+    const double mn0 = alpha_g + sigma_g * (double)T_ne, mn1 = alpha_g + sigma_g * (double)(T_ne - 1);
+    GlobalParam g;
+    g.LMN0 = (F > 0 && mn0 > 0.0) ? (float)log2(mn0) : kMasked;
+    g.LMN1 = (F > 0 && mn1 > 0.0) ? (float)log2(mn1) : kMasked;
+    g.nfree = F;
+    const uint32_t next = sweep + ((flags & kFinAdvance) ? 1u : 0u);
+    g.sweep = next;
+    *c.gparam = g;
+    *c.sweep = next;
+    if (S.err) atomicOr(c.status, S.err);
+  }
+}
+
+cudaError_t launch_finalize(const Ctx& c, int32_t flags, cudaStream_t s) {
+  if (c.cap > kMaxCap || c.world > kMaxWorld || c.V > kMaxViews) return cudaErrorInvalidValue;
+  const int smem = (int)sizeof(FinShared);
+  cudaError_t e = cudaFuncSetAttribute(k_finalize, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+  if (e != cudaSuccess) return e;
+  k_finalize<<<1, kFinThreads, smem, s>>>(c, flags);
+  return cudaGetLastError();
+}
+
+// =============================================================================================
+// initial assignments (multiview_gibbs.cpp:12-62) and small utilities
+// =============================================================================================
+// mode 0: every row to table 0 / dish 0 (used to obtain the pooled variance for tau_v)
+// mode 1: the reference's random start: T = 4 tables, K = 2 dishes per view
+__global__ void k_init_tables(const Ctx c, const int32_t mode) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < c.n_rows) {
+    int t = 0;
+    if (mode == 1) {
+      const U4 r = stream_block(c.seed, c.chain, kDomInitTable, 0, 0, (uint64_t)(c.row_offset + i));
+      t = (int)floor(uniform_f64_from(r.x, r.y) * 4.0);
+      t = t < 0 ? 0 : (t > 3 ? 3 : t);
+    }
+    c.choice[i] = t;
+  }
+  if (i < c.n_chunks) c.birthmask[i] = 0u;
+  if (i < c.V * c.cap) {
+    const int v = i / c.cap, t = i - v * c.cap;
+    int k = -1;
+    if (mode == 0) k = (t == 0) ? 0 : -1;
+    else if (t < 4) {
+      const U4 r = stream_block(c.seed, c.chain, kDomInitDish, (uint32_t)v, 0, (uint64_t)t);
+      k = (int)floor(uniform_f64_from(r.x, r.y) * 2.0);
+      k = k < 0 ? 0 : (k > 1 ? 1 : k);
+    }
+    c.dish_of[i] = k;
+    c.l_vk[i] = 0;
+    c.n_vk[i] = 0;
+  }
+  if (i < c.cap) c.n_t[i] = 0;
+  if (i == 0) {
+    c.gparam->nfree = 0;
+    int32_t* hdr = reinterpret_cast<int32_t*>(c.packet + (size_t)c.rank * c.pkt.bytes + c.pkt.off_hdr);
+    hdr[0] = 0; hdr[1] = 0; hdr[2] = c.rank; hdr[3] = 0;
+    *reinterpret_cast<int64_t*>(hdr + 4) = c.row_offset;
+    hdr[6] = 0; hdr[7] = 0;
+  }
+}
+
+cudaError_t launch_init_tables(const Ctx& c, int32_t mode, cudaStream_t s) {
+  int n = c.n_rows;
+  if (c.V * c.cap > n) n = c.V * c.cap;
+  if (c.n_chunks > n) n = c.n_chunks;
+  k_init_tables<<<(n + 255) / 256, 256, 0, s>>>(c, mode);
+  return cudaGetLastError();
+}
+
+__global__ void k_f64_to_f32(const double* __restrict__ src, float* __restrict__ dst, int64_t n) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) dst[i] = (float)src[i];
+}
+cudaError_t launch_f64_to_f32(const double* src, float* dst, int64_t n, cudaStream_t s) {
+  if (n <= 0) return cudaSuccess;
+  k_f64_to_f32<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(src, dst, n);
+  return cudaGetLastError();
+}
+
+}  // namespace mv

@@ -27,8 +27,8 @@ void mvo_philox_block(uint64_t seed, uint32_t chain, uint32_t domain, uint32_t s
                       uint64_t index, uint32_t out[4]) {
   mvo_stream_block(seed, chain, domain, slot, sweep, index, out);
 }
-float mvo_u24(uint64_t seed, uint32_t chain, uint32_t domain, uint32_t slot, uint32_t sweep, uint64_t index) {
-  return mvo_uniform24(seed, chain, domain, slot, sweep, index);
+float mvo_uf(uint64_t seed, uint32_t chain, uint32_t domain, uint32_t slot, uint32_t sweep, uint64_t index) {
+  return mvo_uniform_f32(seed, chain, domain, slot, sweep, index);
 }
 double mvo_u53(uint64_t seed, uint32_t chain, uint32_t domain, uint32_t slot, uint32_t sweep, uint64_t index) {
   return mvo_uniform53(seed, chain, domain, slot, sweep, index);
@@ -264,7 +264,7 @@ int mvo_draw_rows(const mvo_state* s, int32_t* choice, int threads) {
 #endif
     for (int i = 0; i < s->n; ++i) {
       mvo_row_logweights(s, i, lw, NULL);
-      double u = (double)mvo_uniform24(s->seed, s->chain, MVO_DOM_TABLE, 0, s->sweep,
+      double u = (double)mvo_uniform_f32(s->seed, s->chain, MVO_DOM_TABLE, 0, s->sweep,
                                        (uint64_t)(s->row_offset + i));
       choice[i] = mvo_draw_from_logweights(s, i, lw, u);
     }
@@ -583,7 +583,7 @@ void mvo_stageA_f32(const float* x, int D, const float* m, int cap, float* acc, 
   }
 }
 
-int mvo_stageB_f32(const mvo_params_f32* p, const float* acc, const float* xx, int t0, float u24,
+int mvo_stageB_f32(const mvo_params_f32* p, const float* acc, const float* xx, int t0, float uf,
                    float* lw_out) {
   const int V = p->V, cap = p->cap;
   float* lw = (float*)malloc(sizeof(float) * (size_t)cap);
@@ -621,7 +621,7 @@ int mvo_stageB_f32(const mvo_params_f32* p, const float* acc, const float* xx, i
   } else {
     float total = mvo_exp2m(lnew - M);
     for (int t = 0; t < cap; ++t) { term[t] = mvo_exp2m(lw[t] - M); total = total + term[t]; }
-    float target = u24 * total;
+    float target = uf * total;
     float cum = 0.0f;
     int found = 0;
     for (int t = 0; t < cap; ++t) {

@@ -64,7 +64,7 @@ typedef struct mvo_state {
 void mvo_philox_block(uint64_t seed, uint32_t chain, uint32_t domain, uint32_t slot, uint32_t sweep,
                       uint64_t index, uint32_t out[4]);
 void mvo_philox_raw(const uint32_t ctr[4], const uint32_t key[2], uint32_t out[4]);
-float mvo_u24(uint64_t seed, uint32_t chain, uint32_t domain, uint32_t slot, uint32_t sweep, uint64_t index);
+float mvo_uf(uint64_t seed, uint32_t chain, uint32_t domain, uint32_t slot, uint32_t sweep, uint64_t index);
 double mvo_u53(uint64_t seed, uint32_t chain, uint32_t domain, uint32_t slot, uint32_t sweep, uint64_t index);
 double mvo_z(uint64_t seed, uint32_t chain, uint32_t domain, uint32_t slot, uint32_t sweep, uint64_t index);
 
@@ -131,8 +131,8 @@ int mvo_make_params(const mvo_state* s, int32_t* dish, float* A, float* C, float
  * xx = sum_d x[d]^2 likewise.  acc has cap entries. */
 void mvo_stageA_f32(const float* x, int D, const float* m, int cap, float* acc, float* xx);
 /* Stage B: from per-view dot products acc[v][t] (V*cap) and squared norms xx[v] of ONE row, its
- * current table t0 and uniform u24, reproduce the device's choice bit for bit. */
-int mvo_stageB_f32(const mvo_params_f32* p, const float* acc, const float* xx, int t0, float u24,
+ * current table t0 and uniform uf, reproduce the device's choice bit for bit. */
+int mvo_stageB_f32(const mvo_params_f32* p, const float* acc, const float* xx, int t0, float uf,
                    float* lw_out /* cap+1 or NULL */);
 float mvo_exp2m(float d);
 float mvo_log2m(float s);

@@ -22,8 +22,8 @@
  *   domain 6  call-ordered stream (index = call number) backing R::runif/R::rnorm when
  *             the compiled reference is driven from ref_shim.cpp
  *
- *   u24 = ((x0 >> 8) + 0.5) * 2^-24          float  in (0,1), exact in FP32
- *   u53 = (((x0 >> 5) << 26 | (x1 >> 6)) + 0.5) * 2^-53   double in (0,1)
+ *   uf  = ((x0 >> 9) + 0.5) * 2^-23          float  in (0,1); k + 0.5 is exact in FP32 for k < 2^23
+ *   u53 = ((x0 >> 5) * 2^26 + (x1 >> 6) + 0.5) * 2^-53     double in (0,1) (rounded once)
  *   z   = sqrt(-2 ln u53(x0,x1)) * cos(2 pi u53(x2,x3))    standard normal (Box-Muller)
  */
 #ifndef MV_PHILOX_REF_H
@@ -66,8 +66,8 @@ static inline void mvo_stream_block(uint64_t seed, uint32_t chain, uint32_t doma
   mvo_philox4x32_10(ctr, key, out);
 }
 
-static inline float mvo_u24_from(uint32_t x0) {
-  return ((float)(x0 >> 8) + 0.5f) * 5.9604644775390625e-08f; /* 2^-24; (k+0.5) is exact for k < 2^24 */
+static inline float mvo_uf_from(uint32_t x0) {
+  return ((float)(x0 >> 9) + 0.5f) * 1.1920928955078125e-07f; /* 2^-23; every step is exact */
 }
 
 static inline double mvo_u53_from(uint32_t a, uint32_t b) {
@@ -75,11 +75,11 @@ static inline double mvo_u53_from(uint32_t a, uint32_t b) {
   return ((double)k + 0.5) * 1.1102230246251565e-16; /* 2^-53 */
 }
 
-static inline float mvo_uniform24(uint64_t seed, uint32_t chain, uint32_t domain, uint32_t slot,
+static inline float mvo_uniform_f32(uint64_t seed, uint32_t chain, uint32_t domain, uint32_t slot,
                                   uint32_t sweep, uint64_t index) {
   uint32_t x[4];
   mvo_stream_block(seed, chain, domain, slot, sweep, index, x);
-  return mvo_u24_from(x[0]);
+  return mvo_uf_from(x[0]);
 }
 
 static inline double mvo_uniform53(uint64_t seed, uint32_t chain, uint32_t domain, uint32_t slot,

@@ -73,12 +73,12 @@ def lib():
         if not path.exists():
             build()
         L = C.CDLL(str(path))
-        L.mvo_u24.restype = C.c_float
-        L.mvo_u24.argtypes = [C.c_uint64, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint64]
+        L.mvo_uf.restype = C.c_float
+        L.mvo_uf.argtypes = [C.c_uint64, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint64]
         L.mvo_u53.restype = C.c_double
-        L.mvo_u53.argtypes = L.mvo_u24.argtypes
+        L.mvo_u53.argtypes = L.mvo_uf.argtypes
         L.mvo_z.restype = C.c_double
-        L.mvo_z.argtypes = L.mvo_u24.argtypes
+        L.mvo_z.argtypes = L.mvo_uf.argtypes
         L.mvo_philox_raw.argtypes = [C.POINTER(C.c_uint32)] * 3
         L.mvo_log_f_vk.restype = C.c_double
         L.mvo_log_f_vk.argtypes = [C.POINTER(_MvoState), C.c_int, C.c_int, _f32p, C.c_int]
@@ -304,11 +304,11 @@ def stageA_f32(x_row, m):
     return acc, np.float32(xx.value)
 
 
-def stageB_f32(pstruct, acc, xx, t0, u24, want_lw=False):
+def stageB_f32(pstruct, acc, xx, t0, uf, want_lw=False):
     acc = np.ascontiguousarray(acc, np.float32)
     xx = np.ascontiguousarray(xx, np.float32)
     lw = np.empty(pstruct.cap + 1, np.float32) if want_lw else None
-    ch = lib().mvo_stageB_f32(C.byref(pstruct), _ptr(acc, _f32p), _ptr(xx, _f32p), int(t0), C.c_float(float(u24)),
+    ch = lib().mvo_stageB_f32(C.byref(pstruct), _ptr(acc, _f32p), _ptr(xx, _f32p), int(t0), C.c_float(float(uf)),
                               _ptr(lw, _f32p) if want_lw else None)
     return (ch, lw) if want_lw else ch
 
@@ -329,7 +329,7 @@ def mirror_draw_rows(state: OracleState, P=None, acc=None, xx=None):
                 a[v], q[v] = stageA_f32(state.views[v][i], P["m"][v])
         else:
             a, q = acc[i], xx[i]
-        u = L.mvo_u24(state.c.seed, state.c.chain, 0, 0, state.c.sweep, state.c.row_offset + i)
+        u = L.mvo_uf(state.c.seed, state.c.chain, 0, 0, state.c.sweep, state.c.row_offset + i)
         out[i] = stageB_f32(ps, a, q, state.table_of[i], u)
     return out
 

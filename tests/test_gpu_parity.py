@@ -1,0 +1,200 @@
+"""GPU parity tests (run with -m gpu on the B200 box).  Everything goes through the C ABI
+(libmvg_b200.so via ctypes); the CPU oracle is the checker:
+
+  * the FP32 parameter block equals the oracle's (computed independently in FP64 then rounded);
+  * stage A (dot products) — CUDA-core engine: bit-exact against the fmaf-chain restatement;
+    log-likelihoods within 1e-5 relative of the FP64 restatement (the tolerance north_star states);
+  * stage B (draw): integer choices bit-exact against oracle/mv_oracle.c:mvo_stageB_f32 fed the
+    device's own dot products and the same Philox uniforms;
+  * births / deaths / counts (table_of, n_t, dish_of, n_vk, l_vk): bit-exact against mvo_reseat;
+  * float statistics within 1e-5 relative; hyperparameters against mvo_hyper_step.
+"""
+import numpy as np
+import pytest
+from conftest import c1_data, make_mixture
+
+pytestmark = pytest.mark.gpu
+RTOL_LOGLIK = 1e-5     # north_star: "<= 1e-5 FP32"
+RTOL_STATS = 1e-5
+
+
+def _mk_sampler(views, cap, seed, engine=1, debug=True, **kw):
+    import mvc_b200
+    s = mvc_b200.Sampler(views[0].shape[0], [v.reshape(len(v), -1).shape[1] for v in views], cap=cap, seed=seed,
+                         engine=engine, debug_export=debug, **kw)
+    for v, x in enumerate(views):
+        s.upload_view(v, x)
+    return s
+
+
+def _oracle_from_device(po, views, cap, seed, st, n_global=None, row_offset=0):
+    o = po.OracleState(views, cap, seed=seed, row_offset=row_offset, n_global=n_global)
+    o.alpha_v[:] = st["alpha_v"]; o.sigma_v[:] = st["sigma_v"]; o.tau_v[:] = st["tau_v"]
+    o.alpha_g, o.sigma_g = st["alpha_g"], st["sigma_g"]
+    o.sweep = st["sweep"]
+    o.set_assignment(st["table_of"], st["dish_of"])
+    return o
+
+
+def _check_params(po, o, P):
+    Q = o.make_params()
+    for k in ("dish", "lone", "single"):
+        np.testing.assert_array_equal(P[k], Q[k], err_msg=k)
+    for k in ("A", "C", "A1", "C1", "W", "W1", "AN", "CN", "WN", "LD", "LM", "LM1", "LMN"):
+        a, b = P[k].astype(np.float64), Q[k].astype(np.float64)
+        masked = b < -1e29
+        np.testing.assert_array_equal(a[masked] < -1e29, True, err_msg=k)
+        np.testing.assert_allclose(a[~masked], b[~masked], rtol=2e-5, atol=1e-6, err_msg=k)
+    for v in range(o.V):
+        np.testing.assert_allclose(P["m"][v], Q["m"][v], rtol=2e-5, atol=1e-6)
+
+
+def _one_sweep_parity(po, s, views, cap, seed, do_hyper, simt_bit_exact=True):
+    """Compare ONE device sweep with the oracle started from the device's own pre-sweep state."""
+    pre = s.get_state()
+    P = s.get_params()
+    o = _oracle_from_device(po, views, cap, seed, pre)
+    _check_params(po, o, P)
+    s.sweep(1, do_hyper=do_hyper)
+    acc, xx, raw = s.get_debug_rows()
+    n = o.n
+    # ---- stage A
+    ps = po.params_struct(P)
+    L = po.lib()
+    worst = 0.0
+    for i in range(n):
+        if simt_bit_exact:
+            for v in range(o.V):
+                a, q = po.stageA_f32(o.views[v][i], P["m"][v])
+                assert np.array_equal(a, acc[i, v]) and q == xx[i, v], (i, v)
+        u = L.mvo_uf(seed, 0, 0, 0, pre["sweep"], i)
+        ch, lw32 = po.stageB_f32(ps, acc[i], xx[i], pre["table_of"][i], u, want_lw=True)
+        assert ch == raw[i], (i, ch, raw[i])                    # integer draw: bit-exact
+        if i % 7 == 0:
+            lw64 = o.row_logweights(i) / np.log(2.0)
+            ok = np.isfinite(lw64)
+            assert np.all(lw32[~ok] < -1e29)
+            worst = max(worst, float(np.max(np.abs(lw32[ok] - lw64[ok]) / np.maximum(1.0, np.abs(lw64[ok])))))
+    assert worst < RTOL_LOGLIK, worst
+    # FP64 restatement draws agree except at CDF edges
+    agree = float((o.draw_rows(threads=4) == raw).mean())
+    assert agree > 0.99, agree
+    # ---- births / deaths / counts from the device's raw draws
+    ns, rows, w = o.reseat(raw, want_births=True)
+    post = s.get_state()
+    np.testing.assert_array_equal(post["table_of"], o.table_of)
+    np.testing.assert_array_equal(post["n_t"], o.n_t)
+    np.testing.assert_array_equal(post["dish_of"], o.dish_of)
+    np.testing.assert_array_equal(post["n_vk"], o.n_vk)
+    np.testing.assert_array_equal(post["l_vk"], o.l_vk)
+    dns, drows, dw = s.get_debug_births()
+    assert dns == ns and list(drows) == list(rows)
+    if ns:
+        np.testing.assert_allclose(dw, w, rtol=1e-9, atol=1e-12)
+    for v in range(o.V):
+        np.testing.assert_allclose(post["S1"][v], o.S1[v], rtol=RTOL_STATS, atol=1e-4)
+    np.testing.assert_allclose(post["sum_y2"], o.S2, rtol=RTOL_STATS, atol=1e-4)
+    assert post["sweep"] == pre["sweep"] + 1
+    # ---- hyper step: feed the oracle the device's statistics so both see identical inputs
+    if do_hyper:
+        for v in range(o.V):
+            o.S1[v][:] = post["S1"][v]
+        o.S2[:] = post["sum_y2"]
+        o.hyper_step(use_lgamma=True)
+        np.testing.assert_allclose(post["alpha_v"], o.alpha_v, rtol=1e-9)
+        np.testing.assert_allclose(post["sigma_v"], o.sigma_v, rtol=1e-9)
+        np.testing.assert_allclose(post["tau_v"], o.tau_v, rtol=1e-9)
+        np.testing.assert_allclose([post["alpha_g"], post["sigma_g"]], [o.alpha_g, o.sigma_g], rtol=1e-9)
+    else:
+        np.testing.assert_array_equal(post["tau_v"], pre["tau_v"])
+    return ns
+
+
+def test_scalar_views_config1_parity(oracle):
+    """Config 1 shape: two scalar views (D = 1), reference init, 12 sweeps with births and deaths."""
+    views, _ = c1_data(500)
+    s = _mk_sampler(views, 32, seed=1999)
+    s.init_state_reference()
+    st = s.get_state()
+    o = oracle.OracleState(views, 32, seed=1999)
+    o.init_reference()
+    np.testing.assert_array_equal(st["table_of"], o.table_of)        # same Philox init
+    np.testing.assert_array_equal(st["dish_of"], o.dish_of)
+    np.testing.assert_allclose(st["tau_v"], o.tau_v, rtol=1e-5)
+    births = 0
+    for it in range(12):
+        births += _one_sweep_parity(oracle, s, views, 32, 1999, do_hyper=True)
+    assert births > 0                                                # the run exercised the birth path
+    s.close()
+
+
+@pytest.mark.parametrize("dims,cap,n", [([8, 8, 8], 32, 700), ([64, 64, 64], 64, 900), ([5, 12], 64, 333), ([3], 32, 65)])
+def test_dense_views_parity(oracle, dims, cap, n):
+    views, z = make_mixture(n, dims, 6, seed=21)
+    s = _mk_sampler(views, cap, seed=77)
+    rng = np.random.default_rng(1)
+    tab = np.where(rng.random(n) < 0.15, rng.integers(0, 6, n), z).astype(np.int32)
+    tab[:3] = [7, 8, 9]                                              # three customers alone at their tables
+    dish = np.full((len(dims), cap), -1, np.int32)
+    for t in range(10):
+        dish[:, t] = rng.integers(0, 5, len(dims))
+    V = len(dims)
+    s.set_state(tab, dish, np.full(V, 1.0), np.full(V, 0.5), np.full(V, 0.9), 1.0, 0.6, sweep=5)
+    for it in range(6):
+        _one_sweep_parity(oracle, s, views, cap, 77, do_hyper=(it % 2 == 0))
+    s.close()
+
+
+def test_full_capacity_masks_new_table(oracle):
+    """All cap slots occupied: no birth may happen (capacity rule) and nothing is lost."""
+    n, cap = 640, 32
+    views, z = make_mixture(n, [4, 4], 32, seed=3)
+    s = _mk_sampler(views, cap, seed=5)
+    tab = (np.arange(n) % cap).astype(np.int32)
+    dish = np.tile(np.arange(cap, dtype=np.int32), (2, 1))
+    s.set_state(tab, dish, [1.0, 1.0], [0.5, 0.5], [1.0, 1.0], 5.0, 0.9)
+    for _ in range(4):
+        _one_sweep_parity(oracle, s, views, cap, 5, do_hyper=False)
+        _, _, raw = s.get_debug_rows()
+        assert (raw >= 0).all()
+    assert s.get_state()["n_t"].sum() == n
+    s.close()
+
+
+def test_error_codes_and_ordering():
+    import mvc_b200
+    s = mvc_b200.Sampler(64, [2, 2], cap=32)
+    with pytest.raises(mvc_b200.MvgError) as e:
+        s.sweep(1)
+    assert e.value.code == -4                                        # MVG_ESTATE: no state yet
+    s.upload_view(0, np.zeros((64, 2), np.float32))
+    with pytest.raises(mvc_b200.MvgError) as e:
+        s.init_state_reference()
+    assert e.value.code == -4 and "view 1" in str(e.value)           # second view missing
+    s.upload_view(1, np.zeros((64, 2), np.float32))
+    with pytest.raises(mvc_b200.MvgError) as e:
+        s.set_state(np.full(64, 40), np.zeros((2, 32)), [1, 1], [.5, .5], [1, 1], 1, .6)
+    assert e.value.code == -1                                        # MVG_EINVAL: table outside [0,cap)
+    s.close()
+
+
+def test_run_gibbs_posterior_summaries_match_reference(oracle):
+    """north_star's third bullet: posterior summaries of a long GPU chain (synchronous sweeps)
+    against the sequential reference chain on config-1 data: ARI vs truth, kernel variance, cluster count."""
+    from sklearn.metrics import adjusted_rand_score as ari
+    import mvc_b200
+    views, truth = c1_data(500)
+    res = mvc_b200.run_gibbs([v.astype(np.float64) for v in views], M=1500, burn_in=1200, thin=10, cap=32, seed=1999,
+                             engine=1)
+    assert len(res["table_of"]) == 30 and len(res["alpha_v"]) == 2 and res["loglik"] == []
+    aris = np.array([[ari(truth[v], np.asarray(res["dish_of"][s][v])[res["table_of"][s]]) for v in range(2)]
+                     for s in range(30)])
+    tau = np.array([res["tau_v"][v].mean() for v in range(2)])
+    assert aris[:, 0].mean() > 0.85 and aris[:, 1].mean() > 0.75, aris.mean(0)
+    if oracle.have_ref():
+        y = np.stack([v.astype(np.float64) for v in views])
+        tr = oracle.ref_run_gibbs(y, 1500, 1200, 10, seed=1999)
+        ref_ari = np.array([[ari(truth[v], t["dish_of"][v][t["table_of"]]) for v in range(2)] for t in tr])
+        ref_tau = np.array([[t["tau_v"][v] for v in range(2)] for t in tr]).mean(0)
+        assert np.all(np.abs(aris.mean(0) - ref_ari.mean(0)) < 0.12), (aris.mean(0), ref_ari.mean(0))
+        assert np.all(np.abs(tau / ref_tau - 1.0) < 0.25), (tau, ref_tau)

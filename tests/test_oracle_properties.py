@@ -1,0 +1,148 @@
+"""Properties of the CPU oracle itself: FP32 mirror vs FP64 restatement, leave-one-out, reseating,
+hyper-step closed forms, and that the synchronous sampler recovers planted clusters."""
+import numpy as np
+import pytest
+from conftest import c1_data, make_mixture
+
+
+def test_exp2m_log2m_accuracy(oracle):
+    L = oracle.lib()
+    d = np.concatenate([np.linspace(-124.5, 0, 4001), -np.logspace(-6, 1, 200)]).astype(np.float32)
+    got = np.array([L.mvo_exp2m(float(x)) for x in d], np.float64)
+    np.testing.assert_allclose(got, np.exp2(d.astype(np.float64)), rtol=4e-7)
+    assert L.mvo_exp2m(0.0) == 1.0
+    assert 0.0 < L.mvo_exp2m(-1e30) < 1e-37              # masked options get a negligible, positive weight
+    s = np.concatenate([np.linspace(1, 70, 3001), np.logspace(-20, 20, 300)]).astype(np.float32)
+    got = np.array([L.mvo_log2m(float(x)) for x in s], np.float64)
+    np.testing.assert_allclose(got, np.log2(s.astype(np.float64)), rtol=3e-7, atol=3e-7)
+
+
+@pytest.mark.parametrize("dims,cap", [([1, 1], 32), ([8, 8, 8], 32), ([64, 64, 64], 64), ([5, 12], 64)])
+def test_fp32_mirror_agrees_with_fp64_restatement(oracle, dims, cap):
+    views, z = make_mixture(600, dims, 5, seed=11)
+    s = oracle.OracleState(views, cap, seed=42)
+    dish = np.full((len(dims), cap), -1, np.int32)
+    dish[:, :5] = np.arange(5)
+    # a slightly scrambled seating so that plenty of rows want to move
+    rng = np.random.default_rng(0)
+    tab = np.where(rng.random(600) < 0.2, rng.integers(0, 5, 600), z)
+    s.set_assignment(tab, dish)
+    s.tau_v[:] = 0.8
+    ch64 = s.draw_rows()
+    ch32 = oracle.mirror_draw_rows(s)
+    assert (ch64 == ch32).mean() > 0.995                  # draws differ only at CDF edges
+    P = s.make_params()
+    ps = oracle.params_struct(P)
+    worst = 0.0
+    for i in range(0, 600, 13):
+        a = np.stack([oracle.stageA_f32(views[v][i], P["m"][v])[0] for v in range(len(dims))])
+        q = np.array([oracle.stageA_f32(views[v][i], P["m"][v])[1] for v in range(len(dims))])
+        _, lw32 = oracle.stageB_f32(ps, a, q, tab[i], 0.5, want_lw=True)
+        lw64 = s.row_logweights(i) / np.log(2.0)
+        ok = np.isfinite(lw64)
+        assert np.all(lw32[~ok] < -1e29)
+        worst = max(worst, np.max(np.abs(lw32[ok] - lw64[ok]) / np.maximum(1.0, np.abs(lw64[ok]))))
+    assert worst < 1e-5                                    # the stated FP32 tolerance
+
+
+def test_leave_one_out_equals_explicit_removal(oracle):
+    """Row weights must equal what one gets by really deleting the row and rebuilding the state."""
+    views, z = make_mixture(80, [3, 2], 4, seed=2)
+    cap = 16
+    dish = np.full((2, cap), -1, np.int32)
+    tab = z * 2
+    tab[7] = 9                                             # a customer alone at its table ...
+    for t in set(tab.tolist()):
+        dish[:, t] = [t % 3, (t + 1) % 3]
+    dish[1, 9] = 7                                         # ... eating a dish nobody else eats
+    s = oracle.OracleState(views, cap)
+    s.set_assignment(tab, dish)
+    s.tau_v[:] = [0.7, 1.3]
+    for i in (0, 7, 33, 79):
+        keep = np.arange(80) != i
+        s2 = oracle.OracleState([v[keep] for v in views] , cap)
+        s2.set_assignment(tab[keep], dish)
+        s2.tau_v[:] = s.tau_v
+        # score row i against the reduced state: append it as a fresh singleton at a free slot
+        free = [t for t in range(cap) if s2.n_t[t] == 0][0]
+        s3 = oracle.OracleState([np.vstack([v[keep], v[i:i + 1]]) for v in views], cap)
+        d3 = s2.dish_of.copy()
+        d3[:, free] = [5, 5]                               # an otherwise unused dish: removed again by LOO
+        s3.set_assignment(np.append(tab[keep], free), d3)
+        s3.tau_v[:] = s.tau_v
+        lw_a = s.row_logweights(i)
+        lw_b = s3.row_logweights(79)
+        own = tab[i]
+        mask = np.ones(cap + 1, bool)
+        mask[[free]] = False
+        if s.n_t[own] == 1:
+            mask[own] = False
+        np.testing.assert_allclose(lw_a[mask], lw_b[mask], rtol=1e-10, atol=1e-10)
+
+
+def test_reseat_births_overflow_and_deaths(oracle):
+    views, z = make_mixture(64, [2], 3, seed=4)
+    cap = 8
+    dish = np.full((1, cap), -1, np.int32)
+    dish[0, :6] = [0, 1, 2, 0, 1, 2]
+    tab = np.arange(64) % 6
+    s = oracle.OracleState(views, cap, seed=9)
+    s.set_assignment(tab, dish)
+    choice = tab.copy()
+    choice[tab == 5] = 0                                   # table 5 is abandoned (its would-be births stay though)
+    births = [3, 10, 11, 40]                               # four rows ask for a new table, two slots are free
+    choice[births] = -1
+    stay = [b for b in births if tab[b] == 5]
+    ns, rows, w = s.reseat(choice, want_births=True)
+    assert ns == 2 and list(rows) == births[:2]
+    assert s.table_of[births[0]] == 6 and s.table_of[births[1]] == 7
+    for b in births[2:]:
+        assert s.table_of[b] == tab[b]                     # overflow: stays where it was
+    assert s.n_t.sum() == 64 and np.all(s.n_t >= 0)
+    assert (s.n_t[5] == len(stay)) and ((s.dish_of[0, 5] == -1) == (len(stay) == 0))
+    assert np.all((s.dish_of[0] >= 0) == (s.n_t > 0))
+    for k in range(cap):
+        assert s.l_vk[0, k] == np.sum(s.dish_of[0] == k)
+        assert s.n_vk[0, k] == np.sum(s.n_t[s.dish_of[0] == k])
+    np.testing.assert_allclose(s.S1[0].sum(0), views[0].astype(np.float64).sum(0), rtol=1e-12)
+    assert np.all(w >= 0) and np.all(w.max(axis=2) == 1.0)
+
+
+def test_eppf_closed_form_equals_loops(oracle):
+    views, z = make_mixture(300, [1, 1], 6, seed=8)
+    s = oracle.OracleState(views, 32)
+    s.init_reference()
+    s.sweep_n(5, do_hyper=True)
+    L = oracle.lib()
+    for a, sg in [(1.0, 0.5), (0.3, 0.9), (5.0, 0.01), (2.0, 0.999)]:
+        for v in range(2):
+            np.testing.assert_allclose(L.mvo_log_EPPF_view(s.ref(), v, a, sg, 1), L.mvo_log_EPPF_view(s.ref(), v, a, sg, 0), rtol=1e-11)
+        np.testing.assert_allclose(L.mvo_log_EPPF_global(s.ref(), a, sg, 1), L.mvo_log_EPPF_global(s.ref(), a, sg, 0), rtol=1e-11)
+    assert L.mvo_log_EPPF_view(s.ref(), 0, 1.0, 1e-7, 1) == -np.inf        # guards of multiview_hyper.cpp:297-298
+    assert L.mvo_log_EPPF_view(s.ref(), 0, -0.6, 0.5, 1) == -np.inf
+
+
+def test_sync_sampler_recovers_planted_clusters(oracle):
+    """Config-1-shaped data: two scalar views with 2 and 3 planted groups."""
+    from sklearn.metrics import adjusted_rand_score as ari
+    views, truth = c1_data(500)
+    s = oracle.OracleState(views, 32, seed=1999)
+    s.init_reference()
+    s.sweep_n(700, threads=4, do_hyper=True)     # the synchronous kernel mixes slower than the sequential one
+    lab = s.labels()
+    assert ari(truth[0], lab[:, 0]) > 0.85
+    assert ari(truth[1], lab[:, 1]) > 0.75
+    # kernel variance learnt by the tau update: the compiled reference ends near (1.82, 1.55) on this data
+    assert 1.3 < s.tau_v[0] < 2.4 and 1.1 < s.tau_v[1] < 2.1
+
+
+def test_reference_init_matches_reference_shape(oracle):
+    views, _ = c1_data(200)
+    s = oracle.OracleState(views, 32, seed=3)
+    s.init_reference()
+    assert s.n_t[:4].sum() == 200 and np.all(s.n_t[4:] == 0)
+    assert np.all(s.dish_of[:, :4] >= 0) and np.all(s.dish_of[:, :4] < 2)
+    for v in range(2):
+        var = np.var(views[v].astype(np.float64), ddof=1)
+        np.testing.assert_allclose(s.tau_v[v], var * 0.25 * 0.01, rtol=1e-12)   # multiview_gibbs.cpp:94
+    assert s.alpha_g == 1.0 and s.sigma_g == 0.6 and np.all(s.alpha_v == 1.0) and np.all(s.sigma_v == 0.5)
