@@ -116,7 +116,7 @@ cudaError_t launch_pack(const Ctx& c, cudaStream_t s) {
 constexpr int kStatWarps = 8;
 constexpr int kStatThreads = kStatWarps * 32;
 constexpr int kStatCols = 64;     // feature columns per pass: lane handles columns lane and lane+32
-constexpr int kStatPrefetch = 8;  // rows whose loads are issued before their accumulation
+constexpr int kStatPrefetch = 16; // rows per batch; the next batch's loads are issued before this one is accumulated
 
 int stats_smem_bytes(const Ctx& c) {
   return kStatWarps * c.cap * (kStatCols + 32) * (int)sizeof(float) + kStatWarps * c.cap * (int)sizeof(int32_t);
@@ -158,6 +158,22 @@ __global__ void __launch_bounds__(kStatThreads, 1) k_stats(const Ctx c) {
       const int col0 = dc + lane, col1 = dc + lane + 32;
       const bool has0 = col0 < D, has1 = col1 < D;
 
+      // Loads are unconditional (clamped addresses) and issued a whole batch ahead of their use, so
+      // that kStatPrefetch*2 requests per warp are in flight while the previous batch is accumulated.
+      const int cc0 = has0 ? col0 : (D - 1), cc1 = has1 ? col1 : (D - 1);
+      const int last_row = c.n_rows - 1;
+      float nx0[kStatPrefetch], nx1[kStatPrefetch];
+      auto issue = [&](int ch, int j0) {
+#pragma unroll
+        for (int u = 0; u < kStatPrefetch; ++u) {
+          int r = ch * 32 + j0 + u;
+          r = r < last_row ? r : last_row;
+          const float* p = xv + (size_t)r * D;
+          nx0[u] = __ldg(p + cc0);
+          nx1[u] = __ldg(p + cc1);
+        }
+      };
+      if (w_lo < w_hi) issue(w_lo, 0);
       for (int ch = w_lo; ch < w_hi; ++ch) {
         const int row = ch * 32 + lane;
         int tj = -3;                                   // beyond the end
@@ -175,23 +191,20 @@ __global__ void __launch_bounds__(kStatThreads, 1) k_stats(const Ctx c) {
         }
         for (int j0 = 0; j0 < 32; j0 += kStatPrefetch) {
           float x0[kStatPrefetch], x1[kStatPrefetch];
-          int tt[kStatPrefetch];
+#pragma unroll
+          for (int u = 0; u < kStatPrefetch; ++u) { x0[u] = nx0[u]; x1[u] = nx1[u]; }
+          if (j0 + kStatPrefetch < 32) issue(ch, j0 + kStatPrefetch);
+          else if (ch + 1 < w_hi) issue(ch + 1, 0);
 #pragma unroll
           for (int u = 0; u < kStatPrefetch; ++u) {
-            tt[u] = __shfl_sync(0xffffffffu, tj, j0 + u);
-            const size_t base = (size_t)(ch * 32 + j0 + u) * D;
-            x0[u] = (tt[u] >= 0 && has0) ? __ldg(xv + base + col0) : 0.0f;
-            x1[u] = (tt[u] >= 0 && has1) ? __ldg(xv + base + col1) : 0.0f;
-          }
-#pragma unroll
-          for (int u = 0; u < kStatPrefetch; ++u) {
-            const int t = tt[u];
+            const int t = __shfl_sync(0xffffffffu, tj, j0 + u);
             if (t < 0) continue;                        // warp-uniform
+            const float v0 = has0 ? x0[u] : 0.0f, v1 = has1 ? x1[u] : 0.0f;
             float* a = acc + t * kStatCols;
-            a[lane] = __fadd_rn(a[lane], x0[u]);
-            a[lane + 32] = __fadd_rn(a[lane + 32], x1[u]);
+            a[lane] = __fadd_rn(a[lane], v0);
+            a[lane + 32] = __fadd_rn(a[lane + 32], v1);
             float* q = accq + t * 32;
-            q[lane] = __fadd_rn(q[lane], __fmaf_rn(x1[u], x1[u], __fmul_rn(x0[u], x0[u])));
+            q[lane] = __fadd_rn(q[lane], __fmaf_rn(v1, v1, __fmul_rn(v0, v0)));
             if (first_pass && lane == 0) cntw[t] += 1;
           }
         }
@@ -278,11 +291,13 @@ struct FinShared {
   int32_t cand_final[kMaxWorld * kMaxCap];
   int32_t ncand_total, nseat, nfree, err;
   double s1sq[kMaxViews][kMaxCap];        // |S1k|^2
-  double termA[2][kMaxCap + 1];           // scratch of the EPPF evaluations (two parameter sets)
-  double termB[2][kMaxCap + 1];
+  double sse[kMaxViews][kMaxCap];         // max(0, S2k - |S1k|^2 / n_k)     (multiview_hyper.cpp:191-193)
+  double termA[2 * (kMaxViews + 1)][kMaxCap + 1];   // scratch of the batched EPPF evaluations
+  double termB[2 * (kMaxViews + 1)][kMaxCap + 1];
+  double eppf[2 * (kMaxViews + 1)];
   double wbuf[kMaxCap + 1];
   double result[4];
-  double prop[2];
+  double prop[kMaxViews + 1];
   double hyp[3 * kMaxViews + 2];
 };
 
@@ -311,58 +326,61 @@ __device__ __forceinline__ double reflect_unit(double value) {      // :110-122
   return fmin(fmax(p, kEps), 1.0 - kEps);
 }
 
-// log EPPF of a partition with cluster sizes counts[0..n) (zeros = absent) of `total` items, for
-// two parameter sets at once (multiview_hyper.cpp:53-83 and :295-342; the two inner loops in closed
-// form: sum_{i=1}^{M-1} log(alpha+i) = lgamma(alpha+M) - lgamma(alpha+1) and
-// sum_{m=1}^{c-1} log(m-sigma) = lgamma(c-sigma) - lgamma(1-sigma)).  The terms are evaluated by
-// the block in parallel; threads 0/1 add them in ascending cluster order.  Block-uniform call.
-__device__ void eppf_pair(FinShared& S, const int32_t* counts, int n, long long total,
-                          double a0, double s0, double a1, double s1, double out[2]) {
-  const int tid = threadIdx.x;
+// log EPPF (multiview_hyper.cpp:53-83 global, :295-342 per view) for a batch of parameter sets.
+// Set 2j+q (q = 0 old / 1 proposed) belongs to level j: j < V is view j (cluster sizes = tables per
+// dish l_vk, items = tables), j = V is the franchise (sizes = customers per table n_t, items = all
+// customers).  The two inner loops are taken in closed form,
+//   sum_{i=1}^{M-1} log(alpha+i) = lgamma(alpha+M) - lgamma(alpha+1),
+//   sum_{m=1}^{c-1} log(m-sigma) = lgamma(c-sigma) - lgamma(1-sigma),
+// the per-cluster terms are evaluated by the block in parallel and one thread per set adds them in
+// ascending cluster order (the order of oracle/mv_oracle.c:eppf_core).  Block-uniform call.
+__device__ void eppf_batch(const Ctx& c, FinShared& S, const double* alpha, const double* sigma) {
+  const int tid = threadIdx.x, cap = c.cap, V = c.V;
+  const int nsets = 2 * (V + 1);
   __syncthreads();
-  if (tid < 2 * n) {
-    const int p = tid / n, i = tid - p * n;
-    const double alpha = p ? a1 : a0, sigma = p ? s1 : s0;
+  for (int idx = tid; idx < nsets * cap; idx += kFinThreads) {
+    const int set = idx / cap, i = idx - set * cap, j = set >> 1;
+    const int32_t* counts = (j < V) ? S.l_live[j] : S.n_new;
     const int cnt = counts[i];
-    S.termB[p][i] = (cnt > 1) ? lgamma((double)cnt - sigma) - lgamma(1.0 - sigma) : 0.0;
-    int j = 0;                                    // rank of cluster i among the live ones
-    for (int q = 0; q < i; ++q) j += (counts[q] > 0);
-    const double term = alpha + (double)j * sigma;
-    S.termA[p][i] = (cnt > 0) ? ((term <= 0.0) ? -INFINITY : log(term)) : 0.0;
+    const double al = alpha[set], sg = sigma[set];
+    S.termB[set][i] = (cnt > 1) ? lgamma((double)cnt - sg) - lgamma(1.0 - sg) : 0.0;
+    int r = 0;                                      // rank of cluster i among the live ones
+    for (int q = 0; q < i; ++q) r += (counts[q] > 0);
+    const double term = al + (double)r * sg;
+    S.termA[set][i] = (cnt > 0) ? ((term <= 0.0) ? -INFINITY : log(term)) : 0.0;
   }
   __syncthreads();
-  if (tid < 2) {
-    const int p = tid;
-    const double alpha = p ? a1 : a0, sigma = p ? s1 : s0;
+  if (tid < nsets) {
+    const int set = tid, j = set >> 1;
+    const int32_t* counts = (j < V) ? S.l_live[j] : S.n_new;
+    const double al = alpha[set], sg = sigma[set];
+    long long total = 0;
+    if (j < V) { for (int i = 0; i < cap; ++i) total += counts[i]; } else total = (long long)c.n_global;
     double logp;
-    if (!(sigma > kEps && sigma < 1.0 - kEps) || alpha <= -sigma) {
+    if (!(sg > kEps && sg < 1.0 - kEps) || al <= -sg) {
       logp = -INFINITY;
     } else if (total <= 0) {
       logp = 0.0;
     } else {
       logp = 0.0;
-      for (int i = 0; i < n; ++i) if (counts[i] > 0) logp += S.termA[p][i];
-      if (total > 1) logp -= lgamma(alpha + (double)total) - lgamma(alpha + 1.0);
-      for (int i = 0; i < n; ++i) if (counts[i] > 1) logp += S.termB[p][i];
+      for (int i = 0; i < cap; ++i) if (counts[i] > 0) logp += S.termA[set][i];
+      if (total > 1) logp -= lgamma(al + (double)total) - lgamma(al + 1.0);
+      for (int i = 0; i < cap; ++i) if (counts[i] > 1) logp += S.termB[set][i];
     }
-    S.result[p] = logp;
+    S.eppf[set] = logp;
   }
-  __syncthreads();
-  out[0] = S.result[0];
-  out[1] = S.result[1];
   __syncthreads();
 }
 
 __device__ double log_posterior_tau(const Ctx& c, const FinShared& S, int v, double tau) {  // :176-209
   if (tau <= 0.0) return -INFINITY;
-  const int D = c.D[v];
+  const double lg = log(2.0 * kPi * tau);      // same value in every term of the reference's loop
+  const double Dd = (double)c.D[v];
   double loglik = 0.0;
   for (int k = 0; k < c.cap; ++k) {
     const int n_k = S.n_vk[v][k];
     if (n_k == 0) continue;
-    double sse = c.S2k[v * c.cap + k] - S.s1sq[v][k] / (double)n_k;       // :191
-    if (sse < 0.0) sse = 0.0;
-    loglik += -0.5 * (double)n_k * (double)D * log(2.0 * kPi * tau) - 0.5 * (sse / tau);
+    loglik += -0.5 * (double)n_k * Dd * lg - 0.5 * (S.sse[v][k] / tau);
   }
   const double a_tau = 2.0, b_tau = 1.0;                                   // :133-134
   return loglik + (a_tau * log(b_tau) - lgamma(a_tau) - (a_tau + 1.0) * log(tau) - b_tau / tau);
@@ -597,6 +615,9 @@ __global__ void __launch_bounds__(kFinThreads, 1) k_finalize(const Ctx c, const 
     double q = 0.0;
     for (int dd = 0; dd < D; ++dd) q += S1[dd] * S1[dd];
     S.s1sq[v][k] = q;
+    const int n_k = S.n_vk[v][k];
+    double sse = (n_k > 0) ? c.S2k[i] - q / (double)n_k : 0.0;
+    S.sse[v][k] = sse < 0.0 ? 0.0 : sse;
   }
   __syncthreads();
 
@@ -618,106 +639,89 @@ __global__ void __launch_bounds__(kFinThreads, 1) k_finalize(const Ctx c, const 
   }
 
   // ---- D. hyperparameter step (multiview_hyper.cpp:233-292) -------------------------------------
+  // The tau_v updates are independent across views, and so are the (alpha, sigma) pairs of the V views
+  // and of the franchise: they run side by side, one thread per level, on Philox numbers addressed by
+  // the position the reference's sequential code would draw them at.
   if (flags & kFinHyper) {
-    if (tid == 0) {                                           // update_tau_v_MH, :211-231
-      for (int v = 0; v < V; ++v) {
-        double tau_old = tau_v[v];
-        if (tau_old <= 0.0) tau_old = kEps;
-        const double log_old = log_posterior_tau(c, S, v, tau_old);
-        const double tau_prop = exp(log(tau_old) + 0.0 + 0.3 * dev_normal(c, sweep, v));   // :166-174
-        const double log_new = log_posterior_tau(c, S, v, tau_prop);
-        const double log_acc = (log_new - log_old) + (log(tau_prop) - log(tau_old));
-        if (log(dev_unif(c, sweep, v)) < log_acc) tau_v[v] = tau_prop;
-      }
+    if (tid < V) {                                            // update_tau_v_MH, :211-231
+      const int v = tid;
+      double tau_old = tau_v[v];
+      if (tau_old <= 0.0) tau_old = kEps;
+      const double log_old = log_posterior_tau(c, S, v, tau_old);
+      const double tau_prop = exp(log(tau_old) + 0.0 + 0.3 * dev_normal(c, sweep, v));   // :166-174
+      const double log_new = log_posterior_tau(c, S, v, tau_prop);
+      const double log_acc = (log_new - log_old) + (log(tau_prop) - log(tau_old));
+      if (log(dev_unif(c, sweep, v)) < log_acc) tau_v[v] = tau_prop;
     }
     __syncthreads();
-    for (int v = 0; v < V; ++v) {
-      long long total = 0;
-      for (int k = 0; k < cap; ++k) total += S.l_live[v][k];
-      double lp[2];
-      // alpha_v: log-normal random walk, :242-255
-      double a_old = alpha_v[v];
+    __shared__ double s_alpha[2 * (kMaxViews + 1)], s_sigma[2 * (kMaxViews + 1)];
+    // level j: its alpha/sigma slots in S.hyp and its Philox indices (alpha: base, sigma: base+1)
+    const int j = tid;
+    const bool is_level = j <= V;
+    const int ia = (j < V) ? j : 3 * V, is = (j < V) ? V + j : 3 * V + 1;
+    const int base = (j < V) ? V + 2 * j : 3 * V;
+    // alpha: log-normal random walk, :242-255 / :268-281
+    double a_old = 0.0, a_prop = 0.0;
+    if (is_level) {
+      a_old = S.hyp[ia];
       if (a_old <= 0.0) a_old = kEps;
-      if (tid == 0) {
-        const double cand = exp(log(a_old > kEps ? a_old : kEps) + 0.0 + 0.1 * dev_normal(c, sweep, V + 2 * v));
-        S.prop[0] = cand > kEps ? cand : kEps;
-      }
-      __syncthreads();
-      const double a_prop = S.prop[0];
-      eppf_pair(S, S.l_live[v], cap, total, a_old, sigma_v[v], a_prop, sigma_v[v], lp);
-      if (tid == 0) {
-        const double lo = lp[0] + log_prior_alpha(a_old), ln = lp[1] + log_prior_alpha(a_prop);
-        const double log_acc = (ln - lo) + (log(a_prop) - log(a_old));
-        if (log(dev_unif(c, sweep, V + 2 * v)) < log_acc) alpha_v[v] = a_prop;
-        S.prop[1] = reflect_unit(sigma_v[v] + 0.0 + 0.05 * dev_normal(c, sweep, V + 2 * v + 1));   // :124-128
-      }
-      __syncthreads();
-      // sigma_v: reflected random walk, :257-265
-      const double s_old = sigma_v[v], s_prop = S.prop[1], a_cur = alpha_v[v];
-      eppf_pair(S, S.l_live[v], cap, total, a_cur, s_old, a_cur, s_prop, lp);
-      if (tid == 0) {
-        const double lpo = (s_old <= kEps || s_old >= 1.0 - kEps) ? -INFINITY : lp[0] + log_prior_sigma(s_old);
-        const double lpn = (s_prop <= kEps || s_prop >= 1.0 - kEps) ? -INFINITY : lp[1] + log_prior_sigma(s_prop);
-        if (log(dev_unif(c, sweep, V + 2 * v + 1)) < lpn - lpo) sigma_v[v] = s_prop;
-      }
-      __syncthreads();
+      const double cand = exp(log(a_old > kEps ? a_old : kEps) + 0.0 + 0.1 * dev_normal(c, sweep, base));   // :100-108
+      a_prop = cand > kEps ? cand : kEps;
+      s_alpha[2 * j] = a_old; s_alpha[2 * j + 1] = a_prop;
+      s_sigma[2 * j] = S.hyp[is]; s_sigma[2 * j + 1] = S.hyp[is];
     }
-    {                                                          // global level, :268-291
-      double lp[2];
-      double a_old = alpha_g;
-      if (a_old <= 0.0) a_old = kEps;
-      if (tid == 0) {
-        const double cand = exp(log(a_old > kEps ? a_old : kEps) + 0.0 + 0.1 * dev_normal(c, sweep, 3 * V));
-        S.prop[0] = cand > kEps ? cand : kEps;
-      }
-      __syncthreads();
-      const double a_prop = S.prop[0];
-      eppf_pair(S, S.n_new, cap, (long long)c.n_global, a_old, sigma_g, a_prop, sigma_g, lp);
-      if (tid == 0) {
-        const double lo = lp[0] + log_prior_alpha(a_old), ln = lp[1] + log_prior_alpha(a_prop);
-        const double log_acc = (ln - lo) + (log(a_prop) - log(a_old));
-        if (log(dev_unif(c, sweep, 3 * V)) < log_acc) alpha_g = a_prop;
-        S.prop[1] = reflect_unit(sigma_g + 0.0 + 0.05 * dev_normal(c, sweep, 3 * V + 1));
-      }
-      __syncthreads();
-      const double s_old = sigma_g, s_prop = S.prop[1], a_cur = alpha_g;
-      eppf_pair(S, S.n_new, cap, (long long)c.n_global, a_cur, s_old, a_cur, s_prop, lp);
-      if (tid == 0) {
-        const double lpo = (s_old <= kEps || s_old >= 1.0 - kEps) ? -INFINITY : lp[0] + log_prior_sigma(s_old);
-        const double lpn = (s_prop <= kEps || s_prop >= 1.0 - kEps) ? -INFINITY : lp[1] + log_prior_sigma(s_prop);
-        if (log(dev_unif(c, sweep, 3 * V + 1)) < lpn - lpo) sigma_g = s_prop;
-      }
-      __syncthreads();
+    eppf_batch(c, S, s_alpha, s_sigma);
+    double s_old = 0.0, s_prop = 0.0;
+    if (is_level) {
+      const double lo = S.eppf[2 * j] + log_prior_alpha(a_old), ln = S.eppf[2 * j + 1] + log_prior_alpha(a_prop);
+      const double log_acc = (ln - lo) + (log(a_prop) - log(a_old));
+      if (log(dev_unif(c, sweep, base)) < log_acc) S.hyp[ia] = a_prop;
+      // sigma: reflected random walk, :257-265 / :283-291
+      s_old = S.hyp[is];
+      s_prop = reflect_unit(s_old + 0.0 + 0.05 * dev_normal(c, sweep, base + 1));                             // :124-128
+      s_alpha[2 * j] = S.hyp[ia]; s_alpha[2 * j + 1] = S.hyp[ia];
+      s_sigma[2 * j] = s_old; s_sigma[2 * j + 1] = s_prop;
     }
+    eppf_batch(c, S, s_alpha, s_sigma);
+    if (is_level) {
+      const double lpo = (s_old <= kEps || s_old >= 1.0 - kEps) ? -INFINITY : S.eppf[2 * j] + log_prior_sigma(s_old);
+      const double lpn = (s_prop <= kEps || s_prop >= 1.0 - kEps) ? -INFINITY : S.eppf[2 * j + 1] + log_prior_sigma(s_prop);
+      if (log(dev_unif(c, sweep, base + 1)) < lpn - lpo) S.hyp[is] = s_prop;
+    }
+    __syncthreads();
   }
   for (int i = tid; i < 3 * V + 2; i += kFinThreads) c.hyp[i] = S.hyp[i];
 
   // ---- E. FP32 parameter block of the next sweep (oracle/mv_oracle.c:mvo_make_params) ----------
+  for (int i = tid; i < cap * c.Dsum; i += kFinThreads) {    // per-table posterior means, one element each
+    int v = 0;
+    while (v + 1 < V && i >= cap * c.doff[v + 1]) ++v;
+    const int D = c.D[v];
+    const int local = i - cap * c.doff[v];
+    const int t = local / D, dd = local - t * D;
+    const int k = S.dish[v][t];
+    float m = 0.f;
+    if (k >= 0) m = (float)(c.S1k[(size_t)cap * c.doff[v] + (size_t)k * D + dd] / (tau_v[v] + (double)S.n_vk[v][k]));
+    c.mean[i] = m;
+    if (c.mean_hi) {
+      const float hi = __uint_as_float(__float_as_uint(m) & 0xFFFFE000u);   // TF32-exact part
+      c.mean_hi[i] = hi;
+      c.mean_lo[i] = __fadd_rn(m, -hi);
+    }
+  }
+  __syncthreads();
   for (int i = tid; i < V * cap; i += kFinThreads) {
     const int v = i / cap, t = i - v * cap;
     const int D = c.D[v];
     const int k = S.dish[v][t];
-    float* mt = c.mean + (size_t)cap * c.doff[v] + (size_t)t * D;
-    float* mh = c.mean_hi ? c.mean_hi + (size_t)cap * c.doff[v] + (size_t)t * D : nullptr;
-    float* ml = c.mean_lo ? c.mean_lo + (size_t)cap * c.doff[v] + (size_t)t * D : nullptr;
+    const float* mt = c.mean + (size_t)cap * c.doff[v] + (size_t)t * D;
     TableParam q;
     if (k < 0) {
       q.A = 0.f; q.C = kMasked; q.A1 = 0.f; q.C1 = kMasked; q.W = kMasked; q.W1 = kMasked; q.dish = -1; q.lone = 0;
-      for (int dd = 0; dd < D; ++dd) { mt[dd] = 0.f; if (mh) { mh[dd] = 0.f; ml[dd] = 0.f; } }
     } else {
       const double tau = tau_v[v], n = (double)S.n_vk[v][k];
-      const double* S1 = c.S1k + (size_t)cap * c.doff[v] + (size_t)k * D;
       double mm = 0.0;
-      for (int dd = 0; dd < D; ++dd) {
-        const float m = (float)(S1[dd] / (tau + n));
-        mt[dd] = m;
-        if (mh) {
-          const float hi = __uint_as_float(__float_as_uint(m) & 0xFFFFE000u);   // TF32-exact part
-          mh[dd] = hi;
-          ml[dd] = __fadd_rn(m, -hi);
-        }
-        mm += (double)m * (double)m;
-      }
+      for (int dd = 0; dd < D; ++dd) mm += (double)mt[dd] * (double)mt[dd];
       const double a = (tau + n) / (2.0 * tau * (tau + n + 1.0));
       const double cc = -0.5 * log(2.0 * kPi * tau * (tau + n + 1.0) / (tau + n));
       q.A = (float)(kLog2e * a);
