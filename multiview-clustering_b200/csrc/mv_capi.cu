@@ -6,6 +6,7 @@
 #include <dlfcn.h>
 
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 #include <new>
@@ -75,6 +76,7 @@ struct mvg_handle {
   int64_t launches = 0;
   float last_ms = 0.f;
   int sms = 148;
+  void* tc_maps = nullptr;           // host copy of the TMA tensor maps (tcgen05 engine)
 };
 
 namespace {
@@ -150,6 +152,11 @@ int ensure_layout(mvg_handle* h) {
   } else if (h->cfg.engine == MVG_ENGINE_AUTO && draw_tc_supported(c)) {
     h->engine = MVG_ENGINE_TCGEN05;
   }
+  if (h->engine == MVG_ENGINE_TCGEN05) {
+    if (posix_memalign(&h->tc_maps, 128, draw_tc_maps_bytes()) != 0) return fail(h, MVG_ENOMEM, "tensor map allocation");
+    cudaError_t e = draw_tc_make_maps(c, h->tc_maps);
+    if (e != cudaSuccess) return fail(h, MVG_ECUDA, std::string("cuTensorMapEncodeTiled: ") + cudaGetErrorString(e));
+  }
   return MVG_OK;
 }
 
@@ -179,7 +186,7 @@ int rebuild_pipeline(mvg_handle* h, int32_t flags, cudaEvent_t* marks /* 4 event
 }
 
 int launch_draw(mvg_handle* h) {
-  if (h->engine == MVG_ENGINE_TCGEN05) MVG_CUDA(h, launch_draw_tc(h->c, h->stream));
+  if (h->engine == MVG_ENGINE_TCGEN05) MVG_CUDA(h, launch_draw_tc(h->c, h->tc_maps, h->stream));
   else MVG_CUDA(h, launch_draw_simt(h->c, h->stream));
   h->launches += 1;
   return MVG_OK;
@@ -259,6 +266,7 @@ int mvg_destroy(mvg_handle* h) {
   for (void* p : h->view_owned) if (p) cudaFree(p);
   for (auto& ev : h->ev) if (ev) cudaEventDestroy(ev);
   if (h->stream) cudaStreamDestroy(h->stream);
+  free(h->tc_maps);
   delete h;
   return MVG_OK;
 }

@@ -1,8 +1,425 @@
-// mv_draw_tc.cu — likelihood + draw on the tcgen05 tensor cores (engine MVG_ENGINE_TCGEN05).
-// Placeholder until the TMA/TMEM kernel lands: reports "unsupported" so AUTO selects the SIMT engine.
+// mv_draw_tc.cu — likelihood + draw on the 5th-generation tensor cores (engine MVG_ENGINE_TCGEN05).
+//
+// Shape: cap = 64 table slots, every view dense with dim 64, at most 3 views (BASELINE config C3).
+// One persistent CTA per SM walks row tiles of 128 customers.  For every (tile, view):
+//
+//   TMA producer (1 thread)   cp.async.bulk.tensor: the tile's [128 x 64] FP32 features arrive in
+//                             shared memory as two K-halves of [128 x 32] in the 128B-swizzled
+//                             K-major layout UMMA reads directly.
+//   converter (128 threads)   per row: |x|^2 and the TF32 remainder x_lo = x - trunc_tf32(x),
+//                             written to a second buffer in the same swizzled positions.
+//   MMA issuer (1 thread)     tcgen05.mma kind::tf32, M=128 N=64 K=8, three passes accumulated in
+//                             one TMEM tile:  x.m_hi + x.m_lo + x_lo.m_hi  (the hardware reads the
+//                             top 19 bits of each FP32 operand, so the raw tile serves as x_hi).
+//                             The split restores ~2^-21 relative accuracy (north_star: FP32 tolerance).
+//   epilogue (128 threads)    tcgen05.ld: thread r owns TMEM lane r = customer r: its 64 dot
+//                             products land in registers and feed RowEpilogue (mv_device.cuh) —
+//                             leave-one-out weights, log-sum-exp marginal, inverse-CDF draw.
+//
+// The [N x 64] log-likelihood matrices never exist in memory: HBM traffic is the features once
+// (N*V*256 B) plus 8 B per customer (table in, choice out).
+//
+// Replaces, per customer: remove_customer + compute_table_probs_with_cache + the draw of
+// /root/reference/Multiview/multiview_utils.cpp:71-192, :307-350 and multiview_gibbs.cpp:157-199.
+#include <cuda.h>
+
 #include "mv_ctx.h"
 
 namespace mv {
-bool draw_tc_supported(const Ctx&) { return false; }
-cudaError_t launch_draw_tc(const Ctx&, cudaStream_t) { return cudaErrorNotSupported; }
+
+namespace {
+
+constexpr int kTileRows = 128;
+constexpr int kHalfCols = 32;                       // floats per 128-byte swizzled row
+constexpr int kHalfBytes = kTileRows * 128;         // 16 KB: one K-half of an A tile
+constexpr int kBHalfBytes = 64 * 128;               // 8 KB: one K-half of a B matrix (64 tables)
+constexpr int kRawStages = 5;                       // K-halves of raw features in flight
+constexpr int kLoStages = 2;
+constexpr int kDStages = 4;                         // TMEM accumulator tiles (64 columns each)
+constexpr int kTmemCols = 256;
+constexpr int kMaxTcViews = 3;
+constexpr int kThreads = 384;                       // WG0: control, WG1: epilogue, WG2: converter
+
+struct __align__(64) TcMaps {
+  CUtensorMap x[kMaxTcViews];
+  CUtensorMap mean_hi;
+  CUtensorMap mean_lo;
+};
+
+// ---- shared memory carve-up (dynamic, 1024-byte aligned for SWIZZLE_128B) --------------------
+struct SmemLayout {
+  static constexpr int b_off = 0;                                            // [V][hi,lo][2 halves][8 KB]
+  static constexpr int raw_off = b_off + kMaxTcViews * 4 * kBHalfBytes;      // 96 KB
+  static constexpr int lo_off = raw_off + kRawStages * kHalfBytes;           // +80 KB
+  static constexpr int tp_off = lo_off + kLoStages * kHalfBytes;             // +32 KB
+  static constexpr int tm_off = tp_off + kMaxTcViews * 64 * (int)sizeof(TableParam);
+  static constexpr int vp_off = tm_off + 64 * (int)sizeof(TableMass);
+  static constexpr int xx_off = vp_off + kMaxTcViews * (int)sizeof(ViewParam);
+  static constexpr int bar_off = xx_off + kDStages * kTileRows * (int)sizeof(float);
+  static constexpr int n_bars = 2 * kRawStages + 2 * kLoStages + 3 * kDStages + 1;
+  static constexpr int misc_off = bar_off + n_bars * 8;
+  static constexpr int total = misc_off + 64;
+};
+static_assert(SmemLayout::total <= 227 * 1024, "shared memory budget");
+
+// ---- PTX helpers ----------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "WAIT_LOOP:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+      "@p bra DONE;\n\t"
+      "bra WAIT_LOOP;\n\t"
+      "DONE:\n\t"
+      "}\n" ::"r"(bar), "r"(parity)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+__device__ __forceinline__ void umma_tf32(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t"
+      "}\n" ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+
+// K-major, SWIZZLE_128B operand descriptor (cute::UMMA::SmemDescriptor): start address >> 4 in bits
+// [0,14), leading byte offset [16,30) (unused for swizzled K-major: 1), stride byte offset [32,46) =
+// 1024 B between 8-row groups, version 1 at [46,48), layout type SWIZZLE_128B = 2 at [61,64).
+__device__ __forceinline__ uint64_t make_desc(uint32_t smem_addr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr >> 4) & 0x3FFF);
+  d |= (uint64_t)1 << 16;
+  d |= (uint64_t)(1024 >> 4) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)2 << 61;
+  return d;
+}
+// cute::UMMA::InstrDescriptor for kind::tf32: D = F32 (1 at [4,6)), A = B = TF32 (2 at [7,10) and
+// [10,13)), both K-major, N >> 3 at [17,23), M >> 4 at [24,29).
+constexpr uint32_t kIdesc = (1u << 4) | (2u << 7) | (2u << 10) | ((64u >> 3) << 17) | ((128u >> 4) << 24);
+
+template <int REGS> __device__ __forceinline__ void reg_dec() { asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(REGS)); }
+template <int REGS> __device__ __forceinline__ void reg_inc() { asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(REGS)); }
+
+struct Ring {   // stage index + mbarrier phase parity of one pipeline role
+  int stage = 0;
+  uint32_t phase = 0;
+  int n;
+  __device__ explicit Ring(int n_) : n(n_) {}
+  __device__ __forceinline__ void next() { if (++stage == n) { stage = 0; phase ^= 1u; } }
+};
+
+}  // namespace
+
+__global__ void __launch_bounds__(kThreads, 1) k_draw_tc(const Ctx c, const __grid_constant__ TcMaps maps) {
+  extern __shared__ __align__(1024) unsigned char smem[];
+  const uint32_t sbase = smem_u32(smem);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int V = c.V;
+
+  TableParam* s_tp = reinterpret_cast<TableParam*>(smem + SmemLayout::tp_off);
+  TableMass* s_tm = reinterpret_cast<TableMass*>(smem + SmemLayout::tm_off);
+  ViewParam* s_vp = reinterpret_cast<ViewParam*>(smem + SmemLayout::vp_off);
+  float* s_xx = reinterpret_cast<float*>(smem + SmemLayout::xx_off);
+  uint32_t* s_misc = reinterpret_cast<uint32_t*>(smem + SmemLayout::misc_off);   // [0] TMEM base, [1] sweep, [2..3] GlobalParam floats
+
+  // barrier addresses
+  const uint32_t bar0 = sbase + SmemLayout::bar_off;
+  auto raw_full = [&](int s) { return bar0 + 8u * s; };
+  auto raw_empty = [&](int s) { return bar0 + 8u * (kRawStages + s); };
+  auto lo_full = [&](int s) { return bar0 + 8u * (2 * kRawStages + s); };
+  auto lo_empty = [&](int s) { return bar0 + 8u * (2 * kRawStages + kLoStages + s); };
+  auto d_full = [&](int s) { return bar0 + 8u * (2 * kRawStages + 2 * kLoStages + s); };
+  auto d_empty = [&](int s) { return bar0 + 8u * (2 * kRawStages + 2 * kLoStages + kDStages + s); };
+  auto xx_full = [&](int s) { return bar0 + 8u * (2 * kRawStages + 2 * kLoStages + 2 * kDStages + s); };
+  const uint32_t b_full = bar0 + 8u * (2 * kRawStages + 2 * kLoStages + 3 * kDStages);
+
+  // ---- one-time setup --------------------------------------------------------------------------
+  for (int i = tid; i < V * 64; i += kThreads) s_tp[i] = c.tparam[i];
+  for (int i = tid; i < 64; i += kThreads) s_tm[i] = c.tmass[i];
+  if (tid < V) s_vp[tid] = c.vparam[tid];
+  if (tid == 0) {
+    const GlobalParam g = *c.gparam;
+    s_misc[1] = g.sweep;
+    s_misc[2] = __float_as_uint(g.LMN0);
+    s_misc[3] = __float_as_uint(g.LMN1);
+    for (int s = 0; s < kRawStages; ++s) { mbar_init(raw_full(s), 1); mbar_init(raw_empty(s), 129); }   // 128 converter threads + the MMA commit
+    for (int s = 0; s < kLoStages; ++s) { mbar_init(lo_full(s), 128); mbar_init(lo_empty(s), 1); }
+    for (int s = 0; s < kDStages; ++s) { mbar_init(d_full(s), 1); mbar_init(d_empty(s), 128); mbar_init(xx_full(s), 128); }
+    mbar_init(b_full, 1);
+    fence_barrier_init();
+  }
+  if (warp == 1) {   // TMEM allocation: one warp, address published through shared memory
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&s_misc[0])), "n"(kTmemCols));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = s_misc[0];
+  const uint32_t sweep = s_misc[1];
+  GlobalParam gp;
+  gp.LMN0 = __uint_as_float(s_misc[2]);
+  gp.LMN1 = __uint_as_float(s_misc[3]);
+
+  const int n_tiles = (c.n_rows + kTileRows - 1) / kTileRows;
+
+  if (warp < 4) {
+    // =========================== WG0: control ==================================================
+    reg_dec<40>();
+    if (warp == 0 && lane == 0) {
+      // ---- TMA producer ----
+      mbar_expect_tx(b_full, (uint32_t)(V * 4 * kBHalfBytes));
+      for (int v = 0; v < V; ++v)
+        for (int part = 0; part < 2; ++part)         // 0: m_hi, 1: m_lo
+          for (int h = 0; h < 2; ++h)
+            tma_load_2d(sbase + SmemLayout::b_off + ((v * 2 + part) * 2 + h) * kBHalfBytes,
+                        part ? &maps.mean_lo : &maps.mean_hi, b_full, h * kHalfCols, v * 64);
+      Ring r(kRawStages);
+      for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x)
+        for (int v = 0; v < V; ++v)
+          for (int h = 0; h < 2; ++h) {
+            mbar_wait(raw_empty(r.stage), r.phase ^ 1u);
+            mbar_expect_tx(raw_full(r.stage), kHalfBytes);
+            tma_load_2d(sbase + SmemLayout::raw_off + r.stage * kHalfBytes, &maps.x[v], raw_full(r.stage),
+                        h * kHalfCols, tile * kTileRows);
+            r.next();
+          }
+    } else if (warp == 1 && lane == 0) {
+      // ---- MMA issuer ----
+      mbar_wait(b_full, 0);
+      tc_fence_after();
+      Ring rr(kRawStages), rl(kLoStages), rd(kDStages);
+      for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x)
+        for (int v = 0; v < V; ++v) {
+          mbar_wait(d_empty(rd.stage), rd.phase ^ 1u);
+          tc_fence_after();
+          const uint32_t d_tmem = tmem_base + (uint32_t)(rd.stage * 64);
+          uint32_t accumulate = 0;
+          // passes 1+2 on the raw halves: x_hi . m_hi  and  x_hi . m_lo
+          for (int h = 0; h < 2; ++h) {
+            mbar_wait(raw_full(rr.stage), rr.phase);
+            tc_fence_after();
+            const uint32_t a_addr = sbase + SmemLayout::raw_off + rr.stage * kHalfBytes;
+            for (int part = 0; part < 2; ++part) {
+              const uint32_t b_addr = sbase + SmemLayout::b_off + ((v * 2 + part) * 2 + h) * kBHalfBytes;
+#pragma unroll
+              for (int k = 0; k < 4; ++k) {           // 4 x (K = 8 floats = 32 bytes) per 128-byte row
+                umma_tf32(d_tmem, make_desc(a_addr + k * 32), make_desc(b_addr + k * 32), kIdesc, accumulate);
+                accumulate = 1;
+              }
+            }
+            umma_commit(raw_empty(rr.stage));         // this raw half is free once these MMAs retire
+            rr.next();
+          }
+          // pass 3 on the remainder halves: x_lo . m_hi
+          for (int h = 0; h < 2; ++h) {
+            mbar_wait(lo_full(rl.stage), rl.phase);
+            tc_fence_after();
+            const uint32_t a_addr = sbase + SmemLayout::lo_off + rl.stage * kHalfBytes;
+            const uint32_t b_addr = sbase + SmemLayout::b_off + ((v * 2 + 0) * 2 + h) * kBHalfBytes;
+#pragma unroll
+            for (int k = 0; k < 4; ++k) umma_tf32(d_tmem, make_desc(a_addr + k * 32), make_desc(b_addr + k * 32), kIdesc, 1);
+            umma_commit(lo_empty(rl.stage));
+            rl.next();
+          }
+          umma_commit(d_full(rd.stage));
+          rd.next();
+        }
+    }
+  } else if (warp < 8) {
+    // =========================== WG1: epilogue (thread r <-> TMEM lane r <-> customer r) ========
+    reg_inc<232>();
+    const int r = tid - 128;
+    const uint32_t lane_base = (uint32_t)((warp & 3) * 32) << 16;
+    Ring rd(kDStages);
+    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+      const int row = tile * kTileRows + r;
+      const bool live = row < c.n_rows;
+      const int rowc = live ? row : (c.n_rows - 1);
+      RowEpilogue<64> epi;
+      epi.begin(s_tm, gp, c.table_cur[rowc]);
+      for (int v = 0; v < V; ++v) {
+        mbar_wait(d_full(rd.stage), rd.phase);
+        mbar_wait(xx_full(rd.stage), rd.phase);
+        tc_fence_after();
+        float acc[64];
+        {
+          uint32_t u[64];
+          const uint32_t taddr = tmem_base + lane_base + (uint32_t)(rd.stage * 64);
+          asm volatile(
+              "tcgen05.ld.sync.aligned.32x32b.x64.b32 "
+              "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+              "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, "
+              "%32, %33, %34, %35, %36, %37, %38, %39, %40, %41, %42, %43, %44, %45, %46, %47, "
+              "%48, %49, %50, %51, %52, %53, %54, %55, %56, %57, %58, %59, %60, %61, %62, %63}, [%64];"
+              : "=r"(u[0]), "=r"(u[1]), "=r"(u[2]), "=r"(u[3]), "=r"(u[4]), "=r"(u[5]), "=r"(u[6]), "=r"(u[7]),
+                "=r"(u[8]), "=r"(u[9]), "=r"(u[10]), "=r"(u[11]), "=r"(u[12]), "=r"(u[13]), "=r"(u[14]), "=r"(u[15]),
+                "=r"(u[16]), "=r"(u[17]), "=r"(u[18]), "=r"(u[19]), "=r"(u[20]), "=r"(u[21]), "=r"(u[22]), "=r"(u[23]),
+                "=r"(u[24]), "=r"(u[25]), "=r"(u[26]), "=r"(u[27]), "=r"(u[28]), "=r"(u[29]), "=r"(u[30]), "=r"(u[31]),
+                "=r"(u[32]), "=r"(u[33]), "=r"(u[34]), "=r"(u[35]), "=r"(u[36]), "=r"(u[37]), "=r"(u[38]), "=r"(u[39]),
+                "=r"(u[40]), "=r"(u[41]), "=r"(u[42]), "=r"(u[43]), "=r"(u[44]), "=r"(u[45]), "=r"(u[46]), "=r"(u[47]),
+                "=r"(u[48]), "=r"(u[49]), "=r"(u[50]), "=r"(u[51]), "=r"(u[52]), "=r"(u[53]), "=r"(u[54]), "=r"(u[55]),
+                "=r"(u[56]), "=r"(u[57]), "=r"(u[58]), "=r"(u[59]), "=r"(u[60]), "=r"(u[61]), "=r"(u[62]), "=r"(u[63])
+              : "r"(taddr));
+          asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+          for (int t = 0; t < 64; ++t) acc[t] = __uint_as_float(u[t]);
+        }
+        const float xx = s_xx[rd.stage * kTileRows + r];
+        tc_fence_before();
+        mbar_arrive(d_empty(rd.stage));               // accumulator tile and xx slot are free again
+        if (c.debug_export && live) {
+          float* da = c.dbg_acc + ((size_t)row * V + v) * 64;
+#pragma unroll
+          for (int t = 0; t < 64; ++t) da[t] = acc[t];
+          c.dbg_xx[(size_t)row * V + v] = xx;
+        }
+        epi.view(s_tp + v * 64, s_vp[v], acc, xx, v == 0);
+        rd.next();
+      }
+      const U4 rnd = stream_block(c.seed, c.chain, kDomTable, 0, sweep, (uint64_t)(c.row_offset + rowc));
+      const int choice = epi.finish(s_tm, uniform_f32_from(rnd.x));
+      if (live) {
+        c.choice[row] = choice;
+        if (c.debug_export) c.dbg_choice[row] = choice;
+      }
+      const unsigned births = __ballot_sync(0xffffffffu, live && choice == kNewTable);
+      if (lane == 0 && (row >> 5) < c.n_chunks) c.birthmask[row >> 5] = births;
+    }
+  } else {
+    // =========================== WG2: converter ==================================================
+    reg_dec<80>();
+    const int r = tid - 256;                           // row of the tile = 128-byte line of each half
+    Ring rr(kRawStages), rl(kLoStages), rd(kDStages);
+    const uint32_t line = (uint32_t)r * 128u;
+    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x)
+      for (int v = 0; v < V; ++v) {
+        float xx = 0.0f;
+        for (int h = 0; h < 2; ++h) {
+          mbar_wait(raw_full(rr.stage), rr.phase);
+          mbar_wait(lo_empty(rl.stage), rl.phase ^ 1u);
+          const unsigned char* src = smem + SmemLayout::raw_off + rr.stage * kHalfBytes + line;
+          unsigned char* dst = smem + SmemLayout::lo_off + rl.stage * kHalfBytes + line;
+#pragma unroll
+          for (int cidx = 0; cidx < 8; ++cidx) {       // logical 16-byte chunk cidx sits at physical chunk cidx ^ (r & 7)
+            const int off = ((cidx ^ (r & 7)) << 4);
+            const float4 x4 = *reinterpret_cast<const float4*>(src + off);
+            float4 l4;
+            l4.x = __fadd_rn(x4.x, -__uint_as_float(__float_as_uint(x4.x) & 0xFFFFE000u));
+            l4.y = __fadd_rn(x4.y, -__uint_as_float(__float_as_uint(x4.y) & 0xFFFFE000u));
+            l4.z = __fadd_rn(x4.z, -__uint_as_float(__float_as_uint(x4.z) & 0xFFFFE000u));
+            l4.w = __fadd_rn(x4.w, -__uint_as_float(__float_as_uint(x4.w) & 0xFFFFE000u));
+            xx = __fmaf_rn(x4.x, x4.x, xx);
+            xx = __fmaf_rn(x4.y, x4.y, xx);
+            xx = __fmaf_rn(x4.z, x4.z, xx);
+            xx = __fmaf_rn(x4.w, x4.w, xx);
+            *reinterpret_cast<float4*>(dst + off) = l4;
+          }
+          fence_proxy_async();                         // generic-proxy stores -> visible to the MMA (async proxy)
+          mbar_arrive(lo_full(rl.stage));
+          mbar_arrive(raw_empty(rr.stage));            // this thread no longer reads the raw half
+          rr.next();
+          rl.next();
+        }
+        mbar_wait(d_empty(rd.stage), rd.phase ^ 1u);   // the epilogue has consumed this xx slot
+        s_xx[rd.stage * kTileRows + r] = xx;
+        mbar_arrive(xx_full(rd.stage));
+        rd.next();
+      }
+  }
+
+  // ---- teardown ------------------------------------------------------------------------------------
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(kTmemCols));
+  }
+}
+
+// =================================================================================================
+// host side
+// =================================================================================================
+bool draw_tc_supported(const Ctx& c) {
+  if (c.cap != 64 || c.V < 1 || c.V > kMaxTcViews) return false;
+  for (int v = 0; v < c.V; ++v)
+    if (c.D[v] != 64 || (reinterpret_cast<uintptr_t>(c.x[v]) & 15) != 0) return false;
+  return true;
+}
+
+size_t draw_tc_maps_bytes() { return sizeof(TcMaps); }
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static cudaError_t encode_2d(EncodeTiledFn fn, CUtensorMap* map, const void* base, uint64_t rows, uint32_t box_rows) {
+  cuuint64_t dims[2] = {64, rows};
+  cuuint64_t strides[1] = {64 * sizeof(float)};
+  cuuint32_t box[2] = {kHalfCols, box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<void*>(base), dims, strides, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS ? cudaSuccess : cudaErrorInvalidValue;
+}
+
+cudaError_t draw_tc_make_maps(const Ctx& c, void* maps_out) {
+  void* fnp = nullptr;
+  cudaDriverEntryPointQueryResult q;
+  cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fnp, cudaEnableDefault, &q);
+  if (e != cudaSuccess) return e;
+  if (!fnp || q != cudaDriverEntryPointSuccess) return cudaErrorNotSupported;
+  EncodeTiledFn fn = reinterpret_cast<EncodeTiledFn>(fnp);
+  TcMaps* m = static_cast<TcMaps*>(maps_out);
+  for (int v = 0; v < c.V; ++v)
+    if ((e = encode_2d(fn, &m->x[v], c.x[v], (uint64_t)c.n_rows, kTileRows)) != cudaSuccess) return e;
+  for (int v = c.V; v < kMaxTcViews; ++v) m->x[v] = m->x[0];
+  if ((e = encode_2d(fn, &m->mean_hi, c.mean_hi, (uint64_t)c.V * 64, 64)) != cudaSuccess) return e;
+  if ((e = encode_2d(fn, &m->mean_lo, c.mean_lo, (uint64_t)c.V * 64, 64)) != cudaSuccess) return e;
+  return cudaSuccess;
+}
+
+cudaError_t launch_draw_tc(const Ctx& c, const void* maps, cudaStream_t s) {
+  if (c.n_rows <= 0) return cudaSuccess;
+  if (!draw_tc_supported(c) || !maps) return cudaErrorInvalidValue;
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  const int n_tiles = (c.n_rows + kTileRows - 1) / kTileRows;
+  const int grid = n_tiles < sms ? n_tiles : sms;
+  cudaError_t e = cudaFuncSetAttribute(k_draw_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, SmemLayout::total);
+  if (e != cudaSuccess) return e;
+  k_draw_tc<<<grid, kThreads, SmemLayout::total, s>>>(c, *static_cast<const TcMaps*>(maps));
+  return cudaGetLastError();
+}
+
 }  // namespace mv
