@@ -56,7 +56,12 @@ enum {
   MVG_EUNSUPPORTED = -6 /* shape outside what the kernels were built for */
 };
 
-enum { MVG_ENGINE_AUTO = 0, MVG_ENGINE_SIMT = 1, MVG_ENGINE_TCGEN05 = 2 };
+enum {
+  MVG_ENGINE_AUTO = 0,
+  MVG_ENGINE_SIMT = 1,          /* FP32 CUDA cores; every FP32 operation mirrored by the CPU checker */
+  MVG_ENGINE_TCGEN05 = 2,       /* tensor-core dot products (3-pass TF32), mirrored epilogue */
+  MVG_ENGINE_TCGEN05_FAST = 3   /* same, weights through MUFU ex2.approx (tolerance-level weights) */
+};
 enum { MVG_VIEW_DENSE = 0, MVG_VIEW_CSR = 1 };
 
 #define MVG_NEW_TABLE (-1)

@@ -146,13 +146,13 @@ int ensure_layout(mvg_handle* h) {
   h->layout_done = true;
   // engine choice
   h->engine = MVG_ENGINE_SIMT;
-  if (h->cfg.engine == MVG_ENGINE_TCGEN05) {
+  if (h->cfg.engine == MVG_ENGINE_TCGEN05 || h->cfg.engine == MVG_ENGINE_TCGEN05_FAST) {
     if (!draw_tc_supported(c)) return fail(h, MVG_EUNSUPPORTED, "tcgen05 engine needs cap = 64 and every dim = 64");
-    h->engine = MVG_ENGINE_TCGEN05;
+    h->engine = h->cfg.engine;
   } else if (h->cfg.engine == MVG_ENGINE_AUTO && draw_tc_supported(c)) {
     h->engine = MVG_ENGINE_TCGEN05;
   }
-  if (h->engine == MVG_ENGINE_TCGEN05) {
+  if (h->engine == MVG_ENGINE_TCGEN05 || h->engine == MVG_ENGINE_TCGEN05_FAST) {
     if (posix_memalign(&h->tc_maps, 128, draw_tc_maps_bytes()) != 0) return fail(h, MVG_ENOMEM, "tensor map allocation");
     cudaError_t e = draw_tc_make_maps(c, h->tc_maps);
     if (e != cudaSuccess) return fail(h, MVG_ECUDA, std::string("cuTensorMapEncodeTiled: ") + cudaGetErrorString(e));
@@ -186,7 +186,8 @@ int rebuild_pipeline(mvg_handle* h, int32_t flags, cudaEvent_t* marks /* 4 event
 }
 
 int launch_draw(mvg_handle* h) {
-  if (h->engine == MVG_ENGINE_TCGEN05) MVG_CUDA(h, launch_draw_tc(h->c, h->tc_maps, h->stream));
+  if (h->engine == MVG_ENGINE_TCGEN05 || h->engine == MVG_ENGINE_TCGEN05_FAST)
+    MVG_CUDA(h, launch_draw_tc(h->c, h->tc_maps, h->engine == MVG_ENGINE_TCGEN05_FAST, h->stream));
   else MVG_CUDA(h, launch_draw_simt(h->c, h->stream));
   h->launches += 1;
   return MVG_OK;

@@ -93,11 +93,11 @@ __global__ void __launch_bounds__(kSimtThreads, 2) k_draw_simt(const Ctx c) {
         for (int t = 0; t < CAP; ++t) da[t] = acc[t];
         c.dbg_xx[(size_t)row * c.V + v] = xx;
       }
-      epi.view(s_tp, s_vp, acc, xx, v == 0);
+      epi.view(s_tp, s_vp, acc, xx);
     }
 
     const U4 rnd = stream_block(c.seed, c.chain, kDomTable, 0, sweep, (uint64_t)(c.row_offset + rowc));
-    int choice = epi.finish(s_tm, uniform_f32_from(rnd.x));
+    int choice = epi.finish(uniform_f32_from(rnd.x));
     if (live) {
       c.choice[row] = choice;
       if (c.debug_export) c.dbg_choice[row] = choice;

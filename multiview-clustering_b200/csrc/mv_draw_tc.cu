@@ -6,15 +6,16 @@
 //   TMA producer (1 thread)   cp.async.bulk.tensor: the tile's [128 x 64] FP32 features arrive in
 //                             shared memory as two K-halves of [128 x 32] in the 128B-swizzled
 //                             K-major layout UMMA reads directly.
-//   converter (128 threads)   per row: |x|^2 and the TF32 remainder x_lo = x - trunc_tf32(x),
+//   converter (128 threads)   per row: |x|^2 and the TF32 remainder x_lo = rn_tf32(x - trunc_tf32(x)),
 //                             written to a second buffer in the same swizzled positions.
 //   MMA issuer (1 thread)     tcgen05.mma kind::tf32, M=128 N=64 K=8, three passes accumulated in
 //                             one TMEM tile:  x.m_hi + x.m_lo + x_lo.m_hi  (the hardware reads the
 //                             top 19 bits of each FP32 operand, so the raw tile serves as x_hi).
 //                             The split restores ~2^-21 relative accuracy (north_star: FP32 tolerance).
-//   epilogue (128 threads)    tcgen05.ld: thread r owns TMEM lane r = customer r: its 64 dot
-//                             products land in registers and feed RowEpilogue (mv_device.cuh) —
-//                             leave-one-out weights, log-sum-exp marginal, inverse-CDF draw.
+//   epilogue (2 x 128 threads) two warpgroups take alternate row tiles.  tcgen05.ld: thread r owns
+//                             TMEM lane r = customer r: its 64 dot products land in registers and
+//                             feed RowEpilogue (mv_device.cuh) — leave-one-out weights, log-sum-exp
+//                             marginal, inverse-CDF draw.
 //
 // The [N x 64] log-likelihood matrices never exist in memory: HBM traffic is the features once
 // (N*V*256 B) plus 8 B per customer (table in, choice out).
@@ -38,7 +39,8 @@ constexpr int kLoStages = 2;
 constexpr int kDStages = 4;                         // TMEM accumulator tiles (64 columns each)
 constexpr int kTmemCols = 256;
 constexpr int kMaxTcViews = 3;
-constexpr int kThreads = 384;                       // WG0: control, WG1: epilogue, WG2: converter
+constexpr int kThreads = 512;                       // WG0: control, WG1: converter, WG2+WG3: epilogue (alternate tiles)
+constexpr int kEpiGroups = 2;
 
 struct __align__(64) TcMaps {
   CUtensorMap x[kMaxTcViews];
@@ -139,6 +141,42 @@ struct Ring {   // stage index + mbarrier phase parity of one pipeline role
 
 }  // namespace
 
+__device__ __forceinline__ float rn_tf32(float x) {   // round to nearest TF32 (10 explicit mantissa bits)
+  uint32_t r;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+  return __uint_as_float(r);
+}
+
+// 16 consecutive accumulator columns of this thread's TMEM lane (issue only; pair with tmem_ld_wait).
+__device__ __forceinline__ void tmem_ld_16(uint32_t taddr, uint32_t (&u)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(u[0]), "=r"(u[1]), "=r"(u[2]), "=r"(u[3]), "=r"(u[4]), "=r"(u[5]), "=r"(u[6]), "=r"(u[7]),
+        "=r"(u[8]), "=r"(u[9]), "=r"(u[10]), "=r"(u[11]), "=r"(u[12]), "=r"(u[13]), "=r"(u[14]), "=r"(u[15])
+      : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// One 16-table chunk of one view: wait for its columns (already requested into `cur`), request the
+// next chunk into `nxt` so that the TMEM read overlaps this chunk's arithmetic, then run the epilogue.
+template <int BASE, bool FAST>
+__device__ __forceinline__ void epi_chunk(RowEpilogue<64, FAST>& epi, const TableParam* tpv, uint32_t taddr,
+                                          uint32_t (&cur)[16], uint32_t (&nxt)[16], const Ctx& c, int row, int v, bool live) {
+  tmem_ld_wait();
+  if (BASE + 16 < 64) tmem_ld_16(taddr + BASE + 16, nxt);
+  float ch[16];
+#pragma unroll
+  for (int t = 0; t < 16; ++t) ch[t] = __uint_as_float(cur[t]);
+  if (c.debug_export && live) {
+    float* da = c.dbg_acc + ((size_t)row * c.V + v) * 64 + BASE;
+#pragma unroll
+    for (int t = 0; t < 16; ++t) da[t] = ch[t];
+  }
+  epi.template view_chunk<BASE>(tpv, ch);
+}
+
+template <bool FAST>
 __global__ void __launch_bounds__(kThreads, 1) k_draw_tc(const Ctx c, const __grid_constant__ TcMaps maps) {
   extern __shared__ __align__(1024) unsigned char smem[];
   const uint32_t sbase = smem_u32(smem);
@@ -256,69 +294,9 @@ __global__ void __launch_bounds__(kThreads, 1) k_draw_tc(const Ctx c, const __gr
         }
     }
   } else if (warp < 8) {
-    // =========================== WG1: epilogue (thread r <-> TMEM lane r <-> customer r) ========
-    reg_inc<232>();
-    const int r = tid - 128;
-    const uint32_t lane_base = (uint32_t)((warp & 3) * 32) << 16;
-    Ring rd(kDStages);
-    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-      const int row = tile * kTileRows + r;
-      const bool live = row < c.n_rows;
-      const int rowc = live ? row : (c.n_rows - 1);
-      RowEpilogue<64> epi;
-      epi.begin(s_tm, gp, c.table_cur[rowc]);
-      for (int v = 0; v < V; ++v) {
-        mbar_wait(d_full(rd.stage), rd.phase);
-        mbar_wait(xx_full(rd.stage), rd.phase);
-        tc_fence_after();
-        float acc[64];
-        {
-          uint32_t u[64];
-          const uint32_t taddr = tmem_base + lane_base + (uint32_t)(rd.stage * 64);
-          asm volatile(
-              "tcgen05.ld.sync.aligned.32x32b.x64.b32 "
-              "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-              "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, "
-              "%32, %33, %34, %35, %36, %37, %38, %39, %40, %41, %42, %43, %44, %45, %46, %47, "
-              "%48, %49, %50, %51, %52, %53, %54, %55, %56, %57, %58, %59, %60, %61, %62, %63}, [%64];"
-              : "=r"(u[0]), "=r"(u[1]), "=r"(u[2]), "=r"(u[3]), "=r"(u[4]), "=r"(u[5]), "=r"(u[6]), "=r"(u[7]),
-                "=r"(u[8]), "=r"(u[9]), "=r"(u[10]), "=r"(u[11]), "=r"(u[12]), "=r"(u[13]), "=r"(u[14]), "=r"(u[15]),
-                "=r"(u[16]), "=r"(u[17]), "=r"(u[18]), "=r"(u[19]), "=r"(u[20]), "=r"(u[21]), "=r"(u[22]), "=r"(u[23]),
-                "=r"(u[24]), "=r"(u[25]), "=r"(u[26]), "=r"(u[27]), "=r"(u[28]), "=r"(u[29]), "=r"(u[30]), "=r"(u[31]),
-                "=r"(u[32]), "=r"(u[33]), "=r"(u[34]), "=r"(u[35]), "=r"(u[36]), "=r"(u[37]), "=r"(u[38]), "=r"(u[39]),
-                "=r"(u[40]), "=r"(u[41]), "=r"(u[42]), "=r"(u[43]), "=r"(u[44]), "=r"(u[45]), "=r"(u[46]), "=r"(u[47]),
-                "=r"(u[48]), "=r"(u[49]), "=r"(u[50]), "=r"(u[51]), "=r"(u[52]), "=r"(u[53]), "=r"(u[54]), "=r"(u[55]),
-                "=r"(u[56]), "=r"(u[57]), "=r"(u[58]), "=r"(u[59]), "=r"(u[60]), "=r"(u[61]), "=r"(u[62]), "=r"(u[63])
-              : "r"(taddr));
-          asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-#pragma unroll
-          for (int t = 0; t < 64; ++t) acc[t] = __uint_as_float(u[t]);
-        }
-        const float xx = s_xx[rd.stage * kTileRows + r];
-        tc_fence_before();
-        mbar_arrive(d_empty(rd.stage));               // accumulator tile and xx slot are free again
-        if (c.debug_export && live) {
-          float* da = c.dbg_acc + ((size_t)row * V + v) * 64;
-#pragma unroll
-          for (int t = 0; t < 64; ++t) da[t] = acc[t];
-          c.dbg_xx[(size_t)row * V + v] = xx;
-        }
-        epi.view(s_tp + v * 64, s_vp[v], acc, xx, v == 0);
-        rd.next();
-      }
-      const U4 rnd = stream_block(c.seed, c.chain, kDomTable, 0, sweep, (uint64_t)(c.row_offset + rowc));
-      const int choice = epi.finish(s_tm, uniform_f32_from(rnd.x));
-      if (live) {
-        c.choice[row] = choice;
-        if (c.debug_export) c.dbg_choice[row] = choice;
-      }
-      const unsigned births = __ballot_sync(0xffffffffu, live && choice == kNewTable);
-      if (lane == 0 && (row >> 5) < c.n_chunks) c.birthmask[row >> 5] = births;
-    }
-  } else {
-    // =========================== WG2: converter ==================================================
-    reg_dec<80>();
-    const int r = tid - 256;                           // row of the tile = 128-byte line of each half
+    // =========================== WG1: converter ==================================================
+    reg_dec<72>();
+    const int r = tid - 128;                           // row of the tile = 128-byte line of each half
     Ring rr(kRawStages), rl(kLoStages), rd(kDStages);
     const uint32_t line = (uint32_t)r * 128u;
     for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x)
@@ -333,11 +311,11 @@ __global__ void __launch_bounds__(kThreads, 1) k_draw_tc(const Ctx c, const __gr
           for (int cidx = 0; cidx < 8; ++cidx) {       // logical 16-byte chunk cidx sits at physical chunk cidx ^ (r & 7)
             const int off = ((cidx ^ (r & 7)) << 4);
             const float4 x4 = *reinterpret_cast<const float4*>(src + off);
-            float4 l4;
-            l4.x = __fadd_rn(x4.x, -__uint_as_float(__float_as_uint(x4.x) & 0xFFFFE000u));
-            l4.y = __fadd_rn(x4.y, -__uint_as_float(__float_as_uint(x4.y) & 0xFFFFE000u));
-            l4.z = __fadd_rn(x4.z, -__uint_as_float(__float_as_uint(x4.z) & 0xFFFFE000u));
-            l4.w = __fadd_rn(x4.w, -__uint_as_float(__float_as_uint(x4.w) & 0xFFFFE000u));
+            float4 l4;                                 // the hardware reads trunc_tf32(x); the remainder is exact, then rounded
+            l4.x = rn_tf32(__fadd_rn(x4.x, -__uint_as_float(__float_as_uint(x4.x) & 0xFFFFE000u)));
+            l4.y = rn_tf32(__fadd_rn(x4.y, -__uint_as_float(__float_as_uint(x4.y) & 0xFFFFE000u)));
+            l4.z = rn_tf32(__fadd_rn(x4.z, -__uint_as_float(__float_as_uint(x4.z) & 0xFFFFE000u)));
+            l4.w = rn_tf32(__fadd_rn(x4.w, -__uint_as_float(__float_as_uint(x4.w) & 0xFFFFE000u)));
             xx = __fmaf_rn(x4.x, x4.x, xx);
             xx = __fmaf_rn(x4.y, x4.y, xx);
             xx = __fmaf_rn(x4.z, x4.z, xx);
@@ -355,6 +333,50 @@ __global__ void __launch_bounds__(kThreads, 1) k_draw_tc(const Ctx c, const __gr
         mbar_arrive(xx_full(rd.stage));
         rd.next();
       }
+  } else {
+    // =========================== WG2, WG3: epilogue (thread r <-> TMEM lane r <-> customer r) ====
+    reg_inc<200>();
+    const int grp = (warp >> 2) - 2;                   // 0 or 1: this warpgroup takes tiles j = grp, grp+2, ...
+    const int r = tid & 127;
+    const uint32_t lane_base = (uint32_t)((warp & 3) * 32) << 16;
+    int j = grp;
+    for (int tile = blockIdx.x + grp * gridDim.x; tile < n_tiles; tile += kEpiGroups * gridDim.x, j += kEpiGroups) {
+      const int row = tile * kTileRows + r;
+      const bool live = row < c.n_rows;
+      const int rowc = live ? row : (c.n_rows - 1);
+      RowEpilogue<64, FAST> epi;
+      epi.begin(s_tm, gp, c.table_cur[rowc]);
+      for (int v = 0; v < V; ++v) {
+        const int idx = j * V + v;
+        const int stage = idx % kDStages;
+        const uint32_t phase = (uint32_t)(idx / kDStages) & 1u;
+        mbar_wait(d_full(stage), phase);
+        mbar_wait(xx_full(stage), phase);
+        tc_fence_after();
+        const uint32_t taddr = tmem_base + lane_base + (uint32_t)(stage * 64);
+        const float xx = s_xx[stage * kTileRows + r];
+        const TableParam* tpv = s_tp + v * 64;
+        epi.view_begin(tpv, xx);
+        if (c.debug_export && live) c.dbg_xx[(size_t)row * V + v] = xx;
+        uint32_t ua[16], ub[16];
+        tmem_ld_16(taddr, ua);
+        epi_chunk<0>(epi, tpv, taddr, ua, ub, c, row, v, live);
+        epi_chunk<16>(epi, tpv, taddr, ub, ua, c, row, v, live);
+        epi_chunk<32>(epi, tpv, taddr, ua, ub, c, row, v, live);
+        tc_fence_before();
+        mbar_arrive(d_empty(stage));                  // all four chunks are in registers: the accumulator tile and xx slot are free
+        epi_chunk<48>(epi, tpv, taddr, ub, ua, c, row, v, live);
+        epi.view_end(s_vp[v], xx);
+      }
+      const U4 rnd = stream_block(c.seed, c.chain, kDomTable, 0, sweep, (uint64_t)(c.row_offset + rowc));
+      const int choice = epi.finish(uniform_f32_from(rnd.x));
+      if (live) {
+        c.choice[row] = choice;
+        if (c.debug_export) c.dbg_choice[row] = choice;
+      }
+      const unsigned births = __ballot_sync(0xffffffffu, live && choice == kNewTable);
+      if (lane == 0 && (row >> 5) < c.n_chunks) c.birthmask[row >> 5] = births;
+    }
   }
 
   // ---- teardown ------------------------------------------------------------------------------------
@@ -408,7 +430,7 @@ cudaError_t draw_tc_make_maps(const Ctx& c, void* maps_out) {
   return cudaSuccess;
 }
 
-cudaError_t launch_draw_tc(const Ctx& c, const void* maps, cudaStream_t s) {
+cudaError_t launch_draw_tc(const Ctx& c, const void* maps, bool fast, cudaStream_t s) {
   if (c.n_rows <= 0) return cudaSuccess;
   if (!draw_tc_supported(c) || !maps) return cudaErrorInvalidValue;
   int dev = 0, sms = 148;
@@ -416,9 +438,10 @@ cudaError_t launch_draw_tc(const Ctx& c, const void* maps, cudaStream_t s) {
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   const int n_tiles = (c.n_rows + kTileRows - 1) / kTileRows;
   const int grid = n_tiles < sms ? n_tiles : sms;
-  cudaError_t e = cudaFuncSetAttribute(k_draw_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, SmemLayout::total);
+  auto kern = fast ? k_draw_tc<true> : k_draw_tc<false>;
+  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SmemLayout::total);
   if (e != cudaSuccess) return e;
-  k_draw_tc<<<grid, kThreads, SmemLayout::total, s>>>(c, *static_cast<const TcMaps*>(maps));
+  kern<<<grid, kThreads, SmemLayout::total, s>>>(c, *static_cast<const TcMaps*>(maps));
   return cudaGetLastError();
 }
 

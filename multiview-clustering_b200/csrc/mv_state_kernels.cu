@@ -704,9 +704,12 @@ __global__ void __launch_bounds__(kFinThreads, 1) k_finalize(const Ctx c, const 
     if (k >= 0) m = (float)(c.S1k[(size_t)cap * c.doff[v] + (size_t)k * D + dd] / (tau_v[v] + (double)S.n_vk[v][k]));
     c.mean[i] = m;
     if (c.mean_hi) {
-      const float hi = __uint_as_float(__float_as_uint(m) & 0xFFFFE000u);   // TF32-exact part
+      uint32_t hb, lb;                                            // TF32 split, both parts rounded to nearest
+      asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(hb) : "f"(m));
+      const float hi = __uint_as_float(hb);
+      asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(lb) : "f"(__fadd_rn(m, -hi)));
       c.mean_hi[i] = hi;
-      c.mean_lo[i] = __fadd_rn(m, -hi);
+      c.mean_lo[i] = __uint_as_float(lb);
     }
   }
   __syncthreads();

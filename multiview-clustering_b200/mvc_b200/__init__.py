@@ -19,7 +19,7 @@ import numpy as np
 _HERE = Path(__file__).resolve().parent
 LIB_PATH = _HERE / "libmvg_b200.so"
 
-ENGINE_AUTO, ENGINE_SIMT, ENGINE_TCGEN05 = 0, 1, 2
+ENGINE_AUTO, ENGINE_SIMT, ENGINE_TCGEN05, ENGINE_TCGEN05_FAST = 0, 1, 2, 3
 NEW_TABLE = -1
 
 _i32p = C.POINTER(C.c_int32)

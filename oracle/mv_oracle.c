@@ -560,7 +560,14 @@ float mvo_log2m(float s) {
   int32_t e = (int32_t)(b >> 23) - 127;
   float m = f32_from_bits((b & 0x007FFFFFu) | 0x3F800000u);
   if (m > 1.41421354f) { m = m * 0.5f; e += 1; }
-  float t = (m - 1.0f) / (m + 1.0f);
+  /* the quotient as the device forms it: linear seed, three Newton steps, one residual correction */
+  float num = m - 1.0f, den = m + 1.0f;
+  float y = fmaf(-0.24264069f, den, 0.99258476f);
+  y = fmaf(y, fmaf(-den, y, 1.0f), y);
+  y = fmaf(y, fmaf(-den, y, 1.0f), y);
+  y = fmaf(y, fmaf(-den, y, 1.0f), y);
+  float t = num * y;
+  t = fmaf(fmaf(-t, den, num), y, t);
   float t2 = t * t;
   float q = 0x1.c71c72p-4f;             /* 1/9 */
   q = fmaf(q, t2, 0x1.24924ap-3f);      /* 1/7 */
@@ -583,58 +590,87 @@ void mvo_stageA_f32(const float* x, int D, const float* m, int cap, float* acc, 
   }
 }
 
-int mvo_stageB_f32(const mvo_params_f32* p, const float* acc, const float* xx, int t0, float uf,
-                   float* lw_out) {
+/* Restates RowEpilogue<CAP,false> of multiview-clustering_b200/csrc/mv_device.cuh operation by
+ * operation: begin (table masses), view (leave-one-out log2 f, 2-way max, 4-way partial sums of the
+ * dish marginal), finish (4-way partial total, sequential prefix count).  margin_out, if not NULL,
+ * receives the distance of u*total to the nearest CDF edge relative to total (how close the draw
+ * was to flipping) — used to grade engines whose weights are tolerance-level. */
+int mvo_stageB_f32_ex(const mvo_params_f32* p, const float* acc, const float* xx, int t0, float uf,
+                      float* lw_out, float* margin_out) {
   const int V = p->V, cap = p->cap;
   float* lw = (float*)malloc(sizeof(float) * (size_t)cap);
   float* term = (float*)malloc(sizeof(float) * (size_t)cap);
   const int single = p->single[t0];
   float lnew = single ? p->LMN[1] : p->LMN[0];
+  for (int t = 0; t < cap; ++t) lw[t] = (t == t0) ? p->LM1[t0] : p->LM[t];
   for (int v = 0; v < V; ++v) {
     const size_t o = (size_t)v * cap;
     const int k0 = p->dish[o + t0];
+    const float A1r = p->A1[o + t0], C1r = p->C1[o + t0];
     const float nxx = -xx[v];
-    for (int t = 0; t < cap; ++t) {
-      float e = fmaf(2.0f, acc[o + t], nxx);
-      int same = (p->dish[o + t] == k0);
-      float L = same ? fmaf(p->A1[o + t], e, p->C1[o + t]) : fmaf(p->A[o + t], e, p->C[o + t]);
-      lw[t] = (v == 0) ? L : lw[t] + L;
-      float w = (same && single) ? p->W1[o + t] : p->W[o + t];
-      term[t] = L + w;
+    float mx = MVO_MASKED, s = 0.0f;
+    for (int base = 0; base < cap; base += 16) {           /* kEpiChunk = 16 tables at a time */
+      float cp[2] = {MVO_MASKED, MVO_MASKED};
+      for (int j = 0; j < 16; ++j) {
+        const int t = base + j;
+        float e = fmaf(2.0f, acc[o + t], nxx);
+        int same = (p->dish[o + t] == k0);
+        float L = same ? fmaf(A1r, e, C1r) : fmaf(p->A[o + t], e, p->C[o + t]);
+        lw[t] = lw[t] + L;
+        float w = (same && single) ? p->W1[o + t] : p->W[o + t];
+        term[t] = L + w;
+        cp[j & 1] = fmaxf(cp[j & 1], term[t]);
+      }
+      float mn = fmaxf(mx, fmaxf(cp[0], cp[1]));
+      s = s * mvo_exp2m(mx - mn);
+      mx = mn;
+      float sp[4] = {0.0f, 0.0f, 0.0f, 0.0f};
+      for (int j = 0; j < 16; ++j) sp[j & 3] = sp[j & 3] + mvo_exp2m(term[base + j] - mn);
+      s = s + ((sp[0] + sp[1]) + (sp[2] + sp[3]));
     }
     float Lnew = fmaf(-p->AN[v], xx[v], p->CN[v]);
     float termnew = Lnew + ((single && p->lone[o + t0]) ? p->WN[2 * v + 1] : p->WN[2 * v]);
-    float mx = termnew;
-    for (int t = 0; t < cap; ++t) mx = fmaxf(mx, term[t]);
-    float s = mvo_exp2m(termnew - mx);
-    for (int t = 0; t < cap; ++t) s = s + mvo_exp2m(term[t] - mx);
-    float logmarg = (mx + mvo_log2m(s)) - (single ? p->LD[2 * v + 1] : p->LD[2 * v]);
+    float mn = fmaxf(mx, termnew);
+    s = s * mvo_exp2m(mx - mn);
+    s = s + mvo_exp2m(termnew - mn);
+    float logmarg = (mn + mvo_log2m(s)) - (single ? p->LD[2 * v + 1] : p->LD[2 * v]);
     lnew = lnew + logmarg;
   }
-  for (int t = 0; t < cap; ++t) lw[t] = lw[t] + ((t == t0) ? p->LM1[t] : p->LM[t]);
-  float M = lnew;
-  for (int t = 0; t < cap; ++t) M = fmaxf(M, lw[t]);
+  float Mp[2] = {lnew, MVO_MASKED};
+  for (int t = 0; t < cap; ++t) Mp[t & 1] = fmaxf(Mp[t & 1], lw[t]);
+  float M = fmaxf(Mp[0], Mp[1]);
   if (lw_out) { memcpy(lw_out, lw, sizeof(float) * (size_t)cap); lw_out[cap] = lnew; }
+  if (margin_out) *margin_out = 1.0f;
   int choice = MVO_NEW;
   if (!(M > -1.0e29f)) {
     choice = t0;
   } else {
-    float total = mvo_exp2m(lnew - M);
-    for (int t = 0; t < cap; ++t) { term[t] = mvo_exp2m(lw[t] - M); total = total + term[t]; }
+    float qp[4] = {0.0f, 0.0f, 0.0f, 0.0f};
+    for (int t = 0; t < cap; ++t) { term[t] = mvo_exp2m(lw[t] - M); qp[t & 3] = qp[t & 3] + term[t]; }
+    float total = ((qp[0] + qp[1]) + (qp[2] + qp[3])) + mvo_exp2m(lnew - M);
     float target = uf * total;
-    float cum = 0.0f;
-    int found = 0;
+    float cum = 0.0f, margin = 1.0f;
+    int cnt = 0;
     for (int t = 0; t < cap; ++t) {
       cum = cum + term[t];
-      if (!found && target < cum) { choice = t; found = 1; }
+      cnt += (target < cum) ? 0 : 1;
+      float dist = fabsf(target - cum) / total;
+      if (dist < margin) margin = dist;
     }
-    if (!found && !(lnew > -1.0e29f)) {
+    if (margin_out) *margin_out = margin;
+    choice = (cnt < cap) ? cnt : MVO_NEW;
+    if (cnt >= cap && !(lnew > -1.0e29f)) {
       choice = t0;
-      for (int t = 0; t < cap; ++t) if (lw[t] > -1.0e29f) choice = t;
+      for (int t = 0; t < cap; ++t) if (term[t] > 1.0e-30f) choice = t;
     }
   }
   free(lw); free(term);
   return choice;
+}
+
+int mvo_stageB_f32(const mvo_params_f32* p, const float* acc, const float* xx, int t0, float uf,
+                   float* lw_out) {
+  return mvo_stageB_f32_ex(p, acc, xx, t0, uf, lw_out, NULL);
 }
 
 int mvo_make_params(const mvo_state* s, int32_t* dish, float* A, float* C, float* A1, float* C1,

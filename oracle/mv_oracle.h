@@ -134,6 +134,9 @@ void mvo_stageA_f32(const float* x, int D, const float* m, int cap, float* acc, 
  * current table t0 and uniform uf, reproduce the device's choice bit for bit. */
 int mvo_stageB_f32(const mvo_params_f32* p, const float* acc, const float* xx, int t0, float uf,
                    float* lw_out /* cap+1 or NULL */);
+/* Same, also reporting how close u*total came to a CDF edge (relative to total). */
+int mvo_stageB_f32_ex(const mvo_params_f32* p, const float* acc, const float* xx, int t0, float uf,
+                      float* lw_out, float* margin_out);
 float mvo_exp2m(float d);
 float mvo_log2m(float s);
 

@@ -104,6 +104,7 @@ def lib():
         L.mvo_log2m.argtypes = [C.c_float]
         L.mvo_stageA_f32.argtypes = [_f32p, C.c_int, _f32p, C.c_int, _f32p, _f32p]
         L.mvo_stageB_f32.argtypes = [C.POINTER(_MvoParams), _f32p, _f32p, C.c_int, C.c_float, _f32p]
+        L.mvo_stageB_f32_ex.argtypes = [C.POINTER(_MvoParams), _f32p, _f32p, C.c_int, C.c_float, _f32p, _f32p]
         L.mvo_make_params.argtypes = ([C.POINTER(_MvoState), _i32p] + [_f32p] * 6 + [_i32p] + [_f32p] * 6
                                       + [_i32p, _f32p, C.POINTER(_f32p)])
         _lib = L
@@ -311,6 +312,16 @@ def stageB_f32(pstruct, acc, xx, t0, uf, want_lw=False):
     ch = lib().mvo_stageB_f32(C.byref(pstruct), _ptr(acc, _f32p), _ptr(xx, _f32p), int(t0), C.c_float(float(uf)),
                               _ptr(lw, _f32p) if want_lw else None)
     return (ch, lw) if want_lw else ch
+
+
+def stageB_f32_margin(pstruct, acc, xx, t0, uf):
+    """Stage B plus the relative distance of the draw to the nearest CDF edge."""
+    acc = np.ascontiguousarray(acc, np.float32)
+    xx = np.ascontiguousarray(xx, np.float32)
+    mg = C.c_float()
+    ch = lib().mvo_stageB_f32_ex(C.byref(pstruct), _ptr(acc, _f32p), _ptr(xx, _f32p), int(t0), C.c_float(float(uf)),
+                                 None, C.byref(mg))
+    return ch, mg.value
 
 
 def mirror_draw_rows(state: OracleState, P=None, acc=None, xx=None):

@@ -59,7 +59,7 @@ def _check_params(po, o, P):
         np.testing.assert_allclose(P["m"][v], Q["m"][v], rtol=2e-5, atol=1e-6)
 
 
-def _one_sweep_parity(po, s, views, cap, seed, do_hyper, simt_bit_exact=True):
+def _one_sweep_parity(po, s, views, cap, seed, do_hyper, simt_bit_exact=True, fast_weights=False):
     """Compare ONE device sweep with the oracle started from the device's own pre-sweep state."""
     pre = s.get_state()
     P = s.get_params()
@@ -72,6 +72,7 @@ def _one_sweep_parity(po, s, views, cap, seed, do_hyper, simt_bit_exact=True):
     ps = po.params_struct(P)
     L = po.lib()
     worst = 0.0
+    flips = 0
     mm = [np.sum(P["m"][v].astype(np.float64) ** 2, axis=1) for v in range(o.V)]
     for i in range(n):
         if simt_bit_exact:
@@ -80,7 +81,14 @@ def _one_sweep_parity(po, s, views, cap, seed, do_hyper, simt_bit_exact=True):
                 assert np.array_equal(a, acc[i, v]) and q == xx[i, v], (i, v)
         u = L.mvo_uf(seed, 0, 0, 0, pre["sweep"], i)
         ch, lw32 = po.stageB_f32(ps, acc[i], xx[i], pre["table_of"][i], u, want_lw=True)
-        assert ch == raw[i], (i, ch, raw[i])                    # integer draw: bit-exact
+        if not fast_weights:
+            assert ch == raw[i], (i, ch, raw[i])                # integer draw: bit-exact
+        elif ch != raw[i]:
+            # MUFU weights (<= 2 ulp each): a draw may differ from the mirrored one only when u*total
+            # fell within rounding distance of a CDF edge, and then only to the neighbouring option
+            _, margin = po.stageB_f32_margin(ps, acc[i], xx[i], pre["table_of"][i], u)
+            assert margin < 1e-5, (i, ch, raw[i], margin)
+            flips += 1
         if i % 7 == 0:
             lw64 = o.row_logweights(i) / np.log(2.0)
             ok = np.isfinite(lw64)
@@ -94,6 +102,7 @@ def _one_sweep_parity(po, s, views, cap, seed, do_hyper, simt_bit_exact=True):
             denom = np.maximum(np.maximum(1.0, np.abs(lw64[ok])), scale[ok])
             worst = max(worst, float(np.max(np.abs(lw32[ok] - lw64[ok]) / denom)))
     assert worst < RTOL_LOGLIK, worst
+    assert flips <= max(2, n // 2000), flips
     # FP64 restatement draws agree except at CDF edges
     agree = float((o.draw_rows(threads=4) == raw).mean())
     assert agree > 0.99, agree
@@ -222,11 +231,11 @@ def test_run_gibbs_posterior_summaries_match_reference(oracle):
 # tcgen05 engine (MVG_ENGINE_TCGEN05): stage A runs on the tensor cores (3-pass TF32 split), so the
 # dot products are tolerance-level; everything downstream of them is bit-exact against the mirror.
 # ---------------------------------------------------------------------------------------------
-@pytest.mark.parametrize("n,k_true", [(900, 6), (128 * 148 + 77, 40)])
-def test_tcgen05_engine_parity(oracle, n, k_true):
+@pytest.mark.parametrize("n,k_true,engine", [(900, 6, 2), (128 * 148 + 77, 40, 2), (128 * 148 * 2 + 5, 40, 3), (700, 5, 3)])
+def test_tcgen05_engine_parity(oracle, n, k_true, engine):
     dims, cap = [64, 64, 64], 64
     views, z = make_mixture(n, dims, k_true, seed=11)
-    s = _mk_sampler(views, cap, seed=123, engine=2)
+    s = _mk_sampler(views, cap, seed=123, engine=engine)
     rng = np.random.default_rng(2)
     tab = np.where(rng.random(n) < 0.15, rng.integers(0, k_true, n), z).astype(np.int32)
     tab[:3] = [k_true + 1, k_true + 2, k_true + 3]                   # three customers alone at their tables
@@ -236,12 +245,13 @@ def test_tcgen05_engine_parity(oracle, n, k_true):
     s.set_state(tab, dish, np.full(3, 1.0), np.full(3, 0.5), np.full(3, 0.9), 1.0, 0.6, sweep=3)
     for it in range(3):
         P = s.get_params()
-        _one_sweep_parity(oracle, s, views, cap, 123, do_hyper=(it % 2 == 0), simt_bit_exact=False)
+        _one_sweep_parity(oracle, s, views, cap, 123, do_hyper=(it % 2 == 0), simt_bit_exact=False,
+                          fast_weights=(engine == 3))
         acc, xx, _ = s.get_debug_rows()
         for v in range(3):                                           # stage A against FP64
             x64, m64 = views[v].astype(np.float64), P["m"][v].astype(np.float64)
             ref = x64 @ m64.T
             bound = np.abs(x64) @ np.abs(m64).T
-            assert np.max(np.abs(acc[:, v, :] - ref) / (bound + 1e-30)) < 2.0 ** -18
+            assert np.max(np.abs(acc[:, v, :] - ref) / (bound + 1e-30)) < 2.0 ** -18     # measured 1.9e-6: the tensor core truncates when it aligns addends
             np.testing.assert_allclose(xx[:, v], (x64 * x64).sum(1), rtol=1e-6)
     s.close()
