@@ -1,22 +1,25 @@
-// mv_draw_tc.cu — likelihood + draw on the 5th-generation tensor cores (engine MVG_ENGINE_TCGEN05).
+// mv_draw_tc.cu — likelihood + draw on the 5th-generation tensor cores (engines MVG_ENGINE_TCGEN05*).
 //
 // Shape: cap = 64 table slots, every view dense with dim 64, at most 3 views (BASELINE config C3).
 // One persistent CTA per SM walks row tiles of 128 customers.  For every (tile, view):
 //
-//   TMA producer (1 thread)   cp.async.bulk.tensor: the tile's [128 x 64] FP32 features arrive in
-//                             shared memory as two K-halves of [128 x 32] in the 128B-swizzled
-//                             K-major layout UMMA reads directly.
-//   converter (128 threads)   per row: |x|^2 and the TF32 remainder x_lo = rn_tf32(x - trunc_tf32(x)),
-//                             written to a second buffer in the same swizzled positions.
-//   MMA issuer (1 thread)     tcgen05.mma kind::tf32, M=128 N=64 K=8, three passes accumulated in
-//                             one TMEM tile:  x.m_hi + x.m_lo + x_lo.m_hi  (the hardware reads the
-//                             top 19 bits of each FP32 operand, so the raw tile serves as x_hi).
-//                             The split restores ~2^-21 relative accuracy (north_star: FP32 tolerance).
+//   TMA producer (1 thread)    cp.async.bulk.tensor: the tile's [128 x 64] FP32 features arrive in
+//                              shared memory as two K-halves of [128 x 32] in the 128B-swizzled
+//                              K-major layout UMMA reads directly (7-deep ring, 112 KB in flight).
+//   converters (2 x 128 thr.)  one warpgroup per K-half; thread r owns customer r: partial |x|^2 and
+//                              the TF32 remainder x_lo = rn_tf32(x - trunc_tf32(x)), written with
+//                              tcgen05.st into TMEM lane r (the remainder tile never touches shared memory).
+//   MMA issuer (1 thread)      tcgen05.mma kind::tf32, M=128 N=64 K=8, three passes accumulated in
+//                              one TMEM tile:  x.m_hi + x.m_lo (A = the raw tile in shared memory; the
+//                              hardware reads the top 19 bits of each FP32 word, so it serves as
+//                              x_hi) and x_lo.m_hi (A = the remainder tile in TMEM).  The split
+//                              restores ~2^-19 relative accuracy (north_star: FP32 tolerance).
 //   epilogue (2 x 128 threads) two warpgroups take alternate row tiles.  tcgen05.ld: thread r owns
-//                             TMEM lane r = customer r: its 64 dot products land in registers and
-//                             feed RowEpilogue (mv_device.cuh) — leave-one-out weights, log-sum-exp
-//                             marginal, inverse-CDF draw.
+//                              TMEM lane r = customer r: its 64 dot products arrive 16 at a time and
+//                              feed RowEpilogue (mv_device.cuh) — leave-one-out weights, streaming
+//                              log-sum-exp marginal, inverse-CDF draw.
 //
+// TMEM (512 columns): [0,256) four accumulator tiles, [256,512) four remainder tiles.
 // The [N x 64] log-likelihood matrices never exist in memory: HBM traffic is the features once
 // (N*V*256 B) plus 8 B per customer (table in, choice out).
 //
@@ -34,12 +37,13 @@ constexpr int kTileRows = 128;
 constexpr int kHalfCols = 32;                       // floats per 128-byte swizzled row
 constexpr int kHalfBytes = kTileRows * 128;         // 16 KB: one K-half of an A tile
 constexpr int kBHalfBytes = 64 * 128;               // 8 KB: one K-half of a B matrix (64 tables)
-constexpr int kRawStages = 5;                       // K-halves of raw features in flight
-constexpr int kLoStages = 2;
+constexpr int kRawStages = 7;                       // K-halves of raw features in flight
+constexpr int kLoStages = 4;                        // TMEM remainder tiles (64 columns each)
 constexpr int kDStages = 4;                         // TMEM accumulator tiles (64 columns each)
-constexpr int kTmemCols = 256;
+constexpr int kTmemCols = 512;
+constexpr int kLoCol0 = kDStages * 64;              // first TMEM column of the remainder tiles
 constexpr int kMaxTcViews = 3;
-constexpr int kThreads = 512;                       // WG0: control, WG1: converter, WG2+WG3: epilogue (alternate tiles)
+constexpr int kThreads = 640;                       // WG0: control, WG1+WG2: converters (one per K-half), WG3+WG4: epilogue (alternate tiles)
 constexpr int kEpiGroups = 2;
 
 struct __align__(64) TcMaps {
@@ -52,12 +56,11 @@ struct __align__(64) TcMaps {
 struct SmemLayout {
   static constexpr int b_off = 0;                                            // [V][hi,lo][2 halves][8 KB]
   static constexpr int raw_off = b_off + kMaxTcViews * 4 * kBHalfBytes;      // 96 KB
-  static constexpr int lo_off = raw_off + kRawStages * kHalfBytes;           // +80 KB
-  static constexpr int tp_off = lo_off + kLoStages * kHalfBytes;             // +32 KB
+  static constexpr int tp_off = raw_off + kRawStages * kHalfBytes;           // +112 KB
   static constexpr int tm_off = tp_off + kMaxTcViews * 64 * (int)sizeof(TableParam);
   static constexpr int vp_off = tm_off + 64 * (int)sizeof(TableMass);
   static constexpr int xx_off = vp_off + kMaxTcViews * (int)sizeof(ViewParam);
-  static constexpr int bar_off = xx_off + kDStages * kTileRows * (int)sizeof(float);
+  static constexpr int bar_off = xx_off + kDStages * 2 * kTileRows * (int)sizeof(float);   // [stage][K-half][row]
   static constexpr int n_bars = 2 * kRawStages + 2 * kLoStages + 3 * kDStages + 1;
   static constexpr int misc_off = bar_off + n_bars * 8;
   static constexpr int total = misc_off + 64;
@@ -108,6 +111,25 @@ __device__ __forceinline__ void umma_tf32(uint32_t d_tmem, uint64_t a_desc, uint
       "}\n" ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
       : "memory");
 }
+// Same with the A operand in tensor memory: lane = row, one 32-bit column per K element.
+__device__ __forceinline__ void umma_tf32_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t"
+      "}\n" ::"r"(d_tmem), "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_st_16(uint32_t taddr, const uint32_t (&u)[16]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], "
+      "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};"
+      ::"r"(taddr), "r"(u[0]), "r"(u[1]), "r"(u[2]), "r"(u[3]), "r"(u[4]), "r"(u[5]), "r"(u[6]), "r"(u[7]),
+        "r"(u[8]), "r"(u[9]), "r"(u[10]), "r"(u[11]), "r"(u[12]), "r"(u[13]), "r"(u[14]), "r"(u[15])
+      : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 __device__ __forceinline__ void umma_commit(uint32_t bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
 }
@@ -140,12 +162,6 @@ struct Ring {   // stage index + mbarrier phase parity of one pipeline role
 };
 
 }  // namespace
-
-__device__ __forceinline__ float rn_tf32(float x) {   // round to nearest TF32 (10 explicit mantissa bits)
-  uint32_t r;
-  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
-  return __uint_as_float(r);
-}
 
 // 16 consecutive accumulator columns of this thread's TMEM lane (issue only; pair with tmem_ld_wait).
 __device__ __forceinline__ void tmem_ld_16(uint32_t taddr, uint32_t (&u)[16]) {
@@ -186,7 +202,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_draw_tc(const Ctx c, const __gr
   TableParam* s_tp = reinterpret_cast<TableParam*>(smem + SmemLayout::tp_off);
   TableMass* s_tm = reinterpret_cast<TableMass*>(smem + SmemLayout::tm_off);
   ViewParam* s_vp = reinterpret_cast<ViewParam*>(smem + SmemLayout::vp_off);
-  float* s_xx = reinterpret_cast<float*>(smem + SmemLayout::xx_off);
+  float* s_xx = reinterpret_cast<float*>(smem + SmemLayout::xx_off);             // [stage][K-half][row]
   uint32_t* s_misc = reinterpret_cast<uint32_t*>(smem + SmemLayout::misc_off);   // [0] TMEM base, [1] sweep, [2..3] GlobalParam floats
 
   // barrier addresses
@@ -209,9 +225,9 @@ __global__ void __launch_bounds__(kThreads, 1) k_draw_tc(const Ctx c, const __gr
     s_misc[1] = g.sweep;
     s_misc[2] = __float_as_uint(g.LMN0);
     s_misc[3] = __float_as_uint(g.LMN1);
-    for (int s = 0; s < kRawStages; ++s) { mbar_init(raw_full(s), 1); mbar_init(raw_empty(s), 129); }   // 128 converter threads + the MMA commit
-    for (int s = 0; s < kLoStages; ++s) { mbar_init(lo_full(s), 128); mbar_init(lo_empty(s), 1); }
-    for (int s = 0; s < kDStages; ++s) { mbar_init(d_full(s), 1); mbar_init(d_empty(s), 128); mbar_init(xx_full(s), 128); }
+    for (int s = 0; s < kRawStages; ++s) { mbar_init(raw_full(s), 1); mbar_init(raw_empty(s), 129); }   // one converter warpgroup + the MMA commit
+    for (int s = 0; s < kLoStages; ++s) { mbar_init(lo_full(s), 256); mbar_init(lo_empty(s), 1); }      // both converter warpgroups
+    for (int s = 0; s < kDStages; ++s) { mbar_init(d_full(s), 1); mbar_init(d_empty(s), 128); mbar_init(xx_full(s), 256); }
     mbar_init(b_full, 1);
     fence_barrier_init();
   }
@@ -232,7 +248,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_draw_tc(const Ctx c, const __gr
 
   if (warp < 4) {
     // =========================== WG0: control ==================================================
-    reg_dec<40>();
+    reg_dec<24>();
     if (warp == 0 && lane == 0) {
       // ---- TMA producer ----
       mbar_expect_tx(b_full, (uint32_t)(V * 4 * kBHalfBytes));
@@ -244,6 +260,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_draw_tc(const Ctx c, const __gr
       Ring r(kRawStages);
       for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x)
         for (int v = 0; v < V; ++v)
+#pragma unroll 1
           for (int h = 0; h < 2; ++h) {
             mbar_wait(raw_empty(r.stage), r.phase ^ 1u);
             mbar_expect_tx(raw_full(r.stage), kHalfBytes);
@@ -263,10 +280,12 @@ __global__ void __launch_bounds__(kThreads, 1) k_draw_tc(const Ctx c, const __gr
           const uint32_t d_tmem = tmem_base + (uint32_t)(rd.stage * 64);
           uint32_t accumulate = 0;
           // passes 1+2 on the raw halves: x_hi . m_hi  and  x_hi . m_lo
+#pragma unroll 1
           for (int h = 0; h < 2; ++h) {
             mbar_wait(raw_full(rr.stage), rr.phase);
             tc_fence_after();
             const uint32_t a_addr = sbase + SmemLayout::raw_off + rr.stage * kHalfBytes;
+#pragma unroll
             for (int part = 0; part < 2; ++part) {
               const uint32_t b_addr = sbase + SmemLayout::b_off + ((v * 2 + part) * 2 + h) * kBHalfBytes;
 #pragma unroll
@@ -278,65 +297,74 @@ __global__ void __launch_bounds__(kThreads, 1) k_draw_tc(const Ctx c, const __gr
             umma_commit(raw_empty(rr.stage));         // this raw half is free once these MMAs retire
             rr.next();
           }
-          // pass 3 on the remainder halves: x_lo . m_hi
+          // pass 3 from tensor memory: x_lo . m_hi
+          mbar_wait(lo_full(rl.stage), rl.phase);
+          tc_fence_after();
+          const uint32_t a_tmem = tmem_base + (uint32_t)(kLoCol0 + rl.stage * 64);
+#pragma unroll
           for (int h = 0; h < 2; ++h) {
-            mbar_wait(lo_full(rl.stage), rl.phase);
-            tc_fence_after();
-            const uint32_t a_addr = sbase + SmemLayout::lo_off + rl.stage * kHalfBytes;
             const uint32_t b_addr = sbase + SmemLayout::b_off + ((v * 2 + 0) * 2 + h) * kBHalfBytes;
 #pragma unroll
-            for (int k = 0; k < 4; ++k) umma_tf32(d_tmem, make_desc(a_addr + k * 32), make_desc(b_addr + k * 32), kIdesc, 1);
-            umma_commit(lo_empty(rl.stage));
-            rl.next();
+            for (int k = 0; k < 4; ++k)
+              umma_tf32_ts(d_tmem, a_tmem + (uint32_t)(h * 32 + k * 8), make_desc(b_addr + k * 32), kIdesc, 1);
           }
+          umma_commit(lo_empty(rl.stage));
           umma_commit(d_full(rd.stage));
+          rl.next();
           rd.next();
         }
     }
-  } else if (warp < 8) {
-    // =========================== WG1: converter ==================================================
-    reg_dec<72>();
-    const int r = tid - 128;                           // row of the tile = 128-byte line of each half
-    Ring rr(kRawStages), rl(kLoStages), rd(kDStages);
+  } else if (warp < 12) {
+    // =========================== WG1, WG2: converters, one K-half each ===========================
+    reg_dec<56>();
+    const int h = (warp >> 2) - 1;                     // K-half of this warpgroup
+    const int r = tid & 127;                           // row of the tile = 128-byte line of the half = TMEM lane
+    const uint32_t lane_base = (uint32_t)((warp & 3) * 32) << 16;
     const uint32_t line = (uint32_t)r * 128u;
+    int i = 0;                                         // tile-view counter of this CTA
     for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x)
-      for (int v = 0; v < V; ++v) {
+      for (int v = 0; v < V; ++v, ++i) {
+        const int rs = (2 * i + h) % kRawStages;
+        const uint32_t rph = (uint32_t)((2 * i + h) / kRawStages) & 1u;
+        const int ls = i % kLoStages;                  // == accumulator stage (kLoStages == kDStages)
+        const uint32_t lph = (uint32_t)(i / kLoStages) & 1u;
+        mbar_wait(raw_full(rs), rph);
+        mbar_wait(lo_empty(ls), lph ^ 1u);
+        tc_fence_after();
+        const unsigned char* src = smem + SmemLayout::raw_off + rs * kHalfBytes + line;
+        const uint32_t lo_addr = tmem_base + lane_base + (uint32_t)(kLoCol0 + ls * 64 + h * 32);
         float xx = 0.0f;
-        for (int h = 0; h < 2; ++h) {
-          mbar_wait(raw_full(rr.stage), rr.phase);
-          mbar_wait(lo_empty(rl.stage), rl.phase ^ 1u);
-          const unsigned char* src = smem + SmemLayout::raw_off + rr.stage * kHalfBytes + line;
-          unsigned char* dst = smem + SmemLayout::lo_off + rl.stage * kHalfBytes + line;
 #pragma unroll
-          for (int cidx = 0; cidx < 8; ++cidx) {       // logical 16-byte chunk cidx sits at physical chunk cidx ^ (r & 7)
-            const int off = ((cidx ^ (r & 7)) << 4);
-            const float4 x4 = *reinterpret_cast<const float4*>(src + off);
-            float4 l4;                                 // the hardware reads trunc_tf32(x); the remainder is exact, then rounded
-            l4.x = rn_tf32(__fadd_rn(x4.x, -__uint_as_float(__float_as_uint(x4.x) & 0xFFFFE000u)));
-            l4.y = rn_tf32(__fadd_rn(x4.y, -__uint_as_float(__float_as_uint(x4.y) & 0xFFFFE000u)));
-            l4.z = rn_tf32(__fadd_rn(x4.z, -__uint_as_float(__float_as_uint(x4.z) & 0xFFFFE000u)));
-            l4.w = rn_tf32(__fadd_rn(x4.w, -__uint_as_float(__float_as_uint(x4.w) & 0xFFFFE000u)));
-            xx = __fmaf_rn(x4.x, x4.x, xx);
-            xx = __fmaf_rn(x4.y, x4.y, xx);
-            xx = __fmaf_rn(x4.z, x4.z, xx);
-            xx = __fmaf_rn(x4.w, x4.w, xx);
-            *reinterpret_cast<float4*>(dst + off) = l4;
+        for (int half16 = 0; half16 < 2; ++half16) {
+          uint32_t lo[16];
+#pragma unroll
+          for (int cc = 0; cc < 4; ++cc) {             // logical 16-byte chunk cidx sits at physical chunk cidx ^ (r & 7)
+            const int cidx = half16 * 4 + cc;
+            const float4 x4 = *reinterpret_cast<const float4*>(src + ((cidx ^ (r & 7)) << 4));
+            const float xs[4] = {x4.x, x4.y, x4.z, x4.w};
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              // the tensor core reads trunc_tf32(x); the remainder is exact in FP32 and is rounded to the
+              // nearest TF32 by adding half a TF32 ulp before the hardware drops the low 13 bits
+              const float rem = __fadd_rn(xs[e], -__uint_as_float(__float_as_uint(xs[e]) & 0xFFFFE000u));
+              lo[cc * 4 + e] = __float_as_uint(rem) + 0x1000u;
+              xx = __fmaf_rn(xs[e], xs[e], xx);
+            }
           }
-          fence_proxy_async();                         // generic-proxy stores -> visible to the MMA (async proxy)
-          mbar_arrive(lo_full(rl.stage));
-          mbar_arrive(raw_empty(rr.stage));            // this thread no longer reads the raw half
-          rr.next();
-          rl.next();
+          tmem_st_16(lo_addr + (uint32_t)(half16 * 16), lo);
         }
-        mbar_wait(d_empty(rd.stage), rd.phase ^ 1u);   // the epilogue has consumed this xx slot
-        s_xx[rd.stage * kTileRows + r] = xx;
-        mbar_arrive(xx_full(rd.stage));
-        rd.next();
+        mbar_arrive(raw_empty(rs));                    // this thread no longer reads the raw half
+        tmem_st_wait();
+        tc_fence_before();
+        mbar_arrive(lo_full(ls));
+        mbar_wait(d_empty(ls), lph ^ 1u);              // the epilogue has consumed this xx slot
+        s_xx[(ls * 2 + h) * kTileRows + r] = xx;
+        mbar_arrive(xx_full(ls));
       }
   } else {
-    // =========================== WG2, WG3: epilogue (thread r <-> TMEM lane r <-> customer r) ====
-    reg_inc<200>();
-    const int grp = (warp >> 2) - 2;                   // 0 or 1: this warpgroup takes tiles j = grp, grp+2, ...
+    // =========================== WG3, WG4: epilogue (thread r <-> TMEM lane r <-> customer r) ====
+    reg_inc<168>();   // pool: 640 threads x 96 registers; 24 + 56 + 56 + 168 + 168 = 472 <= 480 per thread-slot
+    const int grp = (warp >> 2) - 3;                   // 0 or 1: this warpgroup takes tiles j = grp, grp+2, ...
     const int r = tid & 127;
     const uint32_t lane_base = (uint32_t)((warp & 3) * 32) << 16;
     int j = grp;
@@ -354,7 +382,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_draw_tc(const Ctx c, const __gr
         mbar_wait(xx_full(stage), phase);
         tc_fence_after();
         const uint32_t taddr = tmem_base + lane_base + (uint32_t)(stage * 64);
-        const float xx = s_xx[stage * kTileRows + r];
+        const float xx = __fadd_rn(s_xx[(stage * 2 + 0) * kTileRows + r], s_xx[(stage * 2 + 1) * kTileRows + r]);
         const TableParam* tpv = s_tp + v * 64;
         epi.view_begin(tpv, xx);
         if (c.debug_export && live) c.dbg_xx[(size_t)row * V + v] = xx;
