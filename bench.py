@@ -50,6 +50,7 @@ def parse():
     ap.add_argument("--rows", type=int, default=N_ROWS, help="total customers (default: the named config)")
     ap.add_argument("--engine", type=int, default=0, help="0 auto, 1 CUDA-core, 2 tcgen05")
     ap.add_argument("--no-hyper", action="store_true")
+    ap.add_argument("--role-profile", action="store_true", help="print the tcgen05 kernel's per-role wait cycles (debug)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-rows", type=int, default=0, help="rows of the CPU sample (0: sized for ~15 s)")
@@ -202,7 +203,7 @@ def main():
 
     def make_sampler(attach):
         s = mvc_b200.Sampler(n_local, DIMS, cap=CAP, seed=SEED, device=local_rank, engine=args.engine, rank=rank,
-                             world=world, row_offset=lo, n_rows_global=n_total)
+                             world=world, row_offset=lo, n_rows_global=n_total, debug_export=2 if args.role_profile else 0)
         if world > 1:
             uid = [mvc_b200.Sampler.nccl_unique_id() if rank == 0 else None]
             dist.broadcast_object_list(uid, src=0)
@@ -252,6 +253,13 @@ def main():
     roofline = {"bound": "hbm", "kernel": "likelihood+draw", "achieved": achieved, "peak": peak, "unit": "GB/s",
                 "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": alg_bytes, "kernel_ms": kern}
+    if args.role_profile and rank == 0:
+        pr = s.get_debug_prof()
+        names = ["tma.wait_raw_empty", "tma.total", "mma.wait_d_empty", "mma.wait_raw_full", "mma.wait_lo_full", "mma.total",
+                 "conv0.wait_raw_full", "conv0.wait_lo_empty", "conv0.total", "conv1.wait_raw_full", "conv1.wait_lo_empty",
+                 "conv1.total", "epi0.wait", "epi0.total", "epi1.wait", "epi1.total"]
+        med = np.median(pr, axis=0)
+        print("role profile (median cycles over CTAs):", {n: int(m) for n, m in zip(names, med)}, file=sys.stderr)
     final = s.get_state(with_rows=False)
     s.close()
 

@@ -80,7 +80,7 @@ typedef struct mvg_config {
   uint64_t seed;           /* Philox key (echo of set.seed(1999), New_Simulation.R:12) */
   uint32_t chain;          /* chain id, folded into the Philox key */
   int32_t engine;          /* MVG_ENGINE_* : which likelihood+draw kernel */
-  int32_t debug_export;    /* !=0: keep the per-row dot products of the last sweep for mvg_get_debug_* */
+  int32_t debug_export;    /* bit 0: keep the per-row dot products of the last sweep for mvg_get_debug_*; bit 1: role wait counters */
   int32_t rank;            /* shard index 0..world-1 (0 on one GPU) */
   int32_t world;           /* number of shards (1 on one GPU) */
   int32_t reserved[5];
@@ -162,6 +162,9 @@ int mvg_get_debug_rows(mvg_handle* h, float* acc, float* xx, int32_t* choice);
 /* Births of the LAST sweep: rows (global index) seated at new tables in order, and the
  * V*(cap+1) max-normalised dish weights each saw.  rows holds cap entries, w cap*V*(cap+1). */
 int mvg_get_debug_births(mvg_handle* h, int32_t* n_seated, int64_t* rows, double* w);
+/* With debug_export & 2 (tcgen05 engines): cycles each role of the draw kernel spent waiting on its
+ * barriers during the LAST sweep, 16 counters per CTA (layout: csrc/mv_draw_tc.cu). */
+int mvg_get_debug_prof(mvg_handle* h, int64_t* out, int32_t n_ctas);
 /* Device time of the last mvg_sweep call's kernels, by CUDA events on the handle's stream (ms). */
 int mvg_last_sweep_ms(mvg_handle* h, float* ms_total);
 /* Number of kernel launches the library issued since the handle was created. */

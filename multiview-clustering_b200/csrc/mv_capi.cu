@@ -130,6 +130,7 @@ int ensure_layout(mvg_handle* h) {
   A(c.partial_f, (size_t)c.stat_ctas * (cap * dsum + V * cap)); A(c.partial_n, (size_t)c.stat_ctas * cap);
   A(c.birth_lf, cap * V * (cap + 1));
   A(c.dbg_birth_rows, cap); A(c.dbg_birth_w, cap * V * (cap + 1)); A(c.dbg_nseated, 1);
+  A(c.dbg_prof, (size_t)256 * 16);
   PacketLayout& p = c.pkt;
   int off = 0;
   p.off_hdr = off; off += 32;
@@ -141,7 +142,7 @@ int ensure_layout(mvg_handle* h) {
   p.off_cand_x = off; off += align16(4 * c.cap * dsum);
   p.bytes = off;
   A(c.packet, (size_t)c.world * p.bytes);
-  if (c.debug_export) { A(c.dbg_acc, N * V * cap); A(c.dbg_xx, N * V); A(c.dbg_choice, N); }
+  if (c.debug_export & 1) { A(c.dbg_acc, N * V * cap); A(c.dbg_xx, N * V); A(c.dbg_choice, N); }
 #undef A
   h->layout_done = true;
   // engine choice
@@ -551,7 +552,7 @@ int mvg_get_params(mvg_handle* h, const mvg_params_host* o) {
 int mvg_get_debug_rows(mvg_handle* h, float* acc, float* xx, int32_t* choice) {
   if (!h) return MVG_EINVAL;
   const Ctx& c = h->c;
-  if (!c.debug_export || !c.dbg_acc) return fail(h, MVG_ESTATE, "handle was not created with debug_export");
+  if (!(c.debug_export & 1) || !c.dbg_acc) return fail(h, MVG_ESTATE, "handle was not created with debug_export");
   MVG_CUDA(h, cudaSetDevice(h->cfg.device));
   const size_t N = (size_t)c.n_rows;
   if (acc) MVG_CUDA(h, cudaMemcpyAsync(acc, c.dbg_acc, sizeof(float) * N * c.V * c.cap, cudaMemcpyDeviceToHost, h->stream));
@@ -569,6 +570,15 @@ int mvg_get_debug_births(mvg_handle* h, int32_t* n_seated, int64_t* rows, double
   if (n_seated) MVG_CUDA(h, cudaMemcpyAsync(n_seated, c.dbg_nseated, sizeof(int32_t), cudaMemcpyDeviceToHost, h->stream));
   if (rows) MVG_CUDA(h, cudaMemcpyAsync(rows, c.dbg_birth_rows, sizeof(int64_t) * (size_t)c.cap, cudaMemcpyDeviceToHost, h->stream));
   if (w) MVG_CUDA(h, cudaMemcpyAsync(w, c.dbg_birth_w, sizeof(double) * (size_t)c.cap * c.V * (c.cap + 1), cudaMemcpyDeviceToHost, h->stream));
+  MVG_CUDA(h, cudaStreamSynchronize(h->stream));
+  return MVG_OK;
+}
+
+int mvg_get_debug_prof(mvg_handle* h, int64_t* out, int32_t n_ctas) {
+  if (!h || !out || n_ctas < 0 || n_ctas > 256) return MVG_EINVAL;
+  if (!h->c.dbg_prof) return fail(h, MVG_ESTATE, "no profile buffer");
+  MVG_CUDA(h, cudaSetDevice(h->cfg.device));
+  MVG_CUDA(h, cudaMemcpyAsync(out, h->c.dbg_prof, sizeof(int64_t) * 16 * (size_t)n_ctas, cudaMemcpyDeviceToHost, h->stream));
   MVG_CUDA(h, cudaStreamSynchronize(h->stream));
   return MVG_OK;
 }

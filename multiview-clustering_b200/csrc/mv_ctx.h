@@ -87,6 +87,7 @@ struct Ctx {
   int64_t* dbg_birth_rows;  // [cap]
   double* dbg_birth_w;      // [cap][V][cap+1]
   int32_t* dbg_nseated;     // [1]
+  long long* dbg_prof;      // [CTAs][16] cycles spent waiting per role of the tcgen05 kernel (debug_export & 2)
 };
 
 enum FinalizeFlags : int32_t {

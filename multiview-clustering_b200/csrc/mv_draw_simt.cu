@@ -87,7 +87,7 @@ __global__ void __launch_bounds__(kSimtThreads, 2) k_draw_simt(const Ctx c) {
           }
         }
       }
-      if (c.debug_export && live) {
+      if ((c.debug_export & 1) && live) {
         float* da = c.dbg_acc + ((size_t)row * c.V + v) * CAP;
 #pragma unroll
         for (int t = 0; t < CAP; ++t) da[t] = acc[t];
@@ -100,7 +100,7 @@ __global__ void __launch_bounds__(kSimtThreads, 2) k_draw_simt(const Ctx c) {
     int choice = epi.finish(uniform_f32_from(rnd.x));
     if (live) {
       c.choice[row] = choice;
-      if (c.debug_export) c.dbg_choice[row] = choice;
+      if (c.debug_export & 1) c.dbg_choice[row] = choice;
     }
     const unsigned births = __ballot_sync(0xffffffffu, live && choice == kNewTable);
     if ((tid & 31) == 0 && (row >> 5) < c.n_chunks) c.birthmask[row >> 5] = births;

@@ -19,7 +19,7 @@
 //                              feed RowEpilogue (mv_device.cuh) — leave-one-out weights, streaming
 //                              log-sum-exp marginal, inverse-CDF draw.
 //
-// TMEM (512 columns): [0,256) four accumulator tiles, [256,512) four remainder tiles.
+// TMEM (512 columns): [0,384) six accumulator tiles, [384,512) two remainder tiles.
 // The [N x 64] log-likelihood matrices never exist in memory: HBM traffic is the features once
 // (N*V*256 B) plus 8 B per customer (table in, choice out).
 //
@@ -38,8 +38,9 @@ constexpr int kHalfCols = 32;                       // floats per 128-byte swizz
 constexpr int kHalfBytes = kTileRows * 128;         // 16 KB: one K-half of an A tile
 constexpr int kBHalfBytes = 64 * 128;               // 8 KB: one K-half of a B matrix (64 tables)
 constexpr int kRawStages = 7;                       // K-halves of raw features in flight
-constexpr int kLoStages = 4;                        // TMEM remainder tiles (64 columns each)
-constexpr int kDStages = 4;                         // TMEM accumulator tiles (64 columns each)
+constexpr int kLoStages = 2;                        // TMEM remainder tiles (64 columns each)
+constexpr int kDStages = 6;                         // TMEM accumulator tiles (64 columns each): one whole row tile (3 views) per epilogue warpgroup
+constexpr int kXxSlots = 8;                         // ring of per-row |x|^2 partials; >= kDStages + kLoStages keeps it race-free
 constexpr int kTmemCols = 512;
 constexpr int kLoCol0 = kDStages * 64;              // first TMEM column of the remainder tiles
 constexpr int kMaxTcViews = 3;
@@ -60,8 +61,8 @@ struct SmemLayout {
   static constexpr int tm_off = tp_off + kMaxTcViews * 64 * (int)sizeof(TableParam);
   static constexpr int vp_off = tm_off + 64 * (int)sizeof(TableMass);
   static constexpr int xx_off = vp_off + kMaxTcViews * (int)sizeof(ViewParam);
-  static constexpr int bar_off = xx_off + kDStages * 2 * kTileRows * (int)sizeof(float);   // [stage][K-half][row]
-  static constexpr int n_bars = 2 * kRawStages + 2 * kLoStages + 3 * kDStages + 1;
+  static constexpr int bar_off = xx_off + kXxSlots * 2 * kTileRows * (int)sizeof(float);   // [slot][K-half][row]
+  static constexpr int n_bars = 2 * kRawStages + 2 * kLoStages + 2 * kDStages + kXxSlots + 1;
   static constexpr int misc_off = bar_off + n_bars * 8;
   static constexpr int total = misc_off + 64;
 };
@@ -91,6 +92,16 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
       "}\n" ::"r"(bar), "r"(parity)
       : "memory");
 }
+// mbar_wait that also adds the cycles spent waiting to *acc when profiling is on (debug_export & 2).
+__device__ __forceinline__ void mbar_wait_t(uint32_t bar, uint32_t parity, bool prof, long long& acc) {
+  if (prof) {
+    const long long t0 = clock64();
+    mbar_wait(bar, parity);
+    acc += clock64() - t0;
+  } else {
+    mbar_wait(bar, parity);
+  }
+}
 __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {
   asm volatile(
       "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
@@ -102,23 +113,35 @@ __device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarr
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 
-__device__ __forceinline__ void umma_tf32(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+// cute::UMMA::InstrDescriptor for kind::tf32: D = F32 (1 at [4,6)), A = B = TF32 (2 at [7,10) and
+// [10,13)), both K-major, N >> 3 at [17,23), M >> 4 at [24,29).
+constexpr uint32_t kIdesc = (1u << 4) | (2u << 7) | (2u << 10) | ((64u >> 3) << 17) | ((128u >> 4) << 24);
+
+// The shared-memory operand descriptor is 64 bits; everything that varies per MMA (the start address,
+// bits [0,14), in 16-byte units) lives in the low word, so the issuer only ever adds to `lo`.
+template <bool ACC>
+__device__ __forceinline__ void umma_tf32(uint32_t d_tmem, uint32_t a_lo, uint32_t b_lo, uint32_t desc_hi) {
   asm volatile(
       "{\n\t"
       ".reg .pred p;\n\t"
-      "setp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t"
-      "}\n" ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      ".reg .b64 da, db;\n\t"
+      "setp.ne.b32 p, %5, 0;\n\t"
+      "mov.b64 da, {%1, %3};\n\t"
+      "mov.b64 db, {%2, %3};\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], da, db, %4, p;\n\t"
+      "}\n" ::"r"(d_tmem), "r"(a_lo), "r"(b_lo), "r"(desc_hi), "r"(kIdesc), "n"(ACC ? 1 : 0)
       : "memory");
 }
 // Same with the A operand in tensor memory: lane = row, one 32-bit column per K element.
-__device__ __forceinline__ void umma_tf32_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+__device__ __forceinline__ void umma_tf32_ts(uint32_t d_tmem, uint32_t a_tmem, uint32_t b_lo, uint32_t desc_hi) {
   asm volatile(
       "{\n\t"
       ".reg .pred p;\n\t"
-      "setp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t"
-      "}\n" ::"r"(d_tmem), "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      ".reg .b64 db;\n\t"
+      "setp.ne.b32 p, 1, 0;\n\t"
+      "mov.b64 db, {%2, %3};\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], db, %4, p;\n\t"
+      "}\n" ::"r"(d_tmem), "r"(a_tmem), "r"(b_lo), "r"(desc_hi), "r"(kIdesc)
       : "memory");
 }
 __device__ __forceinline__ void tmem_st_16(uint32_t taddr, const uint32_t (&u)[16]) {
@@ -137,18 +160,21 @@ __device__ __forceinline__ void umma_commit(uint32_t bar) {
 // K-major, SWIZZLE_128B operand descriptor (cute::UMMA::SmemDescriptor): start address >> 4 in bits
 // [0,14), leading byte offset [16,30) (unused for swizzled K-major: 1), stride byte offset [32,46) =
 // 1024 B between 8-row groups, version 1 at [46,48), layout type SWIZZLE_128B = 2 at [61,64).
-__device__ __forceinline__ uint64_t make_desc(uint32_t smem_addr) {
-  uint64_t d = 0;
-  d |= (uint64_t)((smem_addr >> 4) & 0x3FFF);
-  d |= (uint64_t)1 << 16;
-  d |= (uint64_t)(1024 >> 4) << 32;
-  d |= (uint64_t)1 << 46;
-  d |= (uint64_t)2 << 61;
-  return d;
+__device__ __forceinline__ uint32_t desc_lo(uint32_t smem_addr) { return ((smem_addr >> 4) & 0x3FFFu) | (1u << 16); }
+constexpr uint32_t kDescHi = (uint32_t)(1024 >> 4) | (1u << 14) | (2u << 29);
+
+// One lane of a converged warp (cute::elect_one_sync): lets ptxas keep single-lane tcgen05 issue
+// free of the lane-serialising loop it otherwise wraps around uniform-datapath instructions.
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t"
+      ".reg .pred P;\n\t"
+      "elect.sync _|P, 0xffffffff;\n\t"
+      "selp.u32 %0, 1, 0, P;\n\t"
+      "}\n" : "=r"(pred));
+  return pred != 0;
 }
-// cute::UMMA::InstrDescriptor for kind::tf32: D = F32 (1 at [4,6)), A = B = TF32 (2 at [7,10) and
-// [10,13)), both K-major, N >> 3 at [17,23), M >> 4 at [24,29).
-constexpr uint32_t kIdesc = (1u << 4) | (2u << 7) | (2u << 10) | ((64u >> 3) << 17) | ((128u >> 4) << 24);
 
 template <int REGS> __device__ __forceinline__ void reg_dec() { asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(REGS)); }
 template <int REGS> __device__ __forceinline__ void reg_inc() { asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(REGS)); }
@@ -184,7 +210,7 @@ __device__ __forceinline__ void epi_chunk(RowEpilogue<64, FAST>& epi, const Tabl
   float ch[16];
 #pragma unroll
   for (int t = 0; t < 16; ++t) ch[t] = __uint_as_float(cur[t]);
-  if (c.debug_export && live) {
+  if ((c.debug_export & 1) && live) {
     float* da = c.dbg_acc + ((size_t)row * c.V + v) * 64 + BASE;
 #pragma unroll
     for (int t = 0; t < 16; ++t) da[t] = ch[t];
@@ -214,7 +240,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_draw_tc(const Ctx c, const __gr
   auto d_full = [&](int s) { return bar0 + 8u * (2 * kRawStages + 2 * kLoStages + s); };
   auto d_empty = [&](int s) { return bar0 + 8u * (2 * kRawStages + 2 * kLoStages + kDStages + s); };
   auto xx_full = [&](int s) { return bar0 + 8u * (2 * kRawStages + 2 * kLoStages + 2 * kDStages + s); };
-  const uint32_t b_full = bar0 + 8u * (2 * kRawStages + 2 * kLoStages + 3 * kDStages);
+  const uint32_t b_full = bar0 + 8u * (2 * kRawStages + 2 * kLoStages + 2 * kDStages + kXxSlots);
 
   // ---- one-time setup --------------------------------------------------------------------------
   for (int i = tid; i < V * 64; i += kThreads) s_tp[i] = c.tparam[i];
@@ -227,7 +253,8 @@ __global__ void __launch_bounds__(kThreads, 1) k_draw_tc(const Ctx c, const __gr
     s_misc[3] = __float_as_uint(g.LMN1);
     for (int s = 0; s < kRawStages; ++s) { mbar_init(raw_full(s), 1); mbar_init(raw_empty(s), 129); }   // one converter warpgroup + the MMA commit
     for (int s = 0; s < kLoStages; ++s) { mbar_init(lo_full(s), 256); mbar_init(lo_empty(s), 1); }      // both converter warpgroups
-    for (int s = 0; s < kDStages; ++s) { mbar_init(d_full(s), 1); mbar_init(d_empty(s), 128); mbar_init(xx_full(s), 256); }
+    for (int s = 0; s < kDStages; ++s) { mbar_init(d_full(s), 1); mbar_init(d_empty(s), 128); }
+    for (int s = 0; s < kXxSlots; ++s) mbar_init(xx_full(s), 256);
     mbar_init(b_full, 1);
     fence_barrier_init();
   }
@@ -245,6 +272,10 @@ __global__ void __launch_bounds__(kThreads, 1) k_draw_tc(const Ctx c, const __gr
   gp.LMN1 = __uint_as_float(s_misc[3]);
 
   const int n_tiles = (c.n_rows + kTileRows - 1) / kTileRows;
+  const bool prof = (c.debug_export & 2) != 0 && c.dbg_prof != nullptr;
+  long long* prof_out = prof ? c.dbg_prof + (size_t)blockIdx.x * 16 : nullptr;
+  long long w0 = 0, w1 = 0, w2 = 0;
+  const long long t_start = prof ? clock64() : 0;
 
   if (warp < 4) {
     // =========================== WG0: control ==================================================
@@ -262,57 +293,74 @@ __global__ void __launch_bounds__(kThreads, 1) k_draw_tc(const Ctx c, const __gr
         for (int v = 0; v < V; ++v)
 #pragma unroll 1
           for (int h = 0; h < 2; ++h) {
-            mbar_wait(raw_empty(r.stage), r.phase ^ 1u);
+            mbar_wait_t(raw_empty(r.stage), r.phase ^ 1u, prof, w0);
             mbar_expect_tx(raw_full(r.stage), kHalfBytes);
             tma_load_2d(sbase + SmemLayout::raw_off + r.stage * kHalfBytes, &maps.x[v], raw_full(r.stage),
                         h * kHalfCols, tile * kTileRows);
             r.next();
           }
-    } else if (warp == 1 && lane == 0) {
-      // ---- MMA issuer ----
+      if (prof) { prof_out[0] = w0; prof_out[1] = clock64() - t_start; }
+    } else if (warp == 1) {
+      // ---- MMA issuer: the whole warp walks the loop (descriptor arithmetic stays warp-uniform),
+      //      lane 0 issues ----
       mbar_wait(b_full, 0);
       tc_fence_after();
+      const uint32_t a_lo0 = desc_lo(sbase + SmemLayout::raw_off);
+      const uint32_t b_lo0 = desc_lo(sbase + SmemLayout::b_off);
       Ring rr(kRawStages), rl(kLoStages), rd(kDStages);
       for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x)
         for (int v = 0; v < V; ++v) {
-          mbar_wait(d_empty(rd.stage), rd.phase ^ 1u);
+          mbar_wait_t(d_empty(rd.stage), rd.phase ^ 1u, prof, w0);
           tc_fence_after();
           const uint32_t d_tmem = tmem_base + (uint32_t)(rd.stage * 64);
-          uint32_t accumulate = 0;
-          // passes 1+2 on the raw halves: x_hi . m_hi  and  x_hi . m_lo
-#pragma unroll 1
-          for (int h = 0; h < 2; ++h) {
-            mbar_wait(raw_full(rr.stage), rr.phase);
+          const uint32_t b_v = b_lo0 + (uint32_t)(v * 4 * (kBHalfBytes >> 4));   // [hi|lo][h] blocks of this view
+          // passes 1+2 on the raw halves: x_hi . m_hi  and  x_hi . m_lo   (4 x K=8 per 128-byte row, +32 B each)
+          {
+            mbar_wait_t(raw_full(rr.stage), rr.phase, prof, w1);
             tc_fence_after();
-            const uint32_t a_addr = sbase + SmemLayout::raw_off + rr.stage * kHalfBytes;
+            const uint32_t a = a_lo0 + (uint32_t)(rr.stage * (kHalfBytes >> 4));
+            if (elect_one()) {
+              umma_tf32<false>(d_tmem, a, b_v, kDescHi);
 #pragma unroll
-            for (int part = 0; part < 2; ++part) {
-              const uint32_t b_addr = sbase + SmemLayout::b_off + ((v * 2 + part) * 2 + h) * kBHalfBytes;
+              for (int k = 1; k < 4; ++k) umma_tf32<true>(d_tmem, a + 2 * k, b_v + 2 * k, kDescHi);
 #pragma unroll
-              for (int k = 0; k < 4; ++k) {           // 4 x (K = 8 floats = 32 bytes) per 128-byte row
-                umma_tf32(d_tmem, make_desc(a_addr + k * 32), make_desc(b_addr + k * 32), kIdesc, accumulate);
-                accumulate = 1;
-              }
+              for (int k = 0; k < 4; ++k) umma_tf32<true>(d_tmem, a + 2 * k, b_v + 2 * (kBHalfBytes >> 4) + 2 * k, kDescHi);
+              umma_commit(raw_empty(rr.stage));       // this raw half is free once these MMAs retire
             }
-            umma_commit(raw_empty(rr.stage));         // this raw half is free once these MMAs retire
+            __syncwarp();
+            rr.next();
+          }
+          {
+            mbar_wait_t(raw_full(rr.stage), rr.phase, prof, w1);
+            tc_fence_after();
+            const uint32_t a = a_lo0 + (uint32_t)(rr.stage * (kHalfBytes >> 4));
+            if (elect_one()) {
+#pragma unroll
+              for (int k = 0; k < 4; ++k) umma_tf32<true>(d_tmem, a + 2 * k, b_v + (kBHalfBytes >> 4) + 2 * k, kDescHi);
+#pragma unroll
+              for (int k = 0; k < 4; ++k) umma_tf32<true>(d_tmem, a + 2 * k, b_v + 3 * (kBHalfBytes >> 4) + 2 * k, kDescHi);
+              umma_commit(raw_empty(rr.stage));
+            }
+            __syncwarp();
             rr.next();
           }
           // pass 3 from tensor memory: x_lo . m_hi
-          mbar_wait(lo_full(rl.stage), rl.phase);
+          mbar_wait_t(lo_full(rl.stage), rl.phase, prof, w2);
           tc_fence_after();
-          const uint32_t a_tmem = tmem_base + (uint32_t)(kLoCol0 + rl.stage * 64);
+          if (elect_one()) {
+            const uint32_t a_tmem = tmem_base + (uint32_t)(kLoCol0 + rl.stage * 64);
 #pragma unroll
-          for (int h = 0; h < 2; ++h) {
-            const uint32_t b_addr = sbase + SmemLayout::b_off + ((v * 2 + 0) * 2 + h) * kBHalfBytes;
+            for (int k = 0; k < 4; ++k) umma_tf32_ts(d_tmem, a_tmem + (uint32_t)(k * 8), b_v + 2 * k, kDescHi);
 #pragma unroll
-            for (int k = 0; k < 4; ++k)
-              umma_tf32_ts(d_tmem, a_tmem + (uint32_t)(h * 32 + k * 8), make_desc(b_addr + k * 32), kIdesc, 1);
+            for (int k = 0; k < 4; ++k) umma_tf32_ts(d_tmem, a_tmem + (uint32_t)(32 + k * 8), b_v + (kBHalfBytes >> 4) + 2 * k, kDescHi);
+            umma_commit(lo_empty(rl.stage));
+            umma_commit(d_full(rd.stage));
           }
-          umma_commit(lo_empty(rl.stage));
-          umma_commit(d_full(rd.stage));
+          __syncwarp();
           rl.next();
           rd.next();
         }
+      if (prof && lane == 0) { prof_out[2] = w0; prof_out[3] = w1; prof_out[4] = w2; prof_out[5] = clock64() - t_start; }
     }
   } else if (warp < 12) {
     // =========================== WG1, WG2: converters, one K-half each ===========================
@@ -326,10 +374,11 @@ __global__ void __launch_bounds__(kThreads, 1) k_draw_tc(const Ctx c, const __gr
       for (int v = 0; v < V; ++v, ++i) {
         const int rs = (2 * i + h) % kRawStages;
         const uint32_t rph = (uint32_t)((2 * i + h) / kRawStages) & 1u;
-        const int ls = i % kLoStages;                  // == accumulator stage (kLoStages == kDStages)
+        const int ls = i % kLoStages;
         const uint32_t lph = (uint32_t)(i / kLoStages) & 1u;
-        mbar_wait(raw_full(rs), rph);
-        mbar_wait(lo_empty(ls), lph ^ 1u);
+        const int xs = i % kXxSlots;
+        mbar_wait_t(raw_full(rs), rph, prof, w0);
+        mbar_wait_t(lo_empty(ls), lph ^ 1u, prof, w1);
         tc_fence_after();
         const unsigned char* src = smem + SmemLayout::raw_off + rs * kHalfBytes + line;
         const uint32_t lo_addr = tmem_base + lane_base + (uint32_t)(kLoCol0 + ls * 64 + h * 32);
@@ -357,10 +406,12 @@ __global__ void __launch_bounds__(kThreads, 1) k_draw_tc(const Ctx c, const __gr
         tmem_st_wait();
         tc_fence_before();
         mbar_arrive(lo_full(ls));
-        mbar_wait(d_empty(ls), lph ^ 1u);              // the epilogue has consumed this xx slot
-        s_xx[(ls * 2 + h) * kTileRows + r] = xx;
-        mbar_arrive(xx_full(ls));
+        // slot i % 8 was last read for tile-view i-8, whose accumulator stage had to be released before the
+        // MMA of tile-view i-2 could issue, which in turn freed the remainder stage waited for above
+        s_xx[(xs * 2 + h) * kTileRows + r] = xx;
+        mbar_arrive(xx_full(xs));
       }
+    if (prof && r == 0) { prof_out[6 + 3 * h] = w0; prof_out[7 + 3 * h] = w1; prof_out[8 + 3 * h] = clock64() - t_start; }
   } else {
     // =========================== WG3, WG4: epilogue (thread r <-> TMEM lane r <-> customer r) ====
     reg_inc<168>();   // pool: 640 threads x 96 registers; 24 + 56 + 56 + 168 + 168 = 472 <= 480 per thread-slot
@@ -378,14 +429,15 @@ __global__ void __launch_bounds__(kThreads, 1) k_draw_tc(const Ctx c, const __gr
         const int idx = j * V + v;
         const int stage = idx % kDStages;
         const uint32_t phase = (uint32_t)(idx / kDStages) & 1u;
-        mbar_wait(d_full(stage), phase);
-        mbar_wait(xx_full(stage), phase);
+        const int xs = idx % kXxSlots;
+        mbar_wait_t(d_full(stage), phase, prof, w0);
+        mbar_wait_t(xx_full(xs), (uint32_t)(idx / kXxSlots) & 1u, prof, w1);
         tc_fence_after();
         const uint32_t taddr = tmem_base + lane_base + (uint32_t)(stage * 64);
-        const float xx = __fadd_rn(s_xx[(stage * 2 + 0) * kTileRows + r], s_xx[(stage * 2 + 1) * kTileRows + r]);
+        const float xx = __fadd_rn(s_xx[(xs * 2 + 0) * kTileRows + r], s_xx[(xs * 2 + 1) * kTileRows + r]);
         const TableParam* tpv = s_tp + v * 64;
         epi.view_begin(tpv, xx);
-        if (c.debug_export && live) c.dbg_xx[(size_t)row * V + v] = xx;
+        if ((c.debug_export & 1) && live) c.dbg_xx[(size_t)row * V + v] = xx;
         uint32_t ua[16], ub[16];
         tmem_ld_16(taddr, ua);
         epi_chunk<0>(epi, tpv, taddr, ua, ub, c, row, v, live);
@@ -400,11 +452,12 @@ __global__ void __launch_bounds__(kThreads, 1) k_draw_tc(const Ctx c, const __gr
       const int choice = epi.finish(uniform_f32_from(rnd.x));
       if (live) {
         c.choice[row] = choice;
-        if (c.debug_export) c.dbg_choice[row] = choice;
+        if (c.debug_export & 1) c.dbg_choice[row] = choice;
       }
       const unsigned births = __ballot_sync(0xffffffffu, live && choice == kNewTable);
       if (lane == 0 && (row >> 5) < c.n_chunks) c.birthmask[row >> 5] = births;
     }
+    if (prof && r == 0) { prof_out[12 + 2 * grp] = w0 + w1; prof_out[13 + 2 * grp] = clock64() - t_start; }
   }
 
   // ---- teardown ------------------------------------------------------------------------------------

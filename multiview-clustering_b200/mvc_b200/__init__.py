@@ -94,6 +94,7 @@ def lib():
         L.mvg_get_params.argtypes = [H, C.POINTER(_ParamsHost)]
         L.mvg_get_debug_rows.argtypes = [H, _f32p, _f32p, _i32p]
         L.mvg_get_debug_births.argtypes = [H, _i32p, C.POINTER(C.c_int64), _f64p]
+        L.mvg_get_debug_prof.argtypes = [H, C.POINTER(C.c_int64), C.c_int32]
         L.mvg_last_sweep_ms.argtypes = [H, _f32p]
         L.mvg_launch_count.restype = C.c_int64
         L.mvg_launch_count.argtypes = [H]
@@ -313,6 +314,12 @@ class Sampler:
         ch = np.empty(self.n_rows, np.int32)
         self._ck(self.L.mvg_get_debug_rows(self.h, _p(acc, _f32p), _p(xx, _f32p), _p(ch, _i32p)))
         return acc, xx, ch
+
+    def get_debug_prof(self, n_ctas=148):
+        """Role wait counters of the last tcgen05 draw (needs debug_export & 2): [n_ctas, 16] cycles."""
+        out = np.zeros((n_ctas, 16), np.int64)
+        self._ck(self.L.mvg_get_debug_prof(self.h, _p(out, C.POINTER(C.c_int64)), n_ctas))
+        return out
 
     def get_debug_births(self):
         ns = C.c_int32(0)
