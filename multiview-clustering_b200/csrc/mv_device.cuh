@@ -94,9 +94,27 @@ __device__ __forceinline__ float log2m(float s) {
   return __fadd_rn((float)e, r);
 }
 
-// 2^d for the weights.  EXACT: the polynomial above (the CPU mirror reproduces it bit for bit).
-// FAST: one MUFU.EX2 (ex2.approx.ftz, <= 2 ulp) — the weights are then tolerance-level and only
-// the scan that turns them into a table index is mirrored exactly.
+// ---- packed FP32 (sm_100 FFMA2 / FADD2): two IEEE-rounded operations per instruction ------------
+// Each half is rounded exactly like the scalar fmaf / add, so packing changes the instruction count,
+// not a single bit of the result (the CPU mirror stays scalar).
+__device__ __forceinline__ float2 ffma2(float2 a, float2 b, float2 c) {
+  unsigned long long d;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d)
+      : "l"(*reinterpret_cast<unsigned long long*>(&a)), "l"(*reinterpret_cast<unsigned long long*>(&b)),
+        "l"(*reinterpret_cast<unsigned long long*>(&c)));
+  return *reinterpret_cast<float2*>(&d);
+}
+__device__ __forceinline__ float2 fadd2(float2 a, float2 b) {
+  unsigned long long d;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d)
+      : "l"(*reinterpret_cast<unsigned long long*>(&a)), "l"(*reinterpret_cast<unsigned long long*>(&b)));
+  return *reinterpret_cast<float2*>(&d);
+}
+__device__ __forceinline__ float2 splat2(float x) { return make_float2(x, x); }
+
+// 2^d for the weights, two at a time.  EXACT: the polynomial of exp2m (the CPU mirror reproduces it
+// bit for bit).  FAST: MUFU.EX2 (ex2.approx.ftz, <= 2 ulp) — the weights are then tolerance-level and
+// only the scan that turns them into a table index is mirrored exactly.
 template <bool FAST>
 __device__ __forceinline__ float exp2w(float d) {
   if (FAST) {
@@ -105,6 +123,52 @@ __device__ __forceinline__ float exp2w(float d) {
     return r;
   } else {
     return exp2m(d);
+  }
+}
+template <bool FAST>
+__device__ __forceinline__ float2 exp2w2(float2 d) {
+  if (FAST) {
+    return make_float2(exp2w<true>(d.x), exp2w<true>(d.y));
+  } else {
+    d.x = fmaxf(d.x, -125.0f);
+    d.y = fmaxf(d.y, -125.0f);
+    const float2 r = fadd2(d, splat2(12582912.0f));
+    const float2 n = fadd2(r, splat2(-12582912.0f));
+    const float2 f = ffma2(n, splat2(-1.0f), d);                 // d - n, one rounding of the exact difference
+    float2 p = splat2(0x1.5bba14p-10f);
+    p = ffma2(p, f, splat2(0x1.3cea88p-7f));
+    p = ffma2(p, f, splat2(0x1.c6b752p-5f));
+    p = ffma2(p, f, splat2(0x1.ebf9bcp-3f));
+    p = ffma2(p, f, splat2(0x1.62e42ap-1f));
+    p = ffma2(p, f, splat2(1.0f));
+    return make_float2(__uint_as_float(__float_as_uint(p.x) + (__float_as_uint(r.x) << 23)),
+                       __uint_as_float(__float_as_uint(p.y) + (__float_as_uint(r.y) << 23)));
+  }
+}
+
+// ---- shared-memory staging of the parameter block for the epilogue ----------------------------------
+// Hot part, per PAIR of tables (2t, 2t+1) so that packed arithmetic reads its operands as 64-bit halves
+// of two 128-bit loads; cold part per table, read once per customer and view at its own table.
+struct __align__(16) PairHot {
+  float A0, A1, C0, C1;
+  float W0, W1;
+  int32_t dish0, dish1;
+};
+struct __align__(16) TableCold {
+  float A1, C1, W1;
+  int32_t lone;
+};
+// Cooperative copy of one view's TableParam[cap] from global memory into the two shared arrays.
+__device__ __forceinline__ void stage_view_params(const TableParam* __restrict__ g, int cap, PairHot* hot,
+                                                  TableCold* cold, int tid, int nthreads) {
+  for (int t = tid; t < cap; t += nthreads) {
+    const TableParam q = g[t];
+    PairHot& h = hot[t >> 1];
+    if (t & 1) { h.A1 = q.A; h.C1 = q.C; h.W1 = q.W; h.dish1 = q.dish; }
+    else { h.A0 = q.A; h.C0 = q.C; h.W0 = q.W; h.dish0 = q.dish; }
+    TableCold cq;
+    cq.A1 = q.A1; cq.C1 = q.C1; cq.W1 = q.W1; cq.lone = q.lone;
+    cold[t] = cq;
   }
 }
 
@@ -124,10 +188,10 @@ constexpr int kEpiChunk = 16;
 template <int CAP, bool FAST = false>
 struct RowEpilogue {
   static_assert(CAP % kEpiChunk == 0, "table capacity must be a multiple of the epilogue chunk");
-  float lw[CAP];   // running log2 weight of each table
-  float lnew;      // running log2 weight of a new table
-  int t0;          // current table of the customer
-  int single;      // the customer sits alone at t0
+  float2 lw2[CAP / 2];   // running log2 weight of tables (2i, 2i+1)
+  float lnew;            // running log2 weight of a new table
+  int t0;                // current table of the customer
+  int single;            // the customer sits alone at t0
   // per-view state
   float mx, s, nxx, A1r, C1r;
   int k0, lone0, any_single;
@@ -139,54 +203,66 @@ struct RowEpilogue {
     any_single = __any_sync(0xffffffffu, single);   // customers alone at their table are rare: warp-uniform slow path
     lnew = single ? g.LMN1 : g.LMN0;
 #pragma unroll
-    for (int t = 0; t < CAP; ++t) lw[t] = (t == t0_) ? own.LM1 : tm[t].LM;
+    for (int i = 0; i < CAP / 2; ++i) {
+      lw2[i].x = (2 * i == t0_) ? own.LM1 : tm[2 * i].LM;
+      lw2[i].y = (2 * i + 1 == t0_) ? own.LM1 : tm[2 * i + 1].LM;
+    }
   }
 
-  __device__ __forceinline__ void view_begin(const TableParam* __restrict__ tp, float xx) {
-    const TableParam own = tp[t0];
-    k0 = own.dish; lone0 = own.lone; A1r = own.A1; C1r = own.C1;
+  __device__ __forceinline__ void view_begin(const PairHot* __restrict__ hot, const TableCold* __restrict__ cold, float xx) {
+    const TableCold own = cold[t0];
+    k0 = reinterpret_cast<const int32_t*>(&hot[t0 >> 1].dish0)[t0 & 1];
+    lone0 = own.lone; A1r = own.A1; C1r = own.C1;
     nxx = -xx;
     mx = kMasked;
     s = 0.0f;
   }
 
-  // acc[j] = x . m_{v, base + j} for the kEpiChunk tables of chunk `base / kEpiChunk` (consumed).
+  // acc[j] = x . m_{v, BASE + j} for the kEpiChunk tables of chunk BASE / kEpiChunk (consumed).
   template <int BASE, bool SINGLE>
-  __device__ __forceinline__ void chunk_impl(const TableParam* __restrict__ tp, float (&acc)[kEpiChunk]) {
+  __device__ __forceinline__ void chunk_impl(const PairHot* __restrict__ hot, const TableCold* __restrict__ cold,
+                                             float (&acc)[kEpiChunk]) {
+    float2 term[kEpiChunk / 2];
     float c0 = kMasked, c1 = kMasked;
+    const float2 two = splat2(2.0f), nxx2 = splat2(nxx), a1r2 = splat2(A1r), c1r2 = splat2(C1r);
 #pragma unroll
-    for (int j = 0; j < kEpiChunk; ++j) {
-      const int t = BASE + j;
-      const float4 q = *reinterpret_cast<const float4*>(&tp[t]);          // A, C, W, dish
-      const float e = __fmaf_rn(2.0f, acc[j], nxx);
-      const bool same = (__float_as_int(q.w) == k0);
-      const float L = same ? __fmaf_rn(A1r, e, C1r) : __fmaf_rn(q.x, e, q.y);
-      lw[t] = __fadd_rn(lw[t], L);
-      float w = q.z;
-      if (SINGLE) w = (same && single) ? tp[t].W1 : q.z;
-      const float term = __fadd_rn(L, w);
-      acc[j] = term;
-      if (j & 1) c1 = fmaxf(c1, term); else c0 = fmaxf(c0, term);
-      if ((j & 7) == 7) asm volatile("" ::: "memory");   // keep at most 8 parameter loads in flight (registers)
+    for (int p = 0; p < kEpiChunk / 2; ++p) {
+      const float4 qa = reinterpret_cast<const float4*>(&hot[BASE / 2 + p])[0];   // A0 A1 C0 C1
+      const float4 qb = reinterpret_cast<const float4*>(&hot[BASE / 2 + p])[1];   // W0 W1 dish0 dish1
+      const float2 e = ffma2(two, make_float2(acc[2 * p], acc[2 * p + 1]), nxx2);
+      const float2 Lg = ffma2(make_float2(qa.x, qa.y), e, make_float2(qa.z, qa.w));
+      const float2 Ls = ffma2(a1r2, e, c1r2);
+      const bool same0 = (__float_as_int(qb.z) == k0), same1 = (__float_as_int(qb.w) == k0);
+      const float2 L = make_float2(same0 ? Ls.x : Lg.x, same1 ? Ls.y : Lg.y);
+      lw2[BASE / 2 + p] = fadd2(lw2[BASE / 2 + p], L);
+      float2 w = make_float2(qb.x, qb.y);
+      if (SINGLE) {
+        if (same0 && single) w.x = cold[BASE + 2 * p].W1;
+        if (same1 && single) w.y = cold[BASE + 2 * p + 1].W1;
+      }
+      term[p] = fadd2(L, w);
+      c0 = fmaxf(c0, term[p].x);
+      c1 = fmaxf(c1, term[p].y);
+      if ((p & 3) == 3) asm volatile("" ::: "memory");   // keep at most 8 parameter loads in flight (registers)
     }
     const float mn = fmaxf(mx, fmaxf(c0, c1));
     s = __fmul_rn(s, exp2w<FAST>(__fadd_rn(mx, -mn)));
     mx = mn;
-    float p0 = 0.0f, p1 = 0.0f, p2 = 0.0f, p3 = 0.0f;
+    const float2 nmn2 = splat2(-mn);
+    float2 pa = splat2(0.0f), pb = splat2(0.0f);        // partial sums over j mod 4 = (0,1) and (2,3)
 #pragma unroll
-    for (int j = 0; j < kEpiChunk; j += 4) {
-      p0 = __fadd_rn(p0, exp2w<FAST>(__fadd_rn(acc[j], -mn)));
-      p1 = __fadd_rn(p1, exp2w<FAST>(__fadd_rn(acc[j + 1], -mn)));
-      p2 = __fadd_rn(p2, exp2w<FAST>(__fadd_rn(acc[j + 2], -mn)));
-      p3 = __fadd_rn(p3, exp2w<FAST>(__fadd_rn(acc[j + 3], -mn)));
+    for (int p = 0; p < kEpiChunk / 2; p += 2) {
+      pa = fadd2(pa, exp2w2<FAST>(fadd2(term[p], nmn2)));
+      pb = fadd2(pb, exp2w2<FAST>(fadd2(term[p + 1], nmn2)));
     }
-    s = __fadd_rn(s, __fadd_rn(__fadd_rn(p0, p1), __fadd_rn(p2, p3)));
+    s = __fadd_rn(s, __fadd_rn(__fadd_rn(pa.x, pa.y), __fadd_rn(pb.x, pb.y)));
   }
 
   template <int BASE>
-  __device__ __forceinline__ void view_chunk(const TableParam* __restrict__ tp, float (&acc)[kEpiChunk]) {
-    if (any_single) chunk_impl<BASE, true>(tp, acc);
-    else chunk_impl<BASE, false>(tp, acc);
+  __device__ __forceinline__ void view_chunk(const PairHot* __restrict__ hot, const TableCold* __restrict__ cold,
+                                             float (&acc)[kEpiChunk]) {
+    if (any_single) chunk_impl<BASE, true>(hot, cold, acc);
+    else chunk_impl<BASE, false>(hot, cold, acc);
   }
 
   __device__ __forceinline__ void view_end(const ViewParam& vp, float xx) {
@@ -201,52 +277,57 @@ struct RowEpilogue {
 
   // Whole view from an array of CAP dot products (CUDA-core engine).
   template <int BASE>
-  __device__ __forceinline__ void view_chunks_from(const TableParam* __restrict__ tp, float (&acc)[CAP]) {
+  __device__ __forceinline__ void view_chunks_from(const PairHot* __restrict__ hot, const TableCold* __restrict__ cold,
+                                                   float (&acc)[CAP]) {
     if constexpr (BASE < CAP) {
       float ch[kEpiChunk];
 #pragma unroll
       for (int j = 0; j < kEpiChunk; ++j) ch[j] = acc[BASE + j];
-      view_chunk<BASE>(tp, ch);
-      view_chunks_from<BASE + kEpiChunk>(tp, acc);
+      view_chunk<BASE>(hot, cold, ch);
+      view_chunks_from<BASE + kEpiChunk>(hot, cold, acc);
     }
   }
-  __device__ __forceinline__ void view(const TableParam* __restrict__ tp, const ViewParam& vp,
-                                       float (&acc)[CAP], float xx) {
-    view_begin(tp, xx);
-    view_chunks_from<0>(tp, acc);
+  __device__ __forceinline__ void view(const PairHot* __restrict__ hot, const TableCold* __restrict__ cold,
+                                       const ViewParam& vp, float (&acc)[CAP], float xx) {
+    view_begin(hot, cold, xx);
+    view_chunks_from<0>(hot, cold, acc);
     view_end(vp, xx);
   }
 
-  // uf in (0,1). Returns the table slot or kNewTable.  lw[] is left holding the weights.
+  // uf in (0,1). Returns the table slot or kNewTable.  lw2[] is left holding the weights.
   __device__ __forceinline__ int finish(float uf) {
     float M0 = lnew, M1 = kMasked;
 #pragma unroll
-    for (int t = 0; t < CAP; t += 2) { M0 = fmaxf(M0, lw[t]); M1 = fmaxf(M1, lw[t + 1]); }
+    for (int i = 0; i < CAP / 2; ++i) { M0 = fmaxf(M0, lw2[i].x); M1 = fmaxf(M1, lw2[i].y); }
     const float M = fmaxf(M0, M1);
     if (!(M > -1.0e29f)) return t0;   // nothing has weight: stay (cf. multiview_gibbs.cpp:172-176)
-    float q0 = 0.0f, q1 = 0.0f, q2 = 0.0f, q3 = 0.0f;
+    const float2 nM2 = splat2(-M);
+    float2 qa = splat2(0.0f), qb = splat2(0.0f);          // partial sums over t mod 4 = (0,1) and (2,3)
 #pragma unroll
-    for (int t = 0; t < CAP; t += 4) {
-      lw[t] = exp2w<FAST>(__fadd_rn(lw[t], -M));         q0 = __fadd_rn(q0, lw[t]);
-      lw[t + 1] = exp2w<FAST>(__fadd_rn(lw[t + 1], -M)); q1 = __fadd_rn(q1, lw[t + 1]);
-      lw[t + 2] = exp2w<FAST>(__fadd_rn(lw[t + 2], -M)); q2 = __fadd_rn(q2, lw[t + 2]);
-      lw[t + 3] = exp2w<FAST>(__fadd_rn(lw[t + 3], -M)); q3 = __fadd_rn(q3, lw[t + 3]);
+    for (int i = 0; i < CAP / 2; i += 2) {
+      lw2[i] = exp2w2<FAST>(fadd2(lw2[i], nM2));         qa = fadd2(qa, lw2[i]);
+      lw2[i + 1] = exp2w2<FAST>(fadd2(lw2[i + 1], nM2)); qb = fadd2(qb, lw2[i + 1]);
     }
-    const float total = __fadd_rn(__fadd_rn(__fadd_rn(q0, q1), __fadd_rn(q2, q3)), exp2w<FAST>(__fadd_rn(lnew, -M)));
+    const float total = __fadd_rn(__fadd_rn(__fadd_rn(qa.x, qa.y), __fadd_rn(qb.x, qb.y)), exp2w<FAST>(__fadd_rn(lnew, -M)));
     const float target = __fmul_rn(uf, total);
     // first t with target < cum_t  ==  number of t with cum_t <= target (cum is non-decreasing)
     float cum = 0.0f;
     int cnt = 0;
 #pragma unroll
-    for (int t = 0; t < CAP; ++t) {
-      cum = __fadd_rn(cum, lw[t]);
+    for (int i = 0; i < CAP / 2; ++i) {
+      cum = __fadd_rn(cum, lw2[i].x);
+      cnt += (target < cum) ? 0 : 1;
+      cum = __fadd_rn(cum, lw2[i].y);
       cnt += (target < cum) ? 0 : 1;
     }
     int choice = (cnt < CAP) ? cnt : kNewTable;
     if (cnt >= CAP && !(lnew > -1.0e29f)) {   // rounding fall-through with no new-table mass: last live table
       choice = t0;
 #pragma unroll
-      for (int t = 0; t < CAP; ++t) if (lw[t] > 1.0e-30f) choice = t;
+      for (int i = 0; i < CAP / 2; ++i) {
+        if (lw2[i].x > 1.0e-30f) choice = 2 * i;
+        if (lw2[i].y > 1.0e-30f) choice = 2 * i + 1;
+      }
     }
     return choice;
   }

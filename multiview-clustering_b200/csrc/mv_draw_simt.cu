@@ -20,7 +20,8 @@ __global__ void __launch_bounds__(kSimtThreads, 2) k_draw_simt(const Ctx c) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   float* s_m = reinterpret_cast<float*>(smem_raw);                       // [CAP][dch]
   const int dch_max = (c.Dsum < kSimtDChunk) ? c.Dsum : kSimtDChunk;     // upper bound on any view's chunk
-  TableParam* s_tp = reinterpret_cast<TableParam*>(smem_raw + sizeof(float) * (size_t)CAP * (size_t)dch_max);
+  PairHot* s_hot = reinterpret_cast<PairHot*>(smem_raw + sizeof(float) * (size_t)CAP * (size_t)dch_max);   // [CAP/2]
+  TableCold* s_cold = reinterpret_cast<TableCold*>(s_hot + CAP / 2);                                        // [CAP]
   __shared__ TableMass s_tm[CAP];
   __shared__ GlobalParam s_g;
   __shared__ ViewParam s_vp;
@@ -50,13 +51,13 @@ __global__ void __launch_bounds__(kSimtThreads, 2) k_draw_simt(const Ctx c) {
 
       for (int d0 = 0; d0 < D; d0 += kSimtDChunk) {
         const int dch = (D - d0 < kSimtDChunk) ? (D - d0) : kSimtDChunk;
-        __syncthreads();   // previous users of s_m / s_tp are done
+        __syncthreads();   // previous users of s_m / s_hot / s_cold are done
         for (int idx = tid; idx < CAP * dch; idx += kSimtThreads) {
           const int t = idx / dch, dd = idx - t * dch;
           s_m[t * dch + dd] = mean_v[(size_t)t * D + d0 + dd];
         }
         if (d0 == 0) {
-          for (int t = tid; t < CAP; t += kSimtThreads) s_tp[t] = c.tparam[v * CAP + t];
+          stage_view_params(c.tparam + v * CAP, CAP, s_hot, s_cold, tid, kSimtThreads);
           if (tid == 0) s_vp = c.vparam[v];
         }
         __syncthreads();
@@ -93,7 +94,7 @@ __global__ void __launch_bounds__(kSimtThreads, 2) k_draw_simt(const Ctx c) {
         for (int t = 0; t < CAP; ++t) da[t] = acc[t];
         c.dbg_xx[(size_t)row * c.V + v] = xx;
       }
-      epi.view(s_tp, s_vp, acc, xx);
+      epi.view(s_hot, s_cold, s_vp, acc, xx);
     }
 
     const U4 rnd = stream_block(c.seed, c.chain, kDomTable, 0, sweep, (uint64_t)(c.row_offset + rowc));

@@ -58,7 +58,7 @@ struct SmemLayout {
   static constexpr int b_off = 0;                                            // [V][hi,lo][2 halves][8 KB]
   static constexpr int raw_off = b_off + kMaxTcViews * 4 * kBHalfBytes;      // 96 KB
   static constexpr int tp_off = raw_off + kRawStages * kHalfBytes;           // +112 KB
-  static constexpr int tm_off = tp_off + kMaxTcViews * 64 * (int)sizeof(TableParam);
+  static constexpr int tm_off = tp_off + kMaxTcViews * 64 * (int)sizeof(TableParam);   // per view: PairHot[32] then TableCold[64]
   static constexpr int vp_off = tm_off + 64 * (int)sizeof(TableMass);
   static constexpr int xx_off = vp_off + kMaxTcViews * (int)sizeof(ViewParam);
   static constexpr int bar_off = xx_off + kXxSlots * 2 * kTileRows * (int)sizeof(float);   // [slot][K-half][row]
@@ -203,7 +203,7 @@ __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.
 // One 16-table chunk of one view: wait for its columns (already requested into `cur`), request the
 // next chunk into `nxt` so that the TMEM read overlaps this chunk's arithmetic, then run the epilogue.
 template <int BASE, bool FAST>
-__device__ __forceinline__ void epi_chunk(RowEpilogue<64, FAST>& epi, const TableParam* tpv, uint32_t taddr,
+__device__ __forceinline__ void epi_chunk(RowEpilogue<64, FAST>& epi, const PairHot* hot, const TableCold* cold, uint32_t taddr,
                                           uint32_t (&cur)[16], uint32_t (&nxt)[16], const Ctx& c, int row, int v, bool live) {
   tmem_ld_wait();
   if (BASE + 16 < 64) tmem_ld_16(taddr + BASE + 16, nxt);
@@ -215,7 +215,7 @@ __device__ __forceinline__ void epi_chunk(RowEpilogue<64, FAST>& epi, const Tabl
 #pragma unroll
     for (int t = 0; t < 16; ++t) da[t] = ch[t];
   }
-  epi.template view_chunk<BASE>(tpv, ch);
+  epi.template view_chunk<BASE>(hot, cold, ch);
 }
 
 template <bool FAST>
@@ -225,7 +225,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_draw_tc(const Ctx c, const __gr
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int V = c.V;
 
-  TableParam* s_tp = reinterpret_cast<TableParam*>(smem + SmemLayout::tp_off);
+  unsigned char* s_tp = smem + SmemLayout::tp_off;   // per view 2 KB: PairHot[32] (hot, pair-interleaved) then TableCold[64]
   TableMass* s_tm = reinterpret_cast<TableMass*>(smem + SmemLayout::tm_off);
   ViewParam* s_vp = reinterpret_cast<ViewParam*>(smem + SmemLayout::vp_off);
   float* s_xx = reinterpret_cast<float*>(smem + SmemLayout::xx_off);             // [stage][K-half][row]
@@ -243,7 +243,9 @@ __global__ void __launch_bounds__(kThreads, 1) k_draw_tc(const Ctx c, const __gr
   const uint32_t b_full = bar0 + 8u * (2 * kRawStages + 2 * kLoStages + 2 * kDStages + kXxSlots);
 
   // ---- one-time setup --------------------------------------------------------------------------
-  for (int i = tid; i < V * 64; i += kThreads) s_tp[i] = c.tparam[i];
+  for (int v = 0; v < V; ++v)
+    stage_view_params(c.tparam + v * 64, 64, reinterpret_cast<PairHot*>(s_tp + v * 2048),
+                      reinterpret_cast<TableCold*>(s_tp + v * 2048 + 1024), tid, kThreads);
   for (int i = tid; i < 64; i += kThreads) s_tm[i] = c.tmass[i];
   if (tid < V) s_vp[tid] = c.vparam[tid];
   if (tid == 0) {
@@ -435,17 +437,18 @@ __global__ void __launch_bounds__(kThreads, 1) k_draw_tc(const Ctx c, const __gr
         tc_fence_after();
         const uint32_t taddr = tmem_base + lane_base + (uint32_t)(stage * 64);
         const float xx = __fadd_rn(s_xx[(xs * 2 + 0) * kTileRows + r], s_xx[(xs * 2 + 1) * kTileRows + r]);
-        const TableParam* tpv = s_tp + v * 64;
-        epi.view_begin(tpv, xx);
+        const PairHot* hot = reinterpret_cast<const PairHot*>(s_tp + v * 2048);
+        const TableCold* cold = reinterpret_cast<const TableCold*>(s_tp + v * 2048 + 1024);
+        epi.view_begin(hot, cold, xx);
         if ((c.debug_export & 1) && live) c.dbg_xx[(size_t)row * V + v] = xx;
         uint32_t ua[16], ub[16];
         tmem_ld_16(taddr, ua);
-        epi_chunk<0>(epi, tpv, taddr, ua, ub, c, row, v, live);
-        epi_chunk<16>(epi, tpv, taddr, ub, ua, c, row, v, live);
-        epi_chunk<32>(epi, tpv, taddr, ua, ub, c, row, v, live);
+        epi_chunk<0>(epi, hot, cold, taddr, ua, ub, c, row, v, live);
+        epi_chunk<16>(epi, hot, cold, taddr, ub, ua, c, row, v, live);
+        epi_chunk<32>(epi, hot, cold, taddr, ua, ub, c, row, v, live);
         tc_fence_before();
         mbar_arrive(d_empty(stage));                  // all four chunks are in registers: the accumulator tile and xx slot are free
-        epi_chunk<48>(epi, tpv, taddr, ub, ua, c, row, v, live);
+        epi_chunk<48>(epi, hot, cold, taddr, ub, ua, c, row, v, live);
         epi.view_end(s_vp[v], xx);
       }
       const U4 rnd = stream_block(c.seed, c.chain, kDomTable, 0, sweep, (uint64_t)(c.row_offset + rowc));
