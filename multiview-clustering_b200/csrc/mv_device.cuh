@@ -173,42 +173,47 @@ __device__ __forceinline__ void stage_view_params(const TableParam* __restrict__
 }
 
 // ---- one customer's epilogue ---------------------------------------------------------------
-// Order of operations (restated by oracle/mv_oracle.c:mvo_stageB_f32):
-//   begin       lw[t] = log2 mass of table t (customer removed), lnew = log2 mass of a new table
-//   view_begin / view_chunk x CAP/16 / view_end, once per view:
-//               L[t] = log2 f under table t's dish (leave-one-out for the customer's own dish),
-//               lw[t] += L[t]; streaming log-sum-exp over the dishes in chunks of 16 tables
-//               (running max mx, sum s rescaled when mx moves), then the new-dish term
-//               -> marginal of a new table -> lnew
-//   finish      max-normalised weights, total, inverse-CDF count
-// Chunks of 16 keep the live state at lw[CAP] + 16 terms, so the tensor-core kernel can feed a chunk
-// straight from one tcgen05.ld.x16 and stay inside its register budget (measured: no spills at 168).
+// The cap table slots of a customer are handled as two HALVES of cap/2 tables.  In the tensor-core
+// kernel two threads (one per half) share a customer and trade a few scalars through shared memory;
+// in the CUDA-core kernel one thread runs both halves back to back.  Either way the arithmetic is the
+// sequence below, restated by oracle/mv_oracle.c:mvo_stageB_f32:
+//   begin        lw[t] = log2 mass of table t (customer removed)
+//   per view     view_begin, view_chunk x (cap/2)/16: L[t] = log2 f under table t's dish (leave-one-out
+//                for the customer's own dish), lw[t] += L[t], streaming log-sum-exp (running max mx,
+//                sum s) over this half's dishes;  merge_view: the two halves' (mx, s) and the new-dish
+//                term -> log2 marginal of a new table, added to lnew
+//   draw         M = max over both halves and lnew; weights(M) -> half totals HA, HB;
+//                total = (HA + HB) + 2^(lnew - M); target = u * total; scan: half A counts its
+//                cumulative weights <= target starting from 0, half B starting from HA;
+//                choice = count (cap = new table)
 constexpr int kEpiChunk = 16;
 
-template <int CAP, bool FAST = false>
-struct RowEpilogue {
-  static_assert(CAP % kEpiChunk == 0, "table capacity must be a multiple of the epilogue chunk");
-  float2 lw2[CAP / 2];   // running log2 weight of tables (2i, 2i+1)
-  float lnew;            // running log2 weight of a new table
-  int t0;                // current table of the customer
+template <int HALF, bool FAST = false>
+struct HalfEpilogue {
+  static_assert(HALF % kEpiChunk == 0, "half of the table capacity must be a multiple of the epilogue chunk");
+  float2 lw2[HALF / 2];  // running log2 weight of tables tbase + (2i, 2i+1); after weights(): the weights
+  int t0;                // current table of the customer (absolute slot)
   int single;            // the customer sits alone at t0
+  int any_single;        // some customer of this warp does (warp-uniform slow path)
   // per-view state
   float mx, s, nxx, A1r, C1r;
-  int k0, lone0, any_single;
+  int k0, lone0;
 
-  __device__ __forceinline__ void begin(const TableMass* __restrict__ tm, const GlobalParam& g, int t0_) {
+  // tm: all cap table masses; this object covers tables [tbase, tbase + HALF).
+  __device__ __forceinline__ void begin(const TableMass* __restrict__ tm, int t0_, int tbase) {
     t0 = t0_;
     const TableMass own = tm[t0_];
     single = own.single;
-    any_single = __any_sync(0xffffffffu, single);   // customers alone at their table are rare: warp-uniform slow path
-    lnew = single ? g.LMN1 : g.LMN0;
+    any_single = __any_sync(0xffffffffu, single);
+    const int rel = t0_ - tbase;
 #pragma unroll
-    for (int i = 0; i < CAP / 2; ++i) {
-      lw2[i].x = (2 * i == t0_) ? own.LM1 : tm[2 * i].LM;
-      lw2[i].y = (2 * i + 1 == t0_) ? own.LM1 : tm[2 * i + 1].LM;
+    for (int i = 0; i < HALF / 2; ++i) {
+      lw2[i].x = (2 * i == rel) ? own.LM1 : tm[tbase + 2 * i].LM;
+      lw2[i].y = (2 * i + 1 == rel) ? own.LM1 : tm[tbase + 2 * i + 1].LM;
     }
   }
 
+  // hot/cold: the FULL per-view arrays (the customer's own table may lie in the other half).
   __device__ __forceinline__ void view_begin(const PairHot* __restrict__ hot, const TableCold* __restrict__ cold, float xx) {
     const TableCold own = cold[t0];
     k0 = reinterpret_cast<const int32_t*>(&hot[t0 >> 1].dish0)[t0 & 1];
@@ -218,17 +223,17 @@ struct RowEpilogue {
     s = 0.0f;
   }
 
-  // acc[j] = x . m_{v, BASE + j} for the kEpiChunk tables of chunk BASE / kEpiChunk (consumed).
+  // hoth/coldh: the arrays offset to this half's first table.  acc[j] = x . m_{tbase + BASE + j} (consumed).
   template <int BASE, bool SINGLE>
-  __device__ __forceinline__ void chunk_impl(const PairHot* __restrict__ hot, const TableCold* __restrict__ cold,
+  __device__ __forceinline__ void chunk_impl(const PairHot* __restrict__ hoth, const TableCold* __restrict__ coldh,
                                              float (&acc)[kEpiChunk]) {
     float2 term[kEpiChunk / 2];
     float c0 = kMasked, c1 = kMasked;
     const float2 two = splat2(2.0f), nxx2 = splat2(nxx), a1r2 = splat2(A1r), c1r2 = splat2(C1r);
 #pragma unroll
     for (int p = 0; p < kEpiChunk / 2; ++p) {
-      const float4 qa = reinterpret_cast<const float4*>(&hot[BASE / 2 + p])[0];   // A0 A1 C0 C1
-      const float4 qb = reinterpret_cast<const float4*>(&hot[BASE / 2 + p])[1];   // W0 W1 dish0 dish1
+      const float4 qa = reinterpret_cast<const float4*>(&hoth[BASE / 2 + p])[0];   // A0 A1 C0 C1
+      const float4 qb = reinterpret_cast<const float4*>(&hoth[BASE / 2 + p])[1];   // W0 W1 dish0 dish1
       const float2 e = ffma2(two, make_float2(acc[2 * p], acc[2 * p + 1]), nxx2);
       const float2 Lg = ffma2(make_float2(qa.x, qa.y), e, make_float2(qa.z, qa.w));
       const float2 Ls = ffma2(a1r2, e, c1r2);
@@ -237,8 +242,8 @@ struct RowEpilogue {
       lw2[BASE / 2 + p] = fadd2(lw2[BASE / 2 + p], L);
       float2 w = make_float2(qb.x, qb.y);
       if (SINGLE) {
-        if (same0 && single) w.x = cold[BASE + 2 * p].W1;
-        if (same1 && single) w.y = cold[BASE + 2 * p + 1].W1;
+        if (same0 && single) w.x = coldh[BASE + 2 * p].W1;
+        if (same1 && single) w.y = coldh[BASE + 2 * p + 1].W1;
       }
       term[p] = fadd2(L, w);
       c0 = fmaxf(c0, term[p].x);
@@ -259,75 +264,116 @@ struct RowEpilogue {
   }
 
   template <int BASE>
-  __device__ __forceinline__ void view_chunk(const PairHot* __restrict__ hot, const TableCold* __restrict__ cold,
+  __device__ __forceinline__ void view_chunk(const PairHot* __restrict__ hoth, const TableCold* __restrict__ coldh,
                                              float (&acc)[kEpiChunk]) {
-    if (any_single) chunk_impl<BASE, true>(hot, cold, acc);
-    else chunk_impl<BASE, false>(hot, cold, acc);
+    if (any_single) chunk_impl<BASE, true>(hoth, coldh, acc);
+    else chunk_impl<BASE, false>(hoth, coldh, acc);
   }
 
-  __device__ __forceinline__ void view_end(const ViewParam& vp, float xx) {
-    const float Lnew = __fmaf_rn(-vp.AN, xx, vp.CN);
-    const float termnew = __fadd_rn(Lnew, (single && lone0) ? vp.WN1 : vp.WN0);
-    const float mn = fmaxf(mx, termnew);
-    s = __fmul_rn(s, exp2w<FAST>(__fadd_rn(mx, -mn)));
-    s = __fadd_rn(s, exp2w<FAST>(__fadd_rn(termnew, -mn)));
-    const float logmarg = __fadd_rn(__fadd_rn(mn, log2m(s)), -(single ? vp.LD1 : vp.LD0));
-    lnew = __fadd_rn(lnew, logmarg);
-  }
-
-  // Whole view from an array of CAP dot products (CUDA-core engine).
+  // All chunks of this half from an array of HALF dot products (CUDA-core engine).
   template <int BASE>
-  __device__ __forceinline__ void view_chunks_from(const PairHot* __restrict__ hot, const TableCold* __restrict__ cold,
-                                                   float (&acc)[CAP]) {
-    if constexpr (BASE < CAP) {
+  __device__ __forceinline__ void view_chunks_from(const PairHot* __restrict__ hoth, const TableCold* __restrict__ coldh,
+                                                   const float* acc) {
+    if constexpr (BASE < HALF) {
       float ch[kEpiChunk];
 #pragma unroll
       for (int j = 0; j < kEpiChunk; ++j) ch[j] = acc[BASE + j];
-      view_chunk<BASE>(hot, cold, ch);
-      view_chunks_from<BASE + kEpiChunk>(hot, cold, acc);
+      view_chunk<BASE>(hoth, coldh, ch);
+      view_chunks_from<BASE + kEpiChunk>(hoth, coldh, acc);
     }
   }
-  __device__ __forceinline__ void view(const PairHot* __restrict__ hot, const TableCold* __restrict__ cold,
-                                       const ViewParam& vp, float (&acc)[CAP], float xx) {
-    view_begin(hot, cold, xx);
-    view_chunks_from<0>(hot, cold, acc);
-    view_end(vp, xx);
+
+  __device__ __forceinline__ float halfmax() const {
+    float M0 = kMasked, M1 = kMasked;
+#pragma unroll
+    for (int i = 0; i < HALF / 2; ++i) { M0 = fmaxf(M0, lw2[i].x); M1 = fmaxf(M1, lw2[i].y); }
+    return fmaxf(M0, M1);
   }
 
-  // uf in (0,1). Returns the table slot or kNewTable.  lw2[] is left holding the weights.
-  __device__ __forceinline__ int finish(float uf) {
-    float M0 = lnew, M1 = kMasked;
-#pragma unroll
-    for (int i = 0; i < CAP / 2; ++i) { M0 = fmaxf(M0, lw2[i].x); M1 = fmaxf(M1, lw2[i].y); }
-    const float M = fmaxf(M0, M1);
-    if (!(M > -1.0e29f)) return t0;   // nothing has weight: stay (cf. multiview_gibbs.cpp:172-176)
+  // lw2 <- 2^(lw2 - M); returns this half's total (partial sums over t mod 4, then a fixed tree).
+  __device__ __forceinline__ float weights(float M) {
     const float2 nM2 = splat2(-M);
-    float2 qa = splat2(0.0f), qb = splat2(0.0f);          // partial sums over t mod 4 = (0,1) and (2,3)
+    float2 qa = splat2(0.0f), qb = splat2(0.0f);
 #pragma unroll
-    for (int i = 0; i < CAP / 2; i += 2) {
+    for (int i = 0; i < HALF / 2; i += 2) {
       lw2[i] = exp2w2<FAST>(fadd2(lw2[i], nM2));         qa = fadd2(qa, lw2[i]);
       lw2[i + 1] = exp2w2<FAST>(fadd2(lw2[i + 1], nM2)); qb = fadd2(qb, lw2[i + 1]);
     }
-    const float total = __fadd_rn(__fadd_rn(__fadd_rn(qa.x, qa.y), __fadd_rn(qb.x, qb.y)), exp2w<FAST>(__fadd_rn(lnew, -M)));
-    const float target = __fmul_rn(uf, total);
-    // first t with target < cum_t  ==  number of t with cum_t <= target (cum is non-decreasing)
-    float cum = 0.0f;
+    return __fadd_rn(__fadd_rn(qa.x, qa.y), __fadd_rn(qb.x, qb.y));
+  }
+
+  // Number of this half's tables whose cumulative weight (starting from cum0) is <= target.
+  __device__ __forceinline__ int scan(float target, float cum0) const {
+    float cum = cum0;
     int cnt = 0;
 #pragma unroll
-    for (int i = 0; i < CAP / 2; ++i) {
+    for (int i = 0; i < HALF / 2; ++i) {
       cum = __fadd_rn(cum, lw2[i].x);
       cnt += (target < cum) ? 0 : 1;
       cum = __fadd_rn(cum, lw2[i].y);
       cnt += (target < cum) ? 0 : 1;
     }
+    return cnt;
+  }
+
+  // Highest table of this half (relative index) that still has weight, or -1.
+  __device__ __forceinline__ int last_live() const {
+    int last = -1;
+#pragma unroll
+    for (int i = 0; i < HALF / 2; ++i) {
+      if (lw2[i].x > 1.0e-30f) last = 2 * i;
+      if (lw2[i].y > 1.0e-30f) last = 2 * i + 1;
+    }
+    return last;
+  }
+};
+
+// log2 marginal of a new table in one view from the two halves' streaming sums (half A first).
+template <bool FAST>
+__device__ __forceinline__ float merge_view(float mxA, float sA, float mxB, float sB, const ViewParam& vp, float xx,
+                                            int single, int lone0) {
+  float mn = fmaxf(mxA, mxB);
+  float s = __fadd_rn(__fmul_rn(sA, exp2w<FAST>(__fadd_rn(mxA, -mn))), __fmul_rn(sB, exp2w<FAST>(__fadd_rn(mxB, -mn))));
+  const float Lnew = __fmaf_rn(-vp.AN, xx, vp.CN);
+  const float termnew = __fadd_rn(Lnew, (single && lone0) ? vp.WN1 : vp.WN0);
+  const float m2 = fmaxf(mn, termnew);
+  s = __fmul_rn(s, exp2w<FAST>(__fadd_rn(mn, -m2)));
+  s = __fadd_rn(s, exp2w<FAST>(__fadd_rn(termnew, -m2)));
+  return __fadd_rn(__fadd_rn(m2, log2m(s)), -(single ? vp.LD1 : vp.LD0));
+}
+
+// The whole draw of one customer by ONE thread (CUDA-core engine): both halves back to back.
+template <int CAP, bool FAST = false>
+struct RowEpilogue {
+  static constexpr int HALF = CAP / 2;
+  HalfEpilogue<HALF, FAST> ha, hb;
+  float lnew;
+
+  __device__ __forceinline__ void begin(const TableMass* __restrict__ tm, const GlobalParam& g, int t0) {
+    ha.begin(tm, t0, 0);
+    hb.begin(tm, t0, HALF);
+    lnew = ha.single ? g.LMN1 : g.LMN0;
+  }
+  __device__ __forceinline__ void view(const PairHot* __restrict__ hot, const TableCold* __restrict__ cold,
+                                       const ViewParam& vp, const float (&acc)[CAP], float xx) {
+    ha.view_begin(hot, cold, xx);
+    ha.template view_chunks_from<0>(hot, cold, acc);
+    hb.view_begin(hot, cold, xx);
+    hb.template view_chunks_from<0>(hot + HALF / 2, cold + HALF, acc + HALF);
+    lnew = __fadd_rn(lnew, merge_view<FAST>(ha.mx, ha.s, hb.mx, hb.s, vp, xx, ha.single, ha.lone0));
+  }
+  // uf in (0,1). Returns the table slot or kNewTable.
+  __device__ __forceinline__ int finish(float uf) {
+    const float M = fmaxf(fmaxf(lnew, ha.halfmax()), hb.halfmax());
+    if (!(M > -1.0e29f)) return ha.t0;   // nothing has weight: stay (cf. multiview_gibbs.cpp:172-176)
+    const float HA = ha.weights(M), HB = hb.weights(M);
+    const float total = __fadd_rn(__fadd_rn(HA, HB), exp2w<FAST>(__fadd_rn(lnew, -M)));
+    const float target = __fmul_rn(uf, total);
+    const int cnt = ha.scan(target, 0.0f) + hb.scan(target, HA);
     int choice = (cnt < CAP) ? cnt : kNewTable;
     if (cnt >= CAP && !(lnew > -1.0e29f)) {   // rounding fall-through with no new-table mass: last live table
-      choice = t0;
-#pragma unroll
-      for (int i = 0; i < CAP / 2; ++i) {
-        if (lw2[i].x > 1.0e-30f) choice = 2 * i;
-        if (lw2[i].y > 1.0e-30f) choice = 2 * i + 1;
-      }
+      const int lb = hb.last_live(), la = ha.last_live();
+      choice = (lb >= 0) ? (HALF + lb) : ((la >= 0) ? la : ha.t0);
     }
     return choice;
   }

@@ -5,7 +5,7 @@
 //
 //   TMA producer (1 thread)    cp.async.bulk.tensor: the tile's [128 x 64] FP32 features arrive in
 //                              shared memory as two K-halves of [128 x 32] in the 128B-swizzled
-//                              K-major layout UMMA reads directly (7-deep ring, 112 KB in flight).
+//                              K-major layout UMMA reads directly (6-deep ring, 96 KB in flight).
 //   converters (2 x 128 thr.)  one warpgroup per K-half; thread r owns customer r: partial |x|^2 and
 //                              the TF32 remainder x_lo = rn_tf32(x - trunc_tf32(x)), written with
 //                              tcgen05.st into TMEM lane r (the remainder tile never touches shared memory).
@@ -14,10 +14,14 @@
 //                              hardware reads the top 19 bits of each FP32 word, so it serves as
 //                              x_hi) and x_lo.m_hi (A = the remainder tile in TMEM).  The split
 //                              restores ~2^-19 relative accuracy (north_star: FP32 tolerance).
-//   epilogue (2 x 128 threads) two warpgroups take alternate row tiles.  tcgen05.ld: thread r owns
-//                              TMEM lane r = customer r: its 64 dot products arrive 16 at a time and
-//                              feed RowEpilogue (mv_device.cuh) — leave-one-out weights, streaming
-//                              log-sum-exp marginal, inverse-CDF draw.
+//   epilogue (4 x 128 threads) two PAIRS of warpgroups take alternate row tiles; inside a pair each
+//                              warpgroup owns one half of the 64 tables.  tcgen05.ld: thread r of either
+//                              warpgroup reads TMEM lane r = customer r, 16 dot products at a time, and
+//                              feeds HalfEpilogue (mv_device.cuh): leave-one-out weights and a streaming
+//                              log-sum-exp over its half.  The two threads of a customer trade nine
+//                              scalars through shared memory (three named-barrier rendezvous per tile)
+//                              to merge marginals, totals and the inverse-CDF counts.  Twice the warps
+//                              at half the registers each: the epilogue is latency-bound, not issue-bound.
 //
 // TMEM (512 columns): [0,384) six accumulator tiles, [384,512) two remainder tiles.
 // The [N x 64] log-likelihood matrices never exist in memory: HBM traffic is the features once
@@ -37,14 +41,15 @@ constexpr int kTileRows = 128;
 constexpr int kHalfCols = 32;                       // floats per 128-byte swizzled row
 constexpr int kHalfBytes = kTileRows * 128;         // 16 KB: one K-half of an A tile
 constexpr int kBHalfBytes = 64 * 128;               // 8 KB: one K-half of a B matrix (64 tables)
-constexpr int kRawStages = 7;                       // K-halves of raw features in flight
+constexpr int kRawStages = 6;                       // K-halves of raw features in flight (96 KB)
 constexpr int kLoStages = 2;                        // TMEM remainder tiles (64 columns each)
 constexpr int kDStages = 6;                         // TMEM accumulator tiles (64 columns each): one whole row tile (3 views) per epilogue warpgroup
 constexpr int kXxSlots = 8;                         // ring of per-row |x|^2 partials; >= kDStages + kLoStages keeps it race-free
 constexpr int kTmemCols = 512;
 constexpr int kLoCol0 = kDStages * 64;              // first TMEM column of the remainder tiles
 constexpr int kMaxTcViews = 3;
-constexpr int kThreads = 640;                       // WG0: control, WG1+WG2: converters (one per K-half), WG3+WG4: epilogue (alternate tiles)
+constexpr int kThreads = 896;                       // WG0: control, WG1+WG2: converters (one per K-half), WG3..WG6: epilogue
+constexpr int kExFields = 9;                        // scalars two epilogue threads of one customer trade per tile
 constexpr int kEpiGroups = 2;
 
 struct __align__(64) TcMaps {
@@ -61,7 +66,8 @@ struct SmemLayout {
   static constexpr int tm_off = tp_off + kMaxTcViews * 64 * (int)sizeof(TableParam);   // per view: PairHot[32] then TableCold[64]
   static constexpr int vp_off = tm_off + 64 * (int)sizeof(TableMass);
   static constexpr int xx_off = vp_off + kMaxTcViews * (int)sizeof(ViewParam);
-  static constexpr int bar_off = xx_off + kXxSlots * 2 * kTileRows * (int)sizeof(float);   // [slot][K-half][row]
+  static constexpr int ex_off = xx_off + kXxSlots * 2 * kTileRows * (int)sizeof(float);    // xx: [slot][K-half][row]
+  static constexpr int bar_off = ex_off + 4 * kExFields * kTileRows * (int)sizeof(float);   // ex: [pair][half][field][row]
   static constexpr int n_bars = 2 * kRawStages + 2 * kLoStages + 2 * kDStages + kXxSlots + 1;
   static constexpr int misc_off = bar_off + n_bars * 8;
   static constexpr int total = misc_off + 64;
@@ -200,22 +206,20 @@ __device__ __forceinline__ void tmem_ld_16(uint32_t taddr, uint32_t (&u)[16]) {
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
-// One 16-table chunk of one view: wait for its columns (already requested into `cur`), request the
-// next chunk into `nxt` so that the TMEM read overlaps this chunk's arithmetic, then run the epilogue.
+// One 16-table chunk of one view (its dot products already sit in `cur`): export them when asked, then
+// run the half-epilogue on them.
 template <int BASE, bool FAST>
-__device__ __forceinline__ void epi_chunk(RowEpilogue<64, FAST>& epi, const PairHot* hot, const TableCold* cold, uint32_t taddr,
-                                          uint32_t (&cur)[16], uint32_t (&nxt)[16], const Ctx& c, int row, int v, bool live) {
-  tmem_ld_wait();
-  if (BASE + 16 < 64) tmem_ld_16(taddr + BASE + 16, nxt);
+__device__ __forceinline__ void epi_chunk(HalfEpilogue<32, FAST>& epi, const PairHot* hoth, const TableCold* coldh,
+                                          uint32_t (&cur)[16], const Ctx& c, int row, int v, int tbase, bool live) {
   float ch[16];
 #pragma unroll
   for (int t = 0; t < 16; ++t) ch[t] = __uint_as_float(cur[t]);
   if ((c.debug_export & 1) && live) {
-    float* da = c.dbg_acc + ((size_t)row * c.V + v) * 64 + BASE;
+    float* da = c.dbg_acc + ((size_t)row * c.V + v) * 64 + tbase + BASE;
 #pragma unroll
     for (int t = 0; t < 16; ++t) da[t] = ch[t];
   }
-  epi.template view_chunk<BASE>(hot, cold, ch);
+  epi.template view_chunk<BASE>(hoth, coldh, ch);
 }
 
 template <bool FAST>
@@ -255,7 +259,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_draw_tc(const Ctx c, const __gr
     s_misc[3] = __float_as_uint(g.LMN1);
     for (int s = 0; s < kRawStages; ++s) { mbar_init(raw_full(s), 1); mbar_init(raw_empty(s), 129); }   // one converter warpgroup + the MMA commit
     for (int s = 0; s < kLoStages; ++s) { mbar_init(lo_full(s), 256); mbar_init(lo_empty(s), 1); }      // both converter warpgroups
-    for (int s = 0; s < kDStages; ++s) { mbar_init(d_full(s), 1); mbar_init(d_empty(s), 128); }
+    for (int s = 0; s < kDStages; ++s) { mbar_init(d_full(s), 1); mbar_init(d_empty(s), 256); }   // both halves of a pair
     for (int s = 0; s < kXxSlots; ++s) mbar_init(xx_full(s), 256);
     mbar_init(b_full, 1);
     fence_barrier_init();
@@ -366,7 +370,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_draw_tc(const Ctx c, const __gr
     }
   } else if (warp < 12) {
     // =========================== WG1, WG2: converters, one K-half each ===========================
-    reg_dec<56>();
+    reg_dec<48>();
     const int h = (warp >> 2) - 1;                     // K-half of this warpgroup
     const int r = tid & 127;                           // row of the tile = 128-byte line of the half = TMEM lane
     const uint32_t lane_base = (uint32_t)((warp & 3) * 32) << 16;
@@ -415,18 +419,26 @@ __global__ void __launch_bounds__(kThreads, 1) k_draw_tc(const Ctx c, const __gr
       }
     if (prof && r == 0) { prof_out[6 + 3 * h] = w0; prof_out[7 + 3 * h] = w1; prof_out[8 + 3 * h] = clock64() - t_start; }
   } else {
-    // =========================== WG3, WG4: epilogue (thread r <-> TMEM lane r <-> customer r) ====
-    reg_inc<168>();   // pool: 640 threads x 96 registers; 24 + 56 + 56 + 168 + 168 = 472 <= 480 per thread-slot
-    const int grp = (warp >> 2) - 3;                   // 0 or 1: this warpgroup takes tiles j = grp, grp+2, ...
+    // =========================== WG3..WG6: epilogue (thread r <-> TMEM lane r <-> customer r) ====
+    // pool: 896 threads x 72 registers = 128 x (24 + 2*48 + 4*96)
+    reg_inc<96>();
+    const int wg = (warp >> 2) - 3;
+    const int pair = wg >> 1;                          // this pair takes tiles j = pair, pair+2, ...
+    const int hf = wg & 1;                             // tables [32 hf, 32 hf + 32)
     const int r = tid & 127;
     const uint32_t lane_base = (uint32_t)((warp & 3) * 32) << 16;
-    int j = grp;
-    for (int tile = blockIdx.x + grp * gridDim.x; tile < n_tiles; tile += kEpiGroups * gridDim.x, j += kEpiGroups) {
+    float* ex_own = reinterpret_cast<float*>(smem + SmemLayout::ex_off) + ((pair * 2 + hf) * kExFields) * kTileRows + r;
+    float* ex_oth = reinterpret_cast<float*>(smem + SmemLayout::ex_off) + ((pair * 2 + (hf ^ 1)) * kExFields) * kTileRows + r;
+    auto rendezvous = [&]() { asm volatile("bar.sync %0, 256;" ::"r"(1 + pair) : "memory"); };
+    int j = pair;
+    for (int tile = blockIdx.x + pair * gridDim.x; tile < n_tiles; tile += kEpiGroups * gridDim.x, j += kEpiGroups) {
       const int row = tile * kTileRows + r;
       const bool live = row < c.n_rows;
       const int rowc = live ? row : (c.n_rows - 1);
-      RowEpilogue<64, FAST> epi;
-      epi.begin(s_tm, gp, c.table_cur[rowc]);
+      HalfEpilogue<32, FAST> epi;
+      epi.begin(s_tm, c.table_cur[rowc], 32 * hf);
+      float lnew = epi.single ? gp.LMN1 : gp.LMN0;
+      float xxv[kMaxTcViews];
       for (int v = 0; v < V; ++v) {
         const int idx = j * V + v;
         const int stage = idx % kDStages;
@@ -435,32 +447,81 @@ __global__ void __launch_bounds__(kThreads, 1) k_draw_tc(const Ctx c, const __gr
         mbar_wait_t(d_full(stage), phase, prof, w0);
         mbar_wait_t(xx_full(xs), (uint32_t)(idx / kXxSlots) & 1u, prof, w1);
         tc_fence_after();
-        const uint32_t taddr = tmem_base + lane_base + (uint32_t)(stage * 64);
+        const uint32_t taddr = tmem_base + lane_base + (uint32_t)(stage * 64 + 32 * hf);
         const float xx = __fadd_rn(s_xx[(xs * 2 + 0) * kTileRows + r], s_xx[(xs * 2 + 1) * kTileRows + r]);
         const PairHot* hot = reinterpret_cast<const PairHot*>(s_tp + v * 2048);
         const TableCold* cold = reinterpret_cast<const TableCold*>(s_tp + v * 2048 + 1024);
         epi.view_begin(hot, cold, xx);
-        if ((c.debug_export & 1) && live) c.dbg_xx[(size_t)row * V + v] = xx;
+        if ((c.debug_export & 1) && live && hf == 0) c.dbg_xx[(size_t)row * V + v] = xx;
         uint32_t ua[16], ub[16];
         tmem_ld_16(taddr, ua);
-        epi_chunk<0>(epi, hot, cold, taddr, ua, ub, c, row, v, live);
-        epi_chunk<16>(epi, hot, cold, taddr, ub, ua, c, row, v, live);
-        epi_chunk<32>(epi, hot, cold, taddr, ua, ub, c, row, v, live);
+        tmem_ld_wait();
+        tmem_ld_16(taddr + 16, ub);
+        epi_chunk<0>(epi, hot + 16 * hf, cold + 32 * hf, ua, c, row, v, 32 * hf, live);
+        tmem_ld_wait();
         tc_fence_before();
-        mbar_arrive(d_empty(stage));                  // all four chunks are in registers: the accumulator tile and xx slot are free
-        epi_chunk<48>(epi, hot, cold, taddr, ub, ua, c, row, v, live);
-        epi.view_end(s_vp[v], xx);
+        mbar_arrive(d_empty(stage));                  // this half's columns are in registers
+        epi_chunk<16>(epi, hot + 16 * hf, cold + 32 * hf, ub, c, row, v, 32 * hf, live);
+        ex_own[(2 * v) * kTileRows] = epi.mx;
+        ex_own[(2 * v + 1) * kTileRows] = epi.s;
+        if (v == 0) xxv[0] = xx; else if (v == 1) xxv[1] = xx; else xxv[2] = xx;
       }
-      const U4 rnd = stream_block(c.seed, c.chain, kDomTable, 0, sweep, (uint64_t)(c.row_offset + rowc));
-      const int choice = epi.finish(uniform_f32_from(rnd.x));
-      if (live) {
-        c.choice[row] = choice;
-        if (c.debug_export & 1) c.dbg_choice[row] = choice;
+      float uf = 0.0f;
+      if (hf == 0) {
+        const U4 rnd = stream_block(c.seed, c.chain, kDomTable, 0, sweep, (uint64_t)(c.row_offset + rowc));
+        uf = uniform_f32_from(rnd.x);
+        ex_own[8 * kTileRows] = uf;
       }
-      const unsigned births = __ballot_sync(0xffffffffu, live && choice == kNewTable);
-      if (lane == 0 && (row >> 5) < c.n_chunks) c.birthmask[row >> 5] = births;
+      ex_own[6 * kTileRows] = epi.halfmax();
+      rendezvous();                                   // #1: streaming sums, half maxima, the uniform
+      for (int v = 0; v < V; ++v) {
+        const float mo = ex_oth[(2 * v) * kTileRows], so = ex_oth[(2 * v + 1) * kTileRows];
+        const float mi = ex_own[(2 * v) * kTileRows], si = ex_own[(2 * v + 1) * kTileRows];
+        const TableCold* cold = reinterpret_cast<const TableCold*>(s_tp + v * 2048 + 1024);
+        const float xx = (v == 0) ? xxv[0] : ((v == 1) ? xxv[1] : xxv[2]);
+        lnew = __fadd_rn(lnew, merge_view<FAST>(hf ? mo : mi, hf ? so : si, hf ? mi : mo, hf ? si : so, s_vp[v], xx,
+                                                epi.single, cold[epi.t0].lone));
+      }
+      if (hf == 1) uf = ex_oth[8 * kTileRows];
+      const float M = hf ? fmaxf(fmaxf(lnew, ex_oth[6 * kTileRows]), ex_own[6 * kTileRows])
+                         : fmaxf(fmaxf(lnew, ex_own[6 * kTileRows]), ex_oth[6 * kTileRows]);
+      int choice = epi.t0;                            // nothing has weight: stay (cf. multiview_gibbs.cpp:172-176)
+      const bool any_weight = (M > -1.0e29f);         // identical in both threads of the customer
+      float Hown = 0.0f;
+      if (any_weight) Hown = epi.weights(M);
+      ex_own[7 * kTileRows] = Hown;
+      rendezvous();                                   // #2: half totals
+      const float Hoth = ex_oth[7 * kTileRows];
+      const float HA = hf ? Hoth : Hown, HB = hf ? Hown : Hoth;
+      const float total = __fadd_rn(__fadd_rn(HA, HB), exp2w<FAST>(__fadd_rn(lnew, -M)));
+      const float target = __fmul_rn(uf, total);
+      int cnt = 0;
+      if (any_weight) cnt = epi.scan(target, hf ? HA : 0.0f);
+      if (hf == 1) {
+        int enc = cnt;
+        if (cnt == 32) enc |= (epi.last_live() + 1) << 8;   // only needed when the draw ran past every table
+        ex_own[8 * kTileRows] = __int_as_float(enc);
+      }
+      rendezvous();                                   // #3: the upper half's count
+      if (hf == 0) {
+        if (any_weight) {
+          const int enc = __float_as_int(ex_oth[8 * kTileRows]);
+          const int total_cnt = cnt + (enc & 0xFF);
+          choice = (total_cnt < 64) ? total_cnt : kNewTable;
+          if (total_cnt >= 64 && !(lnew > -1.0e29f)) {   // rounding fall-through with no new-table mass: last live table
+            const int lb = (enc >> 8) - 1, la = epi.last_live();
+            choice = (lb >= 0) ? (32 + lb) : ((la >= 0) ? la : epi.t0);
+          }
+        }
+        if (live) {
+          c.choice[row] = choice;
+          if (c.debug_export & 1) c.dbg_choice[row] = choice;
+        }
+        const unsigned births = __ballot_sync(0xffffffffu, live && choice == kNewTable);
+        if (lane == 0 && (row >> 5) < c.n_chunks) c.birthmask[row >> 5] = births;
+      }
     }
-    if (prof && r == 0) { prof_out[12 + 2 * grp] = w0 + w1; prof_out[13 + 2 * grp] = clock64() - t_start; }
+    if (prof && r == 0 && hf == 0) { prof_out[12 + 2 * pair] = w0 + w1; prof_out[13 + 2 * pair] = clock64() - t_start; }
   }
 
   // ---- teardown ------------------------------------------------------------------------------------

@@ -590,14 +590,16 @@ void mvo_stageA_f32(const float* x, int D, const float* m, int cap, float* acc, 
   }
 }
 
-/* Restates RowEpilogue<CAP,false> of multiview-clustering_b200/csrc/mv_device.cuh operation by
- * operation: begin (table masses), view (leave-one-out log2 f, 2-way max, 4-way partial sums of the
- * dish marginal), finish (4-way partial total, sequential prefix count).  margin_out, if not NULL,
- * receives the distance of u*total to the nearest CDF edge relative to total (how close the draw
- * was to flipping) — used to grade engines whose weights are tolerance-level. */
+/* Restates HalfEpilogue / merge_view / RowEpilogue::finish of multiview-clustering_b200/csrc/mv_device.cuh
+ * operation by operation.  The cap tables are two halves of cap/2; per view each half streams a
+ * log-sum-exp over its dishes in chunks of 16 tables (2-way chunk max, rescale, 4-way partial sums),
+ * the halves are merged (half A first) together with the new-dish term.  The draw: global max, per-half
+ * totals (4-way partials + tree), total = (HA + HB) + new, per-half prefix counts (half B starts at HA).
+ * margin_out, if not NULL, receives the distance of u*total to the nearest CDF edge relative to total
+ * (how close the draw was to flipping) — used to grade engines whose weights are tolerance-level. */
 int mvo_stageB_f32_ex(const mvo_params_f32* p, const float* acc, const float* xx, int t0, float uf,
                       float* lw_out, float* margin_out) {
-  const int V = p->V, cap = p->cap;
+  const int V = p->V, cap = p->cap, half = cap / 2;
   float* lw = (float*)malloc(sizeof(float) * (size_t)cap);
   float* term = (float*)malloc(sizeof(float) * (size_t)cap);
   const int single = p->single[t0];
@@ -608,54 +610,71 @@ int mvo_stageB_f32_ex(const mvo_params_f32* p, const float* acc, const float* xx
     const int k0 = p->dish[o + t0];
     const float A1r = p->A1[o + t0], C1r = p->C1[o + t0];
     const float nxx = -xx[v];
-    float mx = MVO_MASKED, s = 0.0f;
-    for (int base = 0; base < cap; base += 16) {           /* kEpiChunk = 16 tables at a time */
-      float cp[2] = {MVO_MASKED, MVO_MASKED};
-      for (int j = 0; j < 16; ++j) {
-        const int t = base + j;
-        float e = fmaf(2.0f, acc[o + t], nxx);
-        int same = (p->dish[o + t] == k0);
-        float L = same ? fmaf(A1r, e, C1r) : fmaf(p->A[o + t], e, p->C[o + t]);
-        lw[t] = lw[t] + L;
-        float w = (same && single) ? p->W1[o + t] : p->W[o + t];
-        term[t] = L + w;
-        cp[j & 1] = fmaxf(cp[j & 1], term[t]);
+    float hmx[2], hs[2];
+    for (int h = 0; h < 2; ++h) {
+      float mx = MVO_MASKED, s = 0.0f;
+      for (int base = h * half; base < (h + 1) * half; base += 16) {   /* kEpiChunk = 16 tables at a time */
+        float cp[2] = {MVO_MASKED, MVO_MASKED};
+        for (int j = 0; j < 16; ++j) {
+          const int t = base + j;
+          float e = fmaf(2.0f, acc[o + t], nxx);
+          int same = (p->dish[o + t] == k0);
+          float L = same ? fmaf(A1r, e, C1r) : fmaf(p->A[o + t], e, p->C[o + t]);
+          lw[t] = lw[t] + L;
+          float w = (same && single) ? p->W1[o + t] : p->W[o + t];
+          term[t] = L + w;
+          cp[j & 1] = fmaxf(cp[j & 1], term[t]);
+        }
+        float mn = fmaxf(mx, fmaxf(cp[0], cp[1]));
+        s = s * mvo_exp2m(mx - mn);
+        mx = mn;
+        float sp[4] = {0.0f, 0.0f, 0.0f, 0.0f};
+        for (int j = 0; j < 16; ++j) sp[j & 3] = sp[j & 3] + mvo_exp2m(term[base + j] - mn);
+        s = s + ((sp[0] + sp[1]) + (sp[2] + sp[3]));
       }
-      float mn = fmaxf(mx, fmaxf(cp[0], cp[1]));
-      s = s * mvo_exp2m(mx - mn);
-      mx = mn;
-      float sp[4] = {0.0f, 0.0f, 0.0f, 0.0f};
-      for (int j = 0; j < 16; ++j) sp[j & 3] = sp[j & 3] + mvo_exp2m(term[base + j] - mn);
-      s = s + ((sp[0] + sp[1]) + (sp[2] + sp[3]));
+      hmx[h] = mx; hs[h] = s;
     }
+    /* merge_view */
+    float mn = fmaxf(hmx[0], hmx[1]);
+    float s = (hs[0] * mvo_exp2m(hmx[0] - mn)) + (hs[1] * mvo_exp2m(hmx[1] - mn));
     float Lnew = fmaf(-p->AN[v], xx[v], p->CN[v]);
     float termnew = Lnew + ((single && p->lone[o + t0]) ? p->WN[2 * v + 1] : p->WN[2 * v]);
-    float mn = fmaxf(mx, termnew);
-    s = s * mvo_exp2m(mx - mn);
-    s = s + mvo_exp2m(termnew - mn);
-    float logmarg = (mn + mvo_log2m(s)) - (single ? p->LD[2 * v + 1] : p->LD[2 * v]);
+    float m2 = fmaxf(mn, termnew);
+    s = s * mvo_exp2m(mn - m2);
+    s = s + mvo_exp2m(termnew - m2);
+    float logmarg = (m2 + mvo_log2m(s)) - (single ? p->LD[2 * v + 1] : p->LD[2 * v]);
     lnew = lnew + logmarg;
   }
-  float Mp[2] = {lnew, MVO_MASKED};
-  for (int t = 0; t < cap; ++t) Mp[t & 1] = fmaxf(Mp[t & 1], lw[t]);
-  float M = fmaxf(Mp[0], Mp[1]);
+  float M = lnew;
+  for (int t = 0; t < cap; ++t) M = fmaxf(M, lw[t]);
   if (lw_out) { memcpy(lw_out, lw, sizeof(float) * (size_t)cap); lw_out[cap] = lnew; }
   if (margin_out) *margin_out = 1.0f;
   int choice = MVO_NEW;
   if (!(M > -1.0e29f)) {
     choice = t0;
   } else {
-    float qp[4] = {0.0f, 0.0f, 0.0f, 0.0f};
-    for (int t = 0; t < cap; ++t) { term[t] = mvo_exp2m(lw[t] - M); qp[t & 3] = qp[t & 3] + term[t]; }
-    float total = ((qp[0] + qp[1]) + (qp[2] + qp[3])) + mvo_exp2m(lnew - M);
+    float H[2];
+    for (int h = 0; h < 2; ++h) {
+      float qp[4] = {0.0f, 0.0f, 0.0f, 0.0f};
+      for (int j = 0; j < half; ++j) {
+        const int t = h * half + j;
+        term[t] = mvo_exp2m(lw[t] - M);
+        qp[j & 3] = qp[j & 3] + term[t];
+      }
+      H[h] = (qp[0] + qp[1]) + (qp[2] + qp[3]);
+    }
+    float total = (H[0] + H[1]) + mvo_exp2m(lnew - M);
     float target = uf * total;
-    float cum = 0.0f, margin = 1.0f;
+    float margin = 1.0f;
     int cnt = 0;
-    for (int t = 0; t < cap; ++t) {
-      cum = cum + term[t];
-      cnt += (target < cum) ? 0 : 1;
-      float dist = fabsf(target - cum) / total;
-      if (dist < margin) margin = dist;
+    for (int h = 0; h < 2; ++h) {
+      float cum = h ? H[0] : 0.0f;
+      for (int j = 0; j < half; ++j) {
+        cum = cum + term[h * half + j];
+        cnt += (target < cum) ? 0 : 1;
+        float dist = fabsf(target - cum) / total;
+        if (dist < margin) margin = dist;
+      }
     }
     if (margin_out) *margin_out = margin;
     choice = (cnt < cap) ? cnt : MVO_NEW;
