@@ -49,6 +49,8 @@ def parse():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--rows", type=int, default=N_ROWS, help="total customers (default: the named config)")
     ap.add_argument("--engine", type=int, default=0, help="0 auto, 1 CUDA-core, 2 tcgen05")
+    ap.add_argument("--k-true", type=int, default=CAP, help="planted clusters (default 64 = every table slot in use; "
+                    "fewer leaves free slots, so the new-table marginal is evaluated as well)")
     ap.add_argument("--no-hyper", action="store_true")
     ap.add_argument("--role-profile", action="store_true", help="print the tcgen05 kernel's per-role wait cycles (debug)")
     ap.add_argument("--no-e2e", action="store_true")
@@ -64,7 +66,7 @@ def planted_means(rng):
     return [rng.normal(0.0, 2.0, (CAP, d)).astype(np.float32) for d in DIMS]
 
 
-def make_rows_numpy(lo, hi, mus, seed=SEED):
+def make_rows_numpy(lo, hi, mus, seed=SEED, k_true=CAP):
     """Rows [lo, hi) of the global data set, reproducible per 65536-row block (shard-invariant)."""
     B = 65536
     views = [np.empty((hi - lo, d), np.float32) for d in DIMS]
@@ -73,6 +75,8 @@ def make_rows_numpy(lo, hi, mus, seed=SEED):
     while b * B < hi:
         rng = np.random.default_rng([seed, b])
         zb = rng.integers(0, CAP, B).astype(np.int32)
+        if k_true < CAP:
+            zb = zb % k_true
         nb = [rng.standard_normal((B, d), dtype=np.float32) for d in DIMS]
         s, e = max(lo, b * B), min(hi, (b + 1) * B)
         z[s - lo:e - lo] = zb[s - b * B:e - b * B]
@@ -82,8 +86,9 @@ def make_rows_numpy(lo, hi, mus, seed=SEED):
     return views, z
 
 
-def initial_state(z):
+def initial_state(z, k_true=CAP):
     dish = np.tile(np.arange(CAP, dtype=np.int32), (len(DIMS), 1))      # dish_of[v][t] = t
+    dish[:, k_true:] = -1                                               # unused table slots are free
     hyp = dict(alpha_v=[1.0] * len(DIMS), sigma_v=[0.5] * len(DIMS), tau_v=[1.0] * len(DIMS), alpha_g=1.0, sigma_g=0.6)
     return z.astype(np.int32), dish, hyp
 
@@ -195,8 +200,8 @@ def main():
     lo, hi = rank * n_total // world, (rank + 1) * n_total // world
     n_local = hi - lo
     mus = planted_means(np.random.default_rng(SEED))
-    views_np, z = make_rows_numpy(lo, hi, mus)
-    tab, dish, hyp = initial_state(z)
+    views_np, z = make_rows_numpy(lo, hi, mus, k_true=args.k_true)
+    tab, dish, hyp = initial_state(z, args.k_true)
     views_pinned = [torch.from_numpy(v).pin_memory() for v in views_np]
     views_dev = [v.cuda(non_blocking=True) for v in views_pinned]
     torch.cuda.synchronize()
@@ -302,7 +307,7 @@ def main():
                 "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
                 "dtype": "f32", "data": "synthetic",
                 "config": {"workload": "C3: synthetic 3-view Gaussian mixture, N=%d, D=64/view, K(cap)=64, row-sharded" % n_total,
-                           "rows_per_gpu": n_local, "hyper_step": do_hyper, "engine": args.engine,
+                           "rows_per_gpu": n_local, "hyper_step": do_hyper, "engine": args.engine, "planted_clusters": args.k_true,
                            "l2": "inputs (768 MB per sweep) larger than L2; no flush"},
                 "sweeps_per_s": args.steps / (dev_ms * 1e-3), "wall_ms_per_step": wall_ms / args.steps,
                 "clocks": clocks.summary(), "gpu_launches": int(launches),

@@ -199,17 +199,20 @@ struct HalfEpilogue {
   float mx, s, nxx, A1r, C1r;
   int k0, lone0;
 
-  // tm: all cap table masses; this object covers tables [tbase, tbase + HALF).
-  __device__ __forceinline__ void begin(const TableMass* __restrict__ tm, int t0_, int tbase) {
+  // tm: all cap table masses, lm: the same LM values as a plain float array (vector loads); this
+  // object covers tables [tbase, tbase + HALF).
+  __device__ __forceinline__ void begin(const TableMass* __restrict__ tm, const float* __restrict__ lm, int t0_, int tbase) {
     t0 = t0_;
     const TableMass own = tm[t0_];
     single = own.single;
     any_single = __any_sync(0xffffffffu, single);
     const int rel = t0_ - tbase;
+    const float4* lm4 = reinterpret_cast<const float4*>(lm + tbase);
 #pragma unroll
-    for (int i = 0; i < HALF / 2; ++i) {
-      lw2[i].x = (2 * i == rel) ? own.LM1 : tm[tbase + 2 * i].LM;
-      lw2[i].y = (2 * i + 1 == rel) ? own.LM1 : tm[tbase + 2 * i + 1].LM;
+    for (int i = 0; i < HALF / 4; ++i) {              // the customer's own table (if in this half) counts n_t - 1
+      const float4 q = lm4[i];
+      lw2[2 * i] = make_float2((rel == 4 * i) ? own.LM1 : q.x, (rel == 4 * i + 1) ? own.LM1 : q.y);
+      lw2[2 * i + 1] = make_float2((rel == 4 * i + 2) ? own.LM1 : q.z, (rel == 4 * i + 3) ? own.LM1 : q.w);
     }
   }
 
@@ -224,7 +227,9 @@ struct HalfEpilogue {
   }
 
   // hoth/coldh: the arrays offset to this half's first table.  acc[j] = x . m_{tbase + BASE + j} (consumed).
-  template <int BASE, bool SINGLE>
+  // WITH_NEW = false: no table slot is free, so a new table has no weight (capacity rule) and the
+  // per-view marginal over the dishes — the whole log-sum-exp — is not needed; only lw is updated.
+  template <int BASE, bool SINGLE, bool WITH_NEW>
   __device__ __forceinline__ void chunk_impl(const PairHot* __restrict__ hoth, const TableCold* __restrict__ coldh,
                                              float (&acc)[kEpiChunk]) {
     float2 term[kEpiChunk / 2];
@@ -240,6 +245,7 @@ struct HalfEpilogue {
       const bool same0 = (__float_as_int(qb.z) == k0), same1 = (__float_as_int(qb.w) == k0);
       const float2 L = make_float2(same0 ? Ls.x : Lg.x, same1 ? Ls.y : Lg.y);
       lw2[BASE / 2 + p] = fadd2(lw2[BASE / 2 + p], L);
+      if (!WITH_NEW) continue;
       float2 w = make_float2(qb.x, qb.y);
       if (SINGLE) {
         if (same0 && single) w.x = coldh[BASE + 2 * p].W1;
@@ -250,6 +256,7 @@ struct HalfEpilogue {
       c1 = fmaxf(c1, term[p].y);
       if ((p & 3) == 3) asm volatile("" ::: "memory");   // keep at most 8 parameter loads in flight (registers)
     }
+    if (!WITH_NEW) return;
     const float mn = fmaxf(mx, fmaxf(c0, c1));
     s = __fmul_rn(s, exp2w<FAST>(__fadd_rn(mx, -mn)));
     mx = mn;
@@ -263,11 +270,12 @@ struct HalfEpilogue {
     s = __fadd_rn(s, __fadd_rn(__fadd_rn(pa.x, pa.y), __fadd_rn(pb.x, pb.y)));
   }
 
-  template <int BASE>
+  template <int BASE, bool WITH_NEW = true>
   __device__ __forceinline__ void view_chunk(const PairHot* __restrict__ hoth, const TableCold* __restrict__ coldh,
                                              float (&acc)[kEpiChunk]) {
-    if (any_single) chunk_impl<BASE, true>(hoth, coldh, acc);
-    else chunk_impl<BASE, false>(hoth, coldh, acc);
+    if (!WITH_NEW) chunk_impl<BASE, false, false>(hoth, coldh, acc);
+    else if (any_single) chunk_impl<BASE, true, true>(hoth, coldh, acc);
+    else chunk_impl<BASE, false, true>(hoth, coldh, acc);
   }
 
   // All chunks of this half from an array of HALF dot products (CUDA-core engine).
@@ -349,9 +357,10 @@ struct RowEpilogue {
   HalfEpilogue<HALF, FAST> ha, hb;
   float lnew;
 
-  __device__ __forceinline__ void begin(const TableMass* __restrict__ tm, const GlobalParam& g, int t0) {
-    ha.begin(tm, t0, 0);
-    hb.begin(tm, t0, HALF);
+  __device__ __forceinline__ void begin(const TableMass* __restrict__ tm, const float* __restrict__ lm,
+                                        const GlobalParam& g, int t0) {
+    ha.begin(tm, lm, t0, 0);
+    hb.begin(tm, lm, t0, HALF);
     lnew = ha.single ? g.LMN1 : g.LMN0;
   }
   __device__ __forceinline__ void view(const PairHot* __restrict__ hot, const TableCold* __restrict__ cold,

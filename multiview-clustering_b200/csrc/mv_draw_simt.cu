@@ -23,11 +23,12 @@ __global__ void __launch_bounds__(kSimtThreads, 2) k_draw_simt(const Ctx c) {
   PairHot* s_hot = reinterpret_cast<PairHot*>(smem_raw + sizeof(float) * (size_t)CAP * (size_t)dch_max);   // [CAP/2]
   TableCold* s_cold = reinterpret_cast<TableCold*>(s_hot + CAP / 2);                                        // [CAP]
   __shared__ TableMass s_tm[CAP];
+  __shared__ __align__(16) float s_lm[CAP];
   __shared__ GlobalParam s_g;
   __shared__ ViewParam s_vp;
 
   const int tid = threadIdx.x;
-  for (int t = tid; t < CAP; t += kSimtThreads) s_tm[t] = c.tmass[t];
+  for (int t = tid; t < CAP; t += kSimtThreads) { s_tm[t] = c.tmass[t]; s_lm[t] = c.tmass[t].LM; }
   if (tid == 0) s_g = *c.gparam;
   __syncthreads();
   const uint32_t sweep = s_g.sweep;
@@ -38,7 +39,7 @@ __global__ void __launch_bounds__(kSimtThreads, 2) k_draw_simt(const Ctx c) {
     const bool live = row < c.n_rows;
     const int rowc = live ? row : (c.n_rows - 1);
     RowEpilogue<CAP> epi;
-    epi.begin(s_tm, s_g, c.table_cur[rowc]);
+    epi.begin(s_tm, s_lm, s_g, c.table_cur[rowc]);
 
     for (int v = 0; v < c.V; ++v) {
       const int D = c.D[v];

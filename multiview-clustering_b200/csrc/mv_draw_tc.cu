@@ -65,7 +65,8 @@ struct SmemLayout {
   static constexpr int tp_off = raw_off + kRawStages * kHalfBytes;           // +112 KB
   static constexpr int tm_off = tp_off + kMaxTcViews * 64 * (int)sizeof(TableParam);   // per view: PairHot[32] then TableCold[64]
   static constexpr int vp_off = tm_off + 64 * (int)sizeof(TableMass);
-  static constexpr int xx_off = vp_off + kMaxTcViews * (int)sizeof(ViewParam);
+  static constexpr int lm_off = vp_off + kMaxTcViews * (int)sizeof(ViewParam);              // float[64]: LM of every table
+  static constexpr int xx_off = lm_off + 64 * (int)sizeof(float);
   static constexpr int ex_off = xx_off + kXxSlots * 2 * kTileRows * (int)sizeof(float);    // xx: [slot][K-half][row]
   static constexpr int bar_off = ex_off + 4 * kExFields * kTileRows * (int)sizeof(float);   // ex: [pair][half][field][row]
   static constexpr int n_bars = 2 * kRawStages + 2 * kLoStages + 2 * kDStages + kXxSlots + 1;
@@ -208,7 +209,7 @@ __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.
 
 // One 16-table chunk of one view (its dot products already sit in `cur`): export them when asked, then
 // run the half-epilogue on them.
-template <int BASE, bool FAST>
+template <int BASE, bool WITH_NEW, bool FAST>
 __device__ __forceinline__ void epi_chunk(HalfEpilogue<32, FAST>& epi, const PairHot* hoth, const TableCold* coldh,
                                           uint32_t (&cur)[16], const Ctx& c, int row, int v, int tbase, bool live) {
   float ch[16];
@@ -219,7 +220,7 @@ __device__ __forceinline__ void epi_chunk(HalfEpilogue<32, FAST>& epi, const Pai
 #pragma unroll
     for (int t = 0; t < 16; ++t) da[t] = ch[t];
   }
-  epi.template view_chunk<BASE>(hoth, coldh, ch);
+  epi.template view_chunk<BASE, WITH_NEW>(hoth, coldh, ch);
 }
 
 template <bool FAST>
@@ -232,6 +233,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_draw_tc(const Ctx c, const __gr
   unsigned char* s_tp = smem + SmemLayout::tp_off;   // per view 2 KB: PairHot[32] (hot, pair-interleaved) then TableCold[64]
   TableMass* s_tm = reinterpret_cast<TableMass*>(smem + SmemLayout::tm_off);
   ViewParam* s_vp = reinterpret_cast<ViewParam*>(smem + SmemLayout::vp_off);
+  float* s_lm = reinterpret_cast<float*>(smem + SmemLayout::lm_off);
   float* s_xx = reinterpret_cast<float*>(smem + SmemLayout::xx_off);             // [stage][K-half][row]
   uint32_t* s_misc = reinterpret_cast<uint32_t*>(smem + SmemLayout::misc_off);   // [0] TMEM base, [1] sweep, [2..3] GlobalParam floats
 
@@ -250,7 +252,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_draw_tc(const Ctx c, const __gr
   for (int v = 0; v < V; ++v)
     stage_view_params(c.tparam + v * 64, 64, reinterpret_cast<PairHot*>(s_tp + v * 2048),
                       reinterpret_cast<TableCold*>(s_tp + v * 2048 + 1024), tid, kThreads);
-  for (int i = tid; i < 64; i += kThreads) s_tm[i] = c.tmass[i];
+  for (int i = tid; i < 64; i += kThreads) { s_tm[i] = c.tmass[i]; s_lm[i] = c.tmass[i].LM; }
   if (tid < V) s_vp[tid] = c.vparam[tid];
   if (tid == 0) {
     const GlobalParam g = *c.gparam;
@@ -430,13 +432,21 @@ __global__ void __launch_bounds__(kThreads, 1) k_draw_tc(const Ctx c, const __gr
     float* ex_own = reinterpret_cast<float*>(smem + SmemLayout::ex_off) + ((pair * 2 + hf) * kExFields) * kTileRows + r;
     float* ex_oth = reinterpret_cast<float*>(smem + SmemLayout::ex_off) + ((pair * 2 + (hf ^ 1)) * kExFields) * kTileRows + r;
     auto rendezvous = [&]() { asm volatile("bar.sync %0, 256;" ::"r"(1 + pair) : "memory"); };
+    // no free table slot => a new table has no weight and the per-view marginals are skipped (CTA-uniform)
+    const bool with_new = (gp.LMN0 > -1.0e29f) || (gp.LMN1 > -1.0e29f);
     int j = pair;
-    for (int tile = blockIdx.x + pair * gridDim.x; tile < n_tiles; tile += kEpiGroups * gridDim.x, j += kEpiGroups) {
+    const int tile0 = blockIdx.x + pair * gridDim.x;
+    int t0_next = (tile0 < n_tiles) ? c.table_cur[min(tile0 * kTileRows + r, c.n_rows - 1)] : 0;
+    for (int tile = tile0; tile < n_tiles; tile += kEpiGroups * gridDim.x, j += kEpiGroups) {
       const int row = tile * kTileRows + r;
       const bool live = row < c.n_rows;
       const int rowc = live ? row : (c.n_rows - 1);
       HalfEpilogue<32, FAST> epi;
-      epi.begin(s_tm, c.table_cur[rowc], 32 * hf);
+      epi.begin(s_tm, s_lm, t0_next, 32 * hf);
+      {                                               // the next tile's tables travel while this one is computed
+        const int tn = tile + kEpiGroups * gridDim.x;
+        if (tn < n_tiles) t0_next = c.table_cur[min(tn * kTileRows + r, c.n_rows - 1)];
+      }
       float lnew = epi.single ? gp.LMN1 : gp.LMN0;
       float xxv[kMaxTcViews];
       for (int v = 0; v < V; ++v) {
@@ -457,14 +467,19 @@ __global__ void __launch_bounds__(kThreads, 1) k_draw_tc(const Ctx c, const __gr
         tmem_ld_16(taddr, ua);
         tmem_ld_wait();
         tmem_ld_16(taddr + 16, ub);
-        epi_chunk<0>(epi, hot + 16 * hf, cold + 32 * hf, ua, c, row, v, 32 * hf, live);
+        if (with_new) epi_chunk<0, true>(epi, hot + 16 * hf, cold + 32 * hf, ua, c, row, v, 32 * hf, live);
+        else epi_chunk<0, false>(epi, hot + 16 * hf, cold + 32 * hf, ua, c, row, v, 32 * hf, live);
         tmem_ld_wait();
         tc_fence_before();
         mbar_arrive(d_empty(stage));                  // this half's columns are in registers
-        epi_chunk<16>(epi, hot + 16 * hf, cold + 32 * hf, ub, c, row, v, 32 * hf, live);
-        ex_own[(2 * v) * kTileRows] = epi.mx;
-        ex_own[(2 * v + 1) * kTileRows] = epi.s;
-        if (v == 0) xxv[0] = xx; else if (v == 1) xxv[1] = xx; else xxv[2] = xx;
+        if (with_new) {
+          epi_chunk<16, true>(epi, hot + 16 * hf, cold + 32 * hf, ub, c, row, v, 32 * hf, live);
+          ex_own[(2 * v) * kTileRows] = epi.mx;
+          ex_own[(2 * v + 1) * kTileRows] = epi.s;
+          if (v == 0) xxv[0] = xx; else if (v == 1) xxv[1] = xx; else xxv[2] = xx;
+        } else {
+          epi_chunk<16, false>(epi, hot + 16 * hf, cold + 32 * hf, ub, c, row, v, 32 * hf, live);
+        }
       }
       float uf = 0.0f;
       if (hf == 0) {
@@ -474,7 +489,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_draw_tc(const Ctx c, const __gr
       }
       ex_own[6 * kTileRows] = epi.halfmax();
       rendezvous();                                   // #1: streaming sums, half maxima, the uniform
-      for (int v = 0; v < V; ++v) {
+      for (int v = 0; with_new && v < V; ++v) {
         const float mo = ex_oth[(2 * v) * kTileRows], so = ex_oth[(2 * v + 1) * kTileRows];
         const float mi = ex_own[(2 * v) * kTileRows], si = ex_own[(2 * v + 1) * kTileRows];
         const TableCold* cold = reinterpret_cast<const TableCold*>(s_tp + v * 2048 + 1024);
