@@ -148,7 +148,7 @@ int ensure_layout(mvg_handle* h) {
   // engine choice
   h->engine = MVG_ENGINE_SIMT;
   if (h->cfg.engine == MVG_ENGINE_TCGEN05 || h->cfg.engine == MVG_ENGINE_TCGEN05_FAST) {
-    if (!draw_tc_supported(c)) return fail(h, MVG_EUNSUPPORTED, "tcgen05 engine needs cap = 64 and every dim = 64");
+    if (!draw_tc_supported(c)) return fail(h, MVG_EUNSUPPORTED, "tcgen05 engine needs cap = 64 and exactly three views of dim 64");
     h->engine = h->cfg.engine;
   } else if (h->cfg.engine == MVG_ENGINE_AUTO && draw_tc_supported(c)) {
     h->engine = MVG_ENGINE_TCGEN05;

@@ -5,7 +5,7 @@
 //
 //   TMA producer (1 thread)    cp.async.bulk.tensor: the tile's [128 x 64] FP32 features arrive in
 //                              shared memory as two K-halves of [128 x 32] in the 128B-swizzled
-//                              K-major layout UMMA reads directly (6-deep ring, 96 KB in flight).
+//                              K-major layout UMMA reads directly (4-deep ring plus an L2 prefetch of the tile-views behind it).
 //   converters (2 x 128 thr.)  one warpgroup per K-half; thread r owns customer r: partial |x|^2 and
 //                              the TF32 remainder x_lo = rn_tf32(x - trunc_tf32(x)), written with
 //                              tcgen05.st into TMEM lane r (the remainder tile never touches shared memory).
@@ -41,14 +41,15 @@ constexpr int kTileRows = 128;
 constexpr int kHalfCols = 32;                       // floats per 128-byte swizzled row
 constexpr int kHalfBytes = kTileRows * 128;         // 16 KB: one K-half of an A tile
 constexpr int kBHalfBytes = 64 * 128;               // 8 KB: one K-half of a B matrix (64 tables)
-constexpr int kRawStages = 6;                       // K-halves of raw features in flight (96 KB)
+constexpr int kRawStages = 4;                       // K-halves of raw features in flight (64 KB) + L2 prefetch two tile-views ahead
 constexpr int kLoStages = 2;                        // TMEM remainder tiles (64 columns each)
-constexpr int kDStages = 6;                         // TMEM accumulator tiles (64 columns each): one whole row tile (3 views) per epilogue warpgroup
-constexpr int kXxSlots = 8;                         // ring of per-row |x|^2 partials; >= kDStages + kLoStages keeps it race-free
+constexpr int kDStages = 6;                         // TMEM accumulator tiles (64 columns each): three per epilogue pair
+constexpr int kXxSlots = 8;                         // ring of per-row |x|^2 partials, >= kDStages + kLoStages (see the converter)
 constexpr int kTmemCols = 512;
 constexpr int kLoCol0 = kDStages * 64;              // first TMEM column of the remainder tiles
 constexpr int kMaxTcViews = 3;
 constexpr int kThreads = 896;                       // WG0: control, WG1+WG2: converters (one per K-half), WG3..WG6: epilogue
+constexpr int kMmaWarps = 2;                        // MMA-issuing warps of WG0; tile-view i belongs to warp 1 + i % 2
 constexpr int kExFields = 9;                        // scalars two epilogue threads of one customer trade per tile
 constexpr int kEpiGroups = 2;
 
@@ -305,70 +306,82 @@ __global__ void __launch_bounds__(kThreads, 1) k_draw_tc(const Ctx c, const __gr
             mbar_expect_tx(raw_full(r.stage), kHalfBytes);
             tma_load_2d(sbase + SmemLayout::raw_off + r.stage * kHalfBytes, &maps.x[v], raw_full(r.stage),
                         h * kHalfCols, tile * kTileRows);
+            {                                           // pull the same half of the CTA's next tile into L2 meanwhile
+              const int tn = tile + gridDim.x;
+              if (tn < n_tiles)
+                asm volatile("cp.async.bulk.prefetch.tensor.2d.L2.global [%0, {%1, %2}];"
+                             ::"l"(reinterpret_cast<uint64_t>(&maps.x[v])), "r"(h * kHalfCols), "r"(tn * kTileRows) : "memory");
+            }
             r.next();
           }
       if (prof) { prof_out[0] = w0; prof_out[1] = clock64() - t_start; }
-    } else if (warp == 1) {
-      // ---- MMA issuer: the whole warp walks the loop (descriptor arithmetic stays warp-uniform),
-      //      lane 0 issues ----
+    } else if (warp >= 1 && warp <= kMmaWarps) {
+      // ---- MMA issuers: warps 1 and 2 take alternate tile-views.  One tcgen05.mma of this shape keeps the
+      //      tensor pipe busy for 32 cycles but costs its issuing warp ~100 cycles of uniform-datapath
+      //      bookkeeping, so a single issuer cannot feed the pipe.  An mbarrier phase is one parity bit: a
+      //      waiter that is a whole use ahead would sail through, so every barrier must be waited on in
+      //      use order by ONE thread of control.  The stage counts are chosen for that: tile-view i goes to
+      //      warp i % 2, and raw stages (4 = 2 per tile-view), remainder stages (2) and accumulator stages
+      //      (6) all give consecutive uses of a stage the same parity of i.  The whole warp walks the loop
+      //      (descriptor arithmetic stays warp-uniform); one elected lane issues. ----
       mbar_wait(b_full, 0);
       tc_fence_after();
-      const uint32_t a_lo0 = desc_lo(sbase + SmemLayout::raw_off);
+      const int me = warp - 1;
+      const uint32_t a_me = desc_lo(sbase + SmemLayout::raw_off + me * 2 * kHalfBytes);   // this warp's two raw stages
       const uint32_t b_lo0 = desc_lo(sbase + SmemLayout::b_off);
-      Ring rr(kRawStages), rl(kLoStages), rd(kDStages);
-      for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x)
-        for (int v = 0; v < V; ++v) {
-          mbar_wait_t(d_empty(rd.stage), rd.phase ^ 1u, prof, w0);
-          tc_fence_after();
-          const uint32_t d_tmem = tmem_base + (uint32_t)(rd.stage * 64);
-          const uint32_t b_v = b_lo0 + (uint32_t)(v * 4 * (kBHalfBytes >> 4));   // [hi|lo][h] blocks of this view
-          // passes 1+2 on the raw halves: x_hi . m_hi  and  x_hi . m_lo   (4 x K=8 per 128-byte row, +32 B each)
-          {
-            mbar_wait_t(raw_full(rr.stage), rr.phase, prof, w1);
-            tc_fence_after();
-            const uint32_t a = a_lo0 + (uint32_t)(rr.stage * (kHalfBytes >> 4));
-            if (elect_one()) {
-              umma_tf32<false>(d_tmem, a, b_v, kDescHi);
+      const uint32_t lo_tmem = tmem_base + (uint32_t)(kLoCol0 + me * 64);                 // this warp's remainder stage
+      const int n_tv = ((n_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x) * V;
+      int v = me % V, ds = me;                       // view and accumulator stage of tile-view i
+      uint32_t use = 0;                              // how many tile-views this warp has issued
+      uint32_t dph = 0;                              // accumulator-stage phase: flips every third tile-view of this warp
+      int dcnt = 0;
+      for (int i = me; i < n_tv; i += kMmaWarps) {
+        const uint32_t ph = use & 1u;                // raw and remainder stages: one use per tile-view of this warp
+        mbar_wait_t(d_empty(ds), dph ^ 1u, prof, w0);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + (uint32_t)(ds * 64);
+        const uint32_t b_v = b_lo0 + (uint32_t)(v * 4 * (kBHalfBytes >> 4));   // [hi|lo][h] blocks of this view
+        // passes 1+2 on the raw halves: x_hi . m_hi  and  x_hi . m_lo   (4 x K=8 per 128-byte row, +32 B each)
+        mbar_wait_t(raw_full(2 * me), ph, prof, w1);
+        tc_fence_after();
+        if (elect_one()) {
+          umma_tf32<false>(d_tmem, a_me, b_v, kDescHi);
 #pragma unroll
-              for (int k = 1; k < 4; ++k) umma_tf32<true>(d_tmem, a + 2 * k, b_v + 2 * k, kDescHi);
+          for (int k = 1; k < 4; ++k) umma_tf32<true>(d_tmem, a_me + 2 * k, b_v + 2 * k, kDescHi);
 #pragma unroll
-              for (int k = 0; k < 4; ++k) umma_tf32<true>(d_tmem, a + 2 * k, b_v + 2 * (kBHalfBytes >> 4) + 2 * k, kDescHi);
-              umma_commit(raw_empty(rr.stage));       // this raw half is free once these MMAs retire
-            }
-            __syncwarp();
-            rr.next();
-          }
-          {
-            mbar_wait_t(raw_full(rr.stage), rr.phase, prof, w1);
-            tc_fence_after();
-            const uint32_t a = a_lo0 + (uint32_t)(rr.stage * (kHalfBytes >> 4));
-            if (elect_one()) {
-#pragma unroll
-              for (int k = 0; k < 4; ++k) umma_tf32<true>(d_tmem, a + 2 * k, b_v + (kBHalfBytes >> 4) + 2 * k, kDescHi);
-#pragma unroll
-              for (int k = 0; k < 4; ++k) umma_tf32<true>(d_tmem, a + 2 * k, b_v + 3 * (kBHalfBytes >> 4) + 2 * k, kDescHi);
-              umma_commit(raw_empty(rr.stage));
-            }
-            __syncwarp();
-            rr.next();
-          }
-          // pass 3 from tensor memory: x_lo . m_hi
-          mbar_wait_t(lo_full(rl.stage), rl.phase, prof, w2);
-          tc_fence_after();
-          if (elect_one()) {
-            const uint32_t a_tmem = tmem_base + (uint32_t)(kLoCol0 + rl.stage * 64);
-#pragma unroll
-            for (int k = 0; k < 4; ++k) umma_tf32_ts(d_tmem, a_tmem + (uint32_t)(k * 8), b_v + 2 * k, kDescHi);
-#pragma unroll
-            for (int k = 0; k < 4; ++k) umma_tf32_ts(d_tmem, a_tmem + (uint32_t)(32 + k * 8), b_v + (kBHalfBytes >> 4) + 2 * k, kDescHi);
-            umma_commit(lo_empty(rl.stage));
-            umma_commit(d_full(rd.stage));
-          }
-          __syncwarp();
-          rl.next();
-          rd.next();
+          for (int k = 0; k < 4; ++k) umma_tf32<true>(d_tmem, a_me + 2 * k, b_v + 2 * (kBHalfBytes >> 4) + 2 * k, kDescHi);
+          umma_commit(raw_empty(2 * me));             // this raw half is free once these MMAs retire
         }
-      if (prof && lane == 0) { prof_out[2] = w0; prof_out[3] = w1; prof_out[4] = w2; prof_out[5] = clock64() - t_start; }
+        __syncwarp();
+        mbar_wait_t(raw_full(2 * me + 1), ph, prof, w1);
+        tc_fence_after();
+        if (elect_one()) {
+          const uint32_t a = a_me + (uint32_t)(kHalfBytes >> 4);
+#pragma unroll
+          for (int k = 0; k < 4; ++k) umma_tf32<true>(d_tmem, a + 2 * k, b_v + (kBHalfBytes >> 4) + 2 * k, kDescHi);
+#pragma unroll
+          for (int k = 0; k < 4; ++k) umma_tf32<true>(d_tmem, a + 2 * k, b_v + 3 * (kBHalfBytes >> 4) + 2 * k, kDescHi);
+          umma_commit(raw_empty(2 * me + 1));
+        }
+        __syncwarp();
+        // pass 3 from tensor memory: x_lo . m_hi
+        mbar_wait_t(lo_full(me), ph, prof, w2);
+        tc_fence_after();
+        if (elect_one()) {
+#pragma unroll
+          for (int k = 0; k < 4; ++k) umma_tf32_ts(d_tmem, lo_tmem + (uint32_t)(k * 8), b_v + 2 * k, kDescHi);
+#pragma unroll
+          for (int k = 0; k < 4; ++k) umma_tf32_ts(d_tmem, lo_tmem + (uint32_t)(32 + k * 8), b_v + (kBHalfBytes >> 4) + 2 * k, kDescHi);
+          umma_commit(lo_empty(me));
+          umma_commit(d_full(ds));
+        }
+        __syncwarp();
+        ++use;
+        v += kMmaWarps; if (v >= V) v -= V;          // V = 3, step 2
+        ds += kMmaWarps; if (ds >= kDStages) ds -= kDStages;
+        if (++dcnt == kDStages / kMmaWarps) { dcnt = 0; dph ^= 1u; }
+      }
+      if (prof && lane == 0 && me == 0) { prof_out[2] = w0; prof_out[3] = w1; prof_out[4] = w2; prof_out[5] = clock64() - t_start; }
     }
   } else if (warp < 12) {
     // =========================== WG1, WG2: converters, one K-half each ===========================
@@ -414,8 +427,10 @@ __global__ void __launch_bounds__(kThreads, 1) k_draw_tc(const Ctx c, const __gr
         tmem_st_wait();
         tc_fence_before();
         mbar_arrive(lo_full(ls));
-        // slot i % 8 was last read for tile-view i-8, whose accumulator stage had to be released before the
-        // MMA of tile-view i-2 could issue, which in turn freed the remainder stage waited for above
+        // Slot i % 8 was last read for tile-view i-8.  Reaching this point needed the remainder stage of
+        // tile-view i-2 to be free, hence its MMA issued, hence (the issuers acquire accumulator stages in
+        // tile-view order, six of them, V = 3) the accumulator of tile-view i-8 released — and an epilogue
+        // thread reads |x|^2 before it releases the accumulator.
         s_xx[(xs * 2 + h) * kTileRows + r] = xx;
         mbar_arrive(xx_full(xs));
       }
@@ -450,11 +465,9 @@ __global__ void __launch_bounds__(kThreads, 1) k_draw_tc(const Ctx c, const __gr
       float lnew = epi.single ? gp.LMN1 : gp.LMN0;
       float xxv[kMaxTcViews];
       for (int v = 0; v < V; ++v) {
-        const int idx = j * V + v;
-        const int stage = idx % kDStages;
-        const uint32_t phase = (uint32_t)(idx / kDStages) & 1u;
-        const int xs = idx % kXxSlots;
-        mbar_wait_t(d_full(stage), phase, prof, w0);
+        const int idx = j * V + v, xs = idx % kXxSlots;
+        const int stage = idx % kDStages;             // V = 3: stages 0-2 serve this CTA's even tiles, 3-5 the odd ones
+        mbar_wait_t(d_full(stage), (uint32_t)(idx / kDStages) & 1u, prof, w0);
         mbar_wait_t(xx_full(xs), (uint32_t)(idx / kXxSlots) & 1u, prof, w1);
         tc_fence_after();
         const uint32_t taddr = tmem_base + lane_base + (uint32_t)(stage * 64 + 32 * hf);
@@ -551,7 +564,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_draw_tc(const Ctx c, const __gr
 // host side
 // =================================================================================================
 bool draw_tc_supported(const Ctx& c) {
-  if (c.cap != 64 || c.V < 1 || c.V > kMaxTcViews) return false;
+  if (c.cap != 64 || c.V != kMaxTcViews) return false;   // the stage/slot schedule of the kernel is laid out for three views
   for (int v = 0; v < c.V; ++v)
     if (c.D[v] != 64 || (reinterpret_cast<uintptr_t>(c.x[v]) & 15) != 0) return false;
   return true;
