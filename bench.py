@@ -259,7 +259,10 @@ def main():
                 "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": alg_bytes, "kernel_ms": kern}
     if args.role_profile and rank == 0:
-        pr = s.get_debug_prof()
+        pr = s.get_debug_prof(n_ctas=256)
+        print("finalize section stamps (cycles since kernel start: sums|births|dish stats|tau init|hyper|params):",
+              pr[200, :6].tolist(), file=sys.stderr)
+        pr = pr[:148]
         names = ["tma.wait_raw_empty", "tma.total", "mma.wait_d_empty", "mma.wait_raw_full", "mma.wait_lo_full", "mma.total",
                  "conv0.wait_raw_full", "conv0.wait_lo_empty", "conv0.total", "conv1.wait_raw_full", "conv1.wait_lo_empty",
                  "conv1.total", "epi0.wait", "epi0.total", "epi1.wait", "epi1.total"]

@@ -71,7 +71,8 @@ __global__ void __launch_bounds__(kPackThreads, 1) k_pack(const Ctx c) {
   }
   __syncthreads();
   int running = s_warp[wid] + incl - cnt;
-  for (int ch = lo; ch < hi; ++ch) {
+  // chunk_prefix is only read for rows that drew a new table: with no birth anywhere it is not needed
+  if (s_total > 0) for (int ch = lo; ch < hi; ++ch) {
     c.chunk_prefix[ch] = running;
     unsigned m = c.birthmask[ch];
     while (m) {
@@ -113,136 +114,174 @@ cudaError_t launch_pack(const Ctx& c, cudaStream_t s) {
 // =============================================================================================
 // k_stats
 // =============================================================================================
-constexpr int kStatWarps = 8;
-constexpr int kStatThreads = kStatWarps * 32;
-constexpr int kStatCols = 64;     // feature columns per pass: lane handles columns lane and lane+32
-constexpr int kStatPrefetch = 16; // rows per batch; the next batch's loads are issued before this one is accumulated
+// Segmented reduction of the rows into per-TABLE statistics, HBM-bound by design: one CTA per SM walks a
+// fixed range of 32-row chunks.  Its warps form R row groups x G column groups: a warp owns 32 of the
+// concatenated feature columns (lane = column, so a row is one coalesced 128-byte load) and, for the rows
+// of its row group, adds them into a private [cap][32] block of sums and of squares in shared memory —
+// no two warps ever touch the same cell, rows are added in ascending order, the row groups are summed in
+// ascending order: a fixed tree, bit-reproducible for a given launch shape.  Loads run a batch of rows
+// ahead of their use.
+struct StatsPlan { int Gp, R, passes, smem; };
 
-int stats_smem_bytes(const Ctx& c) {
-  return kStatWarps * c.cap * (kStatCols + 32) * (int)sizeof(float) + kStatWarps * c.cap * (int)sizeof(int32_t);
+static StatsPlan stats_plan(const Ctx& c) {
+  const int Gtot = (c.Dsum + 31) / 32;
+  const int slot_bytes = 2 * c.cap * 32 * (int)sizeof(float);            // sums + squares of one (row group, column group)
+  const int slots = (200 * 1024) / slot_bytes;
+  StatsPlan pl;
+  int gmax = slots / 2 > 1 ? slots / 2 : 1;          // leave room for at least two row groups
+  if (gmax > 16) gmax = 16;
+  pl.Gp = Gtot < gmax ? Gtot : gmax;
+  int R = slots / pl.Gp;
+  if (R > 8) R = 8;
+  if (R * pl.Gp > 16) R = 16 / pl.Gp;                  // at most 16 warps: 128 registers each
+  if (R < 1) R = 1;
+  pl.R = R;
+  pl.passes = (Gtot + pl.Gp - 1) / pl.Gp;
+  pl.smem = R * pl.Gp * slot_bytes + R * c.cap * (int)sizeof(int32_t);
+  return pl;
 }
+int stats_smem_bytes(const Ctx& c) { return stats_plan(c).smem; }
 
-__global__ void __launch_bounds__(kStatThreads, 1) k_stats(const Ctx c) {
+constexpr int kStatBatch = 16;   // rows whose loads are in flight per warp while the previous batch is accumulated
+constexpr int kStatAhead = 12;   // chunks (of 32 rows) the L2 prefetch runs ahead of the loads
+
+__global__ void __launch_bounds__(512, 1) k_stats(const Ctx c, const int Gp, const int R, const int passes) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int cap = c.cap;
-  float* s_acc = reinterpret_cast<float*>(smem_raw);                     // [warps][cap][64]
-  float* s_q = s_acc + (size_t)kStatWarps * cap * kStatCols;             // [warps][cap][32]
-  int32_t* s_cnt = reinterpret_cast<int32_t*>(s_q + (size_t)kStatWarps * cap * 32);   // [warps][cap]
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-  float* acc = s_acc + (size_t)wid * cap * kStatCols;
-  float* accq = s_q + (size_t)wid * cap * 32;
-  int32_t* cntw = s_cnt + wid * cap;
+  const int nthreads = blockDim.x;
+  const int rg = wid / Gp, cg = wid - rg * Gp;
+  float* s_sum = reinterpret_cast<float*>(smem_raw);                            // [R][Gp][cap][32]
+  float* s_sq = s_sum + (size_t)R * Gp * cap * 32;                              // [R][Gp][cap][32]
+  int32_t* s_cnt = reinterpret_cast<int32_t*>(s_sq + (size_t)R * Gp * cap * 32);   // [R][cap]
+  float* acc = s_sum + ((size_t)rg * Gp + cg) * cap * 32;
+  float* accq = s_sq + ((size_t)rg * Gp + cg) * cap * 32;
+  int32_t* cntw = s_cnt + rg * cap;
 
-  // fixed mapping rows -> CTA -> warp, in whole 32-row chunks
+  // fixed mapping rows -> CTA -> row group, in whole 32-row chunks
   const int chunks_per_cta = (c.n_chunks + gridDim.x - 1) / gridDim.x;
   const int cta_lo = min((int)blockIdx.x * chunks_per_cta, c.n_chunks);
   const int cta_hi = min(cta_lo + chunks_per_cta, c.n_chunks);
-  const int chunks_per_warp = (cta_hi - cta_lo + kStatWarps - 1) / kStatWarps;
-  const int w_lo = min(cta_lo + wid * chunks_per_warp, cta_hi);
-  const int w_hi = min(w_lo + chunks_per_warp, cta_hi);
+  const int chunks_per_rg = (cta_hi - cta_lo + R - 1) / R;
+  const int w_lo = min(cta_lo + rg * chunks_per_rg, cta_hi);
+  const int w_hi = min(w_lo + chunks_per_rg, cta_hi);
   const int nfree = c.gparam->nfree;
+  const int last_row = c.n_rows - 1;
 
   const size_t part_stride = (size_t)cap * c.Dsum + (size_t)c.V * cap;
   float* part = c.partial_f + (size_t)blockIdx.x * part_stride;
   float* part_s2 = part + (size_t)cap * c.Dsum;
 
-  bool first_pass = true;
-  for (int v = 0; v < c.V; ++v) {
+  for (int pass = 0; pass < passes; ++pass) {
+    // this lane's column of the concatenated views
+    const int col = (pass * Gp + cg) * 32 + lane;
+    const bool has = col < c.Dsum;
+    int v = 0;
+    while (v + 1 < c.V && col >= c.doff[v + 1]) ++v;
     const int D = c.D[v];
-    const float* __restrict__ xv = c.x[v];
-    for (int dc = 0; dc < D; dc += kStatCols) {
-      for (int i = lane; i < cap * kStatCols; i += 32) acc[i] = 0.0f;
-      for (int i = lane; i < cap * 32; i += 32) accq[i] = 0.0f;
-      if (first_pass) for (int i = lane; i < cap; i += 32) cntw[i] = 0;
-      __syncwarp();
-      const int col0 = dc + lane, col1 = dc + lane + 32;
-      const bool has0 = col0 < D, has1 = col1 < D;
+    const float* __restrict__ base = c.x[v] + (has ? (col - c.doff[v]) : 0);
+    for (int i = lane; i < cap * 32; i += 32) { acc[i] = 0.0f; accq[i] = 0.0f; }
+    if (pass == 0 && cg == 0) for (int i = lane; i < cap; i += 32) cntw[i] = 0;
+    __syncwarp();
+    const bool owner = (pass == 0 && cg == 0);      // the warp that records the resolved assignment of its rows
 
-      // Loads are unconditional (clamped addresses) and issued a whole batch ahead of their use, so
-      // that kStatPrefetch*2 requests per warp are in flight while the previous batch is accumulated.
-      const int cc0 = has0 ? col0 : (D - 1), cc1 = has1 ? col1 : (D - 1);
-      const int last_row = c.n_rows - 1;
-      float nx0[kStatPrefetch], nx1[kStatPrefetch];
-      auto issue = [&](int ch, int j0) {
+    float nx[kStatBatch];
+    auto issue = [&](int ch, int j0) {
 #pragma unroll
-        for (int u = 0; u < kStatPrefetch; ++u) {
-          int r = ch * 32 + j0 + u;
-          r = r < last_row ? r : last_row;
-          const float* p = xv + (size_t)r * D;
-          nx0[u] = __ldg(p + cc0);
-          nx1[u] = __ldg(p + cc1);
+      for (int u = 0; u < kStatBatch; ++u) {
+        int r = ch * 32 + j0 + u;
+        r = r < last_row ? r : last_row;
+        nx[u] = __ldg(base + (size_t)r * D);
+      }
+    };
+    // the assignment of a chunk's rows is fetched one chunk ahead of its use, like the features
+    auto load_choice = [&](int ch) {
+      const int row = ch * 32 + lane;
+      return (ch < w_hi && row < c.n_rows) ? c.choice[row] : -3;
+    };
+    int tj_next = load_choice(w_lo);
+    if (w_lo < w_hi) issue(w_lo, 0);
+    for (int ch = w_lo; ch < w_hi; ++ch) {
+      {   // one instruction pulls this warp's 128-byte segments of 32 rows, kStatAhead chunks on, into L2
+        int pr = (ch + kStatAhead) * 32 + lane;
+        pr = pr < last_row ? pr : last_row;
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(base + (size_t)pr * D));
+      }
+      const int row = ch * 32 + lane;
+      int tj = tj_next;                              // -3: beyond the end
+      tj_next = load_choice(ch + 1);
+      if (row < c.n_rows) {
+        if (tj == kNewTable) {                       // a birth: seated (candidate, -2) or overflow (stays put)
+          const unsigned m = c.birthmask[ch];
+          const int rank = c.chunk_prefix[ch] + __popc(m & ((1u << lane) - 1u));
+          tj = (rank < nfree) ? -2 : c.table_cur[row];
+          if (owner) c.choice[row] = tj;
         }
-      };
-      if (w_lo < w_hi) issue(w_lo, 0);
-      for (int ch = w_lo; ch < w_hi; ++ch) {
-        const int row = ch * 32 + lane;
-        int tj = -3;                                   // beyond the end
-        if (row < c.n_rows) {
-          tj = c.choice[row];
-          if (first_pass) {
-            if (tj == kNewTable) {
-              const unsigned m = c.birthmask[ch];
-              const int rank = c.chunk_prefix[ch] + __popc(m & ((1u << lane) - 1u));
-              tj = (rank < nfree) ? -2 : c.table_cur[row];   // candidate : overflow stays put
-              c.choice[row] = tj;
-            }
-            if (tj >= 0) c.table_cur[row] = tj;
-          }
-        }
-        for (int j0 = 0; j0 < 32; j0 += kStatPrefetch) {
-          float x0[kStatPrefetch], x1[kStatPrefetch];
+        if (owner && tj >= 0) c.table_cur[row] = tj;
+      }
+      for (int j0 = 0; j0 < 32; j0 += kStatBatch) {
+        float xs[kStatBatch];
 #pragma unroll
-          for (int u = 0; u < kStatPrefetch; ++u) { x0[u] = nx0[u]; x1[u] = nx1[u]; }
-          if (j0 + kStatPrefetch < 32) issue(ch, j0 + kStatPrefetch);
-          else if (ch + 1 < w_hi) issue(ch + 1, 0);
+        for (int u = 0; u < kStatBatch; ++u) xs[u] = nx[u];
+        if (j0 + kStatBatch < 32) issue(ch, j0 + kStatBatch);
+        else if (ch + 1 < w_hi) issue(ch + 1, 0);
 #pragma unroll
-          for (int u = 0; u < kStatPrefetch; ++u) {
-            const int t = __shfl_sync(0xffffffffu, tj, j0 + u);
-            if (t < 0) continue;                        // warp-uniform
-            const float v0 = has0 ? x0[u] : 0.0f, v1 = has1 ? x1[u] : 0.0f;
-            float* a = acc + t * kStatCols;
-            a[lane] = __fadd_rn(a[lane], v0);
-            a[lane + 32] = __fadd_rn(a[lane + 32], v1);
-            float* q = accq + t * 32;
-            q[lane] = __fadd_rn(q[lane], __fmaf_rn(v1, v1, __fmul_rn(v0, v0)));
-            if (first_pass && lane == 0) cntw[t] += 1;
-          }
+        for (int u = 0; u < kStatBatch; ++u) {
+          const int t = __shfl_sync(0xffffffffu, tj, j0 + u);
+          if (t < 0) continue;                        // warp-uniform
+          const float xv = has ? xs[u] : 0.0f;
+          float* a = acc + t * 32 + lane;
+          float* q = accq + t * 32 + lane;
+          *a = __fadd_rn(*a, xv);
+          *q = __fmaf_rn(xv, xv, *q);
+          if (owner && lane == 0) cntw[t] += 1;
         }
       }
-      __syncthreads();
-      // fixed-order sum over the warps of this CTA
-      for (int i = tid; i < cap * kStatCols; i += kStatThreads) {
-        const int t = i / kStatCols, col = i - t * kStatCols;
-        if (dc + col < D) {
-          float sum = 0.0f;
-#pragma unroll
-          for (int w = 0; w < kStatWarps; ++w) sum = __fadd_rn(sum, s_acc[((size_t)w * cap + t) * kStatCols + col]);
-          part[(size_t)cap * c.doff[v] + (size_t)t * D + dc + col] = sum;
-        }
-      }
-      for (int t = tid; t < cap; t += kStatThreads) {
-        float sum = 0.0f;
-        for (int w = 0; w < kStatWarps; ++w)
-          for (int l = 0; l < 32; ++l) sum = __fadd_rn(sum, s_q[((size_t)w * cap + t) * 32 + l]);
-        if (dc == 0) part_s2[v * cap + t] = sum;
-        else part_s2[v * cap + t] = __fadd_rn(part_s2[v * cap + t], sum);
-        if (first_pass) {
-          int n = 0;
-          for (int w = 0; w < kStatWarps; ++w) n += s_cnt[w * cap + t];
-          c.partial_n[(size_t)blockIdx.x * cap + t] = n;
-        }
-      }
-      __syncthreads();
-      first_pass = false;
     }
+    __syncthreads();
+    // fixed-order sums over the row groups -> this CTA's partials
+    const int ncols_pass = Gp * 32;
+    for (int i = tid; i < cap * ncols_pass; i += nthreads) {
+      const int t = i / ncols_pass, cc = i - t * ncols_pass;
+      const int gcol = pass * ncols_pass + cc;
+      if (gcol < c.Dsum) {
+        const int g = cc >> 5, l = cc & 31;
+        float sum = 0.0f;
+        for (int r = 0; r < R; ++r) sum = __fadd_rn(sum, s_sum[(((size_t)r * Gp + g) * cap + t) * 32 + l]);
+        int vv = 0;
+        while (vv + 1 < c.V && gcol >= c.doff[vv + 1]) ++vv;
+        part[(size_t)cap * c.doff[vv] + (size_t)t * c.D[vv] + (gcol - c.doff[vv])] = sum;
+      }
+    }
+    for (int i = tid; i < c.V * cap; i += nthreads) {
+      const int vv = i / cap, t = i - vv * cap;
+      // columns of view vv that this pass covered, ascending; row groups innermost
+      const int lo = max(c.doff[vv], pass * ncols_pass), hi = min(c.doff[vv] + c.D[vv], (pass + 1) * ncols_pass);
+      float sum = 0.0f;
+      for (int gcol = lo; gcol < hi; ++gcol) {
+        const int cc = gcol - pass * ncols_pass, g = cc >> 5, l = cc & 31;
+        for (int r = 0; r < R; ++r) sum = __fadd_rn(sum, s_sq[(((size_t)r * Gp + g) * cap + t) * 32 + l]);
+      }
+      if (lo < hi || pass == 0) {
+        const bool first = (pass * ncols_pass <= c.doff[vv]);
+        part_s2[i] = first ? sum : __fadd_rn(part_s2[i], sum);
+      }
+    }
+    if (pass == 0)
+      for (int t = tid; t < cap; t += nthreads) {
+        int n = 0;
+        for (int r = 0; r < R; ++r) n += s_cnt[r * cap + t];
+        c.partial_n[(size_t)blockIdx.x * cap + t] = n;
+      }
+    __syncthreads();
   }
 }
 
 cudaError_t launch_stats(const Ctx& c, cudaStream_t s) {
-  const int smem = stats_smem_bytes(c);
-  cudaError_t e = cudaFuncSetAttribute(k_stats, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+  const StatsPlan pl = stats_plan(c);
+  cudaError_t e = cudaFuncSetAttribute(k_stats, cudaFuncAttributeMaxDynamicSharedMemorySize, pl.smem);
   if (e != cudaSuccess) return e;
-  k_stats<<<c.stat_ctas, kStatThreads, smem, s>>>(c);
+  k_stats<<<c.stat_ctas, pl.R * pl.Gp * 32, pl.smem, s>>>(c, pl.Gp, pl.R, pl.passes);
   return cudaGetLastError();
 }
 
@@ -290,6 +329,9 @@ struct FinShared {
   int32_t cand_j[kMaxWorld * kMaxCap];
   int32_t cand_final[kMaxWorld * kMaxCap];
   int32_t ncand_total, nseat, nfree, err;
+  unsigned long long tmask[kMaxViews][kMaxCap];   // bit t: table t serves dish k of view v (after births and deaths)
+  unsigned long long live[kMaxViews + 1];          // bit i: cluster i of level j has members (dishes: l_vk > 0; level V: n_t > 0)
+  long long total[kMaxViews + 1];                  // items of level j (tables of view j; customers for level V)
   double s1sq[kMaxViews][kMaxCap];        // |S1k|^2
   double sse[kMaxViews][kMaxCap];         // max(0, S2k - |S1k|^2 / n_k)     (multiview_hyper.cpp:191-193)
   double termA[2 * (kMaxViews + 1)][kMaxCap + 1];   // scratch of the batched EPPF evaluations
@@ -336,38 +378,45 @@ __device__ __forceinline__ double reflect_unit(double value) {      // :110-122
 // ascending cluster order (the order of oracle/mv_oracle.c:eppf_core).  Block-uniform call.
 __device__ void eppf_batch(const Ctx& c, FinShared& S, const double* alpha, const double* sigma) {
   const int tid = threadIdx.x, cap = c.cap, V = c.V;
+  const int lane = tid & 31, wid = tid >> 5;
   const int nsets = 2 * (V + 1);
   __syncthreads();
-  for (int idx = tid; idx < nsets * cap; idx += kFinThreads) {
-    const int set = idx / cap, i = idx - set * cap, j = set >> 1;
-    const int32_t* counts = (j < V) ? S.l_live[j] : S.n_new;
-    const int cnt = counts[i];
-    const double al = alpha[set], sg = sigma[set];
-    S.termB[set][i] = (cnt > 1) ? lgamma((double)cnt - sg) - lgamma(1.0 - sg) : 0.0;
-    int r = 0;                                      // rank of cluster i among the live ones
-    for (int q = 0; q < i; ++q) r += (counts[q] > 0);
-    const double term = al + (double)r * sg;
-    S.termA[set][i] = (cnt > 0) ? ((term <= 0.0) ? -INFINITY : log(term)) : 0.0;
-  }
-  __syncthreads();
-  if (tid < nsets) {
-    const int set = tid, j = set >> 1;
+  // one warp per parameter set: lanes stride over the clusters, per-cluster terms summed by a fixed
+  // shuffle tree; the rank of a cluster among the live ones is a popcount of the level's live mask
+  for (int set = wid; set < nsets; set += kFinThreads / 32) {
+    const int j = set >> 1;
     const int32_t* counts = (j < V) ? S.l_live[j] : S.n_new;
     const double al = alpha[set], sg = sigma[set];
-    long long total = 0;
-    if (j < V) { for (int i = 0; i < cap; ++i) total += counts[i]; } else total = (long long)c.n_global;
-    double logp;
-    if (!(sg > kEps && sg < 1.0 - kEps) || al <= -sg) {
-      logp = -INFINITY;
-    } else if (total <= 0) {
-      logp = 0.0;
-    } else {
-      logp = 0.0;
-      for (int i = 0; i < cap; ++i) if (counts[i] > 0) logp += S.termA[set][i];
-      if (total > 1) logp -= lgamma(al + (double)total) - lgamma(al + 1.0);
-      for (int i = 0; i < cap; ++i) if (counts[i] > 1) logp += S.termB[set][i];
+    const unsigned long long lm = S.live[j];
+    double sa = 0.0, sb = 0.0;
+    bool bad = false;
+    for (int i = lane; i < cap; i += 32) {
+      const int cnt = counts[i];
+      if (cnt > 0) {
+        const int r = __popcll(lm & ((1ull << i) - 1ull));
+        const double term = al + (double)r * sg;
+        if (term <= 0.0) bad = true; else sa += log(term);
+      }
+      if (cnt > 1) sb += lgamma((double)cnt - sg) - lgamma(1.0 - sg);
     }
-    S.eppf[set] = logp;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      sa += __shfl_xor_sync(0xffffffffu, sa, o);
+      sb += __shfl_xor_sync(0xffffffffu, sb, o);
+    }
+    bad = __any_sync(0xffffffffu, bad);
+    if (lane == 0) {
+      const long long total = S.total[j];
+      double logp;
+      if (!(sg > kEps && sg < 1.0 - kEps) || al <= -sg) logp = -INFINITY;
+      else if (total <= 0) logp = 0.0;
+      else {
+        logp = bad ? -INFINITY : sa;
+        if (total > 1) logp -= lgamma(al + (double)total) - lgamma(al + 1.0);
+        logp += sb;
+      }
+      S.eppf[set] = logp;
+    }
   }
   __syncthreads();
 }
@@ -416,6 +465,10 @@ __global__ void __launch_bounds__(kFinThreads, 1) k_finalize(const Ctx c, const 
   double& alpha_g = S.hyp[3 * V];
   double& sigma_g = S.hyp[3 * V + 1];
 
+  const bool prof = (c.debug_export & 2) != 0 && c.dbg_prof != nullptr && tid == 0;
+  long long* pout = c.dbg_prof + 200 * 16;            // slots 200.. of the profile buffer: finalize section stamps
+  const long long t_begin = prof ? clock64() : 0;
+  auto stamp = [&](int k) { if (prof) pout[k] = clock64() - t_begin; };
   if (tid == 0) { S.err = 0; S.ncand_total = 0; S.nseat = 0; S.nfree = 0; }
   for (int i = tid; i < 3 * V + 2; i += kFinThreads) S.hyp[i] = c.hyp[i];
   // ---- A. rank-ordered sums of the shards' packets ------------------------------------------
@@ -441,6 +494,7 @@ __global__ void __launch_bounds__(kFinThreads, 1) k_finalize(const Ctx c, const 
   }
   __syncthreads();
 
+  stamp(0);
   // ---- B. births: candidates in global row order, the first nfree are seated -----------------
   if (flags & kFinReseat) {
     if (tid == 0) {
@@ -575,6 +629,7 @@ __global__ void __launch_bounds__(kFinThreads, 1) k_finalize(const Ctx c, const 
     __syncthreads();
   }
 
+  stamp(1);
   // ---- C. deaths and per-dish statistics -------------------------------------------------------
   for (int i = tid; i < V * cap; i += kFinThreads) {
     const int v = i / cap, t = i - v * cap;
@@ -596,31 +651,57 @@ __global__ void __launch_bounds__(kFinThreads, 1) k_finalize(const Ctx c, const 
     c.dish_of[i] = S.dish[v][k];                             // (index reuse: i = v*cap + slot)
   }
   for (int t = tid; t < cap; t += kFinThreads) c.n_t[t] = S.n_new[t];
-  for (int i = tid; i < cap * c.Dsum; i += kFinThreads) {
-    int v = 0;
-    while (v + 1 < V && i >= cap * c.doff[v + 1]) ++v;
-    const int D = c.D[v];
-    const int local = i - cap * c.doff[v];
-    const int k = local / D, dd = local - k * D;
-    double sum = 0.0;
-    for (int t = 0; t < cap; ++t)
-      if (S.dish[v][t] == k) sum += c.S1t[(size_t)cap * c.doff[v] + (size_t)t * D + dd];
-    c.S1k[i] = sum;
+  __syncthreads();
+  for (int i = tid; i < V * cap; i += kFinThreads) {          // which tables serve dish (v, k)
+    const int v = i / cap, k = i - v * cap;
+    unsigned long long m = 0ull;
+    for (int t = 0; t < cap; ++t) if (S.dish[v][t] == k) m |= 1ull << t;
+    S.tmask[v][k] = m;
+  }
+  if (tid <= V) {                                              // live masks and item totals of the EPPF levels
+    const int j = tid;
+    const int32_t* counts = (j < V) ? S.l_live[j] : S.n_new;
+    unsigned long long m = 0ull;
+    long long tot = 0;
+    for (int i = 0; i < cap; ++i) { if (counts[i] > 0) m |= 1ull << i; tot += counts[i]; }
+    S.live[j] = m;
+    S.total[j] = (j < V) ? tot : (long long)c.n_global;
   }
   __syncthreads();
-  for (int i = tid; i < V * cap; i += kFinThreads) {
-    const int v = i / cap, k = i - v * cap;
-    const int D = c.D[v];
-    const double* S1 = c.S1k + (size_t)cap * c.doff[v] + (size_t)k * D;
-    double q = 0.0;
-    for (int dd = 0; dd < D; ++dd) q += S1[dd] * S1[dd];
-    S.s1sq[v][k] = q;
-    const int n_k = S.n_vk[v][k];
-    double sse = (n_k > 0) ? c.S2k[i] - q / (double)n_k : 0.0;
-    S.sse[v][k] = sse < 0.0 ? 0.0 : sse;
+  {
+    // one warp per dish (v, k): lanes stride over the coordinates; the tables serving the dish are added in
+    // ascending order (warp-uniform test), then |S1k|^2 by a fixed shuffle tree
+    const int lane = tid & 31, wid = tid >> 5;
+    for (int i = wid; i < V * cap; i += kFinThreads / 32) {
+      const int v = i / cap, k = i - v * cap;
+      const int D = c.D[v];
+      const double* S1t_v = c.S1t + (size_t)cap * c.doff[v];
+      double* S1k_vk = c.S1k + (size_t)cap * c.doff[v] + (size_t)k * D;
+      double q = 0.0;
+      for (int d0 = 0; d0 < D; d0 += 64) {
+        const int da = d0 + lane, db = d0 + 32 + lane;
+        double sa = 0.0, sb = 0.0;
+        for (unsigned long long m = S.tmask[v][k]; m; m &= m - 1ull) {
+          const int t = __ffsll((long long)m) - 1;
+          if (da < D) sa += S1t_v[(size_t)t * D + da];
+          if (db < D) sb += S1t_v[(size_t)t * D + db];
+        }
+        if (da < D) { S1k_vk[da] = sa; q += sa * sa; }
+        if (db < D) { S1k_vk[db] = sb; q += sb * sb; }
+      }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) q += __shfl_xor_sync(0xffffffffu, q, o);
+      if (lane == 0) {
+        S.s1sq[v][k] = q;
+        const int n_k = S.n_vk[v][k];
+        double sse = (n_k > 0) ? c.S2k[i] - q / (double)n_k : 0.0;
+        S.sse[v][k] = sse < 0.0 ? 0.0 : sse;
+      }
+    }
   }
   __syncthreads();
 
+  stamp(2);
   // ---- reference initialisation of the hyperparameters (multiview_gibbs.cpp:75-98) ------------
   if (flags & kFinTauInit) {
     if (tid < V) {
@@ -638,20 +719,41 @@ __global__ void __launch_bounds__(kFinThreads, 1) k_finalize(const Ctx c, const 
     __syncthreads();
   }
 
+  stamp(3);
   // ---- D. hyperparameter step (multiview_hyper.cpp:233-292) -------------------------------------
   // The tau_v updates are independent across views, and so are the (alpha, sigma) pairs of the V views
   // and of the franchise: they run side by side, one thread per level, on Philox numbers addressed by
   // the position the reference's sequential code would draw them at.
   if (flags & kFinHyper) {
-    if (tid < V) {                                            // update_tau_v_MH, :211-231
-      const int v = tid;
-      double tau_old = tau_v[v];
-      if (tau_old <= 0.0) tau_old = kEps;
-      const double log_old = log_posterior_tau(c, S, v, tau_old);
-      const double tau_prop = exp(log(tau_old) + 0.0 + 0.3 * dev_normal(c, sweep, v));   // :166-174
-      const double log_new = log_posterior_tau(c, S, v, tau_prop);
-      const double log_acc = (log_new - log_old) + (log(tau_prop) - log(tau_old));
-      if (log(dev_unif(c, sweep, v)) < log_acc) tau_v[v] = tau_prop;
+    {                                                          // update_tau_v_MH, :211-231: one warp per view
+      const int lane = tid & 31, wid = tid >> 5;
+      for (int v = wid; v < V; v += kFinThreads / 32) {
+        double tau_old = tau_v[v];
+        if (tau_old <= 0.0) tau_old = kEps;
+        const double tau_prop = exp(log(tau_old) + 0.0 + 0.3 * dev_normal(c, sweep, v));   // :166-174
+        // log_posterior_given_tau (:176-209) at both values: lanes stride over the dishes, shuffle-tree sum
+        const double lg_o = log(2.0 * kPi * tau_old), lg_p = log(2.0 * kPi * tau_prop);
+        const double Dd = (double)c.D[v];
+        double lo = 0.0, ln = 0.0;
+        for (int k = lane; k < cap; k += 32) {
+          const int n_k = S.n_vk[v][k];
+          if (n_k == 0) continue;
+          lo += -0.5 * (double)n_k * Dd * lg_o - 0.5 * (S.sse[v][k] / tau_old);
+          ln += -0.5 * (double)n_k * Dd * lg_p - 0.5 * (S.sse[v][k] / tau_prop);
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+          lo += __shfl_xor_sync(0xffffffffu, lo, o);
+          ln += __shfl_xor_sync(0xffffffffu, ln, o);
+        }
+        if (lane == 0) {
+          const double a_tau = 2.0, b_tau = 1.0;                                    // :133-134
+          const double log_old = lo + (a_tau * log(b_tau) - lgamma(a_tau) - (a_tau + 1.0) * log(tau_old) - b_tau / tau_old);
+          const double log_new = ln + (a_tau * log(b_tau) - lgamma(a_tau) - (a_tau + 1.0) * log(tau_prop) - b_tau / tau_prop);
+          const double log_acc = (log_new - log_old) + (log(tau_prop) - log(tau_old));
+          if (log(dev_unif(c, sweep, v)) < log_acc) tau_v[v] = tau_prop;
+        }
+      }
     }
     __syncthreads();
     __shared__ double s_alpha[2 * (kMaxViews + 1)], s_sigma[2 * (kMaxViews + 1)];
@@ -692,60 +794,65 @@ __global__ void __launch_bounds__(kFinThreads, 1) k_finalize(const Ctx c, const 
   }
   for (int i = tid; i < 3 * V + 2; i += kFinThreads) c.hyp[i] = S.hyp[i];
 
+  stamp(4);
   // ---- E. FP32 parameter block of the next sweep (oracle/mv_oracle.c:mvo_make_params) ----------
-  for (int i = tid; i < cap * c.Dsum; i += kFinThreads) {    // per-table posterior means, one element each
-    int v = 0;
-    while (v + 1 < V && i >= cap * c.doff[v + 1]) ++v;
-    const int D = c.D[v];
-    const int local = i - cap * c.doff[v];
-    const int t = local / D, dd = local - t * D;
-    const int k = S.dish[v][t];
-    float m = 0.f;
-    if (k >= 0) m = (float)(c.S1k[(size_t)cap * c.doff[v] + (size_t)k * D + dd] / (tau_v[v] + (double)S.n_vk[v][k]));
-    c.mean[i] = m;
-    if (c.mean_hi) {
-      uint32_t hb, lb;                                            // TF32 split, both parts rounded to nearest
-      asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(hb) : "f"(m));
-      const float hi = __uint_as_float(hb);
-      asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(lb) : "f"(__fadd_rn(m, -hi)));
-      c.mean_hi[i] = hi;
-      c.mean_lo[i] = __uint_as_float(lb);
-    }
-  }
-  __syncthreads();
-  for (int i = tid; i < V * cap; i += kFinThreads) {
-    const int v = i / cap, t = i - v * cap;
-    const int D = c.D[v];
-    const int k = S.dish[v][t];
-    const float* mt = c.mean + (size_t)cap * c.doff[v] + (size_t)t * D;
-    TableParam q;
-    if (k < 0) {
-      q.A = 0.f; q.C = kMasked; q.A1 = 0.f; q.C1 = kMasked; q.W = kMasked; q.W1 = kMasked; q.dish = -1; q.lone = 0;
-    } else {
-      const double tau = tau_v[v], n = (double)S.n_vk[v][k];
+  {
+    // one warp per (view, table): lanes stride over the coordinates of the posterior mean m = S1k / (tau + n),
+    // write it (and its TF32 split) and reduce |m|^2 by a fixed shuffle tree; lane 0 forms the parameters
+    const int lane = tid & 31, wid = tid >> 5;
+    for (int i = wid; i < V * cap; i += kFinThreads / 32) {
+      const int v = i / cap, t = i - v * cap;
+      const int D = c.D[v];
+      const int k = S.dish[v][t];
+      const size_t off = (size_t)cap * c.doff[v] + (size_t)t * D;
       double mm = 0.0;
-      for (int dd = 0; dd < D; ++dd) mm += (double)mt[dd] * (double)mt[dd];
-      const double a = (tau + n) / (2.0 * tau * (tau + n + 1.0));
-      const double cc = -0.5 * log(2.0 * kPi * tau * (tau + n + 1.0) / (tau + n));
-      q.A = (float)(kLog2e * a);
-      q.C = (float)(kLog2e * ((double)D * cc - a * mm));
-      if (n >= 2.0) {
-        const double a1 = (tau + n) / (2.0 * tau * (tau + n - 1.0));
-        const double c1 = -0.5 * log(2.0 * kPi * tau * (tau + n) / (tau + n - 1.0));
-        q.A1 = (float)(kLog2e * a1);
-        q.C1 = (float)(kLog2e * ((double)D * c1 - a1 * mm));
-      } else {
-        q.A1 = 0.f; q.C1 = kMasked;
+      const double inv_den = (k >= 0) ? 1.0 : 0.0;
+      const double den = (k >= 0) ? tau_v[v] + (double)S.n_vk[v][k] : 1.0;
+      const double* S1 = c.S1k + (size_t)cap * c.doff[v] + (size_t)(k >= 0 ? k : 0) * D;
+      for (int dd = lane; dd < D; dd += 32) {
+        const float m = (k >= 0) ? (float)(S1[dd] / den) : 0.f;
+        c.mean[off + dd] = m;
+        if (c.mean_hi) {
+          uint32_t hb, lb;                                            // TF32 split, both parts rounded to nearest
+          asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(hb) : "f"(m));
+          const float hi = __uint_as_float(hb);
+          asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(lb) : "f"(__fadd_rn(m, -hi)));
+          c.mean_hi[off + dd] = hi;
+          c.mean_lo[off + dd] = __uint_as_float(lb);
+        }
+        mm += (double)m * (double)m;
       }
-      bool rep = true;
-      for (int t2 = 0; t2 < t; ++t2) if (S.dish[v][t2] == k) { rep = false; break; }
-      const double w = (double)S.l_live[v][k] - sigma_v[v], w1 = w - 1.0;
-      q.W = (rep && w > 0.0) ? (float)log2(w) : kMasked;
-      q.W1 = (rep && w1 > 0.0) ? (float)log2(w1) : kMasked;
-      q.dish = k;
-      q.lone = (S.l_live[v][k] == 1);
+      (void)inv_den;
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) mm += __shfl_xor_sync(0xffffffffu, mm, o);
+      if (lane == 0) {
+        TableParam q;
+        if (k < 0) {
+          q.A = 0.f; q.C = kMasked; q.A1 = 0.f; q.C1 = kMasked; q.W = kMasked; q.W1 = kMasked; q.dish = -1; q.lone = 0;
+        } else {
+          const double tau = tau_v[v], n = (double)S.n_vk[v][k];
+          const double a = (tau + n) / (2.0 * tau * (tau + n + 1.0));
+          const double cc = -0.5 * log(2.0 * kPi * tau * (tau + n + 1.0) / (tau + n));
+          q.A = (float)(kLog2e * a);
+          q.C = (float)(kLog2e * ((double)D * cc - a * mm));
+          if (n >= 2.0) {
+            const double a1 = (tau + n) / (2.0 * tau * (tau + n - 1.0));
+            const double c1 = -0.5 * log(2.0 * kPi * tau * (tau + n) / (tau + n - 1.0));
+            q.A1 = (float)(kLog2e * a1);
+            q.C1 = (float)(kLog2e * ((double)D * c1 - a1 * mm));
+          } else {
+            q.A1 = 0.f; q.C1 = kMasked;
+          }
+          const bool rep = (__ffsll((long long)S.tmask[v][k]) - 1 == t);      // lowest table of its dish
+          const double w = (double)S.l_live[v][k] - sigma_v[v], w1 = w - 1.0;
+          q.W = (rep && w > 0.0) ? (float)log2(w) : kMasked;
+          q.W1 = (rep && w1 > 0.0) ? (float)log2(w1) : kMasked;
+          q.dish = k;
+          q.lone = (S.l_live[v][k] == 1);
+        }
+        c.tparam[i] = q;
+      }
     }
-    c.tparam[i] = q;
   }
   if (tid < V) {
     const int v = tid;
@@ -789,6 +896,7 @@ __global__ void __launch_bounds__(kFinThreads, 1) k_finalize(const Ctx c, const 
     *c.sweep = next;
     if (S.err) atomicOr(c.status, S.err);
   }
+  stamp(5);
 }
 
 cudaError_t launch_finalize(const Ctx& c, int32_t flags, cudaStream_t s) {
