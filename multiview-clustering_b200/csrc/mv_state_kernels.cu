@@ -143,7 +143,7 @@ static StatsPlan stats_plan(const Ctx& c) {
 int stats_smem_bytes(const Ctx& c) { return stats_plan(c).smem; }
 
 constexpr int kStatBatch = 16;   // rows whose loads are in flight per warp while the previous batch is accumulated
-constexpr int kStatAhead = 12;   // chunks (of 32 rows) the L2 prefetch runs ahead of the loads
+constexpr int kStatAhead = 4;    // chunks (of 32 rows) the L2 prefetch runs ahead of the loads
 
 __global__ void __launch_bounds__(512, 1) k_stats(const Ctx c, const int Gp, const int R, const int passes) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -219,22 +219,31 @@ __global__ void __launch_bounds__(512, 1) k_stats(const Ctx c, const int Gp, con
         }
         if (owner && tj >= 0) c.table_cur[row] = tj;
       }
+      if (owner) {
+        // customers per table: the lanes of one table elect a leader, which adds their number — one
+        // shared-memory update per distinct table of the chunk instead of one per row
+        const unsigned peers = __match_any_sync(0xffffffffu, tj);
+        if (tj >= 0 && lane == __ffs(peers) - 1) cntw[tj] += __popc(peers);
+      }
       for (int j0 = 0; j0 < 32; j0 += kStatBatch) {
         float xs[kStatBatch];
+        int ts[kStatBatch];
 #pragma unroll
-        for (int u = 0; u < kStatBatch; ++u) xs[u] = nx[u];
+        for (int u = 0; u < kStatBatch; ++u) {
+          xs[u] = has ? nx[u] : 0.0f;
+          ts[u] = __shfl_sync(0xffffffffu, tj, j0 + u);
+        }
         if (j0 + kStatBatch < 32) issue(ch, j0 + kStatBatch);
         else if (ch + 1 < w_hi) issue(ch + 1, 0);
 #pragma unroll
         for (int u = 0; u < kStatBatch; ++u) {
-          const int t = __shfl_sync(0xffffffffu, tj, j0 + u);
+          const int t = ts[u];
           if (t < 0) continue;                        // warp-uniform
-          const float xv = has ? xs[u] : 0.0f;
           float* a = acc + t * 32 + lane;
           float* q = accq + t * 32 + lane;
-          *a = __fadd_rn(*a, xv);
-          *q = __fmaf_rn(xv, xv, *q);
-          if (owner && lane == 0) cntw[t] += 1;
+          const float av = *a, qv = *q;               // both loads before either store: one round trip per row
+          *a = __fadd_rn(av, xs[u]);
+          *q = __fmaf_rn(xs[u], xs[u], qv);
         }
       }
     }
