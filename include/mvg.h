@@ -129,6 +129,10 @@ int mvg_get_state(mvg_handle* h, const mvg_state_host* out);
  * Asynchronous on the handle's stream; any mvg_get_* / mvg_sync observes the result. */
 int mvg_sweep(mvg_handle* h, int32_t n_sweeps, int32_t do_hyper);
 int mvg_hyper_step(mvg_handle* h);
+/* The same restricted to some of its Metropolis-Hastings updates: update_tau_v_MH alone
+ * (multiview_hyper.cpp:211-231), the per-view alpha/sigma pairs (:242-265), the franchise pair (:268-291). */
+enum { MVG_HYPER_TAU = 1, MVG_HYPER_LOCAL = 2, MVG_HYPER_GLOBAL = 4 };
+int mvg_hyper_step_parts(mvg_handle* h, int32_t parts);
 int mvg_sync(mvg_handle* h);
 /* gibbs_sampler(M, burn_in, thin): M sweeps; after sweep `iter` with iter >= burn_in and
  * (iter - burn_in) % thin == 0 the state is appended to the caller's trace buffers

@@ -419,7 +419,7 @@ int mvg_sweep(mvg_handle* h, int32_t n_sweeps, int32_t do_hyper) {
   if (!h->state_ready) return fail(h, MVG_ESTATE, "no state yet: call mvg_set_state or mvg_init_state_reference");
   if (n_sweeps < 0) return fail(h, MVG_EINVAL, "n_sweeps < 0");
   MVG_CUDA(h, cudaSetDevice(h->cfg.device));
-  const int32_t flags = kFinReseat | kFinAdvance | (do_hyper ? kFinHyper : 0);
+  const int32_t flags = kFinReseat | kFinAdvance | (do_hyper ? kFinHyperAll : 0);
   MVG_CUDA(h, cudaEventRecord(h->ev[0], h->stream));
   for (int it = 0; it < n_sweeps; ++it) {
     int rc = launch_draw(h);
@@ -432,15 +432,23 @@ int mvg_sweep(mvg_handle* h, int32_t n_sweeps, int32_t do_hyper) {
   return MVG_OK;
 }
 
-int mvg_hyper_step(mvg_handle* h) {
+int mvg_hyper_step_parts(mvg_handle* h, int32_t parts) {
   if (!h) return MVG_EINVAL;
   if (!h->state_ready) return fail(h, MVG_ESTATE, "no state yet");
+  if (parts & ~(MVG_HYPER_TAU | MVG_HYPER_LOCAL | MVG_HYPER_GLOBAL)) return fail(h, MVG_EINVAL, "unknown hyper part");
   MVG_CUDA(h, cudaSetDevice(h->cfg.device));
-  // rebuild the statistics of the current assignment, then one hyper step (no draw, no reseat)
+  // rebuild the statistics of the current assignment, then the selected Metropolis-Hastings updates
+  // (no draw, no reseat).  The sweep counter that addresses the Philox stream does not advance.
   MVG_CUDA(h, cudaMemcpyAsync(h->c.choice, h->c.table_cur, sizeof(int32_t) * (size_t)h->c.n_rows,
                               cudaMemcpyDeviceToDevice, h->stream));
-  return rebuild_pipeline(h, kFinHyper, nullptr);
+  int32_t flags = kFinHyper;
+  if (parts & MVG_HYPER_TAU) flags |= kFinHyperTau;
+  if (parts & MVG_HYPER_LOCAL) flags |= kFinHyperLocal;
+  if (parts & MVG_HYPER_GLOBAL) flags |= kFinHyperGlobal;
+  return rebuild_pipeline(h, flags, nullptr);
 }
+
+int mvg_hyper_step(mvg_handle* h) { return mvg_hyper_step_parts(h, MVG_HYPER_TAU | MVG_HYPER_LOCAL | MVG_HYPER_GLOBAL); }
 
 int mvg_sync(mvg_handle* h) {
   if (!h) return MVG_EINVAL;
@@ -597,7 +605,7 @@ int mvg_profile_sweep(mvg_handle* h, int32_t do_hyper, float ms_out[6]) {
   if (!h || !ms_out) return MVG_EINVAL;
   if (!h->state_ready) return fail(h, MVG_ESTATE, "no state yet");
   MVG_CUDA(h, cudaSetDevice(h->cfg.device));
-  const int32_t flags = kFinReseat | kFinAdvance | (do_hyper ? kFinHyper : 0);
+  const int32_t flags = kFinReseat | kFinAdvance | (do_hyper ? kFinHyperAll : 0);
   MVG_CUDA(h, cudaEventRecord(h->ev[2], h->stream));
   int rc = launch_draw(h);
   if (rc != MVG_OK) return rc;

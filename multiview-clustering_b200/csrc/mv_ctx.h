@@ -92,7 +92,11 @@ struct Ctx {
 
 enum FinalizeFlags : int32_t {
   kFinReseat = 1,      // seat births / resolve candidates (after a draw)
-  kFinHyper = 2,       // run the hyperparameter step
+  kFinHyper = 2,       // run the hyperparameter step: the parts selected by the three bits below
+  kFinHyperTau = 16,   //   tau_v            (update_tau_v_MH)
+  kFinHyperLocal = 32, //   alpha_v, sigma_v
+  kFinHyperGlobal = 64,//   alpha_global, sigma_global
+  kFinHyperAll = 2 | 16 | 32 | 64,
   kFinAdvance = 4,     // sweep += 1
   kFinTauInit = 8      // derive tau_v from pooled variance (reference init), alpha/sigma literals
 };

@@ -734,7 +734,7 @@ __global__ void __launch_bounds__(kFinThreads, 1) k_finalize(const Ctx c, const 
   // and of the franchise: they run side by side, one thread per level, on Philox numbers addressed by
   // the position the reference's sequential code would draw them at.
   if (flags & kFinHyper) {
-    {                                                          // update_tau_v_MH, :211-231: one warp per view
+    if (flags & kFinHyperTau) {                                // update_tau_v_MH, :211-231: one warp per view
       const int lane = tid & 31, wid = tid >> 5;
       for (int v = wid; v < V; v += kFinThreads / 32) {
         double tau_old = tau_v[v];
@@ -768,7 +768,7 @@ __global__ void __launch_bounds__(kFinThreads, 1) k_finalize(const Ctx c, const 
     __shared__ double s_alpha[2 * (kMaxViews + 1)], s_sigma[2 * (kMaxViews + 1)];
     // level j: its alpha/sigma slots in S.hyp and its Philox indices (alpha: base, sigma: base+1)
     const int j = tid;
-    const bool is_level = j <= V;
+    const bool is_level = (j < V) ? (flags & kFinHyperLocal) != 0 : (j == V && (flags & kFinHyperGlobal) != 0);
     const int ia = (j < V) ? j : 3 * V, is = (j < V) ? V + j : 3 * V + 1;
     const int base = (j < V) ? V + 2 * j : 3 * V;
     // alpha: log-normal random walk, :242-255 / :268-281
@@ -815,7 +815,6 @@ __global__ void __launch_bounds__(kFinThreads, 1) k_finalize(const Ctx c, const 
       const int k = S.dish[v][t];
       const size_t off = (size_t)cap * c.doff[v] + (size_t)t * D;
       double mm = 0.0;
-      const double inv_den = (k >= 0) ? 1.0 : 0.0;
       const double den = (k >= 0) ? tau_v[v] + (double)S.n_vk[v][k] : 1.0;
       const double* S1 = c.S1k + (size_t)cap * c.doff[v] + (size_t)(k >= 0 ? k : 0) * D;
       for (int dd = lane; dd < D; dd += 32) {
@@ -831,37 +830,42 @@ __global__ void __launch_bounds__(kFinThreads, 1) k_finalize(const Ctx c, const 
         }
         mm += (double)m * (double)m;
       }
-      (void)inv_den;
 #pragma unroll
       for (int o = 16; o > 0; o >>= 1) mm += __shfl_xor_sync(0xffffffffu, mm, o);
-      if (lane == 0) {
-        TableParam q;
-        if (k < 0) {
-          q.A = 0.f; q.C = kMasked; q.A1 = 0.f; q.C1 = kMasked; q.W = kMasked; q.W1 = kMasked; q.dish = -1; q.lone = 0;
-        } else {
-          const double tau = tau_v[v], n = (double)S.n_vk[v][k];
-          const double a = (tau + n) / (2.0 * tau * (tau + n + 1.0));
-          const double cc = -0.5 * log(2.0 * kPi * tau * (tau + n + 1.0) / (tau + n));
-          q.A = (float)(kLog2e * a);
-          q.C = (float)(kLog2e * ((double)D * cc - a * mm));
-          if (n >= 2.0) {
-            const double a1 = (tau + n) / (2.0 * tau * (tau + n - 1.0));
-            const double c1 = -0.5 * log(2.0 * kPi * tau * (tau + n) / (tau + n - 1.0));
-            q.A1 = (float)(kLog2e * a1);
-            q.C1 = (float)(kLog2e * ((double)D * c1 - a1 * mm));
-          } else {
-            q.A1 = 0.f; q.C1 = kMasked;
-          }
-          const bool rep = (__ffsll((long long)S.tmask[v][k]) - 1 == t);      // lowest table of its dish
-          const double w = (double)S.l_live[v][k] - sigma_v[v], w1 = w - 1.0;
-          q.W = (rep && w > 0.0) ? (float)log2(w) : kMasked;
-          q.W1 = (rep && w1 > 0.0) ? (float)log2(w1) : kMasked;
-          q.dish = k;
-          q.lone = (S.l_live[v][k] == 1);
-        }
-        c.tparam[i] = q;
-      }
+      if (lane == 0) S.s1sq[v][t] = mm;               // (s1sq is free again: reused for |m_t|^2)
     }
+  }
+  __syncthreads();
+  for (int i = tid; i < V * cap; i += kFinThreads) {          // the scalar part, one thread per (view, table)
+    const int v = i / cap, t = i - v * cap;
+    const int D = c.D[v];
+    const int k = S.dish[v][t];
+    const double mm = S.s1sq[v][t];
+    TableParam q;
+    if (k < 0) {
+      q.A = 0.f; q.C = kMasked; q.A1 = 0.f; q.C1 = kMasked; q.W = kMasked; q.W1 = kMasked; q.dish = -1; q.lone = 0;
+    } else {
+      const double tau = tau_v[v], n = (double)S.n_vk[v][k];
+      const double a = (tau + n) / (2.0 * tau * (tau + n + 1.0));
+      const double cc = -0.5 * log(2.0 * kPi * tau * (tau + n + 1.0) / (tau + n));
+      q.A = (float)(kLog2e * a);
+      q.C = (float)(kLog2e * ((double)D * cc - a * mm));
+      if (n >= 2.0) {
+        const double a1 = (tau + n) / (2.0 * tau * (tau + n - 1.0));
+        const double c1 = -0.5 * log(2.0 * kPi * tau * (tau + n) / (tau + n - 1.0));
+        q.A1 = (float)(kLog2e * a1);
+        q.C1 = (float)(kLog2e * ((double)D * c1 - a1 * mm));
+      } else {
+        q.A1 = 0.f; q.C1 = kMasked;
+      }
+      const bool rep = (__ffsll((long long)S.tmask[v][k]) - 1 == t);      // lowest table of its dish
+      const double w = (double)S.l_live[v][k] - sigma_v[v], w1 = w - 1.0;
+      q.W = (rep && w > 0.0) ? (float)log2(w) : kMasked;
+      q.W1 = (rep && w1 > 0.0) ? (float)log2(w1) : kMasked;
+      q.dish = k;
+      q.lone = (S.l_live[v][k] == 1);
+    }
+    c.tparam[i] = q;
   }
   if (tid < V) {
     const int v = tid;

@@ -1,0 +1,101 @@
+// multiview_gibbs.cpp — Rcpp entry, initialisation and chain loop of the B200 sampler.
+// Reference: /root/reference/Multiview/multiview_gibbs.cpp (run_gibbs_cpp :105-131,
+// initialize_state_from_data :12-103, gibbs_sampler :134-212).  Built with sourceCpp / R CMD SHLIB and
+// linked against the prebuilt libmvg_b200.so; every sweep runs on the GPU.
+#include "multiview_gibbs.h"
+
+#include <cmath>
+#include <string>
+
+#include "../../include/mvg.h"
+#include "multiview_hyper.h"
+#include "multiview_state.h"
+
+void mvhost_rcpp_stop(const std::string& msg) { Rcpp::stop(msg); }
+
+// multiview_gibbs.cpp:12-103: T = 4 random tables, 2 random dishes per view, statistics rebuild,
+// alpha_v = 1, sigma_v = .5, tau_v = 0.0025 Var(y_v), alpha_global = 1, sigma_global = .6 — on the
+// device, from the Philox initialisation domains.
+static void initialize_state_from_data() {
+  mvhost::open_chain();
+  if (mvg_init_state_reference(mvhost::chain()) != MVG_OK) mvhost::fail("initialize_state_from_data");
+  mvhost::pull_state();
+  saved_table_of.clear(); saved_dish_of.clear(); saved_loglik.clear();
+  saved_alpha_v.assign((size_t)d, {}); saved_sigma_v.assign((size_t)d, {}); saved_tau_v.assign((size_t)d, {});
+  saved_alpha_global.clear(); saved_sigma_global.clear();
+}
+
+// save_state of the reference (multiview_utils.cpp:291-303) on the mirrored state
+static void save_mirrored_state() {
+  saved_table_of.push_back(table_of);
+  saved_dish_of.push_back(dish_of);
+  for (int v = 0; v < d; ++v) {
+    saved_alpha_v[(size_t)v].push_back(views[(size_t)v].alpha_v);
+    saved_sigma_v[(size_t)v].push_back(views[(size_t)v].sigma_v);
+    saved_tau_v[(size_t)v].push_back(views[(size_t)v].tau_v);
+  }
+  saved_alpha_global.push_back(alpha_global);
+  saved_sigma_global.push_back(sigma_global);
+}
+
+// multiview_gibbs.cpp:134-212.  One mvg_sweep = the loop over all customers (:157-200) followed by
+// update_hyperparameters (:202); launches are asynchronous, the device is only read on kept sweeps.
+void gibbs_sampler(int M, int burn_in, int thin) {
+  if (!mvhost::chain()) Rcpp::stop("gibbs_sampler: state not initialised");
+  if (thin <= 0) Rcpp::stop("gibbs_sampler: thin must be positive");
+  for (int iter = 0; iter < M; ++iter) {
+    if ((iter + 1) % 100 == 0) Rcpp::Rcout << "Iteration " << (iter + 1) << " / " << M << "\n";   // :152-155
+    if (mvg_sweep(mvhost::chain(), 1, 1) != MVG_OK) mvhost::fail("gibbs_sampler");
+    if (iter >= burn_in && ((iter - burn_in) % thin == 0)) {                                       // :205
+      mvhost::pull_state();
+      save_mirrored_state();
+    }
+  }
+  mvhost::pull_state();
+}
+
+// Declared by the reference (multiview_gibbs.h:13) but never defined there.  Here: the collapsed log
+// marginal likelihood of the data given the current partition, sum over views and dishes of
+// logp(n, S1, S2) as multiview_utils.cpp:307-338 writes it (prior mean 0, prior variance 1).
+double compute_log_likelihood() {
+  double total = 0.0;
+  for (int v = 0; v < d; ++v) {
+    const ViewState& V = views[(size_t)v];
+    const int D = mvhost::view_dim.empty() ? 1 : mvhost::view_dim[(size_t)v];
+    const double tau = V.tau_v;
+    for (int k = 0; k < V.K; ++k) {
+      const double nk = (double)V.n_vk[(size_t)k];
+      if (nk <= 0.0) continue;
+      double s1sq = 0.0;
+      for (int j = 0; j < D; ++j) s1sq += V.sum_y[(size_t)k * D + j] * V.sum_y[(size_t)k * D + j];
+      total += (double)D * (-0.5 * nk * std::log(2.0 * M_PI * tau) - 0.5 * std::log(tau * (tau + nk)))
+               - 0.5 * V.sum_y2[(size_t)k] / tau + 0.5 * s1sq / (tau * (tau + nk));
+    }
+  }
+  return total;
+}
+
+// [[Rcpp::export]]
+Rcpp::List run_gibbs_cpp(const Rcpp::List& data_views,
+                         int M, int burn_in, int thin) {
+  d = data_views.size();
+  n = Rcpp::as<Rcpp::NumericVector>(data_views[0]).size();
+  y.clear();
+  y.resize((size_t)d);
+  for (int v = 0; v < d; ++v) y[(size_t)v] = Rcpp::as<std::vector<double>>(data_views[v]);
+  if (!mvhost::view_dim.empty()) n /= mvhost::view_dim[0];   // matrix views arrive flattened row-major
+
+  initialize_state_from_data();
+  gibbs_sampler(M, burn_in, thin);
+  mvhost::close_chain();
+
+  return Rcpp::List::create(
+      Rcpp::Named("table_of") = saved_table_of,
+      Rcpp::Named("dish_of") = saved_dish_of,
+      Rcpp::Named("loglik") = saved_loglik,
+      Rcpp::Named("alpha_v") = saved_alpha_v,
+      Rcpp::Named("sigma_v") = saved_sigma_v,
+      Rcpp::Named("tau_v") = saved_tau_v,
+      Rcpp::Named("alpha_global") = saved_alpha_global,
+      Rcpp::Named("sigma_global") = saved_sigma_global);
+}

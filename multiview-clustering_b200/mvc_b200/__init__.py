@@ -86,6 +86,7 @@ def lib():
         L.mvg_get_state.argtypes = [H, C.POINTER(_StateHost)]
         L.mvg_sweep.argtypes = [H, C.c_int32, C.c_int32]
         L.mvg_hyper_step.argtypes = [H]
+        L.mvg_hyper_step_parts.argtypes = [H, C.c_int32]
         L.mvg_sync.argtypes = [H]
         L.mvg_run.argtypes = [H, C.c_int32, C.c_int32, C.c_int32, C.c_int32, _i32p, _i32p, _f64p, _i32p]
         L.mvg_comm_attach.argtypes = [H, C.c_void_p]

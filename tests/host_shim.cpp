@@ -1,0 +1,61 @@
+// tests/host_shim.cpp — TEST scaffolding for the host layer (multiview-clustering_b200/host): R is not
+// installed here, so the sources are compiled against the stand-in Rcpp.h of oracle/refshim and driven
+// through these C hooks instead of through R.  Nothing here is product code.
+#include <Rcpp.h>
+
+#include <cstring>
+#include <sstream>
+
+#include "multiview_gibbs.h"
+#include "multiview_hyper.h"
+#include "multiview_rng.h"
+#include "multiview_state.h"
+
+namespace R {
+double runif(double, double) { return 0.5; }   // unused by the host layer (the device draws from Philox)
+double rnorm(double, double) { return 0.0; }
+}  // namespace R
+namespace Rcpp {
+static std::ostringstream g_sink;
+std::ostream Rcout(g_sink.rdbuf());
+}  // namespace Rcpp
+
+static std::string g_err;
+
+extern "C" {
+const char* host_last_error() { return g_err.c_str(); }
+
+// run_gibbs_cpp on d scalar views of n customers (y is [d][n]); returns the number of saved states
+int host_run(int n_, int d_, const double* y_, int M, int burn_in, int thin, int cap, unsigned long long seed) {
+  try {
+    mvhost::table_capacity = cap;
+    mvhost::seed = seed;
+    Rcpp::List data;
+    for (int v = 0; v < d_; ++v) data.push_back(std::vector<double>(y_ + (size_t)v * n_, y_ + (size_t)(v + 1) * n_));
+    run_gibbs_cpp(data, M, burn_in, thin);
+    return (int)saved_table_of.size();
+  } catch (const std::exception& e) {
+    g_err = e.what();
+    return -1;
+  }
+}
+int host_saved_T(int s) { return (int)saved_dish_of[(size_t)s][0].size(); }
+void host_saved_table_of(int s, int* out) { std::memcpy(out, saved_table_of[(size_t)s].data(), sizeof(int) * saved_table_of[(size_t)s].size()); }
+void host_saved_dish_of(int s, int v, int* out) { std::memcpy(out, saved_dish_of[(size_t)s][(size_t)v].data(), sizeof(int) * saved_dish_of[(size_t)s][(size_t)v].size()); }
+void host_saved_hypers(int s, int d_, double* out) {   // alpha_v[d], sigma_v[d], tau_v[d], alpha_g, sigma_g
+  for (int v = 0; v < d_; ++v) {
+    out[v] = saved_alpha_v[(size_t)v][(size_t)s];
+    out[d_ + v] = saved_sigma_v[(size_t)v][(size_t)s];
+    out[2 * d_ + v] = saved_tau_v[(size_t)v][(size_t)s];
+  }
+  out[3 * d_] = saved_alpha_global[(size_t)s];
+  out[3 * d_ + 1] = saved_sigma_global[(size_t)s];
+}
+// inspectors on the final mirrored state
+double host_log_EPPF(int v, double a, double s) { return log_EPPF(v, a, s); }
+double host_log_posterior_given_tau(int v, double tau) { return log_posterior_given_tau(v, tau); }
+double host_compute_log_likelihood() { return compute_log_likelihood(); }
+int host_final_T() { return T; }
+int host_final_K(int v) { return views[(size_t)v].K; }
+double host_uniform01(unsigned seed, int skip) { set_rng_seed(seed); double u = 0; for (int i = 0; i <= skip; ++i) u = uniform01(); return u; }
+}

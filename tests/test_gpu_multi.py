@@ -1,0 +1,21 @@
+"""Row-sharded chain over 2 GPUs (NCCL all-gather of the per-table statistics each sweep) against the
+one-GPU chain.  Needs two GPUs; run with `gpurun --gpus 2 -- python -m pytest tests -m gpu -k multi`."""
+import subprocess
+import sys
+from pathlib import Path
+
+import pytest
+
+ROOT = Path(__file__).resolve().parents[1]
+
+
+@pytest.mark.gpu
+def test_two_gpu_row_sharded_chain_matches_one_gpu():
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1",
+           "--master-port", "29517", str(ROOT / "tests" / "mp_gpu_shard.py")]
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-4000:]
+    assert "SHARD_OK" in r.stdout, r.stdout[-2000:]

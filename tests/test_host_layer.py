@@ -1,0 +1,84 @@
+"""The host layer (multiview-clustering_b200/host): the reference's C++ interface — run_gibbs_cpp,
+gibbs_sampler, update_hyperparameters, struct ViewState and the mirrored globals — over the C ABI.
+R is not installed in this image, so the sources are compiled against the stand-in Rcpp.h of
+oracle/refshim and driven through the C hooks of tests/host_shim.cpp."""
+import ctypes as C
+import subprocess
+from pathlib import Path
+
+import numpy as np
+import pytest
+from conftest import c1_data
+
+ROOT = Path(__file__).resolve().parents[1]
+HOST = ROOT / "multiview-clustering_b200" / "host"
+OUT = ROOT / "tests" / "_build" / "libmvhost_test.so"
+
+
+def build_host():
+    OUT.parent.mkdir(exist_ok=True)
+    srcs = [str(HOST / f) for f in ("multiview_gibbs.cpp", "multiview_hyper.cpp", "multiview_state.cpp")]
+    cmd = ["g++", "-O2", "-fPIC", "-std=c++17", "-Wall", "-DMVHOST_WITH_RCPP", f"-I{ROOT / 'oracle' / 'refshim'}", f"-I{HOST}",
+           "-shared", "-o", str(OUT), *srcs, str(ROOT / "tests" / "host_shim.cpp"),
+           f"-L{ROOT / 'multiview-clustering_b200' / 'mvc_b200'}", "-lmvg_b200",
+           f"-Wl,-rpath,{ROOT / 'multiview-clustering_b200' / 'mvc_b200'}"]
+    subprocess.run(cmd, check=True, capture_output=True, text=True)
+    return C.CDLL(str(OUT))
+
+
+def test_host_layer_compiles_and_keeps_the_reference_names():
+    """Every name of multiview_gibbs.h / multiview_hyper.h / multiview_state.h resolves in the built library."""
+    import mvc_b200
+    mvc_b200.lib()
+    build_host()
+    syms = subprocess.run(["nm", "-DC", str(OUT)], capture_output=True, text=True, check=True).stdout
+    for name in ["run_gibbs_cpp(Rcpp::List const&, int, int, int)", "gibbs_sampler(int, int, int)", "update_hyperparameters()",
+                 "update_tau_v_MH()", "log_EPPF(int, double, double)", "log_prior_alpha(double)", "log_prior_sigma(double)",
+                 "log_posterior_given_tau(int, double)", "propose_tau(double)", "initialize_hyperparameters()",
+                 "compute_log_likelihood()", "table_of", "dish_of", "views", "saved_table_of", "alpha_global", "sigma_global"]:
+        assert name in syms, name
+
+
+def test_host_philox_stream_is_the_c_abi_stream():
+    import mvc_b200
+    L = build_host()
+    L.host_uniform01.restype = C.c_double
+    M = mvc_b200.lib()
+    for skip in (0, 3, 17):
+        u = L.host_uniform01(C.c_uint(7), skip)
+        assert u == M.mvg_philox_uniform_f64(7, 0, 6, 0, 0, skip)
+
+
+@pytest.mark.gpu
+def test_run_gibbs_cpp_through_the_host_layer_equals_the_c_abi_chain():
+    """run_gibbs_cpp (host C++) and the ctypes binding drive the same device chain: same saved partitions."""
+    import mvc_b200
+    views, _ = c1_data(400)
+    y = np.ascontiguousarray(np.stack([v.astype(np.float64) for v in views]))
+    L = build_host()
+    L.host_last_error.restype = C.c_char_p
+    S = L.host_run(400, 2, y.ctypes.data_as(C.POINTER(C.c_double)), 60, 40, 5, 32, C.c_ulonglong(1999))
+    assert S == 4, L.host_last_error()
+    ref = mvc_b200.run_gibbs([y[0], y[1]], 60, 40, 5, cap=32, seed=1999)
+    for s in range(S):
+        T = L.host_saved_T(s)
+        tab = np.empty(400, np.int32)
+        L.host_saved_table_of(s, tab.ctypes.data_as(C.POINTER(C.c_int)))
+        rt = np.asarray(ref["table_of"][s])
+        live = np.unique(rt)                                    # slots -> dense labels in slot order
+        assert T == len(live)
+        np.testing.assert_array_equal(tab, np.searchsorted(live, rt))
+        for v in range(2):
+            dish = np.empty(T, np.int32)
+            L.host_saved_dish_of(s, v, dish.ctypes.data_as(C.POINTER(C.c_int)))
+            rd = np.asarray(ref["dish_of"][s][v])[live]
+            np.testing.assert_array_equal(dish, np.searchsorted(np.unique(rd), rd))
+        hyp = np.empty(8)
+        L.host_saved_hypers(s, 2, hyp.ctypes.data_as(C.POINTER(C.c_double)))
+        np.testing.assert_array_equal(hyp[:2], [ref["alpha_v"][v][s] for v in range(2)])
+        np.testing.assert_array_equal(hyp[4:6], [ref["tau_v"][v][s] for v in range(2)])
+        assert hyp[6] == ref["alpha_global"][s] and hyp[7] == ref["sigma_global"][s]
+    L.host_compute_log_likelihood.restype = C.c_double
+    L.host_log_EPPF.restype = C.c_double
+    assert np.isfinite(L.host_compute_log_likelihood())
+    assert np.isfinite(L.host_log_EPPF(0, C.c_double(1.0), C.c_double(0.5)))
