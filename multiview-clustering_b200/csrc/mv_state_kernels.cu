@@ -390,23 +390,27 @@ __device__ void eppf_batch(const Ctx& c, FinShared& S, const double* alpha, cons
   const int lane = tid & 31, wid = tid >> 5;
   const int nsets = 2 * (V + 1);
   __syncthreads();
-  // one warp per parameter set: lanes stride over the clusters, per-cluster terms summed by a fixed
-  // shuffle tree; the rank of a cluster among the live ones is a popcount of the level's live mask
-  for (int set = wid; set < nsets; set += kFinThreads / 32) {
-    const int j = set >> 1;
-    const int32_t* counts = (j < V) ? S.l_live[j] : S.n_new;
-    const double al = alpha[set], sg = sigma[set];
-    const unsigned long long lm = S.live[j];
+  // one thread per (parameter set, cluster): its two terms, summed per warp by a fixed shuffle tree into
+  // termA/termB[set][warp-in-set]; then one thread per set adds the warp partials in ascending order.
+  // The rank of a cluster among the live ones is a popcount of the level's live mask.
+  const int wps = (cap + 31) / 32;                   // warps per set
+  for (int base = 0; base < nsets * wps; base += kFinThreads / 32) {
+    const int unit = base + wid;                     // (set, 32-cluster block)
     double sa = 0.0, sb = 0.0;
     bool bad = false;
-    for (int i = lane; i < cap; i += 32) {
-      const int cnt = counts[i];
-      if (cnt > 0) {
-        const int r = __popcll(lm & ((1ull << i) - 1ull));
-        const double term = al + (double)r * sg;
-        if (term <= 0.0) bad = true; else sa += log(term);
+    if (unit < nsets * wps) {
+      const int set = unit / wps, i = (unit - set * wps) * 32 + lane, j = set >> 1;
+      if (i < cap) {
+        const int32_t* counts = (j < V) ? S.l_live[j] : S.n_new;
+        const double al = alpha[set], sg = sigma[set];
+        const int cnt = counts[i];
+        if (cnt > 0) {
+          const int r = __popcll(S.live[j] & ((1ull << i) - 1ull));
+          const double term = al + (double)r * sg;
+          if (term <= 0.0) bad = true; else sa = log(term);
+        }
+        if (cnt > 1) sb = lgamma((double)cnt - sg);   // minus lgamma(1 - sigma) per such cluster: added below
       }
-      if (cnt > 1) sb += lgamma((double)cnt - sg) - lgamma(1.0 - sg);
     }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
@@ -414,18 +418,31 @@ __device__ void eppf_batch(const Ctx& c, FinShared& S, const double* alpha, cons
       sb += __shfl_xor_sync(0xffffffffu, sb, o);
     }
     bad = __any_sync(0xffffffffu, bad);
-    if (lane == 0) {
-      const long long total = S.total[j];
-      double logp;
-      if (!(sg > kEps && sg < 1.0 - kEps) || al <= -sg) logp = -INFINITY;
-      else if (total <= 0) logp = 0.0;
-      else {
-        logp = bad ? -INFINITY : sa;
-        if (total > 1) logp -= lgamma(al + (double)total) - lgamma(al + 1.0);
-        logp += sb;
-      }
-      S.eppf[set] = logp;
+    if (unit < nsets * wps && lane == 0) {
+      const int set = unit / wps, blk = unit - set * wps;
+      S.termA[set][blk] = bad ? -INFINITY : sa;
+      S.termB[set][blk] = sb;
     }
+  }
+  __syncthreads();
+  if (tid < nsets) {
+    const int set = tid, j = set >> 1;
+    const int32_t* counts = (j < V) ? S.l_live[j] : S.n_new;
+    const double al = alpha[set], sg = sigma[set];
+    const long long total = S.total[j];
+    double logp;
+    if (!(sg > kEps && sg < 1.0 - kEps) || al <= -sg) logp = -INFINITY;
+    else if (total <= 0) logp = 0.0;
+    else {
+      int multi = 0;
+      for (int i = 0; i < cap; ++i) multi += counts[i] > 1;
+      double sa = 0.0, sb = 0.0;
+      for (int w = 0; w < wps; ++w) { sa += S.termA[set][w]; sb += S.termB[set][w]; }
+      logp = sa;
+      if (total > 1) logp -= lgamma(al + (double)total) - lgamma(al + 1.0);
+      logp += sb - (double)multi * lgamma(1.0 - sg);
+    }
+    S.eppf[set] = logp;
   }
   __syncthreads();
 }
@@ -681,30 +698,48 @@ __global__ void __launch_bounds__(kFinThreads, 1) k_finalize(const Ctx c, const 
     // one warp per dish (v, k): lanes stride over the coordinates; the tables serving the dish are added in
     // ascending order (warp-uniform test), then |S1k|^2 by a fixed shuffle tree
     const int lane = tid & 31, wid = tid >> 5;
-    for (int i = wid; i < V * cap; i += kFinThreads / 32) {
-      const int v = i / cap, k = i - v * cap;
-      const int D = c.D[v];
-      const double* S1t_v = c.S1t + (size_t)cap * c.doff[v];
-      double* S1k_vk = c.S1k + (size_t)cap * c.doff[v] + (size_t)k * D;
-      double q = 0.0;
-      for (int d0 = 0; d0 < D; d0 += 64) {
-        const int da = d0 + lane, db = d0 + 32 + lane;
-        double sa = 0.0, sb = 0.0;
-        for (unsigned long long m = S.tmask[v][k]; m; m &= m - 1ull) {
-          const int t = __ffsll((long long)m) - 1;
-          if (da < D) sa += S1t_v[(size_t)t * D + da];
-          if (db < D) sb += S1t_v[(size_t)t * D + db];
+    constexpr int kU = 4;                              // dishes in flight per warp: their loads overlap
+    for (int i0 = wid; i0 < V * cap; i0 += kU * (kFinThreads / 32)) {
+      double sa[kU], sb[kU];
+#pragma unroll
+      for (int u = 0; u < kU; ++u) {
+        const int i = i0 + u * (kFinThreads / 32);
+        sa[u] = 0.0; sb[u] = 0.0;
+        if (i >= V * cap) continue;
+        const int v = i / cap, k = i - v * cap;
+        const int D = c.D[v];
+        const double* S1t_v = c.S1t + (size_t)cap * c.doff[v];
+        for (unsigned long long m = S.tmask[v][k]; m; m &= m - 1ull) {   // tables of the dish, ascending
+          const int t = __ffsll((long long)m) - 1;   // (coordinates beyond 64 are handled by the strided pass below)
+          if (lane < D) sa[u] += S1t_v[(size_t)t * D + lane];
+          if (32 + lane < D) sb[u] += S1t_v[(size_t)t * D + 32 + lane];
         }
-        if (da < D) { S1k_vk[da] = sa; q += sa * sa; }
-        if (db < D) { S1k_vk[db] = sb; q += sb * sb; }
       }
 #pragma unroll
-      for (int o = 16; o > 0; o >>= 1) q += __shfl_xor_sync(0xffffffffu, q, o);
-      if (lane == 0) {
-        S.s1sq[v][k] = q;
-        const int n_k = S.n_vk[v][k];
-        double sse = (n_k > 0) ? c.S2k[i] - q / (double)n_k : 0.0;
-        S.sse[v][k] = sse < 0.0 ? 0.0 : sse;
+      for (int u = 0; u < kU; ++u) {
+        const int i = i0 + u * (kFinThreads / 32);
+        if (i >= V * cap) continue;
+        const int v = i / cap, k = i - v * cap;
+        const int D = c.D[v];
+        const double* S1t_v = c.S1t + (size_t)cap * c.doff[v];
+        double* S1k_vk = c.S1k + (size_t)cap * c.doff[v] + (size_t)k * D;
+        double q = 0.0;
+        if (lane < D) { S1k_vk[lane] = sa[u]; q += sa[u] * sa[u]; }
+        if (32 + lane < D) { S1k_vk[32 + lane] = sb[u]; q += sb[u] * sb[u]; }
+        for (int dd = 64 + lane; dd < D; dd += 32) {  // coordinates beyond 64: plain strided pass
+          double sum = 0.0;
+          for (unsigned long long m = S.tmask[v][k]; m; m &= m - 1ull) sum += S1t_v[(size_t)(__ffsll((long long)m) - 1) * D + dd];
+          S1k_vk[dd] = sum;
+          q += sum * sum;
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) q += __shfl_xor_sync(0xffffffffu, q, o);
+        if (lane == 0) {
+          S.s1sq[v][k] = q;
+          const int n_k = S.n_vk[v][k];
+          double sse = (n_k > 0) ? c.S2k[i] - q / (double)n_k : 0.0;
+          S.sse[v][k] = sse < 0.0 ? 0.0 : sse;
+        }
       }
     }
   }
@@ -809,30 +844,49 @@ __global__ void __launch_bounds__(kFinThreads, 1) k_finalize(const Ctx c, const 
     // one warp per (view, table): lanes stride over the coordinates of the posterior mean m = S1k / (tau + n),
     // write it (and its TF32 split) and reduce |m|^2 by a fixed shuffle tree; lane 0 forms the parameters
     const int lane = tid & 31, wid = tid >> 5;
-    for (int i = wid; i < V * cap; i += kFinThreads / 32) {
-      const int v = i / cap, t = i - v * cap;
-      const int D = c.D[v];
-      const int k = S.dish[v][t];
-      const size_t off = (size_t)cap * c.doff[v] + (size_t)t * D;
-      double mm = 0.0;
-      const double den = (k >= 0) ? tau_v[v] + (double)S.n_vk[v][k] : 1.0;
-      const double* S1 = c.S1k + (size_t)cap * c.doff[v] + (size_t)(k >= 0 ? k : 0) * D;
-      for (int dd = lane; dd < D; dd += 32) {
-        const float m = (k >= 0) ? (float)(S1[dd] / den) : 0.f;
-        c.mean[off + dd] = m;
-        if (c.mean_hi) {
-          uint32_t hb, lb;                                            // TF32 split, both parts rounded to nearest
-          asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(hb) : "f"(m));
-          const float hi = __uint_as_float(hb);
-          asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(lb) : "f"(__fadd_rn(m, -hi)));
-          c.mean_hi[off + dd] = hi;
-          c.mean_lo[off + dd] = __uint_as_float(lb);
-        }
-        mm += (double)m * (double)m;
+    constexpr int kU = 4;                              // tables in flight per warp: their loads overlap
+    for (int i0 = wid; i0 < V * cap; i0 += kU * (kFinThreads / 32)) {
+      double s1a[kU], s1b[kU];
+#pragma unroll
+      for (int u = 0; u < kU; ++u) {
+        const int i = i0 + u * (kFinThreads / 32);
+        s1a[u] = 0.0; s1b[u] = 0.0;
+        if (i >= V * cap) continue;
+        const int v = i / cap, t = i - v * cap;
+        const int D = c.D[v], k = S.dish[v][t];
+        if (k < 0) continue;
+        const double* S1 = c.S1k + (size_t)cap * c.doff[v] + (size_t)k * D;
+        if (lane < D) s1a[u] = S1[lane];
+        if (32 + lane < D) s1b[u] = S1[32 + lane];
       }
 #pragma unroll
-      for (int o = 16; o > 0; o >>= 1) mm += __shfl_xor_sync(0xffffffffu, mm, o);
-      if (lane == 0) S.s1sq[v][t] = mm;               // (s1sq is free again: reused for |m_t|^2)
+      for (int u = 0; u < kU; ++u) {
+        const int i = i0 + u * (kFinThreads / 32);
+        if (i >= V * cap) continue;
+        const int v = i / cap, t = i - v * cap;
+        const int D = c.D[v], k = S.dish[v][t];
+        const size_t off = (size_t)cap * c.doff[v] + (size_t)t * D;
+        const double den = (k >= 0) ? tau_v[v] + (double)S.n_vk[v][k] : 1.0;
+        const double* S1 = c.S1k + (size_t)cap * c.doff[v] + (size_t)(k >= 0 ? k : 0) * D;
+        double mm = 0.0;
+        for (int dd = lane; dd < D; dd += 32) {
+          const double s1 = (dd == lane) ? s1a[u] : ((dd == 32 + lane) ? s1b[u] : S1[dd]);
+          const float m = (k >= 0) ? (float)(s1 / den) : 0.f;
+          c.mean[off + dd] = m;
+          if (c.mean_hi) {
+            uint32_t hb, lb;                                            // TF32 split, both parts rounded to nearest
+            asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(hb) : "f"(m));
+            const float hi = __uint_as_float(hb);
+            asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(lb) : "f"(__fadd_rn(m, -hi)));
+            c.mean_hi[off + dd] = hi;
+            c.mean_lo[off + dd] = __uint_as_float(lb);
+          }
+          mm += (double)m * (double)m;
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) mm += __shfl_xor_sync(0xffffffffu, mm, o);
+        if (lane == 0) S.s1sq[v][t] = mm;               // (s1sq is free again: reused for |m_t|^2)
+      }
     }
   }
   __syncthreads();
