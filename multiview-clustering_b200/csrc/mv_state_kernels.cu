@@ -23,6 +23,13 @@ constexpr double kEps = 1e-6;            // multiview_hyper.cpp:13
 constexpr double kLog2e = 1.4426950408889634074;
 constexpr double kPi = 3.14159265358979323846;
 
+// k_finalize runs once per sweep with a cold instruction cache, and FP64 log/exp/lgamma expand to hundreds of
+// instructions at every call site: one out-of-line copy of each keeps the kernel small enough to fetch quickly.
+__device__ __noinline__ double fin_log(double x) { return log(x); }
+__device__ __noinline__ double fin_exp(double x) { return exp(x); }
+__device__ __noinline__ double fin_lgamma(double x) { return lgamma(x); }
+__device__ __noinline__ double fin_log2(double x) { return log2(x); }
+
 __device__ __forceinline__ int32_t* pkt_i32(const Ctx& c, int g, int off) {
   return reinterpret_cast<int32_t*>(c.packet + (size_t)g * c.pkt.bytes + off);
 }
@@ -352,21 +359,21 @@ struct FinShared {
   double hyp[3 * kMaxViews + 2];
 };
 
-__device__ __forceinline__ double dev_normal(const Ctx& c, uint32_t sweep, int idx) {
+__device__ __noinline__ double dev_normal(const Ctx& c, uint32_t sweep, int idx) {
   const U4 r = stream_block(c.seed, c.chain, kDomHyperNormal, 0, sweep, (uint64_t)idx);
   const double u1 = uniform_f64_from(r.x, r.y), u2 = uniform_f64_from(r.z, r.w);
-  return sqrt(-2.0 * log(u1)) * cos(6.283185307179586476925286766559 * u2);
+  return sqrt(-2.0 * fin_log(u1)) * cos(6.283185307179586476925286766559 * u2);
 }
-__device__ __forceinline__ double dev_unif(const Ctx& c, uint32_t sweep, int idx) {
+__device__ __noinline__ double dev_unif(const Ctx& c, uint32_t sweep, int idx) {
   const U4 r = stream_block(c.seed, c.chain, kDomHyperUnif, 0, sweep, (uint64_t)idx);
   return uniform_f64_from(r.x, r.y);
 }
 
 __device__ __forceinline__ double log_prior_alpha(double a) {       // multiview_hyper.cpp:344-351
-  return (a <= 0.0) ? -INFINITY : (4.0 - 1.0) * log(a) - 3.0 * a;
+  return (a <= 0.0) ? -INFINITY : (4.0 - 1.0) * fin_log(a) - 3.0 * a;
 }
 __device__ __forceinline__ double log_prior_sigma(double s) {       // :353-360
-  return (s <= 0.0 || s >= 1.0) ? -INFINITY : (1.0 - 1.0) * log(s) + (5.0 - 1.0) * log(1.0 - s);
+  return (s <= 0.0 || s >= 1.0) ? -INFINITY : (1.0 - 1.0) * fin_log(s) + (5.0 - 1.0) * fin_log(1.0 - s);
 }
 __device__ __forceinline__ double reflect_unit(double value) {      // :110-122
   double p = value;
@@ -381,11 +388,11 @@ __device__ __forceinline__ double reflect_unit(double value) {      // :110-122
 // Set 2j+q (q = 0 old / 1 proposed) belongs to level j: j < V is view j (cluster sizes = tables per
 // dish l_vk, items = tables), j = V is the franchise (sizes = customers per table n_t, items = all
 // customers).  The two inner loops are taken in closed form,
-//   sum_{i=1}^{M-1} log(alpha+i) = lgamma(alpha+M) - lgamma(alpha+1),
-//   sum_{m=1}^{c-1} log(m-sigma) = lgamma(c-sigma) - lgamma(1-sigma),
+//   sum_{i=1}^{M-1} fin_log(alpha+i) = fin_lgamma(alpha+M) - fin_lgamma(alpha+1),
+//   sum_{m=1}^{c-1} fin_log(m-sigma) = fin_lgamma(c-sigma) - fin_lgamma(1-sigma),
 // the per-cluster terms are evaluated by the block in parallel and one thread per set adds them in
 // ascending cluster order (the order of oracle/mv_oracle.c:eppf_core).  Block-uniform call.
-__device__ void eppf_batch(const Ctx& c, FinShared& S, const double* alpha, const double* sigma) {
+__device__ __noinline__ void eppf_batch(const Ctx& c, FinShared& S, const double* alpha, const double* sigma) {
   const int tid = threadIdx.x, cap = c.cap, V = c.V;
   const int lane = tid & 31, wid = tid >> 5;
   const int nsets = 2 * (V + 1);
@@ -407,9 +414,9 @@ __device__ void eppf_batch(const Ctx& c, FinShared& S, const double* alpha, cons
         if (cnt > 0) {
           const int r = __popcll(S.live[j] & ((1ull << i) - 1ull));
           const double term = al + (double)r * sg;
-          if (term <= 0.0) bad = true; else sa = log(term);
+          if (term <= 0.0) bad = true; else sa = fin_log(term);
         }
-        if (cnt > 1) sb = lgamma((double)cnt - sg);   // minus lgamma(1 - sigma) per such cluster: added below
+        if (cnt > 1) sb = fin_lgamma((double)cnt - sg);   // minus fin_lgamma(1 - sigma) per such cluster: added below
       }
     }
 #pragma unroll
@@ -439,17 +446,17 @@ __device__ void eppf_batch(const Ctx& c, FinShared& S, const double* alpha, cons
       double sa = 0.0, sb = 0.0;
       for (int w = 0; w < wps; ++w) { sa += S.termA[set][w]; sb += S.termB[set][w]; }
       logp = sa;
-      if (total > 1) logp -= lgamma(al + (double)total) - lgamma(al + 1.0);
-      logp += sb - (double)multi * lgamma(1.0 - sg);
+      if (total > 1) logp -= fin_lgamma(al + (double)total) - fin_lgamma(al + 1.0);
+      logp += sb - (double)multi * fin_lgamma(1.0 - sg);
     }
     S.eppf[set] = logp;
   }
   __syncthreads();
 }
 
-__device__ double log_posterior_tau(const Ctx& c, const FinShared& S, int v, double tau) {  // :176-209
+__device__ __noinline__ double log_posterior_tau(const Ctx& c, const FinShared& S, int v, double tau) {  // :176-209
   if (tau <= 0.0) return -INFINITY;
-  const double lg = log(2.0 * kPi * tau);      // same value in every term of the reference's loop
+  const double lg = fin_log(2.0 * kPi * tau);      // same value in every term of the reference's loop
   const double Dd = (double)c.D[v];
   double loglik = 0.0;
   for (int k = 0; k < c.cap; ++k) {
@@ -458,12 +465,12 @@ __device__ double log_posterior_tau(const Ctx& c, const FinShared& S, int v, dou
     loglik += -0.5 * (double)n_k * Dd * lg - 0.5 * (S.sse[v][k] / tau);
   }
   const double a_tau = 2.0, b_tau = 1.0;                                   // :133-134
-  return loglik + (a_tau * log(b_tau) - lgamma(a_tau) - (a_tau + 1.0) * log(tau) - b_tau / tau);
+  return loglik + (a_tau * fin_log(b_tau) - fin_lgamma(a_tau) - (a_tau + 1.0) * fin_log(tau) - b_tau / tau);
 }
 
 // log predictive density of x (views concatenated, FP32) under dish k of view v, optionally with
 // x removed from the dish first (multiview_utils.cpp:307-338 in closed form, per coordinate).
-__device__ double log_f_dish(const Ctx& c, const FinShared& S, int v, int k, const float* x, bool loo,
+__device__ __noinline__ double log_f_dish(const Ctx& c, const FinShared& S, int v, int k, const float* x, bool loo,
                              double tau) {
   const int D = c.D[v];
   const double* S1 = c.S1k + (size_t)c.cap * c.doff[v] + (size_t)k * D;
@@ -476,7 +483,7 @@ __device__ double log_f_dish(const Ctx& c, const FinShared& S, int v, int k, con
     const double diff = xv - s1 / (tau + n);
     dist += diff * diff;
   }
-  return -0.5 * (double)D * log(2.0 * kPi * var) - 0.5 * dist / var;
+  return -0.5 * (double)D * fin_log(2.0 * kPi * var) - 0.5 * dist / var;
 }
 
 __global__ void __launch_bounds__(kFinThreads, 1) k_finalize(const Ctx c, const int32_t flags) {
@@ -549,7 +556,7 @@ __global__ void __launch_bounds__(kFinThreads, 1) k_finalize(const Ctx c, const 
         const int D = c.D[v];
         double q = 0.0;
         for (int dd = 0; dd < D; ++dd) q += (double)x[c.doff[v] + dd] * (double)x[c.doff[v] + dd];
-        val = -0.5 * (double)D * log(2.0 * kPi * tau_v[v]) - 0.5 * q / tau_v[v];
+        val = -0.5 * (double)D * fin_log(2.0 * kPi * tau_v[v]) - 0.5 * q / tau_v[v];
       } else {
         const int t0 = pkt_i32(c, S.cand_g[b], c.pkt.off_cand_t0)[S.cand_j[b]];
         val = log_f_dish(c, S, v, k, x, (k == S.dish[v][t0]) && S.n_vk[v][k] > 0, tau_v[v]);
@@ -573,12 +580,12 @@ __global__ void __launch_bounds__(kFinThreads, 1) k_finalize(const Ctx c, const 
           if (tid < cap) {
             const int l = S.l_live[v][tid] - ((single && tid == k0) ? 1 : 0);
             const double w = (double)l - sigma_v[v];                       // :232-233
-            if (l > 0 && w > 0.0) lw = log(w) + lf[tid];
+            if (l > 0 && w > 0.0) lw = fin_log(w) + lf[tid];
           } else {
             int K_act = 0;
             for (int k = 0; k < cap; ++k) K_act += (S.l_live[v][k] - ((single && k == k0) ? 1 : 0)) > 0;
             const double wn = alpha_v[v] + sigma_v[v] * (double)K_act;     // :241-243
-            if (wn > 0.0) lw = log(wn) + lf[cap];
+            if (wn > 0.0) lw = fin_log(wn) + lf[cap];
           }
           S.wbuf[tid] = lw;
         }
@@ -591,7 +598,7 @@ __global__ void __launch_bounds__(kFinThreads, 1) k_finalize(const Ctx c, const 
         __syncthreads();
         if (tid <= cap) {
           const double M = S.result[0], lw = S.wbuf[tid];
-          const double w = (M > -INFINITY && lw > -INFINITY) ? exp(lw - M) : 0.0;
+          const double w = (M > -INFINITY && lw > -INFINITY) ? fin_exp(lw - M) : 0.0;
           S.termA[0][tid] = w;
           if (c.debug_export) c.dbg_birth_w[((size_t)b * V + v) * (cap + 1) + tid] = w;
         }
@@ -774,9 +781,9 @@ __global__ void __launch_bounds__(kFinThreads, 1) k_finalize(const Ctx c, const 
       for (int v = wid; v < V; v += kFinThreads / 32) {
         double tau_old = tau_v[v];
         if (tau_old <= 0.0) tau_old = kEps;
-        const double tau_prop = exp(log(tau_old) + 0.0 + 0.3 * dev_normal(c, sweep, v));   // :166-174
+        const double tau_prop = fin_exp(fin_log(tau_old) + 0.0 + 0.3 * dev_normal(c, sweep, v));   // :166-174
         // log_posterior_given_tau (:176-209) at both values: lanes stride over the dishes, shuffle-tree sum
-        const double lg_o = log(2.0 * kPi * tau_old), lg_p = log(2.0 * kPi * tau_prop);
+        const double lg_o = fin_log(2.0 * kPi * tau_old), lg_p = fin_log(2.0 * kPi * tau_prop);
         const double Dd = (double)c.D[v];
         double lo = 0.0, ln = 0.0;
         for (int k = lane; k < cap; k += 32) {
@@ -792,10 +799,10 @@ __global__ void __launch_bounds__(kFinThreads, 1) k_finalize(const Ctx c, const 
         }
         if (lane == 0) {
           const double a_tau = 2.0, b_tau = 1.0;                                    // :133-134
-          const double log_old = lo + (a_tau * log(b_tau) - lgamma(a_tau) - (a_tau + 1.0) * log(tau_old) - b_tau / tau_old);
-          const double log_new = ln + (a_tau * log(b_tau) - lgamma(a_tau) - (a_tau + 1.0) * log(tau_prop) - b_tau / tau_prop);
-          const double log_acc = (log_new - log_old) + (log(tau_prop) - log(tau_old));
-          if (log(dev_unif(c, sweep, v)) < log_acc) tau_v[v] = tau_prop;
+          const double log_old = lo + (a_tau * fin_log(b_tau) - fin_lgamma(a_tau) - (a_tau + 1.0) * fin_log(tau_old) - b_tau / tau_old);
+          const double log_new = ln + (a_tau * fin_log(b_tau) - fin_lgamma(a_tau) - (a_tau + 1.0) * fin_log(tau_prop) - b_tau / tau_prop);
+          const double log_acc = (log_new - log_old) + (fin_log(tau_prop) - fin_log(tau_old));
+          if (fin_log(dev_unif(c, sweep, v)) < log_acc) tau_v[v] = tau_prop;
         }
       }
     }
@@ -811,7 +818,7 @@ __global__ void __launch_bounds__(kFinThreads, 1) k_finalize(const Ctx c, const 
     if (is_level) {
       a_old = S.hyp[ia];
       if (a_old <= 0.0) a_old = kEps;
-      const double cand = exp(log(a_old > kEps ? a_old : kEps) + 0.0 + 0.1 * dev_normal(c, sweep, base));   // :100-108
+      const double cand = fin_exp(fin_log(a_old > kEps ? a_old : kEps) + 0.0 + 0.1 * dev_normal(c, sweep, base));   // :100-108
       a_prop = cand > kEps ? cand : kEps;
       s_alpha[2 * j] = a_old; s_alpha[2 * j + 1] = a_prop;
       s_sigma[2 * j] = S.hyp[is]; s_sigma[2 * j + 1] = S.hyp[is];
@@ -820,8 +827,8 @@ __global__ void __launch_bounds__(kFinThreads, 1) k_finalize(const Ctx c, const 
     double s_old = 0.0, s_prop = 0.0;
     if (is_level) {
       const double lo = S.eppf[2 * j] + log_prior_alpha(a_old), ln = S.eppf[2 * j + 1] + log_prior_alpha(a_prop);
-      const double log_acc = (ln - lo) + (log(a_prop) - log(a_old));
-      if (log(dev_unif(c, sweep, base)) < log_acc) S.hyp[ia] = a_prop;
+      const double log_acc = (ln - lo) + (fin_log(a_prop) - fin_log(a_old));
+      if (fin_log(dev_unif(c, sweep, base)) < log_acc) S.hyp[ia] = a_prop;
       // sigma: reflected random walk, :257-265 / :283-291
       s_old = S.hyp[is];
       s_prop = reflect_unit(s_old + 0.0 + 0.05 * dev_normal(c, sweep, base + 1));                             // :124-128
@@ -832,7 +839,7 @@ __global__ void __launch_bounds__(kFinThreads, 1) k_finalize(const Ctx c, const 
     if (is_level) {
       const double lpo = (s_old <= kEps || s_old >= 1.0 - kEps) ? -INFINITY : S.eppf[2 * j] + log_prior_sigma(s_old);
       const double lpn = (s_prop <= kEps || s_prop >= 1.0 - kEps) ? -INFINITY : S.eppf[2 * j + 1] + log_prior_sigma(s_prop);
-      if (log(dev_unif(c, sweep, base + 1)) < lpn - lpo) S.hyp[is] = s_prop;
+      if (fin_log(dev_unif(c, sweep, base + 1)) < lpn - lpo) S.hyp[is] = s_prop;
     }
     __syncthreads();
   }
@@ -901,12 +908,12 @@ __global__ void __launch_bounds__(kFinThreads, 1) k_finalize(const Ctx c, const 
     } else {
       const double tau = tau_v[v], n = (double)S.n_vk[v][k];
       const double a = (tau + n) / (2.0 * tau * (tau + n + 1.0));
-      const double cc = -0.5 * log(2.0 * kPi * tau * (tau + n + 1.0) / (tau + n));
+      const double cc = -0.5 * fin_log(2.0 * kPi * tau * (tau + n + 1.0) / (tau + n));
       q.A = (float)(kLog2e * a);
       q.C = (float)(kLog2e * ((double)D * cc - a * mm));
       if (n >= 2.0) {
         const double a1 = (tau + n) / (2.0 * tau * (tau + n - 1.0));
-        const double c1 = -0.5 * log(2.0 * kPi * tau * (tau + n) / (tau + n - 1.0));
+        const double c1 = -0.5 * fin_log(2.0 * kPi * tau * (tau + n) / (tau + n - 1.0));
         q.A1 = (float)(kLog2e * a1);
         q.C1 = (float)(kLog2e * ((double)D * c1 - a1 * mm));
       } else {
@@ -914,8 +921,8 @@ __global__ void __launch_bounds__(kFinThreads, 1) k_finalize(const Ctx c, const 
       }
       const bool rep = (__ffsll((long long)S.tmask[v][k]) - 1 == t);      // lowest table of its dish
       const double w = (double)S.l_live[v][k] - sigma_v[v], w1 = w - 1.0;
-      q.W = (rep && w > 0.0) ? (float)log2(w) : kMasked;
-      q.W1 = (rep && w1 > 0.0) ? (float)log2(w1) : kMasked;
+      q.W = (rep && w > 0.0) ? (float)fin_log2(w) : kMasked;
+      q.W1 = (rep && w1 > 0.0) ? (float)fin_log2(w1) : kMasked;
       q.dish = k;
       q.lone = (S.l_live[v][k] == 1);
     }
@@ -929,21 +936,21 @@ __global__ void __launch_bounds__(kFinThreads, 1) k_finalize(const Ctx c, const 
     for (int k = 0; k < cap; ++k) if (S.l_live[v][k] > 0) { K_act++; sum_l += S.l_live[v][k]; }
     ViewParam p;
     p.AN = (float)(kLog2e / (2.0 * tau));
-    p.CN = (float)(kLog2e * (-0.5 * (double)c.D[v] * log(2.0 * kPi * tau)));
+    p.CN = (float)(kLog2e * (-0.5 * (double)c.D[v] * fin_log(2.0 * kPi * tau)));
     const double wn0 = alpha_v[v] + (double)K_act * sigma_v[v], wn1 = alpha_v[v] + (double)(K_act - 1) * sigma_v[v];
-    p.WN0 = wn0 > 0.0 ? (float)log2(wn0) : kMasked;
-    p.WN1 = wn1 > 0.0 ? (float)log2(wn1) : kMasked;
+    p.WN0 = wn0 > 0.0 ? (float)fin_log2(wn0) : kMasked;
+    p.WN1 = wn1 > 0.0 ? (float)fin_log2(wn1) : kMasked;
     const double d0 = alpha_v[v] + (double)sum_l, d1 = alpha_v[v] + (double)(sum_l - 1);
-    p.LD0 = d0 > 0.0 ? (float)log2(d0) : 0.f;
-    p.LD1 = d1 > 0.0 ? (float)log2(d1) : 0.f;
+    p.LD0 = d0 > 0.0 ? (float)fin_log2(d0) : 0.f;
+    p.LD1 = d1 > 0.0 ? (float)fin_log2(d1) : 0.f;
     p.pad0 = p.pad1 = 0.f;
     c.vparam[v] = p;
   }
   for (int t = tid; t < cap; t += kFinThreads) {
     const double mass = (double)S.n_new[t] - sigma_g, mass1 = mass - 1.0;
     TableMass tm;
-    tm.LM = (S.n_new[t] > 0 && mass > 0.0) ? (float)log2(mass) : kMasked;
-    tm.LM1 = (S.n_new[t] > 1 && mass1 > 0.0) ? (float)log2(mass1) : kMasked;
+    tm.LM = (S.n_new[t] > 0 && mass > 0.0) ? (float)fin_log2(mass) : kMasked;
+    tm.LM1 = (S.n_new[t] > 1 && mass1 > 0.0) ? (float)fin_log2(mass1) : kMasked;
     tm.single = (S.n_new[t] == 1);
     tm.pad = 0;
     c.tmass[t] = tm;
@@ -954,8 +961,8 @@ __global__ void __launch_bounds__(kFinThreads, 1) k_finalize(const Ctx c, const 
     const int F = cap - T_ne;
     const double mn0 = alpha_g + sigma_g * (double)T_ne, mn1 = alpha_g + sigma_g * (double)(T_ne - 1);
     GlobalParam g;
-    g.LMN0 = (F > 0 && mn0 > 0.0) ? (float)log2(mn0) : kMasked;
-    g.LMN1 = (F > 0 && mn1 > 0.0) ? (float)log2(mn1) : kMasked;
+    g.LMN0 = (F > 0 && mn0 > 0.0) ? (float)fin_log2(mn0) : kMasked;
+    g.LMN1 = (F > 0 && mn1 > 0.0) ? (float)fin_log2(mn1) : kMasked;
     g.nfree = F;
     const uint32_t next = sweep + ((flags & kFinAdvance) ? 1u : 0u);
     g.sweep = next;
