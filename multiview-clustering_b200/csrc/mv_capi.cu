@@ -201,7 +201,7 @@ int check_status(mvg_handle* h) {
   if (st[0] != 0) {
     MVG_CUDA(h, cudaMemsetAsync(h->c.status, 0, sizeof(st), h->stream));
     return fail(h, MVG_EINVAL, "device-side invariant violated, flags=" + std::to_string(st[0]) +
-                                   " (1: no free dish slot for a birth, 2: live table without a dish)");
+                                   " (1: no free dish slot for a birth, 2: live table without a dish, 4: customers lost in the statistics rebuild)");
   }
   return MVG_OK;
 }
@@ -255,6 +255,15 @@ int mvg_create(const mvg_config* cfg, mvg_handle** out) {
   c.n_chunks = (c.n_rows + 31) / 32;
   c.stat_ctas = c.n_chunks < h->sms ? c.n_chunks : h->sms;
   c.debug_export = cfg->debug_export;
+  {
+    void* q = nullptr;
+    if (cudaMalloc(&q, sizeof(float) * (size_t)c.n_rows * c.V) != cudaSuccess) {
+      mvg_destroy(h);
+      return fail(nullptr, MVG_ENOMEM, "cudaMalloc: squared norms");
+    }
+    h->owned.push_back(q);
+    c.xx = static_cast<float*>(q);
+  }
   *out = h;
   return MVG_OK;
 }
@@ -295,6 +304,8 @@ int mvg_upload_view_f32(mvg_handle* h, int32_t v, const float* x_host, int32_t d
   MVG_CUDA(h, cudaMemcpyAsync(h->view_owned[v], x_host, bytes, cudaMemcpyHostToDevice, h->stream));
   h->c.x[v] = static_cast<const float*>(h->view_owned[v]);
   h->c.D[v] = dim;
+  MVG_CUDA(h, launch_rownorms(h->c.x[v], h->c.xx + (size_t)v * h->c.n_rows, h->c.n_rows, dim, h->stream));
+  h->launches += 1;
   return MVG_OK;
 }
 
@@ -318,6 +329,8 @@ int mvg_upload_view_f64(mvg_handle* h, int32_t v, const double* y_host, int32_t 
   h->launches += 1;
   h->c.x[v] = static_cast<const float*>(h->view_owned[v]);
   h->c.D[v] = dim;
+  MVG_CUDA(h, launch_rownorms(h->c.x[v], h->c.xx + (size_t)v * h->c.n_rows, h->c.n_rows, dim, h->stream));
+  h->launches += 1;
   return MVG_OK;
 }
 
@@ -328,6 +341,8 @@ int mvg_attach_view_device_f32(mvg_handle* h, int32_t v, const float* x_dev, int
   if (h->view_owned[v]) { cudaFree(h->view_owned[v]); h->view_owned[v] = nullptr; }
   h->c.x[v] = x_dev;
   h->c.D[v] = dim;
+  MVG_CUDA(h, launch_rownorms(x_dev, h->c.xx + (size_t)v * h->c.n_rows, h->c.n_rows, dim, h->stream));
+  h->launches += 1;
   return MVG_OK;
 }
 

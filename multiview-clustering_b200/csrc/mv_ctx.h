@@ -48,6 +48,7 @@ struct Ctx {
   int32_t D[kMaxViews];
   int32_t doff[kMaxViews];
   const float* x[kMaxViews];
+  float* xx;                // [V][n_rows] squared norms of the rows (computed once per upload)
 
   int32_t* table_cur;
   int32_t* choice;
@@ -112,6 +113,7 @@ cudaError_t launch_stats(const Ctx& c, cudaStream_t s);
 cudaError_t launch_reduce(const Ctx& c, cudaStream_t s);
 cudaError_t launch_finalize(const Ctx& c, int32_t flags, cudaStream_t s);
 cudaError_t launch_init_tables(const Ctx& c, int32_t mode, cudaStream_t s);
+cudaError_t launch_rownorms(const float* x, float* xx, int n, int D, cudaStream_t s);
 cudaError_t launch_f64_to_f32(const double* src, float* dst, int64_t n, cudaStream_t s);
 int stats_smem_bytes(const Ctx& c);
 

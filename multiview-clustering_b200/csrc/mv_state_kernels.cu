@@ -121,18 +121,19 @@ cudaError_t launch_pack(const Ctx& c, cudaStream_t s) {
 // =============================================================================================
 // k_stats
 // =============================================================================================
-// Segmented reduction of the rows into per-TABLE statistics, HBM-bound by design: one CTA per SM walks a
-// fixed range of 32-row chunks.  Its warps form R row groups x G column groups: a warp owns 32 of the
-// concatenated feature columns (lane = column, so a row is one coalesced 128-byte load) and, for the rows
-// of its row group, adds them into a private [cap][32] block of sums and of squares in shared memory —
+// Segmented reduction of the rows into per-TABLE statistics: one CTA per SM walks a fixed range of 32-row
+// chunks.  Its warps form R row groups x G column groups: a warp owns 32 of the concatenated feature
+// columns (lane = column, so a row is one coalesced 128-byte load; the squared norms of the rows, computed
+// once when a view is uploaded, are V more columns) and, for the rows of its row group, adds them into a
+// private [cap][32] block of sums in shared memory —
 // no two warps ever touch the same cell, rows are added in ascending order, the row groups are summed in
 // ascending order: a fixed tree, bit-reproducible for a given launch shape.  Loads run a batch of rows
 // ahead of their use.
 struct StatsPlan { int Gp, R, passes, smem; };
 
 static StatsPlan stats_plan(const Ctx& c) {
-  const int Gtot = (c.Dsum + 31) / 32;
-  const int slot_bytes = 2 * c.cap * 32 * (int)sizeof(float);            // sums + squares of one (row group, column group)
+  const int Gtot = (c.Dsum + c.V + 31) / 32;         // feature columns, then one column of squared norms per view
+  const int slot_bytes = c.cap * 32 * (int)sizeof(float);                // sums of one (row group, column group)
   const int slots = (200 * 1024) / slot_bytes;
   StatsPlan pl;
   int gmax = slots / 2 > 1 ? slots / 2 : 1;          // leave room for at least two row groups
@@ -140,7 +141,7 @@ static StatsPlan stats_plan(const Ctx& c) {
   pl.Gp = Gtot < gmax ? Gtot : gmax;
   int R = slots / pl.Gp;
   if (R > 8) R = 8;
-  if (R * pl.Gp > 16) R = 16 / pl.Gp;                  // at most 16 warps: 128 registers each
+  if (R * pl.Gp > 24) R = 24 / pl.Gp;                  // at most 24 warps: 80 registers each
   if (R < 1) R = 1;
   pl.R = R;
   pl.passes = (Gtot + pl.Gp - 1) / pl.Gp;
@@ -149,20 +150,18 @@ static StatsPlan stats_plan(const Ctx& c) {
 }
 int stats_smem_bytes(const Ctx& c) { return stats_plan(c).smem; }
 
-constexpr int kStatBatch = 16;   // rows whose loads are in flight per warp while the previous batch is accumulated
+constexpr int kStatBatch = 8;    // rows whose loads are in flight per warp while the previous batch is accumulated
 constexpr int kStatAhead = 4;    // chunks (of 32 rows) the L2 prefetch runs ahead of the loads
 
-__global__ void __launch_bounds__(512, 1) k_stats(const Ctx c, const int Gp, const int R, const int passes) {
+__global__ void __launch_bounds__(768, 1) k_stats(const Ctx c, const int Gp, const int R, const int passes) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int cap = c.cap;
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
   const int nthreads = blockDim.x;
   const int rg = wid / Gp, cg = wid - rg * Gp;
   float* s_sum = reinterpret_cast<float*>(smem_raw);                            // [R][Gp][cap][32]
-  float* s_sq = s_sum + (size_t)R * Gp * cap * 32;                              // [R][Gp][cap][32]
-  int32_t* s_cnt = reinterpret_cast<int32_t*>(s_sq + (size_t)R * Gp * cap * 32);   // [R][cap]
+  int32_t* s_cnt = reinterpret_cast<int32_t*>(s_sum + (size_t)R * Gp * cap * 32);  // [R][cap]
   float* acc = s_sum + ((size_t)rg * Gp + cg) * cap * 32;
-  float* accq = s_sq + ((size_t)rg * Gp + cg) * cap * 32;
   int32_t* cntw = s_cnt + rg * cap;
 
   // fixed mapping rows -> CTA -> row group, in whole 32-row chunks
@@ -181,13 +180,15 @@ __global__ void __launch_bounds__(512, 1) k_stats(const Ctx c, const int Gp, con
 
   for (int pass = 0; pass < passes; ++pass) {
     // this lane's column of the concatenated views
+    // (columns Dsum .. Dsum+V-1 are the precomputed squared norms of the rows, one array per view)
     const int col = (pass * Gp + cg) * 32 + lane;
-    const bool has = col < c.Dsum;
+    const bool has = col < c.Dsum + c.V;
     int v = 0;
     while (v + 1 < c.V && col >= c.doff[v + 1]) ++v;
-    const int D = c.D[v];
-    const float* __restrict__ base = c.x[v] + (has ? (col - c.doff[v]) : 0);
-    for (int i = lane; i < cap * 32; i += 32) { acc[i] = 0.0f; accq[i] = 0.0f; }
+    const bool is_norm = col >= c.Dsum;
+    const int D = is_norm ? 1 : c.D[v];
+    const float* __restrict__ base = !has ? c.x[0] : (is_norm ? c.xx + (size_t)(col - c.Dsum) * c.n_rows : c.x[v] + (col - c.doff[v]));
+    for (int i = lane; i < cap * 32; i += 32) acc[i] = 0.0f;
     if (pass == 0 && cg == 0) for (int i = lane; i < cap; i += 32) cntw[i] = 0;
     __syncwarp();
     const bool owner = (pass == 0 && cg == 0);      // the warp that records the resolved assignment of its rows
@@ -247,10 +248,7 @@ __global__ void __launch_bounds__(512, 1) k_stats(const Ctx c, const int Gp, con
           const int t = ts[u];
           if (t < 0) continue;                        // warp-uniform
           float* a = acc + t * 32 + lane;
-          float* q = accq + t * 32 + lane;
-          const float av = *a, qv = *q;               // both loads before either store: one round trip per row
-          *a = __fadd_rn(av, xs[u]);
-          *q = __fmaf_rn(xs[u], xs[u], qv);
+          *a = __fadd_rn(*a, xs[u]);
         }
       }
     }
@@ -269,18 +267,14 @@ __global__ void __launch_bounds__(512, 1) k_stats(const Ctx c, const int Gp, con
         part[(size_t)cap * c.doff[vv] + (size_t)t * c.D[vv] + (gcol - c.doff[vv])] = sum;
       }
     }
-    for (int i = tid; i < c.V * cap; i += nthreads) {
+    for (int i = tid; i < c.V * cap; i += nthreads) {       // sums of squared norms: the column Dsum + vv
       const int vv = i / cap, t = i - vv * cap;
-      // columns of view vv that this pass covered, ascending; row groups innermost
-      const int lo = max(c.doff[vv], pass * ncols_pass), hi = min(c.doff[vv] + c.D[vv], (pass + 1) * ncols_pass);
-      float sum = 0.0f;
-      for (int gcol = lo; gcol < hi; ++gcol) {
-        const int cc = gcol - pass * ncols_pass, g = cc >> 5, l = cc & 31;
-        for (int r = 0; r < R; ++r) sum = __fadd_rn(sum, s_sq[(((size_t)r * Gp + g) * cap + t) * 32 + l]);
-      }
-      if (lo < hi || pass == 0) {
-        const bool first = (pass * ncols_pass <= c.doff[vv]);
-        part_s2[i] = first ? sum : __fadd_rn(part_s2[i], sum);
+      const int cc = c.Dsum + vv - pass * ncols_pass;
+      if (cc >= 0 && cc < ncols_pass) {
+        const int g = cc >> 5, l = cc & 31;
+        float sum = 0.0f;
+        for (int r = 0; r < R; ++r) sum = __fadd_rn(sum, s_sum[(((size_t)r * Gp + g) * cap + t) * 32 + l]);
+        part_s2[i] = sum;
       }
     }
     if (pass == 0)
@@ -684,6 +678,11 @@ __global__ void __launch_bounds__(kFinThreads, 1) k_finalize(const Ctx c, const 
     c.dish_of[i] = S.dish[v][k];                             // (index reuse: i = v*cap + slot)
   }
   for (int t = tid; t < cap; t += kFinThreads) c.n_t[t] = S.n_new[t];
+  if (tid == 0) {                                              // every customer must have been counted exactly once
+    long long tot = 0;
+    for (int t = 0; t < cap; ++t) tot += S.n_new[t];
+    if (tot != (long long)c.n_global) S.err |= 4;
+  }
   __syncthreads();
   for (int i = tid; i < V * cap; i += kFinThreads) {          // which tables serve dish (v, k)
     const int v = i / cap, k = i - v * cap;
@@ -1027,6 +1026,22 @@ cudaError_t launch_init_tables(const Ctx& c, int32_t mode, cudaStream_t s) {
   if (c.V * c.cap > n) n = c.V * c.cap;
   if (c.n_chunks > n) n = c.n_chunks;
   k_init_tables<<<(n + 255) / 256, 256, 0, s>>>(c, mode);
+  return cudaGetLastError();
+}
+
+// Squared norms of the rows of one view, xx[i] = sum_d x[i][d]^2 as one ascending fmaf chain (the order
+// the CUDA-core draw kernel and the CPU mirror use).  The data never change, so this runs once per upload.
+__global__ void k_rownorms(const float* __restrict__ x, float* __restrict__ xx, int n, int D) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const float* r = x + (size_t)i * D;
+  float q = 0.0f;
+  for (int d = 0; d < D; ++d) q = __fmaf_rn(r[d], r[d], q);
+  xx[i] = q;
+}
+cudaError_t launch_rownorms(const float* x, float* xx, int n, int D, cudaStream_t s) {
+  if (n <= 0) return cudaSuccess;
+  k_rownorms<<<(n + 255) / 256, 256, 0, s>>>(x, xx, n, D);
   return cudaGetLastError();
 }
 
