@@ -121,7 +121,7 @@ int ensure_layout(mvg_handle* h) {
   const size_t N = (size_t)c.n_rows, cap = (size_t)c.cap, V = (size_t)c.V;
   int rc;
 #define A(ptr, count) if ((rc = dev_alloc(h, &(ptr), (count))) != MVG_OK) return rc
-  A(c.table_cur, N); A(c.choice, N); A(c.birthmask, (size_t)c.n_chunks); A(c.chunk_prefix, (size_t)c.n_chunks);
+  A(c.table_cur, N); A(c.choice, N + 4 /* bulk copies read whole 16-byte groups */); A(c.birthmask, (size_t)c.n_chunks); A(c.chunk_prefix, (size_t)c.n_chunks);
   A(c.n_t, cap); A(c.dish_of, V * cap); A(c.n_vk, V * cap); A(c.l_vk, V * cap);
   A(c.S1t, cap * dsum); A(c.S2t, V * cap); A(c.S1k, cap * dsum); A(c.S2k, V * cap);
   A(c.hyp, 3 * V + 2); A(c.sweep, 1); A(c.status, 4);
@@ -257,7 +257,8 @@ int mvg_create(const mvg_config* cfg, mvg_handle** out) {
   c.debug_export = cfg->debug_export;
   {
     void* q = nullptr;
-    if (cudaMalloc(&q, sizeof(float) * (size_t)c.n_rows * c.V) != cudaSuccess) {
+    c.xx_stride = ((int64_t)c.n_rows + 3) & ~(int64_t)3;        // rows of xx start 16-byte aligned (bulk copies)
+    if (cudaMalloc(&q, sizeof(float) * (size_t)c.xx_stride * c.V) != cudaSuccess) {
       mvg_destroy(h);
       return fail(nullptr, MVG_ENOMEM, "cudaMalloc: squared norms");
     }
@@ -304,7 +305,7 @@ int mvg_upload_view_f32(mvg_handle* h, int32_t v, const float* x_host, int32_t d
   MVG_CUDA(h, cudaMemcpyAsync(h->view_owned[v], x_host, bytes, cudaMemcpyHostToDevice, h->stream));
   h->c.x[v] = static_cast<const float*>(h->view_owned[v]);
   h->c.D[v] = dim;
-  MVG_CUDA(h, launch_rownorms(h->c.x[v], h->c.xx + (size_t)v * h->c.n_rows, h->c.n_rows, dim, h->stream));
+  MVG_CUDA(h, launch_rownorms(h->c.x[v], h->c.xx + (size_t)v * h->c.xx_stride, h->c.n_rows, dim, h->stream));
   h->launches += 1;
   return MVG_OK;
 }
@@ -329,7 +330,7 @@ int mvg_upload_view_f64(mvg_handle* h, int32_t v, const double* y_host, int32_t 
   h->launches += 1;
   h->c.x[v] = static_cast<const float*>(h->view_owned[v]);
   h->c.D[v] = dim;
-  MVG_CUDA(h, launch_rownorms(h->c.x[v], h->c.xx + (size_t)v * h->c.n_rows, h->c.n_rows, dim, h->stream));
+  MVG_CUDA(h, launch_rownorms(h->c.x[v], h->c.xx + (size_t)v * h->c.xx_stride, h->c.n_rows, dim, h->stream));
   h->launches += 1;
   return MVG_OK;
 }
@@ -341,7 +342,7 @@ int mvg_attach_view_device_f32(mvg_handle* h, int32_t v, const float* x_dev, int
   if (h->view_owned[v]) { cudaFree(h->view_owned[v]); h->view_owned[v] = nullptr; }
   h->c.x[v] = x_dev;
   h->c.D[v] = dim;
-  MVG_CUDA(h, launch_rownorms(x_dev, h->c.xx + (size_t)v * h->c.n_rows, h->c.n_rows, dim, h->stream));
+  MVG_CUDA(h, launch_rownorms(x_dev, h->c.xx + (size_t)v * h->c.xx_stride, h->c.n_rows, dim, h->stream));
   h->launches += 1;
   return MVG_OK;
 }

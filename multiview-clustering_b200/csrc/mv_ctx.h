@@ -48,7 +48,8 @@ struct Ctx {
   int32_t D[kMaxViews];
   int32_t doff[kMaxViews];
   const float* x[kMaxViews];
-  float* xx;                // [V][n_rows] squared norms of the rows (computed once per upload)
+  float* xx;                // [V][xx_stride] squared norms of the rows (computed once per upload)
+  int64_t xx_stride;        // n_rows rounded up to a multiple of 4
 
   int32_t* table_cur;
   int32_t* choice;
@@ -110,6 +111,8 @@ size_t draw_tc_maps_bytes();                                   // host blob hold
 cudaError_t draw_tc_make_maps(const Ctx& c, void* maps_out);  // (re)encode them for the current pointers
 cudaError_t launch_pack(const Ctx& c, cudaStream_t s);
 cudaError_t launch_stats(const Ctx& c, cudaStream_t s);
+bool stats_tile_supported(const Ctx& c);
+cudaError_t launch_stats_tile(const Ctx& c, cudaStream_t s);
 cudaError_t launch_reduce(const Ctx& c, cudaStream_t s);
 cudaError_t launch_finalize(const Ctx& c, int32_t flags, cudaStream_t s);
 cudaError_t launch_init_tables(const Ctx& c, int32_t mode, cudaStream_t s);

@@ -15,6 +15,8 @@
 //                              multiview_utils.cpp:209-289
 //   deaths                     remove_customer's empty-table branch, multiview_utils.cpp:168-191
 //   hyper step                 update_hyperparameters and helpers, multiview_hyper.cpp:53-128,166-360
+#include <stdlib.h>
+
 #include "mv_ctx.h"
 
 namespace mv {
@@ -187,7 +189,7 @@ __global__ void __launch_bounds__(768, 1) k_stats(const Ctx c, const int Gp, con
     while (v + 1 < c.V && col >= c.doff[v + 1]) ++v;
     const bool is_norm = col >= c.Dsum;
     const int D = is_norm ? 1 : c.D[v];
-    const float* __restrict__ base = !has ? c.x[0] : (is_norm ? c.xx + (size_t)(col - c.Dsum) * c.n_rows : c.x[v] + (col - c.doff[v]));
+    const float* __restrict__ base = !has ? c.x[0] : (is_norm ? c.xx + (size_t)(col - c.Dsum) * c.xx_stride : c.x[v] + (col - c.doff[v]));
     for (int i = lane; i < cap * 32; i += 32) acc[i] = 0.0f;
     if (pass == 0 && cg == 0) for (int i = lane; i < cap; i += 32) cntw[i] = 0;
     __syncwarp();
@@ -288,6 +290,11 @@ __global__ void __launch_bounds__(768, 1) k_stats(const Ctx c, const int Gp, con
 }
 
 cudaError_t launch_stats(const Ctx& c, cudaStream_t s) {
+  // the C3 shape has a register-accumulating, bulk-copy fed kernel (mv_stats_tile.cu); MVG_STATS_GENERIC=1
+  // forces the general kernel below (used by the tests to check one against the other)
+  const char* fg = getenv("MVG_STATS_GENERIC");
+  const bool force_generic = fg && fg[0] == '1';
+  if (!force_generic && stats_tile_supported(c)) return launch_stats_tile(c, s);
   const StatsPlan pl = stats_plan(c);
   cudaError_t e = cudaFuncSetAttribute(k_stats, cudaFuncAttributeMaxDynamicSharedMemorySize, pl.smem);
   if (e != cudaSuccess) return e;

@@ -1,0 +1,229 @@
+// mv_stats_tile.cu — sufficient statistics for the C3 shape (cap = 64 table slots, every view dense with
+// dim 64, at most 3 views): a bulk-copy (TMA) fed streaming kernel with the sums held in REGISTERS.
+//
+// One persistent CTA per SM walks a contiguous range of 64-row tiles.
+//
+//   warp 16 (producer, one lane)   per tile: waits for a free stage of the 4-deep ring and issues cp.async.bulk
+//                                  copies: per view the 64 rows x 256 B of features (contiguous in the
+//                                  row-major view: no tensor map needed) and their precomputed squared norms,
+//                                  plus the sweep's raw draws of the tile's rows.
+//   warp 17 (resolver)             turns the raw draws into the table each row now sits at (births: seated
+//                                  candidate / overflow stays put, exactly as k_stats does), writes table_cur
+//                                  and leaves the resolved tables in the stage.  No global load in the common
+//                                  case, so it never stalls the ring.
+//   warps 0..15 (accumulators)     warp w owns tables 4w..4w+3 for the whole kernel: lane l keeps, per table
+//                                  and view, the sums of columns 2l, 2l+1 in two registers (24 + 4 registers
+//                                  per lane), lane v < V the sum of squared norms of view v.  Per tile a warp
+//                                  finds the rows of its tables with two ballots per table and adds them in
+//                                  ascending row order straight from shared memory: no read-modify-write on
+//                                  memory at all, every row is added by exactly one warp.
+//
+// Summation tree (fixed for a given launch shape, so the float sums are reproducible): rows ascending inside
+// a CTA per table, then k_reduce adds the CTAs in ascending order in FP64.  Counts are integers (popc of the
+// ballots) and exact.
+//
+// HBM traffic: the features once (N*V*256 B), 4 B of squared norm per (row, view), 4 B read + 4 B written of
+// assignment per row.  Replaces the rebuild loop of /root/reference/Multiview/multiview_gibbs.cpp:64-73 (and
+// the incremental updates of multiview_utils.cpp:151-163, 199-206) for this shape.
+#include "mv_ctx.h"
+
+namespace mv {
+
+namespace {
+
+constexpr int kTile = 64;                 // rows per stage
+constexpr int kStages = 4;
+constexpr int kAccWarps = 16;             // x 4 tables = cap 64
+constexpr int kTabPerWarp = 4;
+constexpr int kThreadsST = (kAccWarps + 2) * 32;
+constexpr int kMaxV = 3;
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "WAIT_LOOP:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+      "@p bra DONE;\n\t"
+      "bra WAIT_LOOP;\n\t"
+      "DONE:\n\t"
+      "}\n" ::"r"(bar), "r"(parity)
+      : "memory");
+}
+__device__ __forceinline__ void bulk_load(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(dst), "l"(src), "r"(bytes), "r"(bar)
+               : "memory");
+}
+
+template <int V>
+struct Stage {
+  float x[V][kTile][64];      // V x 16 KB, each filled by one bulk copy
+  float xx[kMaxV + 1][kTile]; // squared norms of the rows (row V.. unused), one bulk copy per view
+  int32_t raw[kTile];         // the sweep's raw draws (bulk copy)
+  int32_t tab[kTile];         // resolved table of each row; < 0: nothing to add
+};
+
+template <int V>
+__global__ void __launch_bounds__(kThreadsST, 1) k_stats_tile(const Ctx c) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  Stage<V>* st = reinterpret_cast<Stage<V>*>(smem_raw);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw + sizeof(Stage<V>) * kStages);   // full, ready, empty [kStages] each
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+
+  const int n_tiles = (c.n_rows + kTile - 1) / kTile;
+  const int per_cta = (n_tiles + gridDim.x - 1) / gridDim.x;
+  const int t_lo = min((int)blockIdx.x * per_cta, n_tiles);
+  const int t_hi = min(t_lo + per_cta, n_tiles);
+
+  if (tid == 0) {
+    for (int s = 0; s < kStages; ++s) {
+      mbar_init(smem_u32(&bars[s]), 1);                      // full: the producer's expect_tx arrive + the bytes
+      mbar_init(smem_u32(&bars[kStages + s]), 32);           // ready: the 32 resolver lanes
+      mbar_init(smem_u32(&bars[2 * kStages + s]), kAccWarps);// empty: one lane of every accumulator warp
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+
+  if (wid == kAccWarps) {
+    // ---------------- producer: one lane keeps the ring full ----------------
+    if (lane == 0) {
+      for (int tile = t_lo, k = 0; tile < t_hi; ++tile, ++k) {
+        const int s = k % kStages;
+        const uint32_t full = smem_u32(&bars[s]);
+        if (k >= kStages) mbar_wait(smem_u32(&bars[2 * kStages + s]), ((k / kStages) - 1) & 1);
+        const int row0 = tile * kTile;
+        const int valid = min(kTile, c.n_rows - row0);
+        const uint32_t small = (uint32_t)((valid + 3) & ~3) * 4u;       // whole 16-byte groups (arrays are padded)
+        mbar_expect_tx(full, (uint32_t)(V * valid * 256) + (uint32_t)(V + 1) * small);
+        bulk_load(smem_u32(&st[s].raw[0]), c.choice + row0, small, full);
+#pragma unroll
+        for (int v = 0; v < V; ++v) {
+          bulk_load(smem_u32(&st[s].xx[v][0]), c.xx + (size_t)v * c.xx_stride + row0, small, full);
+          bulk_load(smem_u32(&st[s].x[v][0][0]), c.x[v] + (size_t)row0 * 64, (uint32_t)(valid * 256), full);
+        }
+      }
+    }
+  } else if (wid == kAccWarps + 1) {
+    // ---------------- resolver: raw draws -> the table each row now sits at ----------------
+    const int nfree = c.gparam->nfree;
+    for (int tile = t_lo, k = 0; tile < t_hi; ++tile, ++k) {
+      const int s = k % kStages;
+      mbar_wait(smem_u32(&bars[s]), (k / kStages) & 1);
+      const int row0 = tile * kTile;
+#pragma unroll
+      for (int hf = 0; hf < 2; ++hf) {
+        const int r = hf * 32 + lane, row = row0 + r;
+        int t = -3;
+        if (row < c.n_rows) {
+          t = st[s].raw[r];
+          if (t == kNewTable) {                            // a birth: seated (candidate, -2) or overflow (stays put)
+            const int ch = row >> 5;                       // row0 is a multiple of 64: a chunk is one half of the tile
+            const unsigned m = c.birthmask[ch];
+            const int rank = c.chunk_prefix[ch] + __popc(m & ((1u << lane) - 1u));
+            t = (rank < nfree) ? -2 : c.table_cur[row];
+            c.choice[row] = t;
+          }
+          if (t >= 0) c.table_cur[row] = t;
+        }
+        st[s].tab[r] = t;
+      }
+      mbar_arrive(smem_u32(&bars[kStages + s]));
+    }
+  } else {
+    // ---------------- accumulators ----------------
+    float2 acc[kTabPerWarp][V];
+    float s2[kTabPerWarp];
+    int cnt[kTabPerWarp];
+#pragma unroll
+    for (int j = 0; j < kTabPerWarp; ++j) {
+      s2[j] = 0.0f;
+      cnt[j] = 0;
+#pragma unroll
+      for (int v = 0; v < V; ++v) acc[j][v] = make_float2(0.0f, 0.0f);
+    }
+    const int tbase = wid * kTabPerWarp;
+    for (int tile = t_lo, k = 0; tile < t_hi; ++tile, ++k) {
+      const int s = k % kStages;
+      mbar_wait(smem_u32(&bars[s]), (k / kStages) & 1);              // features and squared norms have landed
+      mbar_wait(smem_u32(&bars[kStages + s]), (k / kStages) & 1);    // and the rows' tables are resolved
+      const Stage<V>& S = st[s];
+      const int ta = S.tab[lane], tb = S.tab[32 + lane];
+#pragma unroll
+      for (int j = 0; j < kTabPerWarp; ++j) {
+        unsigned ma = __ballot_sync(0xffffffffu, ta == tbase + j);
+        unsigned mb = __ballot_sync(0xffffffffu, tb == tbase + j);
+        cnt[j] += __popc(ma) + __popc(mb);
+#pragma unroll
+        for (int hf = 0; hf < 2; ++hf) {
+          unsigned m = hf ? mb : ma;
+          while (m) {
+            const int r = hf * 32 + __ffs(m) - 1;
+            m &= m - 1;
+#pragma unroll
+            for (int v = 0; v < V; ++v) {
+              const float2 xv = *reinterpret_cast<const float2*>(&S.x[v][r][2 * lane]);
+              acc[j][v].x = __fadd_rn(acc[j][v].x, xv.x);
+              acc[j][v].y = __fadd_rn(acc[j][v].y, xv.y);
+            }
+            s2[j] = __fadd_rn(s2[j], S.xx[lane & 3][r]);      // lane v < V keeps view v's sum; the others are ignored
+          }
+        }
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(smem_u32(&bars[2 * kStages + s]));
+    }
+    // this CTA's partials, in the layout k_reduce expects
+    const size_t part_stride = (size_t)64 * c.Dsum + (size_t)V * 64;
+    float* part = c.partial_f + (size_t)blockIdx.x * part_stride;
+    float* part_s2 = part + (size_t)64 * c.Dsum;
+#pragma unroll
+    for (int j = 0; j < kTabPerWarp; ++j) {
+      const int t = tbase + j;
+#pragma unroll
+      for (int v = 0; v < V; ++v)
+        *reinterpret_cast<float2*>(part + (size_t)64 * (64 * v) + (size_t)t * 64 + 2 * lane) = acc[j][v];
+      if (lane < V) part_s2[lane * 64 + t] = s2[j];
+      if (lane == 0) c.partial_n[(size_t)blockIdx.x * 64 + t] = cnt[j];
+    }
+  }
+}
+
+template <int V>
+cudaError_t launch_v(const Ctx& c, cudaStream_t s) {
+  const int smem = (int)sizeof(Stage<V>) * kStages + 3 * kStages * 8;
+  cudaError_t e = cudaFuncSetAttribute(k_stats_tile<V>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+  if (e != cudaSuccess) return e;
+  k_stats_tile<V><<<c.stat_ctas, kThreadsST, smem, s>>>(c);
+  return cudaGetLastError();
+}
+
+}  // namespace
+
+bool stats_tile_supported(const Ctx& c) {
+  if (c.cap != 64 || c.V < 1 || c.V > kMaxV) return false;
+  for (int v = 0; v < c.V; ++v)
+    if (c.D[v] != 64 || (reinterpret_cast<uintptr_t>(c.x[v]) & 15) != 0) return false;
+  return true;
+}
+
+cudaError_t launch_stats_tile(const Ctx& c, cudaStream_t s) {
+  switch (c.V) {
+    case 1: return launch_v<1>(c, s);
+    case 2: return launch_v<2>(c, s);
+    default: return launch_v<3>(c, s);
+  }
+}
+
+}  // namespace mv

@@ -255,3 +255,36 @@ def test_tcgen05_engine_parity(oracle, n, k_true, engine):
             assert np.max(np.abs(acc[:, v, :] - ref) / (bound + 1e-30)) < 2.0 ** -18     # measured 1.9e-6: the tensor core truncates when it aligns addends
             np.testing.assert_allclose(xx[:, v], (x64 * x64).sum(1), rtol=1e-6)
     s.close()
+
+
+def test_tile_statistics_match_general_kernel(oracle, monkeypatch):
+    """The register-accumulating statistics kernel of the C3 shape (mv_stats_tile.cu) against the general
+    kernel (MVG_STATS_GENERIC=1) and the FP64 oracle: counts and assignments bit-exact, sums within 1e-5.
+    Sizes: a partial last tile, fewer tiles than CTAs, and many tiles per CTA."""
+    dims, cap = [64, 64, 64], 64
+    for n, k_true in [(77, 5), (64 * 148 * 3 + 19, 50)]:
+        views, z = make_mixture(n, dims, k_true, seed=4)
+        rng = np.random.default_rng(9)
+        tab = np.where(rng.random(n) < 0.2, rng.integers(0, k_true, n), z).astype(np.int32)
+        dish = np.full((3, cap), -1, np.int32)
+        dish[:, :k_true] = np.arange(k_true)
+        out = []
+        for generic in ("1", "0"):
+            monkeypatch.setenv("MVG_STATS_GENERIC", generic)
+            s = _mk_sampler(views, cap, seed=31, engine=1, debug=False)
+            s.set_state(tab, dish, np.full(3, 1.0), np.full(3, 0.5), np.full(3, 0.9), 1.0, 0.6)
+            s.sweep(2, do_hyper=False)
+            out.append(s.get_state())
+            s.close()
+        g, t = out
+        for k in ("table_of", "n_t", "dish_of", "n_vk", "l_vk"):
+            np.testing.assert_array_equal(g[k], t[k], err_msg=k)
+        for v in range(3):
+            np.testing.assert_allclose(t["S1"][v], g["S1"][v], rtol=RTOL_STATS, atol=1e-4)
+        np.testing.assert_allclose(t["sum_y2"], g["sum_y2"], rtol=RTOL_STATS, atol=1e-4)
+        o = oracle.OracleState(views, cap, seed=31)
+        o.set_assignment(t["table_of"], t["dish_of"])
+        np.testing.assert_array_equal(t["n_vk"], o.n_vk)
+        for v in range(3):
+            np.testing.assert_allclose(t["S1"][v], o.S1[v], rtol=RTOL_STATS, atol=1e-4)
+        np.testing.assert_allclose(t["sum_y2"], o.S2, rtol=RTOL_STATS, atol=1e-4)
