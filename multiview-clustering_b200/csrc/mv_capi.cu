@@ -640,6 +640,15 @@ int mvg_profile_sweep(mvg_handle* h, int32_t do_hyper, float ms_out[6]) {
     cudaEventElapsedTime(&ms_out[3], marks[0], marks[1]);
     cudaEventElapsedTime(&ms_out[5], marks[1], marks[2]);
     cudaEventElapsedTime(&ms_out[4], marks[2], marks[3]);
+    if (getenv("MVG_FIN_TWICE")) {     // experiment: the same kernel again right away (flags 0: idempotent) = warm instruction cache
+      cudaEventRecord(marks[0], h->stream);
+      launch_finalize(h->c, 0, h->stream);
+      cudaEventRecord(marks[1], h->stream);
+      cudaStreamSynchronize(h->stream);
+      float warm = 0.f;
+      cudaEventElapsedTime(&warm, marks[0], marks[1]);
+      fprintf(stderr, "finalize cold %.4f ms (all flags), warm rerun %.4f ms (flags 0)\n", ms_out[4], warm);
+    }
   }
   for (auto& m : marks) cudaEventDestroy(m);
   return rc;

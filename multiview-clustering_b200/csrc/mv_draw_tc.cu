@@ -116,6 +116,20 @@ __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map
       ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(c0), "r"(c1)
       : "memory");
 }
+// Same with an L2 cache policy: the feature stream (768 MB per sweep at C3) is marked evict-first so that it
+// does not push the resident working set (parameters, packets, the other kernels' code) out of the 126 MB L2.
+__device__ __forceinline__ void tma_load_2d_hint(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1,
+                                                 uint64_t policy) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1, {%3, %4}], [%2], %5;"
+      ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(c0), "r"(c1), "l"(policy)
+      : "memory");
+}
+__device__ __forceinline__ uint64_t l2_evict_first_policy() {
+  uint64_t p;
+  asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
+  return p;
+}
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
@@ -298,19 +312,21 @@ __global__ void __launch_bounds__(kThreads, 1) k_draw_tc(const Ctx c, const __gr
             tma_load_2d(sbase + SmemLayout::b_off + ((v * 2 + part) * 2 + h) * kBHalfBytes,
                         part ? &maps.mean_lo : &maps.mean_hi, b_full, h * kHalfCols, v * 64);
       Ring r(kRawStages);
+      const uint64_t stream_policy = l2_evict_first_policy();
       for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x)
         for (int v = 0; v < V; ++v)
 #pragma unroll 1
           for (int h = 0; h < 2; ++h) {
             mbar_wait_t(raw_empty(r.stage), r.phase ^ 1u, prof, w0);
             mbar_expect_tx(raw_full(r.stage), kHalfBytes);
-            tma_load_2d(sbase + SmemLayout::raw_off + r.stage * kHalfBytes, &maps.x[v], raw_full(r.stage),
-                        h * kHalfCols, tile * kTileRows);
+            tma_load_2d_hint(sbase + SmemLayout::raw_off + r.stage * kHalfBytes, &maps.x[v], raw_full(r.stage),
+                             h * kHalfCols, tile * kTileRows, stream_policy);
             {                                           // pull the same half of the CTA's next tile into L2 meanwhile
               const int tn = tile + gridDim.x;
               if (tn < n_tiles)
-                asm volatile("cp.async.bulk.prefetch.tensor.2d.L2.global [%0, {%1, %2}];"
-                             ::"l"(reinterpret_cast<uint64_t>(&maps.x[v])), "r"(h * kHalfCols), "r"(tn * kTileRows) : "memory");
+                asm volatile("cp.async.bulk.prefetch.tensor.2d.L2.global.L2::cache_hint [%0, {%1, %2}], %3;"
+                             ::"l"(reinterpret_cast<uint64_t>(&maps.x[v])), "r"(h * kHalfCols), "r"(tn * kTileRows),
+                               "l"(stream_policy) : "memory");
             }
             r.next();
           }

@@ -305,26 +305,42 @@ cudaError_t launch_stats(const Ctx& c, cudaStream_t s) {
 // =============================================================================================
 // k_reduce
 // =============================================================================================
+// 256 threads = 32 consecutive elements x 8 slices: slice j adds the partials of CTAs j, j+8, ... in ascending
+// order, then the 8 slice sums are added in ascending order — a fixed tree, with 8x the loads in flight of a
+// plain loop over the CTAs and 8x the blocks.
+constexpr int kRedSlices = 8;
+
 __global__ void __launch_bounds__(256) k_reduce(const Ctx c) {
+  __shared__ double s_part[kRedSlices][32];
+  __shared__ int s_cnt[kRedSlices][32];
   const int n_s1 = c.cap * c.Dsum, n_s2 = c.V * c.cap;
   const size_t part_stride = (size_t)n_s1 + n_s2;
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  const int e = threadIdx.x & 31, slice = threadIdx.x >> 5;
+  const int i = blockIdx.x * 32 + e;
+  double sum = 0.0;
+  int n = 0;
   if (i < n_s1 + n_s2) {
-    double sum = 0.0;
-    for (int b = 0; b < c.stat_ctas; ++b) sum += (double)c.partial_f[(size_t)b * part_stride + i];
-    if (i < n_s1) pkt_f64(c, c.rank, c.pkt.off_s1t)[i] = sum;
-    else pkt_f64(c, c.rank, c.pkt.off_s2t)[i - n_s1] = sum;
+    for (int b = slice; b < c.stat_ctas; b += kRedSlices) sum += (double)c.partial_f[(size_t)b * part_stride + i];
   } else if (i < n_s1 + n_s2 + c.cap) {
     const int t = i - n_s1 - n_s2;
-    int n = 0;
-    for (int b = 0; b < c.stat_ctas; ++b) n += c.partial_n[(size_t)b * c.cap + t];
-    pkt_i32(c, c.rank, c.pkt.off_cnt)[t] = n;
+    for (int b = slice; b < c.stat_ctas; b += kRedSlices) n += c.partial_n[(size_t)b * c.cap + t];
+  }
+  s_part[slice][e] = sum;
+  s_cnt[slice][e] = n;
+  __syncthreads();
+  if (slice == 0) {
+    sum = 0.0; n = 0;
+#pragma unroll
+    for (int j = 0; j < kRedSlices; ++j) { sum += s_part[j][e]; n += s_cnt[j][e]; }
+    if (i < n_s1) pkt_f64(c, c.rank, c.pkt.off_s1t)[i] = sum;
+    else if (i < n_s1 + n_s2) pkt_f64(c, c.rank, c.pkt.off_s2t)[i - n_s1] = sum;
+    else if (i < n_s1 + n_s2 + c.cap) pkt_i32(c, c.rank, c.pkt.off_cnt)[i - n_s1 - n_s2] = n;
   }
 }
 
 cudaError_t launch_reduce(const Ctx& c, cudaStream_t s) {
   const int total = c.cap * c.Dsum + c.V * c.cap + c.cap;
-  k_reduce<<<(total + 255) / 256, 256, 0, s>>>(c);
+  k_reduce<<<(total + 31) / 32, 256, 0, s>>>(c);
   return cudaGetLastError();
 }
 
@@ -349,16 +365,23 @@ struct FinShared {
   unsigned long long tmask[kMaxViews][kMaxCap];   // bit t: table t serves dish k of view v (after births and deaths)
   unsigned long long live[kMaxViews + 1];          // bit i: cluster i of level j has members (dishes: l_vk > 0; level V: n_t > 0)
   long long total[kMaxViews + 1];                  // items of level j (tables of view j; customers for level V)
+  double s2t[kMaxViews][kMaxCap];         // sums of squared norms per table (working copy of S2t)
+  double s2k[kMaxViews][kMaxCap];         //   and per dish
   double s1sq[kMaxViews][kMaxCap];        // |S1k|^2
   double sse[kMaxViews][kMaxCap];         // max(0, S2k - |S1k|^2 / n_k)     (multiview_hyper.cpp:191-193)
   double termA[2 * (kMaxViews + 1)][kMaxCap + 1];   // scratch of the batched EPPF evaluations
   double termB[2 * (kMaxViews + 1)][kMaxCap + 1];
+  double termC[2 * (kMaxViews + 1)][4];             // per set: lgamma(alpha + M), lgamma(alpha + 1), lgamma(1 - sigma)
   double eppf[2 * (kMaxViews + 1)];
   double wbuf[kMaxCap + 1];
   double result[4];
   double prop[kMaxViews + 1];
   double hyp[3 * kMaxViews + 2];
+  double rn[3 * kMaxViews + 2];           // the sweep's standard normals of the hyper step, by stream index
+  double lu[3 * kMaxViews + 2];           // log of its uniforms
 };
+
+constexpr int kFinSharedBytes = (int)((sizeof(FinShared) + 15) & ~(size_t)15);
 
 __device__ __noinline__ double dev_normal(const Ctx& c, uint32_t sweep, int idx) {
   const U4 r = stream_block(c.seed, c.chain, kDomHyperNormal, 0, sweep, (uint64_t)idx);
@@ -432,6 +455,15 @@ __device__ __noinline__ void eppf_batch(const Ctx& c, FinShared& S, const double
       S.termB[set][blk] = sb;
     }
   }
+  // the three per-set lgamma values, one thread each (the last warps: the first ones carry the units above)
+  for (int q = tid - (kFinThreads - 128); q >= 0 && q < 3 * nsets; q += kFinThreads) {
+    const int set = q / 3, which = q - 3 * set, j = set >> 1;
+    const double al = alpha[set], sg = sigma[set];
+    double val = 0.0;
+    if ((sg > kEps && sg < 1.0 - kEps) && al > -sg)
+      val = (which == 0) ? fin_lgamma(al + (double)S.total[j]) : ((which == 1) ? fin_lgamma(al + 1.0) : fin_lgamma(1.0 - sg));
+    S.termC[set][which] = val;
+  }
   __syncthreads();
   if (tid < nsets) {
     const int set = tid, j = set >> 1;
@@ -447,8 +479,8 @@ __device__ __noinline__ void eppf_batch(const Ctx& c, FinShared& S, const double
       double sa = 0.0, sb = 0.0;
       for (int w = 0; w < wps; ++w) { sa += S.termA[set][w]; sb += S.termB[set][w]; }
       logp = sa;
-      if (total > 1) logp -= fin_lgamma(al + (double)total) - fin_lgamma(al + 1.0);
-      logp += sb - (double)multi * fin_lgamma(1.0 - sg);
+      if (total > 1) logp -= S.termC[set][0] - S.termC[set][1];
+      logp += sb - (double)multi * S.termC[set][2];
     }
     S.eppf[set] = logp;
   }
@@ -487,11 +519,15 @@ __device__ __noinline__ double log_f_dish(const Ctx& c, const FinShared& S, int 
   return -0.5 * (double)D * fin_log(2.0 * kPi * var) - 0.5 * dist / var;
 }
 
-__global__ void __launch_bounds__(kFinThreads, 1) k_finalize(const Ctx c, const int32_t flags) {
+__global__ void __launch_bounds__(kFinThreads, 1) k_finalize(const Ctx c, const int32_t flags, const int32_t s1_in_smem) {
   extern __shared__ __align__(16) unsigned char fin_smem[];
   FinShared& S = *reinterpret_cast<FinShared*>(fin_smem);
+  // The per-table sums S1t [cap*Dsum] live in shared memory behind FinShared when they fit (96 KB at C3): the
+  // dish statistics and the posterior means are then built from on-chip data instead of global round trips.
+  double* const S1t = s1_in_smem ? reinterpret_cast<double*>(fin_smem + kFinSharedBytes) : c.S1t;
   const int tid = threadIdx.x;
   const int cap = c.cap, V = c.V;
+  const int cshift = (cap == 64) ? 6 : 5;          // cap is 32 or 64 (mvg_create)
   const uint32_t sweep = *c.sweep;
   double* alpha_v = S.hyp;
   double* sigma_v = S.hyp + V;
@@ -505,6 +541,14 @@ __global__ void __launch_bounds__(kFinThreads, 1) k_finalize(const Ctx c, const 
   auto stamp = [&](int k) { if (prof) pout[k] = clock64() - t_begin; };
   if (tid == 0) { S.err = 0; S.ncand_total = 0; S.nseat = 0; S.nfree = 0; }
   for (int i = tid; i < 3 * V + 2; i += kFinThreads) S.hyp[i] = c.hyp[i];
+  // The random numbers of the hyper step depend on nothing but (seed, sweep, index): the last warps draw them
+  // now, while the others wait on the packet loads below, instead of in the middle of the serial MH chain.
+  if ((flags & kFinHyper) && tid >= kFinThreads - 64) {
+    for (int i = tid - (kFinThreads - 64); i < 2 * (3 * V + 2); i += 64) {
+      if (i < 3 * V + 2) S.rn[i] = dev_normal(c, sweep, i);
+      else S.lu[i - (3 * V + 2)] = fin_log(dev_unif(c, sweep, i - (3 * V + 2)));
+    }
+  }
   // ---- A. rank-ordered sums of the shards' packets ------------------------------------------
   for (int t = tid; t < cap; t += kFinThreads) {
     int n = 0;
@@ -512,15 +556,38 @@ __global__ void __launch_bounds__(kFinThreads, 1) k_finalize(const Ctx c, const 
     S.n_new[t] = n;
     S.alive_start[t] = c.n_t[t] > 0;
   }
-  for (int i = tid; i < cap * c.Dsum; i += kFinThreads) {
-    double sum = 0.0;
-    for (int g = 0; g < c.world; ++g) sum += pkt_f64(c, g, c.pkt.off_s1t)[i];
-    c.S1t[i] = sum;
+  {
+    // S1t = sum over the shards in rank order.  Eight elements per thread are in flight at once: the loop is a
+    // chain of global-memory latencies otherwise.
+    constexpr int kB = 8;
+    const double* p0 = pkt_f64(c, 0, c.pkt.off_s1t);
+    const size_t gstride = (size_t)c.pkt.bytes / sizeof(double);     // packet sizes are multiples of 16 bytes
+    const int n_s1 = cap * c.Dsum;
+    for (int i0 = tid; i0 < n_s1; i0 += kB * kFinThreads) {
+      double sum[kB];
+#pragma unroll
+      for (int u = 0; u < kB; ++u) {
+        const int i = i0 + u * kFinThreads;
+        sum[u] = (i < n_s1) ? p0[i] : 0.0;
+      }
+      for (int g = 1; g < c.world; ++g) {
+#pragma unroll
+        for (int u = 0; u < kB; ++u) {
+          const int i = i0 + u * kFinThreads;
+          if (i < n_s1) sum[u] += p0[(size_t)g * gstride + i];
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < kB; ++u) {
+        const int i = i0 + u * kFinThreads;
+        if (i < n_s1) S1t[i] = sum[u];
+      }
+    }
   }
   for (int i = tid; i < V * cap; i += kFinThreads) {
     double sum = 0.0;
     for (int g = 0; g < c.world; ++g) sum += pkt_f64(c, g, c.pkt.off_s2t)[i];
-    c.S2t[i] = sum;
+    (&S.s2t[0][0])[(i / cap) * kMaxCap + (i % cap)] = sum;
     const int v = i / cap, t = i - v * cap;
     S.dish[v][t] = c.dish_of[i];
     S.l_live[v][t] = c.l_vk[i];
@@ -648,7 +715,7 @@ __global__ void __launch_bounds__(kFinThreads, 1) k_finalize(const Ctx c, const 
         const float* x = pkt_f32(c, S.cand_g[b], c.pkt.off_cand_x) + (size_t)S.cand_j[b] * c.Dsum + c.doff[v];
         double q = 0.0;
         for (int dd = 0; dd < c.D[v]; ++dd) q += (double)x[dd] * (double)x[dd];
-        c.S2t[v * cap + S.cand_final[b]] += q;
+        S.s2t[v][S.cand_final[b]] += q;
       }
     }
     for (int e = tid; e < c.Dsum; e += kFinThreads) {
@@ -657,7 +724,7 @@ __global__ void __launch_bounds__(kFinThreads, 1) k_finalize(const Ctx c, const 
       const int dd = e - c.doff[v];
       for (int b = 0; b < ncand; ++b) {
         const float xv = pkt_f32(c, S.cand_g[b], c.pkt.off_cand_x)[(size_t)S.cand_j[b] * c.Dsum + e];
-        c.S1t[(size_t)cap * c.doff[v] + (size_t)S.cand_final[b] * c.D[v] + dd] += (double)xv;
+        S1t[(size_t)cap * c.doff[v] + (size_t)S.cand_final[b] * c.D[v] + dd] += (double)xv;
       }
     }
     __syncthreads();
@@ -671,34 +738,34 @@ __global__ void __launch_bounds__(kFinThreads, 1) k_finalize(const Ctx c, const 
     else if (S.dish[v][t] < 0 || S.dish[v][t] >= cap) { S.err |= 2; S.dish[v][t] = 0; }
   }
   __syncthreads();
+  stamp(6);
   for (int i = tid; i < V * cap; i += kFinThreads) {
     const int v = i / cap, k = i - v * cap;
     int l = 0, n = 0;
     double s2 = 0.0;
+    unsigned long long m = 0ull;                                // which tables serve dish (v, k)
     for (int t = 0; t < cap; ++t)
-      if (S.dish[v][t] == k) { l += 1; n += S.n_new[t]; s2 += c.S2t[v * cap + t]; }
+      if (S.dish[v][t] == k) { l += 1; n += S.n_new[t]; s2 += S.s2t[v][t]; m |= 1ull << t; }
     S.l_live[v][k] = l;
     S.n_vk[v][k] = n;
+    S.s2k[v][k] = s2;
+    S.tmask[v][k] = m;
     c.S2k[i] = s2;
+    c.S2t[i] = S.s2t[v][k];                                 // (index reuse: i = v*cap + slot)
     c.l_vk[i] = l;
     c.n_vk[i] = n;
-    c.dish_of[i] = S.dish[v][k];                             // (index reuse: i = v*cap + slot)
+    c.dish_of[i] = S.dish[v][k];
   }
   for (int t = tid; t < cap; t += kFinThreads) c.n_t[t] = S.n_new[t];
-  if (tid == 0) {                                              // every customer must have been counted exactly once
+  if (tid == kFinThreads - 32) {                               // every customer must have been counted exactly once
     long long tot = 0;
     for (int t = 0; t < cap; ++t) tot += S.n_new[t];
-    if (tot != (long long)c.n_global) S.err |= 4;
+    if (tot != (long long)c.n_global) atomicOr(&S.err, 4);
   }
   __syncthreads();
-  for (int i = tid; i < V * cap; i += kFinThreads) {          // which tables serve dish (v, k)
-    const int v = i / cap, k = i - v * cap;
-    unsigned long long m = 0ull;
-    for (int t = 0; t < cap; ++t) if (S.dish[v][t] == k) m |= 1ull << t;
-    S.tmask[v][k] = m;
-  }
-  if (tid <= V) {                                              // live masks and item totals of the EPPF levels
-    const int j = tid;
+  stamp(7);
+  if (tid >= 64 && tid <= 64 + V) {                            // live masks and item totals of the EPPF levels
+    const int j = tid - 64;
     const int32_t* counts = (j < V) ? S.l_live[j] : S.n_new;
     unsigned long long m = 0ull;
     long long tot = 0;
@@ -706,53 +773,32 @@ __global__ void __launch_bounds__(kFinThreads, 1) k_finalize(const Ctx c, const 
     S.live[j] = m;
     S.total[j] = (j < V) ? tot : (long long)c.n_global;
   }
-  __syncthreads();
   {
     // one warp per dish (v, k): lanes stride over the coordinates; the tables serving the dish are added in
-    // ascending order (warp-uniform test), then |S1k|^2 by a fixed shuffle tree
+    // ascending order (warp-uniform loop), then |S1k|^2 by a fixed shuffle tree
     const int lane = tid & 31, wid = tid >> 5;
-    constexpr int kU = 4;                              // dishes in flight per warp: their loads overlap
-    for (int i0 = wid; i0 < V * cap; i0 += kU * (kFinThreads / 32)) {
-      double sa[kU], sb[kU];
-#pragma unroll
-      for (int u = 0; u < kU; ++u) {
-        const int i = i0 + u * (kFinThreads / 32);
-        sa[u] = 0.0; sb[u] = 0.0;
-        if (i >= V * cap) continue;
-        const int v = i / cap, k = i - v * cap;
-        const int D = c.D[v];
-        const double* S1t_v = c.S1t + (size_t)cap * c.doff[v];
-        for (unsigned long long m = S.tmask[v][k]; m; m &= m - 1ull) {   // tables of the dish, ascending
-          const int t = __ffsll((long long)m) - 1;   // (coordinates beyond 64 are handled by the strided pass below)
-          if (lane < D) sa[u] += S1t_v[(size_t)t * D + lane];
-          if (32 + lane < D) sb[u] += S1t_v[(size_t)t * D + 32 + lane];
-        }
+    for (int i = wid; i < V * cap; i += kFinThreads / 32) {
+      const int v = i >> cshift, k = i & (cap - 1);
+      const int D = c.D[v], base = cap * c.doff[v];
+      const double* S1t_v = S1t + base;
+      double* S1k_vk = c.S1k + base + k * D;
+      const unsigned long long mask = S.tmask[v][k];
+      const int t1 = __ffsll((long long)mask) - 1;             // usually the only table of the dish
+      const unsigned long long more = mask & (mask - 1ull);
+      double q = 0.0;
+      for (int dd = lane; dd < D; dd += 32) {
+        double sum = (t1 >= 0) ? S1t_v[t1 * D + dd] : 0.0;
+        for (unsigned long long m = more; m; m &= m - 1ull) sum += S1t_v[(__ffsll((long long)m) - 1) * D + dd];
+        S1k_vk[dd] = sum;
+        q += sum * sum;
       }
 #pragma unroll
-      for (int u = 0; u < kU; ++u) {
-        const int i = i0 + u * (kFinThreads / 32);
-        if (i >= V * cap) continue;
-        const int v = i / cap, k = i - v * cap;
-        const int D = c.D[v];
-        const double* S1t_v = c.S1t + (size_t)cap * c.doff[v];
-        double* S1k_vk = c.S1k + (size_t)cap * c.doff[v] + (size_t)k * D;
-        double q = 0.0;
-        if (lane < D) { S1k_vk[lane] = sa[u]; q += sa[u] * sa[u]; }
-        if (32 + lane < D) { S1k_vk[32 + lane] = sb[u]; q += sb[u] * sb[u]; }
-        for (int dd = 64 + lane; dd < D; dd += 32) {  // coordinates beyond 64: plain strided pass
-          double sum = 0.0;
-          for (unsigned long long m = S.tmask[v][k]; m; m &= m - 1ull) sum += S1t_v[(size_t)(__ffsll((long long)m) - 1) * D + dd];
-          S1k_vk[dd] = sum;
-          q += sum * sum;
-        }
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) q += __shfl_xor_sync(0xffffffffu, q, o);
-        if (lane == 0) {
-          S.s1sq[v][k] = q;
-          const int n_k = S.n_vk[v][k];
-          double sse = (n_k > 0) ? c.S2k[i] - q / (double)n_k : 0.0;
-          S.sse[v][k] = sse < 0.0 ? 0.0 : sse;
-        }
+      for (int o = 16; o > 0; o >>= 1) q += __shfl_xor_sync(0xffffffffu, q, o);
+      if (lane == 0) {
+        S.s1sq[v][k] = q;
+        const int n_k = S.n_vk[v][k];
+        double sse = (n_k > 0) ? S.s2k[v][k] - q / (double)n_k : 0.0;
+        S.sse[v][k] = sse < 0.0 ? 0.0 : sse;
       }
     }
   }
@@ -766,7 +812,7 @@ __global__ void __launch_bounds__(kFinThreads, 1) k_finalize(const Ctx c, const 
       // all customers sit at table 0 / dish 0 during this call: pooled variance over coordinates
       const double n = (double)c.n_global;
       double var = 1.0;
-      if (c.n_global > 1) var = (c.S2k[v * cap] - S.s1sq[v][0] / n) / ((n - 1.0) * (double)c.D[v]);
+      if (c.n_global > 1) var = (S.s2k[v][0] - S.s1sq[v][0] / n) / ((n - 1.0) * (double)c.D[v]);
       if (!(var > 0.0)) var = 1.0;
       tau_v[v] = var * 0.25 * 0.01;
       alpha_v[v] = 1.0;
@@ -787,7 +833,7 @@ __global__ void __launch_bounds__(kFinThreads, 1) k_finalize(const Ctx c, const 
       for (int v = wid; v < V; v += kFinThreads / 32) {
         double tau_old = tau_v[v];
         if (tau_old <= 0.0) tau_old = kEps;
-        const double tau_prop = fin_exp(fin_log(tau_old) + 0.0 + 0.3 * dev_normal(c, sweep, v));   // :166-174
+        const double tau_prop = fin_exp(fin_log(tau_old) + 0.0 + 0.3 * S.rn[v]);   // :166-174
         // log_posterior_given_tau (:176-209) at both values: lanes stride over the dishes, shuffle-tree sum
         const double lg_o = fin_log(2.0 * kPi * tau_old), lg_p = fin_log(2.0 * kPi * tau_prop);
         const double Dd = (double)c.D[v];
@@ -805,14 +851,16 @@ __global__ void __launch_bounds__(kFinThreads, 1) k_finalize(const Ctx c, const 
         }
         if (lane == 0) {
           const double a_tau = 2.0, b_tau = 1.0;                                    // :133-134
-          const double log_old = lo + (a_tau * fin_log(b_tau) - fin_lgamma(a_tau) - (a_tau + 1.0) * fin_log(tau_old) - b_tau / tau_old);
-          const double log_new = ln + (a_tau * fin_log(b_tau) - fin_lgamma(a_tau) - (a_tau + 1.0) * fin_log(tau_prop) - b_tau / tau_prop);
+          // a log(b) - lgamma(a) = 2 log 1 - lgamma 2 = 0 exactly
+          const double log_old = lo + (-(a_tau + 1.0) * fin_log(tau_old) - b_tau / tau_old);
+          const double log_new = ln + (-(a_tau + 1.0) * fin_log(tau_prop) - b_tau / tau_prop);
           const double log_acc = (log_new - log_old) + (fin_log(tau_prop) - fin_log(tau_old));
-          if (fin_log(dev_unif(c, sweep, v)) < log_acc) tau_v[v] = tau_prop;
+          if (S.lu[v] < log_acc) tau_v[v] = tau_prop;
         }
       }
     }
     __syncthreads();
+    stamp(9);
     __shared__ double s_alpha[2 * (kMaxViews + 1)], s_sigma[2 * (kMaxViews + 1)];
     // level j: its alpha/sigma slots in S.hyp and its Philox indices (alpha: base, sigma: base+1)
     const int j = tid;
@@ -824,28 +872,30 @@ __global__ void __launch_bounds__(kFinThreads, 1) k_finalize(const Ctx c, const 
     if (is_level) {
       a_old = S.hyp[ia];
       if (a_old <= 0.0) a_old = kEps;
-      const double cand = fin_exp(fin_log(a_old > kEps ? a_old : kEps) + 0.0 + 0.1 * dev_normal(c, sweep, base));   // :100-108
+      const double cand = fin_exp(fin_log(a_old > kEps ? a_old : kEps) + 0.0 + 0.1 * S.rn[base]);   // :100-108
       a_prop = cand > kEps ? cand : kEps;
       s_alpha[2 * j] = a_old; s_alpha[2 * j + 1] = a_prop;
       s_sigma[2 * j] = S.hyp[is]; s_sigma[2 * j + 1] = S.hyp[is];
     }
     eppf_batch(c, S, s_alpha, s_sigma);
+    stamp(11);
     double s_old = 0.0, s_prop = 0.0;
     if (is_level) {
       const double lo = S.eppf[2 * j] + log_prior_alpha(a_old), ln = S.eppf[2 * j + 1] + log_prior_alpha(a_prop);
       const double log_acc = (ln - lo) + (fin_log(a_prop) - fin_log(a_old));
-      if (fin_log(dev_unif(c, sweep, base)) < log_acc) S.hyp[ia] = a_prop;
+      if (S.lu[base] < log_acc) S.hyp[ia] = a_prop;
       // sigma: reflected random walk, :257-265 / :283-291
       s_old = S.hyp[is];
-      s_prop = reflect_unit(s_old + 0.0 + 0.05 * dev_normal(c, sweep, base + 1));                             // :124-128
+      s_prop = reflect_unit(s_old + 0.0 + 0.05 * S.rn[base + 1]);                             // :124-128
       s_alpha[2 * j] = S.hyp[ia]; s_alpha[2 * j + 1] = S.hyp[ia];
       s_sigma[2 * j] = s_old; s_sigma[2 * j + 1] = s_prop;
     }
     eppf_batch(c, S, s_alpha, s_sigma);
+    stamp(12);
     if (is_level) {
       const double lpo = (s_old <= kEps || s_old >= 1.0 - kEps) ? -INFINITY : S.eppf[2 * j] + log_prior_sigma(s_old);
       const double lpn = (s_prop <= kEps || s_prop >= 1.0 - kEps) ? -INFINITY : S.eppf[2 * j + 1] + log_prior_sigma(s_prop);
-      if (fin_log(dev_unif(c, sweep, base + 1)) < lpn - lpo) S.hyp[is] = s_prop;
+      if (S.lu[base + 1] < lpn - lpo) S.hyp[is] = s_prop;
     }
     __syncthreads();
   }
@@ -855,54 +905,41 @@ __global__ void __launch_bounds__(kFinThreads, 1) k_finalize(const Ctx c, const 
   // ---- E. FP32 parameter block of the next sweep (oracle/mv_oracle.c:mvo_make_params) ----------
   {
     // one warp per (view, table): lanes stride over the coordinates of the posterior mean m = S1k / (tau + n),
-    // write it (and its TF32 split) and reduce |m|^2 by a fixed shuffle tree; lane 0 forms the parameters
+    // S1k re-summed from the per-table sums (same order as above, so the same value), write it (and its TF32
+    // split) and reduce |m|^2 by a fixed shuffle tree
     const int lane = tid & 31, wid = tid >> 5;
-    constexpr int kU = 4;                              // tables in flight per warp: their loads overlap
-    for (int i0 = wid; i0 < V * cap; i0 += kU * (kFinThreads / 32)) {
-      double s1a[kU], s1b[kU];
-#pragma unroll
-      for (int u = 0; u < kU; ++u) {
-        const int i = i0 + u * (kFinThreads / 32);
-        s1a[u] = 0.0; s1b[u] = 0.0;
-        if (i >= V * cap) continue;
-        const int v = i / cap, t = i - v * cap;
-        const int D = c.D[v], k = S.dish[v][t];
-        if (k < 0) continue;
-        const double* S1 = c.S1k + (size_t)cap * c.doff[v] + (size_t)k * D;
-        if (lane < D) s1a[u] = S1[lane];
-        if (32 + lane < D) s1b[u] = S1[32 + lane];
-      }
-#pragma unroll
-      for (int u = 0; u < kU; ++u) {
-        const int i = i0 + u * (kFinThreads / 32);
-        if (i >= V * cap) continue;
-        const int v = i / cap, t = i - v * cap;
-        const int D = c.D[v], k = S.dish[v][t];
-        const size_t off = (size_t)cap * c.doff[v] + (size_t)t * D;
-        const double den = (k >= 0) ? tau_v[v] + (double)S.n_vk[v][k] : 1.0;
-        const double* S1 = c.S1k + (size_t)cap * c.doff[v] + (size_t)(k >= 0 ? k : 0) * D;
-        double mm = 0.0;
-        for (int dd = lane; dd < D; dd += 32) {
-          const double s1 = (dd == lane) ? s1a[u] : ((dd == 32 + lane) ? s1b[u] : S1[dd]);
-          const float m = (k >= 0) ? (float)(s1 / den) : 0.f;
-          c.mean[off + dd] = m;
-          if (c.mean_hi) {
-            uint32_t hb, lb;                                            // TF32 split, both parts rounded to nearest
-            asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(hb) : "f"(m));
-            const float hi = __uint_as_float(hb);
-            asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(lb) : "f"(__fadd_rn(m, -hi)));
-            c.mean_hi[off + dd] = hi;
-            c.mean_lo[off + dd] = __uint_as_float(lb);
-          }
-          mm += (double)m * (double)m;
+    for (int i = wid; i < V * cap; i += kFinThreads / 32) {
+      const int v = i >> cshift, t = i & (cap - 1);
+      const int D = c.D[v], k = S.dish[v][t], base = cap * c.doff[v];
+      const int off = base + t * D;
+      const double rden = (k >= 0) ? 1.0 / (tau_v[v] + (double)S.n_vk[v][k]) : 0.0;
+      const double* S1t_v = S1t + base;
+      const unsigned long long mask = (k >= 0) ? S.tmask[v][k] : 0ull;
+      const int t1 = __ffsll((long long)mask) - 1;
+      const unsigned long long more = mask & (mask - 1ull);
+      double mm = 0.0;
+      for (int dd = lane; dd < D; dd += 32) {
+        double s1 = (t1 >= 0) ? S1t_v[t1 * D + dd] : 0.0;
+        for (unsigned long long m = more; m; m &= m - 1ull) s1 += S1t_v[(__ffsll((long long)m) - 1) * D + dd];
+        const float m = (float)(s1 * rden);
+        c.mean[off + dd] = m;
+        if (c.mean_hi) {
+          uint32_t hb, lb;                                            // TF32 split, both parts rounded to nearest
+          asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(hb) : "f"(m));
+          const float hi = __uint_as_float(hb);
+          asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(lb) : "f"(__fadd_rn(m, -hi)));
+          c.mean_hi[off + dd] = hi;
+          c.mean_lo[off + dd] = __uint_as_float(lb);
         }
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) mm += __shfl_xor_sync(0xffffffffu, mm, o);
-        if (lane == 0) S.s1sq[v][t] = mm;               // (s1sq is free again: reused for |m_t|^2)
+        mm += (double)m * (double)m;
       }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) mm += __shfl_xor_sync(0xffffffffu, mm, o);
+      if (lane == 0) S.s1sq[v][t] = mm;               // (s1sq is free again: reused for |m_t|^2)
     }
   }
   __syncthreads();
+  stamp(10);
   for (int i = tid; i < V * cap; i += kFinThreads) {          // the scalar part, one thread per (view, table)
     const int v = i / cap, t = i - v * cap;
     const int D = c.D[v];
@@ -934,8 +971,10 @@ __global__ void __launch_bounds__(kFinThreads, 1) k_finalize(const Ctx c, const 
     }
     c.tparam[i] = q;
   }
-  if (tid < V) {
-    const int v = tid;
+  // The three small blocks below are independent of the loop above and of each other: each gets its own warps
+  // (12, 13-14, 15) so that their FP64 log chains run side by side instead of back to back on warp 0.
+  if (tid >= 12 * 32 && tid < 12 * 32 + V) {
+    const int v = tid - 12 * 32;
     const double tau = tau_v[v];
     int K_act = 0;
     long long sum_l = 0;
@@ -952,7 +991,7 @@ __global__ void __launch_bounds__(kFinThreads, 1) k_finalize(const Ctx c, const 
     p.pad0 = p.pad1 = 0.f;
     c.vparam[v] = p;
   }
-  for (int t = tid; t < cap; t += kFinThreads) {
+  for (int t = tid - 13 * 32; t >= 0 && t < cap; t += kFinThreads) {
     const double mass = (double)S.n_new[t] - sigma_g, mass1 = mass - 1.0;
     TableMass tm;
     tm.LM = (S.n_new[t] > 0 && mass > 0.0) ? (float)fin_log2(mass) : kMasked;
@@ -961,7 +1000,7 @@ __global__ void __launch_bounds__(kFinThreads, 1) k_finalize(const Ctx c, const 
     tm.pad = 0;
     c.tmass[t] = tm;
   }
-  if (tid == 0) {
+  if (tid == 15 * 32) {
     int T_ne = 0;
     for (int t = 0; t < cap; ++t) T_ne += S.n_new[t] > 0;
     const int F = cap - T_ne;
@@ -981,10 +1020,12 @@ __global__ void __launch_bounds__(kFinThreads, 1) k_finalize(const Ctx c, const 
 
 cudaError_t launch_finalize(const Ctx& c, int32_t flags, cudaStream_t s) {
   if (c.cap > kMaxCap || c.world > kMaxWorld || c.V > kMaxViews) return cudaErrorInvalidValue;
-  const int smem = (int)sizeof(FinShared);
+  const size_t s1_bytes = sizeof(double) * (size_t)c.cap * c.Dsum;
+  const int s1_in_smem = (kFinSharedBytes + s1_bytes <= (size_t)227 * 1024) ? 1 : 0;
+  const int smem = kFinSharedBytes + (s1_in_smem ? (int)s1_bytes : 0);
   cudaError_t e = cudaFuncSetAttribute(k_finalize, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
   if (e != cudaSuccess) return e;
-  k_finalize<<<1, kFinThreads, smem, s>>>(c, flags);
+  k_finalize<<<1, kFinThreads, smem, s>>>(c, flags, s1_in_smem);
   return cudaGetLastError();
 }
 

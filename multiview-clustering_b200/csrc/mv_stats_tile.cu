@@ -66,6 +66,13 @@ __device__ __forceinline__ void bulk_load(uint32_t dst, const void* src, uint32_
                : "memory");
 }
 
+// With an L2 evict-first policy: the feature stream must not push the resident working set out of L2.
+__device__ __forceinline__ void bulk_load_stream(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar, uint64_t policy) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;"
+               ::"r"(dst), "l"(src), "r"(bytes), "r"(bar), "l"(policy)
+               : "memory");
+}
+
 template <int V>
 struct Stage {
   float x[V][kTile][64];      // V x 16 KB, each filled by one bulk copy
@@ -99,6 +106,8 @@ __global__ void __launch_bounds__(kThreadsST, 1) k_stats_tile(const Ctx c) {
   if (wid == kAccWarps) {
     // ---------------- producer: one lane keeps the ring full ----------------
     if (lane == 0) {
+      uint64_t policy;
+      asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(policy));
       for (int tile = t_lo, k = 0; tile < t_hi; ++tile, ++k) {
         const int s = k % kStages;
         const uint32_t full = smem_u32(&bars[s]);
@@ -111,7 +120,7 @@ __global__ void __launch_bounds__(kThreadsST, 1) k_stats_tile(const Ctx c) {
 #pragma unroll
         for (int v = 0; v < V; ++v) {
           bulk_load(smem_u32(&st[s].xx[v][0]), c.xx + (size_t)v * c.xx_stride + row0, small, full);
-          bulk_load(smem_u32(&st[s].x[v][0][0]), c.x[v] + (size_t)row0 * 64, (uint32_t)(valid * 256), full);
+          bulk_load_stream(smem_u32(&st[s].x[v][0][0]), c.x[v] + (size_t)row0 * 64, (uint32_t)(valid * 256), full, policy);
         }
       }
     }
