@@ -6,9 +6,10 @@
 //   TMA producer (1 thread)    cp.async.bulk.tensor: the tile's [128 x 64] FP32 features arrive in
 //                              shared memory as two K-halves of [128 x 32] in the 128B-swizzled
 //                              K-major layout UMMA reads directly (4-deep ring plus an L2 prefetch of the tile-views behind it).
-//   converters (2 x 128 thr.)  one warpgroup per K-half; thread r owns customer r: partial |x|^2 and
-//                              the TF32 remainder x_lo = rn_tf32(x - trunc_tf32(x)), written with
-//                              tcgen05.st into TMEM lane r (the remainder tile never touches shared memory).
+//   converters (2 x 128 thr.)  one warpgroup per K-half; thread r owns customer r: the remainder
+//                              x_lo = x - trunc_tf32(x) (exact in FP32; two instructions per element), written
+//                              with tcgen05.st into TMEM lane r (the remainder tile never touches shared
+//                              memory).  |x|^2 is not recomputed here: it was stored when the view was uploaded.
 //   MMA issuer (1 thread)      tcgen05.mma kind::tf32, M=128 N=64 K=8, three passes accumulated in
 //                              one TMEM tile:  x.m_hi + x.m_lo (A = the raw tile in shared memory; the
 //                              hardware reads the top 19 bits of each FP32 word, so it serves as
@@ -44,7 +45,6 @@ constexpr int kBHalfBytes = 64 * 128;               // 8 KB: one K-half of a B m
 constexpr int kRawStages = 4;                       // K-halves of raw features in flight (64 KB) + L2 prefetch two tile-views ahead
 constexpr int kLoStages = 2;                        // TMEM remainder tiles (64 columns each)
 constexpr int kDStages = 6;                         // TMEM accumulator tiles (64 columns each): three per epilogue pair
-constexpr int kXxSlots = 8;                         // ring of per-row |x|^2 partials, >= kDStages + kLoStages (see the converter)
 constexpr int kTmemCols = 512;
 constexpr int kLoCol0 = kDStages * 64;              // first TMEM column of the remainder tiles
 constexpr int kMaxTcViews = 3;
@@ -67,10 +67,9 @@ struct SmemLayout {
   static constexpr int tm_off = tp_off + kMaxTcViews * 64 * (int)sizeof(TableParam);   // per view: PairHot[32] then TableCold[64]
   static constexpr int vp_off = tm_off + 64 * (int)sizeof(TableMass);
   static constexpr int lm_off = vp_off + kMaxTcViews * (int)sizeof(ViewParam);              // float[64]: LM of every table
-  static constexpr int xx_off = lm_off + 64 * (int)sizeof(float);
-  static constexpr int ex_off = xx_off + kXxSlots * 2 * kTileRows * (int)sizeof(float);    // xx: [slot][K-half][row]
+  static constexpr int ex_off = lm_off + 64 * (int)sizeof(float);
   static constexpr int bar_off = ex_off + 4 * kExFields * kTileRows * (int)sizeof(float);   // ex: [pair][half][field][row]
-  static constexpr int n_bars = 2 * kRawStages + 2 * kLoStages + 2 * kDStages + kXxSlots + 1;
+  static constexpr int n_bars = 2 * kRawStages + 2 * kLoStages + 2 * kDStages + 1;
   static constexpr int misc_off = bar_off + n_bars * 8;
   static constexpr int total = misc_off + 64;
 };
@@ -249,7 +248,6 @@ __global__ void __launch_bounds__(kThreads, 1) k_draw_tc(const Ctx c, const __gr
   TableMass* s_tm = reinterpret_cast<TableMass*>(smem + SmemLayout::tm_off);
   ViewParam* s_vp = reinterpret_cast<ViewParam*>(smem + SmemLayout::vp_off);
   float* s_lm = reinterpret_cast<float*>(smem + SmemLayout::lm_off);
-  float* s_xx = reinterpret_cast<float*>(smem + SmemLayout::xx_off);             // [stage][K-half][row]
   uint32_t* s_misc = reinterpret_cast<uint32_t*>(smem + SmemLayout::misc_off);   // [0] TMEM base, [1] sweep, [2..3] GlobalParam floats
 
   // barrier addresses
@@ -260,8 +258,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_draw_tc(const Ctx c, const __gr
   auto lo_empty = [&](int s) { return bar0 + 8u * (2 * kRawStages + kLoStages + s); };
   auto d_full = [&](int s) { return bar0 + 8u * (2 * kRawStages + 2 * kLoStages + s); };
   auto d_empty = [&](int s) { return bar0 + 8u * (2 * kRawStages + 2 * kLoStages + kDStages + s); };
-  auto xx_full = [&](int s) { return bar0 + 8u * (2 * kRawStages + 2 * kLoStages + 2 * kDStages + s); };
-  const uint32_t b_full = bar0 + 8u * (2 * kRawStages + 2 * kLoStages + 2 * kDStages + kXxSlots);
+  const uint32_t b_full = bar0 + 8u * (2 * kRawStages + 2 * kLoStages + 2 * kDStages);
 
   // ---- one-time setup --------------------------------------------------------------------------
   for (int v = 0; v < V; ++v)
@@ -277,7 +274,6 @@ __global__ void __launch_bounds__(kThreads, 1) k_draw_tc(const Ctx c, const __gr
     for (int s = 0; s < kRawStages; ++s) { mbar_init(raw_full(s), 1); mbar_init(raw_empty(s), 129); }   // one converter warpgroup + the MMA commit
     for (int s = 0; s < kLoStages; ++s) { mbar_init(lo_full(s), 256); mbar_init(lo_empty(s), 1); }      // both converter warpgroups
     for (int s = 0; s < kDStages; ++s) { mbar_init(d_full(s), 1); mbar_init(d_empty(s), 256); }   // both halves of a pair
-    for (int s = 0; s < kXxSlots; ++s) mbar_init(xx_full(s), 256);
     mbar_init(b_full, 1);
     fence_barrier_init();
   }
@@ -413,13 +409,11 @@ __global__ void __launch_bounds__(kThreads, 1) k_draw_tc(const Ctx c, const __gr
         const uint32_t rph = (uint32_t)((2 * i + h) / kRawStages) & 1u;
         const int ls = i % kLoStages;
         const uint32_t lph = (uint32_t)(i / kLoStages) & 1u;
-        const int xs = i % kXxSlots;
         mbar_wait_t(raw_full(rs), rph, prof, w0);
         mbar_wait_t(lo_empty(ls), lph ^ 1u, prof, w1);
         tc_fence_after();
         const unsigned char* src = smem + SmemLayout::raw_off + rs * kHalfBytes + line;
         const uint32_t lo_addr = tmem_base + lane_base + (uint32_t)(kLoCol0 + ls * 64 + h * 32);
-        float xx = 0.0f;
 #pragma unroll
         for (int half16 = 0; half16 < 2; ++half16) {
           uint32_t lo[16];
@@ -430,11 +424,9 @@ __global__ void __launch_bounds__(kThreads, 1) k_draw_tc(const Ctx c, const __gr
             const float xs[4] = {x4.x, x4.y, x4.z, x4.w};
 #pragma unroll
             for (int e = 0; e < 4; ++e) {
-              // the tensor core reads trunc_tf32(x); the remainder is exact in FP32 and is rounded to the
-              // nearest TF32 by adding half a TF32 ulp before the hardware drops the low 13 bits
-              const float rem = __fadd_rn(xs[e], -__uint_as_float(__float_as_uint(xs[e]) & 0xFFFFE000u));
-              lo[cc * 4 + e] = __float_as_uint(rem) + 0x1000u;
-              xx = __fmaf_rn(xs[e], xs[e], xx);
+              // the tensor core reads trunc_tf32(x); the remainder x - trunc_tf32(x) is exact in FP32 and the
+              // hardware again keeps its top 19 bits: x_hi + x_lo carries >= 21 significant bits of x
+              lo[cc * 4 + e] = __float_as_uint(__fadd_rn(xs[e], -__uint_as_float(__float_as_uint(xs[e]) & 0xFFFFE000u)));
             }
           }
           tmem_st_16(lo_addr + (uint32_t)(half16 * 16), lo);
@@ -443,12 +435,6 @@ __global__ void __launch_bounds__(kThreads, 1) k_draw_tc(const Ctx c, const __gr
         tmem_st_wait();
         tc_fence_before();
         mbar_arrive(lo_full(ls));
-        // Slot i % 8 was last read for tile-view i-8.  Reaching this point needed the remainder stage of
-        // tile-view i-2 to be free, hence its MMA issued, hence (the issuers acquire accumulator stages in
-        // tile-view order, six of them, V = 3) the accumulator of tile-view i-8 released — and an epilogue
-        // thread reads |x|^2 before it releases the accumulator.
-        s_xx[(xs * 2 + h) * kTileRows + r] = xx;
-        mbar_arrive(xx_full(xs));
       }
     if (prof && r == 0) { prof_out[6 + 3 * h] = w0; prof_out[7 + 3 * h] = w1; prof_out[8 + 3 * h] = clock64() - t_start; }
   } else {
@@ -468,26 +454,37 @@ __global__ void __launch_bounds__(kThreads, 1) k_draw_tc(const Ctx c, const __gr
     int j = pair;
     const int tile0 = blockIdx.x + pair * gridDim.x;
     int t0_next = (tile0 < n_tiles) ? c.table_cur[min(tile0 * kTileRows + r, c.n_rows - 1)] : 0;
+    // |x|^2 of the customer in every view: computed once when the view was uploaded (c.xx), fetched a tile ahead
+    float xx_next[kMaxTcViews];
+#pragma unroll
+    for (int v = 0; v < kMaxTcViews; ++v)
+      xx_next[v] = (tile0 < n_tiles) ? c.xx[(size_t)v * c.xx_stride + min(tile0 * kTileRows + r, c.n_rows - 1)] : 0.0f;
     for (int tile = tile0; tile < n_tiles; tile += kEpiGroups * gridDim.x, j += kEpiGroups) {
       const int row = tile * kTileRows + r;
       const bool live = row < c.n_rows;
       const int rowc = live ? row : (c.n_rows - 1);
       HalfEpilogue<32, FAST> epi;
       epi.begin(s_tm, s_lm, t0_next, 32 * hf);
-      {                                               // the next tile's tables travel while this one is computed
+      float xxv[kMaxTcViews];
+#pragma unroll
+      for (int v = 0; v < kMaxTcViews; ++v) xxv[v] = xx_next[v];
+      {                                               // the next tile's tables and norms travel while this one is computed
         const int tn = tile + kEpiGroups * gridDim.x;
-        if (tn < n_tiles) t0_next = c.table_cur[min(tn * kTileRows + r, c.n_rows - 1)];
+        if (tn < n_tiles) {
+          const int rn = min(tn * kTileRows + r, c.n_rows - 1);
+          t0_next = c.table_cur[rn];
+#pragma unroll
+          for (int v = 0; v < kMaxTcViews; ++v) xx_next[v] = c.xx[(size_t)v * c.xx_stride + rn];
+        }
       }
       float lnew = epi.single ? gp.LMN1 : gp.LMN0;
-      float xxv[kMaxTcViews];
       for (int v = 0; v < V; ++v) {
-        const int idx = j * V + v, xs = idx % kXxSlots;
+        const int idx = j * V + v;
         const int stage = idx % kDStages;             // V = 3: stages 0-2 serve this CTA's even tiles, 3-5 the odd ones
         mbar_wait_t(d_full(stage), (uint32_t)(idx / kDStages) & 1u, prof, w0);
-        mbar_wait_t(xx_full(xs), (uint32_t)(idx / kXxSlots) & 1u, prof, w1);
         tc_fence_after();
         const uint32_t taddr = tmem_base + lane_base + (uint32_t)(stage * 64 + 32 * hf);
-        const float xx = __fadd_rn(s_xx[(xs * 2 + 0) * kTileRows + r], s_xx[(xs * 2 + 1) * kTileRows + r]);
+        const float xx = (v == 0) ? xxv[0] : ((v == 1) ? xxv[1] : xxv[2]);
         const PairHot* hot = reinterpret_cast<const PairHot*>(s_tp + v * 2048);
         const TableCold* cold = reinterpret_cast<const TableCold*>(s_tp + v * 2048 + 1024);
         epi.view_begin(hot, cold, xx);
@@ -505,7 +502,6 @@ __global__ void __launch_bounds__(kThreads, 1) k_draw_tc(const Ctx c, const __gr
           epi_chunk<16, true>(epi, hot + 16 * hf, cold + 32 * hf, ub, c, row, v, 32 * hf, live);
           ex_own[(2 * v) * kTileRows] = epi.mx;
           ex_own[(2 * v + 1) * kTileRows] = epi.s;
-          if (v == 0) xxv[0] = xx; else if (v == 1) xxv[1] = xx; else xxv[2] = xx;
         } else {
           epi_chunk<16, false>(epi, hot + 16 * hf, cold + 32 * hf, ub, c, row, v, 32 * hf, live);
         }
