@@ -8,8 +8,10 @@ Workload (BASELINE.json configs[2], SURVEY.md §8d "C3"): synthetic 3-view Gauss
 N = 1M customers, D = 64 per view, cap K = 64 tables/dishes, FP32, seed 1999.  A "step" is ONE sweep
 of the hot path: likelihood + draw for every customer, birth/death bookkeeping, sufficient-statistics
 rebuild and the hyperparameter step.  metric = obs x view x K updates per second (whole job).
-With N GPUs the customers are row-sharded (total work fixed: strong scaling) and the per-table
-statistics are exchanged by one NCCL all-gather per sweep.
+With N GPUs the customers are row-sharded and the per-table statistics are exchanged by one NCCL
+all-gather per sweep.  Default scaling is "weak": every GPU holds one C3-sized shard (1M customers), so
+the chain has N x 1M customers and `value` counts the updates of all ranks; `--scaling strong` keeps the
+chain at 1M customers in total and splits it over the ranks instead.
 
 The timed `value` has the data resident in HBM (inputs 768 MB >> 126 MB L2, so every sweep streams
 from HBM; no extra L2 flush).  `e2e` is the same metric through the reference-facing call with HOST
@@ -48,7 +50,9 @@ def parse():
     ap.add_argument("--steps", type=int, default=300)
     ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--rows", type=int, default=N_ROWS, help="total customers (default: the named config)")
+    ap.add_argument("--rows", type=int, default=N_ROWS, help="customers per GPU (weak) / in total (strong); default: the named config")
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
+                    help="weak: --rows customers per GPU (chain of N x rows); strong: --rows customers split over the GPUs")
     ap.add_argument("--engine", type=int, default=0, help="0 auto, 1 CUDA-core, 2 tcgen05")
     ap.add_argument("--k-true", type=int, default=CAP, help="planted clusters (default 64 = every table slot in use; "
                     "fewer leaves free slots, so the new-table marginal is evaluated as well)")
@@ -151,7 +155,7 @@ def cpu_port_throughput(rows, threads):
     return rows * len(DIMS) * CAP / dt, dt
 
 
-def run_reference(args):
+def run_reference(args, out):
     """--impl reference: the reference's CPU implementation of the path on the host cores.  The
     reference sampler itself has no D > 1 likelihood, so on this configuration the
     CPU arm is the restated port of its arithmetic (oracle/mv_oracle.c, kind "port"), all host threads."""
@@ -170,17 +174,29 @@ def run_reference(args):
     sample = f"one FP64 sweep over the first {rows} customers of the C3 workload per step, {threads} OpenMP threads"
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
             "steps": len(vals), "warmup": min(args.warmup, 1), "ms_per_step": 1e3 * float(np.mean(dts)),
-            "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": "C3: 3-view Gaussian mixture N=1M D=64 K=64 (bounded CPU sample)", "rows_sampled": rows},
             "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-    print(json.dumps(line))
+    print(json.dumps(line), file=out)
 
 
 def main():
     args = parse()
+    # stdout carries exactly ONE JSON line: anything a library prints there while we run (NCCL's version banner,
+    # for one) is sent to stderr instead, and the line is written to the real stdout at the end
+    sys.stdout.flush()
+    real_stdout = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
+    try:
+        _main(args, real_stdout)
+    finally:
+        real_stdout.flush()
+
+
+def _main(args, out):
     if args.impl == "reference":
-        return run_reference(args)
+        return run_reference(args, out)
 
     import torch
     import mvc_b200
@@ -197,7 +213,7 @@ def main():
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
 
-    n_total = args.rows
+    n_total = args.rows * world if args.scaling == "weak" else args.rows
     lo, hi = rank * n_total // world, (rank + 1) * n_total // world
     n_local = hi - lo
     mus = planted_means(np.random.default_rng(SEED))
@@ -314,16 +330,17 @@ def main():
 
     if rank == 0:
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-                "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+                "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None,
                 "dtype": "f32", "data": "synthetic",
-                "config": {"workload": "C3: synthetic 3-view Gaussian mixture, N=%d, D=64/view, K(cap)=64, row-sharded" % n_total,
+                "config": {"workload": "C3: synthetic 3-view Gaussian mixture, N=%d (%d per GPU), D=64/view, K(cap)=64, row-sharded, "
+                                       "one NCCL all-gather of the per-table statistics per sweep" % (n_total, n_local),
                            "rows_per_gpu": n_local, "hyper_step": do_hyper, "engine": args.engine, "planted_clusters": args.k_true,
                            "l2": "inputs (768 MB per sweep) larger than L2; no flush"},
                 "sweeps_per_s": args.steps / (dev_ms * 1e-3), "wall_ms_per_step": wall_ms / args.steps,
                 "clocks": clocks.summary(), "gpu_launches": int(launches),
                 "roofline": roofline, "e2e": e2e, "cpu_baseline": cpu,
                 "state_check": {"tables_live": int((final["n_t"] > 0).sum()), "customers": int(final["n_t"].sum())}}
-        print(json.dumps(line))
+        print(json.dumps(line), file=out)
     if dist is not None:
         dist.destroy_process_group()
 
