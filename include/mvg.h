@@ -179,6 +179,27 @@ int mvg_profile_sweep(mvg_handle* h, int32_t do_hyper, float ms_out[6]);
 /* The CUDA stream (cudaStream_t as void*) all work of this handle is issued on. */
 void* mvg_stream(mvg_handle* h);
 
+/* ---- posterior summaries (what New_Simulation.R does with the trace) ------ */
+/* Joint log marginal likelihood of the data given the current partition: the sum over live dishes of the
+ * reference's log p(y_S) (multiview_utils.cpp:316-320, per coordinate).  This is what the reference's
+ * declared-but-never-defined compute_log_likelihood() (multiview_gibbs.h:13) / saved_loglik
+ * (multiview_state.h:38) would hold.  per_view: [V] or NULL. */
+int mvg_log_likelihood(mvg_handle* h, double* total, double* per_view);
+/* Cluster of every customer in every view, dish_of[v][table_of[i]]: get_final_clusters of
+ * New_Simulation.R:135-149.  labels: host [V][n_rows]. */
+int mvg_cluster_labels(mvg_handle* h, int32_t* labels);
+/* Co-clustering (posterior similarity) counts kept on the device: begin zeroes an [n_rows][n_rows] uint32
+ * matrix for `view` (-1: tables), accumulate adds [label_i == label_j] for the current state, get copies
+ * the counts and the number of accumulated states out.  One GPU holds the whole chain (world = 1). */
+int mvg_coclustering_begin(mvg_handle* h, int32_t view);
+int mvg_coclustering_accumulate(mvg_handle* h);
+int mvg_coclustering_get(mvg_handle* h, uint32_t* counts, int32_t* n_samples);
+/* Adjusted Rand index of the current clustering of `view` (-1: tables) against host labels
+ * truth[n_rows] in [0, n_classes): mcclust::arandi of New_Simulation.R:189.  contingency (optional, host
+ * [cap][n_classes]) receives the Predicted x Truth table of :192-196.  With world > 1 both are this shard's. */
+int mvg_adjusted_rand_index(mvg_handle* h, int32_t view, const int32_t* truth, int32_t n_classes, double* ari,
+                            int32_t* contingency);
+
 /* ---- Philox host mirror (multiview_rng.h surface) ---------------------------------------- */
 void mvg_philox4x32_10(const uint32_t ctr[4], const uint32_t key[2], uint32_t out[4]);
 float mvg_philox_uniform_f32(uint64_t seed, uint32_t chain, uint32_t domain, uint32_t slot,

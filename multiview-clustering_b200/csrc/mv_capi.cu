@@ -77,6 +77,9 @@ struct mvg_handle {
   float last_ms = 0.f;
   int sms = 148;
   void* tc_maps = nullptr;           // host copy of the TMA tensor maps (tcgen05 engine)
+  uint32_t* cocl = nullptr;          // [n_rows][n_rows] co-clustering counts (mvg_coclustering_*)
+  int32_t cocl_view = -2;
+  int32_t cocl_samples = 0;
 };
 
 namespace {
@@ -655,6 +658,125 @@ int mvg_profile_sweep(mvg_handle* h, int32_t do_hyper, float ms_out[6]) {
 }
 
 void* mvg_stream(mvg_handle* h) { return h ? static_cast<void*>(h->stream) : nullptr; }
+
+// ---- posterior summaries (kernels in mv_summary.cu) ---------------------------------------------
+int mvg_log_likelihood(mvg_handle* h, double* total, double* per_view) {
+  if (!h || !total) return MVG_EINVAL;
+  if (!h->state_ready) return fail(h, MVG_ESTATE, "no state yet");
+  MVG_CUDA(h, cudaSetDevice(h->cfg.device));
+  double* d = nullptr;
+  MVG_CUDA(h, cudaMalloc(&d, sizeof(double) * (h->c.V + 1)));
+  cudaError_t e = launch_loglik(h->c, d, h->stream);
+  std::vector<double> out(h->c.V + 1);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(out.data(), d, sizeof(double) * out.size(), cudaMemcpyDeviceToHost, h->stream);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
+  cudaFree(d);
+  if (e != cudaSuccess) return fail(h, MVG_ECUDA, std::string("log_likelihood: ") + cudaGetErrorString(e));
+  h->launches += 1;
+  *total = out[h->c.V];
+  if (per_view) for (int v = 0; v < h->c.V; ++v) per_view[v] = out[v];
+  return MVG_OK;
+}
+
+int mvg_cluster_labels(mvg_handle* h, int32_t* labels) {
+  if (!h || !labels) return MVG_EINVAL;
+  if (!h->state_ready) return fail(h, MVG_ESTATE, "no state yet");
+  MVG_CUDA(h, cudaSetDevice(h->cfg.device));
+  const size_t count = (size_t)h->c.V * h->c.n_rows;
+  int32_t* d = nullptr;
+  MVG_CUDA(h, cudaMalloc(&d, sizeof(int32_t) * count));
+  cudaError_t e = launch_labels(h->c, d, h->stream);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(labels, d, sizeof(int32_t) * count, cudaMemcpyDeviceToHost, h->stream);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
+  cudaFree(d);
+  if (e != cudaSuccess) return fail(h, MVG_ECUDA, std::string("cluster_labels: ") + cudaGetErrorString(e));
+  h->launches += 1;
+  return MVG_OK;
+}
+
+int mvg_coclustering_begin(mvg_handle* h, int32_t view) {
+  if (!h) return MVG_EINVAL;
+  if (view < -1 || view >= h->c.V) return fail(h, MVG_EINVAL, "view must be -1 (tables) or a view index");
+  if (h->c.world != 1) return fail(h, MVG_EUNSUPPORTED, "co-clustering counts need the whole chain on one GPU (world = 1)");
+  if (h->c.n_rows > 46340) return fail(h, MVG_EUNSUPPORTED, "co-clustering matrix limited to n_rows <= 46340 (n^2 counters)");
+  MVG_CUDA(h, cudaSetDevice(h->cfg.device));
+  const size_t bytes = sizeof(uint32_t) * (size_t)h->c.n_rows * h->c.n_rows;
+  if (!h->cocl) {
+    void* q = nullptr;
+    if (cudaMalloc(&q, bytes) != cudaSuccess) return fail(h, MVG_ENOMEM, "cudaMalloc: co-clustering matrix");
+    h->owned.push_back(q);
+    h->cocl = static_cast<uint32_t*>(q);
+  }
+  MVG_CUDA(h, cudaMemsetAsync(h->cocl, 0, bytes, h->stream));
+  h->cocl_view = view;
+  h->cocl_samples = 0;
+  return MVG_OK;
+}
+
+int mvg_coclustering_accumulate(mvg_handle* h) {
+  if (!h) return MVG_EINVAL;
+  if (!h->cocl || h->cocl_view < -1) return fail(h, MVG_ESTATE, "call mvg_coclustering_begin first");
+  if (!h->state_ready) return fail(h, MVG_ESTATE, "no state yet");
+  MVG_CUDA(h, cudaSetDevice(h->cfg.device));
+  MVG_CUDA(h, launch_cocluster(h->c, h->cocl_view, h->cocl, h->stream));
+  h->launches += 1;
+  h->cocl_samples += 1;
+  return MVG_OK;
+}
+
+int mvg_coclustering_get(mvg_handle* h, uint32_t* counts, int32_t* n_samples) {
+  if (!h) return MVG_EINVAL;
+  if (!h->cocl) return fail(h, MVG_ESTATE, "call mvg_coclustering_begin first");
+  MVG_CUDA(h, cudaSetDevice(h->cfg.device));
+  if (counts)
+    MVG_CUDA(h, cudaMemcpyAsync(counts, h->cocl, sizeof(uint32_t) * (size_t)h->c.n_rows * h->c.n_rows, cudaMemcpyDeviceToHost, h->stream));
+  MVG_CUDA(h, cudaStreamSynchronize(h->stream));
+  if (n_samples) *n_samples = h->cocl_samples;
+  return MVG_OK;
+}
+
+int mvg_adjusted_rand_index(mvg_handle* h, int32_t view, const int32_t* truth, int32_t n_classes, double* ari,
+                            int32_t* contingency) {
+  if (!h || !truth || !ari) return MVG_EINVAL;
+  if (view < -1 || view >= h->c.V) return fail(h, MVG_EINVAL, "view must be -1 (tables) or a view index");
+  if (n_classes <= 0 || n_classes > 65536) return fail(h, MVG_EINVAL, "n_classes out of range");
+  if (!h->state_ready) return fail(h, MVG_ESTATE, "no state yet");
+  for (int64_t i = 0; i < h->c.n_rows; ++i)
+    if (truth[i] < 0 || truth[i] >= n_classes) return fail(h, MVG_EINVAL, "truth label outside [0, n_classes)");
+  MVG_CUDA(h, cudaSetDevice(h->cfg.device));
+  const size_t cells = (size_t)h->c.cap * n_classes;
+  int32_t *d_truth = nullptr, *d_tab = nullptr;
+  MVG_CUDA(h, cudaMalloc(&d_truth, sizeof(int32_t) * (size_t)h->c.n_rows));
+  cudaError_t e = cudaMalloc(&d_tab, sizeof(int32_t) * cells);
+  std::vector<int32_t> tab(cells);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(d_truth, truth, sizeof(int32_t) * (size_t)h->c.n_rows, cudaMemcpyHostToDevice, h->stream);
+  if (e == cudaSuccess) e = cudaMemsetAsync(d_tab, 0, sizeof(int32_t) * cells, h->stream);
+  if (e == cudaSuccess) e = launch_contingency(h->c, view, d_truth, n_classes, d_tab, h->stream);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(tab.data(), d_tab, sizeof(int32_t) * cells, cudaMemcpyDeviceToHost, h->stream);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
+  cudaFree(d_truth);
+  cudaFree(d_tab);
+  if (e != cudaSuccess) return fail(h, MVG_ECUDA, std::string("adjusted_rand_index: ") + cudaGetErrorString(e));
+  h->launches += 1;
+  // closed form from the contingency table (Hubert & Arabie), as mcclust::arandi computes it
+  auto c2 = [](double x) { return 0.5 * x * (x - 1.0); };
+  double sum_ij = 0.0, sum_a = 0.0, sum_b = 0.0, n = 0.0;
+  std::vector<double> col(n_classes, 0.0);
+  for (int k = 0; k < h->c.cap; ++k) {
+    double a = 0.0;
+    for (int z = 0; z < n_classes; ++z) {
+      const double x = (double)tab[(size_t)k * n_classes + z];
+      sum_ij += c2(x); a += x; col[z] += x;
+    }
+    sum_a += c2(a); n += a;
+  }
+  for (int z = 0; z < n_classes; ++z) sum_b += c2(col[z]);
+  const double expected = (n > 1.0) ? sum_a * sum_b / c2(n) : 0.0;
+  const double maxidx = 0.5 * (sum_a + sum_b);
+  *ari = (maxidx - expected != 0.0) ? (sum_ij - expected) / (maxidx - expected) : 1.0;
+  if (contingency) memcpy(contingency, tab.data(), sizeof(int32_t) * cells);
+  return MVG_OK;
+}
 
 void mvg_philox4x32_10(const uint32_t ctr[4], const uint32_t key[2], uint32_t out[4]) {
   U4 c{ctr[0], ctr[1], ctr[2], ctr[3]};

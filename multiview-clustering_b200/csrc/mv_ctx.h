@@ -119,5 +119,10 @@ cudaError_t launch_init_tables(const Ctx& c, int32_t mode, cudaStream_t s);
 cudaError_t launch_rownorms(const float* x, float* xx, int n, int D, cudaStream_t s);
 cudaError_t launch_f64_to_f32(const double* src, float* dst, int64_t n, cudaStream_t s);
 int stats_smem_bytes(const Ctx& c);
+// posterior summaries (mv_summary.cu)
+cudaError_t launch_labels(const Ctx& c, int32_t* out, cudaStream_t s);
+cudaError_t launch_cocluster(const Ctx& c, int view, uint32_t* counts, cudaStream_t s);
+cudaError_t launch_contingency(const Ctx& c, int view, const int32_t* truth, int n_classes, int32_t* table, cudaStream_t s);
+cudaError_t launch_loglik(const Ctx& c, double* out, cudaStream_t s);
 
 }  // namespace mv

@@ -99,6 +99,12 @@ def lib():
         L.mvg_last_sweep_ms.argtypes = [H, _f32p]
         L.mvg_launch_count.restype = C.c_int64
         L.mvg_launch_count.argtypes = [H]
+        L.mvg_log_likelihood.argtypes = [H, _f64p, _f64p]
+        L.mvg_cluster_labels.argtypes = [H, _i32p]
+        L.mvg_coclustering_begin.argtypes = [H, C.c_int32]
+        L.mvg_coclustering_accumulate.argtypes = [H]
+        L.mvg_coclustering_get.argtypes = [H, _u32p, _i32p]
+        L.mvg_adjusted_rand_index.argtypes = [H, C.c_int32, _i32p, C.c_int32, _f64p, _i32p]
         L.mvg_profile_sweep.argtypes = [H, C.c_int32, _f32p]
         L.mvg_stream.restype = C.c_void_p
         L.mvg_stream.argtypes = [H]
@@ -287,6 +293,42 @@ class Sampler:
     def comm_init_rank(self, unique_id: bytes):
         buf = C.create_string_buffer(unique_id, 128)
         self._ck(self.L.mvg_comm_init_rank(self.h, buf))
+
+    # -- posterior summaries ------------------------------------------------------------------
+    def log_likelihood(self):
+        """(total, per view): log marginal likelihood of the data given the current partition."""
+        tot = C.c_double()
+        pv = np.empty(self.V, np.float64)
+        self._ck(self.L.mvg_log_likelihood(self.h, C.byref(tot), _p(pv, _f64p)))
+        return tot.value, pv
+
+    def cluster_labels(self):
+        """[V, n_rows] dish of every customer in every view (get_final_clusters, New_Simulation.R:135-149)."""
+        out = np.empty((self.V, self.n_rows), np.int32)
+        self._ck(self.L.mvg_cluster_labels(self.h, _p(out, _i32p)))
+        return out
+
+    def coclustering_begin(self, view=-1):
+        self._ck(self.L.mvg_coclustering_begin(self.h, int(view)))
+
+    def coclustering_accumulate(self):
+        self._ck(self.L.mvg_coclustering_accumulate(self.h))
+
+    def coclustering_get(self):
+        """(counts [n, n] uint32, number of accumulated states)."""
+        out = np.empty((self.n_rows, self.n_rows), np.uint32)
+        ns = C.c_int32(0)
+        self._ck(self.L.mvg_coclustering_get(self.h, _p(out, _u32p), C.byref(ns)))
+        return out, ns.value
+
+    def adjusted_rand_index(self, view, truth, n_classes=None):
+        """(ARI, contingency [cap, n_classes]) of the current clustering of `view` (-1: tables) vs truth."""
+        truth = np.ascontiguousarray(truth, np.int32)
+        n_classes = int(truth.max()) + 1 if n_classes is None else int(n_classes)
+        ari = C.c_double()
+        tab = np.empty((self.cap, n_classes), np.int32)
+        self._ck(self.L.mvg_adjusted_rand_index(self.h, int(view), _p(truth, _i32p), n_classes, C.byref(ari), _p(tab, _i32p)))
+        return ari.value, tab
 
     # -- inspection ---------------------------------------------------------------------------
     def get_params(self):
