@@ -56,6 +56,11 @@ def parse():
     ap.add_argument("--engine", type=int, default=0, help="0 auto, 1 CUDA-core, 2 tcgen05")
     ap.add_argument("--k-true", type=int, default=CAP, help="planted clusters (default 64 = every table slot in use; "
                     "fewer leaves free slots, so the new-table marginal is evaluated as well)")
+    ap.add_argument("--workload", default="c3", choices=["c3", "c1"],
+                    help="c3: the headline configuration (default).  c1: BASELINE configs[0], the reference's own case "
+                         "(New_Simulation.R: N=500, two scalar views), reported in sweeps/s with --chains independent "
+                         "chains per GPU; with --impl reference the UNMODIFIED reference sampler (oracle/_ref) is timed")
+    ap.add_argument("--chains", type=int, default=8, help="c1: independent chains per GPU, one stream each")
     ap.add_argument("--no-hyper", action="store_true")
     ap.add_argument("--role-profile", action="store_true", help="print the tcgen05 kernel's per-role wait cycles (debug)")
     ap.add_argument("--no-e2e", action="store_true")
@@ -155,6 +160,90 @@ def cpu_port_throughput(rows, threads):
     return rows * len(DIMS) * CAP / dt, dt
 
 
+def c1_views(n=500, seed=SEED):
+    """BASELINE configs[0] / SURVEY.md §8d C1: view1 = N(3,1.3^2) U N(-3,1.3^2); view2 = three groups."""
+    rng = np.random.default_rng(seed)
+    h, q = n // 2, n // 4
+    v1 = np.concatenate([rng.normal(3, 1.3, h), rng.normal(-3, 1.3, n - h)])
+    v2 = np.concatenate([rng.normal(0, 1.3, q), rng.normal(-5, 1.3, h), rng.normal(5, 1.3, n - q - h)])
+    return [v1, v2]
+
+
+def run_c1(args, out):
+    """Config 1 in sweeps/s.  b200 arm: --chains independent chains on one GPU (one handle and stream each,
+    launches interleaved).  reference arm: the unmodified reference sampler compiled into oracle/_ref, 1 core."""
+    rank = int(os.environ.get("RANK", "0"))
+    views = c1_views()
+    n, steps = len(views[0]), args.steps
+    if args.impl == "reference":
+        if rank != 0:
+            return
+        sys.path.insert(0, str(ROOT / "oracle"))
+        import pyoracle as po
+        y = np.stack(views)
+        kind = "reference" if po.have_ref() else "port"
+        t0 = time.perf_counter()
+        if kind == "reference":
+            po.ref_run_gibbs(y, steps, steps, 1, seed=SEED)           # M sweeps, nothing saved
+        else:
+            o = po.OracleState([v.astype(np.float32).reshape(-1, 1) for v in views], 32, seed=SEED)
+            o.init_reference()
+            o.sweep_n(steps, threads=1, do_hyper=True)
+        dt = time.perf_counter() - t0
+        line = {"impl": "reference", "metric": "gibbs_sweeps_per_s", "value": steps / dt, "unit": "sweeps/s", "n_gpus": args.gpus,
+                "steps": steps, "warmup": 0, "ms_per_step": 1e3 * dt / steps, "higher_is_better": True, "scaling": "weak",
+                "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+                "config": {"workload": "C1: New_Simulation.R two scalar views, N=%d, one chain" % n},
+                "cpu_baseline": {"value": steps / dt, "unit": "sweeps/s", "cores": 1, "kind": kind,
+                                 "sample": "%d sweeps of one chain from the reference initialisation" % steps},
+                "e2e": {"value": steps / dt, "unit": "sweeps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+        print(json.dumps(line), file=out)
+        return
+    import torch
+    import mvc_b200
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the sweep has no CPU path")
+    torch.cuda.set_device(local_rank)
+    chains = []
+    for ch in range(args.chains):
+        s = mvc_b200.Sampler(n, [1, 1], cap=32, seed=SEED, chain=rank * args.chains + ch, device=local_rank, engine=1)
+        for v, x in enumerate(views):
+            s.upload_view(v, x.astype(np.float32).reshape(-1, 1))
+        s.init_state_reference()
+        chains.append(s)
+    block = 25                                    # sweeps queued per chain before moving to the next stream
+    def run(k):
+        done = 0
+        while done < k:
+            b = min(block, k - done)
+            for s in chains:
+                s.sweep(b, True)
+            done += b
+        for s in chains:
+            s.sync()
+    run(args.warmup)
+    l0 = sum(s.launch_count() for s in chains)
+    t0 = time.perf_counter()
+    run(steps)
+    dt = time.perf_counter() - t0
+    launches = sum(s.launch_count() for s in chains) - l0
+    one_ms = chains[0].last_sweep_ms() / min(block, steps)
+    live = [int((s.get_state(with_rows=False)["n_t"] > 0).sum()) for s in chains]
+    for s in chains:
+        s.close()
+    if rank == 0:
+        line = {"metric": "gibbs_sweeps_per_s", "value": world * args.chains * steps / dt, "unit": "sweeps/s", "n_gpus": world,
+                "steps": steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / steps, "higher_is_better": True,
+                "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+                "config": {"workload": "C1: New_Simulation.R two scalar views, N=%d, %d independent chains per GPU "
+                                       "(one stream each), CUDA-core engine, hyper step on" % (n, args.chains),
+                           "timing": "wall clock around the launches of all chains and their final synchronisation"},
+                "single_chain_ms_per_sweep_device": one_ms, "gpu_launches": int(launches), "tables_live": live}
+        print(json.dumps(line), file=out)
+
+
 def run_reference(args, out):
     """--impl reference: the reference's CPU implementation of the path on the host cores.  The
     reference sampler itself has no D > 1 likelihood, so on this configuration the
@@ -195,6 +284,8 @@ def main():
 
 
 def _main(args, out):
+    if args.workload == "c1":
+        return run_c1(args, out)
     if args.impl == "reference":
         return run_reference(args, out)
 
