@@ -117,6 +117,16 @@ int mvg_upload_view_f64(mvg_handle* h, int32_t v, const double* y_host, int32_t 
 /* Use a DEVICE buffer in place (row-major [n_rows][dim], 16-byte aligned); the caller keeps ownership. */
 int mvg_attach_view_device_f32(mvg_handle* h, int32_t v, const float* x_dev, int32_t dim);
 
+/* Sparse COUNT view v in CSR form, HOST buffers: rowptr int32[n_rows+1], col int32[nnz] in [0, vocab), val
+ * float[nnz] holding non-negative integer counts (the bag-of-words views of dataset/reuters).
+ * The reference has no count likelihood: the model is the plug-in multinomial of SURVEY.md A.3 /
+ * oracle/mv_oracle.c:counts_log_f_vk, log f_vk(x) = sum_w x_w log((beta + c_kw) / (W beta + C_k)) with the row's own
+ * counts removed for its own dish.  One GPU per chain (world = 1); the CUDA-core engine is used. */
+int mvg_upload_view_csr(mvg_handle* h, int32_t v, const int32_t* rowptr, const int32_t* col, const float* val,
+                        int64_t nnz, int32_t vocab);
+/* Symmetric Dirichlet pseudo-count beta of the count views (default 0.5); before the first state call. */
+int mvg_set_count_beta(mvg_handle* h, double beta);
+
 /* ---- state ----------------------------------------------------------------------------- */
 int mvg_init_state_reference(mvg_handle* h);
 /* Needs table_of, dish_of, alpha_v, sigma_v, tau_v, alpha_sigma_global (sweep optional); the
@@ -163,6 +173,11 @@ int mvg_get_params(mvg_handle* h, const mvg_params_host* out);
 /* With debug_export: per-row stage-A outputs of the LAST sweep: acc [n_rows][V][cap] dot products
  * x.m and xx [n_rows][V] squared norms, plus the raw draw (before births are seated) [n_rows]. */
 int mvg_get_debug_rows(mvg_handle* h, float* acc, float* xx, int32_t* choice);
+/* Count view v: the tables of the NEXT sweep, host [vocab][cap] each (NULL skips): log2 theta of the dish each
+ * table slot serves, that dish's word counts, and the word counts per table slot. */
+int mvg_get_count_tables(mvg_handle* h, int32_t v, float* log2_theta, int32_t* dish_counts, int32_t* table_counts);
+/* With debug_export, count views: loo [n_rows][V] leave-one-out log2 f of every row under its own dish (LAST sweep). */
+int mvg_get_debug_loo(mvg_handle* h, float* loo);
 /* Births of the LAST sweep: rows (global index) seated at new tables in order, and the
  * V*(cap+1) max-normalised dish weights each saw.  rows holds cap entries, w cap*V*(cap+1). */
 int mvg_get_debug_births(mvg_handle* h, int32_t* n_seated, int64_t* rows, double* w);

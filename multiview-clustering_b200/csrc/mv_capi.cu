@@ -77,6 +77,7 @@ struct mvg_handle {
   float last_ms = 0.f;
   int sms = 148;
   void* tc_maps = nullptr;           // host copy of the TMA tensor maps (tcgen05 engine)
+  void* csr_owned[kMaxViews][3]{};   // uploaded CSR views: rowptr, col, val
   uint32_t* cocl = nullptr;          // [n_rows][n_rows] co-clustering counts (mvg_coclustering_*)
   int32_t cocl_view = -2;
   int32_t cocl_samples = 0;
@@ -115,12 +116,20 @@ int ensure_layout(mvg_handle* h) {
   if (h->layout_done) return MVG_OK;
   Ctx& c = h->c;
   int dsum = 0;
+  c.n_count_views = 0;
   for (int v = 0; v < c.V; ++v) {
-    if (!c.x[v] || c.D[v] <= 0) return fail(h, MVG_ESTATE, "view " + std::to_string(v) + " has no data yet");
+    if (c.kind[v]) {
+      if (!c.rowptr[v]) return fail(h, MVG_ESTATE, "view " + std::to_string(v) + " has no data yet");
+      c.n_count_views += 1;
+    } else if (!c.x[v] || c.D[v] <= 0) {
+      return fail(h, MVG_ESTATE, "view " + std::to_string(v) + " has no data yet");
+    }
     c.doff[v] = dsum;
     dsum += c.D[v];
   }
   c.Dsum = dsum;
+  if (c.n_count_views && c.world != 1)
+    return fail(h, MVG_EUNSUPPORTED, "count (CSR) views are supported on one GPU per chain (world = 1) in this version");
   const size_t N = (size_t)c.n_rows, cap = (size_t)c.cap, V = (size_t)c.V;
   int rc;
 #define A(ptr, count) if ((rc = dev_alloc(h, &(ptr), (count))) != MVG_OK) return rc
@@ -145,7 +154,12 @@ int ensure_layout(mvg_handle* h) {
   p.off_cand_x = off; off += align16(4 * c.cap * dsum);
   p.bytes = off;
   A(c.packet, (size_t)c.world * p.bytes);
-  if (c.debug_export & 1) { A(c.dbg_acc, N * V * cap); A(c.dbg_xx, N * V); A(c.dbg_choice, N); }
+  if (c.debug_export & 1) { A(c.dbg_acc, N * V * cap); A(c.dbg_xx, N * V); A(c.dbg_choice, N); A(c.dbg_loo, N * V); }
+  for (int v = 0; v < c.V; ++v)
+    if (c.kind[v]) {
+      const size_t cells = (size_t)c.vocab[v] * cap;
+      A(c.cnt_t[v], cells); A(c.cnt_d[v], cells); A(c.l2t[v], cells);
+    }
 #undef A
   h->layout_done = true;
   // engine choice
@@ -184,6 +198,10 @@ int rebuild_pipeline(mvg_handle* h, int32_t flags, cudaEvent_t* marks /* 4 event
   if (rc != MVG_OK) return rc;
   if (marks) MVG_CUDA(h, cudaEventRecord(marks[2], h->stream));
   MVG_CUDA(h, launch_finalize(h->c, flags, h->stream));
+  if (h->c.n_count_views) {          // count views: word counts by the final seating, then the log2 theta tables
+    MVG_CUDA(h, launch_counts_rebuild(h->c, h->stream));
+    h->launches += 2 * h->c.n_count_views;
+  }
   if (marks) MVG_CUDA(h, cudaEventRecord(marks[3], h->stream));
   h->launches += 3;
   return MVG_OK;
@@ -258,6 +276,7 @@ int mvg_create(const mvg_config* cfg, mvg_handle** out) {
   c.n_chunks = (c.n_rows + 31) / 32;
   c.stat_ctas = c.n_chunks < h->sms ? c.n_chunks : h->sms;
   c.debug_export = cfg->debug_export;
+  c.count_beta = 0.5f;
   {
     void* q = nullptr;
     c.xx_stride = ((int64_t)c.n_rows + 3) & ~(int64_t)3;        // rows of xx start 16-byte aligned (bulk copies)
@@ -279,6 +298,7 @@ int mvg_destroy(mvg_handle* h) {
   if (h->comm && h->comm_owned && g_nccl.CommDestroy) g_nccl.CommDestroy(h->comm);
   for (void* p : h->owned) cudaFree(p);
   for (void* p : h->view_owned) if (p) cudaFree(p);
+  for (auto& a : h->csr_owned) for (void* p : a) if (p) cudaFree(p);
   for (auto& ev : h->ev) if (ev) cudaEventDestroy(ev);
   if (h->stream) cudaStreamDestroy(h->stream);
   free(h->tc_maps);
@@ -308,6 +328,7 @@ int mvg_upload_view_f32(mvg_handle* h, int32_t v, const float* x_host, int32_t d
   MVG_CUDA(h, cudaMemcpyAsync(h->view_owned[v], x_host, bytes, cudaMemcpyHostToDevice, h->stream));
   h->c.x[v] = static_cast<const float*>(h->view_owned[v]);
   h->c.D[v] = dim;
+  h->c.kind[v] = 0;
   MVG_CUDA(h, launch_rownorms(h->c.x[v], h->c.xx + (size_t)v * h->c.xx_stride, h->c.n_rows, dim, h->stream));
   h->launches += 1;
   return MVG_OK;
@@ -347,6 +368,78 @@ int mvg_attach_view_device_f32(mvg_handle* h, int32_t v, const float* x_dev, int
   h->c.D[v] = dim;
   MVG_CUDA(h, launch_rownorms(x_dev, h->c.xx + (size_t)v * h->c.xx_stride, h->c.n_rows, dim, h->stream));
   h->launches += 1;
+  return MVG_OK;
+}
+
+int mvg_set_count_beta(mvg_handle* h, double beta) {
+  if (!h) return MVG_EINVAL;
+  if (!(beta > 0.0) || beta > 1.0e6) return fail(h, MVG_EINVAL, "count_beta must be positive");
+  if (h->state_ready) return fail(h, MVG_ESTATE, "count_beta is frozen after the first state call");
+  h->c.count_beta = (float)beta;
+  return MVG_OK;
+}
+
+int mvg_upload_view_csr(mvg_handle* h, int32_t v, const int32_t* rowptr, const int32_t* col, const float* val,
+                        int64_t nnz, int32_t vocab) {
+  if (!h) return MVG_EINVAL;
+  if (v < 0 || v >= h->c.V) return fail(h, MVG_EINVAL, "view index out of range");
+  if (!rowptr || (nnz > 0 && (!col || !val))) return fail(h, MVG_EINVAL, "null data");
+  if (vocab <= 0 || nnz < 0 || nnz > 0x7fffffffLL) return fail(h, MVG_EINVAL, "vocab / nnz out of range");
+  if (h->layout_done) return fail(h, MVG_ESTATE, "views are frozen after the first state call");
+  const int64_t n = h->c.n_rows;
+  if (rowptr[0] != 0 || rowptr[n] != nnz) return fail(h, MVG_EINVAL, "rowptr[0] must be 0 and rowptr[n_rows] = nnz");
+  for (int64_t i = 0; i < n; ++i)
+    if (rowptr[i + 1] < rowptr[i]) return fail(h, MVG_EINVAL, "rowptr must be non-decreasing");
+  for (int64_t j = 0; j < nnz; ++j) {
+    if (col[j] < 0 || col[j] >= vocab) return fail(h, MVG_EINVAL, "column index outside [0, vocab)");
+    if (!(val[j] >= 0.0f) || val[j] > 16777216.0f || val[j] != (float)(int32_t)val[j])
+      return fail(h, MVG_EINVAL, "count views hold non-negative integer counts (< 2^24)");
+  }
+  MVG_CUDA(h, cudaSetDevice(h->cfg.device));
+  for (void*& p : h->csr_owned[v]) { if (p) cudaFree(p); p = nullptr; }
+  if (h->view_owned[v]) { cudaFree(h->view_owned[v]); h->view_owned[v] = nullptr; }
+  const size_t nz = (size_t)(nnz ? nnz : 1);
+  MVG_CUDA(h, cudaMalloc(&h->csr_owned[v][0], sizeof(int32_t) * (size_t)(n + 1)));
+  MVG_CUDA(h, cudaMalloc(&h->csr_owned[v][1], sizeof(int32_t) * nz));
+  MVG_CUDA(h, cudaMalloc(&h->csr_owned[v][2], sizeof(float) * nz));
+  MVG_CUDA(h, cudaMemcpyAsync(h->csr_owned[v][0], rowptr, sizeof(int32_t) * (size_t)(n + 1), cudaMemcpyHostToDevice, h->stream));
+  if (nnz) {
+    MVG_CUDA(h, cudaMemcpyAsync(h->csr_owned[v][1], col, sizeof(int32_t) * nz, cudaMemcpyHostToDevice, h->stream));
+    MVG_CUDA(h, cudaMemcpyAsync(h->csr_owned[v][2], val, sizeof(float) * nz, cudaMemcpyHostToDevice, h->stream));
+  }
+  Ctx& c = h->c;
+  c.kind[v] = 1;
+  c.vocab[v] = vocab;
+  c.D[v] = 0;
+  c.x[v] = nullptr;
+  c.rowptr[v] = static_cast<const int32_t*>(h->csr_owned[v][0]);
+  c.col[v] = static_cast<const int32_t*>(h->csr_owned[v][1]);
+  c.val[v] = static_cast<const float*>(h->csr_owned[v][2]);
+  MVG_CUDA(h, launch_rowtotals(c.rowptr[v], c.val[v], c.xx + (size_t)v * c.xx_stride, c.n_rows, h->stream));
+  MVG_CUDA(h, cudaStreamSynchronize(h->stream));       // the caller's buffers may go away
+  h->launches += 1;
+  return MVG_OK;
+}
+
+int mvg_get_count_tables(mvg_handle* h, int32_t v, float* log2_theta, int32_t* dish_counts, int32_t* table_counts) {
+  if (!h) return MVG_EINVAL;
+  if (v < 0 || v >= h->c.V || !h->c.kind[v]) return fail(h, MVG_EINVAL, "not a count view");
+  if (!h->state_ready) return fail(h, MVG_ESTATE, "no state yet");
+  MVG_CUDA(h, cudaSetDevice(h->cfg.device));
+  const size_t cells = (size_t)h->c.vocab[v] * h->c.cap;
+  if (log2_theta) MVG_CUDA(h, cudaMemcpyAsync(log2_theta, h->c.l2t[v], sizeof(float) * cells, cudaMemcpyDeviceToHost, h->stream));
+  if (dish_counts) MVG_CUDA(h, cudaMemcpyAsync(dish_counts, h->c.cnt_d[v], sizeof(int32_t) * cells, cudaMemcpyDeviceToHost, h->stream));
+  if (table_counts) MVG_CUDA(h, cudaMemcpyAsync(table_counts, h->c.cnt_t[v], sizeof(int32_t) * cells, cudaMemcpyDeviceToHost, h->stream));
+  MVG_CUDA(h, cudaStreamSynchronize(h->stream));
+  return MVG_OK;
+}
+
+int mvg_get_debug_loo(mvg_handle* h, float* loo) {
+  if (!h || !loo) return MVG_EINVAL;
+  if (!h->c.dbg_loo) return fail(h, MVG_ESTATE, "debug_export was not enabled");
+  MVG_CUDA(h, cudaSetDevice(h->cfg.device));
+  MVG_CUDA(h, cudaMemcpyAsync(loo, h->c.dbg_loo, sizeof(float) * (size_t)h->c.n_rows * h->c.V, cudaMemcpyDeviceToHost, h->stream));
+  MVG_CUDA(h, cudaStreamSynchronize(h->stream));
   return MVG_OK;
 }
 

@@ -48,7 +48,19 @@ struct Ctx {
   int32_t D[kMaxViews];
   int32_t doff[kMaxViews];
   const float* x[kMaxViews];
-  float* xx;                // [V][xx_stride] squared norms of the rows (computed once per upload)
+  // sparse COUNT views (CSR).  kind[v] = 1: view v has no dense columns (D[v] = 0); its rows are
+  // val[rowptr[i] .. rowptr[i+1]) at columns col[..] of a vocabulary of vocab[v] words.
+  int32_t kind[kMaxViews];
+  int32_t vocab[kMaxViews];
+  const int32_t* rowptr[kMaxViews];
+  const int32_t* col[kMaxViews];
+  const float* val[kMaxViews];
+  int32_t* cnt_t[kMaxViews];   // [vocab][cap] word counts per TABLE slot (rebuilt after every finalize)
+  int32_t* cnt_d[kMaxViews];   // [vocab][cap] word counts of the DISH each table slot serves
+  float* l2t[kMaxViews];       // [vocab][cap] log2 theta of that dish: log2((beta + cnt_d) / (W beta + total))
+  float count_beta;            // symmetric Dirichlet pseudo-count
+  int32_t n_count_views;
+  float* xx;                // [V][xx_stride] squared norms of the rows (count views: the rows' total counts), computed once per upload
   int64_t xx_stride;        // n_rows rounded up to a multiple of 4
 
   int32_t* table_cur;
@@ -86,6 +98,7 @@ struct Ctx {
   float* dbg_acc;           // [N][V][cap]
   float* dbg_xx;            // [N][V]
   int32_t* dbg_choice;      // [N]
+  float* dbg_loo;           // [N][V] count views: the leave-one-out log2 f of the row under its own dish
   int64_t* dbg_birth_rows;  // [cap]
   double* dbg_birth_w;      // [cap][V][cap+1]
   int32_t* dbg_nseated;     // [1]
@@ -119,6 +132,9 @@ cudaError_t launch_init_tables(const Ctx& c, int32_t mode, cudaStream_t s);
 cudaError_t launch_rownorms(const float* x, float* xx, int n, int D, cudaStream_t s);
 cudaError_t launch_f64_to_f32(const double* src, float* dst, int64_t n, cudaStream_t s);
 int stats_smem_bytes(const Ctx& c);
+// count views (mv_counts.cu)
+cudaError_t launch_rowtotals(const int32_t* rowptr, const float* val, float* out, int n, cudaStream_t s);
+cudaError_t launch_counts_rebuild(const Ctx& c, cudaStream_t s);   // per count view: zero, scatter, dish tables
 // posterior summaries (mv_summary.cu)
 cudaError_t launch_labels(const Ctx& c, int32_t* out, cudaStream_t s);
 cudaError_t launch_cocluster(const Ctx& c, int view, uint32_t* counts, cudaStream_t s);

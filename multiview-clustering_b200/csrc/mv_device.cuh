@@ -371,6 +371,19 @@ struct RowEpilogue {
     hb.template view_chunks_from<0>(hot + HALF / 2, cold + HALF, acc + HALF);
     lnew = __fadd_rn(lnew, merge_view<FAST>(ha.mx, ha.s, hb.mx, hb.s, vp, xx, ha.single, ha.lone0));
   }
+  // A COUNT view (mv_counts.cu): acc[t] is already log2 f under table t's dish (the parameter block carries
+  // A = 1/2, C = 0, so that C + A (2 acc - 0) = acc exactly), acc_loo the leave-one-out value under the customer's
+  // own dish, rowtot = |x| enters only the new-dish term log2 f_new = -|x| log2 W (AN = log2 W, CN = 0).
+  __device__ __forceinline__ void view_counts(const PairHot* __restrict__ hot, const TableCold* __restrict__ cold,
+                                              const ViewParam& vp, const float (&acc)[CAP], float acc_loo, float rowtot) {
+    ha.view_begin(hot, cold, 0.0f);
+    ha.A1r = 0.0f; ha.C1r = acc_loo;
+    ha.template view_chunks_from<0>(hot, cold, acc);
+    hb.view_begin(hot, cold, 0.0f);
+    hb.A1r = 0.0f; hb.C1r = acc_loo;
+    hb.template view_chunks_from<0>(hot + HALF / 2, cold + HALF, acc + HALF);
+    lnew = __fadd_rn(lnew, merge_view<FAST>(ha.mx, ha.s, hb.mx, hb.s, vp, rowtot, ha.single, ha.lone0));
+  }
   // uf in (0,1). Returns the table slot or kNewTable.
   __device__ __forceinline__ int finish(float uf) {
     const float M = fmaxf(fmaxf(lnew, ha.halfmax()), hb.halfmax());

@@ -19,7 +19,7 @@ template <int CAP, bool VEC4>
 __global__ void __launch_bounds__(kSimtThreads, 2) k_draw_simt(const Ctx c) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   float* s_m = reinterpret_cast<float*>(smem_raw);                       // [CAP][dch]
-  const int dch_max = (c.Dsum < kSimtDChunk) ? c.Dsum : kSimtDChunk;     // upper bound on any view's chunk
+  const int dch_max = (c.Dsum < kSimtDChunk) ? (c.Dsum > 0 ? c.Dsum : 1) : kSimtDChunk;   // upper bound on any view's chunk
   PairHot* s_hot = reinterpret_cast<PairHot*>(smem_raw + sizeof(float) * (size_t)CAP * (size_t)dch_max);   // [CAP/2]
   TableCold* s_cold = reinterpret_cast<TableCold*>(s_hot + CAP / 2);                                        // [CAP]
   __shared__ TableMass s_tm[CAP];
@@ -42,6 +42,53 @@ __global__ void __launch_bounds__(kSimtThreads, 2) k_draw_simt(const Ctx c) {
     epi.begin(s_tm, s_lm, s_g, c.table_cur[rowc]);
 
     for (int v = 0; v < c.V; ++v) {
+      if (c.kind[v]) {
+        // ---- sparse count view: acc[t] = sum_j x_j log2 theta[col_j][t], one ascending fmaf chain per table over
+        //      the row's nonzeros (the order of oracle/mv_oracle.c:mvo_stageA_counts_f32); the table is
+        //      feature-major, so one nonzero reads CAP consecutive floats ----
+        __syncthreads();   // previous users of s_hot / s_cold are done
+        stage_view_params(c.tparam + v * CAP, CAP, s_hot, s_cold, tid, kSimtThreads);
+        if (tid == 0) s_vp = c.vparam[v];
+        __syncthreads();
+        const int32_t* __restrict__ colv = c.col[v];
+        const float* __restrict__ valv = c.val[v];
+        const float* __restrict__ l2t = c.l2t[v];
+        const int32_t* __restrict__ cdt = c.cnt_d[v];
+        const int j0 = c.rowptr[v][rowc], j1 = c.rowptr[v][rowc + 1];
+        const int t0 = c.table_cur[rowc];
+        const float rowtot = c.xx[(size_t)v * c.xx_stride + rowc];
+        float acc[CAP];
+#pragma unroll
+        for (int t = 0; t < CAP; ++t) acc[t] = 0.0f;
+        // leave-one-out under the own dish: counts and total with this row removed (TableParam::C1 of a count
+        // view carries W beta + the dish's token total)
+        const float lden = log2m(__fadd_rn(s_cold[t0].C1, -rowtot));
+        float acc_loo = 0.0f;
+        for (int j = j0; j < j1; ++j) {
+          const float xv = __ldg(valv + j);
+          const size_t w = (size_t)__ldg(colv + j) * CAP;
+          const float4* __restrict__ lt = reinterpret_cast<const float4*>(l2t + w);
+#pragma unroll
+          for (int q = 0; q < CAP / 4; ++q) {
+            const float4 l4 = __ldg(lt + q);
+            acc[4 * q] = __fmaf_rn(xv, l4.x, acc[4 * q]);
+            acc[4 * q + 1] = __fmaf_rn(xv, l4.y, acc[4 * q + 1]);
+            acc[4 * q + 2] = __fmaf_rn(xv, l4.z, acc[4 * q + 2]);
+            acc[4 * q + 3] = __fmaf_rn(xv, l4.w, acc[4 * q + 3]);
+          }
+          const float cown = (float)__ldg(cdt + w + t0);
+          acc_loo = __fmaf_rn(xv, __fadd_rn(log2m(__fadd_rn(__fadd_rn(c.count_beta, cown), -xv)), -lden), acc_loo);
+        }
+        if ((c.debug_export & 1) && live) {
+          float* da = c.dbg_acc + ((size_t)row * c.V + v) * CAP;
+#pragma unroll
+          for (int t = 0; t < CAP; ++t) da[t] = acc[t];
+          c.dbg_xx[(size_t)row * c.V + v] = rowtot;
+          c.dbg_loo[(size_t)row * c.V + v] = acc_loo;
+        }
+        epi.view_counts(s_hot, s_cold, s_vp, acc, acc_loo, rowtot);
+        continue;
+      }
       const int D = c.D[v];
       const float* __restrict__ xrow = c.x[v] + (size_t)rowc * D;
       const float* __restrict__ mean_v = c.mean + (size_t)c.cap * c.doff[v];
@@ -113,8 +160,8 @@ template <int CAP>
 static cudaError_t launch_simt_cap(const Ctx& c, cudaStream_t s) {
   bool vec4 = true;
   for (int v = 0; v < c.V; ++v)
-    if ((c.D[v] & 3) != 0 || (reinterpret_cast<uintptr_t>(c.x[v]) & 15) != 0) vec4 = false;
-  const int dch = (c.Dsum < kSimtDChunk) ? c.Dsum : kSimtDChunk;
+    if (!c.kind[v] && ((c.D[v] & 3) != 0 || (reinterpret_cast<uintptr_t>(c.x[v]) & 15) != 0)) vec4 = false;
+  const int dch = (c.Dsum < kSimtDChunk) ? (c.Dsum > 0 ? c.Dsum : 1) : kSimtDChunk;
   const size_t smem = sizeof(float) * (size_t)CAP * dch + sizeof(TableParam) * CAP;
   const int n_tiles = (c.n_rows + kSimtThreads - 1) / kSimtThreads;
   int dev = 0, sms = 148;

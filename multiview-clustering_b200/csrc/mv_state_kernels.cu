@@ -188,8 +188,8 @@ __global__ void __launch_bounds__(768, 1) k_stats(const Ctx c, const int Gp, con
     int v = 0;
     while (v + 1 < c.V && col >= c.doff[v + 1]) ++v;
     const bool is_norm = col >= c.Dsum;
-    const int D = is_norm ? 1 : c.D[v];
-    const float* __restrict__ base = !has ? c.x[0] : (is_norm ? c.xx + (size_t)(col - c.Dsum) * c.xx_stride : c.x[v] + (col - c.doff[v]));
+    const int D = (is_norm || !has) ? 1 : c.D[v];
+    const float* __restrict__ base = !has ? c.xx : (is_norm ? c.xx + (size_t)(col - c.Dsum) * c.xx_stride : c.x[v] + (col - c.doff[v]));
     for (int i = lane; i < cap * 32; i += 32) acc[i] = 0.0f;
     if (pass == 0 && cg == 0) for (int i = lane; i < cap; i += 32) cntw[i] = 0;
     __syncwarp();
@@ -367,6 +367,8 @@ struct FinShared {
   long long total[kMaxViews + 1];                  // items of level j (tables of view j; customers for level V)
   double s2t[kMaxViews][kMaxCap];         // sums of squared norms per table (working copy of S2t)
   double s2k[kMaxViews][kMaxCap];         //   and per dish
+  double s2k_start[kMaxViews][kMaxCap];   // per dish at sweep START (count views: the token totals the births see)
+  int32_t table_of_dish[kMaxViews][kMaxCap];   // at sweep start: lowest table slot serving dish k, -1 = none
   double s1sq[kMaxViews][kMaxCap];        // |S1k|^2
   double sse[kMaxViews][kMaxCap];         // max(0, S2k - |S1k|^2 / n_k)     (multiview_hyper.cpp:191-193)
   double termA[2 * (kMaxViews + 1)][kMaxCap + 1];   // scratch of the batched EPPF evaluations
@@ -519,6 +521,25 @@ __device__ __noinline__ double log_f_dish(const Ctx& c, const FinShared& S, int 
   return -0.5 * (double)D * fin_log(2.0 * kPi * var) - 0.5 * dist / var;
 }
 
+// Count view: log f of local ROW `row` under dish k from the sweep-start dish counts (cnt_d is indexed by TABLE
+// slot: tk is any table serving dish k, or -1 for a dish without tables = empty), FP64
+// (oracle/mv_oracle.c:counts_log_f_vk).
+__device__ __noinline__ double log_f_dish_counts(const Ctx& c, const FinShared& S, int v, int k, int tk, int row, bool loo) {
+  const int32_t* rp = c.rowptr[v];
+  const double beta = (double)c.count_beta;
+  double tot = 0.0;
+  for (int j = rp[row]; j < rp[row + 1]; ++j) tot += (double)c.val[v][j];
+  const double ctot = (tk >= 0) ? S.s2k_start[v][k] : 0.0;
+  const double den = (double)c.vocab[v] * beta + ctot - (loo ? tot : 0.0);
+  double lf = 0.0;
+  for (int j = rp[row]; j < rp[row + 1]; ++j) {
+    const double x = (double)c.val[v][j];
+    const double cd = (tk >= 0) ? (double)c.cnt_d[v][(size_t)c.col[v][j] * c.cap + tk] : 0.0;
+    lf += x * fin_log((beta + cd - (loo ? x : 0.0)) / den);
+  }
+  return lf;
+}
+
 __global__ void __launch_bounds__(kFinThreads, 1) k_finalize(const Ctx c, const int32_t flags, const int32_t s1_in_smem) {
   extern __shared__ __align__(16) unsigned char fin_smem[];
   FinShared& S = *reinterpret_cast<FinShared*>(fin_smem);
@@ -594,6 +615,16 @@ __global__ void __launch_bounds__(kFinThreads, 1) k_finalize(const Ctx c, const 
     S.n_vk[v][t] = c.n_vk[i];
   }
   __syncthreads();
+  if (c.n_count_views) {
+    for (int i = tid; i < V * cap; i += kFinThreads) {
+      const int v = i / cap, k = i - v * cap;
+      S.s2k_start[v][k] = c.S2k[i];
+      int tk = -1;
+      for (int t = cap - 1; t >= 0; --t) if (S.dish[v][t] == k && c.n_t[t] > 0) tk = t;
+      S.table_of_dish[v][k] = tk;
+    }
+    __syncthreads();
+  }
 
   stamp(0);
   // ---- B. births: candidates in global row order, the first nfree are seated -----------------
@@ -620,7 +651,17 @@ __global__ void __launch_bounds__(kFinThreads, 1) k_finalize(const Ctx c, const 
       const int v = rem / (cap + 1), k = rem - v * (cap + 1);
       const float* x = pkt_f32(c, S.cand_g[b], c.pkt.off_cand_x) + (size_t)S.cand_j[b] * c.Dsum;
       double val;
-      if (k == cap) {   // new dish: N(x; 0, tau)   (multiview_utils.cpp:340-350)
+      if (c.kind[v]) {  // count view (one GPU per chain: the candidate's row is local)
+        const int row = pkt_i32(c, S.cand_g[b], c.pkt.off_cand_row)[S.cand_j[b]];
+        if (k == cap) {
+          double tot = 0.0;
+          for (int j = c.rowptr[v][row]; j < c.rowptr[v][row + 1]; ++j) tot += (double)c.val[v][j];
+          val = -tot * fin_log((double)c.vocab[v]);
+        } else {
+          const int t0 = pkt_i32(c, S.cand_g[b], c.pkt.off_cand_t0)[S.cand_j[b]];
+          val = log_f_dish_counts(c, S, v, k, S.table_of_dish[v][k], row, (k == S.dish[v][t0]) && S.n_vk[v][k] > 0);
+        }
+      } else if (k == cap) {   // new dish: N(x; 0, tau)   (multiview_utils.cpp:340-350)
         const int D = c.D[v];
         double q = 0.0;
         for (int dd = 0; dd < D; ++dd) q += (double)x[c.doff[v] + dd] * (double)x[c.doff[v] + dd];
@@ -715,6 +756,8 @@ __global__ void __launch_bounds__(kFinThreads, 1) k_finalize(const Ctx c, const 
         const float* x = pkt_f32(c, S.cand_g[b], c.pkt.off_cand_x) + (size_t)S.cand_j[b] * c.Dsum + c.doff[v];
         double q = 0.0;
         for (int dd = 0; dd < c.D[v]; ++dd) q += (double)x[dd] * (double)x[dd];
+        if (c.kind[v])     // count view: this slot carries token totals; the candidate's row is local (world = 1)
+          q = (double)c.xx[(size_t)v * c.xx_stride + pkt_i32(c, S.cand_g[b], c.pkt.off_cand_row)[S.cand_j[b]]];
         S.s2t[v][S.cand_final[b]] += q;
       }
     }
@@ -814,7 +857,7 @@ __global__ void __launch_bounds__(kFinThreads, 1) k_finalize(const Ctx c, const 
       double var = 1.0;
       if (c.n_global > 1) var = (S.s2k[v][0] - S.s1sq[v][0] / n) / ((n - 1.0) * (double)c.D[v]);
       if (!(var > 0.0)) var = 1.0;
-      tau_v[v] = var * 0.25 * 0.01;
+      tau_v[v] = c.kind[v] ? 1.0 : var * 0.25 * 0.01;      // a count view has no kernel variance
       alpha_v[v] = 1.0;
       sigma_v[v] = 0.5;
     }
@@ -831,6 +874,7 @@ __global__ void __launch_bounds__(kFinThreads, 1) k_finalize(const Ctx c, const 
     if (flags & kFinHyperTau) {                                // update_tau_v_MH, :211-231: one warp per view
       const int lane = tid & 31, wid = tid >> 5;
       for (int v = wid; v < V; v += kFinThreads / 32) {
+        if (c.kind[v]) continue;                               // no tau in a count view (its stream positions stay unused)
         double tau_old = tau_v[v];
         if (tau_old <= 0.0) tau_old = kEps;
         const double tau_prop = fin_exp(fin_log(tau_old) + 0.0 + 0.3 * S.rn[v]);   // :166-174
@@ -948,6 +992,17 @@ __global__ void __launch_bounds__(kFinThreads, 1) k_finalize(const Ctx c, const 
     TableParam q;
     if (k < 0) {
       q.A = 0.f; q.C = kMasked; q.A1 = 0.f; q.C1 = kMasked; q.W = kMasked; q.W1 = kMasked; q.dish = -1; q.lone = 0;
+    } else if (c.kind[v]) {
+      // count view: the dot products are log2 f already (C + A (2 acc - 0) = acc); C1 carries W beta + the token
+      // total of the dish for the leave-one-out term of the kernel
+      q.A = 0.5f; q.C = 0.f; q.A1 = 0.f;
+      q.C1 = (float)((double)c.vocab[v] * (double)c.count_beta + S.s2k[v][k]);
+      const bool rep = (__ffsll((long long)S.tmask[v][k]) - 1 == t);
+      const double w = (double)S.l_live[v][k] - sigma_v[v], w1 = w - 1.0;
+      q.W = (rep && w > 0.0) ? (float)fin_log2(w) : kMasked;
+      q.W1 = (rep && w1 > 0.0) ? (float)fin_log2(w1) : kMasked;
+      q.dish = k;
+      q.lone = (S.l_live[v][k] == 1);
     } else {
       const double tau = tau_v[v], n = (double)S.n_vk[v][k];
       const double a = (tau + n) / (2.0 * tau * (tau + n + 1.0));
@@ -982,6 +1037,7 @@ __global__ void __launch_bounds__(kFinThreads, 1) k_finalize(const Ctx c, const 
     ViewParam p;
     p.AN = (float)(kLog2e / (2.0 * tau));
     p.CN = (float)(kLog2e * (-0.5 * (double)c.D[v] * fin_log(2.0 * kPi * tau)));
+    if (c.kind[v]) { p.AN = (float)fin_log2((double)c.vocab[v]); p.CN = 0.f; }      // log2 f_new = -|x| log2 W
     const double wn0 = alpha_v[v] + (double)K_act * sigma_v[v], wn1 = alpha_v[v] + (double)(K_act - 1) * sigma_v[v];
     p.WN0 = wn0 > 0.0 ? (float)fin_log2(wn0) : kMasked;
     p.WN1 = wn1 > 0.0 ? (float)fin_log2(wn1) : kMasked;

@@ -81,6 +81,10 @@ def lib():
         L.mvg_upload_view_f32.argtypes = [H, C.c_int32, _f32p, C.c_int32]
         L.mvg_upload_view_f64.argtypes = [H, C.c_int32, _f64p, C.c_int32]
         L.mvg_attach_view_device_f32.argtypes = [H, C.c_int32, C.c_void_p, C.c_int32]
+        L.mvg_upload_view_csr.argtypes = [H, C.c_int32, _i32p, _i32p, _f32p, C.c_int64, C.c_int32]
+        L.mvg_set_count_beta.argtypes = [H, C.c_double]
+        L.mvg_get_count_tables.argtypes = [H, C.c_int32, _f32p, _i32p, _i32p]
+        L.mvg_get_debug_loo.argtypes = [H, _f32p]
         L.mvg_init_state_reference.argtypes = [H]
         L.mvg_set_state.argtypes = [H, C.POINTER(_StateHost)]
         L.mvg_get_state.argtypes = [H, C.POINTER(_StateHost)]
@@ -183,6 +187,34 @@ class Sampler:
         else:
             x = np.ascontiguousarray(x, dtype=np.float32)
             self._ck(self.L.mvg_upload_view_f32(self.h, v, _p(x, _f32p), x.shape[1]))
+
+    def upload_view_csr(self, v, rowptr, col, val, vocab):
+        """Sparse count view v (declare it with dim 0 in ``dims``): CSR arrays over a vocabulary of ``vocab`` words."""
+        assert self.dims[v] == 0, "declare count views with dim 0"
+        rowptr = np.ascontiguousarray(rowptr, np.int32)
+        col = np.ascontiguousarray(col, np.int32)
+        val = np.ascontiguousarray(val, np.float32)
+        assert rowptr.shape == (self.n_rows + 1,) and col.shape == val.shape
+        self.vocab = getattr(self, "vocab", {})
+        self.vocab[v] = int(vocab)
+        self._ck(self.L.mvg_upload_view_csr(self.h, v, _p(rowptr, _i32p), _p(col, _i32p), _p(val, _f32p), len(col), int(vocab)))
+
+    def set_count_beta(self, beta):
+        self._ck(self.L.mvg_set_count_beta(self.h, float(beta)))
+
+    def get_count_tables(self, v):
+        """(log2 theta, dish counts, table counts), each [vocab, cap], of count view v for the NEXT sweep."""
+        W = self.vocab[v]
+        l2t = np.empty((W, self.cap), np.float32)
+        cd = np.empty((W, self.cap), np.int32)
+        ct = np.empty((W, self.cap), np.int32)
+        self._ck(self.L.mvg_get_count_tables(self.h, v, _p(l2t, _f32p), _p(cd, _i32p), _p(ct, _i32p)))
+        return l2t, cd, ct
+
+    def get_debug_loo(self):
+        out = np.empty((self.n_rows, self.V), np.float32)
+        self._ck(self.L.mvg_get_debug_loo(self.h, _p(out, _f32p)))
+        return out
 
     def attach_view_device(self, v, tensor):
         """Use a CUDA torch tensor (float32, contiguous, [n_rows, dim]) in place."""

@@ -40,6 +40,8 @@ double mvo_z(uint64_t seed, uint32_t chain, uint32_t domain, uint32_t slot, uint
 /* ======================================================================================
  * State
  * ==================================================================================== */
+static int is_counts(const mvo_state* s, int v) { return s->csr != NULL && s->csr[v].rowptr != NULL; }
+
 int mvo_rebuild_stats(mvo_state* s) {
   const int cap = s->cap, V = s->V;
   memset(s->n_t, 0, sizeof(int32_t) * (size_t)cap);
@@ -63,6 +65,23 @@ int mvo_rebuild_stats(mvo_state* s) {
       if (s->n_t[t] == 0) { dish[t] = -1; continue; }
       if (dish[t] < 0 || dish[t] >= cap) return 2;
       l_vk[dish[t]]++;                                   /* multiview_gibbs.cpp:60 */
+    }
+    if (is_counts(s, v)) {                                 /* count view: word counts per dish */
+      const mvo_csr* cs = &s->csr[v];
+      memset(cs->cd, 0, sizeof(int64_t) * (size_t)cap * cs->vocab);
+      memset(cs->ctot, 0, sizeof(int64_t) * (size_t)cap);
+      for (int i = 0; i < s->n; ++i) {
+        int k = dish[s->table_of[i]];
+        double tot = 0.0;
+        for (int j = cs->rowptr[i]; j < cs->rowptr[i + 1]; ++j) {
+          cs->cd[(size_t)k * cs->vocab + cs->col[j]] += (int64_t)cs->val[j];
+          tot += (double)cs->val[j];
+        }
+        cs->ctot[k] += (int64_t)tot;
+        n_vk[k]++;
+        S2[k] += tot;                                      /* the device keeps the token totals in this slot */
+      }
+      continue;
     }
     for (int i = 0; i < s->n; ++i) {                      /* multiview_gibbs.cpp:64-73 */
       int k = dish[s->table_of[i]];
@@ -104,6 +123,7 @@ int mvo_init_reference(mvo_state* s) {
     s->sigma_v[v] = 0.5;
     /* :78-94, pooled over the D coordinates (equal to the reference at D = 1) */
     const int D = s->D[v];
+    if (is_counts(s, v)) { s->tau_v[v] = 1.0; continue; }   /* no kernel variance in a count view */
     double var_sum = 0.0;
     for (int dd = 0; dd < D; ++dd) {
       double s1 = 0.0;
@@ -159,6 +179,35 @@ double mvo_log_f_new(const mvo_state* s, int v, const float* x) {
   return -0.5 * (double)D * log(2.0 * M_PI * tau) - 0.5 * q / tau;  /* :346-349 */
 }
 
+/* Count views: plug-in multinomial, leave-one-out for the row's own dish. */
+static double counts_log_f_vk(const mvo_state* s, int v, int k, int i, int loo) {
+  const mvo_csr* cs = &s->csr[v];
+  double tot = 0.0;
+  for (int j = cs->rowptr[i]; j < cs->rowptr[i + 1]; ++j) tot += (double)cs->val[j];
+  const double den = (double)cs->vocab * s->count_beta + (double)cs->ctot[k] - (loo ? tot : 0.0);
+  double lf = 0.0;
+  for (int j = cs->rowptr[i]; j < cs->rowptr[i + 1]; ++j) {
+    const double c = (double)cs->cd[(size_t)k * cs->vocab + cs->col[j]] - (loo ? (double)cs->val[j] : 0.0);
+    lf += (double)cs->val[j] * log((s->count_beta + c) / den);
+  }
+  return lf;
+}
+static double counts_log_f_new(const mvo_state* s, int v, int i) {
+  const mvo_csr* cs = &s->csr[v];
+  double tot = 0.0;
+  for (int j = cs->rowptr[i]; j < cs->rowptr[i + 1]; ++j) tot += (double)cs->val[j];
+  return -tot * log((double)cs->vocab);
+}
+/* log f of ROW i under dish k / a new dish, whatever the kind of view v */
+static double row_log_f_vk(const mvo_state* s, int v, int k, int i, int loo) {
+  if (is_counts(s, v)) return counts_log_f_vk(s, v, k, i, loo);
+  return mvo_log_f_vk(s, v, k, s->x[v] + (size_t)i * s->D[v], loo);
+}
+static double row_log_f_new(const mvo_state* s, int v, int i) {
+  if (is_counts(s, v)) return counts_log_f_new(s, v, i);
+  return mvo_log_f_new(s, v, s->x[v] + (size_t)i * s->D[v]);
+}
+
 static double lse2(double a, double b) {
   if (a == -INFINITY) return b;
   if (b == -INFINITY) return a;
@@ -168,7 +217,7 @@ static double lse2(double a, double b) {
 
 /* log marginal likelihood of a new table in view v for row x whose current table is t0
  * (multiview_utils.cpp:40-69), with the row's own contribution removed. lf[k] is filled for live k. */
-static double log_marginal_new_table(const mvo_state* s, int v, const float* x, int t0, double* lf,
+static double log_marginal_new_table(const mvo_state* s, int v, int i, int t0, double* lf,
                                      double lf_new) {
   const int cap = s->cap;
   const int32_t* l_vk = s->l_vk + (size_t)v * cap;
@@ -184,7 +233,7 @@ static double log_marginal_new_table(const mvo_state* s, int v, const float* x, 
     if (l <= 0) continue;
     total_tables += (double)l;
     K_active++;
-    lf[k] = mvo_log_f_vk(s, v, k, x, k == k0);
+    lf[k] = row_log_f_vk(s, v, k, i, k == k0);
     double w = (double)l - sigma;                         /* :56-57 */
     if (w > 0.0) acc = lse2(acc, log(w) + lf[k]);
   }
@@ -207,9 +256,8 @@ int mvo_row_logweights(const mvo_state* s, int i, double* lw, double* Lvt) {
   }
   double log_new = 0.0;
   for (int v = 0; v < V; ++v) {
-    const float* x = s->x[v] + (size_t)i * s->D[v];
-    double lf_new = mvo_log_f_new(s, v, x);
-    double lm = log_marginal_new_table(s, v, x, t0, lf, lf_new);
+    double lf_new = row_log_f_new(s, v, i);
+    double lm = log_marginal_new_table(s, v, i, t0, lf, lf_new);
     log_new += lm;                                         /* multiview_utils.cpp:119-122 */
     for (int t = 0; t < cap; ++t) {
       int k = s->dish_of[(size_t)v * cap + t];
@@ -277,7 +325,6 @@ int mvo_draw_rows(const mvo_state* s, int32_t* choice, int threads) {
  * increments of earlier births of this sweep. Returns the dish slot; *is_new = 1 for a new dish. */
 static int sample_dish_birth(const mvo_state* s, int v, int b, const int32_t* l_live, double* w_out) {
   const int cap = s->cap;
-  const float* x = s->x[v] + (size_t)b * s->D[v];
   const int t0 = s->table_of[b];
   const int k0 = s->dish_of[(size_t)v * cap + t0];
   const int single = (s->n_t[t0] == 1);
@@ -293,11 +340,11 @@ static int sample_dish_birth(const mvo_state* s, int v, int b, const int32_t* l_
     double w = (double)l - sigma;                          /* :232-233 */
     if (w <= 0.0) continue;
     /* a dish opened earlier in this sweep has no rows in the sweep-start statistics: n = 0 */
-    lwt[k] = log(w) + mvo_log_f_vk(s, v, k, x, (k == k0) && s->n_vk[(size_t)v * cap + k] > 0);
+    lwt[k] = log(w) + row_log_f_vk(s, v, k, b, (k == k0) && s->n_vk[(size_t)v * cap + k] > 0);
     if (lwt[k] > M) M = lwt[k];
   }
   double w_new = alpha + sigma * (double)K_active;          /* :241-243 */
-  lwt[cap] = (w_new > 0.0) ? log(w_new) + mvo_log_f_new(s, v, x) : -INFINITY;
+  lwt[cap] = (w_new > 0.0) ? log(w_new) + row_log_f_new(s, v, b) : -INFINITY;
   if (lwt[cap] > M) M = lwt[cap];
   int pick = -1;
   if (M > -INFINITY) {
@@ -467,6 +514,7 @@ int mvo_hyper_step(mvo_state* s, const double* z_in, const double* u_in, int use
 #define NEXT_Z() (z_in ? z_in[hz++] : mvo_normal(s->seed, s->chain, MVO_DOM_HYPER_NORMAL, 0, s->sweep, (uint64_t)(hz++)))
 #define NEXT_U() (u_in ? u_in[hu++] : mvo_uniform53(s->seed, s->chain, MVO_DOM_HYPER_UNIF, 0, s->sweep, (uint64_t)(hu++)))
   for (int v = 0; v < V; ++v) {                             /* update_tau_v_MH, :211-231 */
+    if (is_counts(s, v)) { (void)NEXT_Z(); (void)NEXT_U(); continue; }   /* no tau; stream positions stay fixed */
     double tau_old = s->tau_v[v];
     if (tau_old <= 0.0) tau_old = K_EPS;
     double log_old = mvo_log_posterior_tau(s, v, tau_old);
@@ -599,6 +647,30 @@ void mvo_stageA_f32(const float* x, int D, const float* m, int cap, float* acc, 
  * (how close the draw was to flipping) — used to grade engines whose weights are tolerance-level. */
 int mvo_stageB_f32_ex(const mvo_params_f32* p, const float* acc, const float* xx, int t0, float uf,
                       float* lw_out, float* margin_out) {
+  return mvo_stageB_f32_mixed(p, NULL, acc, xx, NULL, t0, uf, lw_out, margin_out);
+}
+
+void mvo_stageA_counts_f32(const int32_t* col, const float* val, int nnz, const float* l2t, const int32_t* cdt,
+                           int cap, int t0, float beta, float wbeta_plus_ctot, float* acc, float* acc_loo, float* rowtot) {
+  float tot = 0.0f;
+  for (int j = 0; j < nnz; ++j) tot = tot + val[j];
+  *rowtot = tot;
+  for (int t = 0; t < cap; ++t) {
+    float a = 0.0f;
+    for (int j = 0; j < nnz; ++j) a = fmaf(val[j], l2t[(size_t)col[j] * cap + t], a);
+    acc[t] = a;
+  }
+  const float lden = mvo_log2m(wbeta_plus_ctot - tot);
+  float a = 0.0f;
+  for (int j = 0; j < nnz; ++j) {
+    const float c = (float)cdt[(size_t)col[j] * cap + t0];
+    a = fmaf(val[j], mvo_log2m((beta + c) - val[j]) - lden, a);
+  }
+  *acc_loo = a;
+}
+
+int mvo_stageB_f32_mixed(const mvo_params_f32* p, const int32_t* kind, const float* acc, const float* xx,
+                         const float* acc_loo, int t0, float uf, float* lw_out, float* margin_out) {
   const int V = p->V, cap = p->cap, half = cap / 2;
   float* lw = (float*)malloc(sizeof(float) * (size_t)cap);
   float* term = (float*)malloc(sizeof(float) * (size_t)cap);
@@ -608,8 +680,9 @@ int mvo_stageB_f32_ex(const mvo_params_f32* p, const float* acc, const float* xx
   for (int v = 0; v < V; ++v) {
     const size_t o = (size_t)v * cap;
     const int k0 = p->dish[o + t0];
-    const float A1r = p->A1[o + t0], C1r = p->C1[o + t0];
-    const float nxx = -xx[v];
+    const int counts = (kind != NULL && kind[v] != 0);
+    const float A1r = counts ? 0.0f : p->A1[o + t0], C1r = counts ? acc_loo[v] : p->C1[o + t0];
+    const float nxx = counts ? -0.0f : -xx[v];
     float hmx[2], hs[2];
     for (int h = 0; h < 2; ++h) {
       float mx = MVO_MASKED, s = 0.0f;
@@ -716,6 +789,16 @@ int mvo_make_params(const mvo_state* s, int32_t* dish, float* A, float* C, float
         for (int dd = 0; dd < D; ++dd) mt[dd] = 0.f;
         continue;
       }
+      if (is_counts(s, v)) {          /* acc is log2 f itself: log2 f = 0 + 0.5 * (2 acc - 0) */
+        A[o + t] = 0.5f; C[o + t] = 0.f; A1[o + t] = 0.f; C1[o + t] = 0.f;
+        int rep = 1;
+        for (int t2 = 0; t2 < t; ++t2) if (s->n_t[t2] > 0 && s->dish_of[o + t2] == k) { rep = 0; break; }
+        double w = (double)s->l_vk[o + k] - sigma, w1 = w - 1.0;
+        W[o + t] = (rep && w > 0.0) ? (float)log2(w) : MVO_MASKED;
+        W1[o + t] = (rep && w1 > 0.0) ? (float)log2(w1) : MVO_MASKED;
+        lone[o + t] = (s->l_vk[o + k] == 1);
+        continue;
+      }
       const double n = (double)s->n_vk[o + k];
       double mm = 0.0;
       for (int dd = 0; dd < D; ++dd) {
@@ -743,6 +826,7 @@ int mvo_make_params(const mvo_state* s, int32_t* dish, float* A, float* C, float
     }
     AN[v] = (float)(LOG2E / (2.0 * tau));
     CN[v] = (float)(LOG2E * (-0.5 * (double)D * log(2.0 * M_PI * tau)));
+    if (is_counts(s, v)) { AN[v] = (float)log2((double)s->csr[v].vocab); CN[v] = 0.f; }   /* log2 f_new = -|x| log2 W */
     double wn0 = alpha + (double)K_act * sigma, wn1 = alpha + (double)(K_act - 1) * sigma;
     WN[2 * v] = wn0 > 0.0 ? (float)log2(wn0) : MVO_MASKED;
     WN[2 * v + 1] = wn1 > 0.0 ? (float)log2(wn1) : MVO_MASKED;

@@ -34,6 +34,21 @@ extern "C" {
 #define MVO_NEW (-1)           /* choice value: "open a new table" */
 #define MVO_MASKED (-1.0e30f)  /* FP32 sentinel for a zero-weight option in the log2 domain */
 
+/* A sparse COUNT view in CSR form (no reference counterpart, parity unpinned).  Model: the rows of a
+ * dish are draws from one multinomial over the vocabulary whose probabilities are the plug-in estimate
+ * theta_kw = (beta + c_kw) / (W beta + C_k) from the dish's word counts c_kw (C_k their total), so that
+ *   log f_vk(x) = sum_w x_w log theta_kw            (the multinomial coefficient cancels across k),
+ * with the row's own counts removed first for its own dish, and log f_new(x) = -|x| log W (an empty dish). */
+typedef struct mvo_csr {
+  const int32_t* rowptr;   /* [n+1]; NULL: view v is dense */
+  const int32_t* col;      /* [nnz] in [0, vocab) */
+  const float* val;        /* [nnz] non-negative integer counts */
+  int32_t vocab;
+  int32_t pad;
+  int64_t* cd;             /* [cap*vocab] word counts per dish slot, rebuilt by mvo_rebuild_stats */
+  int64_t* ctot;           /* [cap] their totals */
+} mvo_csr;
+
 typedef struct mvo_state {
   int32_t n;            /* rows held here (all of them: the oracle is single-process) */
   int32_t V;            /* views */
@@ -58,6 +73,8 @@ typedef struct mvo_state {
   uint64_t seed;
   uint32_t chain;
   uint32_t sweep;       /* index of the NEXT sweep to run */
+  const mvo_csr* csr;   /* [V] or NULL (all views dense); a count view has D[v] = 0 */
+  double count_beta;    /* symmetric Dirichlet pseudo-count of the count views */
 } mvo_state;
 
 /* --- Philox (host restatement) ------------------------------------------------------- */
@@ -137,6 +154,17 @@ int mvo_stageB_f32(const mvo_params_f32* p, const float* acc, const float* xx, i
 /* Same, also reporting how close u*total came to a CDF edge (relative to total). */
 int mvo_stageB_f32_ex(const mvo_params_f32* p, const float* acc, const float* xx, int t0, float uf,
                       float* lw_out, float* margin_out);
+/* Same for a mix of dense and count views: kind[v] != 0 marks a count view, for which acc[v][t] is already
+ * log2 f under table t's dish, acc_loo[v] the leave-one-out value for the row's own dish and xx[v] the row's
+ * total count (it only enters the new-dish term).  kind == NULL: all dense. */
+int mvo_stageB_f32_mixed(const mvo_params_f32* p, const int32_t* kind, const float* acc, const float* xx,
+                         const float* acc_loo, int t0, float uf, float* lw_out, float* margin_out);
+/* Stage A of a count view on CUDA cores, restated: acc[t] = sum_j val_j * l2t[col_j*cap + t] as one ascending
+ * fmaf chain over the row's nonzeros; *acc_loo = sum_j val_j * (log2m(beta + cdt[col_j*cap + t0] - val_j) -
+ * log2m(W beta + ctot_t0 - rowtot)) likewise; *rowtot = sum_j val_j.  l2t / cdt are the device's tables:
+ * [vocab][cap] log2 theta and dish word counts as seen from each table slot. */
+void mvo_stageA_counts_f32(const int32_t* col, const float* val, int nnz, const float* l2t, const int32_t* cdt,
+                           int cap, int t0, float beta, float wbeta_plus_ctot, float* acc, float* acc_loo, float* rowtot);
 float mvo_exp2m(float d);
 float mvo_log2m(float s);
 

@@ -49,6 +49,14 @@ class _MvoState(C.Structure):
         ("alpha_v", _f64p), ("sigma_v", _f64p), ("tau_v", _f64p),
         ("alpha_g", C.c_double), ("sigma_g", C.c_double),
         ("seed", C.c_uint64), ("chain", C.c_uint32), ("sweep", C.c_uint32),
+        ("csr", C.c_void_p), ("count_beta", C.c_double),
+    ]
+
+
+class _MvoCsr(C.Structure):
+    _fields_ = [
+        ("rowptr", _i32p), ("col", _i32p), ("val", _f32p), ("vocab", C.c_int32), ("pad", C.c_int32),
+        ("cd", C.POINTER(C.c_int64)), ("ctot", C.POINTER(C.c_int64)),
     ]
 
 
@@ -105,6 +113,9 @@ def lib():
         L.mvo_stageA_f32.argtypes = [_f32p, C.c_int, _f32p, C.c_int, _f32p, _f32p]
         L.mvo_stageB_f32.argtypes = [C.POINTER(_MvoParams), _f32p, _f32p, C.c_int, C.c_float, _f32p]
         L.mvo_stageB_f32_ex.argtypes = [C.POINTER(_MvoParams), _f32p, _f32p, C.c_int, C.c_float, _f32p, _f32p]
+        L.mvo_stageB_f32_mixed.argtypes = [C.POINTER(_MvoParams), _i32p, _f32p, _f32p, _f32p, C.c_int, C.c_float, _f32p, _f32p]
+        L.mvo_stageA_counts_f32.argtypes = [_i32p, _f32p, C.c_int, _f32p, _i32p, C.c_int, C.c_int, C.c_float, C.c_float,
+                                            _f32p, _f32p, _f32p]
         L.mvo_make_params.argtypes = ([C.POINTER(_MvoState), _i32p] + [_f32p] * 6 + [_i32p] + [_f32p] * 6
                                       + [_i32p, _f32p, C.POINTER(_f32p)])
         _lib = L
@@ -164,9 +175,14 @@ def ref():
 class OracleState:
     """Owns the numpy arrays behind one ``mvo_state``."""
 
-    def __init__(self, views, cap, seed=1999, chain=0, row_offset=0, n_global=None):
-        self.views = [np.ascontiguousarray(v, dtype=np.float32).reshape(len(v), -1) for v in views]
-        self.n = int(self.views[0].shape[0])
+    def __init__(self, views, cap, seed=1999, chain=0, row_offset=0, n_global=None, count_beta=0.5):
+        """views: dense arrays [n, D], or CSR count views given as dicts
+        {"rowptr": int32[n+1], "col": int32[nnz], "val": float32[nnz], "vocab": W}."""
+        self.csr = [v if isinstance(v, dict) else None for v in views]
+        n_of = lambda v: len(v["rowptr"]) - 1 if isinstance(v, dict) else len(v)
+        self.n = int(n_of(views[0]))
+        self.views = [np.zeros((self.n, 0), np.float32) if isinstance(v, dict)
+                      else np.ascontiguousarray(v, dtype=np.float32).reshape(len(v), -1) for v in views]
         self.V = len(self.views)
         self.cap = int(cap)
         self.D = np.array([v.shape[1] for v in self.views], dtype=np.int32)
@@ -200,6 +216,28 @@ class OracleState:
         s.tau_v = _ptr(self.tau_v, _f64p)
         s.alpha_g, s.sigma_g = 1.0, 0.6
         s.seed, s.chain, s.sweep = seed, chain, 0
+        s.count_beta = float(count_beta)
+        self.count_beta = float(count_beta)
+        if any(c is not None for c in self.csr):
+            self._csr_arr = (_MvoCsr * self.V)()
+            self._csr_keep = []
+            self.cd, self.ctot = [None] * self.V, [None] * self.V
+            for v, cv in enumerate(self.csr):
+                if cv is None:
+                    continue
+                rp = np.ascontiguousarray(cv["rowptr"], np.int32)
+                col = np.ascontiguousarray(cv["col"], np.int32)
+                val = np.ascontiguousarray(cv["val"], np.float32)
+                W = int(cv["vocab"])
+                self.cd[v] = np.zeros((self.cap, W), np.int64)
+                self.ctot[v] = np.zeros(self.cap, np.int64)
+                self.csr[v] = {"rowptr": rp, "col": col, "val": val, "vocab": W}
+                e = self._csr_arr[v]
+                e.rowptr, e.col, e.val, e.vocab = _ptr(rp, _i32p), _ptr(col, _i32p), _ptr(val, _f32p), W
+                e.cd = self.cd[v].ctypes.data_as(C.POINTER(C.c_int64))
+                e.ctot = self.ctot[v].ctypes.data_as(C.POINTER(C.c_int64))
+            s.csr = C.cast(self._csr_arr, C.c_void_p)
+        self.kind = np.array([0 if c is None else 1 for c in self.csr], np.int32)
         self.c = s
 
     # -- scalar fields live in the struct -------------------------------------------------
@@ -312,6 +350,34 @@ def stageB_f32(pstruct, acc, xx, t0, uf, want_lw=False):
     ch = lib().mvo_stageB_f32(C.byref(pstruct), _ptr(acc, _f32p), _ptr(xx, _f32p), int(t0), C.c_float(float(uf)),
                               _ptr(lw, _f32p) if want_lw else None)
     return (ch, lw) if want_lw else ch
+
+
+def stageB_f32_mixed(pstruct, kind, acc, xx, acc_loo, t0, uf, want_lw=False):
+    """Stage B for a mix of dense and count views (kind[v] = 1: count view)."""
+    kind = np.ascontiguousarray(kind, np.int32)
+    acc = np.ascontiguousarray(acc, np.float32)
+    xx = np.ascontiguousarray(xx, np.float32)
+    acc_loo = np.ascontiguousarray(acc_loo, np.float32)
+    lw = np.empty(pstruct.cap + 1, np.float32) if want_lw else None
+    ch = lib().mvo_stageB_f32_mixed(C.byref(pstruct), _ptr(kind, _i32p), _ptr(acc, _f32p), _ptr(xx, _f32p),
+                                    _ptr(acc_loo, _f32p), int(t0), C.c_float(float(uf)),
+                                    _ptr(lw, _f32p) if want_lw else None, None)
+    return (ch, lw) if want_lw else ch
+
+
+def stageA_counts_f32(col, val, l2t, cdt, t0, beta, wbeta_plus_ctot):
+    """Stage A of one CSR row against the device's tables l2t / cdt ([vocab, cap])."""
+    col = np.ascontiguousarray(col, np.int32)
+    val = np.ascontiguousarray(val, np.float32)
+    l2t = np.ascontiguousarray(l2t, np.float32)
+    cdt = np.ascontiguousarray(cdt, np.int32)
+    cap = l2t.shape[1]
+    acc = np.empty(cap, np.float32)
+    loo, tot = C.c_float(), C.c_float()
+    lib().mvo_stageA_counts_f32(_ptr(col, _i32p), _ptr(val, _f32p), len(col), _ptr(l2t, _f32p), _ptr(cdt, _i32p), cap,
+                                int(t0), C.c_float(float(beta)), C.c_float(float(wbeta_plus_ctot)), _ptr(acc, _f32p),
+                                C.byref(loo), C.byref(tot))
+    return acc, np.float32(loo.value), np.float32(tot.value)
 
 
 def stageB_f32_margin(pstruct, acc, xx, t0, uf):

@@ -42,3 +42,19 @@ def oracle():
     import pyoracle
     pyoracle.lib()
     return pyoracle
+
+
+def make_count_view(n, vocab, z, k_true, seed=0, mean_len=30, concentration=0.05):
+    """Synthetic bag-of-words view: row i draws Poisson(mean_len) tokens from the multinomial of its cluster z[i]
+    (some rows are empty, as in Reuters).  Returns a CSR dict {"rowptr", "col", "val", "vocab"}."""
+    rng = np.random.default_rng(seed)
+    theta = rng.dirichlet(np.full(vocab, concentration), k_true)
+    rp, col, val = [0], [], []
+    for i in range(n):
+        ln = rng.poisson(mean_len) if rng.random() > 0.05 else 0
+        r = rng.multinomial(ln, theta[z[i]])
+        nz = np.nonzero(r)[0]
+        col += list(nz)
+        val += list(r[nz])
+        rp.append(len(col))
+    return {"rowptr": np.array(rp, np.int32), "col": np.array(col, np.int32), "val": np.array(val, np.float32), "vocab": int(vocab)}

@@ -365,3 +365,150 @@ def test_state_dump_and_resume_is_bit_identical():
     for k in ("alpha_v", "sigma_v", "tau_v"):
         np.testing.assert_array_equal(got[k], ref[k], err_msg=k)
     assert got["alpha_g"] == ref["alpha_g"] and got["sigma_g"] == ref["sigma_g"] and got["sweep"] == ref["sweep"]
+
+
+# ---------------------------------------------------------------------------------------------
+# Sparse count views (CSR; SURVEY.md A.3 — no reference counterpart: pinned to the FP64 restatement only)
+# ---------------------------------------------------------------------------------------------
+def _mk_mixed_sampler(views, cap, seed):
+    import mvc_b200
+    n = len(views[0]["rowptr"]) - 1 if isinstance(views[0], dict) else len(views[0])
+    dims = [0 if isinstance(v, dict) else np.asarray(v).reshape(n, -1).shape[1] for v in views]
+    s = mvc_b200.Sampler(n, dims, cap=cap, seed=seed, engine=0, debug_export=True)
+    for v, x in enumerate(views):
+        if isinstance(x, dict):
+            s.upload_view_csr(v, x["rowptr"], x["col"], x["val"], x["vocab"])
+        else:
+            s.upload_view(v, x)
+    return s
+
+
+@pytest.mark.parametrize("layout", ["dense+counts", "counts+counts"])
+def test_count_views_parity(oracle, layout):
+    from conftest import make_count_view
+    n, cap, k_true, seed = 600, 32, 5, 91
+    rng = np.random.default_rng(3)
+    z = rng.integers(0, k_true, n)
+    cv1 = make_count_view(n, 200, z, k_true, seed=1)
+    if layout == "dense+counts":
+        mu = rng.normal(0, 2, (k_true, 4))
+        views = [(mu[z] + rng.normal(0, 1, (n, 4))).astype(np.float32), cv1]
+    else:
+        views = [cv1, make_count_view(n, 64, (z + 1) % k_true, k_true, seed=2, mean_len=8)]
+    V = len(views)
+    kind = np.array([1 if isinstance(v, dict) else 0 for v in views], np.int32)
+    s = _mk_mixed_sampler(views, cap, seed)
+    s.init_state_reference()
+    o = oracle.OracleState(views, cap, seed=seed)
+    o.init_reference()
+    st = s.get_state()
+    np.testing.assert_array_equal(st["table_of"], o.table_of)
+    np.testing.assert_array_equal(st["dish_of"], o.dish_of)
+    L = oracle.lib()
+    births = 0
+    for it in range(8):
+        pre, P = s.get_state(), s.get_params()
+        # the oracle restarts from the device's state: integer statistics must agree exactly
+        o = oracle.OracleState(views, cap, seed=seed)
+        o.alpha_v[:] = pre["alpha_v"]; o.sigma_v[:] = pre["sigma_v"]; o.tau_v[:] = pre["tau_v"]
+        o.alpha_g, o.sigma_g, o.sweep = pre["alpha_g"], pre["sigma_g"], pre["sweep"]
+        o.set_assignment(pre["table_of"], pre["dish_of"])
+        for k in ("n_t", "n_vk", "l_vk"):
+            np.testing.assert_array_equal(pre[k], getattr(o, k), err_msg=k)
+        tabs = {}
+        for v in range(V):
+            if not kind[v]:
+                np.testing.assert_allclose(pre["S1"][v], o.S1[v], rtol=RTOL_STATS, atol=1e-4)
+                o.S1[v][:] = pre["S1"][v]
+                continue
+            l2t, cd, ct = s.get_count_tables(v)
+            tabs[v] = (l2t, cd)
+            W = views[v]["vocab"]
+            for t in range(cap):                                     # dish counts as seen from every table slot: exact
+                k = pre["dish_of"][v][t]
+                want = o.cd[v][k] if k >= 0 else np.zeros(W, np.int64)
+                np.testing.assert_array_equal(cd[:, t], want, err_msg=f"dish counts view {v} table {t}")
+                if k >= 0:
+                    ref = np.log2((o.count_beta + o.cd[v][k]) / (W * o.count_beta + o.ctot[v][k]))
+                    np.testing.assert_allclose(l2t[:, t], ref, rtol=2e-6, atol=1e-6)
+            np.testing.assert_array_equal(pre["sum_y2"][v], o.S2[v])  # token totals per dish: exact integers
+        o.S2[:] = pre["sum_y2"]
+        Q = o.make_params()
+        for k in ("dish", "lone", "single"):
+            np.testing.assert_array_equal(P[k], Q[k], err_msg=k)
+        for k in ("A", "C", "W", "W1", "AN", "CN", "WN", "LD", "LM", "LM1", "LMN"):
+            a, b = P[k].astype(np.float64), Q[k].astype(np.float64)
+            masked = b < -1e29
+            np.testing.assert_array_equal(a[masked] < -1e29, True, err_msg=k)
+            np.testing.assert_allclose(a[~masked], b[~masked], rtol=2e-5, atol=1e-6, err_msg=k)
+        s.sweep(1, do_hyper=True)
+        acc, xx, raw = s.get_debug_rows()
+        loo = s.get_debug_loo()
+        ps = oracle.params_struct(P)
+        worst = 0.0
+        for i in range(n):
+            t0 = pre["table_of"][i]
+            for v in range(V):
+                if kind[v]:                                          # stage A of a count row: bit-exact fmaf chains
+                    cv = views[v]
+                    j0, j1 = cv["rowptr"][i], cv["rowptr"][i + 1]
+                    a, l, tot = oracle.stageA_counts_f32(cv["col"][j0:j1], cv["val"][j0:j1], tabs[v][0], tabs[v][1], t0,
+                                                         o.count_beta, P["C1"][v][t0])
+                    assert np.array_equal(a, acc[i, v]) and tot == xx[i, v], (i, v)
+                    assert l == loo[i, v], (i, v, l, loo[i, v])
+                else:
+                    a, q = oracle.stageA_f32(views[v][i], P["m"][v])
+                    assert np.array_equal(a, acc[i, v]) and q == xx[i, v], (i, v)
+            u = L.mvo_uf(seed, 0, 0, 0, pre["sweep"], i)
+            ch, lw32 = oracle.stageB_f32_mixed(ps, kind, acc[i], xx[i], loo[i], t0, u, want_lw=True)
+            assert ch == raw[i], (i, ch, raw[i])                      # integer draw: bit-exact
+            if i % 5 == 0:                                           # log-weights against the FP64 restatement
+                lw64 = o.row_logweights(i) / np.log(2.0)
+                ok = np.isfinite(lw64)
+                assert np.all(lw32[~ok] < -1e29)
+                denom = np.maximum(1.0, np.abs(lw64[ok]))
+                worst = max(worst, float(np.max(np.abs(lw32[ok] - lw64[ok]) / denom)))
+        assert worst < 2e-5, worst                                   # count rows: sums of ~30 FP32 log2 terms
+        ns, rows, w = o.reseat(raw, want_births=True)
+        births += ns
+        post = s.get_state()
+        for k in ("table_of", "n_t", "dish_of", "n_vk", "l_vk"):
+            np.testing.assert_array_equal(post[k], getattr(o, k), err_msg=k)
+        dns, drows, dw = s.get_debug_births()
+        assert dns == ns and list(drows) == list(rows)
+        if ns:
+            np.testing.assert_allclose(dw, w, rtol=1e-9, atol=1e-12)
+        for v in range(V):
+            if not kind[v]:
+                o.S1[v][:] = post["S1"][v]
+        o.S2[:] = post["sum_y2"]
+        o.hyper_step(use_lgamma=True)
+        np.testing.assert_allclose(post["alpha_v"], o.alpha_v, rtol=1e-9)
+        np.testing.assert_allclose(post["sigma_v"], o.sigma_v, rtol=1e-9)
+        np.testing.assert_allclose(post["tau_v"], o.tau_v, rtol=1e-9)
+        np.testing.assert_allclose([post["alpha_g"], post["sigma_g"]], [o.alpha_g, o.sigma_g], rtol=1e-9)
+    assert births > 0
+    s.close()
+
+
+def test_count_views_recover_planted_clusters():
+    """A chain on a dense + a count view finds the planted partition (ARI), counts stay consistent."""
+    from conftest import make_count_view
+    n, cap, k_true = 3000, 32, 4
+    rng = np.random.default_rng(12)
+    z = rng.integers(0, k_true, n)
+    mu = rng.normal(0, 3, (k_true, 3))
+    views = [(mu[z] + rng.normal(0, 1, (n, 3))).astype(np.float32), make_count_view(n, 300, z, k_true, seed=4)]
+    s = _mk_mixed_sampler(views, cap, seed=7)
+    s.init_state_reference()
+    s.sweep(120, do_hyper=True)
+    st = s.get_state()
+    assert st["n_t"].sum() == n
+    a_dense, _ = s.adjusted_rand_index(0, z)
+    a_counts, _ = s.adjusted_rand_index(1, z)
+    # the dense view separates the clusters; the count view only re-labels through the dishes new tables pick (the
+    # reference never re-samples the dish of an existing table), so its partition is coarser
+    assert a_dense > 0.8 and a_counts > 0.2, (a_dense, a_counts)
+    l2t, cd, ct = s.get_count_tables(1)
+    assert ct.sum() == int(views[1]["val"].sum())
+    s.close()

@@ -146,3 +146,94 @@ def test_reference_init_matches_reference_shape(oracle):
         var = np.var(views[v].astype(np.float64), ddof=1)
         np.testing.assert_allclose(s.tau_v[v], var * 0.25 * 0.01, rtol=1e-12)   # multiview_gibbs.cpp:94
     assert s.alpha_g == 1.0 and s.sigma_g == 0.6 and np.all(s.alpha_v == 1.0) and np.all(s.sigma_v == 0.5)
+
+
+# ---------------------------------------------------------------------------------------------
+# count views (no reference counterpart — the oracle is pinned to the written formula)
+# ---------------------------------------------------------------------------------------------
+def _count_state(oracle, n=120, W=40, cap=32, k_true=3, seed=5):
+    from conftest import make_count_view
+    rng = np.random.default_rng(seed)
+    z = rng.integers(0, k_true, n)
+    cv = make_count_view(n, W, z, k_true, seed=seed, mean_len=12)
+    dense = (rng.normal(0, 2, (k_true, 2))[z] + rng.normal(0, 1, (n, 2))).astype(np.float32)
+    o = oracle.OracleState([dense, cv], cap, seed=seed)
+    o.init_reference()
+    return o, cv, z
+
+
+def test_count_view_loglik_matches_formula(oracle):
+    """log f_vk(x) = sum_w x_w log((beta + c_kw - [own] x_w) / (W beta + C_k - [own] |x|)); log f_new = -|x| log W."""
+    o, cv, _ = _count_state(oracle)
+    W, beta, cap = cv["vocab"], o.count_beta, o.cap
+    dense_rows = np.zeros((o.n, W))
+    for i in range(o.n):
+        j0, j1 = cv["rowptr"][i], cv["rowptr"][i + 1]
+        dense_rows[i, cv["col"][j0:j1]] = cv["val"][j0:j1]
+    # the rebuilt dish counts are the column sums of the rows of each dish
+    lab = o.dish_of[1][o.table_of]
+    for k in range(cap):
+        np.testing.assert_array_equal(o.cd[1][k], dense_rows[lab == k].sum(0).astype(np.int64))
+        assert o.ctot[1][k] == int(dense_rows[lab == k].sum())
+    for i in (0, 7, 33, 119):
+        _, L = o.row_logweights(i, want_L=True)
+        k0 = lab[i]
+        x = dense_rows[i]
+        for t in range(cap):
+            k = o.dish_of[1][t]
+            if k < 0 or o.l_vk[1][k] == 0:
+                continue
+            own = (k == k0)
+            c = o.cd[1][k] - (x if own else 0)
+            den = W * beta + o.ctot[1][k] - (x.sum() if own else 0)
+            want = float((x * np.log((beta + c) / den)).sum())
+            np.testing.assert_allclose(L[1][t], want, rtol=1e-12, atol=1e-12)
+        np.testing.assert_allclose(L[1][cap], -x.sum() * np.log(W), rtol=1e-12, atol=1e-12)
+
+
+def test_count_view_chain_keeps_invariants(oracle):
+    o, cv, _ = _count_state(oracle, n=200)
+    total = int(cv["val"].sum())
+    for _ in range(15):
+        o.sweep_n(1, threads=2, do_hyper=True)
+        assert o.n_t.sum() == o.n and (o.n_vk.sum(1) == o.n).all()
+        assert int(o.ctot[1].sum()) == total and int(o.cd[1].sum()) == total
+        assert o.tau_v[1] == 1.0                                   # a count view has no kernel variance
+
+
+def test_count_view_fp32_mirror_tracks_fp64(oracle):
+    """The FP32 stage-A mirror of a count row (fmaf chains over log2 theta) against the FP64 log f, and the mixed
+    stage-B mirror equals the dense one when no view is a count view."""
+    o, cv, _ = _count_state(oracle)
+    W, beta, cap = cv["vocab"], o.count_beta, o.cap
+    P = o.make_params()
+    # tables as the device would build them: per table slot, the dish's counts and log2 theta
+    cdt = np.zeros((W, cap), np.int32)
+    l2t = np.zeros((W, cap), np.float32)
+    for t in range(cap):
+        k = o.dish_of[1][t]
+        if k >= 0:
+            cdt[:, t] = o.cd[1][k]
+            l2t[:, t] = np.log2((beta + o.cd[1][k]) / (W * beta + o.ctot[1][k]))
+    for i in (3, 50, 101):
+        t0 = o.table_of[i]
+        k0 = o.dish_of[1][t0]
+        j0, j1 = cv["rowptr"][i], cv["rowptr"][i + 1]
+        acc, loo, tot = oracle.stageA_counts_f32(cv["col"][j0:j1], cv["val"][j0:j1], l2t, cdt, t0, beta,
+                                                 np.float32(W * beta + o.ctot[1][k0]))
+        _, L = o.row_logweights(i, want_L=True)
+        assert tot == cv["val"][j0:j1].sum()
+        for t in range(cap):
+            k = o.dish_of[1][t]
+            if k < 0 or o.l_vk[1][k] == 0:
+                continue
+            want = L[1][t] / np.log(2.0)
+            got = loo if k == k0 else acc[t]
+            assert abs(got - want) <= 2e-5 * max(1.0, abs(want)), (i, t, got, want)
+    ps = oracle.params_struct(P)
+    rng = np.random.default_rng(0)
+    acc = rng.normal(0, 1, (2, cap)).astype(np.float32)
+    xx = np.abs(rng.normal(0, 1, 2)).astype(np.float32)
+    a = oracle.stageB_f32(ps, acc, xx, int(o.table_of[0]), 0.37)
+    b = oracle.stageB_f32_mixed(ps, np.zeros(2, np.int32), acc, xx, np.zeros(2, np.float32), int(o.table_of[0]), 0.37)
+    assert a == b
