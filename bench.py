@@ -56,10 +56,12 @@ def parse():
     ap.add_argument("--engine", type=int, default=0, help="0 auto, 1 CUDA-core, 2 tcgen05")
     ap.add_argument("--k-true", type=int, default=CAP, help="planted clusters (default 64 = every table slot in use; "
                     "fewer leaves free slots, so the new-table marginal is evaluated as well)")
-    ap.add_argument("--workload", default="c3", choices=["c3", "c1"],
+    ap.add_argument("--workload", default="c3", choices=["c3", "c1", "c2"],
                     help="c3: the headline configuration (default).  c1: BASELINE configs[0], the reference's own case "
                          "(New_Simulation.R: N=500, two scalar views), reported in sweeps/s with --chains independent "
-                         "chains per GPU; with --impl reference the UNMODIFIED reference sampler (oracle/_ref) is timed")
+                         "chains per GPU; with --impl reference the UNMODIFIED reference sampler (oracle/_ref) is timed.  "
+                         "c2: BASELINE configs[1]/[4], three sparse count views with the shapes of Reuters-21578 (synthetic "
+                         "topics; the .sgm files do not travel to the GPU box), --chains chains per GPU")
     ap.add_argument("--chains", type=int, default=8, help="c1: independent chains per GPU, one stream each")
     ap.add_argument("--no-hyper", action="store_true")
     ap.add_argument("--role-profile", action="store_true", help="print the tcgen05 kernel's per-role wait cycles (debug)")
@@ -167,6 +169,81 @@ def c1_views(n=500, seed=SEED):
     v1 = np.concatenate([rng.normal(3, 1.3, h), rng.normal(-3, 1.3, n - h)])
     v2 = np.concatenate([rng.normal(0, 1.3, q), rng.normal(-5, 1.3, h), rng.normal(5, 1.3, n - q - h)])
     return [v1, v2]
+
+
+def run_c2(args, out):
+    """Reuters-shaped sparse count views (BASELINE configs[1]; configs[4] with --chains 8) in sweeps/s."""
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    from mvc_b200 import reuters
+    views, z = reuters.synthetic_like_reuters(seed=SEED)
+    n, steps, cap = len(z), args.steps, 64
+    nnz = [int(len(v["col"])) for v in views]
+    workload = ("C2: three CSR count views shaped like Reuters-21578 (N=%d; vocab 13000/5700/445; nnz %s), cap %d"
+                % (n, "/".join(map(str, nnz)), cap))
+    if args.impl == "reference":
+        if rank != 0:
+            return
+        sys.path.insert(0, str(ROOT / "oracle"))
+        import pyoracle as po
+        threads = os.cpu_count() or 1
+        o = po.OracleState(views, cap, seed=SEED)
+        o.init_reference()
+        k = max(1, min(steps, 3))
+        t0 = time.perf_counter()
+        o.sweep_n(k, threads=threads, do_hyper=True)
+        dt = time.perf_counter() - t0
+        line = {"impl": "reference", "metric": "gibbs_sweeps_per_s", "value": k / dt, "unit": "sweeps/s", "n_gpus": args.gpus,
+                "steps": k, "warmup": 0, "ms_per_step": 1e3 * dt / k, "higher_is_better": True, "scaling": "weak",
+                "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": {"workload": workload + ", one chain"},
+                "cpu_baseline": {"value": k / dt, "unit": "sweeps/s", "cores": threads, "kind": "port",
+                                 "sample": "%d FP64 sweeps of oracle/mv_oracle.c (the reference has no count likelihood)" % k},
+                "e2e": {"value": k / dt, "unit": "sweeps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+        print(json.dumps(line), file=out)
+        return
+    import torch
+    import mvc_b200
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the sweep has no CPU path")
+    torch.cuda.set_device(local_rank)
+    chains = []
+    for ch in range(args.chains):
+        s = mvc_b200.Sampler(n, [0, 0, 0], cap=cap, seed=SEED, chain=rank * args.chains + ch, device=local_rank, engine=1)
+        for v, x in enumerate(views):
+            s.upload_view_csr(v, x["rowptr"], x["col"], x["val"], x["vocab"])
+        s.init_state_reference()
+        chains.append(s)
+    block = 5
+    def run(k):
+        done = 0
+        while done < k:
+            b = min(block, k - done)
+            for s in chains:
+                s.sweep(b, True)
+            done += b
+        for s in chains:
+            s.sync()
+    run(args.warmup)
+    l0 = sum(s.launch_count() for s in chains)
+    t0 = time.perf_counter()
+    run(steps)
+    dt = time.perf_counter() - t0
+    launches = sum(s.launch_count() for s in chains) - l0
+    prof = chains[0].profile_sweep(True)
+    ari = [chains[0].adjusted_rand_index(v, z)[0] for v in range(3)]
+    live = [int((s.get_state(with_rows=False)["n_t"] > 0).sum()) for s in chains]
+    for s in chains:
+        s.close()
+    if rank == 0:
+        line = {"metric": "gibbs_sweeps_per_s", "value": world * args.chains * steps / dt, "unit": "sweeps/s", "n_gpus": world,
+                "steps": steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / steps, "higher_is_better": True,
+                "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+                "config": {"workload": workload + ", %d independent chains per GPU, CUDA-core engine, hyper step on" % args.chains,
+                           "timing": "wall clock around the launches of all chains and their final synchronisation"},
+                "kernel_ms_one_chain": prof, "gpu_launches": int(launches), "tables_live": live,
+                "ari_vs_planted_topics_chain0": ari}
+        print(json.dumps(line), file=out)
 
 
 def run_c1(args, out):
@@ -286,6 +363,8 @@ def main():
 def _main(args, out):
     if args.workload == "c1":
         return run_c1(args, out)
+    if args.workload == "c2":
+        return run_c2(args, out)
     if args.impl == "reference":
         return run_reference(args, out)
 
