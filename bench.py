@@ -171,6 +171,17 @@ def c1_views(n=500, seed=SEED):
     return [v1, v2]
 
 
+def c2_start(n, cap, chain=0):
+    """Start of a count-view chain: cap/2 random tables, each with its own dish in every view.  (From the reference's
+    T=4, K=2 start a count-view chain cannot split: a new dish starts at the uniform prior predictive W^-|x|, which
+    never beats an existing dish in a 13k-word vocabulary; starting over-split lets the sampler merge instead.)"""
+    rng = np.random.default_rng([SEED, chain])
+    tab = rng.integers(0, cap // 2, n).astype(np.int32)
+    dish = np.full((3, cap), -1, np.int32)
+    dish[:, :cap // 2] = np.arange(cap // 2)
+    return tab, dish
+
+
 def run_c2(args, out):
     """Reuters-shaped sparse count views (BASELINE configs[1]; configs[4] with --chains 8) in sweeps/s."""
     rank = int(os.environ.get("RANK", "0"))
@@ -188,7 +199,8 @@ def run_c2(args, out):
         import pyoracle as po
         threads = os.cpu_count() or 1
         o = po.OracleState(views, cap, seed=SEED)
-        o.init_reference()
+        tab0, dish0 = c2_start(n, cap)
+        o.set_assignment(tab0, dish0)
         k = max(1, min(steps, 3))
         t0 = time.perf_counter()
         o.sweep_n(k, threads=threads, do_hyper=True)
@@ -212,7 +224,8 @@ def run_c2(args, out):
         s = mvc_b200.Sampler(n, [0, 0, 0], cap=cap, seed=SEED, chain=rank * args.chains + ch, device=local_rank, engine=1)
         for v, x in enumerate(views):
             s.upload_view_csr(v, x["rowptr"], x["col"], x["val"], x["vocab"])
-        s.init_state_reference()
+        tab0, dish0 = c2_start(n, cap, chain=rank * args.chains + ch)
+        s.set_state(tab0, dish0, [1.0] * 3, [0.5] * 3, [1.0] * 3, 1.0, 0.6)
         chains.append(s)
     block = 5
     def run(k):
