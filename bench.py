@@ -39,7 +39,7 @@ N_ROWS = 1_000_000
 DIMS = [64, 64, 64]
 CAP = 64
 SEED = 1999
-NCU_TRAFFIC_BYTES = 782.6e6     # measured DRAM traffic of one k_draw_tc launch at N=1M (algorithmic: 776 MB)
+NCU_TRAFFIC_BYTES = 792.9e6     # measured DRAM traffic of one k_draw_tc launch at N=1M (algorithmic: 776 MB + 12 MB of stored squared norms)
 METRIC = "obs_x_view_x_K_updates_per_s"
 UNIT = "updates/s"
 
@@ -47,7 +47,7 @@ UNIT = "updates/s"
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=300)
+    ap.add_argument("--steps", type=int, default=1000)
     ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--rows", type=int, default=N_ROWS, help="customers per GPU (weak) / in total (strong); default: the named config")
@@ -124,7 +124,7 @@ class ClockSampler(threading.Thread):
                     self.rows.append([x.strip() for x in out.split(",")])
             except Exception:
                 pass
-            time.sleep(0.1)
+            time.sleep(0.02)
 
     def summary(self):
         sm = [float(r[1]) for r in self.rows if len(r) > 8 and r[1].replace(".", "").isdigit()]
@@ -342,7 +342,7 @@ def run_reference(args, out):
     if rank != 0:
         return
     threads = os.cpu_count() or 1
-    rows = args.cpu_rows or 16384
+    rows = args.cpu_rows or 262144
     for _ in range(min(args.warmup, 1)):
         cpu_port_throughput(min(rows, 2048), threads)
     vals, dts = [], []
@@ -458,7 +458,7 @@ def _main(args, out):
     roofline = {"bound": "hbm", "kernel": "likelihood+draw", "achieved": achieved, "peak": peak, "unit": "GB/s",
                 "frac": achieved / peak, "traffic": NCU_TRAFFIC_BYTES * n_local / N_ROWS if args.engine in (0, 2, 3) else None,
                 "traffic_source": "ncu --set full, dram__bytes_read.sum + dram__bytes_write.sum of k_draw_tc at N=1M "
-                                  "(profiles/r01_ncu_draw_tc.md), scaled to this shard", "peak_source": peak_src,
+                                  "(profiles/r01_ncu_final.md), scaled to this shard", "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": alg_bytes, "kernel_ms": kern}
     if args.role_profile and rank == 0:
         pr = s.get_debug_prof(n_ctas=256)
@@ -487,7 +487,7 @@ def _main(args, out):
             s2.upload_view(v, views_pinned[v].numpy())
         s2.set_state(tab, dish, hyp["alpha_v"], hyp["sigma_v"], hyp["tau_v"], hyp["alpha_g"], hyp["sigma_g"])
         s2.sweep(k_e2e, do_hyper)
-        out = s2.get_state(with_rows=True)
+        final2 = s2.get_state(with_rows=True)
         barrier()
         dt = time.perf_counter() - t0
         tt = torch.tensor([dt], device="cuda")
@@ -500,12 +500,12 @@ def _main(args, out):
                "d2h_bytes_per_step": d2h / k_e2e, "sweeps": k_e2e, "seconds": dt,
                "note": "one chain run through the C ABI with host buffers: H2D of all views (pinned) + table_of, K sweeps, "
                        "D2H of table_of; wall clock, device allocation included; bytes are per sweep (total / K)"}
-        assert int(out["n_t"].sum()) == n_total
+        assert int(final2["n_t"].sum()) == n_total
         s2.close()
 
     cpu = None
     if rank == 0 and not args.no_cpu_baseline:
-        rows = args.cpu_rows or 4096
+        rows = args.cpu_rows or 524288          # ~10 s of one core
         v1, dt1 = cpu_port_throughput(rows, 1)
         cpu = {"value": v1, "unit": UNIT, "cores": 1, "kind": "port",
                "sample": f"one FP64 sweep of oracle/mv_oracle.c over the first {rows} customers of the same workload, "

@@ -92,11 +92,11 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
       "{\n\t"
       ".reg .pred p;\n\t"
       "WAIT_LOOP:\n\t"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
-      "@p bra DONE;\n\t"
-      "bra WAIT_LOOP;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1, %2;\n\t"   // %2: suspend-time hint (ns): a waiting warp
+      "@p bra DONE;\n\t"                                                 //     sleeps in hardware instead of polling
+      "bra WAIT_LOOP;\n\t"                                               //     away the epilogue's issue slots
       "DONE:\n\t"
-      "}\n" ::"r"(bar), "r"(parity)
+      "}\n" ::"r"(bar), "r"(parity), "r"(2000u)
       : "memory");
 }
 // mbar_wait that also adds the cycles spent waiting to *acc when profiling is on (debug_export & 2).
