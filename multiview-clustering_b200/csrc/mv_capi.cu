@@ -159,6 +159,7 @@ int ensure_layout(mvg_handle* h) {
     if (c.kind[v]) {
       const size_t cells = (size_t)c.vocab[v] * cap;
       A(c.cnt_t[v], cells); A(c.cnt_d[v], cells); A(c.l2t[v], cells);
+      A(c.cnt_acc[v], N * cap); A(c.cnt_loo[v], N);
     }
 #undef A
   h->layout_done = true;
@@ -200,7 +201,7 @@ int rebuild_pipeline(mvg_handle* h, int32_t flags, cudaEvent_t* marks /* 4 event
   MVG_CUDA(h, launch_finalize(h->c, flags, h->stream));
   if (h->c.n_count_views) {          // count views: word counts by the final seating, then the log2 theta tables
     MVG_CUDA(h, launch_counts_rebuild(h->c, h->stream));
-    h->launches += 2 * h->c.n_count_views;
+    h->launches += 2;
   }
   if (marks) MVG_CUDA(h, cudaEventRecord(marks[3], h->stream));
   h->launches += 3;
@@ -211,7 +212,7 @@ int launch_draw(mvg_handle* h) {
   if (h->engine == MVG_ENGINE_TCGEN05 || h->engine == MVG_ENGINE_TCGEN05_FAST)
     MVG_CUDA(h, launch_draw_tc(h->c, h->tc_maps, h->engine == MVG_ENGINE_TCGEN05_FAST, h->stream));
   else MVG_CUDA(h, launch_draw_simt(h->c, h->stream));
-  h->launches += 1;
+  h->launches += 1 + ((h->engine == MVG_ENGINE_SIMT && h->c.n_count_views) ? 1 : 0);
   return MVG_OK;
 }
 

@@ -23,7 +23,16 @@ __global__ void k_rowtotals(const int32_t* __restrict__ rowptr, const float* __r
   out[i] = tot;
 }
 
-__global__ void k_counts_scatter(const Ctx c, const int v) {
+// blockIdx.y-th count view of the chain
+__device__ __forceinline__ int nth_count_view(const Ctx& c, int nth) {
+  int v = 0;
+  for (; v < c.V; ++v)
+    if (c.kind[v] && nth-- == 0) break;
+  return v;
+}
+
+__global__ void k_counts_scatter(const Ctx c) {
+  const int v = nth_count_view(c, blockIdx.y);
   const int lane = threadIdx.x & 31;
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = (gridDim.x * blockDim.x) >> 5;
   const int32_t* __restrict__ rp = c.rowptr[v];
@@ -36,9 +45,11 @@ __global__ void k_counts_scatter(const Ctx c, const int v) {
   }
 }
 
-__global__ void k_counts_tables(const Ctx c, const int v) {
+__global__ void k_counts_tables(const Ctx c) {
+  const int v = nth_count_view(c, blockIdx.y);
   __shared__ int32_t s_dish[64];
   __shared__ double s_den[64];
+  __shared__ unsigned long long s_mask[64];      // the table slots serving the same dish as slot t
   const int cap = c.cap;
   if (threadIdx.x < cap) {
     const int k = c.dish_of[v * cap + threadIdx.x];
@@ -47,21 +58,105 @@ __global__ void k_counts_tables(const Ctx c, const int v) {
     s_den[threadIdx.x] = (k >= 0) ? (double)c.vocab[v] * (double)c.count_beta + c.S2k[v * cap + k] : 1.0;
   }
   __syncthreads();
+  if (threadIdx.x < cap) {
+    unsigned long long m = 0ull;
+    const int k = s_dish[threadIdx.x];
+    if (k >= 0) for (int t2 = 0; t2 < cap; ++t2) if (s_dish[t2] == k) m |= 1ull << t2;
+    s_mask[threadIdx.x] = m;
+  }
+  __syncthreads();
   const size_t total = (size_t)c.vocab[v] * cap;
   for (size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (size_t)gridDim.x * blockDim.x) {
     const int t = (int)(e % cap);
     const size_t w = e / cap;
-    const int k = s_dish[t];
     int32_t cd = 0;
     float l2 = 0.0f;
-    if (k >= 0) {
+    if (s_dish[t] >= 0) {
       const int32_t* row = c.cnt_t[v] + w * cap;
-      for (int t2 = 0; t2 < cap; ++t2) if (s_dish[t2] == k) cd += row[t2];
+      cd = row[t];                                              // usually the dish's only table
+      for (unsigned long long m = s_mask[t] & ~(1ull << t); m; m &= m - 1ull) cd += row[__ffsll((long long)m) - 1];
       l2 = (float)log2(((double)c.count_beta + (double)cd) / s_den[t]);
     }
     c.cnt_d[v][e] = cd;
     c.l2t[v][e] = l2;
   }
+}
+
+// Stage A of a count view: log2 f of every row under every table slot's dish, acc[i][t] = sum_j x_j l2t[col_j][t], and
+// the leave-one-out value under the row's own dish.  One WARP per row (a thread per row would make the longest row
+// everybody's wait): lane l owns tables l*PER .. l*PER+PER-1, the row's nonzeros are read 32 at a time and broadcast,
+// eight table rows are in flight at once; per table the chain is ascending over the nonzeros, the order
+// oracle/mv_oracle.c:mvo_stageA_counts_f32 restates.  The table is feature-major: one nonzero reads CAP consecutive
+// floats (the SpMM "CSR row x dense feature-major table" of SURVEY.md A.3).
+template <int CAP>
+__global__ void __launch_bounds__(512) k_counts_loglik(const Ctx c) {
+  const int v = nth_count_view(c, blockIdx.y);
+  constexpr int PER = CAP / 32;
+  const int lane = threadIdx.x & 31;
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = (gridDim.x * blockDim.x) >> 5;
+  const int32_t* __restrict__ rp = c.rowptr[v];
+  const int32_t* __restrict__ colv = c.col[v];
+  const float* __restrict__ valv = c.val[v];
+  const float* __restrict__ l2t = c.l2t[v];
+  const int32_t* __restrict__ cdt = c.cnt_d[v];
+  const TableParam* __restrict__ tp = c.tparam + v * CAP;
+  for (int row = warp; row < c.n_rows; row += nwarps) {
+    const int j0 = rp[row], j1 = rp[row + 1];
+    const int t0 = c.table_cur[row];
+    // leave-one-out under the own dish: counts and total with this row removed (TableParam::C1 of a count view
+    // carries W beta + the dish's token total)
+    const float lden = log2m(__fadd_rn(tp[t0].C1, -c.xx[(size_t)v * c.xx_stride + row]));
+    float a[PER];
+#pragma unroll
+    for (int q = 0; q < PER; ++q) a[q] = 0.0f;
+    float aloo = 0.0f;
+    for (int jb = j0; jb < j1; jb += 32) {
+      const int j = jb + lane;
+      const bool has = j < j1;
+      const float xv_l = has ? __ldg(valv + j) : 0.0f;
+      const int col_l = has ? __ldg(colv + j) : 0;
+      float term_l = 0.0f;
+      if (has) {
+        const float cown = (float)__ldg(cdt + (size_t)col_l * CAP + t0);
+        term_l = __fadd_rn(log2m(__fadd_rn(__fadd_rn(c.count_beta, cown), -xv_l)), -lden);
+      }
+      const int cnt = min(32, j1 - jb);
+      for (int u0 = 0; u0 < cnt; u0 += 8) {
+        float lv[8][PER], xs[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+          const int src = min(u0 + u, cnt - 1);
+          const int cl = __shfl_sync(0xffffffffu, col_l, src);
+          xs[u] = __shfl_sync(0xffffffffu, xv_l, src);
+          const float* p = l2t + (size_t)cl * CAP + lane * PER;
+          if (PER == 2) { const float2 t2 = __ldg(reinterpret_cast<const float2*>(p)); lv[u][0] = t2.x; lv[u][PER - 1] = t2.y; }
+          else lv[u][0] = __ldg(p);
+        }
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+          if (u0 + u < cnt) {                                  // warp-uniform
+#pragma unroll
+            for (int q = 0; q < PER; ++q) a[q] = __fmaf_rn(xs[u], lv[u][q], a[q]);
+            aloo = __fmaf_rn(xs[u], __shfl_sync(0xffffffffu, term_l, u0 + u), aloo);
+          }
+        }
+      }
+    }
+    float* dst = c.cnt_acc[v] + (size_t)row * CAP + lane * PER;
+#pragma unroll
+    for (int q = 0; q < PER; ++q) dst[q] = a[q];
+    if (lane == 0) c.cnt_loo[v][row] = aloo;
+  }
+}
+
+cudaError_t launch_counts_loglik(const Ctx& c, cudaStream_t s) {
+  if (!c.n_count_views) return cudaSuccess;
+  int blocks = (c.n_rows + 15) / 16;               // 16 warps per block
+  if (blocks > 148 * 4) blocks = 148 * 4;
+  const dim3 grid(blocks, c.n_count_views);         // all count views in one launch
+  if (c.cap == 64) k_counts_loglik<64><<<grid, 512, 0, s>>>(c);
+  else k_counts_loglik<32><<<grid, 512, 0, s>>>(c);
+  return cudaGetLastError();
 }
 
 cudaError_t launch_rowtotals(const int32_t* rowptr, const float* val, float* out, int n, cudaStream_t s) {
@@ -70,18 +165,21 @@ cudaError_t launch_rowtotals(const int32_t* rowptr, const float* val, float* out
 }
 
 cudaError_t launch_counts_rebuild(const Ctx& c, cudaStream_t s) {
+  if (!c.n_count_views) return cudaSuccess;
+  size_t max_cells = 0;
   for (int v = 0; v < c.V; ++v) {
     if (!c.kind[v]) continue;
     const size_t cells = (size_t)c.vocab[v] * c.cap;
+    max_cells = cells > max_cells ? cells : max_cells;
     cudaError_t e = cudaMemsetAsync(c.cnt_t[v], 0, sizeof(int32_t) * cells, s);
     if (e != cudaSuccess) return e;
-    int blocks = (c.n_rows + 7) / 8;                 // 8 warps per block, one row per warp per step
-    if (blocks > 148 * 8) blocks = 148 * 8;
-    k_counts_scatter<<<blocks, 256, 0, s>>>(c, v);
-    int tb = (int)((cells + 255) / 256);
-    if (tb > 148 * 16) tb = 148 * 16;
-    k_counts_tables<<<tb, 256, 0, s>>>(c, v);
   }
+  int blocks = (c.n_rows + 7) / 8;                 // 8 warps per block, one row per warp per step
+  if (blocks > 148 * 4) blocks = 148 * 4;
+  k_counts_scatter<<<dim3(blocks, c.n_count_views), 256, 0, s>>>(c);
+  int tb = (int)((max_cells + 255) / 256);
+  if (tb > 148 * 8) tb = 148 * 8;
+  k_counts_tables<<<dim3(tb, c.n_count_views), 256, 0, s>>>(c);
   return cudaGetLastError();
 }
 

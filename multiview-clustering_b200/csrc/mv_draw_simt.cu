@@ -15,12 +15,18 @@ namespace mv {
 constexpr int kSimtThreads = 128;
 constexpr int kSimtDChunk = 128;   // columns of m staged per pass
 
+// Bytes of the first shared-memory region: the staged means of a dense view.
+template <int CAP>
+__host__ __device__ inline size_t simt_first_region_bytes(const Ctx& c) {
+  const int dch_max = (c.Dsum < kSimtDChunk) ? (c.Dsum > 0 ? c.Dsum : 1) : kSimtDChunk;   // upper bound on any view's chunk
+  return (sizeof(float) * (size_t)CAP * (size_t)dch_max + 15) & ~(size_t)15;
+}
+
 template <int CAP, bool VEC4>
 __global__ void __launch_bounds__(kSimtThreads, 2) k_draw_simt(const Ctx c) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   float* s_m = reinterpret_cast<float*>(smem_raw);                       // [CAP][dch]
-  const int dch_max = (c.Dsum < kSimtDChunk) ? (c.Dsum > 0 ? c.Dsum : 1) : kSimtDChunk;   // upper bound on any view's chunk
-  PairHot* s_hot = reinterpret_cast<PairHot*>(smem_raw + sizeof(float) * (size_t)CAP * (size_t)dch_max);   // [CAP/2]
+  PairHot* s_hot = reinterpret_cast<PairHot*>(smem_raw + simt_first_region_bytes<CAP>(c));                 // [CAP/2]
   TableCold* s_cold = reinterpret_cast<TableCold*>(s_hot + CAP / 2);                                        // [CAP]
   __shared__ TableMass s_tm[CAP];
   __shared__ __align__(16) float s_lm[CAP];
@@ -50,35 +56,19 @@ __global__ void __launch_bounds__(kSimtThreads, 2) k_draw_simt(const Ctx c) {
         stage_view_params(c.tparam + v * CAP, CAP, s_hot, s_cold, tid, kSimtThreads);
         if (tid == 0) s_vp = c.vparam[v];
         __syncthreads();
-        const int32_t* __restrict__ colv = c.col[v];
-        const float* __restrict__ valv = c.val[v];
-        const float* __restrict__ l2t = c.l2t[v];
-        const int32_t* __restrict__ cdt = c.cnt_d[v];
-        const int j0 = c.rowptr[v][rowc], j1 = c.rowptr[v][rowc + 1];
-        const int t0 = c.table_cur[rowc];
+        // k_counts_loglik (mv_counts.cu, one warp per row) left the CAP log2 f values of every customer and its
+        // leave-one-out value in global memory (L2-resident at Reuters size); here: the common per-customer epilogue
         const float rowtot = c.xx[(size_t)v * c.xx_stride + rowc];
         float acc[CAP];
-#pragma unroll
-        for (int t = 0; t < CAP; ++t) acc[t] = 0.0f;
-        // leave-one-out under the own dish: counts and total with this row removed (TableParam::C1 of a count
-        // view carries W beta + the dish's token total)
-        const float lden = log2m(__fadd_rn(s_cold[t0].C1, -rowtot));
-        float acc_loo = 0.0f;
-        for (int j = j0; j < j1; ++j) {
-          const float xv = __ldg(valv + j);
-          const size_t w = (size_t)__ldg(colv + j) * CAP;
-          const float4* __restrict__ lt = reinterpret_cast<const float4*>(l2t + w);
+        {
+          const float4* __restrict__ src = reinterpret_cast<const float4*>(c.cnt_acc[v] + (size_t)rowc * CAP);
 #pragma unroll
           for (int q = 0; q < CAP / 4; ++q) {
-            const float4 l4 = __ldg(lt + q);
-            acc[4 * q] = __fmaf_rn(xv, l4.x, acc[4 * q]);
-            acc[4 * q + 1] = __fmaf_rn(xv, l4.y, acc[4 * q + 1]);
-            acc[4 * q + 2] = __fmaf_rn(xv, l4.z, acc[4 * q + 2]);
-            acc[4 * q + 3] = __fmaf_rn(xv, l4.w, acc[4 * q + 3]);
+            const float4 a4 = __ldg(src + q);
+            acc[4 * q] = a4.x; acc[4 * q + 1] = a4.y; acc[4 * q + 2] = a4.z; acc[4 * q + 3] = a4.w;
           }
-          const float cown = (float)__ldg(cdt + w + t0);
-          acc_loo = __fmaf_rn(xv, __fadd_rn(log2m(__fadd_rn(__fadd_rn(c.count_beta, cown), -xv)), -lden), acc_loo);
         }
+        const float acc_loo = __ldg(c.cnt_loo[v] + rowc);
         if ((c.debug_export & 1) && live) {
           float* da = c.dbg_acc + ((size_t)row * c.V + v) * CAP;
 #pragma unroll
@@ -161,8 +151,7 @@ static cudaError_t launch_simt_cap(const Ctx& c, cudaStream_t s) {
   bool vec4 = true;
   for (int v = 0; v < c.V; ++v)
     if (!c.kind[v] && ((c.D[v] & 3) != 0 || (reinterpret_cast<uintptr_t>(c.x[v]) & 15) != 0)) vec4 = false;
-  const int dch = (c.Dsum < kSimtDChunk) ? (c.Dsum > 0 ? c.Dsum : 1) : kSimtDChunk;
-  const size_t smem = sizeof(float) * (size_t)CAP * dch + sizeof(TableParam) * CAP;
+  const size_t smem = simt_first_region_bytes<CAP>(c) + sizeof(TableParam) * CAP;
   const int n_tiles = (c.n_rows + kSimtThreads - 1) / kSimtThreads;
   int dev = 0, sms = 148;
   cudaGetDevice(&dev);
@@ -183,6 +172,10 @@ static cudaError_t launch_simt_cap(const Ctx& c, cudaStream_t s) {
 
 cudaError_t launch_draw_simt(const Ctx& c, cudaStream_t s) {
   if (c.n_rows <= 0) return cudaSuccess;
+  if (c.n_count_views) {                       // stage A of the count views: its own high-occupancy kernel
+    cudaError_t e = launch_counts_loglik(c, s);
+    if (e != cudaSuccess) return e;
+  }
   switch (c.cap) {
     case 32: return launch_simt_cap<32>(c, s);
     case 64: return launch_simt_cap<64>(c, s);

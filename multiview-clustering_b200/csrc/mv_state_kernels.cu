@@ -54,6 +54,17 @@ __global__ void __launch_bounds__(kPackThreads, 1) k_pack(const Ctx c) {
   const int nfree = c.gparam->nfree;
   int32_t* cand_row = pkt_i32(c, c.rank, c.pkt.off_cand_row);
   int32_t* cand_t0 = pkt_i32(c, c.rank, c.pkt.off_cand_t0);
+  if (nfree == 0) {
+    // No free table slot at sweep start: the new-table option had no weight (capacity rule), so no row can have
+    // drawn it and the birth mask is all zero — nothing to scan, nothing to compact.
+    if (tid == 0) {
+      int32_t* hdr = pkt_i32(c, c.rank, c.pkt.off_hdr);
+      hdr[0] = 0; hdr[1] = 0; hdr[2] = c.rank; hdr[3] = 0;
+      *reinterpret_cast<int64_t*>(hdr + 4) = c.row_offset;
+      hdr[6] = 0; hdr[7] = 0;
+    }
+    return;
+  }
   const int per = (c.n_chunks + kPackThreads - 1) / kPackThreads;
   const int lo = min(tid * per, c.n_chunks), hi = min(lo + per, c.n_chunks);
   int cnt = 0;
