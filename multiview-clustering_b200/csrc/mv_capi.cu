@@ -143,7 +143,7 @@ int ensure_layout(mvg_handle* h) {
   A(c.n_t, cap); A(c.dish_of, V * cap); A(c.n_vk, V * cap); A(c.l_vk, V * cap);
   A(c.S1t, cap * dsum); A(c.S2t, V * cap); A(c.S1k, cap * dsum); A(c.S2k, V * cap);
   A(c.hyp, 3 * V + 2); A(c.sweep, 1); A(c.status, 4);
-  A(c.tparam, V * cap); A(c.vparam, V); A(c.tmass, cap); A(c.gparam, 1);
+  A(c.tparam, V * cap); A(c.vparam, V); A(c.tmass, cap); A(c.gparam, 1); A(c.tsame, V * cap);
   A(c.mean, cap * dsum); A(c.mean_hi, cap * dsum); A(c.mean_lo, cap * dsum);
   A(c.partial_f, (size_t)c.stat_ctas * (cap * dsum + V * cap)); A(c.partial_n, (size_t)c.stat_ctas * cap);
   A(c.birth_lf, cap * V * (cap + 1));

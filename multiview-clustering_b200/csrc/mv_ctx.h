@@ -86,6 +86,7 @@ struct Ctx {
   ViewParam* vparam;        // [V]
   TableMass* tmass;         // [cap]
   GlobalParam* gparam;      // [1]
+  unsigned long long* tsame; // [V][cap] bit t2 of entry (v, t): table slot t2 serves the same dish as slot t in view v
   float* mean;              // [cap*Dsum]
   float* mean_hi;           // tensor-core engine: TF32-representable part of mean
   float* mean_lo;           //   and the remainder

@@ -198,6 +198,7 @@ struct HalfEpilogue {
   // per-view state
   float mx, s, nxx, A1r, C1r;
   int k0, lone0;
+  uint32_t samemask;     // USE_MASK engines: bit j = table tbase + j serves the customer's own dish (set by the caller)
 
   // tm: all cap table masses, lm: the same LM values as a plain float array (vector loads); this
   // object covers tables [tbase, tbase + HALF).
@@ -229,21 +230,26 @@ struct HalfEpilogue {
   // hoth/coldh: the arrays offset to this half's first table.  acc[j] = x . m_{tbase + BASE + j} (consumed).
   // WITH_NEW = false: no table slot is free, so a new table has no weight (capacity rule) and the
   // per-view marginal over the dishes — the whole log-sum-exp — is not needed; only lw is updated.
-  template <int BASE, bool SINGLE, bool WITH_NEW>
+  // USE_MASK: the same-dish test comes from `samemask` (one bit per table, precomputed per (view, own table) by the
+  // finalize kernel) instead of a compare against the loaded dish of every table: same values, fewer instructions.
+  template <int BASE, bool SINGLE, bool WITH_NEW, bool USE_MASK>
   __device__ __forceinline__ void chunk_impl(const PairHot* __restrict__ hoth, const TableCold* __restrict__ coldh,
                                              float (&acc)[kEpiChunk]) {
     float2 term[kEpiChunk / 2];
     float c0 = kMasked, c1 = kMasked;
-    const float2 two = splat2(2.0f), nxx2 = splat2(nxx), a1r2 = splat2(A1r), c1r2 = splat2(C1r);
+    const float2 two = splat2(2.0f), nxx2 = splat2(nxx);
 #pragma unroll
     for (int p = 0; p < kEpiChunk / 2; ++p) {
       const float4 qa = reinterpret_cast<const float4*>(&hoth[BASE / 2 + p])[0];   // A0 A1 C0 C1
-      const float4 qb = reinterpret_cast<const float4*>(&hoth[BASE / 2 + p])[1];   // W0 W1 dish0 dish1
+      float4 qb = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (WITH_NEW || !USE_MASK) qb = reinterpret_cast<const float4*>(&hoth[BASE / 2 + p])[1];   // W0 W1 dish0 dish1
       const float2 e = ffma2(two, make_float2(acc[2 * p], acc[2 * p + 1]), nxx2);
       const float2 Lg = ffma2(make_float2(qa.x, qa.y), e, make_float2(qa.z, qa.w));
-      const float2 Ls = ffma2(a1r2, e, c1r2);
-      const bool same0 = (__float_as_int(qb.z) == k0), same1 = (__float_as_int(qb.w) == k0);
-      const float2 L = make_float2(same0 ? Ls.x : Lg.x, same1 ? Ls.y : Lg.y);
+      const bool same0 = USE_MASK ? ((samemask >> (BASE + 2 * p)) & 1u) != 0u : (__float_as_int(qb.z) == k0);
+      const bool same1 = USE_MASK ? ((samemask >> (BASE + 2 * p + 1)) & 1u) != 0u : (__float_as_int(qb.w) == k0);
+      float2 L = Lg;                                   // leave-one-out only where the dish is the customer's own
+      if (same0) L.x = __fmaf_rn(A1r, e.x, C1r);
+      if (same1) L.y = __fmaf_rn(A1r, e.y, C1r);
       lw2[BASE / 2 + p] = fadd2(lw2[BASE / 2 + p], L);
       if (!WITH_NEW) continue;
       float2 w = make_float2(qb.x, qb.y);
@@ -270,12 +276,12 @@ struct HalfEpilogue {
     s = __fadd_rn(s, __fadd_rn(__fadd_rn(pa.x, pa.y), __fadd_rn(pb.x, pb.y)));
   }
 
-  template <int BASE, bool WITH_NEW = true>
+  template <int BASE, bool WITH_NEW = true, bool USE_MASK = false>
   __device__ __forceinline__ void view_chunk(const PairHot* __restrict__ hoth, const TableCold* __restrict__ coldh,
                                              float (&acc)[kEpiChunk]) {
-    if (!WITH_NEW) chunk_impl<BASE, false, false>(hoth, coldh, acc);
-    else if (any_single) chunk_impl<BASE, true, true>(hoth, coldh, acc);
-    else chunk_impl<BASE, false, true>(hoth, coldh, acc);
+    if (!WITH_NEW) chunk_impl<BASE, false, false, USE_MASK>(hoth, coldh, acc);
+    else if (any_single) chunk_impl<BASE, true, true, USE_MASK>(hoth, coldh, acc);
+    else chunk_impl<BASE, false, true, USE_MASK>(hoth, coldh, acc);
   }
 
   // All chunks of this half from an array of HALF dot products (CUDA-core engine).

@@ -67,7 +67,8 @@ struct SmemLayout {
   static constexpr int tm_off = tp_off + kMaxTcViews * 64 * (int)sizeof(TableParam);   // per view: PairHot[32] then TableCold[64]
   static constexpr int vp_off = tm_off + 64 * (int)sizeof(TableMass);
   static constexpr int lm_off = vp_off + kMaxTcViews * (int)sizeof(ViewParam);              // float[64]: LM of every table
-  static constexpr int ex_off = lm_off + 64 * (int)sizeof(float);
+  static constexpr int same_off = lm_off + 64 * (int)sizeof(float);                         // u64[V][64]: same-dish table masks
+  static constexpr int ex_off = same_off + kMaxTcViews * 64 * 8;
   static constexpr int bar_off = ex_off + 4 * kExFields * kTileRows * (int)sizeof(float);   // ex: [pair][half][field][row]
   static constexpr int n_bars = 2 * kRawStages + 2 * kLoStages + 2 * kDStages + 1;
   static constexpr int misc_off = bar_off + n_bars * 8;
@@ -234,7 +235,7 @@ __device__ __forceinline__ void epi_chunk(HalfEpilogue<32, FAST>& epi, const Pai
 #pragma unroll
     for (int t = 0; t < 16; ++t) da[t] = ch[t];
   }
-  epi.template view_chunk<BASE, WITH_NEW>(hoth, coldh, ch);
+  epi.template view_chunk<BASE, WITH_NEW, true>(hoth, coldh, ch);
 }
 
 template <bool FAST>
@@ -265,6 +266,8 @@ __global__ void __launch_bounds__(kThreads, 1) k_draw_tc(const Ctx c, const __gr
     stage_view_params(c.tparam + v * 64, 64, reinterpret_cast<PairHot*>(s_tp + v * 2048),
                       reinterpret_cast<TableCold*>(s_tp + v * 2048 + 1024), tid, kThreads);
   for (int i = tid; i < 64; i += kThreads) { s_tm[i] = c.tmass[i]; s_lm[i] = c.tmass[i].LM; }
+  unsigned long long* s_same = reinterpret_cast<unsigned long long*>(smem + SmemLayout::same_off);
+  for (int i = tid; i < V * 64; i += kThreads) s_same[i] = c.tsame[i];
   if (tid < V) s_vp[tid] = c.vparam[tid];
   if (tid == 0) {
     const GlobalParam g = *c.gparam;
@@ -488,6 +491,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_draw_tc(const Ctx c, const __gr
         const PairHot* hot = reinterpret_cast<const PairHot*>(s_tp + v * 2048);
         const TableCold* cold = reinterpret_cast<const TableCold*>(s_tp + v * 2048 + 1024);
         epi.view_begin(hot, cold, xx);
+        epi.samemask = (uint32_t)(s_same[v * 64 + epi.t0] >> (32 * hf));
         if ((c.debug_export & 1) && live && hf == 0) c.dbg_xx[(size_t)row * V + v] = xx;
         uint32_t ua[16], ub[16];
         tmem_ld_16(taddr, ua);

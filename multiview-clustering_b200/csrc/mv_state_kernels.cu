@@ -1036,6 +1036,7 @@ __global__ void __launch_bounds__(kFinThreads, 1) k_finalize(const Ctx c, const 
       q.lone = (S.l_live[v][k] == 1);
     }
     c.tparam[i] = q;
+    c.tsame[i] = (k >= 0) ? S.tmask[v][k] : 0ull;
   }
   // The three small blocks below are independent of the loop above and of each other: each gets its own warps
   // (12, 13-14, 15) so that their FP64 log chains run side by side instead of back to back on warp 0.

@@ -383,16 +383,24 @@ def _mk_mixed_sampler(views, cap, seed):
     return s
 
 
-@pytest.mark.parametrize("layout", ["dense+counts", "counts+counts"])
+@pytest.mark.parametrize("layout", ["dense+counts", "counts+counts", "c4-mix"])
 def test_count_views_parity(oracle, layout):
     from conftest import make_count_view
     n, cap, k_true, seed = 600, 32, 5, 91
+    if layout == "c4-mix":
+        n, cap = 260, 64                                             # BASELINE configs[3]'s view mix: 4 dense (D = 64) + 4 CSR
     rng = np.random.default_rng(3)
     z = rng.integers(0, k_true, n)
     cv1 = make_count_view(n, 200, z, k_true, seed=1)
     if layout == "dense+counts":
         mu = rng.normal(0, 2, (k_true, 4))
         views = [(mu[z] + rng.normal(0, 1, (n, 4))).astype(np.float32), cv1]
+    elif layout == "c4-mix":
+        views = []
+        for v in range(4):
+            mu = rng.normal(0, 2, (k_true, 64))
+            views.append((mu[z] + rng.normal(0, 1, (n, 64))).astype(np.float32))
+            views.append(make_count_view(n, 300 + 50 * v, z, k_true, seed=10 + v, mean_len=20))
     else:
         views = [cv1, make_count_view(n, 64, (z + 1) % k_true, k_true, seed=2, mean_len=8)]
     V = len(views)
@@ -406,7 +414,7 @@ def test_count_views_parity(oracle, layout):
     np.testing.assert_array_equal(st["dish_of"], o.dish_of)
     L = oracle.lib()
     births = 0
-    for it in range(8):
+    for it in range(3 if layout == "c4-mix" else 8):
         pre, P = s.get_state(), s.get_params()
         # the oracle restarts from the device's state: integer statistics must agree exactly
         o = oracle.OracleState(views, cap, seed=seed)
