@@ -520,3 +520,65 @@ def test_count_views_recover_planted_clusters():
     l2t, cd, ct = s.get_count_tables(1)
     assert ct.sum() == int(views[1]["val"].sum())
     s.close()
+
+
+def test_independent_chains_coclustering_agrees_with_cpu_restatement(oracle):
+    """BASELINE configs[4] in miniature: independent chains (chain id in the Philox key) of a count + dense data set,
+    several per GPU on their own streams; the pooled co-clustering (posterior similarity) matrix of the GPU chains
+    against the one of CPU chains run by the FP64 restatement from the same starts."""
+    from conftest import make_count_view
+    import mvc_b200
+    n, cap, k_true, n_chains, burn, keep = 300, 32, 4, 4, 40, 30
+    rng = np.random.default_rng(21)
+    z = rng.integers(0, k_true, n)
+    mu = rng.normal(0, 2.5, (k_true, 2))
+    views = [make_count_view(n, 120, z, k_true, seed=3, mean_len=25), (mu[z] + rng.normal(0, 1, (n, 2))).astype(np.float32)]
+    starts = []
+    for ch in range(n_chains):
+        r = np.random.default_rng([5, ch])
+        tab = r.integers(0, cap // 2, n).astype(np.int32)
+        dish = np.full((2, cap), -1, np.int32)
+        dish[:, :cap // 2] = np.arange(cap // 2)
+        starts.append((tab, dish))
+    # GPU chains, interleaved launches
+    chains = []
+    for ch in range(n_chains):
+        s = mvc_b200.Sampler(n, [0, 2], cap=cap, seed=77, chain=ch, engine=0)
+        s.upload_view_csr(0, views[0]["rowptr"], views[0]["col"], views[0]["val"], views[0]["vocab"])
+        s.upload_view(1, views[1])
+        s.set_state(starts[ch][0], starts[ch][1], [1.0, 1.0], [0.5, 0.5], [1.0, 0.5], 1.0, 0.6)
+        s.coclustering_begin(1)                 # dishes of the dense view
+        chains.append(s)
+    for s in chains:
+        s.sweep(burn, True)
+    for _ in range(keep):
+        for s in chains:
+            s.sweep(1, True)
+            s.coclustering_accumulate()
+    P_gpu = np.zeros((n, n))
+    ari_gpu = []
+    for s in chains:
+        cnt, ns = s.coclustering_get()
+        assert ns == keep
+        P_gpu += cnt / float(keep)
+        ari_gpu.append(s.adjusted_rand_index(1, z)[0])
+        s.close()
+    P_gpu /= n_chains
+    # CPU chains (FP64 restatement of the same synchronous sampler, same Philox keys)
+    P_cpu = np.zeros((n, n))
+    ari_cpu = []
+    from sklearn.metrics import adjusted_rand_score
+    for ch in range(n_chains):
+        o = oracle.OracleState(views, cap, seed=77, chain=ch)
+        o.tau_v[:] = [1.0, 0.5]
+        o.set_assignment(*starts[ch])
+        o.sweep_n(burn, threads=4, do_hyper=True)
+        for _ in range(keep):
+            o.sweep_n(1, threads=4, do_hyper=True)
+            lab = o.dish_of[1][o.table_of]
+            P_cpu += (lab[:, None] == lab[None, :]) / float(keep)
+        ari_cpu.append(adjusted_rand_score(z, o.dish_of[1][o.table_of]))
+    P_cpu /= n_chains
+    assert np.abs(P_gpu - P_cpu).mean() < 0.05, np.abs(P_gpu - P_cpu).mean()
+    assert abs(np.mean(ari_gpu) - np.mean(ari_cpu)) < 0.15, (ari_gpu, ari_cpu)
+    assert np.mean(ari_gpu) > 0.6, ari_gpu
