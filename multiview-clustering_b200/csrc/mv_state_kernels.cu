@@ -396,13 +396,15 @@ struct FinShared {
 
 constexpr int kFinSharedBytes = (int)((sizeof(FinShared) + 15) & ~(size_t)15);
 
-__device__ __noinline__ double dev_normal(const Ctx& c, uint32_t sweep, int idx) {
-  const U4 r = stream_block(c.seed, c.chain, kDomHyperNormal, 0, sweep, (uint64_t)idx);
+// (The out-of-line helpers below take scalars and pointers, never `const Ctx&`: taking the address of the kernel
+// parameter makes every thread copy the whole 1.5 KB struct into its local memory at kernel start.)
+__device__ __noinline__ double dev_normal(uint64_t seed, uint32_t chain, uint32_t sweep, int idx) {
+  const U4 r = stream_block(seed, chain, kDomHyperNormal, 0, sweep, (uint64_t)idx);
   const double u1 = uniform_f64_from(r.x, r.y), u2 = uniform_f64_from(r.z, r.w);
   return sqrt(-2.0 * fin_log(u1)) * cos(6.283185307179586476925286766559 * u2);
 }
-__device__ __noinline__ double dev_unif(const Ctx& c, uint32_t sweep, int idx) {
-  const U4 r = stream_block(c.seed, c.chain, kDomHyperUnif, 0, sweep, (uint64_t)idx);
+__device__ __noinline__ double dev_unif(uint64_t seed, uint32_t chain, uint32_t sweep, int idx) {
+  const U4 r = stream_block(seed, chain, kDomHyperUnif, 0, sweep, (uint64_t)idx);
   return uniform_f64_from(r.x, r.y);
 }
 
@@ -429,8 +431,8 @@ __device__ __forceinline__ double reflect_unit(double value) {      // :110-122
 //   sum_{m=1}^{c-1} fin_log(m-sigma) = fin_lgamma(c-sigma) - fin_lgamma(1-sigma),
 // the per-cluster terms are evaluated by the block in parallel and one thread per set adds them in
 // ascending cluster order (the order of oracle/mv_oracle.c:eppf_core).  Block-uniform call.
-__device__ __noinline__ void eppf_batch(const Ctx& c, FinShared& S, const double* alpha, const double* sigma) {
-  const int tid = threadIdx.x, cap = c.cap, V = c.V;
+__device__ __noinline__ void eppf_batch(const int cap, const int V, FinShared& S, const double* alpha, const double* sigma) {
+  const int tid = threadIdx.x;
   const int lane = tid & 31, wid = tid >> 5;
   const int nsets = 2 * (V + 1);
   __syncthreads();
@@ -500,31 +502,16 @@ __device__ __noinline__ void eppf_batch(const Ctx& c, FinShared& S, const double
   __syncthreads();
 }
 
-__device__ __noinline__ double log_posterior_tau(const Ctx& c, const FinShared& S, int v, double tau) {  // :176-209
-  if (tau <= 0.0) return -INFINITY;
-  const double lg = fin_log(2.0 * kPi * tau);      // same value in every term of the reference's loop
-  const double Dd = (double)c.D[v];
-  double loglik = 0.0;
-  for (int k = 0; k < c.cap; ++k) {
-    const int n_k = S.n_vk[v][k];
-    if (n_k == 0) continue;
-    loglik += -0.5 * (double)n_k * Dd * lg - 0.5 * (S.sse[v][k] / tau);
-  }
-  const double a_tau = 2.0, b_tau = 1.0;                                   // :133-134
-  return loglik + (a_tau * fin_log(b_tau) - fin_lgamma(a_tau) - (a_tau + 1.0) * fin_log(tau) - b_tau / tau);
-}
 
 // log predictive density of x (views concatenated, FP32) under dish k of view v, optionally with
 // x removed from the dish first (multiview_utils.cpp:307-338 in closed form, per coordinate).
-__device__ __noinline__ double log_f_dish(const Ctx& c, const FinShared& S, int v, int k, const float* x, bool loo,
-                             double tau) {
-  const int D = c.D[v];
-  const double* S1 = c.S1k + (size_t)c.cap * c.doff[v] + (size_t)k * D;
-  const double n = (double)S.n_vk[v][k] - (loo ? 1.0 : 0.0);
+__device__ __noinline__ double log_f_dish(const int D, const double* __restrict__ S1, const double n_vk, const float* x,
+                                          bool loo, double tau) {
+  const double n = n_vk - (loo ? 1.0 : 0.0);
   const double var = tau * (tau + n + 1.0) / (tau + n);
   double dist = 0.0;
   for (int dd = 0; dd < D; ++dd) {
-    const double xv = (double)x[c.doff[v] + dd];
+    const double xv = (double)x[dd];                    // x: the candidate's coordinates in THIS view
     const double s1 = S1[dd] - (loo ? xv : 0.0);
     const double diff = xv - s1 / (tau + n);
     dist += diff * diff;
@@ -535,17 +522,17 @@ __device__ __noinline__ double log_f_dish(const Ctx& c, const FinShared& S, int 
 // Count view: log f of local ROW `row` under dish k from the sweep-start dish counts (cnt_d is indexed by TABLE
 // slot: tk is any table serving dish k, or -1 for a dish without tables = empty), FP64
 // (oracle/mv_oracle.c:counts_log_f_vk).
-__device__ __noinline__ double log_f_dish_counts(const Ctx& c, const FinShared& S, int v, int k, int tk, int row, bool loo) {
-  const int32_t* rp = c.rowptr[v];
-  const double beta = (double)c.count_beta;
+__device__ __noinline__ double log_f_dish_counts(const int32_t* __restrict__ rp, const int32_t* __restrict__ col,
+                                                 const float* __restrict__ val, const int32_t* __restrict__ cnt_d,
+                                                 const int cap, const double wbeta, const double beta, const double ctot_k,
+                                                 const int tk, const int row, const bool loo) {
   double tot = 0.0;
-  for (int j = rp[row]; j < rp[row + 1]; ++j) tot += (double)c.val[v][j];
-  const double ctot = (tk >= 0) ? S.s2k_start[v][k] : 0.0;
-  const double den = (double)c.vocab[v] * beta + ctot - (loo ? tot : 0.0);
+  for (int j = rp[row]; j < rp[row + 1]; ++j) tot += (double)val[j];
+  const double den = wbeta + ((tk >= 0) ? ctot_k : 0.0) - (loo ? tot : 0.0);
   double lf = 0.0;
   for (int j = rp[row]; j < rp[row + 1]; ++j) {
-    const double x = (double)c.val[v][j];
-    const double cd = (tk >= 0) ? (double)c.cnt_d[v][(size_t)c.col[v][j] * c.cap + tk] : 0.0;
+    const double x = (double)val[j];
+    const double cd = (tk >= 0) ? (double)cnt_d[(size_t)col[j] * cap + tk] : 0.0;
     lf += x * fin_log((beta + cd - (loo ? x : 0.0)) / den);
   }
   return lf;
@@ -577,8 +564,8 @@ __global__ void __launch_bounds__(kFinThreads, 1) k_finalize(const Ctx c, const 
   // now, while the others wait on the packet loads below, instead of in the middle of the serial MH chain.
   if ((flags & kFinHyper) && tid >= kFinThreads - 64) {
     for (int i = tid - (kFinThreads - 64); i < 2 * (3 * V + 2); i += 64) {
-      if (i < 3 * V + 2) S.rn[i] = dev_normal(c, sweep, i);
-      else S.lu[i - (3 * V + 2)] = fin_log(dev_unif(c, sweep, i - (3 * V + 2)));
+      if (i < 3 * V + 2) S.rn[i] = dev_normal(c.seed, c.chain, sweep, i);
+      else S.lu[i - (3 * V + 2)] = fin_log(dev_unif(c.seed, c.chain, sweep, i - (3 * V + 2)));
     }
   }
   // ---- A. rank-ordered sums of the shards' packets ------------------------------------------
@@ -670,7 +657,9 @@ __global__ void __launch_bounds__(kFinThreads, 1) k_finalize(const Ctx c, const 
           val = -tot * fin_log((double)c.vocab[v]);
         } else {
           const int t0 = pkt_i32(c, S.cand_g[b], c.pkt.off_cand_t0)[S.cand_j[b]];
-          val = log_f_dish_counts(c, S, v, k, S.table_of_dish[v][k], row, (k == S.dish[v][t0]) && S.n_vk[v][k] > 0);
+          val = log_f_dish_counts(c.rowptr[v], c.col[v], c.val[v], c.cnt_d[v], cap, (double)c.vocab[v] * (double)c.count_beta,
+                                  (double)c.count_beta, S.s2k_start[v][k], S.table_of_dish[v][k], row,
+                                  (k == S.dish[v][t0]) && S.n_vk[v][k] > 0);
         }
       } else if (k == cap) {   // new dish: N(x; 0, tau)   (multiview_utils.cpp:340-350)
         const int D = c.D[v];
@@ -679,7 +668,8 @@ __global__ void __launch_bounds__(kFinThreads, 1) k_finalize(const Ctx c, const 
         val = -0.5 * (double)D * fin_log(2.0 * kPi * tau_v[v]) - 0.5 * q / tau_v[v];
       } else {
         const int t0 = pkt_i32(c, S.cand_g[b], c.pkt.off_cand_t0)[S.cand_j[b]];
-        val = log_f_dish(c, S, v, k, x, (k == S.dish[v][t0]) && S.n_vk[v][k] > 0, tau_v[v]);
+        val = log_f_dish(c.D[v], c.S1k + (size_t)cap * c.doff[v] + (size_t)k * c.D[v], (double)S.n_vk[v][k], x + c.doff[v],
+                         (k == S.dish[v][t0]) && S.n_vk[v][k] > 0, tau_v[v]);
       }
       c.birth_lf[idx] = val;
     }
@@ -932,7 +922,7 @@ __global__ void __launch_bounds__(kFinThreads, 1) k_finalize(const Ctx c, const 
       s_alpha[2 * j] = a_old; s_alpha[2 * j + 1] = a_prop;
       s_sigma[2 * j] = S.hyp[is]; s_sigma[2 * j + 1] = S.hyp[is];
     }
-    eppf_batch(c, S, s_alpha, s_sigma);
+    eppf_batch(cap, V, S, s_alpha, s_sigma);
     stamp(11);
     double s_old = 0.0, s_prop = 0.0;
     if (is_level) {
@@ -945,7 +935,7 @@ __global__ void __launch_bounds__(kFinThreads, 1) k_finalize(const Ctx c, const 
       s_alpha[2 * j] = S.hyp[ia]; s_alpha[2 * j + 1] = S.hyp[ia];
       s_sigma[2 * j] = s_old; s_sigma[2 * j + 1] = s_prop;
     }
-    eppf_batch(c, S, s_alpha, s_sigma);
+    eppf_batch(cap, V, S, s_alpha, s_sigma);
     stamp(12);
     if (is_level) {
       const double lpo = (s_old <= kEps || s_old >= 1.0 - kEps) ? -INFINITY : S.eppf[2 * j] + log_prior_sigma(s_old);
