@@ -358,7 +358,7 @@ cudaError_t launch_reduce(const Ctx& c, cudaStream_t s) {
 // =============================================================================================
 // k_finalize
 // =============================================================================================
-constexpr int kFinThreads = 512;
+constexpr int kFinThreads = 1024;
 constexpr int kMaxCap = 64;
 constexpr int kMaxWorld = 16;
 
