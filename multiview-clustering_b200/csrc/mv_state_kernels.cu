@@ -392,6 +392,7 @@ struct FinShared {
   double hyp[3 * kMaxViews + 2];
   double rn[3 * kMaxViews + 2];           // the sweep's standard normals of the hyper step, by stream index
   double lu[3 * kMaxViews + 2];           // log of its uniforms
+  double warm[2];                         // sink of the instruction-cache warm-up calls
 };
 
 constexpr int kFinSharedBytes = (int)((sizeof(FinShared) + 15) & ~(size_t)15);
@@ -567,6 +568,9 @@ __global__ void __launch_bounds__(kFinThreads, 1) k_finalize(const Ctx c, const 
       if (i < 3 * V + 2) S.rn[i] = dev_normal(c.seed, c.chain, sweep, i);
       else S.lu[i - (3 * V + 2)] = fin_log(dev_unif(c.seed, c.chain, sweep, i - (3 * V + 2)));
     }
+    // ... and touch the other out-of-line FP64 routines of the MH chain, so that their code is in the instruction
+    // cache before the chain needs it
+    if (tid == kFinThreads - 1) { S.warm[0] = fin_lgamma(2.5 + (double)sweep); S.warm[1] = fin_exp(-1.0 - (double)V); }
   }
   // ---- A. rank-ordered sums of the shards' packets ------------------------------------------
   for (int t = tid; t < cap; t += kFinThreads) {
@@ -627,6 +631,15 @@ __global__ void __launch_bounds__(kFinThreads, 1) k_finalize(const Ctx c, const 
   stamp(0);
   // ---- B. births: candidates in global row order, the first nfree are seated -----------------
   if (flags & kFinReseat) {
+    if (tid == 0) {                       // usually no customer drew a new table: then the whole section is skipped
+      int n = 0;
+      for (int g = 0; g < c.world; ++g) n += pkt_i32(c, g, c.pkt.off_hdr)[0];
+      S.ncand_total = n;
+      if (n == 0 && c.debug_export) *c.dbg_nseated = 0;
+    }
+    __syncthreads();
+  }
+  if ((flags & kFinReseat) && S.ncand_total > 0) {
     if (tid == 0) {
       int nf = 0;
       for (int t = 0; t < cap; ++t) if (!S.alive_start[t]) S.free_slots[nf++] = t;
