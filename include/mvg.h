@@ -161,6 +161,15 @@ int mvg_comm_attach(mvg_handle* h, void* nccl_comm);
 int mvg_comm_unique_id(void* unique_id_128);
 int mvg_comm_init_rank(mvg_handle* h, const void* unique_id_128);
 
+/* Peer-memory transport for the same exchange (optional, one node): instead of ncclAllGather every rank stores its
+ * packet straight into its peers' receive buffers over NVLink and raises a flag there; k_finalize's input is assembled
+ * from the local buffer (csrc/mv_exchange.cu).  Setup, after the views are known: every rank calls mvg_comm_p2p_export
+ * (a 64-byte cudaIpcMemHandle_t comes back), the caller all-gathers the handles in rank order and gives the world x 64
+ * bytes to mvg_comm_p2p_attach on every rank.  Without it (or with world = 1) the NCCL path is used. */
+int mvg_prepare(mvg_handle* h);                       /* fix the layout now (all views uploaded/attached) */
+int mvg_comm_p2p_export(mvg_handle* h, void* ipc_handle_64);
+int mvg_comm_p2p_attach(mvg_handle* h, const void* all_handles);
+
 /* ---- inspection (tests, profiling) ----------------------------------------------------- */
 /* The FP32 parameter block of the NEXT sweep, as the likelihood kernel will read it; pointers
  * are host buffers, NULL skips.  Layouts are those of oracle/mv_oracle.h:mvo_params_f32. */

@@ -11,7 +11,7 @@ from pathlib import Path
 HERE = Path(__file__).resolve().parent
 CSRC = HERE / "csrc"
 OUT = HERE / "mvc_b200" / "libmvg_b200.so"
-SOURCES = ["mv_capi.cu", "mv_draw_simt.cu", "mv_draw_tc.cu", "mv_state_kernels.cu", "mv_stats_tile.cu", "mv_summary.cu", "mv_counts.cu"]
+SOURCES = ["mv_capi.cu", "mv_draw_simt.cu", "mv_draw_tc.cu", "mv_state_kernels.cu", "mv_stats_tile.cu", "mv_summary.cu", "mv_counts.cu", "mv_exchange.cu"]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
          "-Xcompiler", "-fPIC", "--fmad=true", "-Xptxas", "-v"]

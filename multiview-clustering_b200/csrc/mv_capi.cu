@@ -87,6 +87,11 @@ struct mvg_handle {
   int64_t sweep_graph_launches[2]{};
   bool graphs_ok = true;
   int64_t sweeps_issued = 0;
+  // peer-memory exchange (optional; ncclAllGather otherwise)
+  unsigned char* xrecv = nullptr;    // this rank's receive buffer (cudaMalloc, exported through CUDA IPC)
+  XchgPeers xpeers{};                // every rank's receive buffer as mapped here ([rank] = xrecv)
+  bool xp2p = false;
+  uint32_t xseq = 0;
 };
 
 namespace {
@@ -187,6 +192,12 @@ int ensure_layout(mvg_handle* h) {
 
 int exchange(mvg_handle* h) {
   if (h->c.world == 1) return MVG_OK;
+  if (h->xp2p) {                     // packets pushed straight into the peers' memory over NVLink
+    h->xseq += 1;
+    MVG_CUDA(h, launch_exchange_p2p(h->c, h->xpeers, h->xrecv, h->xseq, h->stream));
+    h->launches += 1;
+    return MVG_OK;
+  }
   if (!h->comm) return fail(h, MVG_ESTATE, "world > 1 but no NCCL communicator attached");
   unsigned char* base = h->c.packet;
   int r = g_nccl.AllGather(base + (size_t)h->c.rank * h->c.pkt.bytes, base, (size_t)h->c.pkt.bytes, /*ncclChar*/ 0,
@@ -229,7 +240,8 @@ int check_status(mvg_handle* h) {
   if (st[0] != 0) {
     MVG_CUDA(h, cudaMemsetAsync(h->c.status, 0, sizeof(st), h->stream));
     return fail(h, MVG_EINVAL, "device-side invariant violated, flags=" + std::to_string(st[0]) +
-                                   " (1: no free dish slot for a birth, 2: live table without a dish, 4: customers lost in the statistics rebuild)");
+                                   " (1: no free dish slot for a birth, 2: live table without a dish, 4: customers lost in the statistics rebuild, "
+                                   "8: a peer's packet never arrived in the peer-memory exchange)");
   }
   return MVG_OK;
 }
@@ -303,6 +315,10 @@ int mvg_destroy(mvg_handle* h) {
   cudaSetDevice(h->cfg.device);
   if (h->stream) cudaStreamSynchronize(h->stream);
   if (h->comm && h->comm_owned && g_nccl.CommDestroy) g_nccl.CommDestroy(h->comm);
+  if (h->xp2p)
+    for (int g = 0; g < h->c.world; ++g)
+      if (g != h->c.rank && h->xpeers.recv[g]) cudaIpcCloseMemHandle(h->xpeers.recv[g]);
+  if (h->xrecv) cudaFree(h->xrecv);
   for (auto& g : h->sweep_graph) if (g) cudaGraphExecDestroy(g);
   for (void* p : h->owned) cudaFree(p);
   for (void* p : h->view_owned) if (p) cudaFree(p);
@@ -676,6 +692,51 @@ int mvg_comm_init_rank(mvg_handle* h, const void* unique_id_128) {
   if (r != 0) return fail(h, MVG_ENCCL, std::string("ncclCommInitRank: ") + (g_nccl.GetErrorString ? g_nccl.GetErrorString(r) : "?"));
   h->comm = comm;
   h->comm_owned = true;
+  return MVG_OK;
+}
+
+int mvg_prepare(mvg_handle* h) {
+  if (!h) return MVG_EINVAL;
+  MVG_CUDA(h, cudaSetDevice(h->cfg.device));
+  return ensure_layout(h);
+}
+
+int mvg_comm_p2p_export(mvg_handle* h, void* ipc_handle_64) {
+  if (!h || !ipc_handle_64) return MVG_EINVAL;
+  if (h->c.world < 2) return fail(h, MVG_EINVAL, "peer exchange needs world > 1");
+  MVG_CUDA(h, cudaSetDevice(h->cfg.device));
+  int rc = ensure_layout(h);                       // the packet size depends on the views
+  if (rc != MVG_OK) return rc;
+  if (!h->xrecv) {
+    const size_t bytes = (size_t)2 * h->c.world * h->c.pkt.bytes + (size_t)2 * h->c.world * sizeof(uint32_t) + 256;
+    void* q = nullptr;
+    if (cudaMalloc(&q, bytes) != cudaSuccess) return fail(h, MVG_ENOMEM, "cudaMalloc: exchange buffer");
+    MVG_CUDA(h, cudaMemset(q, 0, bytes));
+    h->xrecv = static_cast<unsigned char*>(q);
+  }
+  static_assert(sizeof(cudaIpcMemHandle_t) == 64, "CUDA IPC handle size");
+  cudaIpcMemHandle_t hd;
+  MVG_CUDA(h, cudaIpcGetMemHandle(&hd, h->xrecv));
+  std::memcpy(ipc_handle_64, &hd, 64);
+  return MVG_OK;
+}
+
+int mvg_comm_p2p_attach(mvg_handle* h, const void* all_handles) {
+  if (!h || !all_handles) return MVG_EINVAL;
+  if (!h->xrecv) return fail(h, MVG_ESTATE, "call mvg_comm_p2p_export first");
+  if (h->c.world > 16) return fail(h, MVG_EUNSUPPORTED, "peer exchange supports at most 16 ranks");
+  MVG_CUDA(h, cudaSetDevice(h->cfg.device));
+  for (int g = 0; g < h->c.world; ++g) {
+    if (g == h->c.rank) { h->xpeers.recv[g] = h->xrecv; continue; }
+    cudaIpcMemHandle_t hd;
+    std::memcpy(&hd, static_cast<const unsigned char*>(all_handles) + (size_t)g * 64, 64);
+    void* p = nullptr;
+    cudaError_t e = cudaIpcOpenMemHandle(&p, hd, cudaIpcMemLazyEnablePeerAccess);
+    if (e != cudaSuccess) return fail(h, MVG_ECUDA, std::string("cudaIpcOpenMemHandle (rank ") + std::to_string(g) + "): " + cudaGetErrorString(e));
+    h->xpeers.recv[g] = static_cast<unsigned char*>(p);
+  }
+  h->xp2p = true;
+  h->xseq = 0;
   return MVG_OK;
 }
 

@@ -108,6 +108,9 @@ struct Ctx {
   long long* dbg_prof;      // [CTAs][16] cycles spent waiting per role of the tcgen05 kernel (debug_export & 2)
 };
 
+// Peer-memory exchange (mv_exchange.cu): the receive buffer of every rank, as mapped into this process.
+struct XchgPeers { unsigned char* recv[16]; };
+
 enum FinalizeFlags : int32_t {
   kFinReseat = 1,      // seat births / resolve candidates (after a draw)
   kFinHyper = 2,       // run the hyperparameter step: the parts selected by the three bits below
@@ -139,6 +142,7 @@ int stats_smem_bytes(const Ctx& c);
 cudaError_t launch_rowtotals(const int32_t* rowptr, const float* val, float* out, int n, cudaStream_t s);
 cudaError_t launch_counts_rebuild(const Ctx& c, cudaStream_t s);   // per count view: zero, scatter, dish tables
 cudaError_t launch_counts_loglik(const Ctx& c, cudaStream_t s);    // per count view: log2 f of every row under every table
+cudaError_t launch_exchange_p2p(const Ctx& c, const XchgPeers& peers, unsigned char* recv_local, uint32_t seq, cudaStream_t s);
 // posterior summaries (mv_summary.cu)
 cudaError_t launch_labels(const Ctx& c, int32_t* out, cudaStream_t s);
 cudaError_t launch_cocluster(const Ctx& c, int view, uint32_t* counts, cudaStream_t s);

@@ -96,6 +96,9 @@ def lib():
         L.mvg_comm_attach.argtypes = [H, C.c_void_p]
         L.mvg_comm_unique_id.argtypes = [C.c_void_p]
         L.mvg_comm_init_rank.argtypes = [H, C.c_void_p]
+        L.mvg_prepare.argtypes = [H]
+        L.mvg_comm_p2p_export.argtypes = [H, C.c_void_p]
+        L.mvg_comm_p2p_attach.argtypes = [H, C.c_void_p]
         L.mvg_get_params.argtypes = [H, C.POINTER(_ParamsHost)]
         L.mvg_get_debug_rows.argtypes = [H, _f32p, _f32p, _i32p]
         L.mvg_get_debug_births.argtypes = [H, _i32p, C.POINTER(C.c_int64), _f64p]
@@ -221,6 +224,18 @@ class Sampler:
         assert tensor.is_cuda and tensor.is_contiguous() and tuple(tensor.shape) == (self.n_rows, self.dims[v])
         self._keep.append(tensor)
         self._ck(self.L.mvg_attach_view_device_f32(self.h, v, C.c_void_p(tensor.data_ptr()), self.dims[v]))
+
+    # -- peer-memory exchange (optional transport of the per-sweep packets; NCCL otherwise) -------
+    def p2p_export(self):
+        buf = C.create_string_buffer(64)
+        self._ck(self.L.mvg_comm_p2p_export(self.h, buf))
+        return buf.raw
+
+    def p2p_attach(self, handles):
+        """handles: the 64-byte exports of all ranks, in rank order."""
+        blob = b"".join(handles)
+        assert len(blob) == 64 * len(handles)
+        self._ck(self.L.mvg_comm_p2p_attach(self.h, C.c_char_p(blob)))
 
     # -- state ------------------------------------------------------------------------------
     def init_state_reference(self):

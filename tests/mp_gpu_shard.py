@@ -34,6 +34,10 @@ def main():
     s.comm_init_rank(uid[0])
     for v in range(3):
         s.upload_view(v, views[v][lo:hi])
+    if os.environ.get("MVG_TEST_P2P") == "1":                 # packets over NVLink peer memory instead of ncclAllGather
+        handles = [None] * world
+        dist.all_gather_object(handles, s.p2p_export())
+        s.p2p_attach(handles)
     s.set_state(tab[lo:hi], dish, *hyp)
     s.sweep(1, do_hyper=True)
     st1 = s.get_state()
@@ -68,7 +72,7 @@ def main():
         # last bit and a draw sitting on a CDF edge may flip
         assert aN > 0.999, aN
         np.testing.assert_allclose(ref["tau_v"], parts[0][5], rtol=1e-6)
-        print(f"SHARD_OK world={world} first_sweep={a1} after4={aN}")
+        print(f"SHARD_OK world={world} first_sweep={a1} after4={aN} p2p={os.environ.get('MVG_TEST_P2P', '0')}")
     dist.barrier()
     dist.destroy_process_group()
 

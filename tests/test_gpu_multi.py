@@ -10,12 +10,17 @@ ROOT = Path(__file__).resolve().parents[1]
 
 
 @pytest.mark.gpu
-def test_two_gpu_row_sharded_chain_matches_one_gpu():
+@pytest.mark.parametrize("transport", ["nccl", "p2p"])
+def test_two_gpu_row_sharded_chain_matches_one_gpu(transport):
+    """transport: the once-per-sweep packet exchange through ncclAllGather, or stored straight into the peers' memory
+    over NVLink (csrc/mv_exchange.cu)."""
+    import os
     import torch
     if torch.cuda.device_count() < 2:
         pytest.skip("needs two GPUs")
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1",
-           "--master-port", "29517", str(ROOT / "tests" / "mp_gpu_shard.py")]
-    r = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
+           "--master-port", "29517" if transport == "nccl" else "29518", str(ROOT / "tests" / "mp_gpu_shard.py")]
+    env = dict(os.environ, MVG_TEST_P2P="1" if transport == "p2p" else "0")
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=600, env=env)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-4000:]
     assert "SHARD_OK" in r.stdout, r.stdout[-2000:]
