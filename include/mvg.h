@@ -169,6 +169,7 @@ int mvg_comm_init_rank(mvg_handle* h, const void* unique_id_128);
 int mvg_prepare(mvg_handle* h);                       /* fix the layout now (all views uploaded/attached) */
 int mvg_comm_p2p_export(mvg_handle* h, void* ipc_handle_64);
 int mvg_comm_p2p_attach(mvg_handle* h, const void* all_handles);
+int mvg_comm_p2p_disable(mvg_handle* h);              /* back to the NCCL transport (e.g. a peer failed to attach) */
 
 /* ---- inspection (tests, profiling) ----------------------------------------------------- */
 /* The FP32 parameter block of the NEXT sweep, as the likelihood kernel will read it; pointers

@@ -315,9 +315,8 @@ int mvg_destroy(mvg_handle* h) {
   cudaSetDevice(h->cfg.device);
   if (h->stream) cudaStreamSynchronize(h->stream);
   if (h->comm && h->comm_owned && g_nccl.CommDestroy) g_nccl.CommDestroy(h->comm);
-  if (h->xp2p)
-    for (int g = 0; g < h->c.world; ++g)
-      if (g != h->c.rank && h->xpeers.recv[g]) cudaIpcCloseMemHandle(h->xpeers.recv[g]);
+  for (int g = 0; g < h->c.world && g < 16; ++g)
+    if (g != h->c.rank && h->xpeers.recv[g]) cudaIpcCloseMemHandle(h->xpeers.recv[g]);
   if (h->xrecv) cudaFree(h->xrecv);
   for (auto& g : h->sweep_graph) if (g) cudaGraphExecDestroy(g);
   for (void* p : h->owned) cudaFree(p);
@@ -737,6 +736,12 @@ int mvg_comm_p2p_attach(mvg_handle* h, const void* all_handles) {
   }
   h->xp2p = true;
   h->xseq = 0;
+  return MVG_OK;
+}
+
+int mvg_comm_p2p_disable(mvg_handle* h) {
+  if (!h) return MVG_EINVAL;
+  h->xp2p = false;                                 // back to ncclAllGather; the mappings stay until mvg_destroy
   return MVG_OK;
 }
 

@@ -99,6 +99,7 @@ def lib():
         L.mvg_prepare.argtypes = [H]
         L.mvg_comm_p2p_export.argtypes = [H, C.c_void_p]
         L.mvg_comm_p2p_attach.argtypes = [H, C.c_void_p]
+        L.mvg_comm_p2p_disable.argtypes = [H]
         L.mvg_get_params.argtypes = [H, C.POINTER(_ParamsHost)]
         L.mvg_get_debug_rows.argtypes = [H, _f32p, _f32p, _i32p]
         L.mvg_get_debug_births.argtypes = [H, _i32p, C.POINTER(C.c_int64), _f64p]
@@ -236,6 +237,9 @@ class Sampler:
         blob = b"".join(handles)
         assert len(blob) == 64 * len(handles)
         self._ck(self.L.mvg_comm_p2p_attach(self.h, C.c_char_p(blob)))
+
+    def p2p_disable(self):
+        self._ck(self.L.mvg_comm_p2p_disable(self.h))
 
     # -- state ------------------------------------------------------------------------------
     def init_state_reference(self):
