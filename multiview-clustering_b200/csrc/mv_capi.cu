@@ -177,7 +177,7 @@ int ensure_layout(mvg_handle* h) {
   // engine choice
   h->engine = MVG_ENGINE_SIMT;
   if (h->cfg.engine == MVG_ENGINE_TCGEN05 || h->cfg.engine == MVG_ENGINE_TCGEN05_FAST) {
-    if (!draw_tc_supported(c)) return fail(h, MVG_EUNSUPPORTED, "tcgen05 engine needs cap = 64 and exactly three views of dim 64");
+    if (!draw_tc_supported(c)) return fail(h, MVG_EUNSUPPORTED, "tcgen05 engine needs cap = 64 and one to three dense views of dim 64");
     h->engine = h->cfg.engine;
   } else if (h->cfg.engine == MVG_ENGINE_AUTO && draw_tc_supported(c)) {
     h->engine = MVG_ENGINE_TCGEN05;
@@ -299,7 +299,9 @@ int mvg_create(const mvg_config* cfg, mvg_handle** out) {
   {
     void* q = nullptr;
     c.xx_stride = ((int64_t)c.n_rows + 3) & ~(int64_t)3;        // rows of xx start 16-byte aligned (bulk copies)
-    if (cudaMalloc(&q, sizeof(float) * (size_t)c.xx_stride * c.V) != cudaSuccess) {
+    // at least three rows: the tensor-core epilogue prefetches the norms of three views unconditionally
+    const size_t xx_rows = c.V > 3 ? (size_t)c.V : 3;
+    if (cudaMalloc(&q, sizeof(float) * (size_t)c.xx_stride * xx_rows) != cudaSuccess || cudaMemset(q, 0, sizeof(float) * (size_t)c.xx_stride * xx_rows) != cudaSuccess) {
       mvg_destroy(h);
       return fail(nullptr, MVG_ENOMEM, "cudaMalloc: squared norms");
     }

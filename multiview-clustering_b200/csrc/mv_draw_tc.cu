@@ -1,6 +1,6 @@
 // mv_draw_tc.cu — likelihood + draw on the 5th-generation tensor cores (engines MVG_ENGINE_TCGEN05*).
 //
-// Shape: cap = 64 table slots, every view dense with dim 64, at most 3 views (BASELINE config C3).
+// Shape: cap = 64 table slots, every view dense with dim 64, one to three views (BASELINE config C3 has three).
 // One persistent CTA per SM walks row tiles of 128 customers.  For every (tile, view):
 //
 //   TMA producer (1 thread)    cp.async.bulk.tensor: the tile's [128 x 64] FP32 features arrive in
@@ -347,6 +347,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_draw_tc(const Ctx c, const __gr
       const uint32_t lo_tmem = tmem_base + (uint32_t)(kLoCol0 + me * 64);                 // this warp's remainder stage
       const int n_tv = ((n_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x) * V;
       int v = me % V, ds = me;                       // view and accumulator stage of tile-view i
+      const int vstep = kMmaWarps % V;
       uint32_t use = 0;                              // how many tile-views this warp has issued
       uint32_t dph = 0;                              // accumulator-stage phase: flips every third tile-view of this warp
       int dcnt = 0;
@@ -392,7 +393,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_draw_tc(const Ctx c, const __gr
         }
         __syncwarp();
         ++use;
-        v += kMmaWarps; if (v >= V) v -= V;          // V = 3, step 2
+        v += vstep; if (v >= V) v -= V;              // view of tile-view i + 2 (vstep = 2 mod V, no division on the issue path)
         ds += kMmaWarps; if (ds >= kDStages) ds -= kDStages;
         if (++dcnt == kDStages / kMmaWarps) { dcnt = 0; dph ^= 1u; }
       }
@@ -461,7 +462,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_draw_tc(const Ctx c, const __gr
     float xx_next[kMaxTcViews];
 #pragma unroll
     for (int v = 0; v < kMaxTcViews; ++v)
-      xx_next[v] = (tile0 < n_tiles) ? c.xx[(size_t)v * c.xx_stride + min(tile0 * kTileRows + r, c.n_rows - 1)] : 0.0f;
+      xx_next[v] = (tile0 < n_tiles) ? c.xx[(size_t)v * c.xx_stride + min(tile0 * kTileRows + r, c.n_rows - 1)] : 0.0f;   // (xx has >= 3 rows)
     for (int tile = tile0; tile < n_tiles; tile += kEpiGroups * gridDim.x, j += kEpiGroups) {
       const int row = tile * kTileRows + r;
       const bool live = row < c.n_rows;
@@ -580,7 +581,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_draw_tc(const Ctx c, const __gr
 // host side
 // =================================================================================================
 bool draw_tc_supported(const Ctx& c) {
-  if (c.cap != 64 || c.V != kMaxTcViews) return false;   // the stage/slot schedule of the kernel is laid out for three views
+  if (c.cap != 64 || c.V < 1 || c.V > kMaxTcViews) return false;   // shared memory and TMEM are laid out for up to three views
   for (int v = 0; v < c.V; ++v)
     if (c.D[v] != 64 || (reinterpret_cast<uintptr_t>(c.x[v]) & 15) != 0) return false;
   return true;

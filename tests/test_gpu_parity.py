@@ -231,24 +231,26 @@ def test_run_gibbs_posterior_summaries_match_reference(oracle):
 # tcgen05 engine (MVG_ENGINE_TCGEN05): stage A runs on the tensor cores (3-pass TF32 split), so the
 # dot products are tolerance-level; everything downstream of them is bit-exact against the mirror.
 # ---------------------------------------------------------------------------------------------
-@pytest.mark.parametrize("n,k_true,engine", [(900, 6, 2), (128 * 148 + 77, 40, 2), (128 * 148 * 2 + 5, 40, 3), (700, 5, 3)])
-def test_tcgen05_engine_parity(oracle, n, k_true, engine):
-    dims, cap = [64, 64, 64], 64
+@pytest.mark.parametrize("n,k_true,engine,n_views", [(900, 6, 2, 3), (128 * 148 + 77, 40, 2, 3), (128 * 148 * 2 + 5, 40, 3, 3),
+                                                     (700, 5, 3, 3), (128 * 5 + 9, 6, 2, 1), (128 * 149 + 3, 12, 2, 2)])
+def test_tcgen05_engine_parity(oracle, n, k_true, engine, n_views):
+    dims, cap = [64] * n_views, 64
     views, z = make_mixture(n, dims, k_true, seed=11)
     s = _mk_sampler(views, cap, seed=123, engine=engine)
     rng = np.random.default_rng(2)
     tab = np.where(rng.random(n) < 0.15, rng.integers(0, k_true, n), z).astype(np.int32)
     tab[:3] = [k_true + 1, k_true + 2, k_true + 3]                   # three customers alone at their tables
-    dish = np.full((3, cap), -1, np.int32)
+    V = n_views
+    dish = np.full((V, cap), -1, np.int32)
     for t in range(k_true + 4):
-        dish[:, t] = rng.integers(0, max(2, k_true - 1), 3)
-    s.set_state(tab, dish, np.full(3, 1.0), np.full(3, 0.5), np.full(3, 0.9), 1.0, 0.6, sweep=3)
+        dish[:, t] = rng.integers(0, max(2, k_true - 1), 3)[:V]
+    s.set_state(tab, dish, np.full(V, 1.0), np.full(V, 0.5), np.full(V, 0.9), 1.0, 0.6, sweep=3)
     for it in range(3):
         P = s.get_params()
         _one_sweep_parity(oracle, s, views, cap, 123, do_hyper=(it % 2 == 0), simt_bit_exact=False,
                           fast_weights=(engine == 3))
         acc, xx, _ = s.get_debug_rows()
-        for v in range(3):                                           # stage A against FP64
+        for v in range(V):                                           # stage A against FP64
             x64, m64 = views[v].astype(np.float64), P["m"][v].astype(np.float64)
             ref = x64 @ m64.T
             bound = np.abs(x64) @ np.abs(m64).T
