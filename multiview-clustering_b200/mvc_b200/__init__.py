@@ -423,20 +423,42 @@ class Sampler:
         return ns.value, rows[:ns.value].copy(), w[:ns.value].copy()
 
 
-def run_gibbs(data_views, M, burn_in, thin, cap=64, seed=1999, device=0, engine=ENGINE_AUTO):
+def _as_csr(v):
+    """A sparse count view as (rowptr, col, val, vocab): a dict with those keys, or a scipy.sparse matrix."""
+    if isinstance(v, dict):
+        return (np.asarray(v["rowptr"], np.int32), np.asarray(v["col"], np.int32), np.asarray(v["val"], np.float32), int(v["vocab"]))
+    if hasattr(v, "tocsr"):
+        m = v.tocsr()
+        m.sum_duplicates()
+        m.sort_indices()
+        return (m.indptr.astype(np.int32), m.indices.astype(np.int32), m.data.astype(np.float32), int(m.shape[1]))
+    return None
+
+
+def run_gibbs(data_views, M, burn_in, thin, cap=64, seed=1999, device=0, engine=ENGINE_AUTO, start=None):
     """run_gibbs_cpp(data_views, M, burn_in, thin) on the GPU (multiview_gibbs.cpp:105-131).
 
     ``data_views`` is a list of per-view arrays (vectors as in New_Simulation.R:105-111, or [n, D]
-    matrices).  Returns a dict with the reference's eight keys; ``table_of`` is 0-based, ``dish_of``
-    is indexed [saved][view][table slot] with -1 for a free slot.
+    matrices); a sparse count view (the X_body / X_title / X_topics of dataset/reuters/data pre-process.R) is a
+    scipy.sparse matrix or a dict {"rowptr", "col", "val", "vocab"}.  ``start`` = (table_of, dish_of) replaces the
+    reference's random T = 4 / K = 2 start.  Returns a dict with the reference's eight keys; ``table_of`` is
+    0-based, ``dish_of`` is indexed [saved][view][table slot] with -1 for a free slot.
     """
-    views = [np.asarray(v, dtype=np.float64).reshape(len(v), -1) for v in data_views]
-    n = views[0].shape[0]
-    s = Sampler(n, [v.shape[1] for v in views], cap=cap, seed=seed, device=device, engine=engine)
+    csr = [_as_csr(v) for v in data_views]
+    views = [None if c is not None else np.asarray(v, dtype=np.float64).reshape(len(v), -1) for v, c in zip(data_views, csr)]
+    n = len(csr[0][0]) - 1 if csr[0] is not None else views[0].shape[0]
+    s = Sampler(n, [0 if x is None else x.shape[1] for x in views], cap=cap, seed=seed, device=device, engine=engine)
     try:
         for v, x in enumerate(views):
-            s.upload_view(v, x)
-        s.init_state_reference()
+            if x is None:
+                s.upload_view_csr(v, *csr[v])
+            else:
+                s.upload_view(v, x)
+        if start is None:
+            s.init_state_reference()
+        else:
+            V = len(views)
+            s.set_state(start[0], start[1], [1.0] * V, [0.5] * V, [1.0] * V, 1.0, 0.6)
         tr = s.run(M, burn_in, thin)
     finally:
         s.close()

@@ -633,3 +633,25 @@ def test_over_split_start_merges_to_planted_partition_tensor_core_engine():
     live = int((st["n_t"] > 0).sum())
     assert min(aris) > 0.8 and k_true - 2 <= live <= k_true + 4, (aris, live)     # at most a pair of clusters fused
     s.close()
+
+
+def test_run_gibbs_accepts_sparse_count_views():
+    """run_gibbs with a scipy.sparse document-term matrix and a dense view, from an over-split start."""
+    import scipy.sparse as sp
+    import mvc_b200
+    from conftest import make_count_view
+    n, cap, k_true = 1500, 32, 4
+    rng = np.random.default_rng(8)
+    z = rng.integers(0, k_true, n)
+    cv = make_count_view(n, 150, z, k_true, seed=6)
+    X = sp.csr_matrix((cv["val"], cv["col"], cv["rowptr"]), shape=(n, cv["vocab"]))
+    mu = rng.normal(0, 3, (k_true, 2))
+    dense = mu[z] + rng.normal(0, 1, (n, 2))
+    tab = rng.integers(0, cap // 2, n).astype(np.int32)
+    dish = np.full((2, cap), -1, np.int32)
+    dish[:, :cap // 2] = np.arange(cap // 2)
+    res = mvc_b200.run_gibbs([X, dense], M=120, burn_in=100, thin=5, cap=cap, seed=5, start=(tab, dish))
+    assert len(res["table_of"]) == 4 and len(res["tau_v"]) == 2
+    from sklearn.metrics import adjusted_rand_score as ari
+    last_tab, last_dish = res["table_of"][-1], res["dish_of"][-1]
+    assert ari(z, np.asarray(last_dish[0])[last_tab]) > 0.7 and ari(z, np.asarray(last_dish[1])[last_tab]) > 0.7
