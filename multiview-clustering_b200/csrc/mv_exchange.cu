@@ -10,8 +10,8 @@
 //
 // Two parities: a rank can run at most one exchange ahead of a peer that is still reading the previous packets (it
 // cannot finish exchange s+1 without that peer's packet s+1).  The sequence number is kept by the host (every rank
-// issues the same number of exchanges).  The waits are bounded: a peer that never arrives raises status bit 8 instead
-// of hanging the GPU.  ncclAllGather remains the transport when no peer buffers are attached.
+// issues the same number of exchanges).  The waits are bounded (2^24 polls, a few seconds): a peer that never arrives
+// raises status bit 8 instead of hanging the GPU.  ncclAllGather remains the transport when no peer buffers are attached.
 #include "mv_ctx.h"
 
 namespace mv {
@@ -56,7 +56,7 @@ __global__ void __launch_bounds__(256) k_exchange(const Ctx c, const XchgPeers p
       long long spins = 0;
       do {
         asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(counter) : "memory");
-      } while ((int32_t)(v - want) < 0 && ++spins < (1ll << 24));   // ~ a second: a missing peer must not hang the GPU
+      } while ((int32_t)(v - want) < 0 && ++spins < (1ll << 24));   // seconds at most: a missing peer must not hang the GPU
       ok = ((int32_t)(v - want) >= 0);
       if (!ok) atomicOr(c.status, 8);
     }
