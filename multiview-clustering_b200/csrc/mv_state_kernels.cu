@@ -432,16 +432,22 @@ __device__ __forceinline__ double reflect_unit(double value) {      // :110-122
 //   sum_{m=1}^{c-1} fin_log(m-sigma) = fin_lgamma(c-sigma) - fin_lgamma(1-sigma),
 // the per-cluster terms are evaluated by the block in parallel and one thread per set adds them in
 // ascending cluster order (the order of oracle/mv_oracle.c:eppf_core).  Block-uniform call.
-__device__ __noinline__ void eppf_batch(const int cap, const int V, FinShared& S, const double* alpha, const double* sigma) {
-  const int tid = threadIdx.x;
+// Called by ONE group of gthreads consecutive threads of the CTA (gtid = index inside the group), synchronising on
+// named barrier bar_id: the other half of the CTA is busy with the dish statistics and the posterior means meanwhile.
+__device__ __forceinline__ void group_sync(int bar_id, int gthreads) {
+  asm volatile("bar.sync %0, %1;" ::"r"(bar_id), "r"(gthreads) : "memory");
+}
+__device__ __noinline__ void eppf_batch(const int cap, const int V, FinShared& S, const double* alpha, const double* sigma,
+                                        const int gtid, const int gthreads, const int bar_id) {
+  const int tid = gtid;
   const int lane = tid & 31, wid = tid >> 5;
   const int nsets = 2 * (V + 1);
-  __syncthreads();
+  group_sync(bar_id, gthreads);
   // one thread per (parameter set, cluster): its two terms, summed per warp by a fixed shuffle tree into
   // termA/termB[set][warp-in-set]; then one thread per set adds the warp partials in ascending order.
   // The rank of a cluster among the live ones is a popcount of the level's live mask.
   const int wps = (cap + 31) / 32;                   // warps per set
-  for (int base = 0; base < nsets * wps; base += kFinThreads / 32) {
+  for (int base = 0; base < nsets * wps; base += gthreads / 32) {
     const int unit = base + wid;                     // (set, 32-cluster block)
     double sa = 0.0, sb = 0.0;
     bool bad = false;
@@ -472,7 +478,7 @@ __device__ __noinline__ void eppf_batch(const int cap, const int V, FinShared& S
     }
   }
   // the three per-set lgamma values, one thread each (the last warps: the first ones carry the units above)
-  for (int q = tid - (kFinThreads - 128); q >= 0 && q < 3 * nsets; q += kFinThreads) {
+  for (int q = tid - (gthreads - 128); q >= 0 && q < 3 * nsets; q += gthreads) {
     const int set = q / 3, which = q - 3 * set, j = set >> 1;
     const double al = alpha[set], sg = sigma[set];
     double val = 0.0;
@@ -480,7 +486,7 @@ __device__ __noinline__ void eppf_batch(const int cap, const int V, FinShared& S
       val = (which == 0) ? fin_lgamma(al + (double)S.total[j]) : ((which == 1) ? fin_lgamma(al + 1.0) : fin_lgamma(1.0 - sg));
     S.termC[set][which] = val;
   }
-  __syncthreads();
+  group_sync(bar_id, gthreads);
   if (tid < nsets) {
     const int set = tid, j = set >> 1;
     const int32_t* counts = (j < V) ? S.l_live[j] : S.n_new;
@@ -500,7 +506,7 @@ __device__ __noinline__ void eppf_batch(const int cap, const int V, FinShared& S
     }
     S.eppf[set] = logp;
   }
-  __syncthreads();
+  group_sync(bar_id, gthreads);
 }
 
 
@@ -821,182 +827,193 @@ __global__ void __launch_bounds__(kFinThreads, 1) k_finalize(const Ctx c, const 
   }
   __syncthreads();
   stamp(7);
-  if (tid >= 64 && tid <= 64 + V) {                            // live masks and item totals of the EPPF levels
-    const int j = tid - 64;
-    const int32_t* counts = (j < V) ? S.l_live[j] : S.n_new;
-    unsigned long long m = 0ull;
-    long long tot = 0;
-    for (int i = 0; i < cap; ++i) { if (counts[i] > 0) m |= 1ull << i; tot += counts[i]; }
-    S.live[j] = m;
-    S.total[j] = (j < V) ? tot : (long long)c.n_global;
-  }
-  {
-    // one warp per dish (v, k): lanes stride over the coordinates; the tables serving the dish are added in
-    // ascending order (warp-uniform loop), then |S1k|^2 by a fixed shuffle tree
-    const int lane = tid & 31, wid = tid >> 5;
-    for (int i = wid; i < V * cap; i += kFinThreads / 32) {
-      const int v = i >> cshift, k = i & (cap - 1);
-      const int D = c.D[v], base = cap * c.doff[v];
-      const double* S1t_v = S1t + base;
-      double* S1k_vk = c.S1k + base + k * D;
-      const unsigned long long mask = S.tmask[v][k];
-      const int t1 = __ffsll((long long)mask) - 1;             // usually the only table of the dish
-      const unsigned long long more = mask & (mask - 1ull);
-      double q = 0.0;
-      for (int dd = lane; dd < D; dd += 32) {
-        double sum = (t1 >= 0) ? S1t_v[t1 * D + dd] : 0.0;
-        for (unsigned long long m = more; m; m &= m - 1ull) sum += S1t_v[(__ffsll((long long)m) - 1) * D + dd];
-        S1k_vk[dd] = sum;
-        q += sum * sum;
+  // From here the CTA works as two halves that meet again before the parameter block:
+  //   upper half (named barrier 1): the (alpha, sigma) Metropolis-Hastings steps of the V views and of the franchise —
+  //     they only need the COUNTS fixed above (tables per dish, customers per table);
+  //   lower half (named barrier 2): per-dish statistics -> tau_v step (needs their sums of squares) -> posterior means
+  //     (need the new tau_v).
+  // Two independent FP64 latency chains of similar length: side by side they cost the longer one.
+  __shared__ double s_alpha[2 * (kMaxViews + 1)], s_sigma[2 * (kMaxViews + 1)];
+  constexpr int kGroupThreads = kFinThreads / 2;
+  if (tid >= kGroupThreads) {
+    // =============================== upper half: alpha / sigma ===============================
+    const int gtid = tid - kGroupThreads;
+    if (gtid <= V) {                            // live masks and item totals of the EPPF levels
+      const int j = gtid;
+      const int32_t* counts = (j < V) ? S.l_live[j] : S.n_new;
+      unsigned long long m = 0ull;
+      long long tot = 0;
+      for (int i = 0; i < cap; ++i) { if (counts[i] > 0) m |= 1ull << i; tot += counts[i]; }
+      S.live[j] = m;
+      S.total[j] = (j < V) ? tot : (long long)c.n_global;
+    }
+    group_sync(1, kGroupThreads);
+    // ---- D2. (alpha, sigma) per level (multiview_hyper.cpp:239-291): one thread per level, on Philox numbers addressed
+    //      by the position the reference's sequential code would draw them at ----
+    if (flags & kFinHyper) {
+      // level j: its alpha/sigma slots in S.hyp and its Philox indices (alpha: base, sigma: base+1)
+      const int j = gtid;
+      const bool is_level = (j < V) ? (flags & kFinHyperLocal) != 0 : (j == V && (flags & kFinHyperGlobal) != 0);
+      const int ia = (j < V) ? j : 3 * V, is = (j < V) ? V + j : 3 * V + 1;
+      const int base = (j < V) ? V + 2 * j : 3 * V;
+      // alpha: log-normal random walk, :242-255 / :268-281
+      double a_old = 0.0, a_prop = 0.0;
+      if (is_level) {
+        a_old = S.hyp[ia];
+        if (a_old <= 0.0) a_old = kEps;
+        const double cand = fin_exp(fin_log(a_old > kEps ? a_old : kEps) + 0.0 + 0.1 * S.rn[base]);   // :100-108
+        a_prop = cand > kEps ? cand : kEps;
+        s_alpha[2 * j] = a_old; s_alpha[2 * j + 1] = a_prop;
+        s_sigma[2 * j] = S.hyp[is]; s_sigma[2 * j + 1] = S.hyp[is];
       }
-#pragma unroll
-      for (int o = 16; o > 0; o >>= 1) q += __shfl_xor_sync(0xffffffffu, q, o);
-      if (lane == 0) {
-        S.s1sq[v][k] = q;
-        const int n_k = S.n_vk[v][k];
-        double sse = (n_k > 0) ? S.s2k[v][k] - q / (double)n_k : 0.0;
-        S.sse[v][k] = sse < 0.0 ? 0.0 : sse;
+      eppf_batch(cap, V, S, s_alpha, s_sigma, gtid, kGroupThreads, 1);
+      stamp(11);
+      double s_old = 0.0, s_prop = 0.0;
+      if (is_level) {
+        const double lo = S.eppf[2 * j] + log_prior_alpha(a_old), ln = S.eppf[2 * j + 1] + log_prior_alpha(a_prop);
+        const double log_acc = (ln - lo) + (fin_log(a_prop) - fin_log(a_old));
+        if (S.lu[base] < log_acc) S.hyp[ia] = a_prop;
+        // sigma: reflected random walk, :257-265 / :283-291
+        s_old = S.hyp[is];
+        s_prop = reflect_unit(s_old + 0.0 + 0.05 * S.rn[base + 1]);                             // :124-128
+        s_alpha[2 * j] = S.hyp[ia]; s_alpha[2 * j + 1] = S.hyp[ia];
+        s_sigma[2 * j] = s_old; s_sigma[2 * j + 1] = s_prop;
+      }
+      eppf_batch(cap, V, S, s_alpha, s_sigma, gtid, kGroupThreads, 1);
+      stamp(12);
+      if (is_level) {
+        const double lpo = (s_old <= kEps || s_old >= 1.0 - kEps) ? -INFINITY : S.eppf[2 * j] + log_prior_sigma(s_old);
+        const double lpn = (s_prop <= kEps || s_prop >= 1.0 - kEps) ? -INFINITY : S.eppf[2 * j + 1] + log_prior_sigma(s_prop);
+        if (S.lu[base + 1] < lpn - lpo) S.hyp[is] = s_prop;
       }
     }
-  }
-  __syncthreads();
-
-  stamp(2);
-  // ---- reference initialisation of the hyperparameters (multiview_gibbs.cpp:75-98) ------------
-  if (flags & kFinTauInit) {
-    if (tid < V) {
-      const int v = tid;
-      // all customers sit at table 0 / dish 0 during this call: pooled variance over coordinates
-      const double n = (double)c.n_global;
-      double var = 1.0;
-      if (c.n_global > 1) var = (S.s2k[v][0] - S.s1sq[v][0] / n) / ((n - 1.0) * (double)c.D[v]);
-      if (!(var > 0.0)) var = 1.0;
-      tau_v[v] = c.kind[v] ? 1.0 : var * 0.25 * 0.01;      // a count view has no kernel variance
-      alpha_v[v] = 1.0;
-      sigma_v[v] = 0.5;
-    }
-    if (tid == 0) { alpha_g = 1.0; sigma_g = 0.6; }
-    __syncthreads();
-  }
-
-  stamp(3);
-  // ---- D. hyperparameter step (multiview_hyper.cpp:233-292) -------------------------------------
-  // The tau_v updates are independent across views, and so are the (alpha, sigma) pairs of the V views
-  // and of the franchise: they run side by side, one thread per level, on Philox numbers addressed by
-  // the position the reference's sequential code would draw them at.
-  if (flags & kFinHyper) {
-    if (flags & kFinHyperTau) {                                // update_tau_v_MH, :211-231: one warp per view
+  } else {
+    // =============================== lower half: dish statistics, tau, means ===============================
+    {
+      // one warp per dish (v, k): lanes stride over the coordinates; the tables serving the dish are added in
+      // ascending order (warp-uniform loop), then |S1k|^2 by a fixed shuffle tree
       const int lane = tid & 31, wid = tid >> 5;
-      for (int v = wid; v < V; v += kFinThreads / 32) {
-        if (c.kind[v]) continue;                               // no tau in a count view (its stream positions stay unused)
-        double tau_old = tau_v[v];
-        if (tau_old <= 0.0) tau_old = kEps;
-        const double tau_prop = fin_exp(fin_log(tau_old) + 0.0 + 0.3 * S.rn[v]);   // :166-174
-        // log_posterior_given_tau (:176-209) at both values: lanes stride over the dishes, shuffle-tree sum
-        const double lg_o = fin_log(2.0 * kPi * tau_old), lg_p = fin_log(2.0 * kPi * tau_prop);
-        const double Dd = (double)c.D[v];
-        double lo = 0.0, ln = 0.0;
-        for (int k = lane; k < cap; k += 32) {
-          const int n_k = S.n_vk[v][k];
-          if (n_k == 0) continue;
-          lo += -0.5 * (double)n_k * Dd * lg_o - 0.5 * (S.sse[v][k] / tau_old);
-          ln += -0.5 * (double)n_k * Dd * lg_p - 0.5 * (S.sse[v][k] / tau_prop);
+      for (int i = wid; i < V * cap; i += kGroupThreads / 32) {
+        const int v = i >> cshift, k = i & (cap - 1);
+        const int D = c.D[v], base = cap * c.doff[v];
+        const double* S1t_v = S1t + base;
+        double* S1k_vk = c.S1k + base + k * D;
+        const unsigned long long mask = S.tmask[v][k];
+        const int t1 = __ffsll((long long)mask) - 1;             // usually the only table of the dish
+        const unsigned long long more = mask & (mask - 1ull);
+        double q = 0.0;
+        for (int dd = lane; dd < D; dd += 32) {
+          double sum = (t1 >= 0) ? S1t_v[t1 * D + dd] : 0.0;
+          for (unsigned long long m = more; m; m &= m - 1ull) sum += S1t_v[(__ffsll((long long)m) - 1) * D + dd];
+          S1k_vk[dd] = sum;
+          q += sum * sum;
         }
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) {
-          lo += __shfl_xor_sync(0xffffffffu, lo, o);
-          ln += __shfl_xor_sync(0xffffffffu, ln, o);
-        }
+  #pragma unroll
+        for (int o = 16; o > 0; o >>= 1) q += __shfl_xor_sync(0xffffffffu, q, o);
         if (lane == 0) {
-          const double a_tau = 2.0, b_tau = 1.0;                                    // :133-134
-          // a log(b) - lgamma(a) = 2 log 1 - lgamma 2 = 0 exactly
-          const double log_old = lo + (-(a_tau + 1.0) * fin_log(tau_old) - b_tau / tau_old);
-          const double log_new = ln + (-(a_tau + 1.0) * fin_log(tau_prop) - b_tau / tau_prop);
-          const double log_acc = (log_new - log_old) + (fin_log(tau_prop) - fin_log(tau_old));
-          if (S.lu[v] < log_acc) tau_v[v] = tau_prop;
+          S.s1sq[v][k] = q;
+          const int n_k = S.n_vk[v][k];
+          double sse = (n_k > 0) ? S.s2k[v][k] - q / (double)n_k : 0.0;
+          S.sse[v][k] = sse < 0.0 ? 0.0 : sse;
         }
       }
     }
-    __syncthreads();
+    group_sync(2, kGroupThreads);
+    stamp(2);
+    // ---- reference initialisation of the hyperparameters (multiview_gibbs.cpp:75-98) ------------
+    if (flags & kFinTauInit) {
+      if (tid < V) {
+        const int v = tid;
+        // all customers sit at table 0 / dish 0 during this call: pooled variance over coordinates
+        const double n = (double)c.n_global;
+        double var = 1.0;
+        if (c.n_global > 1) var = (S.s2k[v][0] - S.s1sq[v][0] / n) / ((n - 1.0) * (double)c.D[v]);
+        if (!(var > 0.0)) var = 1.0;
+        tau_v[v] = c.kind[v] ? 1.0 : var * 0.25 * 0.01;      // a count view has no kernel variance
+        alpha_v[v] = 1.0;
+        sigma_v[v] = 0.5;
+      }
+      if (tid == 0) { alpha_g = 1.0; sigma_g = 0.6; }
+      group_sync(2, kGroupThreads);
+    }
+    stamp(3);
+    // ---- D1. tau_v (update_tau_v_MH, multiview_hyper.cpp:211-231): independent across views, one warp per view ----
+    if (flags & kFinHyper) {
+      if (flags & kFinHyperTau) {                                // update_tau_v_MH, :211-231: one warp per view
+        const int lane = tid & 31, wid = tid >> 5;
+        for (int v = wid; v < V; v += kGroupThreads / 32) {
+          if (c.kind[v]) continue;                               // no tau in a count view (its stream positions stay unused)
+          double tau_old = tau_v[v];
+          if (tau_old <= 0.0) tau_old = kEps;
+          const double tau_prop = fin_exp(fin_log(tau_old) + 0.0 + 0.3 * S.rn[v]);   // :166-174
+          // log_posterior_given_tau (:176-209) at both values: lanes stride over the dishes, shuffle-tree sum
+          const double lg_o = fin_log(2.0 * kPi * tau_old), lg_p = fin_log(2.0 * kPi * tau_prop);
+          const double Dd = (double)c.D[v];
+          double lo = 0.0, ln = 0.0;
+          for (int k = lane; k < cap; k += 32) {
+            const int n_k = S.n_vk[v][k];
+            if (n_k == 0) continue;
+            lo += -0.5 * (double)n_k * Dd * lg_o - 0.5 * (S.sse[v][k] / tau_old);
+            ln += -0.5 * (double)n_k * Dd * lg_p - 0.5 * (S.sse[v][k] / tau_prop);
+          }
+  #pragma unroll
+          for (int o = 16; o > 0; o >>= 1) {
+            lo += __shfl_xor_sync(0xffffffffu, lo, o);
+            ln += __shfl_xor_sync(0xffffffffu, ln, o);
+          }
+          if (lane == 0) {
+            const double a_tau = 2.0, b_tau = 1.0;                                    // :133-134
+            // a log(b) - lgamma(a) = 2 log 1 - lgamma 2 = 0 exactly
+            const double log_old = lo + (-(a_tau + 1.0) * fin_log(tau_old) - b_tau / tau_old);
+            const double log_new = ln + (-(a_tau + 1.0) * fin_log(tau_prop) - b_tau / tau_prop);
+            const double log_acc = (log_new - log_old) + (fin_log(tau_prop) - fin_log(tau_old));
+            if (S.lu[v] < log_acc) tau_v[v] = tau_prop;
+          }
+        }
+      }
+    }
+    group_sync(2, kGroupThreads);
     stamp(9);
-    __shared__ double s_alpha[2 * (kMaxViews + 1)], s_sigma[2 * (kMaxViews + 1)];
-    // level j: its alpha/sigma slots in S.hyp and its Philox indices (alpha: base, sigma: base+1)
-    const int j = tid;
-    const bool is_level = (j < V) ? (flags & kFinHyperLocal) != 0 : (j == V && (flags & kFinHyperGlobal) != 0);
-    const int ia = (j < V) ? j : 3 * V, is = (j < V) ? V + j : 3 * V + 1;
-    const int base = (j < V) ? V + 2 * j : 3 * V;
-    // alpha: log-normal random walk, :242-255 / :268-281
-    double a_old = 0.0, a_prop = 0.0;
-    if (is_level) {
-      a_old = S.hyp[ia];
-      if (a_old <= 0.0) a_old = kEps;
-      const double cand = fin_exp(fin_log(a_old > kEps ? a_old : kEps) + 0.0 + 0.1 * S.rn[base]);   // :100-108
-      a_prop = cand > kEps ? cand : kEps;
-      s_alpha[2 * j] = a_old; s_alpha[2 * j + 1] = a_prop;
-      s_sigma[2 * j] = S.hyp[is]; s_sigma[2 * j + 1] = S.hyp[is];
-    }
-    eppf_batch(cap, V, S, s_alpha, s_sigma);
-    stamp(11);
-    double s_old = 0.0, s_prop = 0.0;
-    if (is_level) {
-      const double lo = S.eppf[2 * j] + log_prior_alpha(a_old), ln = S.eppf[2 * j + 1] + log_prior_alpha(a_prop);
-      const double log_acc = (ln - lo) + (fin_log(a_prop) - fin_log(a_old));
-      if (S.lu[base] < log_acc) S.hyp[ia] = a_prop;
-      // sigma: reflected random walk, :257-265 / :283-291
-      s_old = S.hyp[is];
-      s_prop = reflect_unit(s_old + 0.0 + 0.05 * S.rn[base + 1]);                             // :124-128
-      s_alpha[2 * j] = S.hyp[ia]; s_alpha[2 * j + 1] = S.hyp[ia];
-      s_sigma[2 * j] = s_old; s_sigma[2 * j + 1] = s_prop;
-    }
-    eppf_batch(cap, V, S, s_alpha, s_sigma);
-    stamp(12);
-    if (is_level) {
-      const double lpo = (s_old <= kEps || s_old >= 1.0 - kEps) ? -INFINITY : S.eppf[2 * j] + log_prior_sigma(s_old);
-      const double lpn = (s_prop <= kEps || s_prop >= 1.0 - kEps) ? -INFINITY : S.eppf[2 * j + 1] + log_prior_sigma(s_prop);
-      if (S.lu[base + 1] < lpn - lpo) S.hyp[is] = s_prop;
-    }
-    __syncthreads();
-  }
-  for (int i = tid; i < 3 * V + 2; i += kFinThreads) c.hyp[i] = S.hyp[i];
-
-  stamp(4);
-  // ---- E. FP32 parameter block of the next sweep (oracle/mv_oracle.c:mvo_make_params) ----------
-  {
-    // one warp per (view, table): lanes stride over the coordinates of the posterior mean m = S1k / (tau + n),
-    // S1k re-summed from the per-table sums (same order as above, so the same value), write it (and its TF32
-    // split) and reduce |m|^2 by a fixed shuffle tree
-    const int lane = tid & 31, wid = tid >> 5;
-    for (int i = wid; i < V * cap; i += kFinThreads / 32) {
-      const int v = i >> cshift, t = i & (cap - 1);
-      const int D = c.D[v], k = S.dish[v][t], base = cap * c.doff[v];
-      const int off = base + t * D;
-      const double rden = (k >= 0) ? 1.0 / (tau_v[v] + (double)S.n_vk[v][k]) : 0.0;
-      const double* S1t_v = S1t + base;
-      const unsigned long long mask = (k >= 0) ? S.tmask[v][k] : 0ull;
-      const int t1 = __ffsll((long long)mask) - 1;
-      const unsigned long long more = mask & (mask - 1ull);
-      double mm = 0.0;
-      for (int dd = lane; dd < D; dd += 32) {
-        double s1 = (t1 >= 0) ? S1t_v[t1 * D + dd] : 0.0;
-        for (unsigned long long m = more; m; m &= m - 1ull) s1 += S1t_v[(__ffsll((long long)m) - 1) * D + dd];
-        const float m = (float)(s1 * rden);
-        c.mean[off + dd] = m;
-        if (c.mean_hi) {
-          uint32_t hb, lb;                                            // TF32 split, both parts rounded to nearest
-          asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(hb) : "f"(m));
-          const float hi = __uint_as_float(hb);
-          asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(lb) : "f"(__fadd_rn(m, -hi)));
-          c.mean_hi[off + dd] = hi;
-          c.mean_lo[off + dd] = __uint_as_float(lb);
+    // ---- E1. posterior means of the next sweep (oracle/mv_oracle.c:mvo_make_params) ----------
+    {
+      // one warp per (view, table): lanes stride over the coordinates of the posterior mean m = S1k / (tau + n),
+      // S1k re-summed from the per-table sums (same order as above, so the same value), write it (and its TF32
+      // split) and reduce |m|^2 by a fixed shuffle tree
+      const int lane = tid & 31, wid = tid >> 5;
+      for (int i = wid; i < V * cap; i += kGroupThreads / 32) {
+        const int v = i >> cshift, t = i & (cap - 1);
+        const int D = c.D[v], k = S.dish[v][t], base = cap * c.doff[v];
+        const int off = base + t * D;
+        const double rden = (k >= 0) ? 1.0 / (tau_v[v] + (double)S.n_vk[v][k]) : 0.0;
+        const double* S1t_v = S1t + base;
+        const unsigned long long mask = (k >= 0) ? S.tmask[v][k] : 0ull;
+        const int t1 = __ffsll((long long)mask) - 1;
+        const unsigned long long more = mask & (mask - 1ull);
+        double mm = 0.0;
+        for (int dd = lane; dd < D; dd += 32) {
+          double s1 = (t1 >= 0) ? S1t_v[t1 * D + dd] : 0.0;
+          for (unsigned long long m = more; m; m &= m - 1ull) s1 += S1t_v[(__ffsll((long long)m) - 1) * D + dd];
+          const float m = (float)(s1 * rden);
+          c.mean[off + dd] = m;
+          if (c.mean_hi) {
+            uint32_t hb, lb;                                            // TF32 split, both parts rounded to nearest
+            asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(hb) : "f"(m));
+            const float hi = __uint_as_float(hb);
+            asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(lb) : "f"(__fadd_rn(m, -hi)));
+            c.mean_hi[off + dd] = hi;
+            c.mean_lo[off + dd] = __uint_as_float(lb);
+          }
+          mm += (double)m * (double)m;
         }
-        mm += (double)m * (double)m;
+  #pragma unroll
+        for (int o = 16; o > 0; o >>= 1) mm += __shfl_xor_sync(0xffffffffu, mm, o);
+        if (lane == 0) S.s1sq[v][t] = mm;               // (s1sq is free again: reused for |m_t|^2)
       }
-#pragma unroll
-      for (int o = 16; o > 0; o >>= 1) mm += __shfl_xor_sync(0xffffffffu, mm, o);
-      if (lane == 0) S.s1sq[v][t] = mm;               // (s1sq is free again: reused for |m_t|^2)
     }
   }
   __syncthreads();
+  for (int i = tid; i < 3 * V + 2; i += kFinThreads) c.hyp[i] = S.hyp[i];
+  stamp(4);
   stamp(10);
   for (int i = tid; i < V * cap; i += kFinThreads) {          // the scalar part, one thread per (view, table)
     const int v = i / cap, t = i - v * cap;
