@@ -499,8 +499,9 @@ def _main(args, out):
         pr = s.get_debug_prof(n_ctas=256)
         print("finalize section stamps (cycles since kernel start: sums|births|dish stats|tau init|hyper|params):",
               pr[200, :6].tolist(), file=sys.stderr)
-        print("finalize sub-stamps (C: deaths|dish counts+masks; D: tau|eppf alpha|eppf sigma; E: means):",
-              {"C": pr[200, 6:8].tolist(), "D": [int(pr[200, 9]), int(pr[200, 11]), int(pr[200, 12])], "E": [int(pr[200, 10])]},
+        print("finalize sub-stamps:",
+              {"C": pr[200, 6:8].tolist(), "lower half: dish stats|tau init|tau": [int(pr[200, 2]), int(pr[200, 3]), int(pr[200, 9])],
+               "upper half (alpha, sigma) done": int(pr[200, 13]), "halves joined": int(pr[200, 4]), "means done": int(pr[200, 10])},
               file=sys.stderr)
         pr = pr[:148]
         names = ["tma.wait_raw_empty", "tma.total", "mma.wait_d_empty", "mma.wait_raw_full", "mma.wait_lo_full", "mma.total",

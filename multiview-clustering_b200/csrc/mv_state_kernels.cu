@@ -563,7 +563,8 @@ __global__ void __launch_bounds__(kFinThreads, 1) k_finalize(const Ctx c, const 
 
   const bool prof = (c.debug_export & 2) != 0 && c.dbg_prof != nullptr && tid == 0;
   long long* pout = c.dbg_prof + 200 * 16;            // slots 200.. of the profile buffer: finalize section stamps
-  const long long t_begin = prof ? clock64() : 0;
+  const long long t_begin_all = clock64();
+  const long long t_begin = prof ? t_begin_all : 0;
   auto stamp = [&](int k) { if (prof) pout[k] = clock64() - t_begin; };
   if (tid == 0) { S.err = 0; S.ncand_total = 0; S.nseat = 0; S.nfree = 0; }
   for (int i = tid; i < 3 * V + 2; i += kFinThreads) S.hyp[i] = c.hyp[i];
@@ -887,6 +888,7 @@ __global__ void __launch_bounds__(kFinThreads, 1) k_finalize(const Ctx c, const 
         if (S.lu[base + 1] < lpn - lpo) S.hyp[is] = s_prop;
       }
     }
+    if ((c.debug_export & 2) != 0 && c.dbg_prof != nullptr && gtid == 0) pout[13] = clock64() - t_begin_all;   // upper half done
   } else {
     // =============================== lower half: dish statistics, tau, means ===============================
     {
