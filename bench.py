@@ -51,8 +51,9 @@ def parse():
     ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--rows", type=int, default=N_ROWS, help="customers per GPU (weak) / in total (strong); default: the named config")
-    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
-                    help="weak: --rows customers per GPU (chain of N x rows); strong: --rows customers split over the GPUs")
+    ap.add_argument("--scaling", default="strong", choices=["weak", "strong"],
+                    help="strong (default; north_star: N = 1M row-sharded over 1/2/4/8 GPUs): --rows customers split over the "
+                         "GPUs, and the weak figure is measured beside it (`weak` sub-record); weak: --rows customers per GPU")
     ap.add_argument("--engine", type=int, default=0, help="0 auto, 1 CUDA-core, 2 tcgen05")
     ap.add_argument("--k-true", type=int, default=CAP, help="planted clusters (default 64 = every table slot in use; "
                     "fewer leaves free slots, so the new-table marginal is evaluated as well)")
@@ -66,10 +67,13 @@ def parse():
     ap.add_argument("--exchange", default="auto", choices=["auto", "p2p", "nccl"],
                     help="N > 1: transport of the once-per-sweep packets: p2p = stores into the peers' memory over NVLink "
                          "(constant ~26 us per sweep; falls back to NCCL if the buffers cannot be mapped), nccl = "
-                         "ncclAllGather (15 us at 2 GPUs, 39 us at 8); auto = nccl below 4 GPUs, p2p from 4 on")
+                         "ncclAllGather (15 us at 2 GPUs, 39 us at 8); auto = p2p")
     ap.add_argument("--no-hyper", action="store_true")
     ap.add_argument("--role-profile", action="store_true", help="print the tcgen05 kernel's per-role wait cycles (debug)")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-weak", action="store_true", help="N > 1: skip the weak-scaling sub-record")
+    ap.add_argument("--no-free-slots", action="store_true", help="N = 1: skip the run with free table slots")
+    ap.add_argument("--no-checks", action="store_true", help="skip the sharded-vs-one-GPU replay and the CPU-mirror spot check")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-rows", type=int, default=0, help="rows of the CPU sample (0: sized for ~15 s)")
     return ap.parse_args()
@@ -111,36 +115,69 @@ def initial_state(z, k_true=CAP):
 
 # ---------------------------------------------------------------------------------------------
 class ClockSampler(threading.Thread):
-    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+    """SM clock and throttle reasons sampled DURING the timed region: NVML (a query takes ~0.1 ms, so that even a
+    20-sweep region of a few milliseconds gets samples), nvidia-smi as the fallback."""
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    BITS = {"hw_slowdown": 0x8, "hw_thermal_slowdown": 0x40, "sw_thermal_slowdown": 0x20, "sw_power_cap": 0x4}
 
     def __init__(self, gpu_index):
         super().__init__(daemon=True)
-        self.gpu, self.rows, self.stop_flag = gpu_index, [], False
+        self.gpu, self.stop_flag = gpu_index, False
+        self.sm, self.mx, self.reasons, self.power = [], [], set(), []
+        self.nvml = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            # NVML enumerates physical devices: honour CUDA_VISIBLE_DEVICES when it lists plain indices
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES", "")
+            idx = gpu_index
+            if vis and all(t.strip().isdigit() for t in vis.split(",")):
+                idx = int(vis.split(",")[gpu_index])
+            self.handle = pynvml.nvmlDeviceGetHandleByIndex(idx)
+            self.mx.append(float(pynvml.nvmlDeviceGetMaxClockInfo(self.handle, pynvml.NVML_CLOCK_SM)))
+            self.nvml = pynvml
+        except Exception:                                       # noqa: BLE001
+            self.nvml = None
+
+    def sample(self):
+        if self.nvml is not None:
+            n = self.nvml
+            self.sm.append(float(n.nvmlDeviceGetClockInfo(self.handle, n.NVML_CLOCK_SM)))
+            try:
+                r = int(n.nvmlDeviceGetCurrentClocksEventReasons(self.handle))
+            except Exception:                                   # noqa: BLE001
+                r = int(n.nvmlDeviceGetCurrentClocksThrottleReasons(self.handle))
+            for name, bit in self.BITS.items():
+                if r & bit:
+                    self.reasons.add(name)
+            try:
+                self.power.append(n.nvmlDeviceGetPowerUsage(self.handle) / 1e3)
+            except Exception:                                   # noqa: BLE001
+                pass
+            return
+        out = subprocess.run(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-i", str(self.gpu)],
+                             capture_output=True, text=True, timeout=5).stdout.strip()
+        r = [x.strip() for x in out.split(",")]
+        if len(r) > 8 and r[1].replace(".", "").isdigit():
+            self.sm.append(float(r[1])); self.mx.append(float(r[2]))
+            for name, val in zip(["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"], r[5:9]):
+                if val.lower().startswith("active"):
+                    self.reasons.add(name)
 
     def run(self):
         while not self.stop_flag:
             try:
-                out = subprocess.run(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-i",
-                                      str(self.gpu)], capture_output=True, text=True, timeout=5).stdout.strip()
-                if out:
-                    self.rows.append([x.strip() for x in out.split(",")])
-            except Exception:
+                self.sample()
+            except Exception:                                   # noqa: BLE001
                 pass
-            time.sleep(0.02)
+            time.sleep(0.0005 if self.nvml is not None else 0.02)
 
     def summary(self):
-        sm = [float(r[1]) for r in self.rows if len(r) > 8 and r[1].replace(".", "").isdigit()]
-        mx = [float(r[2]) for r in self.rows if len(r) > 8 and r[2].replace(".", "").isdigit()]
-        reasons = set()
-        for r in self.rows:
-            if len(r) > 8:
-                for name, val in zip(["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"], r[5:9]):
-                    if val.lower().startswith("active"):
-                        reasons.add(name)
-        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+        return {"sm_mhz": float(np.median(self.sm)) if self.sm else None, "sm_max_mhz": max(self.mx) if self.mx else None,
+                "reasons": sorted(self.reasons), "samples": len(self.sm),
+                "power_w_median": float(np.median(self.power)) if self.power else None,
+                "source": "nvml" if self.nvml is not None else "nvidia-smi"}
 
 
 def measured_peak():
@@ -400,33 +437,60 @@ def _main(args, out):
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
 
-    n_total = args.rows * world if args.scaling == "weak" else args.rows
-    lo, hi = rank * n_total // world, (rank + 1) * n_total // world
-    n_local = hi - lo
     mus = planted_means(np.random.default_rng(SEED))
-    views_np, z = make_rows_numpy(lo, hi, mus, k_true=args.k_true)
-    tab, dish, hyp = initial_state(z, args.k_true)
-    views_pinned = [torch.from_numpy(v).pin_memory() for v in views_np]
-    views_dev = [v.cuda(non_blocking=True) for v in views_pinned]
-    torch.cuda.synchronize()
+    do_hyper = not args.no_hyper
+    peak, peak_src = measured_peak()
 
-    def make_sampler(attach):
-        s = mvc_b200.Sampler(n_local, DIMS, cap=CAP, seed=SEED, device=local_rank, engine=args.engine, rank=rank,
-                             world=world, row_offset=lo, n_rows_global=n_total, debug_export=2 if args.role_profile else 0)
-        if world > 1:
-            uid = [mvc_b200.Sampler.nccl_unique_id() if rank == 0 else None]
-            dist.broadcast_object_list(uid, src=0)
-            s.comm_init_rank(uid[0])
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def shard_of(n_total):
+        return rank * n_total // world, (rank + 1) * n_total // world
+
+    class Workload:
+        """One chain of n_total customers, this rank's shard resident on its GPU."""
+        def __init__(self, n_total, k_true):
+            self.n_total, self.k_true = n_total, k_true
+            self.lo, self.hi = shard_of(n_total)
+            self.n_local = self.hi - self.lo
+            views_np, z = make_rows_numpy(self.lo, self.hi, mus, k_true=k_true)
+            self.tab, self.dish, self.hyp = initial_state(z, k_true)
+            self.pinned = [torch.from_numpy(v).pin_memory() for v in views_np]
+            self.dev = [v.cuda(non_blocking=True) for v in self.pinned]
+            torch.cuda.synchronize()
+
+        def set_state(self, s):
+            h = self.hyp
+            s.set_state(self.tab, self.dish, h["alpha_v"], h["sigma_v"], h["tau_v"], h["alpha_g"], h["sigma_g"])
+
+    comm_owner = []          # the first multi-GPU sampler owns the NCCL communicator; the others borrow it
+
+    def make_sampler(w, attach, debug_export=0, single=False):
+        """single: a one-GPU chain over this rank's rows only (checks that need no peers)."""
+        ww, rr = (1, 0) if single else (world, rank)
+        s = mvc_b200.Sampler(w.n_local, DIMS, cap=CAP, seed=SEED, device=local_rank, engine=args.engine, rank=rr,
+                             world=ww, row_offset=0 if single else w.lo, n_rows_global=w.n_local if single else w.n_total,
+                             debug_export=debug_export)
+        if ww > 1:
+            if comm_owner:
+                s.comm_attach(comm_owner[0].comm_handle())
+            else:
+                uid = [mvc_b200.Sampler.nccl_unique_id() if rank == 0 else None]
+                dist.broadcast_object_list(uid, src=0)
+                s.comm_init_rank(uid[0])
+                comm_owner.append(s)
         if attach:
             for v in range(len(DIMS)):
-                s.attach_view_device(v, views_dev[v])
+                s.attach_view_device(v, w.dev[v])
         return s
 
     transport = {"used": "none" if world == 1 else "nccl"}
 
     def enable_p2p(s):
         """Peer-memory exchange: every rank exports its receive buffer, all map all."""
-        want = args.exchange if args.exchange != "auto" else ("p2p" if world >= 4 else "nccl")
+        want = args.exchange if args.exchange != "auto" else "p2p"
         if world == 1 or want != "p2p":
             return
         ok = 1
@@ -452,57 +516,58 @@ def _main(args, out):
         elif ok:
             s.p2p_disable()                                     # a peer could not map the buffers: everybody uses NCCL
 
-    do_hyper = not args.no_hyper
-    s = make_sampler(attach=True)
-    enable_p2p(s)
-    s.set_state(tab, dish, hyp["alpha_v"], hyp["sigma_v"], hyp["tau_v"], hyp["alpha_g"], hyp["sigma_g"])
-    s.sweep(args.warmup, do_hyper)
-    s.sync()
-
-    def barrier():
+    def timed_run(w, steps, warmup, sample_clocks):
+        """W warm-up sweeps, then `steps` sweeps timed on the device (CUDA events on the library's stream, barrier and
+        synchronize on both sides, max over ranks)."""
+        s = make_sampler(w, attach=True, debug_export=2 if args.role_profile else 0)
+        enable_p2p(s)
+        w.set_state(s)
+        s.sweep(warmup, do_hyper)
+        s.sync()
+        clocks = ClockSampler(local_rank) if sample_clocks else None
+        barrier()
+        if clocks:
+            clocks.start()
+        l0 = s.launch_count()
+        t_wall = time.perf_counter()
+        s.sweep(steps, do_hyper)
+        s.sync()
+        barrier()
+        wall_ms = 1e3 * (time.perf_counter() - t_wall)
+        if clocks:
+            clocks.stop_flag = True
+        t = torch.tensor([s.last_sweep_ms()], device="cuda")
         if dist is not None:
-            dist.barrier()
-        torch.cuda.synchronize()
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dev_ms = float(t.item())
+        prof = [s.profile_sweep(do_hyper) for _ in range(5)]      # per-kernel device times of a few extra sweeps
+        kern = {k: float(np.median([p[k] for p in prof])) for k in prof[0]}
+        return {"s": s, "dev_ms": dev_ms, "wall_ms": wall_ms, "launches": s.launch_count() - l0, "kern": kern,
+                "clocks": clocks.summary() if clocks else None}
 
-    clocks = ClockSampler(local_rank)
-    barrier()
-    clocks.start()
-    l0 = s.launch_count()
-    t_wall = time.perf_counter()
-    s.sweep(args.steps, do_hyper)           # K sweeps, CUDA events around them on the library's stream
-    s.sync()
-    barrier()
-    wall_ms = 1e3 * (time.perf_counter() - t_wall)
-    clocks.stop_flag = True
-    dev_ms = s.last_sweep_ms()
-    launches = s.launch_count() - l0
-    t = torch.tensor([dev_ms], device="cuda")
-    if dist is not None:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    dev_ms = float(t.item())
-    ms_per_step = dev_ms / args.steps
-    updates = n_total * len(DIMS) * CAP
-    value = updates * args.steps / (dev_ms * 1e-3)
-
-    # per-kernel device times of a few extra sweeps (CUDA events between the launches)
-    prof = [s.profile_sweep(do_hyper) for _ in range(5)]
-    kern = {k: float(np.median([p[k] for p in prof])) for k in prof[0]}
-    peak, peak_src = measured_peak()
-    alg_bytes = n_local * (sum(DIMS) * 4 + 8)
-    achieved = alg_bytes / (kern["draw"] * 1e-3) / 1e9
-    roofline = {"bound": "hbm", "kernel": "likelihood+draw", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                "frac": achieved / peak, "traffic": NCU_TRAFFIC_BYTES * n_local / N_ROWS if args.engine in (0, 2, 3) else None,
+    def roofline_of(w, kern, traffic):
+        alg_bytes = w.n_local * (sum(DIMS) * 4 + 8)
+        achieved = alg_bytes / (kern["draw"] * 1e-3) / 1e9
+        return {"bound": "hbm", "kernel": "likelihood+draw", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                "frac": achieved / peak, "traffic": traffic,
                 "traffic_source": "ncu --set full, dram__bytes_read.sum + dram__bytes_write.sum of k_draw_tc at N=1M "
-                                  "(profiles/r01_ncu_final.md), scaled to this shard", "peak_source": peak_src,
-                "algorithmic_bytes_per_launch": alg_bytes, "kernel_ms": kern}
+                                  "(profiles/), scaled to this shard", "peak_source": peak_src,
+                "algorithmic_bytes_per_launch": alg_bytes, "kernel_ms": kern, "planted_clusters": w.k_true,
+                "free_table_slots": CAP - w.k_true}
+
+    # ---------------- the headline run: `--scaling` (default strong: north_star's N = 1M split over the GPUs) ----------
+    n_total = args.rows * world if args.scaling == "weak" else args.rows
+    W = Workload(n_total, args.k_true)
+    R = timed_run(W, args.steps, args.warmup, sample_clocks=True)
+    s = R["s"]
+    ms_per_step = R["dev_ms"] / args.steps
+    updates = n_total * len(DIMS) * CAP
+    value = updates * args.steps / (R["dev_ms"] * 1e-3)
+    traffic = NCU_TRAFFIC_BYTES * W.n_local / N_ROWS if args.engine in (0, 2, 3) else None
+    roofline = roofline_of(W, R["kern"], traffic)
     if args.role_profile and rank == 0:
         pr = s.get_debug_prof(n_ctas=256)
-        print("finalize section stamps (cycles since kernel start: sums|births|dish stats|tau init|hyper|params):",
-              pr[200, :6].tolist(), file=sys.stderr)
-        print("finalize sub-stamps:",
-              {"C": pr[200, 6:8].tolist(), "lower half: dish stats|tau init|tau": [int(pr[200, 2]), int(pr[200, 3]), int(pr[200, 9])],
-               "upper half (alpha, sigma) done": int(pr[200, 13]), "halves joined": int(pr[200, 4]), "means done": int(pr[200, 10])},
-              file=sys.stderr)
+        print("finalize stamps:", pr[200, :16].tolist(), file=sys.stderr)
         pr = pr[:148]
         names = ["tma.wait_raw_empty", "tma.total", "mma.wait_d_empty", "mma.wait_raw_full", "mma.wait_lo_full", "mma.total",
                  "conv0.wait_raw_full", "conv0.wait_lo_empty", "conv0.total", "conv1.wait_raw_full", "conv1.wait_lo_empty",
@@ -510,36 +575,111 @@ def _main(args, out):
         med = np.median(pr, axis=0)
         print("role profile (median cycles over CTAs):", {n: int(m) for n, m in zip(names, med)}, file=sys.stderr)
     final = s.get_state(with_rows=False)
-    s.close()
+    state_check = {"tables_live": int((final["n_t"] > 0).sum()), "customers": int(final["n_t"].sum())}
+    if not comm_owner or comm_owner[0] is not s:
+        s.close()
 
-    # e2e: the reference-facing call with host buffers (upload + state + K sweeps + read-back), every rank
+    # ---------------- the same kernel with free table slots (the new-table marginal is evaluated): one GPU only ---------
+    roofline_free = None
+    if world == 1 and not args.no_free_slots and args.k_true == CAP:
+        Wf = Workload(n_total, CAP - 4)
+        Rf = timed_run(Wf, min(args.steps, 200), min(args.warmup, 5), sample_clocks=False)
+        roofline_free = roofline_of(Wf, Rf["kern"], None)
+        roofline_free["ms_per_step"] = Rf["dev_ms"] / min(args.steps, 200)
+        Rf["s"].close()
+        del Wf, Rf
+
+    # ---------------- weak scaling beside it (N > 1): one C3-sized shard per GPU ---------------------------------------
+    weak = None
+    if world > 1 and args.scaling == "strong" and not args.no_weak:
+        Ww = Workload(args.rows * world, args.k_true)
+        kw = min(args.steps, 200)
+        Rw = timed_run(Ww, kw, min(args.warmup, 5), sample_clocks=False)
+        weak = {"scaling": "weak", "rows_total": Ww.n_total, "rows_per_gpu": Ww.n_local, "steps": kw,
+                "ms_per_step": Rw["dev_ms"] / kw, "value": Ww.n_total * len(DIMS) * CAP * kw / (Rw["dev_ms"] * 1e-3),
+                "unit": UNIT, "kernel_ms": Rw["kern"]}
+        if not comm_owner or comm_owner[0] is not Rw["s"]:
+            Rw["s"].close()
+        del Ww, Rw
+
+    # ---------------- checks outside every timed region ------------------------------------------------------------------
+    # (1) sharded chain against the same chain on one GPU (N > 1): every rank runs K sweeps sharded, rank 0 replays them
+    #     unsharded over all rows; the draws are addressed by global row, so sweep 1 must be identical.
+    if world > 1 and not args.no_checks:
+        kc = max(2, min(args.steps, 20))
+        s3 = make_sampler(W, attach=True)
+        if transport["used"] == "p2p":
+            enable_p2p(s3)
+        W.set_state(s3)
+        s3.sweep(1, do_hyper)
+        t1 = s3.get_state()["table_of"]
+        s3.sweep(kc - 1, do_hyper)
+        st3 = s3.get_state()
+        parts = [None] * world
+        dist.all_gather_object(parts, (W.lo, t1, st3["table_of"], st3["n_t"], st3["tau_v"]))
+        s3.close()
+        if rank == 0:
+            parts.sort(key=lambda p: p[0])
+            tab1 = np.concatenate([p[1] for p in parts])
+            tabK = np.concatenate([p[2] for p in parts])
+            full_views, zfull = make_rows_numpy(0, n_total, mus, k_true=args.k_true)
+            tab0, dish0, hyp0 = initial_state(zfull, args.k_true)
+            one = mvc_b200.Sampler(n_total, DIMS, cap=CAP, seed=SEED, device=local_rank, engine=args.engine)
+            for v in range(len(DIMS)):
+                one.upload_view(v, full_views[v])
+            one.set_state(tab0, dish0, hyp0["alpha_v"], hyp0["sigma_v"], hyp0["tau_v"], hyp0["alpha_g"], hyp0["sigma_g"])
+            one.sweep(1, do_hyper)
+            a1 = float((one.get_state()["table_of"] == tab1).mean())
+            one.sweep(kc - 1, do_hyper)
+            ref = one.get_state()
+            one.close()
+            del full_views
+            state_check.update({"sharded_vs_one_gpu_sweeps": kc, "first_sweep_identical": bool(a1 == 1.0),
+                                "first_sweep_agreement": a1,
+                                "agreement_after_K": float((ref["table_of"] == tabK).mean()),
+                                "replicas_identical": bool(all(np.array_equal(p[3], parts[0][3]) and
+                                                               np.array_equal(p[4], parts[0][4]) for p in parts)),
+                                "tau_rel_diff_vs_one_gpu": float(np.max(np.abs(ref["tau_v"] - parts[0][4]) / ref["tau_v"]))})
+    # (2) draws of one sweep at full size against the CPU mirror (oracle/mv_oracle.c), fed the device's dot products and
+    #     the same Philox uniforms, on the rows of 12 CTAs spread over the grid (first, middle, last) plus the ragged tail.
+    if rank == 0 and not args.no_checks:
+        state_check.update(spot_check_draws(mvc_b200, W, local_rank, args.engine))
+
+    # ---------------- e2e: one chain through the C ABI with HOST buffers ---------------------------------------------------
     e2e = None
     if not args.no_e2e:
-        k_e2e = args.steps
-        s2 = make_sampler(attach=False)          # handle + NCCL communicator: one-time setup, not part of a chain's run
+        k_e2e = max(args.steps, 200)
+        thin = max(1, k_e2e // 4)
+        s2 = make_sampler(W, attach=False)       # handle (+ borrowed communicator): set-up, not part of a chain's run
         barrier()
         t0 = time.perf_counter()
         for v in range(len(DIMS)):
-            s2.upload_view(v, views_pinned[v].numpy())
+            s2.upload_view(v, W.pinned[v].numpy())
         if transport["used"] == "p2p":
             enable_p2p(s2)
-        s2.set_state(tab, dish, hyp["alpha_v"], hyp["sigma_v"], hyp["tau_v"], hyp["alpha_g"], hyp["sigma_g"])
-        s2.sweep(k_e2e, do_hyper)
-        final2 = s2.get_state(with_rows=True)
+        t_up = time.perf_counter()
+        W.set_state(s2)
+        t_st = time.perf_counter()
+        trace = s2.run(k_e2e, 0, thin)           # gibbs_sampler(M, burn_in, thin): D2H of table_of on every kept sweep
         barrier()
         dt = time.perf_counter() - t0
+        parts_s = {"upload": t_up - t0, "set_state": t_st - t_up, "run": t0 + dt - t_st}
         tt = torch.tensor([dt], device="cuda")
         if dist is not None:
             dist.all_reduce(tt, op=dist.ReduceOp.MAX)
         dt = float(tt.item())
-        h2d = n_local * (sum(DIMS) * 4 + 4)
-        d2h = n_local * 4
+        n_saved = int(trace["table_of"].shape[0])
+        h2d = W.n_local * (sum(DIMS) * 4 + 4)
+        d2h = W.n_local * 4 * n_saved
         e2e = {"value": updates * k_e2e / dt, "unit": UNIT, "h2d_bytes_per_step": h2d / k_e2e,
-               "d2h_bytes_per_step": d2h / k_e2e, "sweeps": k_e2e, "seconds": dt,
-               "note": "one chain run through the C ABI with host buffers: H2D of all views (pinned) + table_of, K sweeps, "
-                       "D2H of table_of; wall clock, device allocation included; bytes are per sweep (total / K)"}
-        assert int(final2["n_t"].sum()) == n_total
+               "d2h_bytes_per_step": d2h / k_e2e, "sweeps": k_e2e, "saved_states": n_saved, "seconds": dt, "seconds_by_part": parts_s,
+               "note": "one chain through the C ABI (mvg_upload_view_f32 from pinned host memory, mvg_set_state, mvg_run = "
+                       "gibbs_sampler(M, burn_in=0, thin) with the D2H of table_of on every kept sweep); wall clock, device "
+                       "allocation included; bytes are per sweep (total / M)"}
+        assert int(np.bincount(trace["table_of"][-1], minlength=CAP).sum()) == W.n_local
         s2.close()
+    for s_ in comm_owner:
+        s_.close()
 
     cpu = None
     if rank == 0 and not args.no_cpu_baseline:
@@ -554,16 +694,57 @@ def _main(args, out):
                 "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None,
                 "dtype": "f32", "data": "synthetic",
                 "config": {"workload": "C3: synthetic 3-view Gaussian mixture, N=%d (%d per GPU), D=64/view, K(cap)=64, row-sharded, "
-                                       "one NCCL all-gather of the per-table statistics per sweep" % (n_total, n_local),
-                           "rows_per_gpu": n_local, "hyper_step": do_hyper, "engine": args.engine, "planted_clusters": args.k_true,
-                           "l2": "inputs (768 MB per sweep) larger than L2; no flush", "exchange": transport["used"]},
-                "sweeps_per_s": args.steps / (dev_ms * 1e-3), "wall_ms_per_step": wall_ms / args.steps,
-                "clocks": clocks.summary(), "gpu_launches": int(launches),
-                "roofline": roofline, "e2e": e2e, "cpu_baseline": cpu,
-                "state_check": {"tables_live": int((final["n_t"] > 0).sum()), "customers": int(final["n_t"].sum())}}
+                                       "one exchange of the per-table statistics per sweep" % (n_total, W.n_local),
+                           "rows_per_gpu": W.n_local, "hyper_step": do_hyper, "engine": args.engine, "planted_clusters": args.k_true,
+                           "l2": "inputs (768 MB per sweep at N=1M) larger than L2; no flush", "exchange": transport["used"]},
+                "sweeps_per_s": args.steps / (R["dev_ms"] * 1e-3), "wall_ms_per_step": R["wall_ms"] / args.steps,
+                "clocks": R["clocks"], "gpu_launches": int(R["launches"]),
+                "roofline": roofline, "roofline_free_slots": roofline_free, "weak": weak, "e2e": e2e, "cpu_baseline": cpu,
+                "state_check": state_check}
         print(json.dumps(line), file=out)
     if dist is not None:
         dist.destroy_process_group()
+
+
+def spot_check_draws(mvc_b200, W, device, engine):
+    """One sweep of a debug handle over this rank's rows (a one-GPU chain), then the CPU mirror of the draw stage on the
+    rows of 12 CTAs of the draw kernel's grid and on the last tile: integer draws must be identical."""
+    sys.path.insert(0, str(ROOT / "oracle"))
+    import pyoracle as po
+    n = W.n_local
+    s = mvc_b200.Sampler(n, DIMS, cap=CAP, seed=SEED, device=device, engine=engine, debug_export=1)
+    for v in range(len(DIMS)):
+        s.attach_view_device(v, W.dev[v])
+    W.set_state(s)
+    s.sweep(1, True)                         # leave the planted state once, so that rows sit at wrong tables too
+    pre = s.get_state()
+    P = s.get_params()
+    s.sweep(1, True)
+    acc, xx, raw = s.get_debug_rows()
+    s.close()
+    n_tiles = (n + 127) // 128
+    grid = min(148, n_tiles)
+    ctas = sorted({c for c in (0, 1, 2, 3, grid // 2 - 1, grid // 2, grid // 2 + 1, grid // 2 + 2, grid - 4, grid - 3,
+                               grid - 2, grid - 1) if 0 <= c < grid})
+    tiles = sorted({t for c in ctas for t in range(c, n_tiles, grid)} | {n_tiles - 1})
+    rows = np.concatenate([np.arange(t * 128, min(n, (t + 1) * 128)) for t in tiles])
+    ps = po.params_struct(P)
+    L = po.lib()
+    bad = 0
+    for i in rows:
+        u = L.mvo_uf(SEED, 0, 0, 0, pre["sweep"], int(i))
+        bad += int(po.stageB_f32(ps, acc[i], xx[i], pre["table_of"][i], u) != raw[i])
+    # dot products against FP64 on a subset (tolerance: 2^-18 of sum |x||m|, DESIGN.md §5)
+    sub = rows[:: max(1, len(rows) // 4096)]
+    worst = 0.0
+    for v in range(len(DIMS)):
+        x = W.pinned[v].numpy()[sub].astype(np.float64)
+        m = P["m"][v].astype(np.float64)
+        ref = x @ m.T
+        bound = np.abs(x) @ np.abs(m).T
+        worst = max(worst, float(np.max(np.abs(acc[sub, v, :] - ref) / bound)))
+    return {"draws_checked_rows": int(len(rows)), "draws_bit_exact_rows": int(len(rows) - bad), "draws_mismatched": int(bad),
+            "dot_rel_err_max": worst, "dot_rel_err_bound": 2.0 ** -18, "rows_moved_in_checked_sweep": int((raw != pre["table_of"]).sum())}
 
 
 if __name__ == "__main__":

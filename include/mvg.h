@@ -156,20 +156,33 @@ int mvg_run(mvg_handle* h, int32_t M, int32_t burn_in, int32_t thin, int32_t n_s
 /* Attach an initialised NCCL communicator (ncclComm_t passed as void*) whose rank/size match the
  * config.  Without one, world must be 1.  The library issues one all-gather per sweep on it. */
 int mvg_comm_attach(mvg_handle* h, void* nccl_comm);
+/* The communicator this handle uses (ncclComm_t as void*, NULL if none): several handles of one process (chains,
+ * or a second run over the same ranks) can share it through mvg_comm_attach; its owner must outlive the borrowers. */
+void* mvg_comm_handle(mvg_handle* h);
 /* Convenience for callers without their own NCCL: unique_id is the 128-byte ncclUniqueId made by
  * mvg_comm_unique_id on rank 0 and distributed by the caller (e.g. over torch.distributed/gloo). */
 int mvg_comm_unique_id(void* unique_id_128);
 int mvg_comm_init_rank(mvg_handle* h, const void* unique_id_128);
 
-/* Peer-memory transport for the same exchange (optional, one node): instead of ncclAllGather every rank stores its
- * packet straight into its peers' receive buffers over NVLink and raises a flag there; k_finalize's input is assembled
- * from the local buffer (csrc/mv_exchange.cu).  Setup, after the views are known: every rank calls mvg_comm_p2p_export
- * (a 64-byte cudaIpcMemHandle_t comes back), the caller all-gathers the handles in rank order and gives the world x 64
- * bytes to mvg_comm_p2p_attach on every rank.  Without it (or with world = 1) the NCCL path is used. */
+/* Peer-memory transport for the same exchange (optional, one node): instead of reduce + ncclAllGather + sum, ONE kernel
+ * (csrc/mv_exchange.cu) stores every reduced value straight into its peers' receive buffers over NVLink as 8-byte
+ * {payload, sequence number} words and adds the peers' words in rank order as they arrive; the results are bit-identical
+ * to the NCCL transport.  With it the whole sweep is one CUDA graph also for world > 1.
+ * Setup, after the views are known: every rank calls mvg_comm_p2p_export (a 64-byte cudaIpcMemHandle_t comes back), the
+ * caller all-gathers the handles in rank order and gives the world x 64 bytes to mvg_comm_p2p_attach on every rank (once
+ * per handle: the mappings and the exchange sequence number live until mvg_destroy; a second attach is MVG_ESTATE).
+ * mvg_comm_p2p_disable / mvg_comm_p2p_enable switch between this transport and NCCL; every rank must switch at the same
+ * point of the chain.
+ * Failure: a peer whose words do not arrive within 2 s (%globaltimer) raises a STICKY fault on this handle: the device
+ * publishes nothing further (the chain stays frozen at this rank's last completed sweep), mvg_sweep refuses to queue
+ * more work and mvg_sync / mvg_get_state / mvg_run return MVG_ENCCL.  mvg_clear_fault re-arms the handle once the
+ * caller has brought the ranks back to a common state (e.g. mvg_set_state on every rank). */
 int mvg_prepare(mvg_handle* h);                       /* fix the layout now (all views uploaded/attached) */
 int mvg_comm_p2p_export(mvg_handle* h, void* ipc_handle_64);
 int mvg_comm_p2p_attach(mvg_handle* h, const void* all_handles);
 int mvg_comm_p2p_disable(mvg_handle* h);              /* back to the NCCL transport (e.g. a peer failed to attach) */
+int mvg_comm_p2p_enable(mvg_handle* h);               /* peer-memory transport again (mappings are kept) */
+int mvg_clear_fault(mvg_handle* h);
 
 /* ---- inspection (tests, profiling) ----------------------------------------------------- */
 /* The FP32 parameter block of the NEXT sweep, as the likelihood kernel will read it; pointers

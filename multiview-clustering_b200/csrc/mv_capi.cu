@@ -91,7 +91,8 @@ struct mvg_handle {
   unsigned char* xrecv = nullptr;    // this rank's receive buffer (cudaMalloc, exported through CUDA IPC)
   XchgPeers xpeers{};                // every rank's receive buffer as mapped here ([rank] = xrecv)
   bool xp2p = false;
-  uint32_t xseq = 0;
+  bool xattached = false;            // peer mappings exist (they live until mvg_destroy)
+  int32_t* host_fault = nullptr;     // mapped pinned host word: the sticky exchange fault, readable without a sync
 };
 
 namespace {
@@ -148,6 +149,7 @@ int ensure_layout(mvg_handle* h) {
   A(c.n_t, cap); A(c.dish_of, V * cap); A(c.n_vk, V * cap); A(c.l_vk, V * cap);
   A(c.S1t, cap * dsum); A(c.S2t, V * cap); A(c.S1k, cap * dsum); A(c.S2k, V * cap);
   A(c.hyp, 3 * V + 2); A(c.sweep, 1); A(c.status, 4);
+  A(c.sum_cnt, cap); A(c.sum_s1t, cap * dsum); A(c.sum_s2t, V * cap); A(c.xseq, 1); A(c.fin_arrive, 1);
   A(c.tparam, V * cap); A(c.vparam, V); A(c.tmass, cap); A(c.gparam, 1); A(c.tsame, V * cap);
   A(c.mean, cap * dsum); A(c.mean_hi, cap * dsum); A(c.mean_lo, cap * dsum);
   A(c.partial_f, (size_t)c.stat_ctas * (cap * dsum + V * cap)); A(c.partial_n, (size_t)c.stat_ctas * cap);
@@ -190,38 +192,41 @@ int ensure_layout(mvg_handle* h) {
   return MVG_OK;
 }
 
-int exchange(mvg_handle* h) {
-  if (h->c.world == 1) return MVG_OK;
-  if (h->xp2p) {                     // packets pushed straight into the peers' memory over NVLink
-    h->xseq += 1;
-    MVG_CUDA(h, launch_exchange_p2p(h->c, h->xpeers, h->xrecv, h->xseq, h->stream));
+// This shard's statistics -> totals over all shards (csrc/mv_exchange.cu).  One launch with the peer-memory
+// transport or on one GPU; reduce, ncclAllGather, rank-ordered sums with the NCCL transport.
+int reduce_exchange(mvg_handle* h, cudaEvent_t* marks) {
+  const Ctx& c = h->c;
+  if (c.world == 1 || h->xp2p) {
+    MVG_CUDA(h, launch_reduce_x(c, c.world == 1 ? 0 : 1, h->xpeers, h->xrecv, h->stream));
     h->launches += 1;
+    if (marks) { MVG_CUDA(h, cudaEventRecord(marks[1], h->stream)); MVG_CUDA(h, cudaEventRecord(marks[2], h->stream)); }
     return MVG_OK;
   }
-  if (!h->comm) return fail(h, MVG_ESTATE, "world > 1 but no NCCL communicator attached");
-  unsigned char* base = h->c.packet;
-  int r = g_nccl.AllGather(base + (size_t)h->c.rank * h->c.pkt.bytes, base, (size_t)h->c.pkt.bytes, /*ncclChar*/ 0,
-                           h->comm, h->stream);
+  if (!h->comm) return fail(h, MVG_ESTATE, "world > 1 but neither an NCCL communicator nor peer buffers are attached");
+  MVG_CUDA(h, launch_reduce_x(c, 0, h->xpeers, h->xrecv, h->stream));
+  if (marks) MVG_CUDA(h, cudaEventRecord(marks[1], h->stream));
+  unsigned char* base = c.packet;
+  int r = g_nccl.AllGather(base + (size_t)c.rank * c.pkt.bytes, base, (size_t)c.pkt.bytes, /*ncclChar*/ 0, h->comm, h->stream);
   if (r != 0) return fail(h, MVG_ENCCL, std::string("ncclAllGather: ") + (g_nccl.GetErrorString ? g_nccl.GetErrorString(r) : "?"));
+  MVG_CUDA(h, launch_reduce_x(c, 2, h->xpeers, h->xrecv, h->stream));
+  if (marks) MVG_CUDA(h, cudaEventRecord(marks[2], h->stream));
+  h->launches += 2;
   return MVG_OK;
 }
 
-// stats -> reduce -> exchange -> finalize: shared by sweeps, set_state and init
+// stats -> reduce + exchange -> finalize: shared by sweeps, set_state and init
 int rebuild_pipeline(mvg_handle* h, int32_t flags, cudaEvent_t* marks /* 4 events or null */) {
   MVG_CUDA(h, launch_stats(h->c, h->stream));
   if (marks) MVG_CUDA(h, cudaEventRecord(marks[0], h->stream));
-  MVG_CUDA(h, launch_reduce(h->c, h->stream));
-  if (marks) MVG_CUDA(h, cudaEventRecord(marks[1], h->stream));
-  int rc = exchange(h);
+  int rc = reduce_exchange(h, marks);
   if (rc != MVG_OK) return rc;
-  if (marks) MVG_CUDA(h, cudaEventRecord(marks[2], h->stream));
   MVG_CUDA(h, launch_finalize(h->c, flags, h->stream));
   if (h->c.n_count_views) {          // count views: word counts by the final seating, then the log2 theta tables
     MVG_CUDA(h, launch_counts_rebuild(h->c, h->stream));
     h->launches += 2;
   }
   if (marks) MVG_CUDA(h, cudaEventRecord(marks[3], h->stream));
-  h->launches += 3;
+  h->launches += 2;
   return MVG_OK;
 }
 
@@ -237,8 +242,11 @@ int check_status(mvg_handle* h) {
   int32_t st[4] = {0, 0, 0, 0};
   MVG_CUDA(h, cudaMemcpyAsync(st, h->c.status, sizeof(st), cudaMemcpyDeviceToHost, h->stream));
   MVG_CUDA(h, cudaStreamSynchronize(h->stream));
+  if (st[1] != 0)
+    return fail(h, MVG_ENCCL, "exchange fault (sticky): a peer's statistics did not arrive within the wait limit; this rank's chain is "
+                              "frozen at its last completed sweep (mvg_get_state still reads it after mvg_clear_fault)");
   if (st[0] != 0) {
-    MVG_CUDA(h, cudaMemsetAsync(h->c.status, 0, sizeof(st), h->stream));
+    MVG_CUDA(h, cudaMemsetAsync(h->c.status, 0, sizeof(int32_t), h->stream));
     return fail(h, MVG_EINVAL, "device-side invariant violated, flags=" + std::to_string(st[0]) +
                                    " (1: no free dish slot for a birth, 2: live table without a dish, 4: customers lost in the statistics rebuild, "
                                    "8: a peer's packet never arrived in the peer-memory exchange)");
@@ -308,6 +316,18 @@ int mvg_create(const mvg_config* cfg, mvg_handle** out) {
     h->owned.push_back(q);
     c.xx = static_cast<float*>(q);
   }
+  if (c.world > 1) {                               // the sticky exchange fault, mirrored where the host reads it without a sync
+    void* hp = nullptr;
+    void* dp = nullptr;
+    if (cudaHostAlloc(&hp, 64, cudaHostAllocMapped) == cudaSuccess && cudaHostGetDevicePointer(&dp, hp, 0) == cudaSuccess) {
+      std::memset(hp, 0, 64);
+      h->host_fault = static_cast<int32_t*>(hp);
+      c.host_fault = static_cast<int32_t*>(dp);
+    } else {
+      cudaGetLastError();
+      if (hp) cudaFreeHost(hp);
+    }
+  }
   *out = h;
   return MVG_OK;
 }
@@ -320,6 +340,7 @@ int mvg_destroy(mvg_handle* h) {
   for (int g = 0; g < h->c.world && g < 16; ++g)
     if (g != h->c.rank && h->xpeers.recv[g]) cudaIpcCloseMemHandle(h->xpeers.recv[g]);
   if (h->xrecv) cudaFree(h->xrecv);
+  if (h->host_fault) cudaFreeHost(h->host_fault);
   for (auto& g : h->sweep_graph) if (g) cudaGraphExecDestroy(g);
   for (void* p : h->owned) cudaFree(p);
   for (void* p : h->view_owned) if (p) cudaFree(p);
@@ -569,7 +590,10 @@ int one_sweep(mvg_handle* h, int32_t flags) {
 // stream usable, if anything about the capture fails: the caller then launches the kernels directly.
 bool ensure_sweep_graph(mvg_handle* h, int which, int32_t flags) {
   if (h->sweep_graph[which]) return true;
-  if (!h->graphs_ok || h->c.world != 1 || (h->c.debug_export & 2)) return false;
+  if (!h->graphs_ok || (h->c.debug_export & 2)) return false;
+  // NCCL transport: launched directly (a collective captured into the sweep graph did not complete on this stack);
+  // the peer-memory transport is an ordinary kernel and is captured with the rest of the sweep
+  if (h->c.world != 1 && !h->xp2p) return false;
   static const bool disabled = [] { const char* e = getenv("MVG_NO_GRAPHS"); return e && e[0] == '1'; }();
   if (disabled) { h->graphs_ok = false; return false; }
   const int64_t before = h->launches;
@@ -593,6 +617,8 @@ int mvg_sweep(mvg_handle* h, int32_t n_sweeps, int32_t do_hyper) {
   if (!h) return MVG_EINVAL;
   if (!h->state_ready) return fail(h, MVG_ESTATE, "no state yet: call mvg_set_state or mvg_init_state_reference");
   if (n_sweeps < 0) return fail(h, MVG_EINVAL, "n_sweeps < 0");
+  if (h->host_fault && *reinterpret_cast<volatile int32_t*>(h->host_fault) != 0)
+    return fail(h, MVG_ENCCL, "exchange fault (sticky): a peer's statistics did not arrive; no further sweeps on this handle");
   MVG_CUDA(h, cudaSetDevice(h->cfg.device));
   const int32_t flags = kFinReseat | kFinAdvance | (do_hyper ? kFinHyperAll : 0);
   const int which = do_hyper ? 1 : 0;
@@ -634,6 +660,18 @@ int mvg_sync(mvg_handle* h) {
   if (!h) return MVG_EINVAL;
   MVG_CUDA(h, cudaSetDevice(h->cfg.device));
   MVG_CUDA(h, cudaStreamSynchronize(h->stream));
+  if (h->host_fault && *reinterpret_cast<volatile int32_t*>(h->host_fault) != 0)
+    return fail(h, MVG_ENCCL, "exchange fault (sticky): a peer's statistics did not arrive within the wait limit");
+  return MVG_OK;
+}
+
+int mvg_clear_fault(mvg_handle* h) {
+  if (!h) return MVG_EINVAL;
+  MVG_CUDA(h, cudaSetDevice(h->cfg.device));
+  MVG_CUDA(h, cudaStreamSynchronize(h->stream));
+  MVG_CUDA(h, cudaMemsetAsync(h->c.status, 0, sizeof(int32_t) * 4, h->stream));
+  MVG_CUDA(h, cudaStreamSynchronize(h->stream));
+  if (h->host_fault) *h->host_fault = 0;
   return MVG_OK;
 }
 
@@ -673,6 +711,8 @@ int mvg_comm_attach(mvg_handle* h, void* nccl_comm) {
   return MVG_OK;
 }
 
+void* mvg_comm_handle(mvg_handle* h) { return h ? h->comm : nullptr; }
+
 int mvg_comm_unique_id(void* unique_id_128) {
   std::string err;
   if (!unique_id_128) return MVG_EINVAL;
@@ -706,13 +746,14 @@ int mvg_comm_p2p_export(mvg_handle* h, void* ipc_handle_64) {
   if (!h || !ipc_handle_64) return MVG_EINVAL;
   if (h->c.world < 2) return fail(h, MVG_EINVAL, "peer exchange needs world > 1");
   MVG_CUDA(h, cudaSetDevice(h->cfg.device));
-  int rc = ensure_layout(h);                       // the packet size depends on the views
+  int rc = ensure_layout(h);                       // the slot size depends on the views
   if (rc != MVG_OK) return rc;
   if (!h->xrecv) {
-    const size_t bytes = (size_t)2 * h->c.world * h->c.pkt.bytes + (size_t)2 * h->c.world * sizeof(uint32_t) + 256;
+    const XchgLayout L = xchg_layout(h->c);
+    const size_t bytes = (size_t)2 * h->c.world * (size_t)L.slot_bytes;
     void* q = nullptr;
     if (cudaMalloc(&q, bytes) != cudaSuccess) return fail(h, MVG_ENOMEM, "cudaMalloc: exchange buffer");
-    MVG_CUDA(h, cudaMemset(q, 0, bytes));
+    MVG_CUDA(h, cudaMemset(q, 0, bytes));          // flag 0 never equals a sequence number (they start at 1)
     h->xrecv = static_cast<unsigned char*>(q);
   }
   static_assert(sizeof(cudaIpcMemHandle_t) == 64, "CUDA IPC handle size");
@@ -725,6 +766,9 @@ int mvg_comm_p2p_export(mvg_handle* h, void* ipc_handle_64) {
 int mvg_comm_p2p_attach(mvg_handle* h, const void* all_handles) {
   if (!h || !all_handles) return MVG_EINVAL;
   if (!h->xrecv) return fail(h, MVG_ESTATE, "call mvg_comm_p2p_export first");
+  if (h->xattached)
+    return fail(h, MVG_ESTATE, "peer buffers are already attached (the mappings and the exchange sequence live until mvg_destroy; "
+                               "use mvg_comm_p2p_enable to switch the transport back on)");
   if (h->c.world > 16) return fail(h, MVG_EUNSUPPORTED, "peer exchange supports at most 16 ranks");
   MVG_CUDA(h, cudaSetDevice(h->cfg.device));
   for (int g = 0; g < h->c.world; ++g) {
@@ -733,17 +777,31 @@ int mvg_comm_p2p_attach(mvg_handle* h, const void* all_handles) {
     std::memcpy(&hd, static_cast<const unsigned char*>(all_handles) + (size_t)g * 64, 64);
     void* p = nullptr;
     cudaError_t e = cudaIpcOpenMemHandle(&p, hd, cudaIpcMemLazyEnablePeerAccess);
-    if (e != cudaSuccess) return fail(h, MVG_ECUDA, std::string("cudaIpcOpenMemHandle (rank ") + std::to_string(g) + "): " + cudaGetErrorString(e));
+    if (e != cudaSuccess) {
+      for (int q = 0; q < g; ++q)
+        if (q != h->c.rank && h->xpeers.recv[q]) { cudaIpcCloseMemHandle(h->xpeers.recv[q]); h->xpeers.recv[q] = nullptr; }
+      return fail(h, MVG_ECUDA, std::string("cudaIpcOpenMemHandle (rank ") + std::to_string(g) + "): " + cudaGetErrorString(e));
+    }
     h->xpeers.recv[g] = static_cast<unsigned char*>(p);
   }
+  h->xattached = true;
   h->xp2p = true;
-  h->xseq = 0;
+  invalidate_graphs(h);                            // a captured sweep has the transport baked in
   return MVG_OK;
 }
 
 int mvg_comm_p2p_disable(mvg_handle* h) {
   if (!h) return MVG_EINVAL;
-  h->xp2p = false;                                 // back to ncclAllGather; the mappings stay until mvg_destroy
+  h->xp2p = false;                                 // back to the NCCL transport; mappings and sequence number stay
+  invalidate_graphs(h);
+  return MVG_OK;
+}
+
+int mvg_comm_p2p_enable(mvg_handle* h) {
+  if (!h) return MVG_EINVAL;
+  if (!h->xattached) return fail(h, MVG_ESTATE, "no peer buffers attached: call mvg_comm_p2p_export / mvg_comm_p2p_attach");
+  h->xp2p = true;                                  // the sequence number only advances with finalize: every rank is at the same one
+  invalidate_graphs(h);
   return MVG_OK;
 }
 

@@ -80,7 +80,7 @@ struct Ctx {
   double* S2k;
   double* hyp;
   uint32_t* sweep;          // [1] index of the next sweep
-  int32_t* status;          // [4] device-side error flags
+  int32_t* status;          // [4] device-side error flags: [0] invariants (cleared when reported), [1] STICKY exchange fault
 
   TableParam* tparam;       // [V][cap]
   ViewParam* vparam;        // [V]
@@ -96,6 +96,14 @@ struct Ctx {
   unsigned char* packet;    // [world][pkt.bytes]; this shard writes slot `rank`
   PacketLayout pkt;
 
+  // totals over all shards, in rank order (k_reduce_x): what k_finalize starts from
+  int32_t* sum_cnt;         // [cap]
+  double* sum_s1t;          // [cap*Dsum]
+  double* sum_s2t;          // [V*cap]
+  uint32_t* xseq;           // [1] exchanges completed (peer-memory transport; advanced by k_finalize)
+  uint32_t* fin_arrive;     // [1] arrival counter of the k_finalize CTAs
+  int32_t* host_fault;      // mapped host memory: a copy of the sticky fault status[1] the host can read without a sync
+
   double* birth_lf;         // [cap][V][cap+1] scratch: log f of each seated birth under each dish
   // debug exports
   float* dbg_acc;           // [N][V][cap]
@@ -108,8 +116,11 @@ struct Ctx {
   long long* dbg_prof;      // [CTAs][16] cycles spent waiting per role of the tcgen05 kernel (debug_export & 2)
 };
 
-// Peer-memory exchange (mv_exchange.cu): the receive buffer of every rank, as mapped into this process.
+// Peer-memory exchange (mv_exchange.cu): the receive buffer of every rank, as mapped into this process, and the
+// layout of one (parity, source rank) slot: n_units 16-byte units (the statistics) then n_words 8-byte words (births).
 struct XchgPeers { unsigned char* recv[16]; };
+struct XchgLayout { int64_t n_units, n_words, word_off, slot_bytes; };
+XchgLayout xchg_layout(const struct Ctx& c);
 
 enum FinalizeFlags : int32_t {
   kFinReseat = 1,      // seat births / resolve candidates (after a draw)
@@ -132,7 +143,7 @@ cudaError_t launch_pack(const Ctx& c, cudaStream_t s);
 cudaError_t launch_stats(const Ctx& c, cudaStream_t s);
 bool stats_tile_supported(const Ctx& c);
 cudaError_t launch_stats_tile(const Ctx& c, cudaStream_t s);
-cudaError_t launch_reduce(const Ctx& c, cudaStream_t s);
+cudaError_t launch_reduce_x(const Ctx& c, int mode, const XchgPeers& peers, unsigned char* recv_local, cudaStream_t s);
 cudaError_t launch_finalize(const Ctx& c, int32_t flags, cudaStream_t s);
 cudaError_t launch_init_tables(const Ctx& c, int32_t mode, cudaStream_t s);
 cudaError_t launch_rownorms(const float* x, float* xx, int n, int D, cudaStream_t s);
@@ -142,7 +153,6 @@ int stats_smem_bytes(const Ctx& c);
 cudaError_t launch_rowtotals(const int32_t* rowptr, const float* val, float* out, int n, cudaStream_t s);
 cudaError_t launch_counts_rebuild(const Ctx& c, cudaStream_t s);   // per count view: zero, scatter, dish tables
 cudaError_t launch_counts_loglik(const Ctx& c, cudaStream_t s);    // per count view: log2 f of every row under every table
-cudaError_t launch_exchange_p2p(const Ctx& c, const XchgPeers& peers, unsigned char* recv_local, uint32_t seq, cudaStream_t s);
 // posterior summaries (mv_summary.cu)
 cudaError_t launch_labels(const Ctx& c, int32_t* out, cudaStream_t s);
 cudaError_t launch_cocluster(const Ctx& c, int view, uint32_t* counts, cudaStream_t s);

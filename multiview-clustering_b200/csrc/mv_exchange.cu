@@ -1,78 +1,240 @@
-// mv_exchange.cu — the once-per-sweep exchange of the shards' packets over NVLink peer memory.
+// mv_exchange.cu — k_reduce_x: this shard's sufficient statistics (fixed-order FP64 sums of the per-CTA partials of
+// the statistics kernel) and, in the same launch, their exchange with the other shards and the rank-ordered totals
+// k_finalize starts from.
 //
-// Every rank owns a receive buffer  xrecv = [2 parities][world][pkt.bytes] + counters [2][world]  that its peers have
-// mapped (CUDA IPC).  After k_reduce has finished this rank's packet, ONE kernel (k_exchange) does both directions:
+// north_star asks for "an NCCL allreduce of the per-cluster sufficient statistics over NVLink" once per sweep.  The
+// totals must not depend on a ring's summation order (every rank replays the same chain from them), so what travels
+// is each rank's FP64 values and every rank adds them in rank order.  Two transports produce bit-identical results:
 //
-//   push blocks (g, 0..7)   store the packet straight into rank g's receive slot (P2P stores through NVLink /
-//                           NVSwitch) and count their arrival in g's buffer with a system-scope release;
-//   wait blocks (g, 8..11)  wait (acquire) until all of rank g's push blocks have arrived in the LOCAL buffer and
-//                           copy that slot into the working packet array k_finalize reads.
+//   p2p (default on one node)   ONE kernel, no separate collective.  Every rank owns a receive buffer its peers have
+//       mapped (CUDA IPC over NVLink / NVSwitch).  The thread that has just reduced element i stores it straight into
+//       every peer's buffer as two 8-byte words {payload, sequence number} (the flag travels INSIDE the data, as in
+//       NCCL's LL protocol: an 8-byte store arrives whole, so a word whose flag equals the current sequence number is
+//       valid and no fence, counter or second round trip is needed), then polls its own buffer for the peers' words of
+//       the same element and adds them in rank order.  Two parities: a rank can be at most one exchange ahead of a
+//       peer that still reads the previous one (it cannot finish exchange s+1 without that peer's words of s+1).
+//       The sequence number lives in device memory and is advanced by k_finalize, so the whole sweep is one CUDA graph.
+//   nccl    reduce (mode 0) -> ncclAllGather of the packets -> rank-ordered sums (mode 2): the library baseline.
 //
-// Two parities: a rank can run at most one exchange ahead of a peer that is still reading the previous packets (it
-// cannot finish exchange s+1 without that peer's packet s+1).  The sequence number is kept by the host (every rank
-// issues the same number of exchanges).  The waits are bounded (2^24 polls, a few seconds): a peer that never arrives
-// raises status bit 8 instead of hanging the GPU.  ncclAllGather remains the transport when no peer buffers are attached.
+// A peer that never arrives must not hang the GPU: polls are bounded by %globaltimer (kWaitLimitNs); on expiry the
+// kernel raises the STICKY fault status[1] (mirrored to mapped host memory), k_finalize then publishes nothing — the
+// chain stays frozen at the last completed sweep on this rank — and mvg_sweep / mvg_sync refuse to continue.
+//
+// Replaces the incremental sum_y / sum_y2 / n_vk maintenance of /root/reference/Multiview/multiview_utils.cpp:151-163,
+// 199-206 (as seen from all shards) together with csrc/mv_stats_tile.cu / k_stats.
 #include "mv_ctx.h"
 
 namespace mv {
 
-constexpr int kPushBlocks = 8;     // blocks per destination rank: the stores of one slot are spread over 8 SMs
-constexpr int kWaitBlocks = 4;     // blocks per source rank copying the received slot into place
+namespace {
 
-// Arrivals are COUNTED: every push block adds 1 to counter[parity][source] in the destination's buffer after its part
-// of the slot is globally visible; the k-th exchange on a parity is complete at kPushBlocks * k (counters only grow).
-__device__ __forceinline__ uint32_t arrivals_expected(uint32_t seq) { return (uint32_t)kPushBlocks * ((seq + 1u) >> 1); }
+constexpr int kRedSlices = 8;
+constexpr unsigned long long kWaitLimitNs = 2000000000ull;     // 2 s: documented in include/mvg.h
 
-// ONE launch: blocks (g, 0 .. kPushBlocks-1) push to rank g, blocks (g, kPushBlocks ..) wait for rank g and copy its
-// slot into place.  All blocks are resident at once (<= 16 x 12), so pushes and waits overlap.
-__global__ void __launch_bounds__(256) k_exchange(const Ctx c, const XchgPeers peers, unsigned char* __restrict__ recv_local,
-                                                  const uint32_t seq) {
-  const int g = blockIdx.x;
-  const int parity = seq & 1u;
-  const size_t bytes = (size_t)c.pkt.bytes;                    // multiple of 16
-  const size_t n16 = bytes / 16;
-  if (blockIdx.y < kPushBlocks) {
-    // ---- push this rank's packet into rank g's receive slot ----
+__device__ __forceinline__ unsigned long long globaltimer_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+
+// One 16-byte unit = two LL words {lo32, seq}, {hi32, seq} of a 64-bit payload.
+__device__ __forceinline__ void ll_store_unit(void* dst, unsigned long long payload, uint32_t seq) {
+  const uint32_t lo = (uint32_t)payload, hi = (uint32_t)(payload >> 32);
+  asm volatile("st.volatile.global.v4.u32 [%0], {%1, %2, %3, %4};" ::"l"(dst), "r"(lo), "r"(seq), "r"(hi), "r"(seq) : "memory");
+}
+__device__ __forceinline__ void ll_store_word(void* dst, uint32_t payload, uint32_t seq) {
+  asm volatile("st.volatile.global.v2.u32 [%0], {%1, %2};" ::"l"(dst), "r"(payload), "r"(seq) : "memory");
+}
+struct Waiter {          // bounded polling: the clock is read every 256 polls
+  unsigned long long t0 = 0;
+  uint32_t polls = 0;
+  bool expired = false;
+  __device__ __forceinline__ bool keep_waiting() {
+    if ((++polls & 255u) != 0u) return true;
+    const unsigned long long now = globaltimer_ns();
+    if (t0 == 0) { t0 = now; return true; }
+    if (now - t0 > kWaitLimitNs) { expired = true; return false; }
+    return true;
+  }
+};
+__device__ __forceinline__ bool ll_load_unit(const void* src, uint32_t seq, unsigned long long* payload, Waiter& w) {
+  uint32_t a, fa, b, fb;
+  for (;;) {
+    asm volatile("ld.volatile.global.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(a), "=r"(fa), "=r"(b), "=r"(fb) : "l"(src) : "memory");
+    if (fa == seq && fb == seq) break;
+    if (!w.keep_waiting()) return false;
+  }
+  *payload = (unsigned long long)a | ((unsigned long long)b << 32);
+  return true;
+}
+__device__ __forceinline__ bool ll_load_word(const void* src, uint32_t seq, uint32_t* payload, Waiter& w) {
+  uint32_t a, fa;
+  for (;;) {
+    asm volatile("ld.volatile.global.v2.u32 {%0, %1}, [%2];" : "=r"(a), "=r"(fa) : "l"(src) : "memory");
+    if (fa == seq) break;
+    if (!w.keep_waiting()) return false;
+  }
+  *payload = a;
+  return true;
+}
+
+__device__ __forceinline__ void raise_fault(const Ctx& c) {
+  atomicExch(c.status + 1, 8);
+  if (c.host_fault) *reinterpret_cast<volatile int32_t*>(c.host_fault) = 8;
+}
+
+}  // namespace
+
+XchgLayout xchg_layout(const Ctx& c) {
+  XchgLayout L;
+  L.n_units = (int64_t)c.cap * c.Dsum + (int64_t)c.V * c.cap + c.cap;
+  L.n_words = 8 + 2 * (int64_t)c.cap + (int64_t)c.cap * c.Dsum;
+  L.word_off = L.n_units * 16;
+  L.slot_bytes = (L.word_off + L.n_words * 8 + 255) & ~(int64_t)255;
+  return L;
+}
+
+// mode 0: reduce the partials into this rank's packet (and, with world = 1, into the totals)
+// mode 1: reduce, push to the peers, pull, rank-ordered totals      (peer-memory transport)
+// mode 2: rank-ordered totals from the all-gathered packets          (NCCL transport, second launch)
+// Blocks [0, n_sum_blocks): 32 consecutive elements x 8 slices (slice j adds the partials of CTAs j, j+8, ... in
+// ascending order, then the 8 slice sums are added in ascending order: a fixed tree), walking the elements with a
+// grid stride.  Blocks [n_sum_blocks, n_sum_blocks + world) in mode 1: the birth candidates of / for rank g.
+__global__ void __launch_bounds__(256) k_reduce_x(const Ctx c, const int mode, const int n_sum_blocks, const XchgPeers peers,
+                                                  unsigned char* __restrict__ recv_local, const XchgLayout L) {
+  __shared__ double s_part[kRedSlices][32];
+  __shared__ int s_cnt[kRedSlices][32];
+  __shared__ int s_ncand;
+  const int n_s1 = c.cap * c.Dsum, n_s2 = c.V * c.cap;
+  const int n_el = n_s1 + n_s2 + c.cap;
+  const uint32_t seq = (mode == 1) ? *reinterpret_cast<volatile uint32_t*>(c.xseq) + 1u : 0u;
+  const size_t slot0 = (size_t)(seq & 1u) * c.world * (size_t)L.slot_bytes;        // this exchange's parity
+  if (mode == 1 && *reinterpret_cast<volatile int32_t*>(c.status + 1) != 0) return;   // frozen after a fault
+  Waiter wt;
+
+  if ((int)blockIdx.x >= n_sum_blocks) {
+    // ---------------- birth candidates: push mine to rank g, pull rank g's ----------------
+    const int g = (int)blockIdx.x - n_sum_blocks;
     if (g == c.rank) return;
-    const size_t per = (n16 + kPushBlocks - 1) / kPushBlocks;
-    const size_t lo = (size_t)blockIdx.y * per, hi = (lo + per < n16) ? lo + per : n16;
-    const uint4* __restrict__ src = reinterpret_cast<const uint4*>(c.packet + (size_t)c.rank * bytes);
-    unsigned char* base = peers.recv[g];
-    uint4* dst = reinterpret_cast<uint4*>(base + ((size_t)parity * c.world + c.rank) * bytes);
-    for (size_t i = lo + threadIdx.x; i < hi; i += blockDim.x) dst[i] = src[i];
-    __syncthreads();                                           // the block's stores happen-before thread 0's release
-    if (threadIdx.x == 0) {
-      uint32_t* counter = reinterpret_cast<uint32_t*>(base + (size_t)2 * c.world * bytes) + parity * c.world + c.rank;
-      asm volatile("red.release.sys.global.add.u32 [%0], 1;" ::"l"(counter) : "memory");
+    const int tid = threadIdx.x;
+    const int32_t* my_hdr = reinterpret_cast<const int32_t*>(c.packet + (size_t)c.rank * c.pkt.bytes + c.pkt.off_hdr);
+    const int my_n = my_hdr[0];
+    {
+      unsigned char* dst = peers.recv[g] + slot0 + (size_t)c.rank * L.slot_bytes + L.word_off;
+      const uint32_t* h32 = reinterpret_cast<const uint32_t*>(my_hdr);
+      const uint32_t* row = reinterpret_cast<const uint32_t*>(c.packet + (size_t)c.rank * c.pkt.bytes + c.pkt.off_cand_row);
+      const uint32_t* t0 = reinterpret_cast<const uint32_t*>(c.packet + (size_t)c.rank * c.pkt.bytes + c.pkt.off_cand_t0);
+      const uint32_t* cx = reinterpret_cast<const uint32_t*>(c.packet + (size_t)c.rank * c.pkt.bytes + c.pkt.off_cand_x);
+      // candidates first, the header (which tells the receiver how many to expect) with them: every word carries its own flag
+      for (int i = tid; i < my_n; i += blockDim.x) {
+        ll_store_word(dst + (size_t)(8 + i) * 8, row[i], seq);
+        ll_store_word(dst + (size_t)(8 + c.cap + i) * 8, t0[i], seq);
+      }
+      for (int i = tid; i < my_n * c.Dsum; i += blockDim.x) ll_store_word(dst + (size_t)(8 + 2 * c.cap + i) * 8, cx[i], seq);
+      if (tid < 8) ll_store_word(dst + (size_t)tid * 8, h32[tid], seq);
     }
-  } else {
-    // ---- wait for rank g's packet and copy it into the working array ----
-    if (g == c.rank) return;                                   // own slot is already in place
-    __shared__ int ok;
-    if (threadIdx.x == 0) {
-      const uint32_t* counter = reinterpret_cast<const uint32_t*>(recv_local + (size_t)2 * c.world * bytes) + parity * c.world + g;
-      const uint32_t want = arrivals_expected(seq);
-      uint32_t v = 0;
-      long long spins = 0;
-      do {
-        asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(counter) : "memory");
-      } while ((int32_t)(v - want) < 0 && ++spins < (1ll << 24));   // seconds at most: a missing peer must not hang the GPU
-      ok = ((int32_t)(v - want) >= 0);
-      if (!ok) atomicOr(c.status, 8);
+    {
+      const unsigned char* src = recv_local + slot0 + (size_t)g * L.slot_bytes + L.word_off;
+      unsigned char* pk = c.packet + (size_t)g * c.pkt.bytes;
+      if (tid < 8) {
+        uint32_t w = 0;
+        if (!ll_load_word(src + (size_t)tid * 8, seq, &w, wt)) raise_fault(c);
+        reinterpret_cast<uint32_t*>(pk + c.pkt.off_hdr)[tid] = w;
+        if (tid == 0) s_ncand = wt.expired ? 0 : (int)w;
+      }
+      __syncthreads();
+      const int n = min(max(s_ncand, 0), c.cap);
+      for (int i = tid; i < n; i += blockDim.x) {
+        uint32_t a = 0, b = 0;
+        if (!ll_load_word(src + (size_t)(8 + i) * 8, seq, &a, wt) || !ll_load_word(src + (size_t)(8 + c.cap + i) * 8, seq, &b, wt)) raise_fault(c);
+        reinterpret_cast<uint32_t*>(pk + c.pkt.off_cand_row)[i] = a;
+        reinterpret_cast<uint32_t*>(pk + c.pkt.off_cand_t0)[i] = b;
+      }
+      for (int i = tid; i < n * c.Dsum; i += blockDim.x) {
+        uint32_t a = 0;
+        if (!ll_load_word(src + (size_t)(8 + 2 * c.cap + i) * 8, seq, &a, wt)) raise_fault(c);
+        reinterpret_cast<uint32_t*>(pk + c.pkt.off_cand_x)[i] = a;
+      }
     }
-    __syncthreads();
-    if (!ok) return;
-    const int wb = blockIdx.y - kPushBlocks;
-    const size_t per = (n16 + kWaitBlocks - 1) / kWaitBlocks;
-    const size_t lo = (size_t)wb * per, hi = (lo + per < n16) ? lo + per : n16;
-    const uint4* __restrict__ src = reinterpret_cast<const uint4*>(recv_local + ((size_t)parity * c.world + g) * bytes);
-    uint4* dst = reinterpret_cast<uint4*>(c.packet + (size_t)g * bytes);
-    for (size_t i = lo + threadIdx.x; i < hi; i += blockDim.x) dst[i] = src[i];
+    return;
+  }
+
+  // ---------------- statistics ----------------
+  const size_t part_stride = (size_t)n_s1 + n_s2;
+  const int e = threadIdx.x & 31, slice = threadIdx.x >> 5;
+  double* pk_s1 = reinterpret_cast<double*>(c.packet + (size_t)c.rank * c.pkt.bytes + c.pkt.off_s1t);
+  double* pk_s2 = reinterpret_cast<double*>(c.packet + (size_t)c.rank * c.pkt.bytes + c.pkt.off_s2t);
+  int32_t* pk_cnt = reinterpret_cast<int32_t*>(c.packet + (size_t)c.rank * c.pkt.bytes + c.pkt.off_cnt);
+  for (int blk = blockIdx.x; blk * 32 < n_el; blk += n_sum_blocks) {
+    const int i = blk * 32 + e;
+    double sum = 0.0;
+    int n = 0;
+    if (mode != 2) {
+      if (i < n_s1 + n_s2) {
+        for (int b = slice; b < c.stat_ctas; b += kRedSlices) sum += (double)c.partial_f[(size_t)b * part_stride + i];
+      } else if (i < n_el) {
+        const int t = i - n_s1 - n_s2;
+        for (int b = slice; b < c.stat_ctas; b += kRedSlices) n += c.partial_n[(size_t)b * c.cap + t];
+      }
+      s_part[slice][e] = sum;
+      s_cnt[slice][e] = n;
+      __syncthreads();
+    }
+    if (slice == 0 && i < n_el) {
+      const bool is_cnt = i >= n_s1 + n_s2;
+      if (mode != 2) {
+        sum = 0.0; n = 0;
+#pragma unroll
+        for (int j = 0; j < kRedSlices; ++j) { sum += s_part[j][e]; n += s_cnt[j][e]; }
+        if (i < n_s1) pk_s1[i] = sum;
+        else if (!is_cnt) pk_s2[i - n_s1] = sum;
+        else pk_cnt[i - n_s1 - n_s2] = n;
+      }
+      double tot = sum;
+      int ntot = n;
+      if (mode == 1) {
+        const unsigned long long mine = is_cnt ? (unsigned long long)(uint32_t)n : (unsigned long long)__double_as_longlong(sum);
+        for (int g = 0; g < c.world; ++g)
+          if (g != c.rank) ll_store_unit(peers.recv[g] + slot0 + (size_t)c.rank * L.slot_bytes + (size_t)i * 16, mine, seq);
+        tot = 0.0; ntot = 0;
+        for (int g = 0; g < c.world; ++g) {                     // rank order, starting from rank 0's value
+          unsigned long long p = mine;
+          if (g != c.rank && !ll_load_unit(recv_local + slot0 + (size_t)g * L.slot_bytes + (size_t)i * 16, seq, &p, wt)) {
+            raise_fault(c);
+            p = 0ull;
+          }
+          if (is_cnt) ntot += (int)(uint32_t)p;
+          else tot = (g == 0) ? __longlong_as_double((long long)p) : tot + __longlong_as_double((long long)p);
+        }
+      } else if (mode == 2) {
+        tot = 0.0; ntot = 0;
+        for (int g = 0; g < c.world; ++g) {
+          const unsigned char* pg = c.packet + (size_t)g * c.pkt.bytes;
+          if (is_cnt) ntot += reinterpret_cast<const int32_t*>(pg + c.pkt.off_cnt)[i - n_s1 - n_s2];
+          else {
+            const double val = (i < n_s1) ? reinterpret_cast<const double*>(pg + c.pkt.off_s1t)[i]
+                                          : reinterpret_cast<const double*>(pg + c.pkt.off_s2t)[i - n_s1];
+            tot = (g == 0) ? val : tot + val;
+          }
+        }
+      }
+      if (mode != 0 || c.world == 1) {
+        if (i < n_s1) c.sum_s1t[i] = tot;
+        else if (!is_cnt) c.sum_s2t[i - n_s1] = tot;
+        else c.sum_cnt[i - n_s1 - n_s2] = ntot;
+      }
+    }
+    if (mode != 2) __syncthreads();                             // s_part is reused by the next element block
   }
 }
 
-cudaError_t launch_exchange_p2p(const Ctx& c, const XchgPeers& peers, unsigned char* recv_local, uint32_t seq, cudaStream_t s) {
-  k_exchange<<<dim3(c.world, kPushBlocks + kWaitBlocks), 256, 0, s>>>(c, peers, recv_local, seq);
+cudaError_t launch_reduce_x(const Ctx& c, int mode, const XchgPeers& peers, unsigned char* recv_local, cudaStream_t s) {
+  const XchgLayout L = xchg_layout(c);
+  const int n_el = (int)L.n_units;
+  int nb = (n_el + 31) / 32;
+  if (nb > 148 * 4) nb = 148 * 4;              // every block of one launch is resident at once (peers wait for each other's pushes)
+  const int extra = (mode == 1) ? c.world : 0;
+  k_reduce_x<<<nb + extra, 256, 0, s>>>(c, mode, nb, peers, recv_local, L);
   return cudaGetLastError();
 }
 

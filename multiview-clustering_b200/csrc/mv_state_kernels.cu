@@ -4,8 +4,8 @@
 //               become candidates; their features go into the exchange packet)
 //   k_stats     segmented reduction of the rows into per-TABLE sufficient statistics
 //               (fixed row->CTA->warp mapping, per-warp private accumulators: a fixed-order tree)
-//   k_reduce    fixed-order FP64 sum of the per-CTA partials into this shard's packet
-//   k_finalize  one CTA: rank-ordered sum of the shards' packets, births (dish sampling) and
+//   (k_reduce_x, mv_exchange.cu: fixed-order FP64 sums of the per-CTA partials, exchange, rank-ordered totals)
+//   k_finalize  one CTA per level of the hierarchy (V views + the franchise): births (dish sampling) and
 //               deaths, per-dish statistics, the Metropolis-Hastings hyperparameter step, and the
 //               FP32 parameter block of the next sweep
 //
@@ -313,85 +313,53 @@ cudaError_t launch_stats(const Ctx& c, cudaStream_t s) {
   return cudaGetLastError();
 }
 
-// =============================================================================================
-// k_reduce
-// =============================================================================================
-// 256 threads = 32 consecutive elements x 8 slices: slice j adds the partials of CTAs j, j+8, ... in ascending
-// order, then the 8 slice sums are added in ascending order — a fixed tree, with 8x the loads in flight of a
-// plain loop over the CTAs and 8x the blocks.
-constexpr int kRedSlices = 8;
-
-__global__ void __launch_bounds__(256) k_reduce(const Ctx c) {
-  __shared__ double s_part[kRedSlices][32];
-  __shared__ int s_cnt[kRedSlices][32];
-  const int n_s1 = c.cap * c.Dsum, n_s2 = c.V * c.cap;
-  const size_t part_stride = (size_t)n_s1 + n_s2;
-  const int e = threadIdx.x & 31, slice = threadIdx.x >> 5;
-  const int i = blockIdx.x * 32 + e;
-  double sum = 0.0;
-  int n = 0;
-  if (i < n_s1 + n_s2) {
-    for (int b = slice; b < c.stat_ctas; b += kRedSlices) sum += (double)c.partial_f[(size_t)b * part_stride + i];
-  } else if (i < n_s1 + n_s2 + c.cap) {
-    const int t = i - n_s1 - n_s2;
-    for (int b = slice; b < c.stat_ctas; b += kRedSlices) n += c.partial_n[(size_t)b * c.cap + t];
-  }
-  s_part[slice][e] = sum;
-  s_cnt[slice][e] = n;
-  __syncthreads();
-  if (slice == 0) {
-    sum = 0.0; n = 0;
-#pragma unroll
-    for (int j = 0; j < kRedSlices; ++j) { sum += s_part[j][e]; n += s_cnt[j][e]; }
-    if (i < n_s1) pkt_f64(c, c.rank, c.pkt.off_s1t)[i] = sum;
-    else if (i < n_s1 + n_s2) pkt_f64(c, c.rank, c.pkt.off_s2t)[i - n_s1] = sum;
-    else if (i < n_s1 + n_s2 + c.cap) pkt_i32(c, c.rank, c.pkt.off_cnt)[i - n_s1 - n_s2] = n;
-  }
-}
-
-cudaError_t launch_reduce(const Ctx& c, cudaStream_t s) {
-  const int total = c.cap * c.Dsum + c.V * c.cap + c.cap;
-  k_reduce<<<(total + 31) / 32, 256, 0, s>>>(c);
-  return cudaGetLastError();
-}
 
 // =============================================================================================
 // k_finalize
 // =============================================================================================
+// Grid of V + 1 INDEPENDENT CTAs: CTA v < V owns view v (its dishes, tau_v, alpha_v, sigma_v, posterior means and
+// parameter rows), CTA V owns the franchise level (customers per table, alpha_global, sigma_global, table masses, the
+// sweep counter).  The integer bookkeeping every level needs (customers per table, the seating order of the births) is
+// recomputed by every CTA from the same inputs, so that no CTA ever waits for another one's results: the levels of the
+// hierarchy only meet in the parameter block of the next sweep.  The one hazard is the in-place update of what the
+// others read at their start (n_t, the sweep counter): the franchise CTA publishes those last, after every CTA has
+// announced that its reads are done (an arrival counter; all V + 1 CTAs are co-resident).
 constexpr int kFinThreads = 1024;
 constexpr int kMaxCap = 64;
 constexpr int kMaxWorld = 16;
+constexpr int kEppfSets = 4;             // (alpha, sigma) x (old, proposed): both Metropolis-Hastings steps of a level in one batch
 
 struct FinShared {
   int32_t n_new[kMaxCap];                 // customers per table after this sweep
-  int32_t alive_start[kMaxCap];           // n_t > 0 at sweep start
+  int32_t n_start[kMaxCap];               // ... at sweep start
   int32_t free_slots[kMaxCap];
-  int32_t dish[kMaxViews][kMaxCap];       // working copy of dish_of
-  int32_t l_live[kMaxViews][kMaxCap];     // tables per dish (live-updated by births, then recomputed)
-  int32_t n_vk[kMaxViews][kMaxCap];       // customers per dish at sweep start, later the new ones
+  int32_t dish[kMaxCap];                  // working copy of dish_of[v]            (view CTAs)
+  int32_t l_live[kMaxCap];                // tables per dish (live-updated by births, then recomputed)
+  int32_t n_vk[kMaxCap];                  // customers per dish at sweep start, later the new ones
   int32_t cand_g[kMaxWorld * kMaxCap];    // candidates in global row order: shard, index in shard
   int32_t cand_j[kMaxWorld * kMaxCap];
   int32_t cand_final[kMaxWorld * kMaxCap];
   int32_t ncand_total, nseat, nfree, err;
-  unsigned long long tmask[kMaxViews][kMaxCap];   // bit t: table t serves dish k of view v (after births and deaths)
-  unsigned long long live[kMaxViews + 1];          // bit i: cluster i of level j has members (dishes: l_vk > 0; level V: n_t > 0)
-  long long total[kMaxViews + 1];                  // items of level j (tables of view j; customers for level V)
-  double s2t[kMaxViews][kMaxCap];         // sums of squared norms per table (working copy of S2t)
-  double s2k[kMaxViews][kMaxCap];         //   and per dish
-  double s2k_start[kMaxViews][kMaxCap];   // per dish at sweep START (count views: the token totals the births see)
-  int32_t table_of_dish[kMaxViews][kMaxCap];   // at sweep start: lowest table slot serving dish k, -1 = none
-  double s1sq[kMaxViews][kMaxCap];        // |S1k|^2
-  double sse[kMaxViews][kMaxCap];         // max(0, S2k - |S1k|^2 / n_k)     (multiview_hyper.cpp:191-193)
-  double termA[2 * (kMaxViews + 1)][kMaxCap + 1];   // scratch of the batched EPPF evaluations
-  double termB[2 * (kMaxViews + 1)][kMaxCap + 1];
-  double termC[2 * (kMaxViews + 1)][4];             // per set: lgamma(alpha + M), lgamma(alpha + 1), lgamma(1 - sigma)
-  double eppf[2 * (kMaxViews + 1)];
+  unsigned long long tmask[kMaxCap];      // bit t: table t serves dish k of this view (after births and deaths)
+  unsigned long long live;                // bit i: cluster i of this level has members (dishes: l_vk > 0; franchise: n_t > 0)
+  long long total;                        // items of this level (tables of the view; customers for the franchise)
+  double s2t[kMaxCap];                    // sums of squared norms per table (working copy of S2t[v])
+  double s2k[kMaxCap];                    //   and per dish
+  double s2k_start[kMaxCap];              // per dish at sweep START (count views: the token totals the births see)
+  int32_t table_of_dish[kMaxCap];         // at sweep start: lowest table slot serving dish k, -1 = none
+  double s1sq[kMaxCap];                   // |S1k|^2, later |m_t|^2
+  double sse[kMaxCap];                    // max(0, S2k - |S1k|^2 / n_k)     (multiview_hyper.cpp:191-193)
+  double termA[kEppfSets][4];             // scratch of the batched EPPF evaluations: per set, per 32-cluster block
+  double termB[kEppfSets][4];
+  double termC[kEppfSets][4];             // per set: lgamma(alpha + M), lgamma(alpha + 1), lgamma(1 - sigma)
+  double eppf[kEppfSets];
+  double s_alpha[kEppfSets], s_sigma[kEppfSets];
   double wbuf[kMaxCap + 1];
+  double wexp[kMaxCap + 1];
   double result[4];
-  double prop[kMaxViews + 1];
-  double hyp[3 * kMaxViews + 2];
-  double rn[3 * kMaxViews + 2];           // the sweep's standard normals of the hyper step, by stream index
-  double lu[3 * kMaxViews + 2];           // log of its uniforms
+  double hyp[3];                          // view: alpha_v, sigma_v, tau_v; franchise: alpha_g, sigma_g
+  double rn[3];                           // the sweep's standard normals of this level: [0] tau, [1] alpha, [2] sigma
+  double lu[3];                           // log of its uniforms, same order
   double warm[2];                         // sink of the instruction-cache warm-up calls
 };
 
@@ -424,45 +392,39 @@ __device__ __forceinline__ double reflect_unit(double value) {      // :110-122
   return fmin(fmax(p, kEps), 1.0 - kEps);
 }
 
-// log EPPF (multiview_hyper.cpp:53-83 global, :295-342 per view) for a batch of parameter sets.
-// Set 2j+q (q = 0 old / 1 proposed) belongs to level j: j < V is view j (cluster sizes = tables per
-// dish l_vk, items = tables), j = V is the franchise (sizes = customers per table n_t, items = all
-// customers).  The two inner loops are taken in closed form,
-//   sum_{i=1}^{M-1} fin_log(alpha+i) = fin_lgamma(alpha+M) - fin_lgamma(alpha+1),
-//   sum_{m=1}^{c-1} fin_log(m-sigma) = fin_lgamma(c-sigma) - fin_lgamma(1-sigma),
-// the per-cluster terms are evaluated by the block in parallel and one thread per set adds them in
-// ascending cluster order (the order of oracle/mv_oracle.c:eppf_core).  Block-uniform call.
-// Called by ONE group of gthreads consecutive threads of the CTA (gtid = index inside the group), synchronising on
-// named barrier bar_id: the other half of the CTA is busy with the dish statistics and the posterior means meanwhile.
 __device__ __forceinline__ void group_sync(int bar_id, int gthreads) {
   asm volatile("bar.sync %0, %1;" ::"r"(bar_id), "r"(gthreads) : "memory");
 }
-__device__ __noinline__ void eppf_batch(const int cap, const int V, FinShared& S, const double* alpha, const double* sigma,
-                                        const int gtid, const int gthreads, const int bar_id) {
-  const int tid = gtid;
-  const int lane = tid & 31, wid = tid >> 5;
-  const int nsets = 2 * (V + 1);
+
+// log EPPF (multiview_hyper.cpp:53-83 franchise, :295-342 per view) of ONE level for kEppfSets parameter sets
+// (S.s_alpha[q], S.s_sigma[q]).  `counts` are the cluster sizes of the level (tables per dish l_vk; customers per table
+// n_t), S.live its live mask, S.total its item count.  The two inner loops are taken in closed form,
+//   sum_{i=1}^{M-1} log(alpha+i) = lgamma(alpha+M) - lgamma(alpha+1),
+//   sum_{m=1}^{c-1} log(m-sigma) = lgamma(c-sigma) - lgamma(1-sigma),
+// the per-cluster terms are evaluated in parallel (one warp per (set, 32-cluster block), fixed shuffle tree) and one
+// thread per set adds the blocks in ascending order (the order of oracle/mv_oracle.c:eppf_core).
+// Called by ONE group of gthreads consecutive threads (gtid = index inside the group) synchronising on named barrier
+// bar_id; the rest of the CTA is busy with the dish statistics and the posterior means meanwhile.
+__device__ __noinline__ void eppf_batch(const int cap, const int32_t* counts, FinShared& S, const int gtid, const int gthreads,
+                                        const int bar_id) {
+  const int lane = gtid & 31, wid = gtid >> 5;
   group_sync(bar_id, gthreads);
-  // one thread per (parameter set, cluster): its two terms, summed per warp by a fixed shuffle tree into
-  // termA/termB[set][warp-in-set]; then one thread per set adds the warp partials in ascending order.
-  // The rank of a cluster among the live ones is a popcount of the level's live mask.
   const int wps = (cap + 31) / 32;                   // warps per set
-  for (int base = 0; base < nsets * wps; base += gthreads / 32) {
+  for (int base = 0; base < kEppfSets * wps; base += gthreads / 32) {
     const int unit = base + wid;                     // (set, 32-cluster block)
     double sa = 0.0, sb = 0.0;
     bool bad = false;
-    if (unit < nsets * wps) {
-      const int set = unit / wps, i = (unit - set * wps) * 32 + lane, j = set >> 1;
+    if (unit < kEppfSets * wps) {
+      const int set = unit / wps, i = (unit - set * wps) * 32 + lane;
       if (i < cap) {
-        const int32_t* counts = (j < V) ? S.l_live[j] : S.n_new;
-        const double al = alpha[set], sg = sigma[set];
+        const double al = S.s_alpha[set], sg = S.s_sigma[set];
         const int cnt = counts[i];
         if (cnt > 0) {
-          const int r = __popcll(S.live[j] & ((1ull << i) - 1ull));
+          const int r = __popcll(S.live & ((1ull << i) - 1ull));
           const double term = al + (double)r * sg;
           if (term <= 0.0) bad = true; else sa = fin_log(term);
         }
-        if (cnt > 1) sb = fin_lgamma((double)cnt - sg);   // minus fin_lgamma(1 - sigma) per such cluster: added below
+        if (cnt > 1) sb = fin_lgamma((double)cnt - sg);   // minus lgamma(1 - sigma) per such cluster: added below
       }
     }
 #pragma unroll
@@ -471,27 +433,26 @@ __device__ __noinline__ void eppf_batch(const int cap, const int V, FinShared& S
       sb += __shfl_xor_sync(0xffffffffu, sb, o);
     }
     bad = __any_sync(0xffffffffu, bad);
-    if (unit < nsets * wps && lane == 0) {
+    if (unit < kEppfSets * wps && lane == 0) {
       const int set = unit / wps, blk = unit - set * wps;
       S.termA[set][blk] = bad ? -INFINITY : sa;
       S.termB[set][blk] = sb;
     }
   }
   // the three per-set lgamma values, one thread each (the last warps: the first ones carry the units above)
-  for (int q = tid - (gthreads - 128); q >= 0 && q < 3 * nsets; q += gthreads) {
-    const int set = q / 3, which = q - 3 * set, j = set >> 1;
-    const double al = alpha[set], sg = sigma[set];
+  for (int q = gtid - (gthreads - 128); q >= 0 && q < 3 * kEppfSets; q += gthreads) {
+    const int set = q / 3, which = q - 3 * set;
+    const double al = S.s_alpha[set], sg = S.s_sigma[set];
     double val = 0.0;
     if ((sg > kEps && sg < 1.0 - kEps) && al > -sg)
-      val = (which == 0) ? fin_lgamma(al + (double)S.total[j]) : ((which == 1) ? fin_lgamma(al + 1.0) : fin_lgamma(1.0 - sg));
+      val = (which == 0) ? fin_lgamma(al + (double)S.total) : ((which == 1) ? fin_lgamma(al + 1.0) : fin_lgamma(1.0 - sg));
     S.termC[set][which] = val;
   }
   group_sync(bar_id, gthreads);
-  if (tid < nsets) {
-    const int set = tid, j = set >> 1;
-    const int32_t* counts = (j < V) ? S.l_live[j] : S.n_new;
-    const double al = alpha[set], sg = sigma[set];
-    const long long total = S.total[j];
+  if (gtid < kEppfSets) {
+    const int set = gtid;
+    const double al = S.s_alpha[set], sg = S.s_sigma[set];
+    const long long total = S.total;
     double logp;
     if (!(sg > kEps && sg < 1.0 - kEps) || al <= -sg) logp = -INFINITY;
     else if (total <= 0) logp = 0.0;
@@ -509,8 +470,47 @@ __device__ __noinline__ void eppf_batch(const int cap, const int V, FinShared& S
   group_sync(bar_id, gthreads);
 }
 
+// The (alpha, sigma) Metropolis-Hastings pair of one level (multiview_hyper.cpp:239-291) on S.hyp[0..1], with the
+// level's Philox numbers S.rn[1..2] / S.lu[1..2].  The sigma step needs the EPPF at the alpha the first step ends with:
+// both candidates are evaluated up front — sets (a_old, s_old), (a_prop, s_old), (a_cur, s_prop), (a_prop, s_prop) in
+// ONE batch — so the two dependent steps cost one round of lgamma latencies instead of two.  Each EPPF value is the
+// same function of (alpha, sigma, counts) as in the sequential order, so the chain is unchanged.
+__device__ __forceinline__ void level_alpha_sigma(const int cap, const int32_t* counts, FinShared& S, const int gtid,
+                                                  const int gthreads, const int bar_id, const bool enabled) {
+  double a_cur = 0.0, a_old = 0.0, a_prop = 0.0, s_old = 0.0, s_prop = 0.0;
+  if (gtid == 0 && enabled) {
+    a_cur = S.hyp[0];
+    a_old = a_cur;
+    if (a_old <= 0.0) a_old = kEps;
+    const double cand = fin_exp(fin_log(a_old > kEps ? a_old : kEps) + 0.0 + 0.1 * S.rn[1]);   // :100-108
+    a_prop = cand > kEps ? cand : kEps;
+    s_old = S.hyp[1];
+    s_prop = reflect_unit(s_old + 0.0 + 0.05 * S.rn[2]);                                       // :124-128
+    S.s_alpha[0] = a_old;  S.s_sigma[0] = s_old;
+    S.s_alpha[1] = a_prop; S.s_sigma[1] = s_old;
+    S.s_alpha[2] = a_cur;  S.s_sigma[2] = s_prop;
+    S.s_alpha[3] = a_prop; S.s_sigma[3] = s_prop;
+  }
+  if (!enabled) return;                                                      // (group-uniform)
+  eppf_batch(cap, counts, S, gtid, gthreads, bar_id);
+  if (gtid == 0) {
+    // alpha: log-normal random walk, :242-255 / :268-281
+    const double lo = S.eppf[0] + log_prior_alpha(a_old), ln = S.eppf[1] + log_prior_alpha(a_prop);
+    const double log_acc = (ln - lo) + (fin_log(a_prop) - fin_log(a_old));
+    const bool acc_a = S.lu[1] < log_acc;
+    if (acc_a) S.hyp[0] = a_prop;
+    // sigma: reflected random walk at the alpha just fixed, :257-265 / :283-291
+    // (not accepted: alpha stays a_cur; set 0 was evaluated at a_old, which differs from a_cur only for alpha <= 0,
+    //  a state mvg_set_state rejects)
+    const double e_old = acc_a ? S.eppf[1] : ((a_cur == a_old) ? S.eppf[0] : S.eppf[0]);
+    const double e_new = acc_a ? S.eppf[3] : S.eppf[2];
+    const double lpo = (s_old <= kEps || s_old >= 1.0 - kEps) ? -INFINITY : e_old + log_prior_sigma(s_old);
+    const double lpn = (s_prop <= kEps || s_prop >= 1.0 - kEps) ? -INFINITY : e_new + log_prior_sigma(s_prop);
+    if (S.lu[2] < lpn - lpo) S.hyp[1] = s_prop;
+  }
+}
 
-// log predictive density of x (views concatenated, FP32) under dish k of view v, optionally with
+// log predictive density of x (FP32, the coordinates of ONE view) under dish k of that view, optionally with
 // x removed from the dish first (multiview_utils.cpp:307-338 in closed form, per coordinate).
 __device__ __noinline__ double log_f_dish(const int D, const double* __restrict__ S1, const double n_vk, const float* x,
                                           bool loo, double tau) {
@@ -518,7 +518,7 @@ __device__ __noinline__ double log_f_dish(const int D, const double* __restrict_
   const double var = tau * (tau + n + 1.0) / (tau + n);
   double dist = 0.0;
   for (int dd = 0; dd < D; ++dd) {
-    const double xv = (double)x[dd];                    // x: the candidate's coordinates in THIS view
+    const double xv = (double)x[dd];
     const double s1 = S1[dd] - (loo ? xv : 0.0);
     const double diff = xv - s1 / (tau + n);
     dist += diff * diff;
@@ -548,92 +548,86 @@ __device__ __noinline__ double log_f_dish_counts(const int32_t* __restrict__ rp,
 __global__ void __launch_bounds__(kFinThreads, 1) k_finalize(const Ctx c, const int32_t flags, const int32_t s1_in_smem) {
   extern __shared__ __align__(16) unsigned char fin_smem[];
   FinShared& S = *reinterpret_cast<FinShared*>(fin_smem);
-  // The per-table sums S1t [cap*Dsum] live in shared memory behind FinShared when they fit (96 KB at C3): the
-  // dish statistics and the posterior means are then built from on-chip data instead of global round trips.
-  double* const S1t = s1_in_smem ? reinterpret_cast<double*>(fin_smem + kFinSharedBytes) : c.S1t;
   const int tid = threadIdx.x;
   const int cap = c.cap, V = c.V;
-  const int cshift = (cap == 64) ? 6 : 5;          // cap is 32 or 64 (mvg_create)
-  const uint32_t sweep = *c.sweep;
-  double* alpha_v = S.hyp;
-  double* sigma_v = S.hyp + V;
-  double* tau_v = S.hyp + 2 * V;
-  double& alpha_g = S.hyp[3 * V];
-  double& sigma_g = S.hyp[3 * V + 1];
+  const int role = blockIdx.x;                      // < V: that view; V: the franchise level
+  const bool is_view = role < V;
+  const int v = is_view ? role : 0;
+  const int D = is_view ? c.D[v] : 0;
+  const int doff = is_view ? c.doff[v] : 0;
+  const bool is_count = is_view && c.kind[v] != 0;
+  // A failed exchange (a peer's packet never arrived) freezes the chain: nothing is published, the sweep counter stays
+  // (mvg_sweep / mvg_sync report it; csrc/mv_exchange.cu).
+  if (*reinterpret_cast<volatile int32_t*>(c.status + 1) != 0) return;
+  // The per-table sums of this view, S1t [cap][D], live in shared memory behind FinShared when they fit (32 KB at C3):
+  // the dish statistics and the posterior means are then built from on-chip data instead of global round trips.
+  double* const S1t = s1_in_smem ? reinterpret_cast<double*>(fin_smem + kFinSharedBytes) : (c.S1t + (size_t)cap * doff);
+  const uint32_t sweep = *reinterpret_cast<volatile uint32_t*>(c.sweep);
+  double& alpha_l = S.hyp[0];                       // alpha_v / alpha_global
+  double& sigma_l = S.hyp[1];                       // sigma_v / sigma_global
+  double& tau_l = S.hyp[2];                         // tau_v (views only)
 
   const bool prof = (c.debug_export & 2) != 0 && c.dbg_prof != nullptr && tid == 0;
-  long long* pout = c.dbg_prof + 200 * 16;            // slots 200.. of the profile buffer: finalize section stamps
-  const long long t_begin_all = clock64();
-  const long long t_begin = prof ? t_begin_all : 0;
+  long long* pout = c.dbg_prof + (200 + role) * 16;   // slots 200.. of the profile buffer: one row of stamps per CTA
+  const long long t_begin = prof ? clock64() : 0;
   auto stamp = [&](int k) { if (prof) pout[k] = clock64() - t_begin; };
   if (tid == 0) { S.err = 0; S.ncand_total = 0; S.nseat = 0; S.nfree = 0; }
-  for (int i = tid; i < 3 * V + 2; i += kFinThreads) S.hyp[i] = c.hyp[i];
-  // The random numbers of the hyper step depend on nothing but (seed, sweep, index): the last warps draw them
-  // now, while the others wait on the packet loads below, instead of in the middle of the serial MH chain.
-  if ((flags & kFinHyper) && tid >= kFinThreads - 64) {
-    for (int i = tid - (kFinThreads - 64); i < 2 * (3 * V + 2); i += 64) {
-      if (i < 3 * V + 2) S.rn[i] = dev_normal(c.seed, c.chain, sweep, i);
-      else S.lu[i - (3 * V + 2)] = fin_log(dev_unif(c.seed, c.chain, sweep, i - (3 * V + 2)));
-    }
-    // ... and touch the other out-of-line FP64 routines of the MH chain, so that their code is in the instruction
-    // cache before the chain needs it
-    if (tid == kFinThreads - 1) { S.warm[0] = fin_lgamma(2.5 + (double)sweep); S.warm[1] = fin_exp(-1.0 - (double)V); }
+  if (tid == 32) {
+    S.hyp[0] = is_view ? c.hyp[v] : c.hyp[3 * V];
+    S.hyp[1] = is_view ? c.hyp[V + v] : c.hyp[3 * V + 1];
+    S.hyp[2] = is_view ? c.hyp[2 * V + v] : 0.0;
   }
-  // ---- A. rank-ordered sums of the shards' packets ------------------------------------------
+  // The random numbers of the hyper step depend on nothing but (seed, sweep, index): the last warps draw them now,
+  // while the others wait on the loads below, instead of in the middle of the serial MH chain.  Stream positions are
+  // those the reference's sequential code would use: tau_v at v, (alpha_v, sigma_v) at V + 2v, the franchise at 3V.
+  if ((flags & kFinHyper) && tid >= kFinThreads - 6 * 32 && (tid & 31) == 0) {
+    const int q = (tid - (kFinThreads - 6 * 32)) >> 5;          // six independent values on six warps
+    const int which = q % 3;                                     // 0 tau, 1 alpha, 2 sigma
+    const int idx = (which == 0) ? v : ((is_view ? V + 2 * v : 3 * V) + which - 1);
+    if (which != 0 || is_view) {
+      if (q < 3) S.rn[which] = dev_normal(c.seed, c.chain, sweep, idx);
+      else S.lu[which] = fin_log(dev_unif(c.seed, c.chain, sweep, idx));
+    }
+  }
+  // ... and touch the other out-of-line FP64 routines of the MH chain, so that their code is in the instruction
+  // cache before the chain needs it
+  if ((flags & kFinHyper) && tid == kFinThreads - 7 * 32) { S.warm[0] = fin_lgamma(2.5 + (double)sweep); S.warm[1] = fin_exp(-1.0 - (double)V); }
+
+  // ---- A. this level's inputs: the statistics summed over the shards (k_reduce_x), the sweep-start state --------
   for (int t = tid; t < cap; t += kFinThreads) {
-    int n = 0;
-    for (int g = 0; g < c.world; ++g) n += pkt_i32(c, g, c.pkt.off_cnt)[t];
-    S.n_new[t] = n;
-    S.alive_start[t] = c.n_t[t] > 0;
+    S.n_new[t] = c.sum_cnt[t];
+    S.n_start[t] = c.n_t[t];
   }
-  {
-    // S1t = sum over the shards in rank order.  Eight elements per thread are in flight at once: the loop is a
-    // chain of global-memory latencies otherwise.
-    constexpr int kB = 8;
-    const double* p0 = pkt_f64(c, 0, c.pkt.off_s1t);
-    const size_t gstride = (size_t)c.pkt.bytes / sizeof(double);     // packet sizes are multiples of 16 bytes
-    const int n_s1 = cap * c.Dsum;
-    for (int i0 = tid; i0 < n_s1; i0 += kB * kFinThreads) {
-      double sum[kB];
-#pragma unroll
-      for (int u = 0; u < kB; ++u) {
-        const int i = i0 + u * kFinThreads;
-        sum[u] = (i < n_s1) ? p0[i] : 0.0;
-      }
-      for (int g = 1; g < c.world; ++g) {
-#pragma unroll
-        for (int u = 0; u < kB; ++u) {
-          const int i = i0 + u * kFinThreads;
-          if (i < n_s1) sum[u] += p0[(size_t)g * gstride + i];
-        }
-      }
-#pragma unroll
-      for (int u = 0; u < kB; ++u) {
-        const int i = i0 + u * kFinThreads;
-        if (i < n_s1) S1t[i] = sum[u];
-      }
+  if (is_view) {
+    if (s1_in_smem) {
+      const double* src = c.sum_s1t + (size_t)cap * doff;
+      const int n_s1 = cap * D;
+      for (int i = tid; i < n_s1; i += kFinThreads) S1t[i] = src[i];
     }
-  }
-  for (int i = tid; i < V * cap; i += kFinThreads) {
-    double sum = 0.0;
-    for (int g = 0; g < c.world; ++g) sum += pkt_f64(c, g, c.pkt.off_s2t)[i];
-    (&S.s2t[0][0])[(i / cap) * kMaxCap + (i % cap)] = sum;
-    const int v = i / cap, t = i - v * cap;
-    S.dish[v][t] = c.dish_of[i];
-    S.l_live[v][t] = c.l_vk[i];
-    S.n_vk[v][t] = c.n_vk[i];
+    for (int t = tid; t < cap; t += kFinThreads) {
+      S.s2t[t] = c.sum_s2t[v * cap + t];
+      S.dish[t] = c.dish_of[v * cap + t];
+      S.l_live[t] = c.l_vk[v * cap + t];
+      S.n_vk[t] = c.n_vk[v * cap + t];
+    }
   }
   __syncthreads();
-  if (c.n_count_views) {
-    for (int i = tid; i < V * cap; i += kFinThreads) {
-      const int v = i / cap, k = i - v * cap;
-      S.s2k_start[v][k] = c.S2k[i];
-      int tk = -1;
-      for (int t = cap - 1; t >= 0; --t) if (S.dish[v][t] == k && c.n_t[t] > 0) tk = t;
-      S.table_of_dish[v][k] = tk;
-    }
-    __syncthreads();
+  if (is_view && !s1_in_smem) {                     // large views: the sums stay in global memory (own block of S1t)
+    const double* src = c.sum_s1t + (size_t)cap * doff;
+    const int n_s1 = cap * D;
+    for (int i = tid; i < n_s1; i += kFinThreads) S1t[i] = src[i];
   }
+  if (is_count) {
+    for (int k = tid; k < cap; k += kFinThreads) {
+      S.s2k_start[k] = c.S2k[v * cap + k];
+      int tk = -1;
+      for (int t = cap - 1; t >= 0; --t) if (S.dish[t] == k && S.n_start[t] > 0) tk = t;
+      S.table_of_dish[k] = tk;
+    }
+  }
+  __syncthreads();
+  // every read of what the franchise CTA updates in place is done: announce it
+  if (tid == 0) { __threadfence(); atomicAdd(c.fin_arrive, 1u); }
 
   stamp(0);
   // ---- B. births: candidates in global row order, the first nfree are seated -----------------
@@ -642,14 +636,14 @@ __global__ void __launch_bounds__(kFinThreads, 1) k_finalize(const Ctx c, const 
       int n = 0;
       for (int g = 0; g < c.world; ++g) n += pkt_i32(c, g, c.pkt.off_hdr)[0];
       S.ncand_total = n;
-      if (n == 0 && c.debug_export) *c.dbg_nseated = 0;
+      if (n == 0 && c.debug_export && !is_view) *c.dbg_nseated = 0;
     }
     __syncthreads();
   }
   if ((flags & kFinReseat) && S.ncand_total > 0) {
     if (tid == 0) {
       int nf = 0;
-      for (int t = 0; t < cap; ++t) if (!S.alive_start[t]) S.free_slots[nf++] = t;
+      for (int t = 0; t < cap; ++t) if (S.n_start[t] <= 0) S.free_slots[nf++] = t;
       S.nfree = nf;
       int n = 0;
       for (int g = 0; g < c.world; ++g) {
@@ -658,63 +652,60 @@ __global__ void __launch_bounds__(kFinThreads, 1) k_finalize(const Ctx c, const 
       }
       S.ncand_total = n;
       S.nseat = n < nf ? n : nf;
-      if (c.debug_export) *c.dbg_nseated = S.nseat;
+      if (c.debug_export && !is_view) *c.dbg_nseated = S.nseat;
     }
     __syncthreads();
     const int nseat = S.nseat, ncand = S.ncand_total;
-    // B1. log f of every seated candidate under every dish slot (and a new dish), in parallel
-    for (int idx = tid; idx < nseat * V * (cap + 1); idx += kFinThreads) {
-      const int b = idx / (V * (cap + 1));
-      const int rem = idx - b * V * (cap + 1);
-      const int v = rem / (cap + 1), k = rem - v * (cap + 1);
-      const float* x = pkt_f32(c, S.cand_g[b], c.pkt.off_cand_x) + (size_t)S.cand_j[b] * c.Dsum;
-      double val;
-      if (c.kind[v]) {  // count view (one GPU per chain: the candidate's row is local)
-        const int row = pkt_i32(c, S.cand_g[b], c.pkt.off_cand_row)[S.cand_j[b]];
-        if (k == cap) {
-          double tot = 0.0;
-          for (int j = c.rowptr[v][row]; j < c.rowptr[v][row + 1]; ++j) tot += (double)c.val[v][j];
-          val = -tot * fin_log((double)c.vocab[v]);
+    if (is_view) {
+      // B1. log f of every seated candidate under every dish slot of this view (and a new dish), in parallel
+      for (int idx = tid; idx < nseat * (cap + 1); idx += kFinThreads) {
+        const int b = idx / (cap + 1), k = idx - b * (cap + 1);
+        const float* x = pkt_f32(c, S.cand_g[b], c.pkt.off_cand_x) + (size_t)S.cand_j[b] * c.Dsum + doff;
+        double val;
+        if (is_count) {  // count view (one GPU per chain: the candidate's row is local)
+          const int row = pkt_i32(c, S.cand_g[b], c.pkt.off_cand_row)[S.cand_j[b]];
+          if (k == cap) {
+            double tot = 0.0;
+            for (int j = c.rowptr[v][row]; j < c.rowptr[v][row + 1]; ++j) tot += (double)c.val[v][j];
+            val = -tot * fin_log((double)c.vocab[v]);
+          } else {
+            const int t0 = pkt_i32(c, S.cand_g[b], c.pkt.off_cand_t0)[S.cand_j[b]];
+            val = log_f_dish_counts(c.rowptr[v], c.col[v], c.val[v], c.cnt_d[v], cap, (double)c.vocab[v] * (double)c.count_beta,
+                                    (double)c.count_beta, S.s2k_start[k], S.table_of_dish[k], row,
+                                    (k == S.dish[t0]) && S.n_vk[k] > 0);
+          }
+        } else if (k == cap) {   // new dish: N(x; 0, tau)   (multiview_utils.cpp:340-350)
+          double q = 0.0;
+          for (int dd = 0; dd < D; ++dd) q += (double)x[dd] * (double)x[dd];
+          val = -0.5 * (double)D * fin_log(2.0 * kPi * tau_l) - 0.5 * q / tau_l;
         } else {
           const int t0 = pkt_i32(c, S.cand_g[b], c.pkt.off_cand_t0)[S.cand_j[b]];
-          val = log_f_dish_counts(c.rowptr[v], c.col[v], c.val[v], c.cnt_d[v], cap, (double)c.vocab[v] * (double)c.count_beta,
-                                  (double)c.count_beta, S.s2k_start[v][k], S.table_of_dish[v][k], row,
-                                  (k == S.dish[v][t0]) && S.n_vk[v][k] > 0);
+          val = log_f_dish(D, c.S1k + (size_t)cap * doff + (size_t)k * D, (double)S.n_vk[k], x,
+                           (k == S.dish[t0]) && S.n_vk[k] > 0, tau_l);
         }
-      } else if (k == cap) {   // new dish: N(x; 0, tau)   (multiview_utils.cpp:340-350)
-        const int D = c.D[v];
-        double q = 0.0;
-        for (int dd = 0; dd < D; ++dd) q += (double)x[c.doff[v] + dd] * (double)x[c.doff[v] + dd];
-        val = -0.5 * (double)D * fin_log(2.0 * kPi * tau_v[v]) - 0.5 * q / tau_v[v];
-      } else {
-        const int t0 = pkt_i32(c, S.cand_g[b], c.pkt.off_cand_t0)[S.cand_j[b]];
-        val = log_f_dish(c.D[v], c.S1k + (size_t)cap * c.doff[v] + (size_t)k * c.D[v], (double)S.n_vk[v][k], x + c.doff[v],
-                         (k == S.dish[v][t0]) && S.n_vk[v][k] > 0, tau_v[v]);
+        c.birth_lf[((size_t)b * V + v) * (cap + 1) + k] = val;
       }
-      c.birth_lf[idx] = val;
-    }
-    __syncthreads();
-    // B2. seating in order; sample_dish_for_new_table (multiview_utils.cpp:224-276) per view
-    for (int b = 0; b < nseat; ++b) {
-      const int g = S.cand_g[b], j = S.cand_j[b];
-      const int t0 = pkt_i32(c, g, c.pkt.off_cand_t0)[j];
-      const int64_t grow = *reinterpret_cast<const int64_t*>(pkt_i32(c, g, c.pkt.off_hdr) + 4) +
-                           (int64_t)pkt_i32(c, g, c.pkt.off_cand_row)[j];
-      const int tn = S.free_slots[b];
-      const bool single = (c.n_t[t0] == 1);
-      for (int v = 0; v < V; ++v) {
-        const int k0 = S.dish[v][t0];
+      __syncthreads();
+      // B2. seating in order; sample_dish_for_new_table (multiview_utils.cpp:224-276) for this view
+      for (int b = 0; b < nseat; ++b) {
+        const int g = S.cand_g[b], j = S.cand_j[b];
+        const int t0 = pkt_i32(c, g, c.pkt.off_cand_t0)[j];
+        const int64_t grow = *reinterpret_cast<const int64_t*>(pkt_i32(c, g, c.pkt.off_hdr) + 4) +
+                             (int64_t)pkt_i32(c, g, c.pkt.off_cand_row)[j];
+        const int tn = S.free_slots[b];
+        const bool single = (S.n_start[t0] == 1);
+        const int k0 = S.dish[t0];
         const double* lf = c.birth_lf + ((size_t)b * V + v) * (cap + 1);
         if (tid <= cap) {
           double lw = -INFINITY;
           if (tid < cap) {
-            const int l = S.l_live[v][tid] - ((single && tid == k0) ? 1 : 0);
-            const double w = (double)l - sigma_v[v];                       // :232-233
+            const int l = S.l_live[tid] - ((single && tid == k0) ? 1 : 0);
+            const double w = (double)l - sigma_l;                            // :232-233
             if (l > 0 && w > 0.0) lw = fin_log(w) + lf[tid];
           } else {
             int K_act = 0;
-            for (int k = 0; k < cap; ++k) K_act += (S.l_live[v][k] - ((single && k == k0) ? 1 : 0)) > 0;
-            const double wn = alpha_v[v] + sigma_v[v] * (double)K_act;     // :241-243
+            for (int k = 0; k < cap; ++k) K_act += (S.l_live[k] - ((single && k == k0) ? 1 : 0)) > 0;
+            const double wn = alpha_l + sigma_l * (double)K_act;             // :241-243
             if (wn > 0.0) lw = fin_log(wn) + lf[cap];
           }
           S.wbuf[tid] = lw;
@@ -729,7 +720,7 @@ __global__ void __launch_bounds__(kFinThreads, 1) k_finalize(const Ctx c, const 
         if (tid <= cap) {
           const double M = S.result[0], lw = S.wbuf[tid];
           const double w = (M > -INFINITY && lw > -INFINITY) ? fin_exp(lw - M) : 0.0;
-          S.termA[0][tid] = w;
+          S.wexp[tid] = w;
           if (c.debug_export) c.dbg_birth_w[((size_t)b * V + v) * (cap + 1) + tid] = w;
         }
         __syncthreads();
@@ -737,186 +728,193 @@ __global__ void __launch_bounds__(kFinThreads, 1) k_finalize(const Ctx c, const 
           int pick = -1;
           if (S.result[0] > -INFINITY) {
             double total = 0.0;
-            for (int k = 0; k <= cap; ++k) total += S.termA[0][k];         // :247-248
+            for (int k = 0; k <= cap; ++k) total += S.wexp[k];               // :247-248
             const U4 r = stream_block(c.seed, c.chain, kDomDish, (uint32_t)v, sweep, (uint64_t)grow);
-            const double u = uniform_f64_from(r.x, r.y) * total;           // :261
+            const double u = uniform_f64_from(r.x, r.y) * total;             // :261
             double cum = 0.0;
             for (int k = 0; k < cap; ++k) {
               if (!(S.wbuf[k] > -INFINITY)) continue;
-              cum += S.termA[0][k];
+              cum += S.wexp[k];
               if (u < cum) { pick = k; break; }
             }
           }
-          if (pick < 0) {                                                   // new dish: lowest free slot
-            for (int k = 0; k < cap; ++k) if (S.l_live[v][k] == 0) { pick = k; break; }
+          if (pick < 0) {                                                     // new dish: lowest free slot
+            for (int k = 0; k < cap; ++k) if (S.l_live[k] == 0) { pick = k; break; }
           }
           if (pick < 0) { S.err |= 1; pick = 0; }
-          S.dish[v][tn] = pick;
-          S.l_live[v][pick] += 1;                                           // :283
+          S.dish[tn] = pick;
+          S.l_live[pick] += 1;                                                // :283
         }
         __syncthreads();
       }
-      if (tid == 0) {
-        S.cand_final[b] = tn;
-        if (c.debug_export) c.dbg_birth_rows[b] = grow;
-      }
     }
-    for (int b = nseat + tid; b < ncand; b += kFinThreads)
-      S.cand_final[b] = pkt_i32(c, S.cand_g[b], c.pkt.off_cand_t0)[S.cand_j[b]];   // overflow: stay put
+    // the seat every candidate ends at: a function of the candidate order and the free slots alone (every CTA's copy)
+    for (int b = tid; b < ncand; b += kFinThreads)
+      S.cand_final[b] = (b < nseat) ? S.free_slots[b] : pkt_i32(c, S.cand_g[b], c.pkt.off_cand_t0)[S.cand_j[b]];   // overflow: stay put
     __syncthreads();
     // B3. candidates join the statistics of their final table, in global row order
     if (tid == 0) for (int b = 0; b < ncand; ++b) S.n_new[S.cand_final[b]] += 1;
-    if (tid == 32) {
-      for (int b = 0; b < ncand; ++b)
-        if (S.cand_g[b] == c.rank)
-          c.table_cur[pkt_i32(c, c.rank, c.pkt.off_cand_row)[S.cand_j[b]]] = S.cand_final[b];
-    }
-    if (tid >= 64 && tid < 64 + V) {
-      const int v = tid - 64;
-      for (int b = 0; b < ncand; ++b) {
-        const float* x = pkt_f32(c, S.cand_g[b], c.pkt.off_cand_x) + (size_t)S.cand_j[b] * c.Dsum + c.doff[v];
-        double q = 0.0;
-        for (int dd = 0; dd < c.D[v]; ++dd) q += (double)x[dd] * (double)x[dd];
-        if (c.kind[v])     // count view: this slot carries token totals; the candidate's row is local (world = 1)
-          q = (double)c.xx[(size_t)v * c.xx_stride + pkt_i32(c, S.cand_g[b], c.pkt.off_cand_row)[S.cand_j[b]]];
-        S.s2t[v][S.cand_final[b]] += q;
+    if (!is_view) {
+      if (tid == 32) {
+        for (int b = 0; b < ncand; ++b)
+          if (S.cand_g[b] == c.rank)
+            c.table_cur[pkt_i32(c, c.rank, c.pkt.off_cand_row)[S.cand_j[b]]] = S.cand_final[b];
       }
-    }
-    for (int e = tid; e < c.Dsum; e += kFinThreads) {
-      int v = 0;
-      while (v + 1 < V && e >= c.doff[v + 1]) ++v;
-      const int dd = e - c.doff[v];
-      for (int b = 0; b < ncand; ++b) {
-        const float xv = pkt_f32(c, S.cand_g[b], c.pkt.off_cand_x)[(size_t)S.cand_j[b] * c.Dsum + e];
-        S1t[(size_t)cap * c.doff[v] + (size_t)S.cand_final[b] * c.D[v] + dd] += (double)xv;
+      if (tid == 64 && c.debug_export)
+        for (int b = 0; b < nseat; ++b)
+          c.dbg_birth_rows[b] = *reinterpret_cast<const int64_t*>(pkt_i32(c, S.cand_g[b], c.pkt.off_hdr) + 4) +
+                                (int64_t)pkt_i32(c, S.cand_g[b], c.pkt.off_cand_row)[S.cand_j[b]];
+    } else {
+      if (tid == 64) {
+        for (int b = 0; b < ncand; ++b) {
+          const float* x = pkt_f32(c, S.cand_g[b], c.pkt.off_cand_x) + (size_t)S.cand_j[b] * c.Dsum + doff;
+          double q = 0.0;
+          for (int dd = 0; dd < D; ++dd) q += (double)x[dd] * (double)x[dd];
+          if (is_count)      // count view: this slot carries token totals; the candidate's row is local (world = 1)
+            q = (double)c.xx[(size_t)v * c.xx_stride + pkt_i32(c, S.cand_g[b], c.pkt.off_cand_row)[S.cand_j[b]]];
+          S.s2t[S.cand_final[b]] += q;
+        }
+      }
+      for (int dd = tid; dd < D; dd += kFinThreads) {
+        for (int b = 0; b < ncand; ++b) {
+          const float xv = pkt_f32(c, S.cand_g[b], c.pkt.off_cand_x)[(size_t)S.cand_j[b] * c.Dsum + doff + dd];
+          S1t[(size_t)S.cand_final[b] * D + dd] += (double)xv;
+        }
       }
     }
     __syncthreads();
   }
 
   stamp(1);
+  constexpr int kGroupThreads = kFinThreads / 2;
+  if (!is_view) {
+    // =============================== the franchise level ===============================
+    if (tid == kFinThreads - 32) {                               // every customer must have been counted exactly once
+      long long tot = 0;
+      for (int t = 0; t < cap; ++t) tot += S.n_new[t];
+      if (tot != (long long)c.n_global) atomicOr(&S.err, 4);
+    }
+    if (tid == 0) {
+      unsigned long long m = 0ull;
+      for (int i = 0; i < cap; ++i) if (S.n_new[i] > 0) m |= 1ull << i;
+      S.live = m;
+      S.total = (long long)c.n_global;
+    }
+    if (flags & kFinTauInit) { if (tid == 0) { alpha_l = 1.0; sigma_l = 0.6; } }      // multiview_gibbs.cpp:97-98
+    __syncthreads();
+    // (alpha_global, sigma_global), multiview_hyper.cpp:268-291, by the first half of the CTA
+    if (tid < kGroupThreads)
+      level_alpha_sigma(cap, S.n_new, S, tid, kGroupThreads, 1, (flags & kFinHyper) && (flags & kFinHyperGlobal));
+    __syncthreads();
+    stamp(2);
+    // publish: only after every CTA has read the sweep-start values this overwrites
+    if (tid == 0) {
+      while (*reinterpret_cast<volatile uint32_t*>(c.fin_arrive) < (uint32_t)(V + 1)) { }
+      __threadfence();
+    }
+    __syncthreads();
+    for (int t = tid; t < cap; t += kFinThreads) {
+      c.n_t[t] = S.n_new[t];
+      const double mass = (double)S.n_new[t] - sigma_l, mass1 = mass - 1.0;
+      TableMass tm;
+      tm.LM = (S.n_new[t] > 0 && mass > 0.0) ? (float)fin_log2(mass) : kMasked;
+      tm.LM1 = (S.n_new[t] > 1 && mass1 > 0.0) ? (float)fin_log2(mass1) : kMasked;
+      tm.single = (S.n_new[t] == 1);
+      tm.pad = 0;
+      c.tmass[t] = tm;
+    }
+    if (tid == 15 * 32) {
+      c.hyp[3 * V] = alpha_l;
+      c.hyp[3 * V + 1] = sigma_l;
+      int T_ne = 0;
+      for (int t = 0; t < cap; ++t) T_ne += S.n_new[t] > 0;
+      const int F = cap - T_ne;
+      const double mn0 = alpha_l + sigma_l * (double)T_ne, mn1 = alpha_l + sigma_l * (double)(T_ne - 1);
+      GlobalParam g;
+      g.LMN0 = (F > 0 && mn0 > 0.0) ? (float)fin_log2(mn0) : kMasked;
+      g.LMN1 = (F > 0 && mn1 > 0.0) ? (float)fin_log2(mn1) : kMasked;
+      g.nfree = F;
+      const uint32_t next = sweep + ((flags & kFinAdvance) ? 1u : 0u);
+      g.sweep = next;
+      *c.gparam = g;
+      *c.sweep = next;
+      *c.fin_arrive = 0u;                                        // ready for the next launch
+      if (c.world > 1) *c.xseq += 1u;                            // one exchange precedes every finalize (mv_exchange.cu)
+      if (S.err) atomicOr(c.status, S.err);
+    }
+    stamp(5);
+    return;
+  }
+
+  // =============================== a view ===============================
   // ---- C. deaths and per-dish statistics -------------------------------------------------------
-  for (int i = tid; i < V * cap; i += kFinThreads) {
-    const int v = i / cap, t = i - v * cap;
-    if (S.n_new[t] == 0) S.dish[v][t] = -1;                  // multiview_utils.cpp:168-191
-    else if (S.dish[v][t] < 0 || S.dish[v][t] >= cap) { S.err |= 2; S.dish[v][t] = 0; }
+  for (int t = tid; t < cap; t += kFinThreads) {
+    if (S.n_new[t] == 0) S.dish[t] = -1;                     // multiview_utils.cpp:168-191
+    else if (S.dish[t] < 0 || S.dish[t] >= cap) { S.err |= 2; S.dish[t] = 0; }
   }
   __syncthreads();
-  stamp(6);
-  for (int i = tid; i < V * cap; i += kFinThreads) {
-    const int v = i / cap, k = i - v * cap;
+  for (int k = tid; k < cap; k += kFinThreads) {
     int l = 0, n = 0;
     double s2 = 0.0;
     unsigned long long m = 0ull;                                // which tables serve dish (v, k)
     for (int t = 0; t < cap; ++t)
-      if (S.dish[v][t] == k) { l += 1; n += S.n_new[t]; s2 += S.s2t[v][t]; m |= 1ull << t; }
-    S.l_live[v][k] = l;
-    S.n_vk[v][k] = n;
-    S.s2k[v][k] = s2;
-    S.tmask[v][k] = m;
+      if (S.dish[t] == k) { l += 1; n += S.n_new[t]; s2 += S.s2t[t]; m |= 1ull << t; }
+    S.l_live[k] = l;
+    S.n_vk[k] = n;
+    S.s2k[k] = s2;
+    S.tmask[k] = m;
+    const int i = v * cap + k;
     c.S2k[i] = s2;
-    c.S2t[i] = S.s2t[v][k];                                 // (index reuse: i = v*cap + slot)
+    c.S2t[i] = S.s2t[k];                                    // (index reuse: slot k as a table)
     c.l_vk[i] = l;
     c.n_vk[i] = n;
-    c.dish_of[i] = S.dish[v][k];
-  }
-  for (int t = tid; t < cap; t += kFinThreads) c.n_t[t] = S.n_new[t];
-  if (tid == kFinThreads - 32) {                               // every customer must have been counted exactly once
-    long long tot = 0;
-    for (int t = 0; t < cap; ++t) tot += S.n_new[t];
-    if (tot != (long long)c.n_global) atomicOr(&S.err, 4);
+    c.dish_of[i] = S.dish[k];
   }
   __syncthreads();
   stamp(7);
   // From here the CTA works as two halves that meet again before the parameter block:
-  //   upper half (named barrier 1): the (alpha, sigma) Metropolis-Hastings steps of the V views and of the franchise —
-  //     they only need the COUNTS fixed above (tables per dish, customers per table);
+  //   upper half (named barrier 1): the (alpha_v, sigma_v) Metropolis-Hastings pair — it only needs the COUNTS fixed
+  //     above (tables per dish);
   //   lower half (named barrier 2): per-dish statistics -> tau_v step (needs their sums of squares) -> posterior means
   //     (need the new tau_v).
   // Two independent FP64 latency chains of similar length: side by side they cost the longer one.
-  __shared__ double s_alpha[2 * (kMaxViews + 1)], s_sigma[2 * (kMaxViews + 1)];
-  constexpr int kGroupThreads = kFinThreads / 2;
   if (tid >= kGroupThreads) {
-    // =============================== upper half: alpha / sigma ===============================
     const int gtid = tid - kGroupThreads;
-    if (gtid <= V) {                            // live masks and item totals of the EPPF levels
-      const int j = gtid;
-      const int32_t* counts = (j < V) ? S.l_live[j] : S.n_new;
+    if (gtid == 0) {                            // live mask and item total of this level
       unsigned long long m = 0ull;
       long long tot = 0;
-      for (int i = 0; i < cap; ++i) { if (counts[i] > 0) m |= 1ull << i; tot += counts[i]; }
-      S.live[j] = m;
-      S.total[j] = (j < V) ? tot : (long long)c.n_global;
+      for (int i = 0; i < cap; ++i) { if (S.l_live[i] > 0) m |= 1ull << i; tot += S.l_live[i]; }
+      S.live = m;
+      S.total = tot;
     }
     group_sync(1, kGroupThreads);
-    // ---- D2. (alpha, sigma) per level (multiview_hyper.cpp:239-291): one thread per level, on Philox numbers addressed
-    //      by the position the reference's sequential code would draw them at ----
-    if (flags & kFinHyper) {
-      // level j: its alpha/sigma slots in S.hyp and its Philox indices (alpha: base, sigma: base+1)
-      const int j = gtid;
-      const bool is_level = (j < V) ? (flags & kFinHyperLocal) != 0 : (j == V && (flags & kFinHyperGlobal) != 0);
-      const int ia = (j < V) ? j : 3 * V, is = (j < V) ? V + j : 3 * V + 1;
-      const int base = (j < V) ? V + 2 * j : 3 * V;
-      // alpha: log-normal random walk, :242-255 / :268-281
-      double a_old = 0.0, a_prop = 0.0;
-      if (is_level) {
-        a_old = S.hyp[ia];
-        if (a_old <= 0.0) a_old = kEps;
-        const double cand = fin_exp(fin_log(a_old > kEps ? a_old : kEps) + 0.0 + 0.1 * S.rn[base]);   // :100-108
-        a_prop = cand > kEps ? cand : kEps;
-        s_alpha[2 * j] = a_old; s_alpha[2 * j + 1] = a_prop;
-        s_sigma[2 * j] = S.hyp[is]; s_sigma[2 * j + 1] = S.hyp[is];
-      }
-      eppf_batch(cap, V, S, s_alpha, s_sigma, gtid, kGroupThreads, 1);
-      stamp(11);
-      double s_old = 0.0, s_prop = 0.0;
-      if (is_level) {
-        const double lo = S.eppf[2 * j] + log_prior_alpha(a_old), ln = S.eppf[2 * j + 1] + log_prior_alpha(a_prop);
-        const double log_acc = (ln - lo) + (fin_log(a_prop) - fin_log(a_old));
-        if (S.lu[base] < log_acc) S.hyp[ia] = a_prop;
-        // sigma: reflected random walk, :257-265 / :283-291
-        s_old = S.hyp[is];
-        s_prop = reflect_unit(s_old + 0.0 + 0.05 * S.rn[base + 1]);                             // :124-128
-        s_alpha[2 * j] = S.hyp[ia]; s_alpha[2 * j + 1] = S.hyp[ia];
-        s_sigma[2 * j] = s_old; s_sigma[2 * j + 1] = s_prop;
-      }
-      eppf_batch(cap, V, S, s_alpha, s_sigma, gtid, kGroupThreads, 1);
-      stamp(12);
-      if (is_level) {
-        const double lpo = (s_old <= kEps || s_old >= 1.0 - kEps) ? -INFINITY : S.eppf[2 * j] + log_prior_sigma(s_old);
-        const double lpn = (s_prop <= kEps || s_prop >= 1.0 - kEps) ? -INFINITY : S.eppf[2 * j + 1] + log_prior_sigma(s_prop);
-        if (S.lu[base + 1] < lpn - lpo) S.hyp[is] = s_prop;
-      }
-    }
-    if ((c.debug_export & 2) != 0 && c.dbg_prof != nullptr && gtid == 0) pout[13] = clock64() - t_begin_all;   // upper half done
+    if (!(flags & kFinTauInit))                 // (the reference's initial values are set by the lower half below)
+      level_alpha_sigma(cap, S.l_live, S, gtid, kGroupThreads, 1, (flags & kFinHyper) && (flags & kFinHyperLocal));
+    if ((c.debug_export & 2) != 0 && c.dbg_prof != nullptr && gtid == 0) pout[13] = clock64() - t_begin;   // upper half done
   } else {
-    // =============================== lower half: dish statistics, tau, means ===============================
     {
-      // one warp per dish (v, k): lanes stride over the coordinates; the tables serving the dish are added in
+      // one warp per dish k: lanes stride over the coordinates; the tables serving the dish are added in
       // ascending order (warp-uniform loop), then |S1k|^2 by a fixed shuffle tree
       const int lane = tid & 31, wid = tid >> 5;
-      for (int i = wid; i < V * cap; i += kGroupThreads / 32) {
-        const int v = i >> cshift, k = i & (cap - 1);
-        const int D = c.D[v], base = cap * c.doff[v];
-        const double* S1t_v = S1t + base;
-        double* S1k_vk = c.S1k + base + k * D;
-        const unsigned long long mask = S.tmask[v][k];
+      for (int k = wid; k < cap; k += kGroupThreads / 32) {
+        double* S1k_vk = c.S1k + (size_t)cap * doff + (size_t)k * D;
+        const unsigned long long mask = S.tmask[k];
         const int t1 = __ffsll((long long)mask) - 1;             // usually the only table of the dish
         const unsigned long long more = mask & (mask - 1ull);
         double q = 0.0;
         for (int dd = lane; dd < D; dd += 32) {
-          double sum = (t1 >= 0) ? S1t_v[t1 * D + dd] : 0.0;
-          for (unsigned long long m = more; m; m &= m - 1ull) sum += S1t_v[(__ffsll((long long)m) - 1) * D + dd];
+          double sum = (t1 >= 0) ? S1t[t1 * D + dd] : 0.0;
+          for (unsigned long long m = more; m; m &= m - 1ull) sum += S1t[(__ffsll((long long)m) - 1) * D + dd];
           S1k_vk[dd] = sum;
           q += sum * sum;
         }
-  #pragma unroll
+#pragma unroll
         for (int o = 16; o > 0; o >>= 1) q += __shfl_xor_sync(0xffffffffu, q, o);
         if (lane == 0) {
-          S.s1sq[v][k] = q;
-          const int n_k = S.n_vk[v][k];
-          double sse = (n_k > 0) ? S.s2k[v][k] - q / (double)n_k : 0.0;
-          S.sse[v][k] = sse < 0.0 ? 0.0 : sse;
+          S.s1sq[k] = q;
+          const int n_k = S.n_vk[k];
+          double sse = (n_k > 0) ? S.s2k[k] - q / (double)n_k : 0.0;
+          S.sse[k] = sse < 0.0 ? 0.0 : sse;
         }
       }
     }
@@ -924,77 +922,67 @@ __global__ void __launch_bounds__(kFinThreads, 1) k_finalize(const Ctx c, const 
     stamp(2);
     // ---- reference initialisation of the hyperparameters (multiview_gibbs.cpp:75-98) ------------
     if (flags & kFinTauInit) {
-      if (tid < V) {
-        const int v = tid;
+      if (tid == 0) {
         // all customers sit at table 0 / dish 0 during this call: pooled variance over coordinates
         const double n = (double)c.n_global;
         double var = 1.0;
-        if (c.n_global > 1) var = (S.s2k[v][0] - S.s1sq[v][0] / n) / ((n - 1.0) * (double)c.D[v]);
+        if (c.n_global > 1) var = (S.s2k[0] - S.s1sq[0] / n) / ((n - 1.0) * (double)D);
         if (!(var > 0.0)) var = 1.0;
-        tau_v[v] = c.kind[v] ? 1.0 : var * 0.25 * 0.01;      // a count view has no kernel variance
-        alpha_v[v] = 1.0;
-        sigma_v[v] = 0.5;
+        tau_l = is_count ? 1.0 : var * 0.25 * 0.01;          // a count view has no kernel variance
+        alpha_l = 1.0;
+        sigma_l = 0.5;
       }
-      if (tid == 0) { alpha_g = 1.0; sigma_g = 0.6; }
       group_sync(2, kGroupThreads);
     }
-    stamp(3);
-    // ---- D1. tau_v (update_tau_v_MH, multiview_hyper.cpp:211-231): independent across views, one warp per view ----
-    if (flags & kFinHyper) {
-      if (flags & kFinHyperTau) {                                // update_tau_v_MH, :211-231: one warp per view
-        const int lane = tid & 31, wid = tid >> 5;
-        for (int v = wid; v < V; v += kGroupThreads / 32) {
-          if (c.kind[v]) continue;                               // no tau in a count view (its stream positions stay unused)
-          double tau_old = tau_v[v];
-          if (tau_old <= 0.0) tau_old = kEps;
-          const double tau_prop = fin_exp(fin_log(tau_old) + 0.0 + 0.3 * S.rn[v]);   // :166-174
-          // log_posterior_given_tau (:176-209) at both values: lanes stride over the dishes, shuffle-tree sum
-          const double lg_o = fin_log(2.0 * kPi * tau_old), lg_p = fin_log(2.0 * kPi * tau_prop);
-          const double Dd = (double)c.D[v];
-          double lo = 0.0, ln = 0.0;
-          for (int k = lane; k < cap; k += 32) {
-            const int n_k = S.n_vk[v][k];
-            if (n_k == 0) continue;
-            lo += -0.5 * (double)n_k * Dd * lg_o - 0.5 * (S.sse[v][k] / tau_old);
-            ln += -0.5 * (double)n_k * Dd * lg_p - 0.5 * (S.sse[v][k] / tau_prop);
-          }
-  #pragma unroll
-          for (int o = 16; o > 0; o >>= 1) {
-            lo += __shfl_xor_sync(0xffffffffu, lo, o);
-            ln += __shfl_xor_sync(0xffffffffu, ln, o);
-          }
-          if (lane == 0) {
-            const double a_tau = 2.0, b_tau = 1.0;                                    // :133-134
-            // a log(b) - lgamma(a) = 2 log 1 - lgamma 2 = 0 exactly
-            const double log_old = lo + (-(a_tau + 1.0) * fin_log(tau_old) - b_tau / tau_old);
-            const double log_new = ln + (-(a_tau + 1.0) * fin_log(tau_prop) - b_tau / tau_prop);
-            const double log_acc = (log_new - log_old) + (fin_log(tau_prop) - fin_log(tau_old));
-            if (S.lu[v] < log_acc) tau_v[v] = tau_prop;
-          }
-        }
+    // ---- D1. tau_v (update_tau_v_MH, multiview_hyper.cpp:211-231): warp 0 ----
+    if ((flags & kFinHyper) && (flags & kFinHyperTau) && !is_count && tid < 32) {   // no tau in a count view (its stream positions stay unused)
+      const int lane = tid;
+      double tau_old = tau_l;
+      if (tau_old <= 0.0) tau_old = kEps;
+      const double tau_prop = fin_exp(fin_log(tau_old) + 0.0 + 0.3 * S.rn[0]);   // :166-174
+      // log_posterior_given_tau (:176-209) at both values: lanes stride over the dishes, shuffle-tree sum
+      const double lg_o = fin_log(2.0 * kPi * tau_old), lg_p = fin_log(2.0 * kPi * tau_prop);
+      const double Dd = (double)D;
+      double lo = 0.0, ln = 0.0;
+      for (int k = lane; k < cap; k += 32) {
+        const int n_k = S.n_vk[k];
+        if (n_k == 0) continue;
+        lo += -0.5 * (double)n_k * Dd * lg_o - 0.5 * (S.sse[k] / tau_old);
+        ln += -0.5 * (double)n_k * Dd * lg_p - 0.5 * (S.sse[k] / tau_prop);
+      }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        lo += __shfl_xor_sync(0xffffffffu, lo, o);
+        ln += __shfl_xor_sync(0xffffffffu, ln, o);
+      }
+      if (lane == 0) {
+        const double a_tau = 2.0, b_tau = 1.0;                                    // :133-134
+        // a log(b) - lgamma(a) = 2 log 1 - lgamma 2 = 0 exactly
+        const double log_old = lo + (-(a_tau + 1.0) * fin_log(tau_old) - b_tau / tau_old);
+        const double log_new = ln + (-(a_tau + 1.0) * fin_log(tau_prop) - b_tau / tau_prop);
+        const double log_acc = (log_new - log_old) + (fin_log(tau_prop) - fin_log(tau_old));
+        if (S.lu[0] < log_acc) tau_l = tau_prop;
       }
     }
     group_sync(2, kGroupThreads);
     stamp(9);
     // ---- E1. posterior means of the next sweep (oracle/mv_oracle.c:mvo_make_params) ----------
     {
-      // one warp per (view, table): lanes stride over the coordinates of the posterior mean m = S1k / (tau + n),
+      // one warp per table: lanes stride over the coordinates of the posterior mean m = S1k / (tau + n),
       // S1k re-summed from the per-table sums (same order as above, so the same value), write it (and its TF32
       // split) and reduce |m|^2 by a fixed shuffle tree
       const int lane = tid & 31, wid = tid >> 5;
-      for (int i = wid; i < V * cap; i += kGroupThreads / 32) {
-        const int v = i >> cshift, t = i & (cap - 1);
-        const int D = c.D[v], k = S.dish[v][t], base = cap * c.doff[v];
-        const int off = base + t * D;
-        const double rden = (k >= 0) ? 1.0 / (tau_v[v] + (double)S.n_vk[v][k]) : 0.0;
-        const double* S1t_v = S1t + base;
-        const unsigned long long mask = (k >= 0) ? S.tmask[v][k] : 0ull;
+      for (int t = wid; t < cap; t += kGroupThreads / 32) {
+        const int k = S.dish[t];
+        const int off = cap * doff + t * D;
+        const double rden = (k >= 0) ? 1.0 / (tau_l + (double)S.n_vk[k]) : 0.0;
+        const unsigned long long mask = (k >= 0) ? S.tmask[k] : 0ull;
         const int t1 = __ffsll((long long)mask) - 1;
         const unsigned long long more = mask & (mask - 1ull);
         double mm = 0.0;
         for (int dd = lane; dd < D; dd += 32) {
-          double s1 = (t1 >= 0) ? S1t_v[t1 * D + dd] : 0.0;
-          for (unsigned long long m = more; m; m &= m - 1ull) s1 += S1t_v[(__ffsll((long long)m) - 1) * D + dd];
+          double s1 = (t1 >= 0) ? S1t[t1 * D + dd] : 0.0;
+          for (unsigned long long m = more; m; m &= m - 1ull) s1 += S1t[(__ffsll((long long)m) - 1) * D + dd];
           const float m = (float)(s1 * rden);
           c.mean[off + dd] = m;
           if (c.mean_hi) {
@@ -1007,37 +995,37 @@ __global__ void __launch_bounds__(kFinThreads, 1) k_finalize(const Ctx c, const 
           }
           mm += (double)m * (double)m;
         }
-  #pragma unroll
+#pragma unroll
         for (int o = 16; o > 0; o >>= 1) mm += __shfl_xor_sync(0xffffffffu, mm, o);
-        if (lane == 0) S.s1sq[v][t] = mm;               // (s1sq is free again: reused for |m_t|^2)
+        if (lane == 0) S.s1sq[t] = mm;               // (s1sq is free again: reused for |m_t|^2)
       }
+    }
+    if (!s1_in_smem) {                               // the next launch re-reads sum_s1t; nothing to write back
     }
   }
   __syncthreads();
-  for (int i = tid; i < 3 * V + 2; i += kFinThreads) c.hyp[i] = S.hyp[i];
   stamp(4);
-  stamp(10);
-  for (int i = tid; i < V * cap; i += kFinThreads) {          // the scalar part, one thread per (view, table)
-    const int v = i / cap, t = i - v * cap;
-    const int D = c.D[v];
-    const int k = S.dish[v][t];
-    const double mm = S.s1sq[v][t];
+  if (tid == 32) { c.hyp[v] = alpha_l; c.hyp[V + v] = sigma_l; c.hyp[2 * V + v] = tau_l; }
+  for (int t = tid; t < cap; t += kFinThreads) {          // the scalar part, one thread per table
+    const int i = v * cap + t;
+    const int k = S.dish[t];
+    const double mm = S.s1sq[t];
     TableParam q;
     if (k < 0) {
       q.A = 0.f; q.C = kMasked; q.A1 = 0.f; q.C1 = kMasked; q.W = kMasked; q.W1 = kMasked; q.dish = -1; q.lone = 0;
-    } else if (c.kind[v]) {
+    } else if (is_count) {
       // count view: the dot products are log2 f already (C + A (2 acc - 0) = acc); C1 carries W beta + the token
       // total of the dish for the leave-one-out term of the kernel
       q.A = 0.5f; q.C = 0.f; q.A1 = 0.f;
-      q.C1 = (float)((double)c.vocab[v] * (double)c.count_beta + S.s2k[v][k]);
-      const bool rep = (__ffsll((long long)S.tmask[v][k]) - 1 == t);
-      const double w = (double)S.l_live[v][k] - sigma_v[v], w1 = w - 1.0;
+      q.C1 = (float)((double)c.vocab[v] * (double)c.count_beta + S.s2k[k]);
+      const bool rep = (__ffsll((long long)S.tmask[k]) - 1 == t);
+      const double w = (double)S.l_live[k] - sigma_l, w1 = w - 1.0;
       q.W = (rep && w > 0.0) ? (float)fin_log2(w) : kMasked;
       q.W1 = (rep && w1 > 0.0) ? (float)fin_log2(w1) : kMasked;
       q.dish = k;
-      q.lone = (S.l_live[v][k] == 1);
+      q.lone = (S.l_live[k] == 1);
     } else {
-      const double tau = tau_v[v], n = (double)S.n_vk[v][k];
+      const double tau = tau_l, n = (double)S.n_vk[k];
       const double a = (tau + n) / (2.0 * tau * (tau + n + 1.0));
       const double cc = -0.5 * fin_log(2.0 * kPi * tau * (tau + n + 1.0) / (tau + n));
       q.A = (float)(kLog2e * a);
@@ -1050,59 +1038,33 @@ __global__ void __launch_bounds__(kFinThreads, 1) k_finalize(const Ctx c, const 
       } else {
         q.A1 = 0.f; q.C1 = kMasked;
       }
-      const bool rep = (__ffsll((long long)S.tmask[v][k]) - 1 == t);      // lowest table of its dish
-      const double w = (double)S.l_live[v][k] - sigma_v[v], w1 = w - 1.0;
+      const bool rep = (__ffsll((long long)S.tmask[k]) - 1 == t);      // lowest table of its dish
+      const double w = (double)S.l_live[k] - sigma_l, w1 = w - 1.0;
       q.W = (rep && w > 0.0) ? (float)fin_log2(w) : kMasked;
       q.W1 = (rep && w1 > 0.0) ? (float)fin_log2(w1) : kMasked;
       q.dish = k;
-      q.lone = (S.l_live[v][k] == 1);
+      q.lone = (S.l_live[k] == 1);
     }
     c.tparam[i] = q;
-    c.tsame[i] = (k >= 0) ? S.tmask[v][k] : 0ull;
+    c.tsame[i] = (k >= 0) ? S.tmask[k] : 0ull;
   }
-  // The three small blocks below are independent of the loop above and of each other: each gets its own warps
-  // (12, 13-14, 15) so that their FP64 log chains run side by side instead of back to back on warp 0.
-  if (tid >= 12 * 32 && tid < 12 * 32 + V) {
-    const int v = tid - 12 * 32;
-    const double tau = tau_v[v];
+  if (tid == 12 * 32) {
+    const double tau = tau_l;
     int K_act = 0;
     long long sum_l = 0;
-    for (int k = 0; k < cap; ++k) if (S.l_live[v][k] > 0) { K_act++; sum_l += S.l_live[v][k]; }
+    for (int k = 0; k < cap; ++k) if (S.l_live[k] > 0) { K_act++; sum_l += S.l_live[k]; }
     ViewParam p;
     p.AN = (float)(kLog2e / (2.0 * tau));
-    p.CN = (float)(kLog2e * (-0.5 * (double)c.D[v] * fin_log(2.0 * kPi * tau)));
-    if (c.kind[v]) { p.AN = (float)fin_log2((double)c.vocab[v]); p.CN = 0.f; }      // log2 f_new = -|x| log2 W
-    const double wn0 = alpha_v[v] + (double)K_act * sigma_v[v], wn1 = alpha_v[v] + (double)(K_act - 1) * sigma_v[v];
+    p.CN = (float)(kLog2e * (-0.5 * (double)D * fin_log(2.0 * kPi * tau)));
+    if (is_count) { p.AN = (float)fin_log2((double)c.vocab[v]); p.CN = 0.f; }      // log2 f_new = -|x| log2 W
+    const double wn0 = alpha_l + (double)K_act * sigma_l, wn1 = alpha_l + (double)(K_act - 1) * sigma_l;
     p.WN0 = wn0 > 0.0 ? (float)fin_log2(wn0) : kMasked;
     p.WN1 = wn1 > 0.0 ? (float)fin_log2(wn1) : kMasked;
-    const double d0 = alpha_v[v] + (double)sum_l, d1 = alpha_v[v] + (double)(sum_l - 1);
+    const double d0 = alpha_l + (double)sum_l, d1 = alpha_l + (double)(sum_l - 1);
     p.LD0 = d0 > 0.0 ? (float)fin_log2(d0) : 0.f;
     p.LD1 = d1 > 0.0 ? (float)fin_log2(d1) : 0.f;
     p.pad0 = p.pad1 = 0.f;
     c.vparam[v] = p;
-  }
-  for (int t = tid - 13 * 32; t >= 0 && t < cap; t += kFinThreads) {
-    const double mass = (double)S.n_new[t] - sigma_g, mass1 = mass - 1.0;
-    TableMass tm;
-    tm.LM = (S.n_new[t] > 0 && mass > 0.0) ? (float)fin_log2(mass) : kMasked;
-    tm.LM1 = (S.n_new[t] > 1 && mass1 > 0.0) ? (float)fin_log2(mass1) : kMasked;
-    tm.single = (S.n_new[t] == 1);
-    tm.pad = 0;
-    c.tmass[t] = tm;
-  }
-  if (tid == 15 * 32) {
-    int T_ne = 0;
-    for (int t = 0; t < cap; ++t) T_ne += S.n_new[t] > 0;
-    const int F = cap - T_ne;
-    const double mn0 = alpha_g + sigma_g * (double)T_ne, mn1 = alpha_g + sigma_g * (double)(T_ne - 1);
-    GlobalParam g;
-    g.LMN0 = (F > 0 && mn0 > 0.0) ? (float)fin_log2(mn0) : kMasked;
-    g.LMN1 = (F > 0 && mn1 > 0.0) ? (float)fin_log2(mn1) : kMasked;
-    g.nfree = F;
-    const uint32_t next = sweep + ((flags & kFinAdvance) ? 1u : 0u);
-    g.sweep = next;
-    *c.gparam = g;
-    *c.sweep = next;
     if (S.err) atomicOr(c.status, S.err);
   }
   stamp(5);
@@ -1110,12 +1072,14 @@ __global__ void __launch_bounds__(kFinThreads, 1) k_finalize(const Ctx c, const 
 
 cudaError_t launch_finalize(const Ctx& c, int32_t flags, cudaStream_t s) {
   if (c.cap > kMaxCap || c.world > kMaxWorld || c.V > kMaxViews) return cudaErrorInvalidValue;
-  const size_t s1_bytes = sizeof(double) * (size_t)c.cap * c.Dsum;
+  int dmax = 0;
+  for (int v = 0; v < c.V; ++v) dmax = c.D[v] > dmax ? c.D[v] : dmax;
+  const size_t s1_bytes = sizeof(double) * (size_t)c.cap * dmax;
   const int s1_in_smem = (kFinSharedBytes + s1_bytes <= (size_t)227 * 1024) ? 1 : 0;
   const int smem = kFinSharedBytes + (s1_in_smem ? (int)s1_bytes : 0);
   cudaError_t e = cudaFuncSetAttribute(k_finalize, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
   if (e != cudaSuccess) return e;
-  k_finalize<<<1, kFinThreads, smem, s>>>(c, flags, s1_in_smem);
+  k_finalize<<<c.V + 1, kFinThreads, smem, s>>>(c, flags, s1_in_smem);
   return cudaGetLastError();
 }
 

@@ -94,12 +94,16 @@ def lib():
         L.mvg_sync.argtypes = [H]
         L.mvg_run.argtypes = [H, C.c_int32, C.c_int32, C.c_int32, C.c_int32, _i32p, _i32p, _f64p, _i32p]
         L.mvg_comm_attach.argtypes = [H, C.c_void_p]
+        L.mvg_comm_handle.restype = C.c_void_p
+        L.mvg_comm_handle.argtypes = [H]
         L.mvg_comm_unique_id.argtypes = [C.c_void_p]
         L.mvg_comm_init_rank.argtypes = [H, C.c_void_p]
         L.mvg_prepare.argtypes = [H]
         L.mvg_comm_p2p_export.argtypes = [H, C.c_void_p]
         L.mvg_comm_p2p_attach.argtypes = [H, C.c_void_p]
         L.mvg_comm_p2p_disable.argtypes = [H]
+        L.mvg_comm_p2p_enable.argtypes = [H]
+        L.mvg_clear_fault.argtypes = [H]
         L.mvg_get_params.argtypes = [H, C.POINTER(_ParamsHost)]
         L.mvg_get_debug_rows.argtypes = [H, _f32p, _f32p, _i32p]
         L.mvg_get_debug_births.argtypes = [H, _i32p, C.POINTER(C.c_int64), _f64p]
@@ -242,6 +246,12 @@ class Sampler:
         self._ck(self.L.mvg_comm_p2p_disable(self.h))
 
     # -- state ------------------------------------------------------------------------------
+    def p2p_enable(self):
+        self._ck(self.L.mvg_comm_p2p_enable(self.h))
+
+    def clear_fault(self):
+        self._ck(self.L.mvg_clear_fault(self.h))
+
     def init_state_reference(self):
         self._ck(self.L.mvg_init_state_reference(self.h))
 
@@ -344,6 +354,13 @@ class Sampler:
     def comm_init_rank(self, unique_id: bytes):
         buf = C.create_string_buffer(unique_id, 128)
         self._ck(self.L.mvg_comm_init_rank(self.h, buf))
+
+    def comm_handle(self):
+        """The NCCL communicator of this handle (an integer address) for comm_attach on another handle."""
+        return self.L.mvg_comm_handle(self.h)
+
+    def comm_attach(self, comm):
+        self._ck(self.L.mvg_comm_attach(self.h, C.c_void_p(comm)))
 
     # -- posterior summaries ------------------------------------------------------------------
     def log_likelihood(self):

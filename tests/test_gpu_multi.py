@@ -21,6 +21,6 @@ def test_two_gpu_row_sharded_chain_matches_one_gpu(transport):
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1",
            "--master-port", "29517" if transport == "nccl" else "29518", str(ROOT / "tests" / "mp_gpu_shard.py")]
     env = dict(os.environ, MVG_TEST_P2P="1" if transport == "p2p" else "0")
-    r = subprocess.run(cmd, capture_output=True, text=True, timeout=600, env=env)
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=240, env=env)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-4000:]
     assert "SHARD_OK" in r.stdout, r.stdout[-2000:]
