@@ -70,6 +70,12 @@ def parse():
                          "ncclAllGather (15 us at 2 GPUs, 39 us at 8); auto = p2p")
     ap.add_argument("--no-hyper", action="store_true")
     ap.add_argument("--role-profile", action="store_true", help="print the tcgen05 kernel's per-role wait cycles (debug)")
+    ap.add_argument("--stats", default="incremental", choices=["incremental", "rebuild"],
+                    help="how the sufficient statistics follow the assignments (include/mvg.h: mvg_set_stats_mode): incremental = only "
+                         "the rows that moved are re-read (running FP64 sums, a full rebuild every 64 sweeps) — the reference's own "
+                         "remove/add bookkeeping, batched; rebuild = every sweep re-reads all rows.  The other mode is measured beside "
+                         "the headline (`stats_rebuild` sub-record)")
+    ap.add_argument("--no-extra", action="store_true", help="skip the sub-records (rebuild mode, overlapping clusters)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-weak", action="store_true", help="N > 1: skip the weak-scaling sub-record")
     ap.add_argument("--no-free-slots", action="store_true", help="N = 1: skip the run with free table slots")
@@ -82,8 +88,8 @@ def parse():
 # ---------------------------------------------------------------------------------------------
 # synthetic workload: z ~ U{0..63}, mu_vk ~ N(0, 2^2 I), x = mu + N(0, I)
 # ---------------------------------------------------------------------------------------------
-def planted_means(rng):
-    return [rng.normal(0.0, 2.0, (CAP, d)).astype(np.float32) for d in DIMS]
+def planted_means(rng, spread=2.0):
+    return [rng.normal(0.0, spread, (CAP, d)).astype(np.float32) for d in DIMS]
 
 
 def make_rows_numpy(lo, hi, mus, seed=SEED, k_true=CAP):
@@ -451,11 +457,12 @@ def _main(args, out):
 
     class Workload:
         """One chain of n_total customers, this rank's shard resident on its GPU."""
-        def __init__(self, n_total, k_true):
+        def __init__(self, n_total, k_true, spread=None):
             self.n_total, self.k_true = n_total, k_true
             self.lo, self.hi = shard_of(n_total)
             self.n_local = self.hi - self.lo
-            views_np, z = make_rows_numpy(self.lo, self.hi, mus, k_true=k_true)
+            self.mus = mus if spread is None else planted_means(np.random.default_rng(SEED), spread)
+            views_np, z = make_rows_numpy(self.lo, self.hi, self.mus, k_true=k_true)
             self.tab, self.dish, self.hyp = initial_state(z, k_true)
             self.pinned = [torch.from_numpy(v).pin_memory() for v in views_np]
             self.dev = [v.cuda(non_blocking=True) for v in self.pinned]
@@ -467,7 +474,7 @@ def _main(args, out):
 
     comm_owner = []          # the first multi-GPU sampler owns the NCCL communicator; the others borrow it
 
-    def make_sampler(w, attach, debug_export=0, single=False):
+    def make_sampler(w, attach, debug_export=0, single=False, incremental=None):
         """single: a one-GPU chain over this rank's rows only (checks that need no peers)."""
         ww, rr = (1, 0) if single else (world, rank)
         s = mvc_b200.Sampler(w.n_local, DIMS, cap=CAP, seed=SEED, device=local_rank, engine=args.engine, rank=rr,
@@ -484,6 +491,8 @@ def _main(args, out):
         if attach:
             for v in range(len(DIMS)):
                 s.attach_view_device(v, w.dev[v])
+        if (args.stats == "incremental") if incremental is None else incremental:
+            s.set_stats_mode(True, 64)
         return s
 
     transport = {"used": "none" if world == 1 else "nccl"}
@@ -516,10 +525,10 @@ def _main(args, out):
         elif ok:
             s.p2p_disable()                                     # a peer could not map the buffers: everybody uses NCCL
 
-    def timed_run(w, steps, warmup, sample_clocks):
+    def timed_run(w, steps, warmup, sample_clocks, incremental=None):
         """W warm-up sweeps, then `steps` sweeps timed on the device (CUDA events on the library's stream, barrier and
         synchronize on both sides, max over ranks)."""
-        s = make_sampler(w, attach=True, debug_export=2 if args.role_profile else 0)
+        s = make_sampler(w, attach=True, debug_export=2 if args.role_profile else 0, incremental=incremental)
         enable_p2p(s)
         w.set_state(s)
         s.sweep(warmup, do_hyper)
@@ -568,6 +577,8 @@ def _main(args, out):
     if args.role_profile and rank == 0:
         pr = s.get_debug_prof(n_ctas=256)
         print("finalize stamps:", pr[200, :16].tolist(), file=sys.stderr)
+        print("epilogue phases of CTA 0 pair 0 (cycles; lower half | upper half): prologue, views, corr+max, rdv1, marg+weights, rdv2, "
+              "scan, rdv3, write, [acc wait]:", pr[230, :10].tolist(), "|", pr[231, :10].tolist(), file=sys.stderr)
         pr = pr[:148]
         names = ["tma.wait_raw_empty", "tma.total", "mma.wait_d_empty", "mma.wait_raw_full", "mma.wait_lo_full", "mma.total",
                  "conv0.wait_raw_full", "conv0.wait_lo_empty", "conv0.total", "conv1.wait_raw_full", "conv1.wait_lo_empty",
@@ -579,6 +590,39 @@ def _main(args, out):
     if not comm_owner or comm_owner[0] is not s:
         s.close()
 
+    # ---------------- e2e: one chain through the C ABI with HOST buffers ---------------------------------------------------
+    e2e = None
+    if not args.no_e2e:
+        k_e2e = max(args.steps, 200)
+        thin = max(1, k_e2e // 4)
+        s2 = make_sampler(W, attach=False)       # handle (+ borrowed communicator): set-up, not part of a chain's run
+        barrier()
+        t0 = time.perf_counter()
+        for v in range(len(DIMS)):
+            s2.upload_view(v, W.pinned[v].numpy())
+        if transport["used"] == "p2p":
+            enable_p2p(s2)
+        t_up = time.perf_counter()
+        W.set_state(s2)
+        t_st = time.perf_counter()
+        trace = s2.run(k_e2e, 0, thin)           # gibbs_sampler(M, burn_in, thin): D2H of table_of on every kept sweep
+        barrier()
+        dt = time.perf_counter() - t0
+        parts_s = {"upload": t_up - t0, "set_state": t_st - t_up, "run": t0 + dt - t_st}
+        tt = torch.tensor([dt], device="cuda")
+        if dist is not None:
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        dt = float(tt.item())
+        n_saved = int(trace["table_of"].shape[0])
+        h2d = W.n_local * (sum(DIMS) * 4 + 4)
+        d2h = W.n_local * 4 * n_saved
+        e2e = {"value": updates * k_e2e / dt, "unit": UNIT, "h2d_bytes_per_step": h2d / k_e2e,
+               "d2h_bytes_per_step": d2h / k_e2e, "sweeps": k_e2e, "saved_states": n_saved, "seconds": dt, "seconds_by_part": parts_s,
+               "note": "one chain through the C ABI (mvg_upload_view_f32 from pinned host memory, mvg_set_state, mvg_run = "
+                       "gibbs_sampler(M, burn_in=0, thin) with the D2H of table_of on every kept sweep); wall clock, device "
+                       "allocation included; bytes are per sweep (total / M)"}
+        assert int(np.bincount(trace["table_of"][-1], minlength=CAP).sum()) == W.n_local
+        s2.close()
     # ---------------- the same kernel with free table slots (the new-table marginal is evaluated): one GPU only ---------
     roofline_free = None
     if world == 1 and not args.no_free_slots and args.k_true == CAP:
@@ -588,6 +632,30 @@ def _main(args, out):
         roofline_free["ms_per_step"] = Rf["dev_ms"] / min(args.steps, 200)
         Rf["s"].close()
         del Wf, Rf
+
+    # ---------------- the other statistics mode, and a data set whose rows keep moving (overlapping clusters) ----------
+    stats_other, moving = None, None
+    if not args.no_extra:
+        ks = min(args.steps, 200)
+        other = args.stats != "incremental"
+        Ro = timed_run(W, ks, min(args.warmup, 5), sample_clocks=False, incremental=other)
+        stats_other = {"stats": "incremental" if other else "rebuild", "steps": ks, "ms_per_step": Ro["dev_ms"] / ks,
+                       "value": updates * ks / (Ro["dev_ms"] * 1e-3), "unit": UNIT, "kernel_ms": Ro["kern"]}
+        if not comm_owner or comm_owner[0] is not Ro["s"]:
+            Ro["s"].close()
+        del Ro
+        if world == 1:
+            Wm = Workload(n_total, args.k_true, spread=0.35)     # cluster centres ~4 sigma apart: a few per cent of the rows move every sweep
+            Rm = timed_run(Wm, ks, 20, sample_clocks=False)
+            t_a = Rm["s"].get_state()["table_of"]
+            Rm["s"].sweep(1, do_hyper)
+            t_b = Rm["s"].get_state()["table_of"]
+            moving = {"workload": "same shape, planted means N(0, 0.35^2 I): overlapping clusters", "stats": args.stats, "steps": ks,
+                      "ms_per_step": Rm["dev_ms"] / ks, "value": updates * ks / (Rm["dev_ms"] * 1e-3), "unit": UNIT,
+                      "kernel_ms": Rm["kern"], "rows_moved_in_one_sweep": int((t_a != t_b).sum()),
+                      "tables_live": int((Rm["s"].get_state(with_rows=False)["n_t"] > 0).sum())}
+            Rm["s"].close()
+            del Wm, Rm
 
     # ---------------- weak scaling beside it (N > 1): one C3-sized shard per GPU ---------------------------------------
     weak = None
@@ -645,39 +713,6 @@ def _main(args, out):
     if rank == 0 and not args.no_checks:
         state_check.update(spot_check_draws(mvc_b200, W, local_rank, args.engine))
 
-    # ---------------- e2e: one chain through the C ABI with HOST buffers ---------------------------------------------------
-    e2e = None
-    if not args.no_e2e:
-        k_e2e = max(args.steps, 200)
-        thin = max(1, k_e2e // 4)
-        s2 = make_sampler(W, attach=False)       # handle (+ borrowed communicator): set-up, not part of a chain's run
-        barrier()
-        t0 = time.perf_counter()
-        for v in range(len(DIMS)):
-            s2.upload_view(v, W.pinned[v].numpy())
-        if transport["used"] == "p2p":
-            enable_p2p(s2)
-        t_up = time.perf_counter()
-        W.set_state(s2)
-        t_st = time.perf_counter()
-        trace = s2.run(k_e2e, 0, thin)           # gibbs_sampler(M, burn_in, thin): D2H of table_of on every kept sweep
-        barrier()
-        dt = time.perf_counter() - t0
-        parts_s = {"upload": t_up - t0, "set_state": t_st - t_up, "run": t0 + dt - t_st}
-        tt = torch.tensor([dt], device="cuda")
-        if dist is not None:
-            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-        dt = float(tt.item())
-        n_saved = int(trace["table_of"].shape[0])
-        h2d = W.n_local * (sum(DIMS) * 4 + 4)
-        d2h = W.n_local * 4 * n_saved
-        e2e = {"value": updates * k_e2e / dt, "unit": UNIT, "h2d_bytes_per_step": h2d / k_e2e,
-               "d2h_bytes_per_step": d2h / k_e2e, "sweeps": k_e2e, "saved_states": n_saved, "seconds": dt, "seconds_by_part": parts_s,
-               "note": "one chain through the C ABI (mvg_upload_view_f32 from pinned host memory, mvg_set_state, mvg_run = "
-                       "gibbs_sampler(M, burn_in=0, thin) with the D2H of table_of on every kept sweep); wall clock, device "
-                       "allocation included; bytes are per sweep (total / M)"}
-        assert int(np.bincount(trace["table_of"][-1], minlength=CAP).sum()) == W.n_local
-        s2.close()
     for s_ in comm_owner:
         s_.close()
 
@@ -696,10 +731,12 @@ def _main(args, out):
                 "config": {"workload": "C3: synthetic 3-view Gaussian mixture, N=%d (%d per GPU), D=64/view, K(cap)=64, row-sharded, "
                                        "one exchange of the per-table statistics per sweep" % (n_total, W.n_local),
                            "rows_per_gpu": W.n_local, "hyper_step": do_hyper, "engine": args.engine, "planted_clusters": args.k_true,
-                           "l2": "inputs (768 MB per sweep at N=1M) larger than L2; no flush", "exchange": transport["used"]},
+                           "l2": "inputs (768 MB per sweep at N=1M) larger than L2; no flush", "exchange": transport["used"],
+                           "statistics": args.stats + (" (moved rows only, full rebuild every 64 sweeps)" if args.stats == "incremental" else " (all rows every sweep)")},
                 "sweeps_per_s": args.steps / (R["dev_ms"] * 1e-3), "wall_ms_per_step": R["wall_ms"] / args.steps,
                 "clocks": R["clocks"], "gpu_launches": int(R["launches"]),
-                "roofline": roofline, "roofline_free_slots": roofline_free, "weak": weak, "e2e": e2e, "cpu_baseline": cpu,
+                "roofline": roofline, "roofline_free_slots": roofline_free, "stats_rebuild" if args.stats == "incremental" else "stats_incremental": stats_other,
+                "moving_rows": moving, "weak": weak, "e2e": e2e, "cpu_baseline": cpu,
                 "state_check": state_check}
         print(json.dumps(line), file=out)
     if dist is not None:
@@ -721,6 +758,7 @@ def spot_check_draws(mvc_b200, W, device, engine):
     P = s.get_params()
     s.sweep(1, True)
     acc, xx, raw = s.get_debug_rows()
+    lnew = s.get_debug_lnew()
     s.close()
     n_tiles = (n + 127) // 128
     grid = min(148, n_tiles)
@@ -733,13 +771,13 @@ def spot_check_draws(mvc_b200, W, device, engine):
     bad = 0
     for i in rows:
         u = L.mvo_uf(SEED, 0, 0, 0, pre["sweep"], int(i))
-        bad += int(po.stageB_f32(ps, acc[i], xx[i], pre["table_of"][i], u) != raw[i])
+        bad += int(po.stageB_tc(ps, acc[i], xx[i], pre["table_of"][i], u, lnew[i]) != raw[i])
     # dot products against FP64 on a subset (tolerance: 2^-18 of sum |x||m|)
     sub = rows[:: max(1, len(rows) // 4096)]
     worst = 0.0
     for v in range(len(DIMS)):
         x = W.pinned[v].numpy()[sub].astype(np.float64)
-        m = P["m"][v].astype(np.float64)
+        m = po.scaled_means(P["A"][v], P["m"][v]).astype(np.float64)      # the engine's B operand: b = float32(2 A m)
         ref = x @ m.T
         bound = np.abs(x) @ np.abs(m).T
         worst = max(worst, float(np.max(np.abs(acc[sub, v, :] - ref) / bound)))

@@ -138,6 +138,25 @@ int mvg_get_state(mvg_handle* h, const mvg_state_host* out);
 /* n_sweeps synchronous allocation sweeps, each followed by the hyper step when do_hyper != 0.
  * Asynchronous on the handle's stream; any mvg_get_* / mvg_sync observes the result. */
 int mvg_sweep(mvg_handle* h, int32_t n_sweeps, int32_t do_hyper);
+/* How the sufficient statistics follow the assignments.
+ *   MVG_STATS_REBUILD (default)  every sweep re-reads all rows: a segmented reduction in a fixed order
+ *                                (multiview_gibbs.cpp:64-73 for all rows), bit-reproducible from the assignments alone.
+ *   MVG_STATS_INCREMENTAL        what the reference does per customer (remove_customer / add_customer_to_*,
+ *                                multiview_utils.cpp:151-163, 199-206), batched per sweep: only the rows whose table
+ *                                changed are re-read, added to their new table and subtracted from their old one, in a
+ *                                fixed order, into running FP64 sums; every `rebuild_every`-th sweep is a full rebuild,
+ *                                which bounds the rounding drift (counts are integers and exact either way).  The
+ *                                sweep then streams the features ONCE instead of twice.  Available where the tile
+ *                                statistics kernel is (cap 64, up to three dense views of dim 64); elsewhere it falls
+ *                                back to rebuilding. */
+enum { MVG_STATS_REBUILD = 0, MVG_STATS_INCREMENTAL = 1 };
+int mvg_set_stats_mode(mvg_handle* h, int32_t mode, int32_t rebuild_every);
+/* Blocked sweeps: one sweep becomes `blocks` passes; pass b redraws the customers with (global row) % blocks == b
+ * against statistics that already hold the moves of passes 0..b-1 (statistics rebuild and birth/death bookkeeping after
+ * every pass, the hyper step after the last).  blocks = 1 (default) is the synchronous sweep; blocks = N is the
+ * reference's sequential order (multiview_gibbs.cpp:157-200) — the knob trades throughput for closeness to it.
+ * The Philox addressing (sweep, row) is unchanged, so chains stay reproducible and shard-invariant. */
+int mvg_set_sweep_blocks(mvg_handle* h, int32_t blocks);
 int mvg_hyper_step(mvg_handle* h);
 /* The same restricted to some of its Metropolis-Hastings updates: update_tau_v_MH alone
  * (multiview_hyper.cpp:211-231), the per-view alpha/sigma pairs (:242-265), the franchise pair (:268-291). */
@@ -196,6 +215,10 @@ int mvg_get_params(mvg_handle* h, const mvg_params_host* out);
 /* With debug_export: per-row stage-A outputs of the LAST sweep: acc [n_rows][V][cap] dot products
  * x.m and xx [n_rows][V] squared norms, plus the raw draw (before births are seated) [n_rows]. */
 int mvg_get_debug_rows(mvg_handle* h, float* acc, float* xx, int32_t* choice);
+/* Tensor-core engines, with debug_export: acc above holds the dot products with the PRE-SCALED means b = 2 A m (the data
+ * term of log2 f), and lnew [n_rows] the log2 weight of a new table as the kernel evaluated it (MUFU log-sum-exp: a float
+ * statistic inside the stated tolerance; the CPU mirror checks it and draws from it). */
+int mvg_get_debug_lnew(mvg_handle* h, float* lnew);
 /* Count view v: the tables of the NEXT sweep, host [vocab][cap] each (NULL skips): log2 theta of the dish each
  * table slot serves, that dish's word counts, and the word counts per table slot. */
 int mvg_get_count_tables(mvg_handle* h, int32_t v, float* log2_theta, int32_t* dish_counts, int32_t* table_counts);

@@ -83,8 +83,13 @@ struct mvg_handle {
   int32_t cocl_samples = 0;
   // One sweep captured as a CUDA graph (world = 1): [0] without, [1] with the hyper step.  A replay costs the host
   // one launch instead of 5-8, which is what bounds several small chains sharing a GPU.
-  cudaGraphExec_t sweep_graph[2]{};
-  int64_t sweep_graph_launches[2]{};
+  cudaGraphExec_t sweep_graph[4]{};   // [hyper step on/off] + 2 * [incremental statistics]
+  int64_t sweep_graph_launches[4]{};
+  // statistics mode (mvg_set_stats_mode): 0 = full rebuild every sweep; 1 = incremental (moved rows only) with a full
+  // rebuild every `rebuild_every` sweeps
+  int stats_mode = 0;
+  int rebuild_every = 64;
+  int since_full = 0;                // incremental sweeps since the last full rebuild
   bool graphs_ok = true;
   int64_t sweeps_issued = 0;
   // peer-memory exchange (optional; ncclAllGather otherwise)
@@ -145,7 +150,7 @@ int ensure_layout(mvg_handle* h) {
   const size_t N = (size_t)c.n_rows, cap = (size_t)c.cap, V = (size_t)c.V;
   int rc;
 #define A(ptr, count) if ((rc = dev_alloc(h, &(ptr), (count))) != MVG_OK) return rc
-  A(c.table_cur, N); A(c.choice, N + 4 /* bulk copies read whole 16-byte groups */); A(c.birthmask, (size_t)c.n_chunks); A(c.chunk_prefix, (size_t)c.n_chunks);
+  A(c.table_cur, N + 4 /* bulk copies read whole 16-byte groups */); A(c.choice, N + 4); A(c.birthmask, (size_t)c.n_chunks); A(c.movedmask, (size_t)c.n_chunks + 2); A(c.chunk_prefix, (size_t)c.n_chunks);
   A(c.n_t, cap); A(c.dish_of, V * cap); A(c.n_vk, V * cap); A(c.l_vk, V * cap);
   A(c.S1t, cap * dsum); A(c.S2t, V * cap); A(c.S1k, cap * dsum); A(c.S2k, V * cap);
   A(c.hyp, 3 * V + 2); A(c.sweep, 1); A(c.status, 4);
@@ -167,7 +172,7 @@ int ensure_layout(mvg_handle* h) {
   p.off_cand_x = off; off += align16(4 * c.cap * dsum);
   p.bytes = off;
   A(c.packet, (size_t)c.world * p.bytes);
-  if (c.debug_export & 1) { A(c.dbg_acc, N * V * cap); A(c.dbg_xx, N * V); A(c.dbg_choice, N); A(c.dbg_loo, N * V); }
+  if (c.debug_export & 1) { A(c.dbg_acc, N * V * cap); A(c.dbg_xx, N * V); A(c.dbg_choice, N); A(c.dbg_loo, N * V); A(c.dbg_lnew, N); }
   for (int v = 0; v < c.V; ++v)
     if (c.kind[v]) {
       const size_t cells = (size_t)c.vocab[v] * cap;
@@ -194,31 +199,31 @@ int ensure_layout(mvg_handle* h) {
 
 // This shard's statistics -> totals over all shards (csrc/mv_exchange.cu).  One launch with the peer-memory
 // transport or on one GPU; reduce, ncclAllGather, rank-ordered sums with the NCCL transport.
-int reduce_exchange(mvg_handle* h, cudaEvent_t* marks) {
+int reduce_exchange(mvg_handle* h, cudaEvent_t* marks, bool delta) {
   const Ctx& c = h->c;
   if (c.world == 1 || h->xp2p) {
-    MVG_CUDA(h, launch_reduce_x(c, c.world == 1 ? 0 : 1, h->xpeers, h->xrecv, h->stream));
+    MVG_CUDA(h, launch_reduce_x(c, c.world == 1 ? 0 : 1, delta, h->xpeers, h->xrecv, h->stream));
     h->launches += 1;
     if (marks) { MVG_CUDA(h, cudaEventRecord(marks[1], h->stream)); MVG_CUDA(h, cudaEventRecord(marks[2], h->stream)); }
     return MVG_OK;
   }
   if (!h->comm) return fail(h, MVG_ESTATE, "world > 1 but neither an NCCL communicator nor peer buffers are attached");
-  MVG_CUDA(h, launch_reduce_x(c, 0, h->xpeers, h->xrecv, h->stream));
+  MVG_CUDA(h, launch_reduce_x(c, 0, delta, h->xpeers, h->xrecv, h->stream));
   if (marks) MVG_CUDA(h, cudaEventRecord(marks[1], h->stream));
   unsigned char* base = c.packet;
   int r = g_nccl.AllGather(base + (size_t)c.rank * c.pkt.bytes, base, (size_t)c.pkt.bytes, /*ncclChar*/ 0, h->comm, h->stream);
   if (r != 0) return fail(h, MVG_ENCCL, std::string("ncclAllGather: ") + (g_nccl.GetErrorString ? g_nccl.GetErrorString(r) : "?"));
-  MVG_CUDA(h, launch_reduce_x(c, 2, h->xpeers, h->xrecv, h->stream));
+  MVG_CUDA(h, launch_reduce_x(c, 2, false, h->xpeers, h->xrecv, h->stream));
   if (marks) MVG_CUDA(h, cudaEventRecord(marks[2], h->stream));
   h->launches += 2;
   return MVG_OK;
 }
 
 // stats -> reduce + exchange -> finalize: shared by sweeps, set_state and init
-int rebuild_pipeline(mvg_handle* h, int32_t flags, cudaEvent_t* marks /* 4 events or null */) {
-  MVG_CUDA(h, launch_stats(h->c, h->stream));
+int rebuild_pipeline(mvg_handle* h, int32_t flags, cudaEvent_t* marks /* 4 events or null */, bool delta = false) {
+  MVG_CUDA(h, launch_stats(h->c, delta, h->stream));
   if (marks) MVG_CUDA(h, cudaEventRecord(marks[0], h->stream));
-  int rc = reduce_exchange(h, marks);
+  int rc = reduce_exchange(h, marks, delta);
   if (rc != MVG_OK) return rc;
   MVG_CUDA(h, launch_finalize(h->c, flags, h->stream));
   if (h->c.n_count_views) {          // count views: word counts by the final seating, then the log2 theta tables
@@ -303,6 +308,8 @@ int mvg_create(const mvg_config* cfg, mvg_handle** out) {
   c.n_chunks = (c.n_rows + 31) / 32;
   c.stat_ctas = c.n_chunks < h->sms ? c.n_chunks : h->sms;
   c.debug_export = cfg->debug_export;
+  c.blk_count = 1;
+  c.blk_index = 0;
   c.count_beta = 0.5f;
   {
     void* q = nullptr;
@@ -578,19 +585,36 @@ int mvg_get_state(mvg_handle* h, const mvg_state_host* o) {
 }
 
 namespace {
-int one_sweep(mvg_handle* h, int32_t flags) {
-  int rc = launch_draw(h);
-  if (rc != MVG_OK) return rc;
-  MVG_CUDA(h, launch_pack(h->c, h->stream));
-  h->launches += 1;
-  return rebuild_pipeline(h, flags, nullptr);
+// Is the next sweep an incremental one?  (Advances the rebuild schedule.)
+bool next_sweep_is_delta(mvg_handle* h) {
+  if (h->stats_mode != 1 || h->c.blk_count > 1 || !stats_delta_supported(h->c)) { h->since_full = 0; return false; }
+  if (h->since_full + 1 >= h->rebuild_every) { h->since_full = 0; return false; }
+  h->since_full += 1;
+  return true;
+}
+
+int one_sweep(mvg_handle* h, int32_t flags, bool delta) {
+  // A blocked sweep (mvg_set_sweep_blocks) is B passes: pass b redraws the rows of block b against statistics that
+  // already contain the moves of blocks 0..b-1; the hyper step and the sweep counter belong to the last pass.
+  const int B = h->c.blk_count;
+  for (int b = 0; b < B; ++b) {
+    h->c.blk_index = b;
+    int rc = launch_draw(h);
+    if (rc != MVG_OK) return rc;
+    MVG_CUDA(h, launch_pack(h->c, h->stream));
+    h->launches += 1;
+    rc = rebuild_pipeline(h, (b == B - 1) ? flags : kFinReseat, nullptr, delta && B == 1);
+    if (rc != MVG_OK) return rc;
+  }
+  h->c.blk_index = 0;
+  return MVG_OK;
 }
 
 // Capture one sweep into an executable graph (once per handle and hyper-step variant).  Returns false, leaving the
 // stream usable, if anything about the capture fails: the caller then launches the kernels directly.
-bool ensure_sweep_graph(mvg_handle* h, int which, int32_t flags) {
+bool ensure_sweep_graph(mvg_handle* h, int which, int32_t flags, bool delta) {
   if (h->sweep_graph[which]) return true;
-  if (!h->graphs_ok || (h->c.debug_export & 2)) return false;
+  if (!h->graphs_ok || (h->c.debug_export & 2) || h->c.blk_count > 1) return false;
   // NCCL transport: launched directly (a collective captured into the sweep graph did not complete on this stack);
   // the peer-memory transport is an ordinary kernel and is captured with the rest of the sweep
   if (h->c.world != 1 && !h->xp2p) return false;
@@ -598,7 +622,7 @@ bool ensure_sweep_graph(mvg_handle* h, int which, int32_t flags) {
   if (disabled) { h->graphs_ok = false; return false; }
   const int64_t before = h->launches;
   if (cudaStreamBeginCapture(h->stream, cudaStreamCaptureModeThreadLocal) != cudaSuccess) { cudaGetLastError(); h->graphs_ok = false; return false; }
-  const int rc = one_sweep(h, flags);
+  const int rc = one_sweep(h, flags, delta);
   cudaGraph_t g = nullptr;
   const cudaError_t e = cudaStreamEndCapture(h->stream, &g);
   h->sweep_graph_launches[which] = h->launches - before;
@@ -621,20 +645,40 @@ int mvg_sweep(mvg_handle* h, int32_t n_sweeps, int32_t do_hyper) {
     return fail(h, MVG_ENCCL, "exchange fault (sticky): a peer's statistics did not arrive; no further sweeps on this handle");
   MVG_CUDA(h, cudaSetDevice(h->cfg.device));
   const int32_t flags = kFinReseat | kFinAdvance | (do_hyper ? kFinHyperAll : 0);
-  const int which = do_hyper ? 1 : 0;
-  const bool use_graph = (n_sweeps >= 2 || h->sweeps_issued >= 1) && n_sweeps >= 1 && ensure_sweep_graph(h, which, flags);
-  h->sweeps_issued += n_sweeps;
   MVG_CUDA(h, cudaEventRecord(h->ev[0], h->stream));
   for (int it = 0; it < n_sweeps; ++it) {
+    const bool delta = next_sweep_is_delta(h);
+    const int which = (do_hyper ? 1 : 0) + (delta ? 2 : 0);
+    const bool use_graph = (n_sweeps >= 2 || h->sweeps_issued >= 1) && ensure_sweep_graph(h, which, flags, delta);
     if (use_graph) {
       MVG_CUDA(h, cudaGraphLaunch(h->sweep_graph[which], h->stream));
       h->launches += h->sweep_graph_launches[which];
     } else {
-      const int rc = one_sweep(h, flags);
+      const int rc = one_sweep(h, flags, delta);
       if (rc != MVG_OK) return rc;
     }
   }
+  h->sweeps_issued += n_sweeps;
   MVG_CUDA(h, cudaEventRecord(h->ev[1], h->stream));
+  return MVG_OK;
+}
+
+int mvg_set_stats_mode(mvg_handle* h, int32_t mode, int32_t rebuild_every) {
+  if (!h) return MVG_EINVAL;
+  if (mode != MVG_STATS_REBUILD && mode != MVG_STATS_INCREMENTAL) return fail(h, MVG_EINVAL, "unknown statistics mode");
+  if (mode == MVG_STATS_INCREMENTAL && rebuild_every < 1) return fail(h, MVG_EINVAL, "rebuild_every must be >= 1");
+  h->stats_mode = mode;
+  h->rebuild_every = (mode == MVG_STATS_INCREMENTAL) ? rebuild_every : 1;
+  h->since_full = 0x3fffffff;        // the next sweep rebuilds
+  return MVG_OK;
+}
+
+int mvg_set_sweep_blocks(mvg_handle* h, int32_t blocks) {
+  if (!h) return MVG_EINVAL;
+  if (blocks < 1 || blocks > (1 << 20)) return fail(h, MVG_EINVAL, "blocks must be in [1, 2^20]");
+  h->c.blk_count = blocks;
+  h->c.blk_index = 0;
+  invalidate_graphs(h);
   return MVG_OK;
 }
 
@@ -859,6 +903,15 @@ int mvg_get_debug_rows(mvg_handle* h, float* acc, float* xx, int32_t* choice) {
   return MVG_OK;
 }
 
+int mvg_get_debug_lnew(mvg_handle* h, float* lnew) {
+  if (!h || !lnew) return MVG_EINVAL;
+  if (!(h->c.debug_export & 1) || !h->c.dbg_lnew) return fail(h, MVG_ESTATE, "handle was not created with debug_export");
+  MVG_CUDA(h, cudaSetDevice(h->cfg.device));
+  MVG_CUDA(h, cudaMemcpyAsync(lnew, h->c.dbg_lnew, sizeof(float) * (size_t)h->c.n_rows, cudaMemcpyDeviceToHost, h->stream));
+  MVG_CUDA(h, cudaStreamSynchronize(h->stream));
+  return MVG_OK;
+}
+
 int mvg_get_debug_births(mvg_handle* h, int32_t* n_seated, int64_t* rows, double* w) {
   if (!h) return MVG_EINVAL;
   const Ctx& c = h->c;
@@ -904,7 +957,7 @@ int mvg_profile_sweep(mvg_handle* h, int32_t do_hyper, float ms_out[6]) {
   MVG_CUDA(h, cudaEventRecord(h->ev[4], h->stream));
   cudaEvent_t marks[4];
   for (auto& m : marks) MVG_CUDA(h, cudaEventCreate(&m));
-  rc = rebuild_pipeline(h, flags, marks);
+  rc = rebuild_pipeline(h, flags, marks, next_sweep_is_delta(h));
   if (rc == MVG_OK) {
     MVG_CUDA(h, cudaStreamSynchronize(h->stream));
     cudaEventElapsedTime(&ms_out[0], h->ev[2], h->ev[3]);

@@ -45,6 +45,7 @@ struct Ctx {
   int32_t n_chunks;         // ceil(n_rows/32)
   int32_t stat_ctas;        // CTAs of the statistics kernel (fixes the summation tree)
   int32_t debug_export;
+  int32_t blk_count, blk_index;   // blocked sweep: only rows with (global row) % blk_count == blk_index are redrawn by this pass
   int32_t D[kMaxViews];
   int32_t doff[kMaxViews];
   const float* x[kMaxViews];
@@ -68,6 +69,7 @@ struct Ctx {
   int32_t* table_cur;
   int32_t* choice;
   uint32_t* birthmask;
+  uint32_t* movedmask;      // [ceil(N/32)] bit r of word c: the draw of row 32c+r differs from its table (incl. new-table draws)
   int32_t* chunk_prefix;
 
   int32_t* n_t;
@@ -109,6 +111,7 @@ struct Ctx {
   float* dbg_acc;           // [N][V][cap]
   float* dbg_xx;            // [N][V]
   int32_t* dbg_choice;      // [N]
+  float* dbg_lnew;          // [N] tensor-core engine: log2 weight of a new table as the kernel evaluated it
   float* dbg_loo;           // [N][V] count views: the leave-one-out log2 f of the row under its own dish
   int64_t* dbg_birth_rows;  // [cap]
   double* dbg_birth_w;      // [cap][V][cap+1]
@@ -140,10 +143,13 @@ bool draw_tc_supported(const Ctx& c);
 size_t draw_tc_maps_bytes();                                   // host blob holding the TMA tensor maps
 cudaError_t draw_tc_make_maps(const Ctx& c, void* maps_out);  // (re)encode them for the current pointers
 cudaError_t launch_pack(const Ctx& c, cudaStream_t s);
-cudaError_t launch_stats(const Ctx& c, cudaStream_t s);
+// delta: only the rows that moved this sweep are visited; the per-CTA partials then hold the CHANGE of the statistics
+// (rows that arrived minus rows that left) and k_reduce_x adds it to the shard's running sums (mode flag there).
+cudaError_t launch_stats(const Ctx& c, bool delta, cudaStream_t s);
 bool stats_tile_supported(const Ctx& c);
-cudaError_t launch_stats_tile(const Ctx& c, cudaStream_t s);
-cudaError_t launch_reduce_x(const Ctx& c, int mode, const XchgPeers& peers, unsigned char* recv_local, cudaStream_t s);
+bool stats_delta_supported(const Ctx& c);
+cudaError_t launch_stats_tile(const Ctx& c, bool delta, cudaStream_t s);
+cudaError_t launch_reduce_x(const Ctx& c, int mode, bool delta, const XchgPeers& peers, unsigned char* recv_local, cudaStream_t s);
 cudaError_t launch_finalize(const Ctx& c, int32_t flags, cudaStream_t s);
 cudaError_t launch_init_tables(const Ctx& c, int32_t mode, cudaStream_t s);
 cudaError_t launch_rownorms(const float* x, float* xx, int n, int D, cudaStream_t s);

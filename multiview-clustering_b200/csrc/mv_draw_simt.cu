@@ -137,12 +137,14 @@ __global__ void __launch_bounds__(kSimtThreads, 2) k_draw_simt(const Ctx c) {
 
     const U4 rnd = stream_block(c.seed, c.chain, kDomTable, 0, sweep, (uint64_t)(c.row_offset + rowc));
     int choice = epi.finish(uniform_f32_from(rnd.x));
+    if (c.blk_count > 1 && (int)((c.row_offset + rowc) % c.blk_count) != c.blk_index) choice = epi.ha.t0;   // not this pass's block
     if (live) {
       c.choice[row] = choice;
       if (c.debug_export & 1) c.dbg_choice[row] = choice;
     }
     const unsigned births = __ballot_sync(0xffffffffu, live && choice == kNewTable);
-    if ((tid & 31) == 0 && (row >> 5) < c.n_chunks) c.birthmask[row >> 5] = births;
+    const unsigned moved = __ballot_sync(0xffffffffu, live && choice != epi.ha.t0);
+    if ((tid & 31) == 0 && (row >> 5) < c.n_chunks) { c.birthmask[row >> 5] = births; c.movedmask[row >> 5] = moved; }
   }
 }
 

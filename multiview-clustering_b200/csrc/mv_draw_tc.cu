@@ -17,12 +17,20 @@
 //                              restores ~2^-19 relative accuracy (north_star: FP32 tolerance).
 //   epilogue (4 x 128 threads) two PAIRS of warpgroups take alternate row tiles; inside a pair each
 //                              warpgroup owns one half of the 64 tables.  tcgen05.ld: thread r of either
-//                              warpgroup reads TMEM lane r = customer r, 16 dot products at a time, and
-//                              feeds HalfEpilogue (mv_device.cuh): leave-one-out weights and a streaming
-//                              log-sum-exp over its half.  The two threads of a customer trade nine
-//                              scalars through shared memory (three named-barrier rendezvous per tile)
-//                              to merge marginals, totals and the inverse-CDF counts.  Twice the warps
-//                              at half the registers each: the epilogue is latency-bound, not issue-bound.
+//                              warpgroup reads TMEM lane r = customer r, 16 dot products at a time.
+//                              The B operand is the means PRE-SCALED by the table's slope (b = 2 A m, written by
+//                              k_finalize), so a dot product is the data term of log2 f and the per-(customer, view,
+//                              table) work is ONE packed add:
+//                                  lw[t] = base[t] + sum_v A_vt (-|x_v|^2) + sum_v x_v.b_vt
+//                              (base = log2 table mass + sum_v C_vt, staged per sweep).  The customer's own dish is
+//                              scored with the customer removed (multiview_utils.cpp:138-192): that is a per-customer
+//                              SCALAR correction delta_v = loo_v - plain_v from the dot product at its own table,
+//                              added to the tables that serve the dish (usually its own table only).  With a free
+//                              table slot the per-view marginal of a new table is a log-sum-exp over the dishes
+//                              (MUFU ex2/lg2: a float statistic inside the stated tolerance, exported for the mirror);
+//                              the categorical weights and the inverse-CDF scan stay bit-reproducible.  The two
+//                              threads of a customer trade a few scalars through shared memory (three named-barrier
+//                              rendezvous per tile) to merge marginals, totals and the inverse-CDF counts.
 //
 // TMEM (512 columns): [0,384) six accumulator tiles, [384,512) two remainder tiles.
 // The [N x 64] log-likelihood matrices never exist in memory: HBM traffic is the features once
@@ -50,7 +58,7 @@ constexpr int kLoCol0 = kDStages * 64;              // first TMEM column of the 
 constexpr int kMaxTcViews = 3;
 constexpr int kThreads = 896;                       // WG0: control, WG1+WG2: converters (one per K-half), WG3..WG6: epilogue
 constexpr int kMmaWarps = 2;                        // MMA-issuing warps of WG0; tile-view i belongs to warp 1 + i % 2
-constexpr int kExFields = 9;                        // scalars two epilogue threads of one customer trade per tile
+constexpr int kExFields = 15;                       // scalars two epilogue threads of one customer trade per tile
 constexpr int kEpiGroups = 2;
 
 struct __align__(64) TcMaps {
@@ -64,10 +72,11 @@ struct SmemLayout {
   static constexpr int b_off = 0;                                            // [V][hi,lo][2 halves][8 KB]
   static constexpr int raw_off = b_off + kMaxTcViews * 4 * kBHalfBytes;      // 96 KB
   static constexpr int tp_off = raw_off + kRawStages * kHalfBytes;           // +112 KB
-  static constexpr int tm_off = tp_off + kMaxTcViews * 64 * (int)sizeof(TableParam);   // per view: PairHot[32] then TableCold[64]
+  static constexpr int tm_off = tp_off + kMaxTcViews * 64 * (int)sizeof(TableParam);   // per view: TcViewParams (2 KB)
   static constexpr int vp_off = tm_off + 64 * (int)sizeof(TableMass);
-  static constexpr int lm_off = vp_off + kMaxTcViews * (int)sizeof(ViewParam);              // float[64]: LM of every table
-  static constexpr int same_off = lm_off + 64 * (int)sizeof(float);                         // u64[V][64]: same-dish table masks
+  static constexpr int lm_off = vp_off + kMaxTcViews * (int)sizeof(ViewParam);              // float[64]: base = LM + sum_v C_v of every table
+  static constexpr int dlm_off = lm_off + 64 * (int)sizeof(float);                          // float[64]: LM1 - LM
+  static constexpr int same_off = dlm_off + 64 * (int)sizeof(float);                        // u64[V][64]: same-dish table masks
   static constexpr int ex_off = same_off + kMaxTcViews * 64 * 8;
   static constexpr int bar_off = ex_off + 4 * kExFields * kTileRows * (int)sizeof(float);   // ex: [pair][half][field][row]
   static constexpr int n_bars = 2 * kRawStages + 2 * kLoStages + 2 * kDStages + 1;
@@ -222,23 +231,88 @@ __device__ __forceinline__ void tmem_ld_16(uint32_t taddr, uint32_t (&u)[16]) {
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
-// One 16-table chunk of one view (its dot products already sit in `cur`): export them when asked, then
-// run the half-epilogue on them.
-template <int BASE, bool WITH_NEW, bool FAST>
-__device__ __forceinline__ void epi_chunk(HalfEpilogue<32, FAST>& epi, const PairHot* hoth, const TableCold* coldh,
-                                          uint32_t (&cur)[16], const Ctx& c, int row, int v, int tbase, bool live) {
-  float ch[16];
+// ---- per-sweep parameters of one view as the epilogue reads them (built at kernel start from TableParam) ----------
+struct __align__(16) TcViewParams {
+  float A[64], C[64], W[64];          // per table, read four tables at a time
+  float A1[64], C1[64], R[64], W1[64];// the customer's own table: leave-one-out slope / offset, R = A1 / A, W with l_vk - 1
+  int32_t lone[64];
+};
+static_assert(sizeof(TcViewParams) == 64 * sizeof(TableParam), "parameter staging area");
+
+__device__ __forceinline__ float ex2f(float d) { float r; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(d)); return r; }
+__device__ __forceinline__ float lg2f(float d) { float r; asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(d)); return r; }
+
+// u[i & 15] for a per-thread index: a binary tree of 15 selects (registers cannot be indexed).
+__device__ __forceinline__ float pick16(const uint32_t (&u)[16], int i) {
+  const bool b0 = i & 1, b1 = i & 2, b2 = i & 4, b3 = i & 8;
+  uint32_t a[8], b[4];
 #pragma unroll
-  for (int t = 0; t < 16; ++t) ch[t] = __uint_as_float(cur[t]);
-  if ((c.debug_export & 1) && live) {
-    float* da = c.dbg_acc + ((size_t)row * c.V + v) * 64 + tbase + BASE;
+  for (int k = 0; k < 8; ++k) a[k] = b0 ? u[2 * k + 1] : u[2 * k];
 #pragma unroll
-    for (int t = 0; t < 16; ++t) da[t] = ch[t];
-  }
-  epi.template view_chunk<BASE, WITH_NEW, true>(hoth, coldh, ch);
+  for (int k = 0; k < 4; ++k) b[k] = b1 ? a[2 * k + 1] : a[2 * k];
+  const uint32_t c0 = b2 ? b[1] : b[0], c1 = b2 ? b[3] : b[2];
+  return __uint_as_float(b3 ? c1 : c0);
 }
 
-template <bool FAST>
+// lw2[BASE/2 ..] += the 16 dot products of one chunk (tables tbase + BASE ..), optionally exported first.
+template <int BASE>
+__device__ __forceinline__ void add_chunk(float2 (&lw2)[16], const uint32_t (&u)[16], const Ctx& c, int row, int v, int tbase, bool live) {
+  if (live) {
+    float* da = c.dbg_acc + ((size_t)row * c.V + v) * 64 + tbase + BASE;
+#pragma unroll
+    for (int t = 0; t < 16; ++t) da[t] = __uint_as_float(u[t]);
+  }
+#pragma unroll
+  for (int p = 0; p < 8; ++p)
+    lw2[BASE / 2 + p] = fadd2(lw2[BASE / 2 + p], make_float2(__uint_as_float(u[2 * p]), __uint_as_float(u[2 * p + 1])));
+}
+
+// Streaming log-sum-exp over the dishes of one chunk for the new-table marginal (a free slot exists):
+// term_t = (x.b_t + (A_t (-|x|^2) + C_t)) + W_t, W masked except at the lowest table of each dish.  MUFU exponentials:
+// the marginal is a float statistic (tolerance), not part of the bit-reproducible draw.
+// MASKED: the term of table `skip` (relative to tbase; the lowest table of the customer's own dish) is left out here and
+// now.  The cheap alternative — sum everything and subtract that one term afterwards — cancels catastrophically when the
+// own dish dominates the sum AND its leave-one-out term is much smaller than its plain term, i.e. for small dishes (a
+// newborn table: the dish is the customer itself); the caller picks MASKED per warp for exactly those.
+template <int BASE, bool MASKED>
+__device__ __forceinline__ void lse_chunk(const TcViewParams& P, int tbase, const uint32_t (&u)[16], float nxx, int skip, float& mx, float& s) {
+  float2 term[8];
+  float c0 = kMasked, c1 = kMasked;
+  const float2 nxx2 = splat2(nxx);
+  const float4* A4 = reinterpret_cast<const float4*>(P.A + tbase + BASE);
+  const float4* C4 = reinterpret_cast<const float4*>(P.C + tbase + BASE);
+  const float4* W4 = reinterpret_cast<const float4*>(P.W + tbase + BASE);
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    const float4 a = A4[q], cc = C4[q], w = W4[q];
+    const float2 L0 = fadd2(make_float2(__uint_as_float(u[4 * q]), __uint_as_float(u[4 * q + 1])), ffma2(make_float2(a.x, a.y), nxx2, make_float2(cc.x, cc.y)));
+    const float2 L1 = fadd2(make_float2(__uint_as_float(u[4 * q + 2]), __uint_as_float(u[4 * q + 3])), ffma2(make_float2(a.z, a.w), nxx2, make_float2(cc.z, cc.w)));
+    term[2 * q] = fadd2(L0, make_float2(w.x, w.y));
+    term[2 * q + 1] = fadd2(L1, make_float2(w.z, w.w));
+    if (MASKED) {
+      if (skip == BASE + 4 * q) term[2 * q].x = kMasked;
+      if (skip == BASE + 4 * q + 1) term[2 * q].y = kMasked;
+      if (skip == BASE + 4 * q + 2) term[2 * q + 1].x = kMasked;
+      if (skip == BASE + 4 * q + 3) term[2 * q + 1].y = kMasked;
+    }
+    c0 = fmaxf(c0, fmaxf(term[2 * q].x, term[2 * q + 1].x));
+    c1 = fmaxf(c1, fmaxf(term[2 * q].y, term[2 * q + 1].y));
+  }
+  const float mn = fmaxf(mx, fmaxf(c0, c1));
+  s *= ex2f(mx - mn);
+  mx = mn;
+  float p0 = 0.f, p1 = 0.f;
+#pragma unroll
+  for (int p = 0; p < 8; ++p) { p0 += ex2f(term[p].x - mn); p1 += ex2f(term[p].y - mn); }
+  s += p0 + p1;
+}
+
+template <bool B> struct BoolC { static constexpr bool value = B; };
+
+// FAST: categorical weights through MUFU as well (tolerance-level draws).  DEBUG: the handle exports per-row intermediates
+// (debug_export bit 0) and / or per-role wait counters (bit 1); a separate instantiation keeps that code and its registers
+// out of the production kernel.
+template <bool FAST, bool DEBUG>
 __global__ void __launch_bounds__(kThreads, 1) k_draw_tc(const Ctx c, const __grid_constant__ TcMaps maps) {
   extern __shared__ __align__(1024) unsigned char smem[];
   const uint32_t sbase = smem_u32(smem);
@@ -262,10 +336,29 @@ __global__ void __launch_bounds__(kThreads, 1) k_draw_tc(const Ctx c, const __gr
   const uint32_t b_full = bar0 + 8u * (2 * kRawStages + 2 * kLoStages + 2 * kDStages);
 
   // ---- one-time setup --------------------------------------------------------------------------
-  for (int v = 0; v < V; ++v)
-    stage_view_params(c.tparam + v * 64, 64, reinterpret_cast<PairHot*>(s_tp + v * 2048),
-                      reinterpret_cast<TableCold*>(s_tp + v * 2048 + 1024), tid, kThreads);
-  for (int i = tid; i < 64; i += kThreads) { s_tm[i] = c.tmass[i]; s_lm[i] = c.tmass[i].LM; }
+  TcViewParams* s_p = reinterpret_cast<TcViewParams*>(s_tp);
+  float* s_dlm = reinterpret_cast<float*>(smem + SmemLayout::dlm_off);
+  int lone_ok = 1;                                    // every live table's dishes are served by that table alone?
+  for (int i = tid; i < V * 64; i += kThreads) {
+    const int v = i >> 6, t = i & 63;
+    const TableParam q = c.tparam[i];
+    TcViewParams& P = s_p[v];
+    P.A[t] = q.A; P.C[t] = q.C; P.W[t] = q.W;
+    P.A1[t] = q.A1; P.C1[t] = q.C1; P.W1[t] = q.W1;
+    P.R[t] = (q.A != 0.0f) ? __fdiv_rn(q.A1, q.A) : 0.0f;
+    // bit 0: the dish is served by this table alone; bit 1: the dish is SMALL (<= ~500 customers: R = 1 + 2 / (tau + n - 1),
+    // or n < 2), where removing the customer changes its likelihood by orders of magnitude (see lse_chunk)
+    P.lone[t] = (q.lone ? 1 : 0) | ((q.dish >= 0 && (P.R[t] > 1.004f || P.R[t] == 0.0f)) ? 2 : 0);
+    if (q.dish >= 0 && !q.lone) lone_ok = 0;
+  }
+  for (int t = tid; t < 64; t += kThreads) {
+    const TableMass m = c.tmass[t];
+    s_tm[t] = m;
+    float b = m.LM;
+    for (int v = 0; v < V; ++v) b = __fadd_rn(b, c.tparam[v * 64 + t].C);
+    s_lm[t] = b;                                      // base: log2 table mass + the views' offsets, in view order
+    s_dlm[t] = __fadd_rn(m.LM1, -m.LM);               // what changes for the customer's own table (n_t - 1)
+  }
   unsigned long long* s_same = reinterpret_cast<unsigned long long*>(smem + SmemLayout::same_off);
   for (int i = tid; i < V * 64; i += kThreads) s_same[i] = c.tsame[i];
   if (tid < V) s_vp[tid] = c.vparam[tid];
@@ -274,9 +367,11 @@ __global__ void __launch_bounds__(kThreads, 1) k_draw_tc(const Ctx c, const __gr
     s_misc[1] = g.sweep;
     s_misc[2] = __float_as_uint(g.LMN0);
     s_misc[3] = __float_as_uint(g.LMN1);
-    for (int s = 0; s < kRawStages; ++s) { mbar_init(raw_full(s), 1); mbar_init(raw_empty(s), 129); }   // one converter warpgroup + the MMA commit
-    for (int s = 0; s < kLoStages; ++s) { mbar_init(lo_full(s), 256); mbar_init(lo_empty(s), 1); }      // both converter warpgroups
-    for (int s = 0; s < kDStages; ++s) { mbar_init(d_full(s), 1); mbar_init(d_empty(s), 256); }   // both halves of a pair
+    for (int s = 0; s < kRawStages; ++s) { mbar_init(raw_full(s), 1); mbar_init(raw_empty(s), 5); }     // the four warps of one converter warpgroup + the MMA commit
+    for (int s = 0; s < kLoStages; ++s) { mbar_init(lo_full(s), 8); mbar_init(lo_empty(s), 1); }        // the eight converter warps
+    for (int s = 0; s < kDStages; ++s) { mbar_init(d_full(s), 1); mbar_init(d_empty(s), 8); }     // the eight warps of a pair
+    // (arrivals are per WARP — one lane after __syncwarp — not per thread: a waiter sleeping on the barrier is woken by every
+    //  arrival, and 256 wake-ups per phase cost the epilogue's schedulers issue slots)
     mbar_init(b_full, 1);
     fence_barrier_init();
   }
@@ -285,7 +380,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_draw_tc(const Ctx c, const __gr
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
   }
   tc_fence_before();
-  __syncthreads();
+  const bool all_lone_rt = __syncthreads_and(lone_ok) != 0;
   tc_fence_after();
   const uint32_t tmem_base = s_misc[0];
   const uint32_t sweep = s_misc[1];
@@ -294,7 +389,8 @@ __global__ void __launch_bounds__(kThreads, 1) k_draw_tc(const Ctx c, const __gr
   gp.LMN1 = __uint_as_float(s_misc[3]);
 
   const int n_tiles = (c.n_rows + kTileRows - 1) / kTileRows;
-  const bool prof = (c.debug_export & 2) != 0 && c.dbg_prof != nullptr;
+  const bool prof = DEBUG && (c.debug_export & 2) != 0 && c.dbg_prof != nullptr;
+  const bool dbg_rows = DEBUG && (c.debug_export & 1) != 0;
   long long* prof_out = prof ? c.dbg_prof + (size_t)blockIdx.x * 16 : nullptr;
   long long w0 = 0, w1 = 0, w2 = 0;
   const long long t_start = prof ? clock64() : 0;
@@ -435,26 +531,39 @@ __global__ void __launch_bounds__(kThreads, 1) k_draw_tc(const Ctx c, const __gr
           }
           tmem_st_16(lo_addr + (uint32_t)(half16 * 16), lo);
         }
-        mbar_arrive(raw_empty(rs));                    // this thread no longer reads the raw half
+        __syncwarp();
+        if (lane == 0) mbar_arrive(raw_empty(rs));     // this warp no longer reads the raw half
         tmem_st_wait();
         tc_fence_before();
-        mbar_arrive(lo_full(ls));
+        __syncwarp();
+        if (lane == 0) mbar_arrive(lo_full(ls));
       }
     if (prof && r == 0) { prof_out[6 + 3 * h] = w0; prof_out[7 + 3 * h] = w1; prof_out[8 + 3 * h] = clock64() - t_start; }
   } else {
     // =========================== WG3..WG6: epilogue (thread r <-> TMEM lane r <-> customer r) ====
     // pool: 896 threads x 72 registers = 128 x (24 + 2*48 + 4*96)
     reg_inc<96>();
+    // Two CTA-uniform properties of the sweep select one of four copies of the loop, so that the registers and the code of
+    // the rarer cases stay out of the common one:
+    //   with_new   a table slot is free: the new-table option has weight and the per-view marginals are evaluated;
+    //   all_lone   every live table's dishes are served by that table alone: the leave-one-out correction touches the
+    //              customer's own table only.
+    auto epilogue = [&](auto WN, auto AL) {
+    constexpr bool with_new = decltype(WN)::value;
+    constexpr bool all_lone = decltype(AL)::value;
     const int wg = (warp >> 2) - 3;
     const int pair = wg >> 1;                          // this pair takes tiles j = pair, pair+2, ...
     const int hf = wg & 1;                             // tables [32 hf, 32 hf + 32)
+    const int tb = 32 * hf;
     const int r = tid & 127;
     const uint32_t lane_base = (uint32_t)((warp & 3) * 32) << 16;
     float* ex_own = reinterpret_cast<float*>(smem + SmemLayout::ex_off) + ((pair * 2 + hf) * kExFields) * kTileRows + r;
     float* ex_oth = reinterpret_cast<float*>(smem + SmemLayout::ex_off) + ((pair * 2 + (hf ^ 1)) * kExFields) * kTileRows + r;
-    auto rendezvous = [&]() { asm volatile("bar.sync %0, 256;" ::"r"(1 + pair) : "memory"); };
-    // no free table slot => a new table has no weight and the per-view marginals are skipped (CTA-uniform)
-    const bool with_new = (gp.LMN0 > -1.0e29f) || (gp.LMN1 > -1.0e29f);
+    // exchange fields: 0-5 (mx, s) of the views' dish sums, 6-8 the own-dish term per view, 9 half maximum, 10 half total,
+    // 11 uniform / upper count, 12-14 the leave-one-out corrections (only when tables share dishes)
+    // the two threads of a customer sit in the same warp slot of the pair's two warpgroups: only those two warps meet
+    auto rendezvous = [&]() { asm volatile("bar.sync %0, 64;" ::"r"(1 + pair * 4 + (warp & 3)) : "memory"); };
+    const float4* base4 = reinterpret_cast<const float4*>(s_lm + tb);
     int j = pair;
     const int tile0 = blockIdx.x + pair * gridDim.x;
     int t0_next = (tile0 < n_tiles) ? c.table_cur[min(tile0 * kTileRows + r, c.n_rows - 1)] : 0;
@@ -463,12 +572,16 @@ __global__ void __launch_bounds__(kThreads, 1) k_draw_tc(const Ctx c, const __gr
 #pragma unroll
     for (int v = 0; v < kMaxTcViews; ++v)
       xx_next[v] = (tile0 < n_tiles) ? c.xx[(size_t)v * c.xx_stride + min(tile0 * kTileRows + r, c.n_rows - 1)] : 0.0f;   // (xx has >= 3 rows)
+    long long ph[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0}, tlast = prof ? clock64() : 0;      // DEBUG: cycles per phase of the tile loop
+    auto phase = [&](int k) { if (prof) { const long long now = clock64(); ph[k] += now - tlast; tlast = now; } };
     for (int tile = tile0; tile < n_tiles; tile += kEpiGroups * gridDim.x, j += kEpiGroups) {
       const int row = tile * kTileRows + r;
       const bool live = row < c.n_rows;
       const int rowc = live ? row : (c.n_rows - 1);
-      HalfEpilogue<32, FAST> epi;
-      epi.begin(s_tm, s_lm, t0_next, 32 * hf);
+      const int t0 = t0_next;
+      const int single = s_tm[t0].single;
+      const int rel = t0 - tb;                        // the customer's own table inside this half?
+      const bool mine = (unsigned)rel < 32u;
       float xxv[kMaxTcViews];
 #pragma unroll
       for (int v = 0; v < kMaxTcViews; ++v) xxv[v] = xx_next[v];
@@ -481,92 +594,234 @@ __global__ void __launch_bounds__(kThreads, 1) k_draw_tc(const Ctx c, const __gr
           for (int v = 0; v < kMaxTcViews; ++v) xx_next[v] = c.xx[(size_t)v * c.xx_stride + rn];
         }
       }
-      float lnew = epi.single ? gp.LMN1 : gp.LMN0;
+      // lw = base + sum_v A_v (-|x_v|^2): everything that does not need the dot products, before they arrive
+      float2 lw2[16];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const float4 q = base4[i];
+        lw2[2 * i] = make_float2(q.x, q.y);
+        lw2[2 * i + 1] = make_float2(q.z, q.w);
+      }
+#pragma unroll
+      for (int v = 0; v < kMaxTcViews; ++v) {
+        if (v < V) {
+          const float2 nxx2 = splat2(-xxv[v]);
+          const float4* A4 = reinterpret_cast<const float4*>(s_p[v].A + tb);
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const float4 a = A4[i];
+            lw2[2 * i] = ffma2(make_float2(a.x, a.y), nxx2, lw2[2 * i]);
+            lw2[2 * i + 1] = ffma2(make_float2(a.z, a.w), nxx2, lw2[2 * i + 1]);
+          }
+        }
+      }
+      float dsum = 0.0f;                              // ((0 + delta_0) + delta_1) + delta_2
+      phase(0);
       for (int v = 0; v < V; ++v) {
         const int idx = j * V + v;
         const int stage = idx % kDStages;             // V = 3: stages 0-2 serve this CTA's even tiles, 3-5 the odd ones
         mbar_wait_t(d_full(stage), (uint32_t)(idx / kDStages) & 1u, prof, w0);
         tc_fence_after();
-        const uint32_t taddr = tmem_base + lane_base + (uint32_t)(stage * 64 + 32 * hf);
+        const uint32_t taddr = tmem_base + lane_base + (uint32_t)(stage * 64 + tb);
         const float xx = (v == 0) ? xxv[0] : ((v == 1) ? xxv[1] : xxv[2]);
-        const PairHot* hot = reinterpret_cast<const PairHot*>(s_tp + v * 2048);
-        const TableCold* cold = reinterpret_cast<const TableCold*>(s_tp + v * 2048 + 1024);
-        epi.view_begin(hot, cold, xx);
-        epi.samemask = (uint32_t)(s_same[v * 64 + epi.t0] >> (32 * hf));
-        if ((c.debug_export & 1) && live && hf == 0) c.dbg_xx[(size_t)row * V + v] = xx;
-        uint32_t ua[16], ub[16];
-        tmem_ld_16(taddr, ua);
+        const float nxx = -xx;
+        const TcViewParams& P = s_p[v];
+        if (dbg_rows && live && hf == 0) c.dbg_xx[(size_t)row * V + v] = xx;
+        // 16 dot products at a time through ONE register buffer (two live buffers do not fit beside the 32 running log-weights)
+        uint32_t u[16];
+        tmem_ld_16(taddr, u);
+        float mx = kMasked, s = 0.0f;
+        const int rep = all_lone ? t0 : (__ffsll((long long)s_same[v * 64 + t0]) - 1);   // lowest table of the own dish
+        const int rrel = rep - tb;
+        // own dish small and its term in this half: leave it out exactly (warp-uniform choice of the variant)
+        const bool masked = with_new && __any_sync(0xffffffffu, (unsigned)rrel < 32u && (P.lone[t0] & 2));
         tmem_ld_wait();
-        tmem_ld_16(taddr + 16, ub);
-        if (with_new) epi_chunk<0, true>(epi, hot + 16 * hf, cold + 32 * hf, ua, c, row, v, 32 * hf, live);
-        else epi_chunk<0, false>(epi, hot + 16 * hf, cold + 32 * hf, ua, c, row, v, 32 * hf, live);
+        add_chunk<0>(lw2, u, c, row, v, tb, live && dbg_rows);
+        if (with_new) {
+          if (masked) lse_chunk<0, true>(P, tb, u, nxx, rrel, mx, s);
+          else lse_chunk<0, false>(P, tb, u, nxx, rrel, mx, s);
+        }
+        const float pa = pick16(u, rel);
+        float pra = 0.0f;
+        if (with_new && !all_lone && !masked) pra = pick16(u, rrel);
+        tmem_ld_16(taddr + 16, u);
         tmem_ld_wait();
         tc_fence_before();
-        mbar_arrive(d_empty(stage));                  // this half's columns are in registers
+        __syncwarp();
+        if (lane == 0) mbar_arrive(d_empty(stage));   // this warp's columns are in registers
+        add_chunk<16>(lw2, u, c, row, v, tb, live && dbg_rows);
         if (with_new) {
-          epi_chunk<16, true>(epi, hot + 16 * hf, cold + 32 * hf, ub, c, row, v, 32 * hf, live);
-          ex_own[(2 * v) * kTileRows] = epi.mx;
-          ex_own[(2 * v + 1) * kTileRows] = epi.s;
-        } else {
-          epi_chunk<16, false>(epi, hot + 16 * hf, cold + 32 * hf, ub, c, row, v, 32 * hf, live);
+          if (masked) lse_chunk<16, true>(P, tb, u, nxx, rrel, mx, s);
+          else lse_chunk<16, false>(P, tb, u, nxx, rrel, mx, s);
+        }
+        const float pb = pick16(u, rel);
+        // the customer's own table in this view: plain and leave-one-out value of log2 f from its dot product
+        const float own_acc = (rel & 16) ? pb : pa;
+        const float plain = __fadd_rn(own_acc, __fmaf_rn(P.A[t0], nxx, P.C[t0]));
+        const float loo = __fmaf_rn(P.R[t0], own_acc, __fmaf_rn(P.A1[t0], nxx, P.C1[t0]));
+        const float dlt = __fadd_rn(loo, -plain);
+        dsum = __fadd_rn(dsum, dlt);
+        if (!all_lone) ex_own[(12 + v) * kTileRows] = mine ? dlt : 0.0f;
+        if (with_new) {
+          // the own dish enters the marginal with the customer removed: take its plain term out of this half's sum
+          // (it sits at the dish's lowest table) and publish the leave-one-out term for the merge
+          if (!masked && (unsigned)rrel < 32u) {
+            float acc_rep = own_acc;
+            if (!all_lone) acc_rep = (rrel & 16) ? pick16(u, rrel) : pra;
+            const float trp = __fadd_rn(__fadd_rn(acc_rep, __fmaf_rn(P.A[rep], nxx, P.C[rep])), P.W[rep]);
+            s = fmaxf(s - ex2f(trp - mx), 0.0f);
+          }
+          ex_own[(2 * v) * kTileRows] = mx;
+          ex_own[(2 * v + 1) * kTileRows] = s;
+          ex_own[(6 + v) * kTileRows] = mine ? __fadd_rn(loo, single ? P.W1[rep] : P.W[rep]) : kMasked;
+        }
+      }
+      phase(1);
+      // ---- the leave-one-out corrections: to the own table alone, or to every table serving an own dish ----
+      if (all_lone) {
+        const float corr = __fadd_rn(dsum, s_dlm[t0]);
+        float* lw = reinterpret_cast<float*>(lw2);
+#pragma unroll
+        for (int q = 0; q < 32; ++q) if (q == rel) lw[q] = __fadd_rn(lw[q], corr);
+      } else {
+        rendezvous();                                 // #0: the corrections, known to the thread that holds the own table
+        float dl[kMaxTcViews];
+        uint32_t mk[kMaxTcViews];
+#pragma unroll
+        for (int v = 0; v < kMaxTcViews; ++v) {
+          dl[v] = (v < V) ? (mine ? ex_own[(12 + v) * kTileRows] : ex_oth[(12 + v) * kTileRows]) : 0.0f;
+          mk[v] = (v < V) ? (uint32_t)(s_same[v * 64 + t0] >> tb) : 0u;
+        }
+        const float dlm = s_dlm[t0];
+        float* lw = reinterpret_cast<float*>(lw2);
+#pragma unroll
+        for (int q = 0; q < 32; ++q) {
+          float cq = 0.0f;
+#pragma unroll
+          for (int v = 0; v < kMaxTcViews; ++v) if ((mk[v] >> q) & 1u) cq = __fadd_rn(cq, dl[v]);
+          if (q == rel) cq = __fadd_rn(cq, dlm);
+          lw[q] = __fadd_rn(lw[q], cq);
         }
       }
       float uf = 0.0f;
       if (hf == 0) {
         const U4 rnd = stream_block(c.seed, c.chain, kDomTable, 0, sweep, (uint64_t)(c.row_offset + rowc));
         uf = uniform_f32_from(rnd.x);
-        ex_own[8 * kTileRows] = uf;
+        ex_own[11 * kTileRows] = uf;
       }
-      ex_own[6 * kTileRows] = epi.halfmax();
-      rendezvous();                                   // #1: streaming sums, half maxima, the uniform
+      float hmax;
+      {
+        float M0 = kMasked, M1 = kMasked;
+#pragma unroll
+        for (int i = 0; i < 16; ++i) { M0 = fmaxf(M0, lw2[i].x); M1 = fmaxf(M1, lw2[i].y); }
+        hmax = fmaxf(M0, M1);
+      }
+      ex_own[9 * kTileRows] = hmax;
+      phase(2);
+      rendezvous();                                   // #1: dish sums, own-dish terms, half maxima, the uniform
+      phase(3);
+      float lnew = single ? gp.LMN1 : gp.LMN0;
       for (int v = 0; with_new && v < V; ++v) {
         const float mo = ex_oth[(2 * v) * kTileRows], so = ex_oth[(2 * v + 1) * kTileRows];
         const float mi = ex_own[(2 * v) * kTileRows], si = ex_own[(2 * v + 1) * kTileRows];
-        const TableCold* cold = reinterpret_cast<const TableCold*>(s_tp + v * 2048 + 1024);
+        const float mA = hf ? mo : mi, sA = hf ? so : si, mB = hf ? mi : mo, sB = hf ? si : so;   // half A first in both threads
+        const float ot = fmaxf(ex_own[(6 + v) * kTileRows], ex_oth[(6 + v) * kTileRows]);
         const float xx = (v == 0) ? xxv[0] : ((v == 1) ? xxv[1] : xxv[2]);
-        lnew = __fadd_rn(lnew, merge_view<FAST>(hf ? mo : mi, hf ? so : si, hf ? mi : mo, hf ? si : so, s_vp[v], xx,
-                                                epi.single, cold[epi.t0].lone));
+        const ViewParam vp = s_vp[v];
+        const float termnew = __fmaf_rn(-vp.AN, xx, vp.CN) + ((single && (s_p[v].lone[t0] & 1)) ? vp.WN1 : vp.WN0);
+        const float m2 = fmaxf(fmaxf(mA, mB), fmaxf(ot, termnew));
+        const float ssum = ((sA * ex2f(mA - m2) + sB * ex2f(mB - m2)) + ex2f(ot - m2)) + ex2f(termnew - m2);
+        lnew += (m2 + lg2f(ssum)) - (single ? vp.LD1 : vp.LD0);
       }
-      if (hf == 1) uf = ex_oth[8 * kTileRows];
-      const float M = hf ? fmaxf(fmaxf(lnew, ex_oth[6 * kTileRows]), ex_own[6 * kTileRows])
-                         : fmaxf(fmaxf(lnew, ex_own[6 * kTileRows]), ex_oth[6 * kTileRows]);
-      int choice = epi.t0;                            // nothing has weight: stay (cf. multiview_gibbs.cpp:172-176)
+      if (hf == 1) uf = ex_oth[11 * kTileRows];
+      const float hoth = ex_oth[9 * kTileRows];
+      const float M = hf ? fmaxf(fmaxf(lnew, hoth), hmax) : fmaxf(fmaxf(lnew, hmax), hoth);
+      int choice = t0;                                // nothing has weight: stay (cf. multiview_gibbs.cpp:172-176)
       const bool any_weight = (M > -1.0e29f);         // identical in both threads of the customer
       float Hown = 0.0f;
-      if (any_weight) Hown = epi.weights(M);
-      ex_own[7 * kTileRows] = Hown;
+      if (any_weight) {                               // lw2 <- 2^(lw2 - M); this half's total (partial sums over t mod 4, fixed tree)
+        const float2 nM2 = splat2(-M);
+        float2 qa = splat2(0.0f), qb = splat2(0.0f);
+#pragma unroll
+        for (int i = 0; i < 16; i += 2) {
+          lw2[i] = exp2w2<FAST>(fadd2(lw2[i], nM2));         qa = fadd2(qa, lw2[i]);
+          lw2[i + 1] = exp2w2<FAST>(fadd2(lw2[i + 1], nM2)); qb = fadd2(qb, lw2[i + 1]);
+        }
+        Hown = __fadd_rn(__fadd_rn(qa.x, qa.y), __fadd_rn(qb.x, qb.y));
+      }
+      ex_own[10 * kTileRows] = Hown;
+      phase(4);
       rendezvous();                                   // #2: half totals
-      const float Hoth = ex_oth[7 * kTileRows];
+      phase(5);
+      const float Hoth = ex_oth[10 * kTileRows];
       const float HA = hf ? Hoth : Hown, HB = hf ? Hown : Hoth;
       const float total = __fadd_rn(__fadd_rn(HA, HB), exp2w<FAST>(__fadd_rn(lnew, -M)));
       const float target = __fmul_rn(uf, total);
-      int cnt = 0;
-      if (any_weight) cnt = epi.scan(target, hf ? HA : 0.0f);
+      int cnt = 0, last = -1;
+      if (any_weight) {                               // tables of this half whose cumulative weight is <= target
+        float cum = hf ? HA : 0.0f;
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+          cum = __fadd_rn(cum, lw2[i].x);
+          cnt += (target < cum) ? 0 : 1;
+          cum = __fadd_rn(cum, lw2[i].y);
+          cnt += (target < cum) ? 0 : 1;
+        }
+      }
       if (hf == 1) {
         int enc = cnt;
-        if (cnt == 32) enc |= (epi.last_live() + 1) << 8;   // only needed when the draw ran past every table
-        ex_own[8 * kTileRows] = __int_as_float(enc);
+        if (cnt == 32) {                              // only needed when the draw ran past every table
+#pragma unroll
+          for (int i = 0; i < 16; ++i) {
+            if (lw2[i].x > 1.0e-30f) last = 2 * i;
+            if (lw2[i].y > 1.0e-30f) last = 2 * i + 1;
+          }
+          enc |= (last + 1) << 8;
+        }
+        ex_own[11 * kTileRows] = __int_as_float(enc);
       }
+      phase(6);
       rendezvous();                                   // #3: the upper half's count
+      phase(7);
       if (hf == 0) {
         if (any_weight) {
-          const int enc = __float_as_int(ex_oth[8 * kTileRows]);
+          const int enc = __float_as_int(ex_oth[11 * kTileRows]);
           const int total_cnt = cnt + (enc & 0xFF);
           choice = (total_cnt < 64) ? total_cnt : kNewTable;
           if (total_cnt >= 64 && !(lnew > -1.0e29f)) {   // rounding fall-through with no new-table mass: last live table
-            const int lb = (enc >> 8) - 1, la = epi.last_live();
-            choice = (lb >= 0) ? (32 + lb) : ((la >= 0) ? la : epi.t0);
+            const int lb = (enc >> 8) - 1;
+            int la = -1;
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+              if (lw2[i].x > 1.0e-30f) la = 2 * i;
+              if (lw2[i].y > 1.0e-30f) la = 2 * i + 1;
+            }
+            choice = (lb >= 0) ? (32 + lb) : ((la >= 0) ? la : t0);
           }
         }
+        if (c.blk_count > 1 && (int)((c.row_offset + rowc) % c.blk_count) != c.blk_index) choice = t0;   // not this pass's block
         if (live) {
           c.choice[row] = choice;
-          if (c.debug_export & 1) c.dbg_choice[row] = choice;
+          if (dbg_rows) { c.dbg_choice[row] = choice; c.dbg_lnew[row] = lnew; }
         }
         const unsigned births = __ballot_sync(0xffffffffu, live && choice == kNewTable);
-        if (lane == 0 && (row >> 5) < c.n_chunks) c.birthmask[row >> 5] = births;
+        const unsigned moved = __ballot_sync(0xffffffffu, live && choice != t0);
+        if (lane == 0 && (row >> 5) < c.n_chunks) { c.birthmask[row >> 5] = births; c.movedmask[row >> 5] = moved; }
       }
     }
+    phase(8);
     if (prof && r == 0 && hf == 0) { prof_out[12 + 2 * pair] = w0 + w1; prof_out[13 + 2 * pair] = clock64() - t_start; }
+    if (prof && r == 0 && blockIdx.x == 0 && pair == 0) {
+      // phases: 0 prologue (base, A|x|^2), 1 views (incl. the accumulator waits, reported separately), 2 corrections + max,
+      // 3 rendezvous 1, 4 marginals + weights, 5 rendezvous 2, 6 scan, 7 rendezvous 3, 8 write-out
+      long long* po = c.dbg_prof + (230 + hf) * 16;
+      for (int k = 0; k < 9; ++k) po[k] = ph[k];
+      po[9] = w0;
+    }
+    };
+    const bool with_new_rt = (gp.LMN0 > -1.0e29f) || (gp.LMN1 > -1.0e29f);
+    if (with_new_rt) { if (all_lone_rt) epilogue(BoolC<true>(), BoolC<true>()); else epilogue(BoolC<true>(), BoolC<false>()); }
+    else { if (all_lone_rt) epilogue(BoolC<false>(), BoolC<true>()); else epilogue(BoolC<false>(), BoolC<false>()); }
   }
 
   // ---- teardown ------------------------------------------------------------------------------------
@@ -628,7 +883,8 @@ cudaError_t launch_draw_tc(const Ctx& c, const void* maps, bool fast, cudaStream
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   const int n_tiles = (c.n_rows + kTileRows - 1) / kTileRows;
   const int grid = n_tiles < sms ? n_tiles : sms;
-  auto kern = fast ? k_draw_tc<true> : k_draw_tc<false>;
+  const bool dbg = c.debug_export != 0;
+  auto kern = fast ? (dbg ? k_draw_tc<true, true> : k_draw_tc<true, false>) : (dbg ? k_draw_tc<false, true> : k_draw_tc<false, false>);
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SmemLayout::total);
   if (e != cudaSuccess) return e;
   kern<<<grid, kThreads, SmemLayout::total, s>>>(c, *static_cast<const TcMaps*>(maps));

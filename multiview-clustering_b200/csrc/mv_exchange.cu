@@ -100,7 +100,9 @@ XchgLayout xchg_layout(const Ctx& c) {
 // Blocks [0, n_sum_blocks): 32 consecutive elements x 8 slices (slice j adds the partials of CTAs j, j+8, ... in
 // ascending order, then the 8 slice sums are added in ascending order: a fixed tree), walking the elements with a
 // grid stride.  Blocks [n_sum_blocks, n_sum_blocks + world) in mode 1: the birth candidates of / for rank g.
-__global__ void __launch_bounds__(256) k_reduce_x(const Ctx c, const int mode, const int n_sum_blocks, const XchgPeers peers,
+// delta: the partials hold the CHANGE of this shard's statistics (mv_stats_tile.cu, DELTA): it is added to the shard's
+// running FP64 sums, which live in its packet, instead of replacing them.
+__global__ void __launch_bounds__(256) k_reduce_x(const Ctx c, const int mode, const int delta, const int n_sum_blocks, const XchgPeers peers,
                                                   unsigned char* __restrict__ recv_local, const XchgLayout L) {
   __shared__ double s_part[kRedSlices][32];
   __shared__ int s_cnt[kRedSlices][32];
@@ -186,6 +188,11 @@ __global__ void __launch_bounds__(256) k_reduce_x(const Ctx c, const int mode, c
         sum = 0.0; n = 0;
 #pragma unroll
         for (int j = 0; j < kRedSlices; ++j) { sum += s_part[j][e]; n += s_cnt[j][e]; }
+        if (delta) {
+          if (i < n_s1) sum += pk_s1[i];
+          else if (!is_cnt) sum += pk_s2[i - n_s1];
+          else n += pk_cnt[i - n_s1 - n_s2];
+        }
         if (i < n_s1) pk_s1[i] = sum;
         else if (!is_cnt) pk_s2[i - n_s1] = sum;
         else pk_cnt[i - n_s1 - n_s2] = n;
@@ -228,13 +235,13 @@ __global__ void __launch_bounds__(256) k_reduce_x(const Ctx c, const int mode, c
   }
 }
 
-cudaError_t launch_reduce_x(const Ctx& c, int mode, const XchgPeers& peers, unsigned char* recv_local, cudaStream_t s) {
+cudaError_t launch_reduce_x(const Ctx& c, int mode, bool delta, const XchgPeers& peers, unsigned char* recv_local, cudaStream_t s) {
   const XchgLayout L = xchg_layout(c);
   const int n_el = (int)L.n_units;
   int nb = (n_el + 31) / 32;
   if (nb > 148 * 4) nb = 148 * 4;              // every block of one launch is resident at once (peers wait for each other's pushes)
   const int extra = (mode == 1) ? c.world : 0;
-  k_reduce_x<<<nb + extra, 256, 0, s>>>(c, mode, nb, peers, recv_local, L);
+  k_reduce_x<<<nb + extra, 256, 0, s>>>(c, mode, delta ? 1 : 0, nb, peers, recv_local, L);
   return cudaGetLastError();
 }
 

@@ -300,19 +300,19 @@ __global__ void __launch_bounds__(768, 1) k_stats(const Ctx c, const int Gp, con
   }
 }
 
-cudaError_t launch_stats(const Ctx& c, cudaStream_t s) {
+cudaError_t launch_stats(const Ctx& c, bool delta, cudaStream_t s) {
   // the C3 shape has a register-accumulating, bulk-copy fed kernel (mv_stats_tile.cu); MVG_STATS_GENERIC=1
   // forces the general kernel below (used by the tests to check one against the other)
   const char* fg = getenv("MVG_STATS_GENERIC");
   const bool force_generic = fg && fg[0] == '1';
-  if (!force_generic && stats_tile_supported(c)) return launch_stats_tile(c, s);
+  if (stats_tile_supported(c) && (delta || !force_generic)) return launch_stats_tile(c, delta, s);
+  if (delta) return cudaErrorInvalidValue;           // the caller asks stats_delta_supported first
   const StatsPlan pl = stats_plan(c);
   cudaError_t e = cudaFuncSetAttribute(k_stats, cudaFuncAttributeMaxDynamicSharedMemorySize, pl.smem);
   if (e != cudaSuccess) return e;
   k_stats<<<c.stat_ctas, pl.R * pl.Gp * 32, pl.smem, s>>>(c, pl.Gp, pl.R, pl.passes);
   return cudaGetLastError();
 }
-
 
 // =============================================================================================
 // k_finalize
@@ -545,6 +545,18 @@ __device__ __noinline__ double log_f_dish_counts(const int32_t* __restrict__ rp,
   return lf;
 }
 
+// The Philox numbers of one level's hyper step, by the calling warp's lanes 0..5: rn/lu[which], which = 0 tau, 1 alpha,
+// 2 sigma.  Stream positions are those the reference's sequential code would use: tau_v at v, (alpha_v, sigma_v) at
+// V + 2v, the franchise pair at 3V.  `first`..`last`: the range of `which` this call draws.
+__device__ __forceinline__ void draw_level_randoms(FinShared& S, uint64_t seed, uint32_t chain, uint32_t sweep, int V, int v,
+                                                   bool is_view, int first, int last, int lane) {
+  const int which = first + (lane >> 1);
+  if (which > last || lane >= 2 * (last - first + 1)) return;
+  const int idx = (which == 0) ? v : ((is_view ? V + 2 * v : 3 * V) + which - 1);
+  if (lane & 1) S.lu[which] = fin_log(dev_unif(seed, chain, sweep, idx));
+  else S.rn[which] = dev_normal(seed, chain, sweep, idx);
+}
+
 __global__ void __launch_bounds__(kFinThreads, 1) k_finalize(const Ctx c, const int32_t flags, const int32_t s1_in_smem) {
   extern __shared__ __align__(16) unsigned char fin_smem[];
   FinShared& S = *reinterpret_cast<FinShared*>(fin_smem);
@@ -577,21 +589,8 @@ __global__ void __launch_bounds__(kFinThreads, 1) k_finalize(const Ctx c, const 
     S.hyp[1] = is_view ? c.hyp[V + v] : c.hyp[3 * V + 1];
     S.hyp[2] = is_view ? c.hyp[2 * V + v] : 0.0;
   }
-  // The random numbers of the hyper step depend on nothing but (seed, sweep, index): the last warps draw them now,
-  // while the others wait on the loads below, instead of in the middle of the serial MH chain.  Stream positions are
-  // those the reference's sequential code would use: tau_v at v, (alpha_v, sigma_v) at V + 2v, the franchise at 3V.
-  if ((flags & kFinHyper) && tid >= kFinThreads - 6 * 32 && (tid & 31) == 0) {
-    const int q = (tid - (kFinThreads - 6 * 32)) >> 5;          // six independent values on six warps
-    const int which = q % 3;                                     // 0 tau, 1 alpha, 2 sigma
-    const int idx = (which == 0) ? v : ((is_view ? V + 2 * v : 3 * V) + which - 1);
-    if (which != 0 || is_view) {
-      if (q < 3) S.rn[which] = dev_normal(c.seed, c.chain, sweep, idx);
-      else S.lu[which] = fin_log(dev_unif(c.seed, c.chain, sweep, idx));
-    }
-  }
-  // ... and touch the other out-of-line FP64 routines of the MH chain, so that their code is in the instruction
-  // cache before the chain needs it
-  if ((flags & kFinHyper) && tid == kFinThreads - 7 * 32) { S.warm[0] = fin_lgamma(2.5 + (double)sweep); S.warm[1] = fin_exp(-1.0 - (double)V); }
+  // (The random numbers of the hyper step depend on nothing but (seed, sweep, index): they are drawn by otherwise idle
+  //  warps right before the chains that use them — see draw_level_randoms — and never hold up a CTA-wide barrier.)
 
   // ---- A. this level's inputs: the statistics summed over the shards (k_reduce_x), the sweep-start state --------
   for (int t = tid; t < cap; t += kFinThreads) {
@@ -754,11 +753,15 @@ __global__ void __launch_bounds__(kFinThreads, 1) k_finalize(const Ctx c, const 
     __syncthreads();
     // B3. candidates join the statistics of their final table, in global row order
     if (tid == 0) for (int b = 0; b < ncand; ++b) S.n_new[S.cand_final[b]] += 1;
+    // (This shard's own candidates also join its RUNNING statistics — the sums in its packet that the incremental mode
+    //  carries from sweep to sweep; a full rebuild overwrites them.)
     if (!is_view) {
       if (tid == 32) {
         for (int b = 0; b < ncand; ++b)
-          if (S.cand_g[b] == c.rank)
+          if (S.cand_g[b] == c.rank) {
             c.table_cur[pkt_i32(c, c.rank, c.pkt.off_cand_row)[S.cand_j[b]]] = S.cand_final[b];
+            pkt_i32(c, c.rank, c.pkt.off_cnt)[S.cand_final[b]] += 1;
+          }
       }
       if (tid == 64 && c.debug_export)
         for (int b = 0; b < nseat; ++b)
@@ -773,12 +776,15 @@ __global__ void __launch_bounds__(kFinThreads, 1) k_finalize(const Ctx c, const 
           if (is_count)      // count view: this slot carries token totals; the candidate's row is local (world = 1)
             q = (double)c.xx[(size_t)v * c.xx_stride + pkt_i32(c, S.cand_g[b], c.pkt.off_cand_row)[S.cand_j[b]]];
           S.s2t[S.cand_final[b]] += q;
+          if (S.cand_g[b] == c.rank) pkt_f64(c, c.rank, c.pkt.off_s2t)[v * cap + S.cand_final[b]] += q;
         }
       }
       for (int dd = tid; dd < D; dd += kFinThreads) {
+        double* loc = pkt_f64(c, c.rank, c.pkt.off_s1t) + (size_t)cap * doff;
         for (int b = 0; b < ncand; ++b) {
           const float xv = pkt_f32(c, S.cand_g[b], c.pkt.off_cand_x)[(size_t)S.cand_j[b] * c.Dsum + doff + dd];
           S1t[(size_t)S.cand_final[b] * D + dd] += (double)xv;
+          if (S.cand_g[b] == c.rank) loc[(size_t)S.cand_final[b] * D + dd] += (double)xv;
         }
       }
     }
@@ -801,6 +807,7 @@ __global__ void __launch_bounds__(kFinThreads, 1) k_finalize(const Ctx c, const 
       S.total = (long long)c.n_global;
     }
     if (flags & kFinTauInit) { if (tid == 0) { alpha_l = 1.0; sigma_l = 0.6; } }      // multiview_gibbs.cpp:97-98
+    if ((flags & kFinHyper) && tid >= 32 && tid < 64) draw_level_randoms(S, c.seed, c.chain, sweep, V, v, false, 1, 2, tid - 32);
     __syncthreads();
     // (alpha_global, sigma_global), multiview_hyper.cpp:268-291, by the first half of the CTA
     if (tid < kGroupThreads)
@@ -852,23 +859,46 @@ __global__ void __launch_bounds__(kFinThreads, 1) k_finalize(const Ctx c, const 
     if (S.n_new[t] == 0) S.dish[t] = -1;                     // multiview_utils.cpp:168-191
     else if (S.dish[t] < 0 || S.dish[t] >= cap) { S.err |= 2; S.dish[t] = 0; }
   }
+  // An empty table has exactly zero statistics: clear what incremental updates may have left of its sums (rounding
+  // residue of the rows that came and went) in the totals and in this shard's running sums.
+  for (int i = tid; i < cap * D; i += kFinThreads) {
+    const int t = i / D;
+    if (S.n_new[t] == 0) { S1t[i] = 0.0; pkt_f64(c, c.rank, c.pkt.off_s1t)[(size_t)cap * doff + i] = 0.0; }
+  }
+  for (int t = tid; t < cap; t += kFinThreads)
+    if (S.n_new[t] == 0) { S.s2t[t] = 0.0; pkt_f64(c, c.rank, c.pkt.off_s2t)[v * cap + t] = 0.0; }
   __syncthreads();
-  for (int k = tid; k < cap; k += kFinThreads) {
-    int l = 0, n = 0;
-    double s2 = 0.0;
-    unsigned long long m = 0ull;                                // which tables serve dish (v, k)
-    for (int t = 0; t < cap; ++t)
-      if (S.dish[t] == k) { l += 1; n += S.n_new[t]; s2 += S.s2t[t]; m |= 1ull << t; }
-    S.l_live[k] = l;
-    S.n_vk[k] = n;
-    S.s2k[k] = s2;
-    S.tmask[k] = m;
-    const int i = v * cap + k;
-    c.S2k[i] = s2;
-    c.S2t[i] = S.s2t[k];                                    // (index reuse: slot k as a table)
-    c.l_vk[i] = l;
-    c.n_vk[i] = n;
-    c.dish_of[i] = S.dish[k];
+  {
+    // one warp per dish k: which tables serve it (ballots over the table slots), how many customers they hold
+    const int lane = tid & 31, wid = tid >> 5;
+    for (int k = wid; k < cap; k += kFinThreads / 32) {
+      unsigned long long m = 0ull;
+      int n = 0;
+      double s2 = 0.0;
+      for (int base = 0; base < cap; base += 32) {
+        const int t = base + lane;
+        const bool mine = (t < cap) && (S.dish[t] == k);
+        m |= (unsigned long long)__ballot_sync(0xffffffffu, mine) << base;
+      }
+      if (lane == 0) {
+        for (unsigned long long r = m; r; r &= r - 1ull) {         // ascending table order (usually one table)
+          const int t = __ffsll((long long)r) - 1;
+          n += S.n_new[t];
+          s2 += S.s2t[t];
+        }
+        const int l = __popcll(m);
+        S.l_live[k] = l;
+        S.n_vk[k] = n;
+        S.s2k[k] = s2;
+        S.tmask[k] = m;
+        const int i = v * cap + k;
+        c.S2k[i] = s2;
+        c.S2t[i] = S.s2t[k];                                  // (index reuse: slot k as a table)
+        c.l_vk[i] = l;
+        c.n_vk[i] = n;
+        c.dish_of[i] = S.dish[k];
+      }
+    }
   }
   __syncthreads();
   stamp(7);
@@ -887,6 +917,7 @@ __global__ void __launch_bounds__(kFinThreads, 1) k_finalize(const Ctx c, const 
       S.live = m;
       S.total = tot;
     }
+    if ((flags & kFinHyper) && gtid >= 32 && gtid < 64) draw_level_randoms(S, c.seed, c.chain, sweep, V, v, true, 1, 2, gtid - 32);
     group_sync(1, kGroupThreads);
     if (!(flags & kFinTauInit))                 // (the reference's initial values are set by the lower half below)
       level_alpha_sigma(cap, S.l_live, S, gtid, kGroupThreads, 1, (flags & kFinHyper) && (flags & kFinHyperLocal));
@@ -894,29 +925,37 @@ __global__ void __launch_bounds__(kFinThreads, 1) k_finalize(const Ctx c, const 
   } else {
     {
       // one warp per dish k: lanes stride over the coordinates; the tables serving the dish are added in
-      // ascending order (warp-uniform loop), then |S1k|^2 by a fixed shuffle tree
+      // ascending order (warp-uniform loop), then |S1k|^2 by a fixed shuffle tree.  The last warp of this half draws the
+      // tau step's Philox numbers meanwhile.
       const int lane = tid & 31, wid = tid >> 5;
-      for (int k = wid; k < cap; k += kGroupThreads / 32) {
-        double* S1k_vk = c.S1k + (size_t)cap * doff + (size_t)k * D;
-        const unsigned long long mask = S.tmask[k];
-        const int t1 = __ffsll((long long)mask) - 1;             // usually the only table of the dish
-        const unsigned long long more = mask & (mask - 1ull);
-        double q = 0.0;
-        for (int dd = lane; dd < D; dd += 32) {
-          double sum = (t1 >= 0) ? S1t[t1 * D + dd] : 0.0;
-          for (unsigned long long m = more; m; m &= m - 1ull) sum += S1t[(__ffsll((long long)m) - 1) * D + dd];
-          S1k_vk[dd] = sum;
-          q += sum * sum;
-        }
+      constexpr int kStatWarps = kGroupThreads / 32 - 1;
+      if (wid == kStatWarps) {
+        if (flags & kFinHyper) draw_level_randoms(S, c.seed, c.chain, sweep, V, v, true, 0, 0, lane);
+      } else {
+        for (int k = wid; k < cap; k += kStatWarps) {
+          double* S1k_vk = c.S1k + (size_t)cap * doff + (size_t)k * D;
+          const unsigned long long mask = S.tmask[k];
+          const int t1 = __ffsll((long long)mask) - 1;             // usually the only table of the dish
+          const unsigned long long more = mask & (mask - 1ull);
+          double q = 0.0;
+          for (int dd = lane; dd < D; dd += 32) {
+            double sum = (t1 >= 0) ? S1t[t1 * D + dd] : 0.0;
+            for (unsigned long long m = more; m; m &= m - 1ull) sum += S1t[(__ffsll((long long)m) - 1) * D + dd];
+            S1k_vk[dd] = sum;
+            q += sum * sum;
+          }
 #pragma unroll
-        for (int o = 16; o > 0; o >>= 1) q += __shfl_xor_sync(0xffffffffu, q, o);
-        if (lane == 0) {
-          S.s1sq[k] = q;
-          const int n_k = S.n_vk[k];
-          double sse = (n_k > 0) ? S.s2k[k] - q / (double)n_k : 0.0;
-          S.sse[k] = sse < 0.0 ? 0.0 : sse;
+          for (int o = 16; o > 0; o >>= 1) q += __shfl_xor_sync(0xffffffffu, q, o);
+          if (lane == 0) S.s1sq[k] = q;
         }
       }
+    }
+    group_sync(2, kGroupThreads);
+    // sums of squared errors, one thread per dish (the FP64 divisions side by side instead of one per warp step)
+    if (tid < cap) {
+      const int n_k = S.n_vk[tid];
+      const double sse = (n_k > 0) ? S.s2k[tid] - S.s1sq[tid] / (double)n_k : 0.0;
+      S.sse[tid] = sse < 0.0 ? 0.0 : sse;
     }
     group_sync(2, kGroupThreads);
     stamp(2);
@@ -976,6 +1015,13 @@ __global__ void __launch_bounds__(kFinThreads, 1) k_finalize(const Ctx c, const 
         const int k = S.dish[t];
         const int off = cap * doff + t * D;
         const double rden = (k >= 0) ? 1.0 / (tau_l + (double)S.n_vk[k]) : 0.0;
+        // The tensor-core engine reads the means pre-scaled by the table's slope, b = 2 A m, so that its dot products
+        // are the data term 2 A x.m of log2 f directly (A as in the parameter block below: same expression, same value).
+        float A_f = 0.f;
+        if (k >= 0 && !is_count) {
+          const double nk = (double)S.n_vk[k];
+          A_f = (float)(kLog2e * ((tau_l + nk) / (2.0 * tau_l * (tau_l + nk + 1.0))));
+        }
         const unsigned long long mask = (k >= 0) ? S.tmask[k] : 0ull;
         const int t1 = __ffsll((long long)mask) - 1;
         const unsigned long long more = mask & (mask - 1ull);
@@ -986,10 +1032,11 @@ __global__ void __launch_bounds__(kFinThreads, 1) k_finalize(const Ctx c, const 
           const float m = (float)(s1 * rden);
           c.mean[off + dd] = m;
           if (c.mean_hi) {
+            const float bm = (float)(2.0 * (double)A_f * (double)m);    // one rounding of the exact product (the mirror repeats it)
             uint32_t hb, lb;                                            // TF32 split, both parts rounded to nearest
-            asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(hb) : "f"(m));
+            asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(hb) : "f"(bm));
             const float hi = __uint_as_float(hb);
-            asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(lb) : "f"(__fadd_rn(m, -hi)));
+            asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(lb) : "f"(__fadd_rn(bm, -hi)));
             c.mean_hi[off + dd] = hi;
             c.mean_lo[off + dd] = __uint_as_float(lb);
           }

@@ -22,6 +22,13 @@
 // a CTA per table, then k_reduce adds the CTAs in ascending order in FP64.  Counts are integers (popc of the
 // ballots) and exact.
 //
+// DELTA mode (incremental statistics, what the reference's remove_customer / add_customer do:
+// multiview_utils.cpp:151-163, 199-206): only the 64-row tiles that contain a row whose draw differs from its table
+// (movedmask, written by the draw kernel) are fetched; a moved row is added to its new table and subtracted from its
+// old one, so the per-CTA partials hold the CHANGE of the statistics and k_reduce_x adds it to the shard's running
+// FP64 sums.  With nothing moved the kernel reads the 4 bytes of mask per 32 rows and nothing else; with everything
+// moved it costs what the full rebuild costs.  Same row -> CTA -> warp mapping, same fixed order.
+//
 // HBM traffic: the features once (N*V*256 B), 4 B of squared norm per (row, view), 4 B read + 4 B written of
 // assignment per row.  Replaces the rebuild loop of /root/reference/Multiview/multiview_gibbs.cpp:64-73 (and
 // the incremental updates of multiview_utils.cpp:151-163, 199-206) for this shape.
@@ -37,6 +44,7 @@ constexpr int kAccWarps = 16;             // x 4 tables = cap 64
 constexpr int kTabPerWarp = 4;
 constexpr int kThreadsST = (kAccWarps + 2) * 32;
 constexpr int kMaxV = 3;
+constexpr int kMaxAct = 2048;             // DELTA: tiles per CTA the list of active tiles can hold (8 KB)
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
@@ -79,13 +87,17 @@ struct Stage {
   float xx[kMaxV + 1][kTile]; // squared norms of the rows (row V.. unused), one bulk copy per view
   int32_t raw[kTile];         // the sweep's raw draws (bulk copy)
   int32_t tab[kTile];         // resolved table of each row; < 0: nothing to add
+  int32_t old[kTile];         // DELTA: the table each row sat at before the sweep (bulk copy)
+  int32_t tabold[kTile];      // DELTA: the table a moved row leaves; < 0: nothing to subtract
 };
 
-template <int V>
+template <int V, bool DELTA>
 __global__ void __launch_bounds__(kThreadsST, 1) k_stats_tile(const Ctx c) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   Stage<V>* st = reinterpret_cast<Stage<V>*>(smem_raw);
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw + sizeof(Stage<V>) * kStages);   // full, ready, empty [kStages] each
+  int32_t* act = reinterpret_cast<int32_t*>(bars + 3 * kStages);                          // DELTA: [kMaxAct] active tiles, ascending
+  __shared__ int s_nact;
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
 
   const int n_tiles = (c.n_rows + kTile - 1) / kTile;
@@ -101,22 +113,41 @@ __global__ void __launch_bounds__(kThreadsST, 1) k_stats_tile(const Ctx c) {
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
+  if (DELTA && wid == 0) {
+    // the tiles of this CTA's range with at least one moved row, in ascending order (a 64-row tile = two mask words)
+    int n = 0;
+    for (int base = t_lo; base < t_hi; base += 32) {
+      const int tile = base + lane;
+      bool any = false;
+      if (tile < t_hi) {
+        const int ch = 2 * tile;
+        any = (c.movedmask[ch] | ((ch + 1 < c.n_chunks) ? c.movedmask[ch + 1] : 0u)) != 0u;
+      }
+      const unsigned m = __ballot_sync(0xffffffffu, any);
+      if (any) act[n + __popc(m & ((1u << lane) - 1u))] = tile;
+      n += __popc(m);
+    }
+    if (lane == 0) s_nact = n;
+  }
   __syncthreads();
+  const int n_iter = DELTA ? s_nact : (t_hi - t_lo);
 
   if (wid == kAccWarps) {
     // ---------------- producer: one lane keeps the ring full ----------------
     if (lane == 0) {
       uint64_t policy;
       asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(policy));
-      for (int tile = t_lo, k = 0; tile < t_hi; ++tile, ++k) {
+      for (int k = 0; k < n_iter; ++k) {
+        const int tile = DELTA ? act[k] : (t_lo + k);
         const int s = k % kStages;
         const uint32_t full = smem_u32(&bars[s]);
         if (k >= kStages) mbar_wait(smem_u32(&bars[2 * kStages + s]), ((k / kStages) - 1) & 1);
         const int row0 = tile * kTile;
         const int valid = min(kTile, c.n_rows - row0);
         const uint32_t small = (uint32_t)((valid + 3) & ~3) * 4u;       // whole 16-byte groups (arrays are padded)
-        mbar_expect_tx(full, (uint32_t)(V * valid * 256) + (uint32_t)(V + 1) * small);
+        mbar_expect_tx(full, (uint32_t)(V * valid * 256) + (uint32_t)(V + 1 + (DELTA ? 1 : 0)) * small);
         bulk_load(smem_u32(&st[s].raw[0]), c.choice + row0, small, full);
+        if (DELTA) bulk_load(smem_u32(&st[s].old[0]), c.table_cur + row0, small, full);
 #pragma unroll
         for (int v = 0; v < V; ++v) {
           bulk_load(smem_u32(&st[s].xx[v][0]), c.xx + (size_t)v * c.xx_stride + row0, small, full);
@@ -127,26 +158,34 @@ __global__ void __launch_bounds__(kThreadsST, 1) k_stats_tile(const Ctx c) {
   } else if (wid == kAccWarps + 1) {
     // ---------------- resolver: raw draws -> the table each row now sits at ----------------
     const int nfree = c.gparam->nfree;
-    for (int tile = t_lo, k = 0; tile < t_hi; ++tile, ++k) {
+    for (int k = 0; k < n_iter; ++k) {
+      const int tile = DELTA ? act[k] : (t_lo + k);
       const int s = k % kStages;
       mbar_wait(smem_u32(&bars[s]), (k / kStages) & 1);
       const int row0 = tile * kTile;
 #pragma unroll
       for (int hf = 0; hf < 2; ++hf) {
         const int r = hf * 32 + lane, row = row0 + r;
-        int t = -3;
+        int t = -3, told = -3;
         if (row < c.n_rows) {
           t = st[s].raw[r];
+          const int cur = DELTA ? st[s].old[r] : 0;
           if (t == kNewTable) {                            // a birth: seated (candidate, -2) or overflow (stays put)
             const int ch = row >> 5;                       // row0 is a multiple of 64: a chunk is one half of the tile
             const unsigned m = c.birthmask[ch];
             const int rank = c.chunk_prefix[ch] + __popc(m & ((1u << lane) - 1u));
-            t = (rank < nfree) ? -2 : c.table_cur[row];
+            t = (rank < nfree) ? -2 : (DELTA ? cur : c.table_cur[row]);
             c.choice[row] = t;
           }
-          if (t >= 0) c.table_cur[row] = t;
+          if (DELTA) {
+            if (t != cur) { told = cur; if (t >= 0) c.table_cur[row] = t; }   // a move: leaves `cur` (a seated birth joins its new table in k_finalize)
+            else t = -3;                                                       // stays: nothing to add, nothing to subtract
+          } else if (t >= 0) {
+            c.table_cur[row] = t;
+          }
         }
         st[s].tab[r] = t;
+        if (DELTA) st[s].tabold[r] = told;
       }
       mbar_arrive(smem_u32(&bars[kStages + s]));
     }
@@ -163,12 +202,13 @@ __global__ void __launch_bounds__(kThreadsST, 1) k_stats_tile(const Ctx c) {
       for (int v = 0; v < V; ++v) acc[j][v] = make_float2(0.0f, 0.0f);
     }
     const int tbase = wid * kTabPerWarp;
-    for (int tile = t_lo, k = 0; tile < t_hi; ++tile, ++k) {
+    for (int k = 0; k < n_iter; ++k) {
       const int s = k % kStages;
       mbar_wait(smem_u32(&bars[s]), (k / kStages) & 1);              // features and squared norms have landed
       mbar_wait(smem_u32(&bars[kStages + s]), (k / kStages) & 1);    // and the rows' tables are resolved
       const Stage<V>& S = st[s];
       const int ta = S.tab[lane], tb = S.tab[32 + lane];
+      const int oa = DELTA ? S.tabold[lane] : -3, ob = DELTA ? S.tabold[32 + lane] : -3;
 #pragma unroll
       for (int j = 0; j < kTabPerWarp; ++j) {
         unsigned ma = __ballot_sync(0xffffffffu, ta == tbase + j);
@@ -187,6 +227,26 @@ __global__ void __launch_bounds__(kThreadsST, 1) k_stats_tile(const Ctx c) {
               acc[j][v].y = __fadd_rn(acc[j][v].y, xv.y);
             }
             s2[j] = __fadd_rn(s2[j], S.xx[lane & 3][r]);      // lane v < V keeps view v's sum; the others are ignored
+          }
+        }
+        if (DELTA) {                                          // the rows that left this table, after the arrivals
+          unsigned na = __ballot_sync(0xffffffffu, oa == tbase + j);
+          unsigned nb = __ballot_sync(0xffffffffu, ob == tbase + j);
+          cnt[j] -= __popc(na) + __popc(nb);
+#pragma unroll
+          for (int hf = 0; hf < 2; ++hf) {
+            unsigned m = hf ? nb : na;
+            while (m) {
+              const int r = hf * 32 + __ffs(m) - 1;
+              m &= m - 1;
+#pragma unroll
+              for (int v = 0; v < V; ++v) {
+                const float2 xv = *reinterpret_cast<const float2*>(&S.x[v][r][2 * lane]);
+                acc[j][v].x = __fadd_rn(acc[j][v].x, -xv.x);
+                acc[j][v].y = __fadd_rn(acc[j][v].y, -xv.y);
+              }
+              s2[j] = __fadd_rn(s2[j], -S.xx[lane & 3][r]);
+            }
           }
         }
       }
@@ -209,12 +269,12 @@ __global__ void __launch_bounds__(kThreadsST, 1) k_stats_tile(const Ctx c) {
   }
 }
 
-template <int V>
+template <int V, bool DELTA>
 cudaError_t launch_v(const Ctx& c, cudaStream_t s) {
-  const int smem = (int)sizeof(Stage<V>) * kStages + 3 * kStages * 8;
-  cudaError_t e = cudaFuncSetAttribute(k_stats_tile<V>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+  const int smem = (int)sizeof(Stage<V>) * kStages + 3 * kStages * 8 + (DELTA ? kMaxAct * 4 : 0);
+  cudaError_t e = cudaFuncSetAttribute(k_stats_tile<V, DELTA>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
   if (e != cudaSuccess) return e;
-  k_stats_tile<V><<<c.stat_ctas, kThreadsST, smem, s>>>(c);
+  k_stats_tile<V, DELTA><<<c.stat_ctas, kThreadsST, smem, s>>>(c);
   return cudaGetLastError();
 }
 
@@ -227,11 +287,24 @@ bool stats_tile_supported(const Ctx& c) {
   return true;
 }
 
-cudaError_t launch_stats_tile(const Ctx& c, cudaStream_t s) {
+bool stats_delta_supported(const Ctx& c) {
+  if (!stats_tile_supported(c) || c.stat_ctas <= 0) return false;
+  const int n_tiles = (c.n_rows + kTile - 1) / kTile;
+  return (n_tiles + c.stat_ctas - 1) / c.stat_ctas <= kMaxAct;
+}
+
+cudaError_t launch_stats_tile(const Ctx& c, bool delta, cudaStream_t s) {
+  if (delta) {
+    switch (c.V) {
+      case 1: return launch_v<1, true>(c, s);
+      case 2: return launch_v<2, true>(c, s);
+      default: return launch_v<3, true>(c, s);
+    }
+  }
   switch (c.V) {
-    case 1: return launch_v<1>(c, s);
-    case 2: return launch_v<2>(c, s);
-    default: return launch_v<3>(c, s);
+    case 1: return launch_v<1, false>(c, s);
+    case 2: return launch_v<2, false>(c, s);
+    default: return launch_v<3, false>(c, s);
   }
 }
 

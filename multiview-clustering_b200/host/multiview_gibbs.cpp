@@ -10,6 +10,7 @@
 #include "../../include/mvg.h"
 #include "multiview_hyper.h"
 #include "multiview_state.h"
+#include "multiview_utils.h"
 
 void mvhost_rcpp_stop(const std::string& msg) { Rcpp::stop(msg); }
 
@@ -25,19 +26,6 @@ static void initialize_state_from_data() {
   saved_alpha_global.clear(); saved_sigma_global.clear();
 }
 
-// save_state of the reference (multiview_utils.cpp:291-303) on the mirrored state
-static void save_mirrored_state() {
-  saved_table_of.push_back(table_of);
-  saved_dish_of.push_back(dish_of);
-  for (int v = 0; v < d; ++v) {
-    saved_alpha_v[(size_t)v].push_back(views[(size_t)v].alpha_v);
-    saved_sigma_v[(size_t)v].push_back(views[(size_t)v].sigma_v);
-    saved_tau_v[(size_t)v].push_back(views[(size_t)v].tau_v);
-  }
-  saved_alpha_global.push_back(alpha_global);
-  saved_sigma_global.push_back(sigma_global);
-}
-
 // multiview_gibbs.cpp:134-212.  One mvg_sweep = the loop over all customers (:157-200) followed by
 // update_hyperparameters (:202); launches are asynchronous, the device is only read on kept sweeps.
 void gibbs_sampler(int M, int burn_in, int thin) {
@@ -48,7 +36,7 @@ void gibbs_sampler(int M, int burn_in, int thin) {
     if (mvg_sweep(mvhost::chain(), 1, 1) != MVG_OK) mvhost::fail("gibbs_sampler");
     if (iter >= burn_in && ((iter - burn_in) % thin == 0)) {                                       // :205
       mvhost::pull_state();
-      save_mirrored_state();
+      save_state();                                  // multiview_utils.cpp:291-303 (+ saved_loglik)
     }
   }
   mvhost::pull_state();

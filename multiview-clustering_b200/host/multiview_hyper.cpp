@@ -4,7 +4,7 @@
 #include <limits>
 
 #include "../../include/mvg.h"
-#include "multiview_rng.h"
+#include "multiview_utils.h"   // rnorm_scalar, uniform01 (as multiview_hyper.cpp:10 of the reference)
 
 namespace {
 constexpr double kEps = 1e-6;                        // multiview_hyper.cpp:13
@@ -24,7 +24,7 @@ void initialize_hyperparameters() {
 // :166-174 — log-normal random walk with step 0.3 (host stream; the device draws its own)
 double propose_tau(double tau_old) {
   if (tau_old <= 0.0) tau_old = kEps;
-  return std::exp(std::log(tau_old) + rnorm(0.0, 0.3));
+  return std::exp(std::log(tau_old) + rnorm_scalar(0.0, 0.3));
 }
 
 // :176-209 — Gaussian part from the within-dish sums of squares, InvGamma(2, 1) prior

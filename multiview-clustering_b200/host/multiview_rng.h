@@ -7,6 +7,7 @@
 
 #include <cstdint>
 #include <limits>
+#include <random>
 
 #include "../../include/mvg.h"
 
@@ -24,21 +25,28 @@ struct mv_philox_engine {            // satisfies UniformRandomBitGenerator
   }
 };
 
-inline mv_philox_engine& global_rng() {
+inline mv_philox_engine& philox_rng() {
   static thread_local mv_philox_engine rng;
   return rng;
 }
+// The reference's signature (multiview_rng.h:9): a std::mt19937 for callers that want a standard engine.  It is seeded
+// from the Philox stream (set_rng_seed re-seeds both); uniform01() / rnorm() below do not go through it.
+inline std::mt19937& global_rng() {
+  static thread_local std::mt19937 rng(1999u);
+  return rng;
+}
 inline void set_rng_seed(unsigned int seed) {
-  global_rng().seed = seed;
-  global_rng().calls = 0;
+  philox_rng().seed = seed;
+  philox_rng().calls = 0;
+  global_rng().seed(seed);
 }
 // Uniform(0, 1), 53 bits, never 0 or 1 (domain 6 = call-ordered host stream)
 inline double uniform01() {
-  mv_philox_engine& g = global_rng();
+  mv_philox_engine& g = philox_rng();
   return mvg_philox_uniform_f64(g.seed, 0u, 6u, 0u, 0u, g.calls++);
 }
 // Normal(mean, sd^2) by Box-Muller on one Philox block
 inline double rnorm(double mean, double sd) {
-  mv_philox_engine& g = global_rng();
+  mv_philox_engine& g = philox_rng();
   return mean + sd * mvg_philox_normal(g.seed, 0u, 6u, 1u, 0u, g.calls++);
 }

@@ -90,6 +90,8 @@ def lib():
         L.mvg_get_state.argtypes = [H, C.POINTER(_StateHost)]
         L.mvg_sweep.argtypes = [H, C.c_int32, C.c_int32]
         L.mvg_hyper_step.argtypes = [H]
+        L.mvg_set_sweep_blocks.argtypes = [H, C.c_int32]
+        L.mvg_set_stats_mode.argtypes = [H, C.c_int32, C.c_int32]
         L.mvg_hyper_step_parts.argtypes = [H, C.c_int32]
         L.mvg_sync.argtypes = [H]
         L.mvg_run.argtypes = [H, C.c_int32, C.c_int32, C.c_int32, C.c_int32, _i32p, _i32p, _f64p, _i32p]
@@ -106,6 +108,7 @@ def lib():
         L.mvg_clear_fault.argtypes = [H]
         L.mvg_get_params.argtypes = [H, C.POINTER(_ParamsHost)]
         L.mvg_get_debug_rows.argtypes = [H, _f32p, _f32p, _i32p]
+        L.mvg_get_debug_lnew.argtypes = [H, _f32p]
         L.mvg_get_debug_births.argtypes = [H, _i32p, C.POINTER(C.c_int64), _f64p]
         L.mvg_get_debug_prof.argtypes = [H, C.POINTER(C.c_int64), C.c_int32]
         L.mvg_last_sweep_ms.argtypes = [H, _f32p]
@@ -311,6 +314,14 @@ class Sampler:
     def sweep(self, n=1, do_hyper=True):
         self._ck(self.L.mvg_sweep(self.h, int(n), int(do_hyper)))
 
+    def set_stats_mode(self, incremental, rebuild_every=64):
+        """incremental: only moved rows are re-read each sweep (running FP64 sums, full rebuild every rebuild_every sweeps)."""
+        self._ck(self.L.mvg_set_stats_mode(self.h, 1 if incremental else 0, int(rebuild_every)))
+
+    def set_sweep_blocks(self, blocks):
+        """One sweep = `blocks` passes over row blocks with the statistics refreshed in between (1 = synchronous)."""
+        self._ck(self.L.mvg_set_sweep_blocks(self.h, int(blocks)))
+
     def hyper_step(self):
         self._ck(self.L.mvg_hyper_step(self.h))
 
@@ -425,6 +436,11 @@ class Sampler:
         ch = np.empty(self.n_rows, np.int32)
         self._ck(self.L.mvg_get_debug_rows(self.h, _p(acc, _f32p), _p(xx, _f32p), _p(ch, _i32p)))
         return acc, xx, ch
+
+    def get_debug_lnew(self):
+        out = np.empty(self.n_rows, np.float32)
+        self._ck(self.L.mvg_get_debug_lnew(self.h, _p(out, _f32p)))
+        return out
 
     def get_debug_prof(self, n_ctas=148):
         """Role wait counters of the last tcgen05 draw (needs debug_export & 2): [n_ctas, 16] cycles."""

@@ -760,6 +760,105 @@ int mvo_stageB_f32_mixed(const mvo_params_f32* p, const int32_t* kind, const flo
   return choice;
 }
 
+/* The tensor-core engine's epilogue (multiview-clustering_b200/csrc/mv_draw_tc.cu), restated operation by operation.
+ * acc[v][t] = x_v . b_vt with the PRE-SCALED means b = 2 A m (mvo_scaled_means), so that
+ *     lw[t] = base[t] + sum_v A_vt (-|x_v|^2) + sum_v acc[v][t]        base[t] = LM[t] + sum_v C_vt  (view order)
+ * is the log2 weight of table t with the customer still counted.  Removing it (multiview_utils.cpp:138-192) is a
+ * scalar correction per view from the dot product at its own table t0,
+ *     plain_v = acc[v][t0] + (A_vt0 (-|x_v|^2) + C_vt0),   loo_v = R_vt0 acc[v][t0] + (A1_vt0 (-|x_v|^2) + C1_vt0),
+ *     delta_v = loo_v - plain_v,   R = A1 / A (FP32 division),
+ * added (in view order, then LM1 - LM for t0 itself) to every table serving the same dish as t0 in view v.
+ * lnew_dev: the log2 weight of a new table as the DEVICE evaluated it (a float statistic checked against the FP64
+ * restatement by tolerance; the draw is bit-exact given it).  Then the common draw: global max, exact exp2, half
+ * totals, inverse-CDF scan. */
+static int draw_from_lw_f32(const float* lw, int cap, float lnew, int t0, float uf, float* margin_out) {
+  const int half = cap / 2;
+  float* term = (float*)malloc(sizeof(float) * (size_t)cap);
+  float M = lnew;
+  for (int t = 0; t < cap; ++t) M = fmaxf(M, lw[t]);
+  if (margin_out) *margin_out = 1.0f;
+  int choice = MVO_NEW;
+  if (!(M > -1.0e29f)) {
+    choice = t0;
+  } else {
+    float H[2];
+    for (int h = 0; h < 2; ++h) {
+      float qp[4] = {0.0f, 0.0f, 0.0f, 0.0f};
+      for (int j = 0; j < half; ++j) {
+        const int t = h * half + j;
+        term[t] = mvo_exp2m(lw[t] - M);
+        qp[j & 3] = qp[j & 3] + term[t];
+      }
+      H[h] = (qp[0] + qp[1]) + (qp[2] + qp[3]);
+    }
+    float total = (H[0] + H[1]) + mvo_exp2m(lnew - M);
+    float target = uf * total;
+    float margin = 1.0f;
+    int cnt = 0;
+    for (int h = 0; h < 2; ++h) {
+      float cum = h ? H[0] : 0.0f;
+      for (int j = 0; j < half; ++j) {
+        cum = cum + term[h * half + j];
+        cnt += (target < cum) ? 0 : 1;
+        float dist = fabsf(target - cum) / total;
+        if (dist < margin) margin = dist;
+      }
+    }
+    if (margin_out) *margin_out = margin;
+    choice = (cnt < cap) ? cnt : MVO_NEW;
+    if (cnt >= cap && !(lnew > -1.0e29f)) {
+      choice = t0;
+      for (int t = 0; t < cap; ++t) if (term[t] > 1.0e-30f) choice = t;
+    }
+  }
+  free(term);
+  return choice;
+}
+
+int mvo_stageB_tc(const mvo_params_f32* p, const float* acc, const float* xx, int t0, float uf, float lnew_dev,
+                  float* lw_out, float* margin_out) {
+  const int V = p->V, cap = p->cap;
+  float* lw = (float*)malloc(sizeof(float) * (size_t)cap);
+  float delta[64];
+  if (V > 64) { free(lw); return -2; }
+  for (int t = 0; t < cap; ++t) {
+    float b = p->LM[t];
+    for (int v = 0; v < V; ++v) b = b + p->C[(size_t)v * cap + t];
+    for (int v = 0; v < V; ++v) b = fmaf(p->A[(size_t)v * cap + t], -xx[v], b);
+    for (int v = 0; v < V; ++v) b = b + acc[(size_t)v * cap + t];
+    lw[t] = b;
+  }
+  for (int v = 0; v < V; ++v) {
+    const size_t o = (size_t)v * cap;
+    const float nxx = -xx[v], a = acc[o + t0];
+    const float A = p->A[o + t0];
+    const float R = (A != 0.0f) ? p->A1[o + t0] / A : 0.0f;
+    const float plain = a + fmaf(A, nxx, p->C[o + t0]);
+    const float loo = fmaf(R, a, fmaf(p->A1[o + t0], nxx, p->C1[o + t0]));
+    delta[v] = loo + (-plain);
+  }
+  for (int t = 0; t < cap; ++t) {
+    float c = 0.0f;
+    for (int v = 0; v < V; ++v) {
+      const size_t o = (size_t)v * cap;
+      if (p->dish[o + t] >= 0 && p->dish[o + t] == p->dish[o + t0]) c = c + delta[v];
+    }
+    if (t == t0) c = c + (p->LM1[t0] + (-p->LM[t0]));
+    lw[t] = lw[t] + c;
+  }
+  if (lw_out) { memcpy(lw_out, lw, sizeof(float) * (size_t)cap); lw_out[cap] = lnew_dev; }
+  const int choice = draw_from_lw_f32(lw, cap, lnew_dev, t0, uf, margin_out);
+  free(lw);
+  return choice;
+}
+
+/* b = (float)(2 A m): the B operand of the tensor-core engine for table t of one view, one rounding of the exact
+ * product (k_finalize computes the same expression). */
+void mvo_scaled_means(const float* A, const float* m, int cap, int D, float* b) {
+  for (int t = 0; t < cap; ++t)
+    for (int dd = 0; dd < D; ++dd) b[(size_t)t * D + dd] = (float)(2.0 * (double)A[t] * (double)m[(size_t)t * D + dd]);
+}
+
 int mvo_stageB_f32(const mvo_params_f32* p, const float* acc, const float* xx, int t0, float uf,
                    float* lw_out) {
   return mvo_stageB_f32_ex(p, acc, xx, t0, uf, lw_out, NULL);

@@ -152,6 +152,10 @@ void mvo_stageA_f32(const float* x, int D, const float* m, int cap, float* acc, 
 int mvo_stageB_f32(const mvo_params_f32* p, const float* acc, const float* xx, int t0, float uf,
                    float* lw_out /* cap+1 or NULL */);
 /* Same, also reporting how close u*total came to a CDF edge (relative to total). */
+/* The tensor-core engine's draw stage (pre-scaled means, leave-one-out as a scalar correction); see mv_oracle.c. */
+int mvo_stageB_tc(const mvo_params_f32* p, const float* acc, const float* xx, int t0, float uf, float lnew_dev,
+                  float* lw_out, float* margin_out);
+void mvo_scaled_means(const float* A, const float* m, int cap, int D, float* b);
 int mvo_stageB_f32_ex(const mvo_params_f32* p, const float* acc, const float* xx, int t0, float uf,
                       float* lw_out, float* margin_out);
 /* Same for a mix of dense and count views: kind[v] != 0 marks a count view, for which acc[v][t] is already

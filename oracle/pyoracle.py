@@ -114,6 +114,7 @@ def lib():
         L.mvo_stageB_f32.argtypes = [C.POINTER(_MvoParams), _f32p, _f32p, C.c_int, C.c_float, _f32p]
         L.mvo_stageB_f32_ex.argtypes = [C.POINTER(_MvoParams), _f32p, _f32p, C.c_int, C.c_float, _f32p, _f32p]
         L.mvo_stageB_f32_mixed.argtypes = [C.POINTER(_MvoParams), _i32p, _f32p, _f32p, _f32p, C.c_int, C.c_float, _f32p, _f32p]
+        L.mvo_stageB_tc.argtypes = [C.POINTER(_MvoParams), _f32p, _f32p, C.c_int, C.c_float, C.c_float, _f32p, _f32p]
         L.mvo_stageA_counts_f32.argtypes = [_i32p, _f32p, C.c_int, _f32p, _i32p, C.c_int, C.c_int, C.c_float, C.c_float,
                                             _f32p, _f32p, _f32p]
         L.mvo_make_params.argtypes = ([C.POINTER(_MvoState), _i32p] + [_f32p] * 6 + [_i32p] + [_f32p] * 6
@@ -350,6 +351,28 @@ def stageB_f32(pstruct, acc, xx, t0, uf, want_lw=False):
     ch = lib().mvo_stageB_f32(C.byref(pstruct), _ptr(acc, _f32p), _ptr(xx, _f32p), int(t0), C.c_float(float(uf)),
                               _ptr(lw, _f32p) if want_lw else None)
     return (ch, lw) if want_lw else ch
+
+
+def stageB_tc(pstruct, acc, xx, t0, uf, lnew_dev, want_lw=False, want_margin=False):
+    """Draw stage of the tensor-core engine: acc = dot products with the pre-scaled means, lnew_dev = the device's
+    log2 weight of a new table."""
+    acc = np.ascontiguousarray(acc, np.float32)
+    xx = np.ascontiguousarray(xx, np.float32)
+    lw = np.empty(pstruct.cap + 1, np.float32) if want_lw else None
+    mg = C.c_float()
+    ch = lib().mvo_stageB_tc(C.byref(pstruct), _ptr(acc, _f32p), _ptr(xx, _f32p), int(t0), C.c_float(float(uf)),
+                             C.c_float(float(lnew_dev)), _ptr(lw, _f32p) if want_lw else None, C.byref(mg))
+    out = (ch,)
+    if want_lw:
+        out += (lw,)
+    if want_margin:
+        out += (mg.value,)
+    return out if len(out) > 1 else ch
+
+
+def scaled_means(A, m):
+    """b[t] = float32(2 * A[t] * m[t]) for one view: the tensor-core engine's B operand."""
+    return (2.0 * A.astype(np.float64)[:, None] * m.astype(np.float64)).astype(np.float32)
 
 
 def stageB_f32_mixed(pstruct, kind, acc, xx, acc_loo, t0, uf, want_lw=False):

@@ -10,6 +10,7 @@
 #include "multiview_hyper.h"
 #include "multiview_rng.h"
 #include "multiview_state.h"
+#include "multiview_utils_decl.h"
 
 namespace R {
 double runif(double, double) { return 0.5; }   // unused by the host layer (the device draws from Philox)
@@ -57,5 +58,35 @@ double host_log_posterior_given_tau(int v, double tau) { return log_posterior_gi
 double host_compute_log_likelihood() { return compute_log_likelihood(); }
 int host_final_T() { return T; }
 int host_final_K(int v) { return views[(size_t)v].K; }
+int host_saved_loglik(double* out) { for (size_t s = 0; s < saved_loglik.size(); ++s) out[s] = saved_loglik[s]; return (int)saved_loglik.size(); }
+int host_final_table_of(int* out) { for (int i = 0; i < n; ++i) out[i] = table_of[(size_t)i]; return T; }
+void host_final_dish_of(int v, int* out) { for (int t = 0; t < T; ++t) out[t] = dish_of[(size_t)v][(size_t)t]; }
+void host_final_hypers(double* out) {
+  for (int v = 0; v < d; ++v) { out[v] = views[(size_t)v].alpha_v; out[d + v] = views[(size_t)v].sigma_v; out[2 * d + v] = views[(size_t)v].tau_v; }
+  out[3 * d] = alpha_global; out[3 * d + 1] = sigma_global;
+}
+// compute_table_probs_with_cache / compute_f_vk / compute_f_vk_new on the mirrored state (multiview_utils.h)
+int host_table_probs(int i, double* pe, double* pn) {
+  try {
+    std::vector<double> p;
+    std::vector<std::unordered_map<int, double>> cache;
+    mvu::table_probs(i, p, *pn, cache);
+    for (size_t t = 0; t < p.size(); ++t) pe[t] = p[t];
+    return (int)p.size();
+  } catch (const std::exception& e) { g_err = e.what(); return -1; }
+}
+double host_f_vk(int v, int k, int i) { return mvu::f_vk(v, k, i); }
+double host_f_vk_new(int v, int i) { return mvu::f_vk_new(v, i); }
+int host_mutator_raises(int which) {               // 1 if the call raised (the documented behaviour)
+  try {
+    switch (which) {
+      case 0: mvu::remove(0); break;
+      case 1: mvu::add_existing(0, 0); break;
+      case 2: mvu::new_table(); break;
+      default: mvu::assign_dishes(0, 0); break;
+    }
+  } catch (const std::exception& e) { g_err = e.what(); return 1; }
+  return 0;
+}
 double host_uniform01(unsigned seed, int skip) { set_rng_seed(seed); double u = 0; for (int i = 0; i <= skip; ++i) u = uniform01(); return u; }
 }

@@ -59,14 +59,17 @@ def _check_params(po, o, P):
         np.testing.assert_allclose(P["m"][v], Q["m"][v], rtol=2e-5, atol=1e-6)
 
 
-def _one_sweep_parity(po, s, views, cap, seed, do_hyper, simt_bit_exact=True, fast_weights=False):
-    """Compare ONE device sweep with the oracle started from the device's own pre-sweep state."""
+def _one_sweep_parity(po, s, views, cap, seed, do_hyper, simt_bit_exact=True, fast_weights=False, tc=False):
+    """Compare ONE device sweep with the oracle started from the device's own pre-sweep state.
+    tc: tensor-core engine — acc holds the dot products with the pre-scaled means b = 2 A m and the mirror is
+    mvo_stageB_tc, fed the device's new-table log-weight as well (itself checked against FP64 below)."""
     pre = s.get_state()
     P = s.get_params()
     o = _oracle_from_device(po, views, cap, seed, pre)
     _check_params(po, o, P)
     s.sweep(1, do_hyper=do_hyper)
     acc, xx, raw = s.get_debug_rows()
+    lnew_dev = s.get_debug_lnew() if tc else None
     n = o.n
     # ---- stage A
     ps = po.params_struct(P)
@@ -80,13 +83,19 @@ def _one_sweep_parity(po, s, views, cap, seed, do_hyper, simt_bit_exact=True, fa
                 a, q = po.stageA_f32(o.views[v][i], P["m"][v])
                 assert np.array_equal(a, acc[i, v]) and q == xx[i, v], (i, v)
         u = L.mvo_uf(seed, 0, 0, 0, pre["sweep"], i)
-        ch, lw32 = po.stageB_f32(ps, acc[i], xx[i], pre["table_of"][i], u, want_lw=True)
+        if tc:
+            ch, lw32 = po.stageB_tc(ps, acc[i], xx[i], pre["table_of"][i], u, lnew_dev[i], want_lw=True)
+        else:
+            ch, lw32 = po.stageB_f32(ps, acc[i], xx[i], pre["table_of"][i], u, want_lw=True)
         if not fast_weights:
             assert ch == raw[i], (i, ch, raw[i])                # integer draw: bit-exact
         elif ch != raw[i]:
             # MUFU weights (<= 2 ulp each): a draw may differ from the mirrored one only when u*total
             # fell within rounding distance of a CDF edge, and then only to the neighbouring option
-            _, margin = po.stageB_f32_margin(ps, acc[i], xx[i], pre["table_of"][i], u)
+            if tc:
+                _, margin = po.stageB_tc(ps, acc[i], xx[i], pre["table_of"][i], u, lnew_dev[i], want_margin=True)
+            else:
+                _, margin = po.stageB_f32_margin(ps, acc[i], xx[i], pre["table_of"][i], u)
             assert margin < 1e-5, (i, ch, raw[i], margin)
             flips += 1
         if i % 7 == 0:
@@ -231,32 +240,88 @@ def test_run_gibbs_posterior_summaries_match_reference(oracle):
 # tcgen05 engine (MVG_ENGINE_TCGEN05): stage A runs on the tensor cores (3-pass TF32 split), so the
 # dot products are tolerance-level; everything downstream of them is bit-exact against the mirror.
 # ---------------------------------------------------------------------------------------------
-@pytest.mark.parametrize("n,k_true,engine,n_views", [(900, 6, 2, 3), (128 * 148 + 77, 40, 2, 3), (128 * 148 * 2 + 5, 40, 3, 3),
-                                                     (700, 5, 3, 3), (128 * 5 + 9, 6, 2, 1), (128 * 149 + 3, 12, 2, 2)])
-def test_tcgen05_engine_parity(oracle, n, k_true, engine, n_views):
+@pytest.mark.parametrize("n,k_true,engine,n_views,own_dishes", [
+    (900, 6, 2, 3, False), (128 * 148 + 77, 40, 2, 3, False), (128 * 148 * 2 + 5, 40, 3, 3, False), (700, 5, 3, 3, False),
+    (128 * 5 + 9, 6, 2, 1, False), (128 * 149 + 3, 12, 2, 2, False),
+    # every table its own dish (the kernel's fast path: the leave-one-out correction touches the own table only),
+    # with free slots (new-table marginal evaluated) and at full capacity (skipped)
+    (128 * 148 + 77, 40, 2, 3, True), (128 * 20 + 5, 64, 2, 3, True), (128 * 7 + 1, 60, 3, 2, True)])
+def test_tcgen05_engine_parity(oracle, n, k_true, engine, n_views, own_dishes):
     dims, cap = [64] * n_views, 64
     views, z = make_mixture(n, dims, k_true, seed=11)
     s = _mk_sampler(views, cap, seed=123, engine=engine)
     rng = np.random.default_rng(2)
     tab = np.where(rng.random(n) < 0.15, rng.integers(0, k_true, n), z).astype(np.int32)
-    tab[:3] = [k_true + 1, k_true + 2, k_true + 3]                   # three customers alone at their tables
     V = n_views
     dish = np.full((V, cap), -1, np.int32)
-    for t in range(k_true + 4):
-        dish[:, t] = rng.integers(0, max(2, k_true - 1), 3)[:V]
+    if own_dishes:
+        tab[:k_true] = np.arange(k_true)                             # every table occupied
+        dish[:, :k_true] = np.arange(k_true)
+    else:
+        tab[:3] = [k_true + 1, k_true + 2, k_true + 3]               # three customers alone at their tables
+        for t in range(k_true + 4):
+            dish[:, t] = rng.integers(0, max(2, k_true - 1), 3)[:V]
     s.set_state(tab, dish, np.full(V, 1.0), np.full(V, 0.5), np.full(V, 0.9), 1.0, 0.6, sweep=3)
     for it in range(3):
         P = s.get_params()
         _one_sweep_parity(oracle, s, views, cap, 123, do_hyper=(it % 2 == 0), simt_bit_exact=False,
-                          fast_weights=(engine == 3))
+                          fast_weights=(engine == 3), tc=True)
         acc, xx, _ = s.get_debug_rows()
-        for v in range(V):                                           # stage A against FP64
-            x64, m64 = views[v].astype(np.float64), P["m"][v].astype(np.float64)
-            ref = x64 @ m64.T
-            bound = np.abs(x64) @ np.abs(m64).T
+        for v in range(V):                                           # stage A against FP64: x . b with b = float32(2 A m)
+            x64, b64 = views[v].astype(np.float64), oracle.scaled_means(P["A"][v], P["m"][v]).astype(np.float64)
+            ref = x64 @ b64.T
+            bound = np.abs(x64) @ np.abs(b64).T
             assert np.max(np.abs(acc[:, v, :] - ref) / (bound + 1e-30)) < 2.0 ** -18     # measured 1.9e-6: the tensor core truncates when it aligns addends
             np.testing.assert_allclose(xx[:, v], (x64 * x64).sum(1), rtol=1e-6)
     s.close()
+
+
+def test_incremental_statistics_parity_and_agreement_with_rebuild(oracle):
+    """MVG_STATS_INCREMENTAL: only moved rows are re-read (added to their new table, subtracted from their old one) into
+    running FP64 sums.  (1) Every sweep still passes the one-sweep parity check against the oracle (counts exact, sums
+    <= 1e-5, births seated identically); (2) a chain run incrementally stays with the chain that rebuilds every sweep:
+    identical counts, sums to 1e-9, assignments identical but for draws on a CDF edge."""
+    n, k_true, cap, V = 128 * 148 + 77, 40, 64, 3
+    views, z = make_mixture(n, [64] * V, k_true, seed=21, spread=1.2)          # overlapping clusters: rows keep moving
+    rng = np.random.default_rng(5)
+    tab = np.where(rng.random(n) < 0.3, rng.integers(0, k_true, n), z).astype(np.int32)
+    dish = np.full((V, cap), -1, np.int32)
+    dish[:, :k_true] = np.arange(k_true)
+    hyp = (np.full(V, 1.0), np.full(V, 0.5), np.full(V, 0.9), 1.0, 0.6)
+    a = _mk_sampler(views, cap, seed=9, engine=2)
+    b = _mk_sampler(views, cap, seed=9, engine=2)
+    b.set_stats_mode(True, rebuild_every=1000)
+    a.set_state(tab, dish, *hyp)
+    b.set_state(tab, dish, *hyp)
+    moved_total = 0
+    for it in range(6):
+        if it in (1, 4):
+            _one_sweep_parity(oracle, b, views, cap, 9, do_hyper=True, simt_bit_exact=False, tc=True)
+            a.sweep(1, do_hyper=True)
+        else:
+            a.sweep(1, do_hyper=True)
+            b.sweep(1, do_hyper=True)
+        sa, sb = a.get_state(), b.get_state()
+        np.testing.assert_array_equal(sa["n_t"].sum(), n)
+        agree = float((sa["table_of"] == sb["table_of"]).mean())
+        assert agree > 0.9995, (it, agree)
+        if agree == 1.0:
+            np.testing.assert_array_equal(sa["n_t"], sb["n_t"])
+            np.testing.assert_array_equal(sa["n_vk"], sb["n_vk"])
+            for v in range(V):
+                np.testing.assert_allclose(sb["S1"][v], sa["S1"][v], rtol=1e-6, atol=1e-3)
+            np.testing.assert_allclose(sb["sum_y2"], sa["sum_y2"], rtol=1e-6)
+        moved_total += int((sb["table_of"] != tab).sum())
+        tab = sb["table_of"]
+    assert moved_total > n // 20, moved_total            # the test did exercise moves
+    # and the incremental sums equal a from-scratch FP64 rebuild of the final assignment
+    o = oracle.OracleState(views, cap, seed=9)
+    fin = b.get_state()
+    o.set_assignment(fin["table_of"], fin["dish_of"])
+    np.testing.assert_array_equal(fin["n_t"], o.n_t)
+    for v in range(V):
+        np.testing.assert_allclose(fin["S1"][v], o.S1[v], rtol=RTOL_STATS, atol=1e-4)
+    a.close(); b.close()
 
 
 def test_tile_statistics_match_general_kernel(oracle, monkeypatch):

@@ -17,9 +17,10 @@ OUT = ROOT / "tests" / "_build" / "libmvhost_test.so"
 
 def build_host():
     OUT.parent.mkdir(exist_ok=True)
-    srcs = [str(HOST / f) for f in ("multiview_gibbs.cpp", "multiview_hyper.cpp", "multiview_state.cpp")]
+    srcs = [str(HOST / f) for f in ("multiview_gibbs.cpp", "multiview_hyper.cpp", "multiview_state.cpp", "multiview_utils.cpp")]
     cmd = ["g++", "-O2", "-fPIC", "-std=c++17", "-Wall", "-DMVHOST_WITH_RCPP", f"-I{ROOT / 'oracle' / 'refshim'}", f"-I{HOST}",
-           "-shared", "-o", str(OUT), *srcs, str(ROOT / "tests" / "host_shim.cpp"),
+           f"-I{ROOT / 'tests'}", "-shared", "-o", str(OUT), *srcs, str(ROOT / "tests" / "host_shim.cpp"),
+           str(ROOT / "tests" / "host_shim_utils.cpp"),
            f"-L{ROOT / 'multiview-clustering_b200' / 'mvc_b200'}", "-lmvg_b200",
            f"-Wl,-rpath,{ROOT / 'multiview-clustering_b200' / 'mvc_b200'}"]
     subprocess.run(cmd, check=True, capture_output=True, text=True)
@@ -35,7 +36,11 @@ def test_host_layer_compiles_and_keeps_the_reference_names():
     for name in ["run_gibbs_cpp(Rcpp::List const&, int, int, int)", "gibbs_sampler(int, int, int)", "update_hyperparameters()",
                  "update_tau_v_MH()", "log_EPPF(int, double, double)", "log_prior_alpha(double)", "log_prior_sigma(double)",
                  "log_posterior_given_tau(int, double)", "propose_tau(double)", "initialize_hyperparameters()",
-                 "compute_log_likelihood()", "table_of", "dish_of", "views", "saved_table_of", "alpha_global", "sigma_global"]:
+                 "compute_log_likelihood()", "compute_f_vk(int, int, int)", "compute_f_vk_new(int, int)",
+                 "compute_table_probs_with_cache(int, std::vector<double", "remove_customer(int)",
+                 "add_customer_to_existing_table(int, int)", "create_empty_table()", "add_customer_to_new_table(int, int)",
+                 "sample_dish_for_new_table(int, int)", "assign_dishes_new_table(int, int)", "save_state()", "uniform01()",
+                 "rnorm_scalar(double, double)", "ensure_global_variances_calculated()", "saved_loglik", "table_of", "dish_of", "views", "saved_table_of", "alpha_global", "sigma_global"]:
         assert name in syms, name
 
 
@@ -82,3 +87,42 @@ def test_run_gibbs_cpp_through_the_host_layer_equals_the_c_abi_chain():
     L.host_log_EPPF.restype = C.c_double
     assert np.isfinite(L.host_compute_log_likelihood())
     assert np.isfinite(L.host_log_EPPF(0, C.c_double(1.0), C.c_double(0.5)))
+
+
+@pytest.mark.gpu
+def test_utils_inspectors_on_the_mirrored_state_equal_the_compiled_reference(oracle):
+    """multiview_utils.h over the device chain: compute_table_probs_with_cache / compute_f_vk on the state mirrored from
+    the GPU give what the UNMODIFIED reference (oracle/_ref/libmvref.so) gives for the same state; saved_loglik is
+    filled on every kept sweep; the single-customer mutators raise."""
+    if not oracle.have_ref():
+        pytest.skip("compiled reference not available")
+    views, _ = c1_data(300)
+    y = np.ascontiguousarray(np.stack([v.astype(np.float64) for v in views]))
+    L = build_host()
+    L.host_last_error.restype = C.c_char_p
+    S = L.host_run(300, 2, y.ctypes.data_as(C.POINTER(C.c_double)), 40, 30, 5, 32, C.c_ulonglong(7))
+    assert S == 2, L.host_last_error()
+    ll = np.empty(8)
+    assert L.host_saved_loglik(ll.ctypes.data_as(C.POINTER(C.c_double))) == S and np.all(np.isfinite(ll[:S])) and np.all(ll[:S] < 0)
+    tab = np.empty(300, np.int32)
+    T = L.host_final_table_of(tab.ctypes.data_as(C.POINTER(C.c_int)))
+    dish = np.empty((2, T), np.int32)
+    for v in range(2):
+        row = np.empty(T, np.int32)
+        L.host_final_dish_of(v, row.ctypes.data_as(C.POINTER(C.c_int)))
+        dish[v] = row
+    hyp = np.empty(8)
+    L.host_final_hypers(hyp.ctypes.data_as(C.POINTER(C.c_double)))
+    K = np.array([dish[v].max() + 1 for v in range(2)], np.int32)
+    oracle.ref_load(y, tab, dish, K, hyp[0:2], hyp[2:4], hyp[4:6], hyp[6], hyp[7])
+    L.host_f_vk.restype = C.c_double
+    L.host_f_vk_new.restype = C.c_double
+    for i in (0, 17, 150, 299):
+        pe, pn = oracle.ref_table_probs(i, T)
+        hpe, hpn = np.zeros(T), C.c_double()
+        assert L.host_table_probs(i, hpe.ctypes.data_as(C.POINTER(C.c_double)), C.byref(hpn)) == T, L.host_last_error()
+        # the mirror holds the device's FP32-tree sums: the statistics agree to 1e-5, so do the weights
+        np.testing.assert_allclose(hpe, pe, rtol=2e-4, atol=1e-300)
+        np.testing.assert_allclose(hpn.value, pn, rtol=2e-4)
+    for which in range(4):
+        assert L.host_mutator_raises(which) == 1 and b"not supported on the device chain" in L.host_last_error()
