@@ -58,7 +58,7 @@ constexpr int kLoCol0 = kDStages * 64;              // first TMEM column of the 
 constexpr int kMaxTcViews = 3;
 constexpr int kThreads = 896;                       // WG0: control, WG1+WG2: converters (one per K-half), WG3..WG6: epilogue
 constexpr int kMmaWarps = 2;                        // MMA-issuing warps of WG0; tile-view i belongs to warp 1 + i % 2
-constexpr int kExFields = 15;                       // scalars two epilogue threads of one customer trade per tile
+constexpr int kExFields = 16;                       // scalars two epilogue threads of one customer trade per tile
 constexpr int kEpiGroups = 2;
 
 struct __align__(64) TcMaps {
@@ -717,6 +717,15 @@ __global__ void __launch_bounds__(kThreads, 1) k_draw_tc(const Ctx c, const __gr
         hmax = fmaxf(M0, M1);
       }
       ex_own[9 * kTileRows] = hmax;
+      // which tables of this half lie within 2^-32 of its best one (see the shortcut below)
+      uint32_t nmask = 0u;
+      {
+        const float thr = __fadd_rn(hmax, -32.0f);
+        const float* lw = reinterpret_cast<const float*>(lw2);
+#pragma unroll
+        for (int q = 0; q < 32; ++q) if (lw[q] > thr) nmask |= 1u << q;
+      }
+      ex_own[15 * kTileRows] = __uint_as_float(nmask);
       phase(2);
       rendezvous();                                   // #1: dish sums, own-dish terms, half maxima, the uniform
       phase(3);
@@ -738,6 +747,23 @@ __global__ void __launch_bounds__(kThreads, 1) k_draw_tc(const Ctx c, const __gr
       const float M = hf ? fmaxf(fmaxf(lnew, hoth), hmax) : fmaxf(fmaxf(lnew, hmax), hoth);
       int choice = t0;                                // nothing has weight: stay (cf. multiview_gibbs.cpp:172-176)
       const bool any_weight = (M > -1.0e29f);         // identical in both threads of the customer
+      // Shortcut.  If ONE option (a table or the new table) beats every other by more than 32 in log2, the draw below is
+      // that option for every uniform the stream can produce: the other weights sum to < 2^-26, so in FP32 the winner's
+      // half total, the grand total and hence the target are exactly 1, 1 and u; every cumulative sum before the winner is
+      // < 2^-26 < 2^-24 <= u and from the winner on it is 1 > u.  So the inverse-CDF scan — and the CPU mirror, which
+      // always runs it — returns the winner, and the exponentials, totals and the scan can be skipped.  Both threads of a
+      // customer decide from the same exchanged values (half maxima, near masks, lnew), and a warp skips only when all
+      // its customers can, so the rendezvous counts of the two warps stay equal.
+      const uint32_t nm_oth = __float_as_uint(ex_oth[15 * kTileRows]);
+      const float near_thr = __fadd_rn(M, -32.0f);
+      const int near_own = (hmax == M) ? __popc(nmask) : ((hmax > near_thr) ? 2 : 0);
+      const int near_oth = (hoth == M) ? __popc(nm_oth) : ((hoth > near_thr) ? 2 : 0);
+      const bool sure = any_weight && (near_own + near_oth + ((lnew > near_thr) ? 1 : 0)) == 1;
+      const bool all_sure = __all_sync(0xffffffffu, sure);
+      if (all_sure) {
+        if (hf == 0) choice = (hmax == M) ? (__ffs(nmask) - 1) : ((hoth == M) ? (32 + __ffs(nm_oth) - 1) : kNewTable);
+        rendezvous();                                 // the partner has read this tile's exchange fields before the next tile's are written
+      } else {
       float Hown = 0.0f;
       if (any_weight) {                               // lw2 <- 2^(lw2 - M); this half's total (partial sums over t mod 4, fixed tree)
         const float2 nM2 = splat2(-M);
@@ -783,8 +809,8 @@ __global__ void __launch_bounds__(kThreads, 1) k_draw_tc(const Ctx c, const __gr
       phase(6);
       rendezvous();                                   // #3: the upper half's count
       phase(7);
-      if (hf == 0) {
-        if (any_weight) {
+      if (hf == 0 && any_weight) {
+        {
           const int enc = __float_as_int(ex_oth[11 * kTileRows]);
           const int total_cnt = cnt + (enc & 0xFF);
           choice = (total_cnt < 64) ? total_cnt : kNewTable;
@@ -799,6 +825,9 @@ __global__ void __launch_bounds__(kThreads, 1) k_draw_tc(const Ctx c, const __gr
             choice = (lb >= 0) ? (32 + lb) : ((la >= 0) ? la : t0);
           }
         }
+      }
+      }   // (full path)
+      if (hf == 0) {
         if (c.blk_count > 1 && (int)((c.row_offset + rowc) % c.blk_count) != c.blk_index) choice = t0;   // not this pass's block
         if (live) {
           c.choice[row] = choice;

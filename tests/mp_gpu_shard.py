@@ -38,6 +38,8 @@ def main():
         handles = [None] * world
         dist.all_gather_object(handles, s.p2p_export())
         s.p2p_attach(handles)
+    if os.environ.get("MVG_TEST_INCR") == "1":                # incremental statistics on every shard
+        s.set_stats_mode(True, 64)
     s.set_state(tab[lo:hi], dish, *hyp)
     s.sweep(1, do_hyper=True)
     st1 = s.get_state()

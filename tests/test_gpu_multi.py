@@ -10,7 +10,7 @@ ROOT = Path(__file__).resolve().parents[1]
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("transport", ["nccl", "p2p"])
+@pytest.mark.parametrize("transport", ["nccl", "p2p", "p2p-incremental"])
 def test_two_gpu_row_sharded_chain_matches_one_gpu(transport):
     """transport: the once-per-sweep packet exchange through ncclAllGather, or stored straight into the peers' memory
     over NVLink (csrc/mv_exchange.cu)."""
@@ -19,8 +19,8 @@ def test_two_gpu_row_sharded_chain_matches_one_gpu(transport):
     if torch.cuda.device_count() < 2:
         pytest.skip("needs two GPUs")
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1",
-           "--master-port", "29517" if transport == "nccl" else "29518", str(ROOT / "tests" / "mp_gpu_shard.py")]
-    env = dict(os.environ, MVG_TEST_P2P="1" if transport == "p2p" else "0")
+           "--master-port", {"nccl": "29517", "p2p": "29518"}.get(transport, "29519"), str(ROOT / "tests" / "mp_gpu_shard.py")]
+    env = dict(os.environ, MVG_TEST_P2P="0" if transport == "nccl" else "1", MVG_TEST_INCR="1" if transport.endswith("incremental") else "0")
     r = subprocess.run(cmd, capture_output=True, text=True, timeout=240, env=env)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-4000:]
     assert "SHARD_OK" in r.stdout, r.stdout[-2000:]
