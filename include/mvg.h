@@ -44,7 +44,7 @@
 extern "C" {
 #endif
 
-#define MVG_ABI_VERSION 1
+#define MVG_ABI_VERSION 2
 
 enum {
   MVG_OK = 0,
@@ -166,10 +166,11 @@ int mvg_sync(mvg_handle* h);
 /* gibbs_sampler(M, burn_in, thin): M sweeps; after sweep `iter` with iter >= burn_in and
  * (iter - burn_in) % thin == 0 the state is appended to the caller's trace buffers
  * (save rule of multiview_gibbs.cpp:205).  Buffers hold n_saved_max entries each:
- * table_of [S][n_rows], dish_of [S][V*cap], hypers [S][3V+2] = alpha_v, sigma_v, tau_v, alpha_g, sigma_g.
- * Returns the number of saved states in *n_saved. */
+ * table_of [S][n_rows], dish_of [S][V*cap], hypers [S][3V+2] = alpha_v, sigma_v, tau_v, alpha_g, sigma_g, loglik [S] =
+ * mvg_log_likelihood of the kept state (the reference declares saved_loglik, multiview_state.h:38, and never fills it).
+ * NULL buffers are skipped.  Returns the number of saved states in *n_saved. */
 int mvg_run(mvg_handle* h, int32_t M, int32_t burn_in, int32_t thin, int32_t n_saved_max,
-            int32_t* saved_table_of, int32_t* saved_dish_of, double* saved_hypers, int32_t* n_saved);
+            int32_t* saved_table_of, int32_t* saved_dish_of, double* saved_hypers, double* saved_loglik, int32_t* n_saved);
 
 /* ---- multi-GPU (row-sharded) -------------------------------------------------------------- */
 /* Attach an initialised NCCL communicator (ncclComm_t passed as void*) whose rank/size match the

@@ -97,6 +97,7 @@ struct mvg_handle {
   XchgPeers xpeers{};                // every rank's receive buffer as mapped here ([rank] = xrecv)
   bool xp2p = false;
   bool xattached = false;            // peer mappings exist (they live until mvg_destroy)
+  double* loglik_dev = nullptr;      // [V + 1] scratch of mvg_run's per-kept-sweep log-likelihood
   int32_t* host_fault = nullptr;     // mapped pinned host word: the sticky exchange fault, readable without a sync
 };
 
@@ -157,7 +158,7 @@ int ensure_layout(mvg_handle* h) {
   A(c.sum_cnt, cap); A(c.sum_s1t, cap * dsum); A(c.sum_s2t, V * cap); A(c.xseq, 1); A(c.fin_arrive, 1);
   A(c.tparam, V * cap); A(c.vparam, V); A(c.tmass, cap); A(c.gparam, 1); A(c.tsame, V * cap);
   A(c.mean, cap * dsum); A(c.mean_hi, cap * dsum); A(c.mean_lo, cap * dsum);
-  A(c.partial_f, (size_t)c.stat_ctas * (cap * dsum + V * cap)); A(c.partial_n, (size_t)c.stat_ctas * cap);
+  A(c.partial_f, (size_t)c.stat_ctas * (cap * dsum + V * cap)); A(c.partial_n, (size_t)c.stat_ctas * cap); A(c.cta_active, (size_t)c.stat_ctas);
   A(c.birth_lf, cap * V * (cap + 1));
   A(c.dbg_birth_rows, cap); A(c.dbg_birth_w, cap * V * (cap + 1)); A(c.dbg_nseated, 1);
   A(c.dbg_prof, (size_t)256 * 16);
@@ -720,7 +721,7 @@ int mvg_clear_fault(mvg_handle* h) {
 }
 
 int mvg_run(mvg_handle* h, int32_t M, int32_t burn_in, int32_t thin, int32_t n_saved_max,
-            int32_t* saved_table_of, int32_t* saved_dish_of, double* saved_hypers, int32_t* n_saved) {
+            int32_t* saved_table_of, int32_t* saved_dish_of, double* saved_hypers, double* saved_loglik, int32_t* n_saved) {
   if (!h) return MVG_EINVAL;
   if (M < 0 || thin <= 0) return fail(h, MVG_EINVAL, "M >= 0 and thin >= 1 required");
   const Ctx& c = h->c;
@@ -739,6 +740,17 @@ int mvg_run(mvg_handle* h, int32_t M, int32_t burn_in, int32_t thin, int32_t n_s
       if (saved_hypers)
         MVG_CUDA(h, cudaMemcpyAsync(saved_hypers + (size_t)saved * (3 * c.V + 2), c.hyp,
                                     sizeof(double) * (size_t)(3 * c.V + 2), cudaMemcpyDeviceToHost, h->stream));
+      if (saved_loglik) {           // saved_loglik of the reference's state (multiview_state.h:38): filled on every kept sweep
+        if (!h->loglik_dev) {
+          void* q = nullptr;
+          MVG_CUDA(h, cudaMalloc(&q, sizeof(double) * (size_t)(kMaxViews + 1)));
+          h->owned.push_back(q);
+          h->loglik_dev = static_cast<double*>(q);
+        }
+        MVG_CUDA(h, launch_loglik(c, h->loglik_dev, h->stream));
+        h->launches += 1;
+        MVG_CUDA(h, cudaMemcpyAsync(saved_loglik + saved, h->loglik_dev + c.V, sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+      }
       ++saved;
     }
   }

@@ -95,6 +95,7 @@ struct Ctx {
 
   float* partial_f;         // [stat_ctas][cap*Dsum + V*cap]
   int32_t* partial_n;       // [stat_ctas][cap]
+  int32_t* cta_active;      // [stat_ctas] incremental statistics: did this CTA of the statistics kernel see a moved row
   unsigned char* packet;    // [world][pkt.bytes]; this shard writes slot `rank`
   PacketLayout pkt;
 

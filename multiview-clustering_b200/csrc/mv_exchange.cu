@@ -102,11 +102,12 @@ XchgLayout xchg_layout(const Ctx& c) {
 // grid stride.  Blocks [n_sum_blocks, n_sum_blocks + world) in mode 1: the birth candidates of / for rank g.
 // delta: the partials hold the CHANGE of this shard's statistics (mv_stats_tile.cu, DELTA): it is added to the shard's
 // running FP64 sums, which live in its packet, instead of replacing them.
-__global__ void __launch_bounds__(256) k_reduce_x(const Ctx c, const int mode, const int delta, const int n_sum_blocks, const XchgPeers peers,
+__global__ void __launch_bounds__(256, 3) k_reduce_x(const Ctx c, const int mode, const int delta, const int n_sum_blocks, const XchgPeers peers,
                                                   unsigned char* __restrict__ recv_local, const XchgLayout L) {
   __shared__ double s_part[kRedSlices][32];
   __shared__ int s_cnt[kRedSlices][32];
   __shared__ int s_ncand;
+  __shared__ unsigned char s_active[1024];       // delta: which CTAs of the statistics kernel wrote partials
   const int n_s1 = c.cap * c.Dsum, n_s2 = c.V * c.cap;
   const int n_el = n_s1 + n_s2 + c.cap;
   const uint32_t seq = (mode == 1) ? *reinterpret_cast<volatile uint32_t*>(c.xseq) + 1u : 0u;
@@ -162,6 +163,11 @@ __global__ void __launch_bounds__(256) k_reduce_x(const Ctx c, const int mode, c
   }
 
   // ---------------- statistics ----------------
+  const bool use_flags = delta && mode != 2 && c.stat_ctas <= 1024;
+  if (use_flags) {
+    for (int b = threadIdx.x; b < c.stat_ctas; b += blockDim.x) s_active[b] = (unsigned char)(c.cta_active[b] != 0);
+    __syncthreads();
+  }
   const size_t part_stride = (size_t)n_s1 + n_s2;
   const int e = threadIdx.x & 31, slice = threadIdx.x >> 5;
   double* pk_s1 = reinterpret_cast<double*>(c.packet + (size_t)c.rank * c.pkt.bytes + c.pkt.off_s1t);
@@ -173,10 +179,12 @@ __global__ void __launch_bounds__(256) k_reduce_x(const Ctx c, const int mode, c
     int n = 0;
     if (mode != 2) {
       if (i < n_s1 + n_s2) {
-        for (int b = slice; b < c.stat_ctas; b += kRedSlices) sum += (double)c.partial_f[(size_t)b * part_stride + i];
+        for (int b = slice; b < c.stat_ctas; b += kRedSlices)
+          if (!use_flags || s_active[b]) sum += (double)c.partial_f[(size_t)b * part_stride + i];
       } else if (i < n_el) {
         const int t = i - n_s1 - n_s2;
-        for (int b = slice; b < c.stat_ctas; b += kRedSlices) n += c.partial_n[(size_t)b * c.cap + t];
+        for (int b = slice; b < c.stat_ctas; b += kRedSlices)
+          if (!use_flags || s_active[b]) n += c.partial_n[(size_t)b * c.cap + t];
       }
       s_part[slice][e] = sum;
       s_cnt[slice][e] = n;
@@ -203,15 +211,33 @@ __global__ void __launch_bounds__(256) k_reduce_x(const Ctx c, const int mode, c
         const unsigned long long mine = is_cnt ? (unsigned long long)(uint32_t)n : (unsigned long long)__double_as_longlong(sum);
         for (int g = 0; g < c.world; ++g)
           if (g != c.rank) ll_store_unit(peers.recv[g] + slot0 + (size_t)c.rank * L.slot_bytes + (size_t)i * 16, mine, seq);
-        tot = 0.0; ntot = 0;
-        for (int g = 0; g < c.world; ++g) {                     // rank order, starting from rank 0's value
-          unsigned long long p = mine;
-          if (g != c.rank && !ll_load_unit(recv_local + slot0 + (size_t)g * L.slot_bytes + (size_t)i * 16, seq, &p, wt)) {
-            raise_fault(c);
-            p = 0ull;
+        // all peers are polled together (their loads are independent: one round trip per pass, not one per peer); the
+        // values are then added in rank order
+        unsigned long long val[16];
+        uint32_t pending = ((c.world >= 32) ? 0xffffffffu : ((1u << c.world) - 1u)) & ~(1u << c.rank);
+        val[c.rank & 15] = mine;
+        while (pending) {
+#pragma unroll
+          for (int g = 0; g < 16; ++g) {
+            if (!((pending >> g) & 1u)) continue;
+            uint32_t a, fa, b, fb;
+            const void* src = recv_local + slot0 + (size_t)g * L.slot_bytes + (size_t)i * 16;
+            asm volatile("ld.volatile.global.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(a), "=r"(fa), "=r"(b), "=r"(fb) : "l"(src) : "memory");
+            if (fa == seq && fb == seq) { val[g] = (unsigned long long)a | ((unsigned long long)b << 32); pending &= ~(1u << g); }
           }
-          if (is_cnt) ntot += (int)(uint32_t)p;
-          else tot = (g == 0) ? __longlong_as_double((long long)p) : tot + __longlong_as_double((long long)p);
+          if (pending && !wt.keep_waiting()) {
+            raise_fault(c);
+#pragma unroll
+            for (int g = 0; g < 16; ++g) if ((pending >> g) & 1u) val[g] = 0ull;
+            pending = 0u;
+          }
+        }
+        tot = 0.0; ntot = 0;
+#pragma unroll
+        for (int g = 0; g < 16; ++g) {                          // rank order, starting from rank 0's value
+          if (g >= c.world) break;
+          if (is_cnt) ntot += (int)(uint32_t)val[g];
+          else tot = (g == 0) ? __longlong_as_double((long long)val[g]) : tot + __longlong_as_double((long long)val[g]);
         }
       } else if (mode == 2) {
         tot = 0.0; ntot = 0;
@@ -239,7 +265,7 @@ cudaError_t launch_reduce_x(const Ctx& c, int mode, bool delta, const XchgPeers&
   const XchgLayout L = xchg_layout(c);
   const int n_el = (int)L.n_units;
   int nb = (n_el + 31) / 32;
-  if (nb > 148 * 4) nb = 148 * 4;              // every block of one launch is resident at once (peers wait for each other's pushes)
+  if (nb > 148 * 3) nb = 148 * 3;              // every block of one launch is resident at once (3 per SM by the launch bounds): peers wait for each other's pushes
   const int extra = (mode == 1) ? c.world : 0;
   k_reduce_x<<<nb + extra, 256, 0, s>>>(c, mode, delta ? 1 : 0, nb, peers, recv_local, L);
   return cudaGetLastError();

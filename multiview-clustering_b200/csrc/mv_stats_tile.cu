@@ -131,6 +131,11 @@ __global__ void __launch_bounds__(kThreadsST, 1) k_stats_tile(const Ctx c) {
   }
   __syncthreads();
   const int n_iter = DELTA ? s_nact : (t_hi - t_lo);
+  if (DELTA) {
+    // nothing moved in this CTA's rows: its partials would be all zero; k_reduce_x skips them (adding zeros changes nothing)
+    if (tid == 0) c.cta_active[blockIdx.x] = (n_iter > 0) ? 1 : 0;
+    if (n_iter == 0) return;
+  }
 
   if (wid == kAccWarps) {
     // ---------------- producer: one lane keeps the ring full ----------------

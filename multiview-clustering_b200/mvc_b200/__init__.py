@@ -94,7 +94,7 @@ def lib():
         L.mvg_set_stats_mode.argtypes = [H, C.c_int32, C.c_int32]
         L.mvg_hyper_step_parts.argtypes = [H, C.c_int32]
         L.mvg_sync.argtypes = [H]
-        L.mvg_run.argtypes = [H, C.c_int32, C.c_int32, C.c_int32, C.c_int32, _i32p, _i32p, _f64p, _i32p]
+        L.mvg_run.argtypes = [H, C.c_int32, C.c_int32, C.c_int32, C.c_int32, _i32p, _i32p, _f64p, _f64p, _i32p]
         L.mvg_comm_attach.argtypes = [H, C.c_void_p]
         L.mvg_comm_handle.restype = C.c_void_p
         L.mvg_comm_handle.argtypes = [H]
@@ -152,7 +152,7 @@ class Sampler:
         self.Dsum = sum(self.dims)
         self.doff = np.concatenate([[0], np.cumsum(self.dims)[:-1]]).astype(int)
         cfg = _Config()
-        cfg.abi_version = 1
+        cfg.abi_version = 2
         cfg.device = device
         cfg.n_rows = self.n_rows
         cfg.n_rows_global = self.n_rows if n_rows_global is None else int(n_rows_global)
@@ -347,11 +347,13 @@ class Sampler:
         tab = np.empty((max(n_saved_max, 1), self.n_rows), np.int32)
         dish = np.empty((max(n_saved_max, 1), self.V, self.cap), np.int32)
         hyp = np.empty((max(n_saved_max, 1), 3 * self.V + 2), np.float64)
+        ll = np.zeros(max(n_saved_max, 1), np.float64)
         ns = C.c_int32(0)
+        dense = all(d > 0 for d in self.dims)            # the log-likelihood kernel covers the Gaussian views
         self._ck(self.L.mvg_run(self.h, M, burn_in, thin, n_saved_max, _p(tab, _i32p), _p(dish, _i32p),
-                                _p(hyp, _f64p), C.byref(ns)))
+                                _p(hyp, _f64p), _p(ll, _f64p) if dense else None, C.byref(ns)))
         S = ns.value
-        return {"table_of": tab[:S], "dish_of": dish[:S], "hypers": hyp[:S]}
+        return {"table_of": tab[:S], "dish_of": dish[:S], "hypers": hyp[:S], "loglik": ll[:S] if dense else ll[:0]}
 
     # -- multi-GPU ----------------------------------------------------------------------------
     @staticmethod
@@ -468,7 +470,7 @@ def _as_csr(v):
     return None
 
 
-def run_gibbs(data_views, M, burn_in, thin, cap=64, seed=1999, device=0, engine=ENGINE_AUTO, start=None):
+def run_gibbs(data_views, M, burn_in, thin, cap=64, seed=1999, device=0, engine=ENGINE_AUTO, start=None, blocks=1):
     """run_gibbs_cpp(data_views, M, burn_in, thin) on the GPU (multiview_gibbs.cpp:105-131).
 
     ``data_views`` is a list of per-view arrays (vectors as in New_Simulation.R:105-111, or [n, D]
@@ -487,6 +489,8 @@ def run_gibbs(data_views, M, burn_in, thin, cap=64, seed=1999, device=0, engine=
                 s.upload_view_csr(v, *csr[v])
             else:
                 s.upload_view(v, x)
+        if blocks > 1:
+            s.set_sweep_blocks(blocks)
         if start is None:
             s.init_state_reference()
         else:
@@ -500,7 +504,7 @@ def run_gibbs(data_views, M, burn_in, thin, cap=64, seed=1999, device=0, engine=
     return {
         "table_of": [t for t in tr["table_of"]],
         "dish_of": [[d[v] for v in range(V)] for d in tr["dish_of"]],
-        "loglik": [],                                   # declared, never filled (multiview_state.h:38)
+        "loglik": list(tr["loglik"]),                   # the reference declares it and never fills it (multiview_state.h:38)
         "alpha_v": [hyp[:, v] for v in range(V)],
         "sigma_v": [hyp[:, V + v] for v in range(V)],
         "tau_v": [hyp[:, 2 * V + v] for v in range(V)],

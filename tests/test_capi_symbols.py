@@ -21,7 +21,7 @@ def test_library_exports_every_declared_symbol():
     assert len(names) >= 25
     for n in names:
         assert hasattr(L, n), f"{n} declared in include/mvg.h but not exported by libmvg_b200.so"
-    assert L.mvg_abi_version() == 1
+    assert L.mvg_abi_version() == 2
 
 
 def test_no_cpu_fallback_without_gpu():
@@ -52,7 +52,7 @@ def test_config_validation_is_host_side():
     h = C.c_void_p()
     cfg.abi_version = 99
     assert L.mvg_create(C.byref(cfg), C.byref(h)) == -1
-    cfg.abi_version = 1
+    cfg.abi_version = 2
     cfg.n_rows = 10
     cfg.n_rows_global = 10
     cfg.n_views = 1
