@@ -39,7 +39,7 @@ N_ROWS = 1_000_000
 DIMS = [64, 64, 64]
 CAP = 64
 SEED = 1999
-NCU_TRAFFIC_BYTES = 792.9e6     # measured DRAM traffic of one k_draw_tc launch at N=1M (algorithmic: 776 MB + 12 MB of stored squared norms)
+NCU_TRAFFIC_BYTES = 791.7e6     # measured DRAM traffic of one k_draw_tc launch at N=1M (profiles/r02_ncu_draw.md; algorithmic: 776 MB + 12 MB of stored squared norms)
 METRIC = "obs_x_view_x_K_updates_per_s"
 UNIT = "updates/s"
 
@@ -63,6 +63,7 @@ def parse():
                          "chains per GPU; with --impl reference the UNMODIFIED reference sampler (oracle/_ref) is timed.  "
                          "c2: BASELINE configs[1]/[4], three sparse count views with the shapes of Reuters-21578 (synthetic "
                          "topics; the .sgm files do not travel to the GPU box), --chains chains per GPU")
+    ap.add_argument("--synthetic-reuters", action="store_true", help="c2: synthetic topics even when the ingested collection is cached")
     ap.add_argument("--chains", type=int, default=8, help="c1: independent chains per GPU, one stream each")
     ap.add_argument("--exchange", default="auto", choices=["auto", "p2p", "nccl"],
                     help="N > 1: transport of the once-per-sweep packets: p2p = stores into the peers' memory over NVLink "
@@ -234,11 +235,17 @@ def run_c2(args, out):
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     from mvc_b200 import reuters
-    views, z = reuters.synthetic_like_reuters(seed=SEED)
-    n, steps, cap = len(z), args.steps, 64
+    cached = reuters.load_cached()           # the real collection, ingested from the .sgm files (data_cache/, travels with the tree)
+    if cached is not None and not args.synthetic_reuters:
+        views, z = cached[0], None
+        source = "Reuters-21578 (real: body / title / category-tag count views ingested from the .sgm files)"
+    else:
+        views, z = reuters.synthetic_like_reuters(seed=SEED)
+        source = "synthetic topics with the shapes of Reuters-21578"
+    n, steps, cap = len(views[0]["rowptr"]) - 1, args.steps, 64
     nnz = [int(len(v["col"])) for v in views]
-    workload = ("C2: three CSR count views shaped like Reuters-21578 (N=%d; vocab 13000/5700/445; nnz %s), cap %d"
-                % (n, "/".join(map(str, nnz)), cap))
+    workload = ("C2: three CSR count views, %s (N=%d; vocab %s; nnz %s), cap %d"
+                % (source, n, "/".join(str(v["vocab"]) for v in views), "/".join(map(str, nnz)), cap))
     if args.impl == "reference":
         if rank != 0:
             return
@@ -291,14 +298,14 @@ def run_c2(args, out):
     dt = time.perf_counter() - t0
     launches = sum(s.launch_count() for s in chains) - l0
     prof = chains[0].profile_sweep(True)
-    ari = [chains[0].adjusted_rand_index(v, z)[0] for v in range(3)]
+    ari = [chains[0].adjusted_rand_index(v, z)[0] for v in range(3)] if z is not None else None
     live = [int((s.get_state(with_rows=False)["n_t"] > 0).sum()) for s in chains]
     for s in chains:
         s.close()
     if rank == 0:
         line = {"metric": "gibbs_sweeps_per_s", "value": world * args.chains * steps / dt, "unit": "sweeps/s", "n_gpus": world,
                 "steps": steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / steps, "higher_is_better": True,
-                "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+                "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic" if z is not None else "Reuters-21578",
                 "config": {"workload": workload + ", %d independent chains per GPU, CUDA-core engine, hyper step on" % args.chains,
                            "timing": "wall clock around the launches of all chains and their final synchronisation"},
                 "kernel_ms_one_chain": prof, "gpu_launches": int(launches), "tables_live": live,

@@ -120,3 +120,41 @@ def synthetic_like_reuters(n=21578, seed=1999, k_true=20):
         out.append({"rowptr": np.asarray(rowptr, np.int32), "col": np.concatenate(col).astype(np.int32),
                     "val": np.concatenate(val).astype(np.float32), "vocab": vocab})
     return out, z
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# Cache of the ingested collection.  The .sgm files live under /root/reference and do not travel to a GPU box; the three
+# CSR views (9 MB) do: `python -m mvc_b200.reuters <sgm dir> <out.npz>` writes them once (data_cache/ is git-ignored but
+# ships with the working tree), load_cached() reads them back where the sampler runs.
+# ---------------------------------------------------------------------------------------------------------------------
+CACHE = __import__("pathlib").Path(__file__).resolve().parents[2] / "data_cache" / "reuters21578_csr.npz"
+
+
+def save_cache(r, path=CACHE):
+    path = __import__("pathlib").Path(path)
+    path.parent.mkdir(parents=True, exist_ok=True)
+    out = {"ids": r["ids"]}
+    for name in ("body", "title", "tags"):
+        for k in ("rowptr", "col", "val"):
+            out[f"{name}_{k}"] = r[name][k]
+        out[f"{name}_vocab"] = np.int64(r[name]["vocab"])
+    np.savez_compressed(path, **out)
+    return path
+
+
+def load_cached(path=CACHE):
+    """The three count views [body, title, tags] as CSR dicts, or None when the cache has not been written."""
+    path = __import__("pathlib").Path(path)
+    if not path.exists():
+        return None
+    z = np.load(path)
+    views = [{"rowptr": z[f"{n}_rowptr"].astype(np.int32), "col": z[f"{n}_col"].astype(np.int32),
+              "val": z[f"{n}_val"].astype(np.float32), "vocab": int(z[f"{n}_vocab"])} for n in ("body", "title", "tags")]
+    return views, z["ids"]
+
+
+if __name__ == "__main__":
+    import sys
+    src = sys.argv[1] if len(sys.argv) > 1 else "/root/reference/dataset/reuters/reuters21578"
+    dst = sys.argv[2] if len(sys.argv) > 2 else CACHE
+    print(save_cache(load_reuters(src), dst))

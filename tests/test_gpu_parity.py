@@ -792,3 +792,47 @@ def test_run_gibbs_accepts_sparse_count_views():
     from sklearn.metrics import adjusted_rand_score as ari
     last_tab, last_dish = res["table_of"][-1], res["dish_of"][-1]
     assert ari(z, np.asarray(last_dish[0])[last_tab]) > 0.7 and ari(z, np.asarray(last_dish[1])[last_tab]) > 0.7
+
+
+def test_real_reuters_collection_on_the_gpu(oracle):
+    """BASELINE configs[1]: the three count views ingested from the Reuters-21578 .sgm files (mvc_b200/reuters.py restating
+    dataset/reuters/data pre-process.R:9-108; cached as CSR in data_cache/, which travels with the working tree) through
+    a GPU chain: 25 sweeps from an over-split start, then against the CPU restatement started from the device's state —
+    customer counts and per-dish word counts exact, and the next sweep's draws agree except on CDF edges."""
+    import mvc_b200
+    from mvc_b200 import reuters
+    cached = reuters.load_cached()
+    if cached is None:
+        pytest.skip("data_cache/reuters21578_csr.npz not present (python -m mvc_b200.reuters writes it where the .sgm files are)")
+    views, ids = cached
+    n, cap, seed = len(ids), 64, 1999
+    assert n == 21578 and [v["vocab"] for v in views][2] == 445
+    rng = np.random.default_rng(seed)
+    tab = rng.integers(0, cap // 2, n).astype(np.int32)
+    dish = np.full((3, cap), -1, np.int32)
+    dish[:, :cap // 2] = np.arange(cap // 2)
+    s = mvc_b200.Sampler(n, [0, 0, 0], cap=cap, seed=seed, engine=1, debug_export=True)
+    for v, x in enumerate(views):
+        s.upload_view_csr(v, x["rowptr"], x["col"], x["val"], x["vocab"])
+    s.set_state(tab, dish, [1.0] * 3, [0.5] * 3, [1.0] * 3, 1.0, 0.6)
+    s.sweep(25, do_hyper=True)
+    pre = s.get_state()
+    assert int(pre["n_t"].sum()) == n
+    o = oracle.OracleState(views, cap, seed=seed)
+    o.alpha_v[:] = pre["alpha_v"]; o.sigma_v[:] = pre["sigma_v"]; o.tau_v[:] = pre["tau_v"]
+    o.alpha_g, o.sigma_g, o.sweep = pre["alpha_g"], pre["sigma_g"], pre["sweep"]
+    o.set_assignment(pre["table_of"], pre["dish_of"])
+    for k in ("n_t", "n_vk", "l_vk"):
+        np.testing.assert_array_equal(pre[k], getattr(o, k), err_msg=k)
+    for v in range(3):                                               # word counts of every dish, as seen from its tables: exact
+        l2t, cd, ct = s.get_count_tables(v)
+        for t in np.nonzero(pre["n_t"] > 0)[0]:
+            np.testing.assert_array_equal(cd[:, t], o.cd[v][pre["dish_of"][v][t]])
+    np.testing.assert_array_equal(pre["sum_y2"], o.S2)               # token totals per dish
+    s.sweep(1, do_hyper=True)
+    _, _, raw = s.get_debug_rows()
+    agree = float((o.draw_rows(threads=8) == raw).mean())
+    assert agree > 0.995, agree
+    live = int((s.get_state(with_rows=False)["n_t"] > 0).sum())
+    print(f"\n[reuters] 26 sweeps on the real collection: {live} tables live, draw agreement with the FP64 restatement {agree:.5f}")
+    s.close()
