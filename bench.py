@@ -57,12 +57,14 @@ def parse():
     ap.add_argument("--engine", type=int, default=0, help="0 auto, 1 CUDA-core, 2 tcgen05")
     ap.add_argument("--k-true", type=int, default=CAP, help="planted clusters (default 64 = every table slot in use; "
                     "fewer leaves free slots, so the new-table marginal is evaluated as well)")
-    ap.add_argument("--workload", default="c3", choices=["c3", "c1", "c2"],
+    ap.add_argument("--workload", default="c3", choices=["c3", "c1", "c2", "c5"],
                     help="c3: the headline configuration (default).  c1: BASELINE configs[0], the reference's own case "
                          "(New_Simulation.R: N=500, two scalar views), reported in sweeps/s with --chains independent "
                          "chains per GPU; with --impl reference the UNMODIFIED reference sampler (oracle/_ref) is timed.  "
                          "c2: BASELINE configs[1]/[4], three sparse count views with the shapes of Reuters-21578 (synthetic "
-                         "topics; the .sgm files do not travel to the GPU box), --chains chains per GPU")
+                         "topics; the .sgm files do not travel to the GPU box), --chains chains per GPU.  "
+                         "c5: BASELINE configs[4], --chains independent chains of the Reuters config per GPU; their pooled posterior "
+                         "co-clustering matrix (a fixed subsample of the documents) is compared with CPU chains of the FP64 restatement")
     ap.add_argument("--synthetic-reuters", action="store_true", help="c2: synthetic topics even when the ingested collection is cached")
     ap.add_argument("--chains", type=int, default=8, help="c1: independent chains per GPU, one stream each")
     ap.add_argument("--exchange", default="auto", choices=["auto", "p2p", "nccl"],
@@ -313,6 +315,136 @@ def run_c2(args, out):
         print(json.dumps(line), file=out)
 
 
+def run_c5(args, out):
+    """BASELINE configs[4]: independent chains of the Reuters configuration, --chains per GPU (64 = 8 per GPU on 8 GPUs),
+    and the agreement of their pooled posterior co-clustering matrix with CPU chains of the FP64 restatement
+    (oracle/mv_oracle.c; the reference has no count likelihood, so that restatement is the CPU reference here)."""
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    from mvc_b200 import reuters
+    cached = reuters.load_cached()
+    if cached is not None and not args.synthetic_reuters:
+        views, source = cached[0], "Reuters-21578 (real, ingested from the .sgm files)"
+    else:
+        views, source = reuters.synthetic_like_reuters(seed=SEED)[0], "synthetic topics with the shapes of Reuters-21578"
+    n, cap, V = len(views[0]["rowptr"]) - 1, 64, 3
+    M, burn, thin = args.steps, args.steps // 2, max(1, args.steps // 20)      # the second half of the chain, ten kept states
+    sub = np.sort(np.random.default_rng(SEED).choice(n, 1500, replace=False))   # documents whose pairs are compared
+
+    def cocl_of(labels_list):
+        acc = [np.zeros((len(sub), len(sub))) for _ in range(V)]
+        for lab in labels_list:                                                  # lab: [V][n]
+            for v in range(V):
+                l = lab[v][sub]
+                acc[v] += l[:, None] == l[None, :]
+        return acc
+
+    if args.impl == "reference":
+        if rank != 0:
+            return
+        sys.path.insert(0, str(ROOT / "oracle"))
+        import pyoracle as po
+        threads = os.cpu_count() or 1
+        t0 = time.perf_counter()
+        o = po.OracleState(views, cap, seed=SEED, chain=1000)
+        tab0, dish0 = c2_start(n, cap, chain=1000)
+        o.set_assignment(tab0, dish0)
+        k = max(1, min(M, 20))
+        o.sweep_n(k, threads=threads, do_hyper=True)
+        dt = time.perf_counter() - t0
+        line = {"impl": "reference", "metric": "gibbs_sweeps_per_s", "value": k / dt, "unit": "sweeps/s", "n_gpus": args.gpus,
+                "steps": k, "warmup": 0, "ms_per_step": 1e3 * dt / k, "higher_is_better": True, "scaling": "weak",
+                "vs_baseline": None, "dtype": "f64", "data": source, "config": {"workload": "C5: one CPU chain of the Reuters configuration"},
+                "cpu_baseline": {"value": k / dt, "unit": "sweeps/s", "cores": threads, "kind": "port", "sample": "%d FP64 sweeps" % k},
+                "e2e": {"value": k / dt, "unit": "sweeps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+        print(json.dumps(line), file=out)
+        return
+    import torch
+    import mvc_b200
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the sweep has no CPU path")
+    torch.cuda.set_device(local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("gloo")
+    chains = []
+    for ch in range(args.chains):
+        cid = rank * args.chains + ch
+        s = mvc_b200.Sampler(n, [0, 0, 0], cap=cap, seed=SEED, chain=cid, device=local_rank, engine=1)
+        for v, x in enumerate(views):
+            s.upload_view_csr(v, x["rowptr"], x["col"], x["val"], x["vocab"])
+        tab0, dish0 = c2_start(n, cap, chain=cid)
+        s.set_state(tab0, dish0, [1.0] * V, [0.5] * V, [1.0] * V, 1.0, 0.6)
+        chains.append(s)
+    kept = []
+    t0 = time.perf_counter()
+    done = 0
+    while done < M:
+        b = min(thin, M - done)
+        for s in chains:
+            s.sweep(b, True)
+        done += b
+        if done > burn:
+            for s in chains:
+                kept.append(s.cluster_labels())                                 # D2H of V x n labels per chain and kept state
+    for s in chains:
+        s.sync()
+    dt = time.perf_counter() - t0
+    launches = sum(s.launch_count() for s in chains)
+    live = [int((s.get_state(with_rows=False)["n_t"] > 0).sum()) for s in chains]
+    for s in chains:
+        s.close()
+    mine = cocl_of(kept)
+    n_kept = len(kept)
+    if dist is not None:
+        parts = [None] * world
+        dist.all_gather_object(parts, (mine, n_kept, dt, live))
+        mine = [sum(p[0][v] for p in parts) for v in range(V)]
+        n_kept = sum(p[1] for p in parts)
+        dt = max(p[2] for p in parts)
+        live = sum((p[3] for p in parts), [])
+    if rank == 0:
+        P_gpu = [m / n_kept for m in mine]
+        # CPU chains of the FP64 restatement: the same schedule, two chains, all host threads
+        sys.path.insert(0, str(ROOT / "oracle"))
+        import pyoracle as po
+        threads = os.cpu_count() or 1
+        cpu_kept, t1 = [], time.perf_counter()
+        n_cpu = 0 if args.no_cpu_baseline else 2
+        for ch in range(n_cpu):
+            o = po.OracleState(views, cap, seed=SEED, chain=1000 + ch)
+            tab0, dish0 = c2_start(n, cap, chain=1000 + ch)
+            o.set_assignment(tab0, dish0)
+            done = 0
+            while done < M:
+                b = min(thin, M - done)
+                o.sweep_n(b, threads=threads, do_hyper=True)
+                done += b
+                if done > burn:
+                    cpu_kept.append(o.labels().T)
+        cpu_dt = time.perf_counter() - t1
+        agree = None
+        if cpu_kept:
+            P_cpu = [m / len(cpu_kept) for m in cocl_of(cpu_kept)]
+            agree = {"mean_abs_dP_per_view": [float(np.abs(P_gpu[v] - P_cpu[v]).mean()) for v in range(V)],
+                     "mean_P_gpu": [float(P_gpu[v].mean()) for v in range(V)], "mean_P_cpu": [float(P_cpu[v].mean()) for v in range(V)],
+                     "documents_compared": int(len(sub)), "gpu_states": int(n_kept), "cpu_states": int(len(cpu_kept)),
+                     "cpu_chains": n_cpu, "cpu_sweeps_per_s": n_cpu * M / cpu_dt, "cpu_threads": threads}
+        total_chains = world * args.chains
+        line = {"metric": "gibbs_sweeps_per_s", "value": total_chains * M / dt, "unit": "sweeps/s", "n_gpus": world,
+                "steps": M, "warmup": 0, "ms_per_step": 1e3 * dt / M, "higher_is_better": True, "scaling": "weak",
+                "vs_baseline": None, "dtype": "f32", "data": source,
+                "config": {"workload": "C5: %d independent chains of the Reuters configuration (%d per GPU), N=%d, cap %d; kept states "
+                                       "every %d sweeps of the second half; wall clock incl. the D2H of the labels" % (total_chains, args.chains, n, cap, thin)},
+                "gpu_launches": int(launches), "tables_live": live, "coclustering_vs_cpu": agree}
+        print(json.dumps(line), file=out)
+    if dist is not None:
+        dist.destroy_process_group()
+
+
 def run_c1(args, out):
     """Config 1 in sweeps/s.  b200 arm: --chains independent chains on one GPU (one handle and stream each,
     launches interleaved).  reference arm: the unmodified reference sampler compiled into oracle/_ref, 1 core."""
@@ -432,6 +564,8 @@ def _main(args, out):
         return run_c1(args, out)
     if args.workload == "c2":
         return run_c2(args, out)
+    if args.workload == "c5":
+        return run_c5(args, out)
     if args.impl == "reference":
         return run_reference(args, out)
 

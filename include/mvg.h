@@ -110,7 +110,12 @@ int mvg_destroy(mvg_handle* h);
 const char* mvg_last_error(const mvg_handle* h);   /* h may be NULL: error of the last failed create */
 
 /* ---- data ------------------------------------------------------------------------------ */
-/* Dense view v, row-major [n_rows][dim] in HOST memory (pageable or pinned); copied to the GPU. */
+/* Dense view v, row-major [n_rows][dim] in HOST memory (pageable or pinned); copied to the GPU.
+ * Numerical range: features are held and summed in FP32 (per-CTA partial sums in a fixed tree, FP64 across CTAs), and the
+ * likelihood uses 2 x.m - |x|^2 in FP32; the reference works in double throughout.  The tolerances of the parity suite
+ * (sums <= 1e-5, log-likelihoods <= 1e-5 of the cancelling terms) hold for views whose |mean| / sd is of order 10 or
+ * less per coordinate (the prior mean of a dish is 0, multiview_utils.cpp:307-338); data with |mean| / sd ~ 100 loses
+ * digits in S2 - |S1|^2 / n (the tau_v step) and should be centred per coordinate before upload. */
 int mvg_upload_view_f32(mvg_handle* h, int32_t v, const float* x_host, int32_t dim);
 /* Same from doubles, the type of the reference's y[v] (multiview_state.h:22); rounded to FP32. */
 int mvg_upload_view_f64(mvg_handle* h, int32_t v, const double* y_host, int32_t dim);
@@ -261,6 +266,22 @@ int mvg_coclustering_get(mvg_handle* h, uint32_t* counts, int32_t* n_samples);
  * [cap][n_classes]) receives the Predicted x Truth table of :192-196.  With world > 1 both are this shard's. */
 int mvg_adjusted_rand_index(mvg_handle* h, int32_t view, const int32_t* truth, int32_t n_classes, double* ari,
                             int32_t* contingency);
+
+/* ---- MVG_ENGINE_SEQ: the reference-exact sequential sampler (csrc/mv_seq_core.h, csrc/mv_seq.cu) ------------------
+ * run_gibbs_cpp(data_views, M, burn_in, thin) of multiview_gibbs.cpp:105-131 for scalar views, every rule of the reference
+ * kept (customers re-seated one after the other, unbounded table / dish slots, swap-with-last deletion, dish slots never
+ * recycled, FP64, the reference's operation order) on the call-ordered Philox stream the compiled reference is driven with
+ * in oracle/refshim: given the same data and seed the chain visits the same integer states as the unmodified reference.
+ * One device thread per chain: the anchor for the reference's own configuration (N ~ 500), not a throughput path.
+ * y: host [d][n] doubles.  t_cap / k_cap: capacities of the table and dish-slot arrays (dish slots are never recycled by the
+ * reference: k_cap ~ 2 + sweeps is safe).  Outputs (host, NULL skips): saved_table_of [S][n] (0-based, dense),
+ * saved_T [S], saved_dish_of [S][d][t_cap] (first saved_T[s] entries of every row valid), saved_hypers [S][3d+2]
+ * (alpha_v, sigma_v, tau_v, alpha_global, sigma_global), *n_saved, *stream_calls (uniforms + normals consumed). */
+int mvg_seq_run(int32_t device, int32_t n, int32_t d, const double* y, int32_t M, int32_t burn_in, int32_t thin,
+                uint64_t seed, int32_t t_cap, int32_t k_cap, int32_t n_saved_max, int32_t* saved_table_of,
+                int32_t* saved_T, int32_t* saved_dish_of, double* saved_hypers, int32_t* n_saved,
+                uint64_t* stream_calls);
+const char* mvg_seq_last_error(void);
 
 /* ---- Philox host mirror (multiview_rng.h surface) ---------------------------------------- */
 void mvg_philox4x32_10(const uint32_t ctr[4], const uint32_t key[2], uint32_t out[4]);

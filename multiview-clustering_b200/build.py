@@ -11,7 +11,9 @@ from pathlib import Path
 HERE = Path(__file__).resolve().parent
 CSRC = HERE / "csrc"
 OUT = HERE / "mvc_b200" / "libmvg_b200.so"
-SOURCES = ["mv_capi.cu", "mv_draw_simt.cu", "mv_draw_tc.cu", "mv_state_kernels.cu", "mv_stats_tile.cu", "mv_summary.cu", "mv_counts.cu", "mv_exchange.cu"]
+SOURCES = ["mv_capi.cu", "mv_draw_simt.cu", "mv_draw_tc.cu", "mv_state_kernels.cu", "mv_stats_tile.cu", "mv_summary.cu", "mv_counts.cu", "mv_exchange.cu", "mv_seq.cu"]
+# per-file overrides: the sequential engine must not contract a*b+c (the compiled reference does not either)
+EXTRA = {"mv_seq.cu": ["--fmad=false"]}
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
          "-Xcompiler", "-fPIC", "--fmad=true", "-Xptxas", "-v"]
@@ -36,7 +38,8 @@ def build(force: bool = False, verbose: bool = False) -> Path:
     for src in SOURCES:
         obj = objdir / (src + ".o")
         objs.append(str(obj))
-        cmd = [NVCC, *FLAGS, "-c", str(CSRC / src), "-o", str(obj)]
+        flags = [f for f in FLAGS if not (src in EXTRA and f == "--fmad=true")] + EXTRA.get(src, [])
+        cmd = [NVCC, *flags, "-c", str(CSRC / src), "-o", str(obj)]
         procs.append((src, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
     log = []
     for src, p in procs:

@@ -4,6 +4,7 @@
 // if CUDA is unavailable mvg_create fails with MVG_ECUDA.
 #include <cuda_runtime.h>
 #include <dlfcn.h>
+#include <nvtx3/nvToolsExt.h>     // header-only NVTX 3: ranges per stage of a sweep; no-ops without a tool attached
 
 #include <cstdio>
 #include <cstdlib>
@@ -19,6 +20,11 @@
 namespace {
 
 using namespace mv;
+
+struct NvtxRange {                 // a stage of the sweep as it is enqueued (and, in a graph replay, one range per sweep)
+  explicit NvtxRange(const char* name) { nvtxRangePushA(name); }
+  ~NvtxRange() { nvtxRangePop(); }
+};
 
 // ---- minimal NCCL surface, resolved at run time so that one-GPU use needs no NCCL at all -------
 struct UidByValue { char internal[128]; };   // ncclUniqueId is passed by value
@@ -222,11 +228,12 @@ int reduce_exchange(mvg_handle* h, cudaEvent_t* marks, bool delta) {
 
 // stats -> reduce + exchange -> finalize: shared by sweeps, set_state and init
 int rebuild_pipeline(mvg_handle* h, int32_t flags, cudaEvent_t* marks /* 4 events or null */, bool delta = false) {
-  MVG_CUDA(h, launch_stats(h->c, delta, h->stream));
+  { NvtxRange r(delta ? "mvg:statistics (moved rows)" : "mvg:statistics (rebuild)"); MVG_CUDA(h, launch_stats(h->c, delta, h->stream)); }
   if (marks) MVG_CUDA(h, cudaEventRecord(marks[0], h->stream));
-  int rc = reduce_exchange(h, marks, delta);
+  int rc;
+  { NvtxRange r("mvg:reduce+exchange"); rc = reduce_exchange(h, marks, delta); }
   if (rc != MVG_OK) return rc;
-  MVG_CUDA(h, launch_finalize(h->c, flags, h->stream));
+  { NvtxRange r("mvg:births, hyper step, parameters"); MVG_CUDA(h, launch_finalize(h->c, flags, h->stream)); }
   if (h->c.n_count_views) {          // count views: word counts by the final seating, then the log2 theta tables
     MVG_CUDA(h, launch_counts_rebuild(h->c, h->stream));
     h->launches += 2;
@@ -600,9 +607,10 @@ int one_sweep(mvg_handle* h, int32_t flags, bool delta) {
   const int B = h->c.blk_count;
   for (int b = 0; b < B; ++b) {
     h->c.blk_index = b;
-    int rc = launch_draw(h);
+    int rc;
+    { NvtxRange r("mvg:likelihood+draw"); rc = launch_draw(h); }
     if (rc != MVG_OK) return rc;
-    MVG_CUDA(h, launch_pack(h->c, h->stream));
+    { NvtxRange r("mvg:pack births"); MVG_CUDA(h, launch_pack(h->c, h->stream)); }
     h->launches += 1;
     rc = rebuild_pipeline(h, (b == B - 1) ? flags : kFinReseat, nullptr, delta && B == 1);
     if (rc != MVG_OK) return rc;
@@ -652,6 +660,7 @@ int mvg_sweep(mvg_handle* h, int32_t n_sweeps, int32_t do_hyper) {
     const int which = (do_hyper ? 1 : 0) + (delta ? 2 : 0);
     const bool use_graph = (n_sweeps >= 2 || h->sweeps_issued >= 1) && ensure_sweep_graph(h, which, flags, delta);
     if (use_graph) {
+      NvtxRange r("mvg:sweep (graph replay)");
       MVG_CUDA(h, cudaGraphLaunch(h->sweep_graph[which], h->stream));
       h->launches += h->sweep_graph_launches[which];
     } else {

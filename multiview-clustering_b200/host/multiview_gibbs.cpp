@@ -4,8 +4,11 @@
 // linked against the prebuilt libmvg_b200.so; every sweep runs on the GPU.
 #include "multiview_gibbs.h"
 
+#include <algorithm>
 #include <cmath>
+#include <cstdint>
 #include <string>
+#include <vector>
 
 #include "../../include/mvg.h"
 #include "multiview_hyper.h"
@@ -73,9 +76,44 @@ Rcpp::List run_gibbs_cpp(const Rcpp::List& data_views,
   for (int v = 0; v < d; ++v) y[(size_t)v] = Rcpp::as<std::vector<double>>(data_views[v]);
   if (!mvhost::view_dim.empty()) n /= mvhost::view_dim[0];   // matrix views arrive flattened row-major
 
-  initialize_state_from_data();
-  gibbs_sampler(M, burn_in, thin);
-  mvhost::close_chain();
+  if (mvhost::sequential) {
+    // MVG_ENGINE_SEQ: the reference's sequential sampler rule for rule on the device (csrc/mv_seq_core.h); scalar views
+    if (!mvhost::view_dim.empty()) Rcpp::stop("run_gibbs_cpp: the sequential engine takes scalar views");
+    if (thin <= 0) Rcpp::stop("run_gibbs_cpp: thin must be positive");
+    const int S = (M > burn_in) ? (M - burn_in + thin - 1) / thin : 0, t_cap = 1024;
+    std::vector<double> flat((size_t)d * n);
+    for (int v = 0; v < d; ++v) std::copy(y[(size_t)v].begin(), y[(size_t)v].end(), flat.begin() + (size_t)v * n);
+    std::vector<int32_t> tab((size_t)std::max(S, 1) * n), Ts((size_t)std::max(S, 1)), dish((size_t)std::max(S, 1) * d * t_cap);
+    std::vector<double> hyp((size_t)std::max(S, 1) * (3 * d + 2));
+    int32_t ns = 0;
+    if (mvg_seq_run(0, n, d, flat.data(), M, burn_in, thin, mvhost::seed, t_cap, 2 * M + 64, S, tab.data(), Ts.data(), dish.data(),
+                    hyp.data(), &ns, nullptr) != MVG_OK)
+      Rcpp::stop(std::string("run_gibbs_cpp (sequential engine): ") + mvg_seq_last_error());
+    saved_table_of.clear(); saved_dish_of.clear(); saved_loglik.clear();
+    saved_alpha_v.assign((size_t)d, {}); saved_sigma_v.assign((size_t)d, {}); saved_tau_v.assign((size_t)d, {});
+    saved_alpha_global.clear(); saved_sigma_global.clear();
+    for (int s = 0; s < ns; ++s) {
+      saved_table_of.emplace_back(tab.begin() + (size_t)s * n, tab.begin() + (size_t)(s + 1) * n);
+      std::vector<std::vector<int>> dd((size_t)d);
+      for (int v = 0; v < d; ++v) {
+        const int32_t* row = dish.data() + ((size_t)s * d + v) * t_cap;
+        dd[(size_t)v].assign(row, row + Ts[(size_t)s]);
+      }
+      saved_dish_of.push_back(dd);
+      const double* h = hyp.data() + (size_t)s * (3 * d + 2);
+      for (int v = 0; v < d; ++v) {
+        saved_alpha_v[(size_t)v].push_back(h[v]);
+        saved_sigma_v[(size_t)v].push_back(h[d + v]);
+        saved_tau_v[(size_t)v].push_back(h[2 * d + v]);
+      }
+      saved_alpha_global.push_back(h[3 * d]);
+      saved_sigma_global.push_back(h[3 * d + 1]);
+    }
+  } else {
+    initialize_state_from_data();
+    gibbs_sampler(M, burn_in, thin);
+    mvhost::close_chain();
+  }
 
   return Rcpp::List::create(
       Rcpp::Named("table_of") = saved_table_of,

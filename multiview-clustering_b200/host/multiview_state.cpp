@@ -37,6 +37,7 @@ int table_capacity = 64;
 unsigned long long seed = 1999ull;
 int engine = MVG_ENGINE_AUTO;
 std::vector<int> view_dim;
+bool sequential = false;
 static mvg_handle* g_chain = nullptr;
 
 mvg_handle* chain() { return g_chain; }

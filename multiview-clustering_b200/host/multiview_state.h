@@ -56,6 +56,7 @@ extern int table_capacity;          // table / dish slots per view on the device
 extern unsigned long long seed;     // Philox key (set.seed(1999) of New_Simulation.R:12 by default)
 extern int engine;                  // MVG_ENGINE_* (0 = automatic)
 extern std::vector<int> view_dim;   // D_v; empty = all 1 (the reference's scalar views)
+extern bool sequential;             // true: run_gibbs_cpp uses MVG_ENGINE_SEQ, the reference-exact sequential sampler (scalar views)
 mvg_handle* chain();                // the live device chain or nullptr
 void open_chain();                  // create the handle from n, d, y, view_dim and upload the views
 void close_chain();

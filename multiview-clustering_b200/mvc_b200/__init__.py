@@ -123,6 +123,9 @@ def lib():
         L.mvg_profile_sweep.argtypes = [H, C.c_int32, _f32p]
         L.mvg_stream.restype = C.c_void_p
         L.mvg_stream.argtypes = [H]
+        L.mvg_seq_run.argtypes = [C.c_int32, C.c_int32, C.c_int32, _f64p, C.c_int32, C.c_int32, C.c_int32, C.c_uint64, C.c_int32,
+                                  C.c_int32, C.c_int32, _i32p, _i32p, _i32p, _f64p, _i32p, C.POINTER(C.c_uint64)]
+        L.mvg_seq_last_error.restype = C.c_char_p
         L.mvg_philox4x32_10.argtypes = [_u32p, _u32p, _u32p]
         args = [C.c_uint64, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint64]
         L.mvg_philox_uniform_f32.restype = C.c_float
@@ -511,3 +514,27 @@ def run_gibbs(data_views, M, burn_in, thin, cap=64, seed=1999, device=0, engine=
         "alpha_global": hyp[:, 3 * V],
         "sigma_global": hyp[:, 3 * V + 1],
     }
+
+
+def run_gibbs_seq(data_views, M, burn_in, thin, seed=1999, device=0, t_cap=1024, k_cap=None):
+    """MVG_ENGINE_SEQ: run_gibbs_cpp of the reference, rule for rule, on the device (scalar views; one thread per chain).
+    Returns the reference's eight keys; table_of is 0-based and dense, dish_of[s][v] has one entry per live table."""
+    y = np.ascontiguousarray(np.stack([np.asarray(v, np.float64).reshape(-1) for v in data_views]))
+    d, n = y.shape
+    S = max(0, (M - burn_in + thin - 1) // thin) if M > burn_in else 0
+    k_cap = int(k_cap or (2 * M + 64))
+    tab = np.zeros((max(S, 1), n), np.int32)
+    T = np.zeros(max(S, 1), np.int32)
+    dish = np.zeros((max(S, 1), d, t_cap), np.int32)
+    hyp = np.zeros((max(S, 1), 3 * d + 2), np.float64)
+    ns, calls = C.c_int32(0), C.c_uint64(0)
+    L = lib()
+    rc = L.mvg_seq_run(device, n, d, _p(y, _f64p), M, burn_in, thin, seed, t_cap, k_cap, S, _p(tab, _i32p), _p(T, _i32p),
+                       _p(dish, _i32p), _p(hyp, _f64p), C.byref(ns), C.byref(calls))
+    if rc != 0:
+        raise MvgError(rc, L.mvg_seq_last_error().decode())
+    S = ns.value
+    return {"table_of": [tab[s] for s in range(S)], "dish_of": [[dish[s, v, :T[s]] for v in range(d)] for s in range(S)],
+            "loglik": [], "alpha_v": [hyp[:S, v] for v in range(d)], "sigma_v": [hyp[:S, d + v] for v in range(d)],
+            "tau_v": [hyp[:S, 2 * d + v] for v in range(d)], "alpha_global": hyp[:S, 3 * d], "sigma_global": hyp[:S, 3 * d + 1],
+            "stream_calls": int(calls.value)}

@@ -40,6 +40,13 @@ int host_run(int n_, int d_, const double* y_, int M, int burn_in, int thin, int
     return -1;
   }
 }
+// the same through MVG_ENGINE_SEQ (mvhost::sequential)
+int host_run_seq(int n_, int d_, const double* y_, int M, int burn_in, int thin, unsigned long long seed) {
+  mvhost::sequential = true;
+  const int rc = host_run(n_, d_, y_, M, burn_in, thin, 64, seed);
+  mvhost::sequential = false;
+  return rc;
+}
 int host_saved_T(int s) { return (int)saved_dish_of[(size_t)s][0].size(); }
 void host_saved_table_of(int s, int* out) { std::memcpy(out, saved_table_of[(size_t)s].data(), sizeof(int) * saved_table_of[(size_t)s].size()); }
 void host_saved_dish_of(int s, int v, int* out) { std::memcpy(out, saved_dish_of[(size_t)s][(size_t)v].data(), sizeof(int) * saved_dish_of[(size_t)s][(size_t)v].size()); }

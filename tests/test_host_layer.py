@@ -126,3 +126,28 @@ def test_utils_inspectors_on_the_mirrored_state_equal_the_compiled_reference(ora
         np.testing.assert_allclose(hpn.value, pn, rtol=2e-4)
     for which in range(4):
         assert L.host_mutator_raises(which) == 1 and b"not supported on the device chain" in L.host_last_error()
+
+
+@pytest.mark.gpu
+def test_run_gibbs_cpp_sequential_engine_equals_the_compiled_reference(oracle):
+    """mvhost::sequential = true: run_gibbs_cpp (host C++, the reference's signature) on MVG_ENGINE_SEQ returns the partitions
+    the UNMODIFIED reference returns for the same data and seed — chain-level integer equality through the host layer."""
+    if not oracle.have_ref():
+        pytest.skip("compiled reference not available")
+    views, _ = c1_data(300)
+    y = np.ascontiguousarray(np.stack([v.astype(np.float64) for v in views]))
+    L = build_host()
+    L.host_last_error.restype = C.c_char_p
+    S = L.host_run_seq(300, 2, y.ctypes.data_as(C.POINTER(C.c_double)), 200, 100, 20, C.c_ulonglong(11))
+    tr = oracle.ref_run_gibbs(y, 200, 100, 20, seed=11)
+    assert S == len(tr) == 5, L.host_last_error()
+    for s in range(S):
+        tab = np.empty(300, np.int32)
+        L.host_saved_table_of(s, tab.ctypes.data_as(C.POINTER(C.c_int)))
+        np.testing.assert_array_equal(tab, tr[s]["table_of"])
+        T = L.host_saved_T(s)
+        assert T == tr[s]["dish_of"].shape[1]
+        for v in range(2):
+            dish = np.empty(T, np.int32)
+            L.host_saved_dish_of(s, v, dish.ctypes.data_as(C.POINTER(C.c_int)))
+            np.testing.assert_array_equal(dish, tr[s]["dish_of"][v])
