@@ -29,7 +29,11 @@
  *   - table and dish slots have a fixed capacity `cap`; a new table can only open in a slot that
  *     was free at sweep start, births are seated in global row order and the overflow stays put;
  *   - the random stream is Philox4x32-10 addressed by (seed, chain, sweep, row, slot) instead of
- *     R's call-ordered generator.
+ *     R's call-ordered generator;
+ *   - a customer for whom NO option has weight stays at its own table; the reference seats it at table 0 without drawing
+ *     (multiview_gibbs.cpp:172-176) — a slot index has no meaning across recycled slots;
+ *   - mvg_set_sweep_blocks moves the sweep back towards the reference's sequential order; mvg_seq_run (MVG_ENGINE_SEQ) IS
+ *     the reference's sampler, rule for rule, for its own scalar-view configuration (see below).
  *
  * Threading: a handle is not re-entrant; calls on one handle must be serialised by the caller.
  * Every call returns MVG_OK (0) or a negative MVG_E*; mvg_last_error gives the message.

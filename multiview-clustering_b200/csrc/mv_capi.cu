@@ -96,6 +96,11 @@ struct mvg_handle {
   int stats_mode = 0;
   int rebuild_every = 64;
   int since_full = 0;                // incremental sweeps since the last full rebuild
+  // The captured sweep is ordered tail-first: pack -> stats -> reduce -> finalize -> DRAW of the next sweep, the draw being
+  // the programmatic successor of finalize (its set-up and first feature loads overlap the serial tail).  So between
+  // replays the draw of the next sweep has already run: a pure function of the state, discarded (the flag cleared) by
+  // anything that changes the state other than a sweep.
+  bool draw_pending = false;
   bool graphs_ok = true;
   int64_t sweeps_issued = 0;
   // peer-memory exchange (optional; ncclAllGather otherwise)
@@ -243,9 +248,9 @@ int rebuild_pipeline(mvg_handle* h, int32_t flags, cudaEvent_t* marks /* 4 event
   return MVG_OK;
 }
 
-int launch_draw(mvg_handle* h) {
+int launch_draw(mvg_handle* h, bool programmatic = false) {
   if (h->engine == MVG_ENGINE_TCGEN05 || h->engine == MVG_ENGINE_TCGEN05_FAST)
-    MVG_CUDA(h, launch_draw_tc(h->c, h->tc_maps, h->engine == MVG_ENGINE_TCGEN05_FAST, h->stream));
+    MVG_CUDA(h, launch_draw_tc(h->c, h->tc_maps, h->engine == MVG_ENGINE_TCGEN05_FAST, programmatic, h->stream));
   else MVG_CUDA(h, launch_draw_simt(h->c, h->stream));
   h->launches += 1 + ((h->engine == MVG_ENGINE_SIMT && h->c.n_count_views) ? 1 : 0);
   return MVG_OK;
@@ -368,6 +373,7 @@ int mvg_destroy(mvg_handle* h) {
 }
 
 static void invalidate_graphs(mvg_handle* h) {     // kernel arguments are baked into a captured sweep
+  h->draw_pending = false;
   for (auto& g : h->sweep_graph) if (g) { cudaGraphExecDestroy(g); g = nullptr; }
 }
 
@@ -511,6 +517,7 @@ int mvg_get_debug_loo(mvg_handle* h, float* loo) {
 
 int mvg_init_state_reference(mvg_handle* h) {
   if (!h) return MVG_EINVAL;
+  h->draw_pending = false;
   MVG_CUDA(h, cudaSetDevice(h->cfg.device));
   int rc = ensure_layout(h);
   if (rc != MVG_OK) return rc;
@@ -528,6 +535,7 @@ int mvg_init_state_reference(mvg_handle* h) {
 
 int mvg_set_state(mvg_handle* h, const mvg_state_host* s) {
   if (!h || !s) return MVG_EINVAL;
+  h->draw_pending = false;
   MVG_CUDA(h, cudaSetDevice(h->cfg.device));
   int rc = ensure_layout(h);
   if (rc != MVG_OK) return rc;
@@ -607,8 +615,9 @@ int one_sweep(mvg_handle* h, int32_t flags, bool delta) {
   const int B = h->c.blk_count;
   for (int b = 0; b < B; ++b) {
     h->c.blk_index = b;
-    int rc;
-    { NvtxRange r("mvg:likelihood+draw"); rc = launch_draw(h); }
+    int rc = MVG_OK;
+    if (!(h->draw_pending && B == 1)) { NvtxRange r("mvg:likelihood+draw"); rc = launch_draw(h); }
+    h->draw_pending = false;
     if (rc != MVG_OK) return rc;
     { NvtxRange r("mvg:pack births"); MVG_CUDA(h, launch_pack(h->c, h->stream)); }
     h->launches += 1;
@@ -619,11 +628,24 @@ int one_sweep(mvg_handle* h, int32_t flags, bool delta) {
   return MVG_OK;
 }
 
+// The sweep as it is captured: everything after the draw, then the draw of the NEXT sweep as the programmatic successor of
+// k_finalize.
+int sweep_tail_then_draw(mvg_handle* h, int32_t flags, bool delta) {
+  { NvtxRange r("mvg:pack births"); MVG_CUDA(h, launch_pack(h->c, h->stream)); }
+  h->launches += 1;
+  int rc = rebuild_pipeline(h, flags, nullptr, delta);
+  if (rc != MVG_OK) return rc;
+  NvtxRange r("mvg:likelihood+draw (next sweep)");
+  static const bool no_pdl = [] { const char* e = getenv("MVG_NO_PDL"); return e && e[0] == '1'; }();   // (A/B switch for measurements)
+  return launch_draw(h, /*programmatic=*/h->c.n_count_views == 0 && !no_pdl);
+}
+
 // Capture one sweep into an executable graph (once per handle and hyper-step variant).  Returns false, leaving the
 // stream usable, if anything about the capture fails: the caller then launches the kernels directly.
 bool ensure_sweep_graph(mvg_handle* h, int which, int32_t flags, bool delta) {
   if (h->sweep_graph[which]) return true;
-  if (!h->graphs_ok || (h->c.debug_export & 2) || h->c.blk_count > 1) return false;
+  // (debug handles read back what the LAST draw exported: no draw of the next sweep may have run behind their back)
+  if (!h->graphs_ok || h->c.debug_export != 0 || h->c.blk_count > 1) return false;
   // NCCL transport: launched directly (a collective captured into the sweep graph did not complete on this stack);
   // the peer-memory transport is an ordinary kernel and is captured with the rest of the sweep
   if (h->c.world != 1 && !h->xp2p) return false;
@@ -631,7 +653,7 @@ bool ensure_sweep_graph(mvg_handle* h, int which, int32_t flags, bool delta) {
   if (disabled) { h->graphs_ok = false; return false; }
   const int64_t before = h->launches;
   if (cudaStreamBeginCapture(h->stream, cudaStreamCaptureModeThreadLocal) != cudaSuccess) { cudaGetLastError(); h->graphs_ok = false; return false; }
-  const int rc = one_sweep(h, flags, delta);
+  const int rc = sweep_tail_then_draw(h, flags, delta);
   cudaGraph_t g = nullptr;
   const cudaError_t e = cudaStreamEndCapture(h->stream, &g);
   h->sweep_graph_launches[which] = h->launches - before;
@@ -660,9 +682,15 @@ int mvg_sweep(mvg_handle* h, int32_t n_sweeps, int32_t do_hyper) {
     const int which = (do_hyper ? 1 : 0) + (delta ? 2 : 0);
     const bool use_graph = (n_sweeps >= 2 || h->sweeps_issued >= 1) && ensure_sweep_graph(h, which, flags, delta);
     if (use_graph) {
+      if (!h->draw_pending) {                        // the first sweep of a run: its draw is not in flight yet
+        NvtxRange r("mvg:likelihood+draw");
+        const int rc = launch_draw(h);
+        if (rc != MVG_OK) return rc;
+      }
       NvtxRange r("mvg:sweep (graph replay)");
       MVG_CUDA(h, cudaGraphLaunch(h->sweep_graph[which], h->stream));
       h->launches += h->sweep_graph_launches[which];
+      h->draw_pending = true;
     } else {
       const int rc = one_sweep(h, flags, delta);
       if (rc != MVG_OK) return rc;
@@ -696,6 +724,7 @@ int mvg_hyper_step_parts(mvg_handle* h, int32_t parts) {
   if (!h) return MVG_EINVAL;
   if (!h->state_ready) return fail(h, MVG_ESTATE, "no state yet");
   if (parts & ~(MVG_HYPER_TAU | MVG_HYPER_LOCAL | MVG_HYPER_GLOBAL)) return fail(h, MVG_EINVAL, "unknown hyper part");
+  h->draw_pending = false;                           // the parameters are about to change
   MVG_CUDA(h, cudaSetDevice(h->cfg.device));
   // rebuild the statistics of the current assignment, then the selected Metropolis-Hastings updates
   // (no draw, no reseat).  The sweep counter that addresses the Philox stream does not advance.
@@ -969,6 +998,7 @@ int mvg_profile_sweep(mvg_handle* h, int32_t do_hyper, float ms_out[6]) {
   if (!h->state_ready) return fail(h, MVG_ESTATE, "no state yet");
   MVG_CUDA(h, cudaSetDevice(h->cfg.device));
   const int32_t flags = kFinReseat | kFinAdvance | (do_hyper ? kFinHyperAll : 0);
+  h->draw_pending = false;                           // (the draw is a pure function of the state: run again under the events)
   MVG_CUDA(h, cudaEventRecord(h->ev[2], h->stream));
   int rc = launch_draw(h);
   if (rc != MVG_OK) return rc;

@@ -139,7 +139,7 @@ enum FinalizeFlags : int32_t {
 
 // launchers (definitions in the .cu files)
 cudaError_t launch_draw_simt(const Ctx& c, cudaStream_t s);
-cudaError_t launch_draw_tc(const Ctx& c, const void* maps, bool fast_exp, cudaStream_t s);
+cudaError_t launch_draw_tc(const Ctx& c, const void* maps, bool fast_exp, bool programmatic, cudaStream_t s);
 bool draw_tc_supported(const Ctx& c);
 size_t draw_tc_maps_bytes();                                   // host blob holding the TMA tensor maps
 cudaError_t draw_tc_make_maps(const Ctx& c, void* maps_out);  // (re)encode them for the current pointers

@@ -207,6 +207,11 @@ __device__ __forceinline__ bool elect_one() {
   return pred != 0;
 }
 
+// Programmatic dependent launch: when this kernel is launched as the programmatic successor of k_finalize (the sweep graph,
+// csrc/mv_capi.cu), its CTAs start while k_finalize is still running; everything k_finalize (or an earlier kernel of the
+// sweep) writes may only be touched after this wait.  A no-op for an ordinary launch.
+__device__ __forceinline__ void grid_dependency_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
 template <int REGS> __device__ __forceinline__ void reg_dec() { asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(REGS)); }
 template <int REGS> __device__ __forceinline__ void reg_inc() { asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(REGS)); }
 
@@ -336,37 +341,13 @@ __global__ void __launch_bounds__(kThreads, 1) k_draw_tc(const Ctx c, const __gr
   const uint32_t b_full = bar0 + 8u * (2 * kRawStages + 2 * kLoStages + 2 * kDStages);
 
   // ---- one-time setup --------------------------------------------------------------------------
+  // Nothing here depends on the previous kernels of the sweep: with a programmatic launch it runs — like the first
+  // feature loads and their conversion below — while k_finalize is still computing the parameters.
   TcViewParams* s_p = reinterpret_cast<TcViewParams*>(s_tp);
   float* s_dlm = reinterpret_cast<float*>(smem + SmemLayout::dlm_off);
-  int lone_ok = 1;                                    // every live table's dishes are served by that table alone?
-  for (int i = tid; i < V * 64; i += kThreads) {
-    const int v = i >> 6, t = i & 63;
-    const TableParam q = c.tparam[i];
-    TcViewParams& P = s_p[v];
-    P.A[t] = q.A; P.C[t] = q.C; P.W[t] = q.W;
-    P.A1[t] = q.A1; P.C1[t] = q.C1; P.W1[t] = q.W1;
-    P.R[t] = (q.A != 0.0f) ? __fdiv_rn(q.A1, q.A) : 0.0f;
-    // bit 0: the dish is served by this table alone; bit 1: the dish is SMALL (<= ~500 customers: R = 1 + 2 / (tau + n - 1),
-    // or n < 2), where removing the customer changes its likelihood by orders of magnitude (see lse_chunk)
-    P.lone[t] = (q.lone ? 1 : 0) | ((q.dish >= 0 && (P.R[t] > 1.004f || P.R[t] == 0.0f)) ? 2 : 0);
-    if (q.dish >= 0 && !q.lone) lone_ok = 0;
-  }
-  for (int t = tid; t < 64; t += kThreads) {
-    const TableMass m = c.tmass[t];
-    s_tm[t] = m;
-    float b = m.LM;
-    for (int v = 0; v < V; ++v) b = __fadd_rn(b, c.tparam[v * 64 + t].C);
-    s_lm[t] = b;                                      // base: log2 table mass + the views' offsets, in view order
-    s_dlm[t] = __fadd_rn(m.LM1, -m.LM);               // what changes for the customer's own table (n_t - 1)
-  }
   unsigned long long* s_same = reinterpret_cast<unsigned long long*>(smem + SmemLayout::same_off);
-  for (int i = tid; i < V * 64; i += kThreads) s_same[i] = c.tsame[i];
-  if (tid < V) s_vp[tid] = c.vparam[tid];
   if (tid == 0) {
-    const GlobalParam g = *c.gparam;
-    s_misc[1] = g.sweep;
-    s_misc[2] = __float_as_uint(g.LMN0);
-    s_misc[3] = __float_as_uint(g.LMN1);
+    s_misc[4] = 1u;                                    // all_lone, and-ed down by the threads that stage the parameters
     for (int s = 0; s < kRawStages; ++s) { mbar_init(raw_full(s), 1); mbar_init(raw_empty(s), 5); }     // the four warps of one converter warpgroup + the MMA commit
     for (int s = 0; s < kLoStages; ++s) { mbar_init(lo_full(s), 8); mbar_init(lo_empty(s), 1); }        // the eight converter warps
     for (int s = 0; s < kDStages; ++s) { mbar_init(d_full(s), 1); mbar_init(d_empty(s), 8); }     // the eight warps of a pair
@@ -380,13 +361,9 @@ __global__ void __launch_bounds__(kThreads, 1) k_draw_tc(const Ctx c, const __gr
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
   }
   tc_fence_before();
-  const bool all_lone_rt = __syncthreads_and(lone_ok) != 0;
+  __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = s_misc[0];
-  const uint32_t sweep = s_misc[1];
-  GlobalParam gp;
-  gp.LMN0 = __uint_as_float(s_misc[2]);
-  gp.LMN1 = __uint_as_float(s_misc[3]);
 
   const int n_tiles = (c.n_rows + kTileRows - 1) / kTileRows;
   const bool prof = DEBUG && (c.debug_export & 2) != 0 && c.dbg_prof != nullptr;
@@ -400,18 +377,27 @@ __global__ void __launch_bounds__(kThreads, 1) k_draw_tc(const Ctx c, const __gr
     reg_dec<24>();
     if (warp == 0 && lane == 0) {
       // ---- TMA producer ----
-      mbar_expect_tx(b_full, (uint32_t)(V * 4 * kBHalfBytes));
-      for (int v = 0; v < V; ++v)
-        for (int part = 0; part < 2; ++part)         // 0: m_hi, 1: m_lo
-          for (int h = 0; h < 2; ++h)
-            tma_load_2d(sbase + SmemLayout::b_off + ((v * 2 + part) * 2 + h) * kBHalfBytes,
-                        part ? &maps.mean_lo : &maps.mean_hi, b_full, h * kHalfCols, v * 64);
+      // The features do not depend on the sweep's parameters: the first ring of tile halves is requested right away; the
+      // B operand (this sweep's scaled means, written by k_finalize) only after the grid dependency has resolved.
       Ring r(kRawStages);
       const uint64_t stream_policy = l2_evict_first_policy();
+      int issued = 0;
+      bool b_loaded = false;
+      auto load_b = [&]() {
+        grid_dependency_wait();
+        mbar_expect_tx(b_full, (uint32_t)(V * 4 * kBHalfBytes));
+        for (int v = 0; v < V; ++v)
+          for (int part = 0; part < 2; ++part)         // 0: b_hi, 1: b_lo
+            for (int h = 0; h < 2; ++h)
+              tma_load_2d(sbase + SmemLayout::b_off + ((v * 2 + part) * 2 + h) * kBHalfBytes,
+                          part ? &maps.mean_lo : &maps.mean_hi, b_full, h * kHalfCols, v * 64);
+        b_loaded = true;
+      };
       for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x)
         for (int v = 0; v < V; ++v)
 #pragma unroll 1
           for (int h = 0; h < 2; ++h) {
+            if (issued == kRawStages && !b_loaded) load_b();   // the ring is full: nothing more to do without the MMAs
             mbar_wait_t(raw_empty(r.stage), r.phase ^ 1u, prof, w0);
             mbar_expect_tx(raw_full(r.stage), kHalfBytes);
             tma_load_2d_hint(sbase + SmemLayout::raw_off + r.stage * kHalfBytes, &maps.x[v], raw_full(r.stage),
@@ -424,7 +410,9 @@ __global__ void __launch_bounds__(kThreads, 1) k_draw_tc(const Ctx c, const __gr
                                "l"(stream_policy) : "memory");
             }
             r.next();
+            ++issued;
           }
+      if (!b_loaded) load_b();
       if (prof) { prof_out[0] = w0; prof_out[1] = clock64() - t_start; }
     } else if (warp >= 1 && warp <= kMmaWarps) {
       // ---- MMA issuers: warps 1 and 2 take alternate tile-views.  One tcgen05.mma of this shape keeps the
@@ -543,6 +531,47 @@ __global__ void __launch_bounds__(kThreads, 1) k_draw_tc(const Ctx c, const __gr
     // =========================== WG3..WG6: epilogue (thread r <-> TMEM lane r <-> customer r) ====
     // pool: 896 threads x 72 registers = 128 x (24 + 2*48 + 4*96)
     reg_inc<96>();
+    // ---- this sweep's parameters: staged by the 512 epilogue threads once the grid dependency has resolved ----
+    grid_dependency_wait();
+    {
+      const int et = tid - 3 * 128;                     // 0 .. 511
+      int lone_ok = 1;                                  // every live table's dishes are served by that table alone?
+      for (int i = et; i < V * 64; i += 512) {
+        const int v = i >> 6, t = i & 63;
+        const TableParam q = c.tparam[i];
+        TcViewParams& P = s_p[v];
+        P.A[t] = q.A; P.C[t] = q.C; P.W[t] = q.W;
+        P.A1[t] = q.A1; P.C1[t] = q.C1; P.W1[t] = q.W1;
+        P.R[t] = (q.A != 0.0f) ? __fdiv_rn(q.A1, q.A) : 0.0f;
+        // bit 0: the dish is served by this table alone; bit 1: the dish is SMALL (<= ~500 customers: R = 1 + 2 / (tau + n - 1),
+        // or n < 2), where removing the customer changes its likelihood by orders of magnitude (see lse_chunk)
+        P.lone[t] = (q.lone ? 1 : 0) | ((q.dish >= 0 && (P.R[t] > 1.004f || P.R[t] == 0.0f)) ? 2 : 0);
+        if (q.dish >= 0 && !q.lone) lone_ok = 0;
+        s_same[i] = c.tsame[i];
+      }
+      for (int t = et; t < 64; t += 512) {
+        const TableMass m = c.tmass[t];
+        s_tm[t] = m;
+        float b = m.LM;
+        for (int v = 0; v < V; ++v) b = __fadd_rn(b, c.tparam[v * 64 + t].C);
+        s_lm[t] = b;                                    // base: log2 table mass + the views' offsets, in view order
+        s_dlm[t] = __fadd_rn(m.LM1, -m.LM);             // what changes for the customer's own table (n_t - 1)
+      }
+      if (et < V) s_vp[et] = c.vparam[et];
+      if (et == 64) {
+        const GlobalParam g = *c.gparam;
+        s_misc[1] = g.sweep;
+        s_misc[2] = __float_as_uint(g.LMN0);
+        s_misc[3] = __float_as_uint(g.LMN1);
+      }
+      if (!lone_ok) atomicAnd(&s_misc[4], 0u);
+      asm volatile("bar.sync 9, 512;" ::: "memory");    // the epilogue warpgroups only: the other roles never read these
+    }
+    const uint32_t sweep = s_misc[1];
+    GlobalParam gp;
+    gp.LMN0 = __uint_as_float(s_misc[2]);
+    gp.LMN1 = __uint_as_float(s_misc[3]);
+    const bool all_lone_rt = s_misc[4] != 0u;
     // Two CTA-uniform properties of the sweep select one of four copies of the loop, so that the registers and the code of
     // the rarer cases stay out of the common one:
     //   with_new   a table slot is free: the new-table option has weight and the per-view marginals are evaluated;
@@ -904,7 +933,7 @@ cudaError_t draw_tc_make_maps(const Ctx& c, void* maps_out) {
   return cudaSuccess;
 }
 
-cudaError_t launch_draw_tc(const Ctx& c, const void* maps, bool fast, cudaStream_t s) {
+cudaError_t launch_draw_tc(const Ctx& c, const void* maps, bool fast, bool programmatic, cudaStream_t s) {
   if (c.n_rows <= 0) return cudaSuccess;
   if (!draw_tc_supported(c) || !maps) return cudaErrorInvalidValue;
   int dev = 0, sms = 148;
@@ -916,8 +945,17 @@ cudaError_t launch_draw_tc(const Ctx& c, const void* maps, bool fast, cudaStream
   auto kern = fast ? (dbg ? k_draw_tc<true, true> : k_draw_tc<true, false>) : (dbg ? k_draw_tc<false, true> : k_draw_tc<false, false>);
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SmemLayout::total);
   if (e != cudaSuccess) return e;
-  kern<<<grid, kThreads, SmemLayout::total, s>>>(c, *static_cast<const TcMaps*>(maps));
-  return cudaGetLastError();
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(grid);
+  cfg.blockDim = dim3(kThreads);
+  cfg.dynamicSmemBytes = SmemLayout::total;
+  cfg.stream = s;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;   // may start while its predecessor in the stream still runs;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;             // the kernel orders itself with griddepcontrol.wait
+  cfg.attrs = attr;
+  cfg.numAttrs = programmatic ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kern, c, *static_cast<const TcMaps*>(maps));
 }
 
 }  // namespace mv

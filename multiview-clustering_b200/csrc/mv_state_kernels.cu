@@ -560,6 +560,9 @@ __device__ __forceinline__ void draw_level_randoms(FinShared& S, uint64_t seed, 
 __global__ void __launch_bounds__(kFinThreads, 1) k_finalize(const Ctx c, const int32_t flags, const int32_t s1_in_smem) {
   extern __shared__ __align__(16) unsigned char fin_smem[];
   FinShared& S = *reinterpret_cast<FinShared*>(fin_smem);
+  // Programmatic dependent launch: the next sweep's draw kernel may be scheduled now (its CTAs set themselves up and
+  // start streaming features on the idle SMs; they wait for this grid's completion before they touch its results).
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
   const int tid = threadIdx.x;
   const int cap = c.cap, V = c.V;
   const int role = blockIdx.x;                      // < V: that view; V: the franchise level
