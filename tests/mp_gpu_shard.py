@@ -38,6 +38,11 @@ def main():
         handles = [None] * world
         dist.all_gather_object(handles, s.p2p_export())
         s.p2p_attach(handles)
+        try:                                                  # a second attach is refused: mappings and sequence number persist
+            s.p2p_attach(handles)
+            raise SystemExit("second p2p_attach was accepted")
+        except mvc_b200.MvgError as e:
+            assert e.code == -4, e
     if os.environ.get("MVG_TEST_INCR") == "1":                # incremental statistics on every shard
         s.set_stats_mode(True, 64)
     s.set_state(tab[lo:hi], dish, *hyp)

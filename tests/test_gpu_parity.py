@@ -836,3 +836,33 @@ def test_real_reuters_collection_on_the_gpu(oracle):
     live = int((s.get_state(with_rows=False)["n_t"] > 0).sum())
     print(f"\n[reuters] 26 sweeps on the real collection: {live} tables live, draw agreement with the FP64 restatement {agree:.5f}")
     s.close()
+
+
+def test_blocked_sweeps_and_statistics_modes_are_deterministic_and_conserve_customers():
+    """mvg_set_sweep_blocks / mvg_set_stats_mode: a chain is a function of (data, seed, start, blocks) — two handles agree
+    exactly; blocks = 1 is the plain sweep; customers are conserved; bad arguments are rejected."""
+    import mvc_b200
+    views, _ = c1_data(400)
+    def chain(blocks, sweeps=40):
+        s = mvc_b200.Sampler(400, [1, 1], cap=32, seed=5, engine=1)
+        for v, x in enumerate(views):
+            s.upload_view(v, x.reshape(-1, 1))
+        if blocks is not None:
+            s.set_sweep_blocks(blocks)
+        s.init_state_reference()
+        s.sweep(sweeps, do_hyper=True)
+        st = s.get_state()
+        s.close()
+        return st
+    a, b, c, d = chain(8), chain(8), chain(1), chain(None)
+    for k in ("table_of", "n_t", "dish_of", "n_vk", "tau_v", "alpha_v"):
+        np.testing.assert_array_equal(a[k], b[k], err_msg=k)
+        np.testing.assert_array_equal(c[k], d[k], err_msg=k)
+    assert int(a["n_t"].sum()) == 400 and int(c["n_t"].sum()) == 400
+    assert not np.array_equal(a["table_of"], c["table_of"])          # blocking changes the chain (it sees fresher statistics)
+    s = mvc_b200.Sampler(64, [1], cap=32, seed=1, engine=1)
+    for bad in (lambda: s.set_sweep_blocks(0), lambda: s.set_stats_mode(True, 0)):
+        with pytest.raises(mvc_b200.MvgError) as e:
+            bad()
+        assert e.value.code == -1
+    s.close()
