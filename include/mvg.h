@@ -142,6 +142,12 @@ int mvg_init_state_reference(mvg_handle* h);
  * sufficient statistics are rebuilt on the device. */
 int mvg_set_state(mvg_handle* h, const mvg_state_host* s);
 int mvg_get_state(mvg_handle* h, const mvg_state_host* out);
+/* Binary checkpoint of the chain state in a file (the reference keeps its chain in process globals and has
+ * no resume: multiview_state.cpp:4-16, multiview_gibbs.cpp:117): assignments, dish_of, hyperparameters, sweep counter.
+ * Loading into a handle of the same shape with the same views restarts the chain bit-identically (statistics are rebuilt in
+ * a fixed order, draws are addressed by (seed, sweep, row)); with the views of a row shard, each rank saves / loads its own file. */
+int mvg_save_checkpoint(mvg_handle* h, const char* path);
+int mvg_load_checkpoint(mvg_handle* h, const char* path);
 
 /* ---- the hot path ---------------------------------------------------------------------- */
 /* n_sweeps synchronous allocation sweeps, each followed by the hyper step when do_hyper != 0.

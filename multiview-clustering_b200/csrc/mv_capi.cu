@@ -571,6 +571,66 @@ int mvg_set_state(mvg_handle* h, const mvg_state_host* s) {
   return check_status(h);
 }
 
+// ---- binary checkpoint of the chain state ------------------------------------------------------
+// File: "MVGCKPT1", then int64 {n_rows, V, cap, seed, chain, row_offset, n_rows_global, sweep}, then table_of int32[n_rows],
+// dish_of int32[V*cap], hyp double[3V+2].  Everything else (counts, sums, parameters) is a function of these and of the
+// data, and is rebuilt on load exactly as mvg_set_state rebuilds it.
+namespace {
+const char kCkptMagic[8] = {'M', 'V', 'G', 'C', 'K', 'P', 'T', '1'};
+}
+
+int mvg_save_checkpoint(mvg_handle* h, const char* path) {
+  if (!h || !path) return MVG_EINVAL;
+  if (!h->state_ready) return fail(h, MVG_ESTATE, "no state yet");
+  const Ctx& c = h->c;
+  std::vector<int32_t> tab((size_t)c.n_rows), dish((size_t)c.V * c.cap);
+  std::vector<double> av(c.V), sv(c.V), tv(c.V);
+  double ag[2];
+  uint32_t sweep = 0;
+  mvg_state_host st{};
+  st.table_of = tab.data(); st.dish_of = dish.data(); st.alpha_v = av.data(); st.sigma_v = sv.data(); st.tau_v = tv.data();
+  st.alpha_sigma_global = ag; st.sweep = &sweep;
+  int rc = mvg_get_state(h, &st);
+  if (rc != MVG_OK) return rc;
+  FILE* f = fopen(path, "wb");
+  if (!f) return fail(h, MVG_EINVAL, std::string("cannot open ") + path + " for writing");
+  const int64_t hdr[8] = {c.n_rows, c.V, c.cap, (int64_t)c.seed, (int64_t)c.chain, c.row_offset, c.n_global, (int64_t)sweep};
+  std::vector<double> hyp;
+  hyp.insert(hyp.end(), av.begin(), av.end()); hyp.insert(hyp.end(), sv.begin(), sv.end()); hyp.insert(hyp.end(), tv.begin(), tv.end());
+  hyp.push_back(ag[0]); hyp.push_back(ag[1]);
+  bool ok = fwrite(kCkptMagic, 1, 8, f) == 8 && fwrite(hdr, sizeof(int64_t), 8, f) == 8 &&
+            fwrite(tab.data(), sizeof(int32_t), tab.size(), f) == tab.size() &&
+            fwrite(dish.data(), sizeof(int32_t), dish.size(), f) == dish.size() &&
+            fwrite(hyp.data(), sizeof(double), hyp.size(), f) == hyp.size();
+  ok = (fclose(f) == 0) && ok;
+  return ok ? MVG_OK : fail(h, MVG_EINVAL, std::string("short write to ") + path);
+}
+
+int mvg_load_checkpoint(mvg_handle* h, const char* path) {
+  if (!h || !path) return MVG_EINVAL;
+  const Ctx& c = h->c;
+  FILE* f = fopen(path, "rb");
+  if (!f) return fail(h, MVG_EINVAL, std::string("cannot open ") + path);
+  char magic[8];
+  int64_t hdr[8];
+  std::vector<int32_t> tab((size_t)c.n_rows), dish((size_t)c.V * c.cap);
+  std::vector<double> hyp((size_t)3 * c.V + 2);
+  bool ok = fread(magic, 1, 8, f) == 8 && memcmp(magic, kCkptMagic, 8) == 0 && fread(hdr, sizeof(int64_t), 8, f) == 8;
+  if (ok && (hdr[0] != c.n_rows || hdr[1] != c.V || hdr[2] != c.cap || hdr[5] != c.row_offset || hdr[6] != c.n_global)) {
+    fclose(f);
+    return fail(h, MVG_EINVAL, "checkpoint was written for another shape (n_rows, views, cap, shard)");
+  }
+  ok = ok && fread(tab.data(), sizeof(int32_t), tab.size(), f) == tab.size() &&
+       fread(dish.data(), sizeof(int32_t), dish.size(), f) == dish.size() && fread(hyp.data(), sizeof(double), hyp.size(), f) == hyp.size();
+  fclose(f);
+  if (!ok) return fail(h, MVG_EINVAL, std::string("not a checkpoint or truncated: ") + path);
+  uint32_t sweep = (uint32_t)hdr[7];
+  mvg_state_host st{};
+  st.table_of = tab.data(); st.dish_of = dish.data(); st.alpha_v = hyp.data(); st.sigma_v = hyp.data() + c.V; st.tau_v = hyp.data() + 2 * c.V;
+  st.alpha_sigma_global = hyp.data() + 3 * c.V; st.sweep = &sweep;
+  return mvg_set_state(h, &st);
+}
+
 int mvg_get_state(mvg_handle* h, const mvg_state_host* o) {
   if (!h || !o) return MVG_EINVAL;
   if (!h->state_ready) return fail(h, MVG_ESTATE, "no state yet: call mvg_set_state or mvg_init_state_reference");

@@ -52,6 +52,7 @@ double compute_log_likelihood() {
   double total = 0.0;
   for (int v = 0; v < d; ++v) {
     const ViewState& V = views[(size_t)v];
+    if ((size_t)v < mvhost::csr_views.size() && mvhost::csr_views[(size_t)v].vocab > 0) continue;   // Gaussian views only (as mvg_log_likelihood)
     const int D = mvhost::view_dim.empty() ? 1 : mvhost::view_dim[(size_t)v];
     const double tau = V.tau_v;
     for (int k = 0; k < V.K; ++k) {
@@ -69,16 +70,65 @@ double compute_log_likelihood() {
 // [[Rcpp::export]]
 Rcpp::List run_gibbs_cpp(const Rcpp::List& data_views,
                          int M, int burn_in, int thin) {
+  // data_views: per view a numeric vector (the reference's scalar views, multiview_gibbs.cpp:109-115), a numeric matrix
+  // (customers x features) or a Matrix::dgCMatrix of counts (customers x vocabulary: the X_body / X_title / X_topics of
+  // dataset/reuters/data pre-process.R:104-108, as sparse matrices).
   d = data_views.size();
-  n = Rcpp::as<Rcpp::NumericVector>(data_views[0]).size();
   y.clear();
   y.resize((size_t)d);
-  for (int v = 0; v < d; ++v) y[(size_t)v] = Rcpp::as<std::vector<double>>(data_views[v]);
-  if (!mvhost::view_dim.empty()) n /= mvhost::view_dim[0];   // matrix views arrive flattened row-major
+  const std::vector<int> flat_dims = mvhost::view_dim;         // caller-declared dims of row-major FLATTENED matrices, if any
+  mvhost::csr_views.assign((size_t)d, mvhost::CsrView{});
+  std::vector<int> dims((size_t)d, 1);
+  bool any_matrix = false;
+  n = -1;
+  for (int v = 0; v < d; ++v) {
+    SEXP el = data_views[v];
+    int rows = 0;
+    if (Rf_isS4(el) && Rcpp::S4(el).is("dgCMatrix")) {
+      // compressed sparse COLUMNS -> the compressed sparse ROWS the device takes (counting sort by row)
+      Rcpp::S4 m(el);
+      const Rcpp::IntegerVector mi = m.slot("i"), mp = m.slot("p"), dim = m.slot("Dim");
+      const Rcpp::NumericVector mx = m.slot("x");
+      rows = dim[0];
+      mvhost::CsrView& cv = mvhost::csr_views[(size_t)v];
+      cv.vocab = dim[1];
+      cv.rowptr.assign((size_t)rows + 1, 0);
+      for (size_t k = 0; k < (size_t)mi.size(); ++k) cv.rowptr[(size_t)mi[k] + 1] += 1;
+      for (int r = 0; r < rows; ++r) cv.rowptr[(size_t)r + 1] += cv.rowptr[(size_t)r];
+      cv.col.assign((size_t)mi.size(), 0);
+      cv.val.assign((size_t)mi.size(), 0.f);
+      std::vector<int> fill(cv.rowptr.begin(), cv.rowptr.end() - 1);
+      for (int c = 0; c < dim[1]; ++c)
+        for (int k = mp[c]; k < mp[c + 1]; ++k) {
+          const int pos = fill[(size_t)mi[k]]++;
+          cv.col[(size_t)pos] = c;
+          cv.val[(size_t)pos] = (float)mx[k];
+        }
+      dims[(size_t)v] = 0;
+      any_matrix = true;
+    } else if (Rf_isMatrix(el)) {
+      const Rcpp::NumericMatrix M(el);                         // column-major in R; the device takes row-major
+      rows = M.nrow();
+      dims[(size_t)v] = M.ncol();
+      y[(size_t)v].resize((size_t)rows * M.ncol());
+      for (int i = 0; i < rows; ++i)
+        for (int j = 0; j < M.ncol(); ++j) y[(size_t)v][(size_t)i * M.ncol() + j] = M(i, j);
+      any_matrix = true;
+    } else {
+      y[(size_t)v] = Rcpp::as<std::vector<double>>(el);
+      const int D = flat_dims.empty() ? 1 : flat_dims[(size_t)v];
+      rows = (int)y[(size_t)v].size() / D;
+      dims[(size_t)v] = D;
+      if (D != 1) any_matrix = true;
+    }
+    if (n < 0) n = rows;
+    else if (rows != n) Rcpp::stop("run_gibbs_cpp: the views have different numbers of customers");
+  }
+  if (any_matrix) mvhost::view_dim = dims;
 
   if (mvhost::sequential) {
     // MVG_ENGINE_SEQ: the reference's sequential sampler rule for rule on the device (csrc/mv_seq_core.h); scalar views
-    if (!mvhost::view_dim.empty()) Rcpp::stop("run_gibbs_cpp: the sequential engine takes scalar views");
+    if (any_matrix) Rcpp::stop("run_gibbs_cpp: the sequential engine takes scalar views");
     if (thin <= 0) Rcpp::stop("run_gibbs_cpp: thin must be positive");
     const int S = (M > burn_in) ? (M - burn_in + thin - 1) / thin : 0, t_cap = 1024;
     std::vector<double> flat((size_t)d * n);
@@ -115,6 +165,7 @@ Rcpp::List run_gibbs_cpp(const Rcpp::List& data_views,
     mvhost::close_chain();
   }
 
+  mvhost::view_dim = flat_dims;                                // (the caller's setting, not what this call derived)
   return Rcpp::List::create(
       Rcpp::Named("table_of") = saved_table_of,
       Rcpp::Named("dish_of") = saved_dish_of,

@@ -9,7 +9,10 @@
 namespace {
 constexpr double kEps = 1e-6;                        // multiview_hyper.cpp:13
 constexpr double kNegInf = -std::numeric_limits<double>::infinity();
-int dim_of(int v) { return mvhost::view_dim.empty() ? 1 : mvhost::view_dim[(size_t)v]; }
+int dim_of(int v) {
+  if ((size_t)v < mvhost::csr_views.size() && mvhost::csr_views[(size_t)v].vocab > 0) return 0;   // a count view has no Gaussian coordinates
+  return mvhost::view_dim.empty() ? 1 : mvhost::view_dim[(size_t)v];
+}
 }  // namespace
 
 // multiview_hyper.cpp:137-163: the literals every chain starts from; on the device they are set by

@@ -37,6 +37,7 @@ int table_capacity = 64;
 unsigned long long seed = 1999ull;
 int engine = MVG_ENGINE_AUTO;
 std::vector<int> view_dim;
+std::vector<CsrView> csr_views;
 bool sequential = false;
 static mvg_handle* g_chain = nullptr;
 
@@ -50,7 +51,8 @@ void fail(const char* where) {
   throw std::runtime_error(msg);
 }
 
-static int dim_of(int v) { return view_dim.empty() ? 1 : view_dim[(size_t)v]; }
+static bool is_counts(int v) { return (size_t)v < csr_views.size() && csr_views[(size_t)v].vocab > 0; }
+static int dim_of(int v) { return is_counts(v) ? 0 : (view_dim.empty() ? 1 : view_dim[(size_t)v]); }
 
 void close_chain() {
   if (g_chain) mvg_destroy(g_chain);
@@ -73,8 +75,15 @@ void open_chain() {
   cfg.rank = 0;
   cfg.world = 1;
   if (mvg_create(&cfg, &g_chain) != MVG_OK) fail("mvg_create");
-  for (int v = 0; v < d; ++v)
-    if (mvg_upload_view_f64(g_chain, v, y[(size_t)v].data(), dim_of(v)) != MVG_OK) fail("mvg_upload_view_f64");
+  for (int v = 0; v < d; ++v) {
+    if (is_counts(v)) {
+      const CsrView& cv = csr_views[(size_t)v];
+      if (mvg_upload_view_csr(g_chain, v, cv.rowptr.data(), cv.col.data(), cv.val.data(), (int64_t)cv.col.size(), cv.vocab) != MVG_OK)
+        fail("mvg_upload_view_csr");
+    } else if (mvg_upload_view_f64(g_chain, v, y[(size_t)v].data(), dim_of(v)) != MVG_OK) {
+      fail("mvg_upload_view_f64");
+    }
+  }
 }
 
 void pull_state() {

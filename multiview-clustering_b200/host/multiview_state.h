@@ -56,6 +56,8 @@ extern int table_capacity;          // table / dish slots per view on the device
 extern unsigned long long seed;     // Philox key (set.seed(1999) of New_Simulation.R:12 by default)
 extern int engine;                  // MVG_ENGINE_* (0 = automatic)
 extern std::vector<int> view_dim;   // D_v; empty = all 1 (the reference's scalar views)
+struct CsrView { std::vector<int> rowptr, col; std::vector<float> val; int vocab = 0; };
+extern std::vector<CsrView> csr_views;   // csr_views[v].vocab > 0: view v is a sparse COUNT view (a dgCMatrix in data_views), y[v] is empty
 extern bool sequential;             // true: run_gibbs_cpp uses MVG_ENGINE_SEQ, the reference-exact sequential sampler (scalar views)
 mvg_handle* chain();                // the live device chain or nullptr
 void open_chain();                  // create the handle from n, d, y, view_dim and upload the views

@@ -13,7 +13,10 @@ void mvhost_rcpp_stop(const std::string& msg);   // multiview_gibbs.cpp: Rcpp::s
 #endif
 
 namespace {
-int dim_of(int v) { return mvhost::view_dim.empty() ? 1 : mvhost::view_dim[(size_t)v]; }
+int dim_of(int v) {
+  if ((size_t)v < mvhost::csr_views.size() && mvhost::csr_views[(size_t)v].vocab > 0) return 0;   // a count view has no Gaussian coordinates
+  return mvhost::view_dim.empty() ? 1 : mvhost::view_dim[(size_t)v];
+}
 
 [[noreturn]] void not_on_device(const char* what) {
   const std::string msg = std::string(what) + ": not supported on the device chain (the sweep moves every customer on the "

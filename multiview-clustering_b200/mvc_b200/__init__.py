@@ -88,6 +88,8 @@ def lib():
         L.mvg_init_state_reference.argtypes = [H]
         L.mvg_set_state.argtypes = [H, C.POINTER(_StateHost)]
         L.mvg_get_state.argtypes = [H, C.POINTER(_StateHost)]
+        L.mvg_save_checkpoint.argtypes = [H, C.c_char_p]
+        L.mvg_load_checkpoint.argtypes = [H, C.c_char_p]
         L.mvg_sweep.argtypes = [H, C.c_int32, C.c_int32]
         L.mvg_hyper_step.argtypes = [H]
         L.mvg_set_sweep_blocks.argtypes = [H, C.c_int32]
@@ -312,6 +314,12 @@ class Sampler:
         o["alpha_g"], o["sigma_g"] = float(o["alpha_sigma_global"][0]), float(o["alpha_sigma_global"][1])
         o["sweep"] = int(o["sweep"][0])
         return o
+
+    def save_checkpoint(self, path):
+        self._ck(self.L.mvg_save_checkpoint(self.h, str(path).encode()))
+
+    def load_checkpoint(self, path):
+        self._ck(self.L.mvg_load_checkpoint(self.h, str(path).encode()))
 
     # -- hot path ---------------------------------------------------------------------------
     def sweep(self, n=1, do_hyper=True):

@@ -40,6 +40,24 @@ int host_run(int n_, int d_, const double* y_, int M, int burn_in, int thin, int
     return -1;
   }
 }
+// run_gibbs_cpp on a list of [matrix (n x D, column-major as in R), dgCMatrix (n x W, compressed columns), vector]
+int host_run_mixed(int n_, int D, const double* colmajor, int W, int nnz, const int* ci, const int* cp, const double* cx,
+                   const double* vec, int M, int burn_in, int thin, int cap, unsigned long long seed) {
+  try {
+    mvhost::table_capacity = cap;
+    mvhost::seed = seed;
+    mvhost::view_dim.clear();
+    Rcpp::List data;
+    data.push_back_matrix(std::vector<double>(colmajor, colmajor + (size_t)n_ * D), n_, D);
+    data.push_back_dgc(std::vector<int>(ci, ci + nnz), std::vector<int>(cp, cp + W + 1), std::vector<double>(cx, cx + nnz), n_, W);
+    data.push_back(std::vector<double>(vec, vec + n_));
+    run_gibbs_cpp(data, M, burn_in, thin);
+    return (int)saved_table_of.size();
+  } catch (const std::exception& e) {
+    g_err = e.what();
+    return -1;
+  }
+}
 // the same through MVG_ENGINE_SEQ (mvhost::sequential)
 int host_run_seq(int n_, int d_, const double* y_, int M, int burn_in, int thin, unsigned long long seed) {
   mvhost::sequential = true;

@@ -506,6 +506,39 @@ def test_state_dump_and_resume_is_bit_identical():
     assert got["alpha_g"] == ref["alpha_g"] and got["sigma_g"] == ref["sigma_g"] and got["sweep"] == ref["sweep"]
 
 
+def test_binary_checkpoint_file_resumes_bit_identically(tmp_path):
+    """mvg_save_checkpoint / mvg_load_checkpoint: the chain continued from the FILE equals the uninterrupted chain; a file
+    of another shape or a damaged file is refused."""
+    import mvc_b200
+    n, dims, cap = 1300, [64, 64], 64
+    views, z = make_mixture(n, dims, 6, seed=8)
+    a = _mk_sampler(views, cap, seed=3, engine=0, debug=False)
+    a.init_state_reference()
+    a.sweep(5, do_hyper=True)
+    ck = tmp_path / "chain.mvg"
+    a.save_checkpoint(ck)
+    a.sweep(4, do_hyper=True)
+    ref = a.get_state()
+    a.close()
+    b = _mk_sampler(views, cap, seed=3, engine=0, debug=False)
+    b.load_checkpoint(ck)
+    b.sweep(4, do_hyper=True)
+    got = b.get_state()
+    for k in ("table_of", "n_t", "dish_of", "n_vk", "l_vk", "alpha_v", "sigma_v", "tau_v"):
+        np.testing.assert_array_equal(got[k], ref[k], err_msg=k)
+    assert got["sweep"] == ref["sweep"] == 9 and got["alpha_g"] == ref["alpha_g"]
+    raw = ck.read_bytes()
+    (tmp_path / "cut.mvg").write_bytes(raw[: len(raw) // 2])
+    with pytest.raises(mvc_b200.MvgError):
+        b.load_checkpoint(tmp_path / "cut.mvg")
+    b.close()
+    c = _mk_sampler([views[0][:700], views[1][:700]], cap, seed=3, engine=0, debug=False)
+    with pytest.raises(mvc_b200.MvgError) as e:
+        c.load_checkpoint(ck)
+    assert "another shape" in str(e.value)
+    c.close()
+
+
 # ---------------------------------------------------------------------------------------------
 # Sparse count views (CSR; SURVEY.md A.3 — no reference counterpart: pinned to the FP64 restatement only)
 # ---------------------------------------------------------------------------------------------

@@ -151,3 +151,35 @@ def test_run_gibbs_cpp_sequential_engine_equals_the_compiled_reference(oracle):
             dish = np.empty(T, np.int32)
             L.host_saved_dish_of(s, v, dish.ctypes.data_as(C.POINTER(C.c_int)))
             np.testing.assert_array_equal(dish, tr[s]["dish_of"][v])
+
+
+@pytest.mark.gpu
+def test_run_gibbs_cpp_accepts_matrices_and_dgCMatrix(oracle):
+    """data_views may hold what dataset/reuters/data pre-process.R builds: a numeric matrix (column-major, n x D), a
+    Matrix::dgCMatrix of counts (compressed COLUMNS) and a plain vector.  run_gibbs_cpp converts them (row-major dense,
+    CSR) and the chain equals the ctypes chain on the same views."""
+    import mvc_b200
+    from conftest import make_count_view
+    rng = np.random.default_rng(4)
+    n, D, W, k = 300, 4, 60, 4
+    z = rng.integers(0, k, n)
+    dense = (rng.normal(0, 2, (k, D))[z] + rng.normal(0, 1, (n, D)))
+    cv = make_count_view(n, W, z, k, seed=2, mean_len=12)
+    vec = rng.normal(0, 2, k)[z] + rng.normal(0, 1, n)
+    import scipy.sparse as sp
+    csr = sp.csr_matrix((cv["val"].astype(np.float64), cv["col"], cv["rowptr"]), shape=(n, W))
+    csc = csr.tocsc()
+    colmajor = np.ascontiguousarray(dense.T).ravel()              # R stores matrices column-major
+    L = build_host()
+    L.host_last_error.restype = C.c_char_p
+    pd, pi = C.POINTER(C.c_double), C.POINTER(C.c_int)
+    ci, cp, cx = csc.indices.astype(np.int32), csc.indptr.astype(np.int32), csc.data.astype(np.float64)
+    S = L.host_run_mixed(n, D, colmajor.ctypes.data_as(pd), W, int(csc.nnz), ci.ctypes.data_as(pi), cp.ctypes.data_as(pi),
+                         cx.ctypes.data_as(pd), np.ascontiguousarray(vec).ctypes.data_as(pd), 30, 20, 5, 32, C.c_ulonglong(77))
+    assert S == 2, L.host_last_error()
+    ref = mvc_b200.run_gibbs([dense, cv, vec], 30, 20, 5, cap=32, seed=77)
+    for s in range(S):
+        tab = np.empty(n, np.int32)
+        L.host_saved_table_of(s, tab.ctypes.data_as(pi))
+        rt = np.asarray(ref["table_of"][s])
+        np.testing.assert_array_equal(tab, np.searchsorted(np.unique(rt), rt))
