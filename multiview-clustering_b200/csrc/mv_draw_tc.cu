@@ -60,6 +60,7 @@ constexpr int kThreads = 896;                       // WG0: control, WG1+WG2: co
 constexpr int kMmaWarps = 2;                        // MMA-issuing warps of WG0; tile-view i belongs to warp 1 + i % 2
 constexpr int kExFields = 16;                       // scalars two epilogue threads of one customer trade per tile
 constexpr int kEpiGroups = 2;
+constexpr int kTcViewParamBytes = 9 * 64 * 4;           // TcViewParams: nine per-table arrays
 
 struct __align__(64) TcMaps {
   CUtensorMap x[kMaxTcViews];
@@ -72,7 +73,7 @@ struct SmemLayout {
   static constexpr int b_off = 0;                                            // [V][hi,lo][2 halves][8 KB]
   static constexpr int raw_off = b_off + kMaxTcViews * 4 * kBHalfBytes;      // 96 KB
   static constexpr int tp_off = raw_off + kRawStages * kHalfBytes;           // +112 KB
-  static constexpr int tm_off = tp_off + kMaxTcViews * 64 * (int)sizeof(TableParam);   // per view: TcViewParams (2 KB)
+  static constexpr int tm_off = tp_off + kMaxTcViews * kTcViewParamBytes;          // per view: TcViewParams
   static constexpr int vp_off = tm_off + 64 * (int)sizeof(TableMass);
   static constexpr int lm_off = vp_off + kMaxTcViews * (int)sizeof(ViewParam);              // float[64]: base = LM + sum_v C_v of every table
   static constexpr int dlm_off = lm_off + 64 * (int)sizeof(float);                          // float[64]: LM1 - LM
@@ -241,9 +242,12 @@ struct __align__(16) TcViewParams {
   float A[64], C[64], W[64];          // per table, read four tables at a time
   float A1[64], C1[64], R[64], W1[64];// the customer's own table: leave-one-out slope / offset, R = A1 / A, W with l_vk - 1
   int32_t lone[64];
+  float CW[64];                       // C + W: the constant of a dish's term of the new-table marginal (masked like W)
 };
-static_assert(sizeof(TcViewParams) == 64 * sizeof(TableParam), "parameter staging area");
+static_assert(sizeof(TcViewParams) == kTcViewParamBytes, "parameter staging area");
 
+// -trunc_tf32(x): mantissa cut to 10 bits; the negation folds into the consuming add
+__device__ __forceinline__ float neg_trunc_tf32(float x) { return -__uint_as_float(__float_as_uint(x) & 0xFFFFE000u); }
 __device__ __forceinline__ float ex2f(float d) { float r; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(d)); return r; }
 __device__ __forceinline__ float lg2f(float d) { float r; asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(d)); return r; }
 
@@ -285,15 +289,12 @@ __device__ __forceinline__ void lse_chunk(const TcViewParams& P, int tbase, cons
   float c0 = kMasked, c1 = kMasked;
   const float2 nxx2 = splat2(nxx);
   const float4* A4 = reinterpret_cast<const float4*>(P.A + tbase + BASE);
-  const float4* C4 = reinterpret_cast<const float4*>(P.C + tbase + BASE);
-  const float4* W4 = reinterpret_cast<const float4*>(P.W + tbase + BASE);
+  const float4* CW4 = reinterpret_cast<const float4*>(P.CW + tbase + BASE);
 #pragma unroll
   for (int q = 0; q < 4; ++q) {
-    const float4 a = A4[q], cc = C4[q], w = W4[q];
-    const float2 L0 = fadd2(make_float2(__uint_as_float(u[4 * q]), __uint_as_float(u[4 * q + 1])), ffma2(make_float2(a.x, a.y), nxx2, make_float2(cc.x, cc.y)));
-    const float2 L1 = fadd2(make_float2(__uint_as_float(u[4 * q + 2]), __uint_as_float(u[4 * q + 3])), ffma2(make_float2(a.z, a.w), nxx2, make_float2(cc.z, cc.w)));
-    term[2 * q] = fadd2(L0, make_float2(w.x, w.y));
-    term[2 * q + 1] = fadd2(L1, make_float2(w.z, w.w));
+    const float4 a = A4[q], cw = CW4[q];
+    term[2 * q] = fadd2(make_float2(__uint_as_float(u[4 * q]), __uint_as_float(u[4 * q + 1])), ffma2(make_float2(a.x, a.y), nxx2, make_float2(cw.x, cw.y)));
+    term[2 * q + 1] = fadd2(make_float2(__uint_as_float(u[4 * q + 2]), __uint_as_float(u[4 * q + 3])), ffma2(make_float2(a.z, a.w), nxx2, make_float2(cw.z, cw.w)));
     if (MASKED) {
       if (skip == BASE + 4 * q) term[2 * q].x = kMasked;
       if (skip == BASE + 4 * q + 1) term[2 * q].y = kMasked;
@@ -306,10 +307,15 @@ __device__ __forceinline__ void lse_chunk(const TcViewParams& P, int tbase, cons
   const float mn = fmaxf(mx, fmaxf(c0, c1));
   s *= ex2f(mx - mn);
   mx = mn;
-  float p0 = 0.f, p1 = 0.f;
+  const float2 nmn2 = splat2(-mn);
+  float2 acc2;
 #pragma unroll
-  for (int p = 0; p < 8; ++p) { p0 += ex2f(term[p].x - mn); p1 += ex2f(term[p].y - mn); }
-  s += p0 + p1;
+  for (int p = 0; p < 8; ++p) {
+    const float2 d = fadd2(term[p], nmn2);
+    const float2 e = make_float2(ex2f(d.x), ex2f(d.y));
+    acc2 = (p == 0) ? e : fadd2(acc2, e);
+  }
+  s += acc2.x + acc2.y;
 }
 
 template <bool B> struct BoolC { static constexpr bool value = B; };
@@ -509,13 +515,14 @@ __global__ void __launch_bounds__(kThreads, 1) k_draw_tc(const Ctx c, const __gr
           for (int cc = 0; cc < 4; ++cc) {             // logical 16-byte chunk cidx sits at physical chunk cidx ^ (r & 7)
             const int cidx = half16 * 4 + cc;
             const float4 x4 = *reinterpret_cast<const float4*>(src + ((cidx ^ (r & 7)) << 4));
-            const float xs[4] = {x4.x, x4.y, x4.z, x4.w};
-#pragma unroll
-            for (int e = 0; e < 4; ++e) {
-              // the tensor core reads trunc_tf32(x); the remainder x - trunc_tf32(x) is exact in FP32 and the
-              // hardware again keeps its top 19 bits: x_hi + x_lo carries >= 21 significant bits of x
-              lo[cc * 4 + e] = __float_as_uint(__fadd_rn(xs[e], -__uint_as_float(__float_as_uint(xs[e]) & 0xFFFFE000u)));
-            }
+            // the tensor core reads trunc_tf32(x); the remainder x - trunc_tf32(x) is exact in FP32 and the
+            // hardware again keeps its top 19 bits: x_hi + x_lo carries >= 21 significant bits of x
+            const float2 l01 = fadd2(make_float2(x4.x, x4.y), make_float2(neg_trunc_tf32(x4.x), neg_trunc_tf32(x4.y)));
+            const float2 l23 = fadd2(make_float2(x4.z, x4.w), make_float2(neg_trunc_tf32(x4.z), neg_trunc_tf32(x4.w)));
+            lo[cc * 4 + 0] = __float_as_uint(l01.x);
+            lo[cc * 4 + 1] = __float_as_uint(l01.y);
+            lo[cc * 4 + 2] = __float_as_uint(l23.x);
+            lo[cc * 4 + 3] = __float_as_uint(l23.y);
           }
           tmem_st_16(lo_addr + (uint32_t)(half16 * 16), lo);
         }
@@ -540,7 +547,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_draw_tc(const Ctx c, const __gr
         const int v = i >> 6, t = i & 63;
         const TableParam q = c.tparam[i];
         TcViewParams& P = s_p[v];
-        P.A[t] = q.A; P.C[t] = q.C; P.W[t] = q.W;
+        P.A[t] = q.A; P.C[t] = q.C; P.W[t] = q.W; P.CW[t] = __fadd_rn(q.C, q.W);
         P.A1[t] = q.A1; P.C1[t] = q.C1; P.W1[t] = q.W1;
         P.R[t] = (q.A != 0.0f) ? __fdiv_rn(q.A1, q.A) : 0.0f;
         // bit 0: the dish is served by this table alone; bit 1: the dish is SMALL (<= ~500 customers: R = 1 + 2 / (tau + n - 1),
@@ -697,7 +704,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_draw_tc(const Ctx c, const __gr
           if (!masked && (unsigned)rrel < 32u) {
             float acc_rep = own_acc;
             if (!all_lone) acc_rep = (rrel & 16) ? pick16(u, rrel) : pra;
-            const float trp = __fadd_rn(__fadd_rn(acc_rep, __fmaf_rn(P.A[rep], nxx, P.C[rep])), P.W[rep]);
+            const float trp = __fadd_rn(acc_rep, __fmaf_rn(P.A[rep], nxx, P.CW[rep]));   // the term exactly as lse_chunk formed it
             s = fmaxf(s - ex2f(trp - mx), 0.0f);
           }
           ex_own[(2 * v) * kTileRows] = mx;
@@ -746,10 +753,10 @@ __global__ void __launch_bounds__(kThreads, 1) k_draw_tc(const Ctx c, const __gr
         hmax = fmaxf(M0, M1);
       }
       ex_own[9 * kTileRows] = hmax;
-      // which tables of this half lie within 2^-32 of its best one (see the shortcut below)
+      // which tables of this half lie within 2^-31 of its best one (see the shortcut below)
       uint32_t nmask = 0u;
       {
-        const float thr = __fadd_rn(hmax, -32.0f);
+        const float thr = __fadd_rn(hmax, -31.0f);
         const float* lw = reinterpret_cast<const float*>(lw2);
 #pragma unroll
         for (int q = 0; q < 32; ++q) if (lw[q] > thr) nmask |= 1u << q;
@@ -776,18 +783,21 @@ __global__ void __launch_bounds__(kThreads, 1) k_draw_tc(const Ctx c, const __gr
       const float M = hf ? fmaxf(fmaxf(lnew, hoth), hmax) : fmaxf(fmaxf(lnew, hmax), hoth);
       int choice = t0;                                // nothing has weight: stay (cf. multiview_gibbs.cpp:172-176)
       const bool any_weight = (M > -1.0e29f);         // identical in both threads of the customer
-      // Shortcut.  If ONE option (a table or the new table) beats every other by more than 32 in log2, the draw below is
-      // that option for every uniform the stream can produce: the other weights sum to < 2^-26, so in FP32 the winner's
-      // half total, the grand total and hence the target are exactly 1, 1 and u; every cumulative sum before the winner is
-      // < 2^-26 < 2^-24 <= u and from the winner on it is 1 > u.  So the inverse-CDF scan — and the CPU mirror, which
-      // always runs it — returns the winner, and the exponentials, totals and the scan can be skipped.  Both threads of a
-      // customer decide from the same exchanged values (half maxima, near masks, lnew), and a warp skips only when all
-      // its customers can, so the rendezvous counts of the two warps stay equal.
+      // Shortcut.  If ONE option dominates — every other TABLE is more than 31 below it in log2 and the new-table option more
+      // than 27 — the draw below is that option for every uniform the stream can produce: the other weights sum to less than
+      // 64 * 2^-31 + 2^-27 < 2^-24, so in FP32 every partial sum that contains the winner's weight (exactly 1) rounds to 1,
+      // the grand total is exactly 1 and the target exactly u >= 2^-24; every cumulative sum before the winner is < 2^-24 <= u
+      // and from the winner on it is 1 > u (u <= 1 - 2^-24).  So the inverse-CDF scan — and the CPU mirror, which always
+      // runs it — returns the winner, and the exponentials, totals and the scan can be skipped.  (With a free table slot the
+      // new-table option of a well-fitting customer sits ~2^-30 below its table: the asymmetric thresholds keep such rows
+      // on the shortcut.)  Both threads of a customer decide from the same exchanged values (half maxima, near masks, lnew),
+      // and a warp skips only when all its customers can, so the rendezvous counts of the two warps stay equal.
       const uint32_t nm_oth = __float_as_uint(ex_oth[15 * kTileRows]);
-      const float near_thr = __fadd_rn(M, -32.0f);
+      const float near_thr = __fadd_rn(M, -31.0f);
       const int near_own = (hmax == M) ? __popc(nmask) : ((hmax > near_thr) ? 2 : 0);
       const int near_oth = (hoth == M) ? __popc(nm_oth) : ((hoth > near_thr) ? 2 : 0);
-      const bool sure = any_weight && (near_own + near_oth + ((lnew > near_thr) ? 1 : 0)) == 1;
+      const int near_new = (lnew == M) ? 1 : ((lnew > __fadd_rn(M, -27.0f)) ? 2 : 0);
+      const bool sure = any_weight && (near_own + near_oth + near_new) == 1;
       const bool all_sure = __all_sync(0xffffffffu, sure);
       if (all_sure) {
         if (hf == 0) choice = (hmax == M) ? (__ffs(nmask) - 1) : ((hoth == M) ? (32 + __ffs(nm_oth) - 1) : kNewTable);
