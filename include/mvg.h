@@ -250,6 +250,12 @@ int mvg_get_debug_prof(mvg_handle* h, int64_t* out, int32_t n_ctas);
 int mvg_last_sweep_ms(mvg_handle* h, float* ms_total);
 /* Number of kernel launches the library issued since the handle was created. */
 int64_t mvg_launch_count(const mvg_handle* h);
+/* In-kernel wall clocks of the tensor-core draw kernel (which = 0) and of the finalize kernel (which = 1): every launch adds
+ * the time from its first CTA in (the draw: from the moment its grid dependency resolved) to its last CTA out, read from
+ * %globaltimer.  total_ms / launches accumulate since the last reset; they also cover launches replayed from a CUDA graph,
+ * where events cannot be placed (bench.py times the kernels of the very sweeps it reports this way).  last_ns (may be NULL):
+ * absolute %globaltimer values {start, end} of the most recent launch and {end} of the one before.  Synchronises. */
+int mvg_kernel_clock(mvg_handle* h, int32_t which, double* total_ms, int64_t* launches, int64_t last_ns[3], int32_t reset);
 /* Per-kernel device time of the most recent sweep measured with CUDA events (ms):
  * [0] likelihood+draw, [1] pack, [2] stats, [3] reduce, [4] finalize, [5] collective. */
 int mvg_profile_sweep(mvg_handle* h, int32_t do_hyper, float ms_out[6]);

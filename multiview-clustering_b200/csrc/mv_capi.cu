@@ -157,6 +157,10 @@ int ensure_layout(mvg_handle* h) {
     dsum += c.D[v];
   }
   c.Dsum = dsum;
+  {
+    static const bool no_pdl = [] { const char* e = getenv("MVG_NO_PDL"); return e && e[0] == '1'; }();   // (A/B switch for measurements)
+    c.pdl = (c.n_count_views == 0 && !no_pdl) ? 1 : 0;     // (the count views put memsets between the kernels of the tail)
+  }
   if (c.n_count_views && c.world != 1)
     return fail(h, MVG_EUNSUPPORTED, "count (CSR) views are supported on one GPU per chain (world = 1) in this version");
   const size_t N = (size_t)c.n_rows, cap = (size_t)c.cap, V = (size_t)c.V;
@@ -166,7 +170,7 @@ int ensure_layout(mvg_handle* h) {
   A(c.n_t, cap); A(c.dish_of, V * cap); A(c.n_vk, V * cap); A(c.l_vk, V * cap);
   A(c.S1t, cap * dsum); A(c.S2t, V * cap); A(c.S1k, cap * dsum); A(c.S2k, V * cap);
   A(c.hyp, 3 * V + 2); A(c.sweep, 1); A(c.status, 4);
-  A(c.sum_cnt, cap); A(c.sum_s1t, cap * dsum); A(c.sum_s2t, V * cap); A(c.xseq, 1); A(c.fin_arrive, 1);
+  A(c.sum_cnt, cap); A(c.sum_s1t, cap * dsum); A(c.sum_s2t, V * cap); A(c.xseq, 1); A(c.fin_arrive, 1); A(c.kclock, (size_t)kClockSlots);
   A(c.tparam, V * cap); A(c.vparam, V); A(c.tmass, cap); A(c.gparam, 1); A(c.tsame, V * cap);
   A(c.mean, cap * dsum); A(c.mean_hi, cap * dsum); A(c.mean_lo, cap * dsum);
   A(c.partial_f, (size_t)c.stat_ctas * (cap * dsum + V * cap)); A(c.partial_n, (size_t)c.stat_ctas * cap); A(c.cta_active, (size_t)c.stat_ctas);
@@ -696,8 +700,7 @@ int sweep_tail_then_draw(mvg_handle* h, int32_t flags, bool delta) {
   int rc = rebuild_pipeline(h, flags, nullptr, delta);
   if (rc != MVG_OK) return rc;
   NvtxRange r("mvg:likelihood+draw (next sweep)");
-  static const bool no_pdl = [] { const char* e = getenv("MVG_NO_PDL"); return e && e[0] == '1'; }();   // (A/B switch for measurements)
-  return launch_draw(h, /*programmatic=*/h->c.n_count_views == 0 && !no_pdl);
+  return launch_draw(h, /*programmatic=*/h->c.pdl != 0);
 }
 
 // Capture one sweep into an executable graph (once per handle and hyper-step variant).  Returns false, leaving the
@@ -1048,6 +1051,23 @@ int mvg_last_sweep_ms(mvg_handle* h, float* ms_total) {
   MVG_CUDA(h, cudaSetDevice(h->cfg.device));
   MVG_CUDA(h, cudaEventSynchronize(h->ev[1]));
   MVG_CUDA(h, cudaEventElapsedTime(ms_total, h->ev[0], h->ev[1]));
+  return MVG_OK;
+}
+
+int mvg_kernel_clock(mvg_handle* h, int32_t which, double* total_ms, int64_t* launches, int64_t last_ns[3], int32_t reset) {
+  if (!h || which < 0 || which >= kClockSlots) return MVG_EINVAL;
+  if (!h->c.kclock) return fail(h, MVG_ESTATE, "no state yet");
+  MVG_CUDA(h, cudaSetDevice(h->cfg.device));
+  KClockSlot k;
+  MVG_CUDA(h, cudaMemcpyAsync(&k, h->c.kclock + which, sizeof(k), cudaMemcpyDeviceToHost, h->stream));
+  MVG_CUDA(h, cudaStreamSynchronize(h->stream));
+  if (total_ms) *total_ms = (double)k.total_ns * 1e-6;
+  if (launches) *launches = (int64_t)k.launches;
+  if (last_ns) { last_ns[0] = (int64_t)k.last_start; last_ns[1] = (int64_t)k.last_end; last_ns[2] = (int64_t)k.prev_end; }
+  if (reset) {
+    MVG_CUDA(h, cudaMemsetAsync(h->c.kclock + which, 0, sizeof(k), h->stream));
+    MVG_CUDA(h, cudaStreamSynchronize(h->stream));
+  }
   return MVG_OK;
 }
 

@@ -106,6 +106,8 @@ struct Ctx {
   uint32_t* xseq;           // [1] exchanges completed (peer-memory transport; advanced by k_finalize)
   uint32_t* fin_arrive;     // [1] arrival counter of the k_finalize CTAs
   int32_t* host_fault;      // mapped host memory: a copy of the sticky fault status[1] the host can read without a sync
+  struct KClockSlot* kclock; // [kClockSlots] in-kernel wall clocks (below)
+  int32_t pdl;              // launch the kernels of the sweep tail as programmatic dependents of one another (below)
 
   double* birth_lf;         // [cap][V][cap+1] scratch: log f of each seated birth under each dish
   // debug exports
@@ -119,6 +121,55 @@ struct Ctx {
   int32_t* dbg_nseated;     // [1]
   long long* dbg_prof;      // [CTAs][16] cycles spent waiting per role of the tcgen05 kernel (debug_export & 2)
 };
+
+// Programmatic dependent launch along the sweep: draw -> pack -> statistics -> reduce -> finalize -> draw.  Every kernel of
+// the chain lets its successor be scheduled at once (pdl_trigger) and orders itself behind its predecessor with pdl_wait
+// before it touches anything: completion of the predecessor implies that the predecessor's own wait returned, so the order
+// of the whole chain is kept while the launch latencies (~1-2 us per kernel, a quarter of the serial tail) overlap.
+// Both are no-ops for an ordinary launch.
+#ifdef __CUDACC__
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+template <class... KArgs, class... Args>
+inline cudaError_t launch_chain(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t s, bool programmatic, Args... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = s;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = programmatic ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kern, args...);
+}
+#endif
+
+// In-kernel wall clocks: %globaltimer (ns) from the first CTA in to the last CTA out of every launch, summed per kernel.
+// Events cannot be placed inside a replayed CUDA graph; this is how bench.py times the kernels of the very sweeps it
+// reports (mvg_kernel_clock).  Zero-initialised: the start is kept complemented so that 0 means "none yet".
+struct KClockSlot { unsigned long long nstart, end, done, total_ns, launches, last_start, last_end, prev_end; };   // last / previous launch: absolute ns
+enum { kClockDraw = 0, kClockFinalize = 1, kClockSlots = 2 };
+#ifdef __CUDACC__
+__device__ __forceinline__ unsigned long long globaltimer_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+// one thread per CTA each
+__device__ __forceinline__ void kclock_begin(KClockSlot* s) { atomicMax(&s->nstart, ~globaltimer_ns()); }
+__device__ __forceinline__ void kclock_end(KClockSlot* s, unsigned n_ctas) {
+  atomicMax(&s->end, globaltimer_ns());
+  __threadfence();
+  if (atomicAdd(&s->done, 1ull) == (unsigned long long)(n_ctas - 1)) {   // the last CTA out closes the launch
+    __threadfence();
+    const unsigned long long a = ~atomicAdd(&s->nstart, 0ull), b = atomicAdd(&s->end, 0ull);
+    s->total_ns += (b > a) ? (b - a) : 0ull;
+    s->launches += 1ull;
+    s->prev_end = s->last_end; s->last_start = a; s->last_end = b;
+    s->nstart = 0ull; s->end = 0ull; s->done = 0ull;
+    __threadfence();
+  }
+}
+#endif
 
 // Peer-memory exchange (mv_exchange.cu): the receive buffer of every rank, as mapped into this process, and the
 // layout of one (parity, source rank) slot: n_units 16-byte units (the statistics) then n_words 8-byte words (births).

@@ -542,6 +542,12 @@ __global__ void __launch_bounds__(kThreads, 1) k_draw_tc(const Ctx c, const __gr
     grid_dependency_wait();
     {
       const int et = tid - 3 * 128;                     // 0 .. 511
+      if (et == 0) {
+        kclock_begin(c.kclock + kClockDraw);            // the launch's clock runs from the moment its inputs exist
+        // The kernels of the sweep's tail may queue up behind this grid from here on (mv_ctx.h) — not earlier: what they
+        // read ahead of their own wait (k_finalize: the sweep-start state) must come from a COMPLETED previous finalize.
+        pdl_trigger();
+      }
       int lone_ok = 1;                                  // every live table's dishes are served by that table alone?
       for (int i = et; i < V * 64; i += 512) {
         const int v = i >> 6, t = i & 63;
@@ -715,10 +721,13 @@ __global__ void __launch_bounds__(kThreads, 1) k_draw_tc(const Ctx c, const __gr
       phase(1);
       // ---- the leave-one-out corrections: to the own table alone, or to every table serving an own dish ----
       if (all_lone) {
+        // registers cannot be indexed: one predicated packed add per PAIR of tables, the partner element gets + 0.0f
+        // (exact for every value a log-weight can take)
         const float corr = __fadd_rn(dsum, s_dlm[t0]);
-        float* lw = reinterpret_cast<float*>(lw2);
+        const int rp = mine ? (rel >> 1) : -1;
+        const float2 c2 = (rel & 1) ? make_float2(0.0f, corr) : make_float2(corr, 0.0f);
 #pragma unroll
-        for (int q = 0; q < 32; ++q) if (q == rel) lw[q] = __fadd_rn(lw[q], corr);
+        for (int p2 = 0; p2 < 16; ++p2) if (p2 == rp) lw2[p2] = fadd2(lw2[p2], c2);
       } else {
         rendezvous();                                 // #0: the corrections, known to the thread that holds the own table
         float dl[kMaxTcViews];
@@ -898,6 +907,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_draw_tc(const Ctx c, const __gr
   if (warp == 1) {
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(kTmemCols));
   }
+  if (tid == 3 * 128) kclock_end(c.kclock + kClockDraw, gridDim.x);
 }
 
 // =================================================================================================

@@ -108,6 +108,8 @@ __global__ void __launch_bounds__(256, 3) k_reduce_x(const Ctx c, const int mode
   __shared__ int s_cnt[kRedSlices][32];
   __shared__ int s_ncand;
   __shared__ unsigned char s_active[1024];       // delta: which CTAs of the statistics kernel wrote partials
+  pdl_trigger();
+  pdl_wait();
   const int n_s1 = c.cap * c.Dsum, n_s2 = c.V * c.cap;
   const int n_el = n_s1 + n_s2 + c.cap;
   const uint32_t seq = (mode == 1) ? *reinterpret_cast<volatile uint32_t*>(c.xseq) + 1u : 0u;
@@ -267,8 +269,7 @@ cudaError_t launch_reduce_x(const Ctx& c, int mode, bool delta, const XchgPeers&
   int nb = (n_el + 31) / 32;
   if (nb > 148 * 3) nb = 148 * 3;              // every block of one launch is resident at once (3 per SM by the launch bounds): peers wait for each other's pushes
   const int extra = (mode == 1) ? c.world : 0;
-  k_reduce_x<<<nb + extra, 256, 0, s>>>(c, mode, delta ? 1 : 0, nb, peers, recv_local, L);
-  return cudaGetLastError();
+  return launch_chain(k_reduce_x, dim3(nb + extra), dim3(256), 0, s, c.pdl != 0, c, mode, delta ? 1 : 0, nb, peers, recv_local, L);
 }
 
 }  // namespace mv

@@ -50,6 +50,8 @@ constexpr int kPackThreads = 1024;
 __global__ void __launch_bounds__(kPackThreads, 1) k_pack(const Ctx c) {
   __shared__ int s_warp[32];
   __shared__ int s_total;
+  pdl_trigger();
+  pdl_wait();
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
   const int nfree = c.gparam->nfree;
   int32_t* cand_row = pkt_i32(c, c.rank, c.pkt.off_cand_row);
@@ -127,8 +129,7 @@ __global__ void __launch_bounds__(kPackThreads, 1) k_pack(const Ctx c) {
 }
 
 cudaError_t launch_pack(const Ctx& c, cudaStream_t s) {
-  k_pack<<<1, kPackThreads, 0, s>>>(c);
-  return cudaGetLastError();
+  return launch_chain(k_pack, dim3(1), dim3(kPackThreads), 0, s, c.pdl != 0, c);
 }
 
 // =============================================================================================
@@ -562,7 +563,7 @@ __global__ void __launch_bounds__(kFinThreads, 1) k_finalize(const Ctx c, const 
   FinShared& S = *reinterpret_cast<FinShared*>(fin_smem);
   // Programmatic dependent launch: the next sweep's draw kernel may be scheduled now (its CTAs set themselves up and
   // start streaming features on the idle SMs; they wait for this grid's completion before they touch its results).
-  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+  pdl_trigger();
   const int tid = threadIdx.x;
   const int cap = c.cap, V = c.V;
   const int role = blockIdx.x;                      // < V: that view; V: the franchise level
@@ -573,7 +574,6 @@ __global__ void __launch_bounds__(kFinThreads, 1) k_finalize(const Ctx c, const 
   const bool is_count = is_view && c.kind[v] != 0;
   // A failed exchange (a peer's packet never arrived) freezes the chain: nothing is published, the sweep counter stays
   // (mvg_sweep / mvg_sync report it; csrc/mv_exchange.cu).
-  if (*reinterpret_cast<volatile int32_t*>(c.status + 1) != 0) return;
   // The per-table sums of this view, S1t [cap][D], live in shared memory behind FinShared when they fit (32 KB at C3):
   // the dish statistics and the posterior means are then built from on-chip data instead of global round trips.
   double* const S1t = s1_in_smem ? reinterpret_cast<double*>(fin_smem + kFinSharedBytes) : (c.S1t + (size_t)cap * doff);
@@ -595,23 +595,30 @@ __global__ void __launch_bounds__(kFinThreads, 1) k_finalize(const Ctx c, const 
   // (The random numbers of the hyper step depend on nothing but (seed, sweep, index): they are drawn by otherwise idle
   //  warps right before the chains that use them — see draw_level_randoms — and never hold up a CTA-wide barrier.)
 
-  // ---- A. this level's inputs: the statistics summed over the shards (k_reduce_x), the sweep-start state --------
-  for (int t = tid; t < cap; t += kFinThreads) {
-    S.n_new[t] = c.sum_cnt[t];
-    S.n_start[t] = c.n_t[t];
+  // ---- A. this level's inputs: the sweep-start state (the previous finalize's, complete long ago: read while the
+  //         statistics kernels of this sweep are still running — the launch is a programmatic dependent, mv_ctx.h) ... ----
+  for (int t = tid; t < cap; t += kFinThreads) S.n_start[t] = c.n_t[t];
+  if (is_view) {
+    for (int t = tid; t < cap; t += kFinThreads) {
+      S.dish[t] = c.dish_of[v * cap + t];
+      S.l_live[t] = c.l_vk[v * cap + t];
+      S.n_vk[t] = c.n_vk[v * cap + t];
+    }
   }
+  // ---- ... and, behind the grid dependency, the statistics summed over the shards (k_reduce_x) ----
+  pdl_wait();
+  // A failed exchange (a peer's packet never arrived) freezes the chain: nothing is published, the sweep counter stays
+  // (mvg_sweep / mvg_sync report it; csrc/mv_exchange.cu).
+  if (*reinterpret_cast<volatile int32_t*>(c.status + 1) != 0) return;
+  if (tid == 0) kclock_begin(c.kclock + kClockFinalize);
+  for (int t = tid; t < cap; t += kFinThreads) S.n_new[t] = c.sum_cnt[t];
   if (is_view) {
     if (s1_in_smem) {
       const double* src = c.sum_s1t + (size_t)cap * doff;
       const int n_s1 = cap * D;
       for (int i = tid; i < n_s1; i += kFinThreads) S1t[i] = src[i];
     }
-    for (int t = tid; t < cap; t += kFinThreads) {
-      S.s2t[t] = c.sum_s2t[v * cap + t];
-      S.dish[t] = c.dish_of[v * cap + t];
-      S.l_live[t] = c.l_vk[v * cap + t];
-      S.n_vk[t] = c.n_vk[v * cap + t];
-    }
+    for (int t = tid; t < cap; t += kFinThreads) S.s2t[t] = c.sum_s2t[v * cap + t];
   }
   __syncthreads();
   if (is_view && !s1_in_smem) {                     // large views: the sums stay in global memory (own block of S1t)
@@ -853,6 +860,8 @@ __global__ void __launch_bounds__(kFinThreads, 1) k_finalize(const Ctx c, const 
       if (S.err) atomicOr(c.status, S.err);
     }
     stamp(5);
+    __syncthreads();
+    if (tid == 0) kclock_end(c.kclock + kClockFinalize, gridDim.x);
     return;
   }
 
@@ -1118,6 +1127,8 @@ __global__ void __launch_bounds__(kFinThreads, 1) k_finalize(const Ctx c, const 
     if (S.err) atomicOr(c.status, S.err);
   }
   stamp(5);
+  __syncthreads();
+  if (tid == 0) kclock_end(c.kclock + kClockFinalize, gridDim.x);
 }
 
 cudaError_t launch_finalize(const Ctx& c, int32_t flags, cudaStream_t s) {
@@ -1129,8 +1140,7 @@ cudaError_t launch_finalize(const Ctx& c, int32_t flags, cudaStream_t s) {
   const int smem = kFinSharedBytes + (s1_in_smem ? (int)s1_bytes : 0);
   cudaError_t e = cudaFuncSetAttribute(k_finalize, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
   if (e != cudaSuccess) return e;
-  k_finalize<<<c.V + 1, kFinThreads, smem, s>>>(c, flags, s1_in_smem);
-  return cudaGetLastError();
+  return launch_chain(k_finalize, dim3(c.V + 1), dim3(kFinThreads), (size_t)smem, s, c.pdl != 0, c, flags, (int32_t)s1_in_smem);
 }
 
 // =============================================================================================

@@ -99,6 +99,8 @@ __global__ void __launch_bounds__(kThreadsST, 1) k_stats_tile(const Ctx c) {
   int32_t* act = reinterpret_cast<int32_t*>(bars + 3 * kStages);                          // DELTA: [kMaxAct] active tiles, ascending
   __shared__ int s_nact;
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  pdl_trigger();
+  pdl_wait();
 
   const int n_tiles = (c.n_rows + kTile - 1) / kTile;
   const int per_cta = (n_tiles + gridDim.x - 1) / gridDim.x;
@@ -279,8 +281,7 @@ cudaError_t launch_v(const Ctx& c, cudaStream_t s) {
   const int smem = (int)sizeof(Stage<V>) * kStages + 3 * kStages * 8 + (DELTA ? kMaxAct * 4 : 0);
   cudaError_t e = cudaFuncSetAttribute(k_stats_tile<V, DELTA>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
   if (e != cudaSuccess) return e;
-  k_stats_tile<V, DELTA><<<c.stat_ctas, kThreadsST, smem, s>>>(c);
-  return cudaGetLastError();
+  return launch_chain(k_stats_tile<V, DELTA>, dim3(c.stat_ctas), dim3(kThreadsST), (size_t)smem, s, c.pdl != 0, c);
 }
 
 }  // namespace

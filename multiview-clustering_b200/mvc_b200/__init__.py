@@ -114,6 +114,7 @@ def lib():
         L.mvg_get_debug_births.argtypes = [H, _i32p, C.POINTER(C.c_int64), _f64p]
         L.mvg_get_debug_prof.argtypes = [H, C.POINTER(C.c_int64), C.c_int32]
         L.mvg_last_sweep_ms.argtypes = [H, _f32p]
+        L.mvg_kernel_clock.argtypes = [H, C.c_int32, C.POINTER(C.c_double), C.POINTER(C.c_int64), C.POINTER(C.c_int64), C.c_int32]
         L.mvg_launch_count.restype = C.c_int64
         L.mvg_launch_count.argtypes = [H]
         L.mvg_log_likelihood.argtypes = [H, _f64p, _f64p]
@@ -348,6 +349,13 @@ class Sampler:
         ms = (C.c_float * 6)()
         self._ck(self.L.mvg_profile_sweep(self.h, int(do_hyper), ms))
         return dict(zip(["draw", "pack", "stats", "reduce", "finalize", "collective"], list(ms)))
+
+    def kernel_clock(self, which=0, reset=False):
+        """(total ms, launches) of the in-kernel wall clock: 0 = tensor-core draw kernel, 1 = finalize."""
+        ms, n, last = C.c_double(0.0), C.c_int64(0), (C.c_int64 * 3)()
+        self._ck(self.L.mvg_kernel_clock(self.h, int(which), C.byref(ms), C.byref(n), last, int(reset)))
+        self.kernel_clock_last = list(last)     # ns: start, end of the latest launch; end of the one before
+        return ms.value, n.value
 
     def launch_count(self):
         return int(self.L.mvg_launch_count(self.h))
