@@ -146,6 +146,8 @@ class ClockSampler(threading.Thread):
             self.handle = pynvml.nvmlDeviceGetHandleByIndex(idx)
             self.mx.append(float(pynvml.nvmlDeviceGetMaxClockInfo(self.handle, pynvml.NVML_CLOCK_SM)))
             self.nvml = pynvml
+            self.sample()                                       # the first query of a process can take tens of ms: not inside the region
+            self.sm, self.power, self.reasons = [], [], set()
         except Exception:                                       # noqa: BLE001
             self.nvml = None
 
@@ -738,7 +740,8 @@ def _main(args, out):
     roofline = roofline_of(W, R["kern"], traffic, R["inreg"])
     if args.role_profile and rank == 0:
         pr = s.get_debug_prof(n_ctas=256)
-        print("finalize stamps:", pr[200, :16].tolist(), file=sys.stderr)
+        for role in range(len(DIMS) + 1):                      # view CTAs, then the franchise CTA (cycles since the CTA began)
+            print("finalize stamps, CTA %d:" % role, pr[200 + role, :13].tolist(), file=sys.stderr)
         print("epilogue phases of CTA 0 pair 0 (cycles; lower half | upper half): prologue, views, corr+max, rdv1, marg+weights, rdv2, "
               "scan, rdv3, write, [acc wait]:", pr[230, :10].tolist(), "|", pr[231, :10].tolist(), file=sys.stderr)
         pr = pr[:148]

@@ -28,6 +28,10 @@
 // old one, so the per-CTA partials hold the CHANGE of the statistics and k_reduce_x adds it to the shard's running
 // FP64 sums.  With nothing moved the kernel reads the 4 bytes of mask per 32 rows and nothing else; with everything
 // moved it costs what the full rebuild costs.  Same row -> CTA -> warp mapping, same fixed order.
+// ROW mode of DELTA: when the moved rows are a small part of the tiles they sit in (one moved row in fifty still touches
+// 72 % of the 64-row tiles), a CTA compacts the moved ROWS of its range instead and fetches only those — one 256-byte
+// bulk copy per (row, view), 64 rows to a stage — so that the statistics kernel reads what actually changed: the sweep
+// then streams X once (the draw kernel) plus the moved rows, the reference's remove/add bookkeeping at its own cost.
 //
 // HBM traffic: the features once (N*V*256 B), 4 B of squared norm per (row, view), 4 B read + 4 B written of
 // assignment per row.  Replaces the rebuild loop of /root/reference/Multiview/multiview_gibbs.cpp:64-73 (and
@@ -44,7 +48,8 @@ constexpr int kAccWarps = 16;             // x 4 tables = cap 64
 constexpr int kTabPerWarp = 4;
 constexpr int kThreadsST = (kAccWarps + 2) * 32;
 constexpr int kMaxV = 3;
-constexpr int kMaxAct = 2048;             // DELTA: tiles per CTA the list of active tiles can hold (8 KB)
+constexpr int kMaxAct = 4096;             // DELTA: entries of the CTA's work list: active tiles, or moved rows in row mode (16 KB)
+constexpr int kRowModeTiles = 2048;       // tile mode: tiles per CTA the list may hold
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
@@ -97,7 +102,7 @@ __global__ void __launch_bounds__(kThreadsST, 1) k_stats_tile(const Ctx c) {
   Stage<V>* st = reinterpret_cast<Stage<V>*>(smem_raw);
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw + sizeof(Stage<V>) * kStages);   // full, ready, empty [kStages] each
   int32_t* act = reinterpret_cast<int32_t*>(bars + 3 * kStages);                          // DELTA: [kMaxAct] active tiles, ascending
-  __shared__ int s_nact;
+  __shared__ int s_nact, s_rowmode, s_nmoved;
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
   pdl_trigger();
   pdl_wait();
@@ -116,22 +121,56 @@ __global__ void __launch_bounds__(kThreadsST, 1) k_stats_tile(const Ctx c) {
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (DELTA && wid == 0) {
-    // the tiles of this CTA's range with at least one moved row, in ascending order (a 64-row tile = two mask words)
+    // this CTA's range: how many tiles hold a moved row, how many rows moved (a 64-row tile = two mask words)
+    int n_act = 0, n_mv = 0;
+    for (int base = t_lo; base < t_hi; base += 32) {
+      const int tile = base + lane;
+      unsigned w0 = 0u, w1 = 0u;
+      if (tile < t_hi) {
+        const int ch = 2 * tile;
+        w0 = c.movedmask[ch];
+        w1 = (ch + 1 < c.n_chunks) ? c.movedmask[ch + 1] : 0u;
+      }
+      n_act += __popc(__ballot_sync(0xffffffffu, (w0 | w1) != 0u));
+      n_mv += __popc(w0) + __popc(w1);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) n_mv += __shfl_xor_sync(0xffffffffu, n_mv, o);
+    // row mode when the moved rows are at most a quarter of the rows of the tiles they sit in
+    const bool rowmode = n_mv > 0 && n_mv <= kMaxAct && n_mv * 4 <= n_act * kTile;
     int n = 0;
     for (int base = t_lo; base < t_hi; base += 32) {
       const int tile = base + lane;
-      bool any = false;
+      unsigned w0 = 0u, w1 = 0u;
       if (tile < t_hi) {
         const int ch = 2 * tile;
-        any = (c.movedmask[ch] | ((ch + 1 < c.n_chunks) ? c.movedmask[ch + 1] : 0u)) != 0u;
+        w0 = c.movedmask[ch];
+        w1 = (ch + 1 < c.n_chunks) ? c.movedmask[ch + 1] : 0u;
       }
-      const unsigned m = __ballot_sync(0xffffffffu, any);
-      if (any) act[n + __popc(m & ((1u << lane) - 1u))] = tile;
-      n += __popc(m);
+      if (rowmode) {                               // the moved rows, ascending
+        const int mine = __popc(w0) + __popc(w1);
+        int incl = mine;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+          const int y = __shfl_up_sync(0xffffffffu, incl, o);
+          if (lane >= o) incl += y;
+        }
+        int at = n + incl - mine;
+        for (unsigned m = w0; m; m &= m - 1u) act[at++] = tile * kTile + __ffs(m) - 1;
+        for (unsigned m = w1; m; m &= m - 1u) act[at++] = tile * kTile + 32 + __ffs(m) - 1;
+        n += __shfl_sync(0xffffffffu, incl, 31);
+      } else {                                     // the tiles with a moved row, ascending
+        const bool any = (w0 | w1) != 0u;
+        const unsigned m = __ballot_sync(0xffffffffu, any);
+        if (any) act[n + __popc(m & ((1u << lane) - 1u))] = tile;
+        n += __popc(m);
+      }
     }
-    if (lane == 0) s_nact = n;
+    if (lane == 0) { s_rowmode = rowmode ? 1 : 0; s_nmoved = rowmode ? n : 0; s_nact = rowmode ? (n + kTile - 1) / kTile : n; }
   }
   __syncthreads();
+  const bool rowmode = DELTA && s_rowmode != 0;
+  const int n_moved = DELTA ? s_nmoved : 0;
   const int n_iter = DELTA ? s_nact : (t_hi - t_lo);
   if (DELTA) {
     // nothing moved in this CTA's rows: its partials would be all zero; k_reduce_x skips them (adding zeros changes nothing)
@@ -141,7 +180,31 @@ __global__ void __launch_bounds__(kThreadsST, 1) k_stats_tile(const Ctx c) {
 
   if (wid == kAccWarps) {
     // ---------------- producer: one lane keeps the ring full ----------------
-    if (lane == 0) {
+    if (rowmode) {
+      // row mode: the whole warp issues — lane l copies rows l and l + 32 of the stage's (up to) 64 moved rows
+      uint64_t policy;
+      asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(policy));
+      for (int k = 0; k < n_iter; ++k) {
+        const int s = k % kStages;
+        const uint32_t full = smem_u32(&bars[s]);
+        const int valid = min(kTile, n_moved - k * kTile);
+        if (lane == 0) {
+          if (k >= kStages) mbar_wait(smem_u32(&bars[2 * kStages + s]), ((k / kStages) - 1) & 1);
+          mbar_expect_tx(full, (uint32_t)(V * valid * 256));
+        }
+        __syncwarp();
+#pragma unroll
+        for (int hf = 0; hf < 2; ++hf) {
+          const int r = hf * 32 + lane;
+          if (r < valid) {
+            const int row = act[k * kTile + r];
+#pragma unroll
+            for (int v = 0; v < V; ++v)
+              bulk_load_stream(smem_u32(&st[s].x[v][r][0]), c.x[v] + (size_t)row * 64, 256u, full, policy);
+          }
+        }
+      }
+    } else if (lane == 0) {
       uint64_t policy;
       asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(policy));
       for (int k = 0; k < n_iter; ++k) {
@@ -166,21 +229,31 @@ __global__ void __launch_bounds__(kThreadsST, 1) k_stats_tile(const Ctx c) {
     // ---------------- resolver: raw draws -> the table each row now sits at ----------------
     const int nfree = c.gparam->nfree;
     for (int k = 0; k < n_iter; ++k) {
-      const int tile = DELTA ? act[k] : (t_lo + k);
+      const int tile = (DELTA && !rowmode) ? act[k] : (t_lo + k);
       const int s = k % kStages;
       mbar_wait(smem_u32(&bars[s]), (k / kStages) & 1);
       const int row0 = tile * kTile;
 #pragma unroll
       for (int hf = 0; hf < 2; ++hf) {
-        const int r = hf * 32 + lane, row = row0 + r;
+        const int r = hf * 32 + lane;
+        int row = row0 + r;
+        bool have = row < c.n_rows;
+        if (rowmode) {                                     // the stage's rows come from the list; draws, tables, norms from global memory
+          have = k * kTile + r < n_moved;
+          row = have ? act[k * kTile + r] : 0;
+        }
         int t = -3, told = -3;
-        if (row < c.n_rows) {
-          t = st[s].raw[r];
-          const int cur = DELTA ? st[s].old[r] : 0;
+        if (have) {
+          t = rowmode ? c.choice[row] : st[s].raw[r];
+          const int cur = DELTA ? (rowmode ? c.table_cur[row] : st[s].old[r]) : 0;
+          if (rowmode) {
+#pragma unroll
+            for (int v = 0; v < V; ++v) st[s].xx[v][r] = c.xx[(size_t)v * c.xx_stride + row];
+          }
           if (t == kNewTable) {                            // a birth: seated (candidate, -2) or overflow (stays put)
-            const int ch = row >> 5;                       // row0 is a multiple of 64: a chunk is one half of the tile
+            const int ch = row >> 5;                       // (tile mode: row0 is a multiple of 64, a chunk is one half of the tile)
             const unsigned m = c.birthmask[ch];
-            const int rank = c.chunk_prefix[ch] + __popc(m & ((1u << lane) - 1u));
+            const int rank = c.chunk_prefix[ch] + __popc(m & ((1u << (row & 31)) - 1u));
             t = (rank < nfree) ? -2 : (DELTA ? cur : c.table_cur[row]);
             c.choice[row] = t;
           }
@@ -279,6 +352,7 @@ __global__ void __launch_bounds__(kThreadsST, 1) k_stats_tile(const Ctx c) {
 template <int V, bool DELTA>
 cudaError_t launch_v(const Ctx& c, cudaStream_t s) {
   const int smem = (int)sizeof(Stage<V>) * kStages + 3 * kStages * 8 + (DELTA ? kMaxAct * 4 : 0);
+  static_assert(sizeof(Stage<V>) * kStages + 3 * kStages * 8 + kMaxAct * 4 <= 227 * 1024 - 64, "shared memory budget");
   cudaError_t e = cudaFuncSetAttribute(k_stats_tile<V, DELTA>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
   if (e != cudaSuccess) return e;
   return launch_chain(k_stats_tile<V, DELTA>, dim3(c.stat_ctas), dim3(kThreadsST), (size_t)smem, s, c.pdl != 0, c);
@@ -296,7 +370,7 @@ bool stats_tile_supported(const Ctx& c) {
 bool stats_delta_supported(const Ctx& c) {
   if (!stats_tile_supported(c) || c.stat_ctas <= 0) return false;
   const int n_tiles = (c.n_rows + kTile - 1) / kTile;
-  return (n_tiles + c.stat_ctas - 1) / c.stat_ctas <= kMaxAct;
+  return (n_tiles + c.stat_ctas - 1) / c.stat_ctas <= kRowModeTiles;
 }
 
 cudaError_t launch_stats_tile(const Ctx& c, bool delta, cudaStream_t s) {
