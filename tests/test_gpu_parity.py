@@ -396,6 +396,33 @@ def test_incremental_statistics_parity_and_agreement_with_rebuild(oracle):
     a.close(); b.close()
 
 
+@pytest.mark.parametrize("misplaced", [0.01, 0.6])
+def test_incremental_statistics_row_and_tile_mode(oracle, misplaced):
+    """The DELTA statistics kernel picks, per CTA, between fetching the 64-row tiles that hold a moved row (many rows
+    moved) and fetching the moved rows alone (few): 1 % and 60 % misplaced customers move back in the first sweep; the
+    running sums must equal a from-scratch FP64 rebuild of the final assignment, counts exactly."""
+    n, k_true, cap, V = 64 * 148 * 2 + 41, 48, 64, 3
+    views, z = make_mixture(n, [64] * V, k_true, seed=33)
+    rng = np.random.default_rng(8)
+    tab = np.where(rng.random(n) < misplaced, rng.integers(0, k_true, n), z).astype(np.int32)
+    dish = np.full((V, cap), -1, np.int32)
+    dish[:, :k_true] = np.arange(k_true)
+    s = _mk_sampler(views, cap, seed=4, engine=2)
+    s.set_stats_mode(True, rebuild_every=1000)
+    s.set_state(tab, dish, np.full(V, 1.0), np.full(V, 0.5), np.full(V, 1.0), 1.0, 0.6)
+    s.sweep(2, do_hyper=False)
+    fin = s.get_state()
+    moved = int((fin["table_of"] != tab).sum())
+    assert moved > 0.5 * misplaced * n * (1 - 1 / k_true), moved
+    o = oracle.OracleState(views, cap, seed=4)
+    o.set_assignment(fin["table_of"], fin["dish_of"])
+    np.testing.assert_array_equal(fin["n_t"], o.n_t)
+    np.testing.assert_array_equal(fin["n_vk"], o.n_vk)
+    for v in range(V):
+        np.testing.assert_allclose(fin["S1"][v], o.S1[v], rtol=RTOL_STATS, atol=1e-3)
+    s.close()
+
+
 def test_tile_statistics_match_general_kernel(oracle, monkeypatch):
     """The register-accumulating statistics kernel of the C3 shape (mv_stats_tile.cu) against the general
     kernel (MVG_STATS_GENERIC=1) and the FP64 oracle: counts and assignments bit-exact, sums within 1e-5.
