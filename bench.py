@@ -133,7 +133,7 @@ class ClockSampler(threading.Thread):
     def __init__(self, gpu_index):
         super().__init__(daemon=True)
         self.gpu, self.stop_flag = gpu_index, False
-        self.sm, self.mx, self.reasons, self.power = [], [], set(), []
+        self.sm, self.mx, self.reasons, self.power, self.mem = [], [], set(), [], []
         self.nvml = None
         try:
             import pynvml
@@ -147,7 +147,7 @@ class ClockSampler(threading.Thread):
             self.mx.append(float(pynvml.nvmlDeviceGetMaxClockInfo(self.handle, pynvml.NVML_CLOCK_SM)))
             self.nvml = pynvml
             self.sample()                                       # the first query of a process can take tens of ms: not inside the region
-            self.sm, self.power, self.reasons = [], [], set()
+            self.sm, self.power, self.reasons, self.mem = [], [], set(), []
         except Exception:                                       # noqa: BLE001
             self.nvml = None
 
@@ -155,6 +155,10 @@ class ClockSampler(threading.Thread):
         if self.nvml is not None:
             n = self.nvml
             self.sm.append(float(n.nvmlDeviceGetClockInfo(self.handle, n.NVML_CLOCK_SM)))
+            try:
+                self.mem.append(float(n.nvmlDeviceGetClockInfo(self.handle, n.NVML_CLOCK_MEM)))
+            except Exception:                                   # noqa: BLE001
+                pass
             try:
                 r = int(n.nvmlDeviceGetCurrentClocksEventReasons(self.handle))
             except Exception:                                   # noqa: BLE001
@@ -188,6 +192,8 @@ class ClockSampler(threading.Thread):
         return {"sm_mhz": float(np.median(self.sm)) if self.sm else None, "sm_max_mhz": max(self.mx) if self.mx else None,
                 "reasons": sorted(self.reasons), "samples": len(self.sm),
                 "power_w_median": float(np.median(self.power)) if self.power else None,
+                "sm_mhz_min": float(np.min(self.sm)) if self.sm else None,
+                "mem_mhz": float(np.median(self.mem)) if self.mem else None,
                 "source": "nvml" if self.nvml is not None else "nvidia-smi"}
 
 

@@ -101,6 +101,7 @@ struct mvg_handle {
   // replays the draw of the next sweep has already run: a pure function of the state, discarded (the flag cleared) by
   // anything that changes the state other than a sweep.
   bool draw_pending = false;
+  bool pdl_draw = false;             // the next sweep's draw is launched as the programmatic dependent of k_finalize
   bool graphs_ok = true;
   int64_t sweeps_issued = 0;
   // peer-memory exchange (optional; ncclAllGather otherwise)
@@ -159,7 +160,9 @@ int ensure_layout(mvg_handle* h) {
   c.Dsum = dsum;
   {
     static const bool no_pdl = [] { const char* e = getenv("MVG_NO_PDL"); return e && e[0] == '1'; }();   // (A/B switch for measurements)
-    c.pdl = (c.n_count_views == 0 && !no_pdl) ? 1 : 0;     // (the count views put memsets between the kernels of the tail)
+    static const bool no_chain = [] { const char* e = getenv("MVG_NO_PDL_CHAIN"); return e && e[0] == '1'; }();   // (the same for the tail alone)
+    h->pdl_draw = c.n_count_views == 0 && !no_pdl;          // (the count views put memsets between the kernels of the tail)
+    c.pdl = (h->pdl_draw && !no_chain) ? 1 : 0;
   }
   if (c.n_count_views && c.world != 1)
     return fail(h, MVG_EUNSUPPORTED, "count (CSR) views are supported on one GPU per chain (world = 1) in this version");
@@ -700,7 +703,7 @@ int sweep_tail_then_draw(mvg_handle* h, int32_t flags, bool delta) {
   int rc = rebuild_pipeline(h, flags, nullptr, delta);
   if (rc != MVG_OK) return rc;
   NvtxRange r("mvg:likelihood+draw (next sweep)");
-  return launch_draw(h, /*programmatic=*/h->c.pdl != 0);
+  return launch_draw(h, /*programmatic=*/h->pdl_draw);
 }
 
 // Capture one sweep into an executable graph (once per handle and hyper-step variant).  Returns false, leaving the
