@@ -39,7 +39,7 @@ N_ROWS = 1_000_000
 DIMS = [64, 64, 64]
 CAP = 64
 SEED = 1999
-NCU_TRAFFIC_BYTES = 791.7e6     # measured DRAM traffic of one k_draw_tc launch at N=1M (profiles/r02_ncu_draw.md; algorithmic: 776 MB + 12 MB of stored squared norms)
+NCU_TRAFFIC_BYTES = 792.1e6     # measured DRAM traffic of one k_draw_tc launch at N=1M (profiles/r02_ncu_draw.md; algorithmic: 776 MB + 12 MB of stored squared norms)
 METRIC = "obs_x_view_x_K_updates_per_s"
 UNIT = "updates/s"
 
