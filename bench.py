@@ -313,9 +313,17 @@ def run_c2(args, out):
     for s in chains:
         s.close()
     if rank == 0:
+        # The count likelihood is a gather from the L2-resident, feature-major log2-theta tables (the data set itself fits
+        # L2): cap floats per nonzero, plus the CSR stream and the [N][cap] result per view.  No HBM roofline applies;
+        # the figure to read is the achieved L2 rate of the two kernels event-timed as "draw".
+        l2_bytes = sum(nnz) * (cap * 4 + 8) + len(views) * n * (cap * 4 * 2 + 8)
+        count_lik = {"bound": "l2 gather", "algorithmic_l2_bytes_per_sweep": l2_bytes, "kernel_ms": prof["draw"],
+                     "achieved_gbs": l2_bytes / (prof["draw"] * 1e-3) / 1e9 if prof["draw"] > 0 else None,
+                     "nonzeros": sum(nnz), "bytes_per_nonzero": cap * 4 + 8}
         line = {"metric": "gibbs_sweeps_per_s", "value": world * args.chains * steps / dt, "unit": "sweeps/s", "n_gpus": world,
                 "steps": steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / steps, "higher_is_better": True,
                 "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic" if z is not None else "Reuters-21578",
+                "count_likelihood": count_lik,
                 "config": {"workload": workload + ", %d independent chains per GPU, CUDA-core engine, hyper step on" % args.chains,
                            "timing": "wall clock around the launches of all chains and their final synchronisation"},
                 "kernel_ms_one_chain": prof, "gpu_launches": int(launches), "tables_live": live,

@@ -12,6 +12,7 @@
 #include <mutex>
 #include <new>
 #include <string>
+#include <algorithm>
 #include <vector>
 
 #include "../../include/mvg.h"
@@ -83,7 +84,7 @@ struct mvg_handle {
   float last_ms = 0.f;
   int sms = 148;
   void* tc_maps = nullptr;           // host copy of the TMA tensor maps (tcgen05 engine)
-  void* csr_owned[kMaxViews][3]{};   // uploaded CSR views: rowptr, col, val
+  void* csr_owned[kMaxViews][4]{};   // uploaded CSR views: rowptr, col, val, rows by descending length
   uint32_t* cocl = nullptr;          // [n_rows][n_rows] co-clustering counts (mvg_coclustering_*)
   int32_t cocl_view = -2;
   int32_t cocl_samples = 0;
@@ -486,9 +487,18 @@ int mvg_upload_view_csr(mvg_handle* h, int32_t v, const int32_t* rowptr, const i
     MVG_CUDA(h, cudaMemcpyAsync(h->csr_owned[v][1], col, sizeof(int32_t) * nz, cudaMemcpyHostToDevice, h->stream));
     MVG_CUDA(h, cudaMemcpyAsync(h->csr_owned[v][2], val, sizeof(float) * nz, cudaMemcpyHostToDevice, h->stream));
   }
+  {
+    // the rows by descending number of nonzeros (ties: ascending row), the order k_counts_loglik deals them out in
+    std::vector<int32_t> order((size_t)n);
+    for (int64_t i = 0; i < n; ++i) order[(size_t)i] = (int32_t)i;
+    std::stable_sort(order.begin(), order.end(), [&](int32_t a, int32_t b) { return rowptr[a + 1] - rowptr[a] > rowptr[b + 1] - rowptr[b]; });
+    MVG_CUDA(h, cudaMalloc(&h->csr_owned[v][3], sizeof(int32_t) * (size_t)(n ? n : 1)));
+    MVG_CUDA(h, cudaMemcpy(h->csr_owned[v][3], order.data(), sizeof(int32_t) * (size_t)n, cudaMemcpyHostToDevice));
+  }
   Ctx& c = h->c;
   c.kind[v] = 1;
   c.vocab[v] = vocab;
+  c.row_order[v] = static_cast<const int32_t*>(h->csr_owned[v][3]);
   c.D[v] = 0;
   c.x[v] = nullptr;
   c.rowptr[v] = static_cast<const int32_t*>(h->csr_owned[v][0]);

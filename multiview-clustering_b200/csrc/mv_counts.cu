@@ -86,7 +86,10 @@ __global__ void k_counts_tables(const Ctx c) {
 // the leave-one-out value under the row's own dish.  One WARP per row (a thread per row would make the longest row
 // everybody's wait): lane l owns tables l*PER .. l*PER+PER-1, the row's nonzeros are read 32 at a time and broadcast,
 // eight table rows are in flight at once; per table the chain is ascending over the nonzeros, the order
-// oracle/mv_oracle.c:mvo_stageA_counts_f32 restates.  The table is feature-major: one nonzero reads CAP consecutive
+// oracle/mv_oracle.c:mvo_stageA_counts_f32 restates.  Document lengths are heavy-tailed (Reuters bodies: 1 .. several
+// hundred distinct words) and there are only two or three rows per warp, so the rows are dealt out by descending
+// length (row_order, built at upload): every warp gets one long, one middling and one short row instead of whatever
+// its index happens to hold.  The table is feature-major: one nonzero reads CAP consecutive
 // floats (the SpMM "CSR row x dense feature-major table" of SURVEY.md A.3).
 template <int CAP>
 __global__ void __launch_bounds__(512) k_counts_loglik(const Ctx c) {
@@ -100,7 +103,10 @@ __global__ void __launch_bounds__(512) k_counts_loglik(const Ctx c) {
   const float* __restrict__ l2t = c.l2t[v];
   const int32_t* __restrict__ cdt = c.cnt_d[v];
   const TableParam* __restrict__ tp = c.tparam + v * CAP;
-  for (int row = warp; row < c.n_rows; row += nwarps) {
+  const int32_t* __restrict__ order = c.row_order[v];
+  constexpr int kFlight = 8;                         // table rows in flight per warp
+  for (int ri = warp; ri < c.n_rows; ri += nwarps) {
+    const int row = order ? __ldg(order + ri) : ri;
     const int j0 = rp[row], j1 = rp[row + 1];
     const int t0 = c.table_cur[row];
     // leave-one-out under the own dish: counts and total with this row removed (TableParam::C1 of a count view
@@ -121,10 +127,10 @@ __global__ void __launch_bounds__(512) k_counts_loglik(const Ctx c) {
         term_l = __fadd_rn(log2m(__fadd_rn(__fadd_rn(c.count_beta, cown), -xv_l)), -lden);
       }
       const int cnt = min(32, j1 - jb);
-      for (int u0 = 0; u0 < cnt; u0 += 8) {
-        float lv[8][PER], xs[8];
+      for (int u0 = 0; u0 < cnt; u0 += kFlight) {
+        float lv[kFlight][PER], xs[kFlight];
 #pragma unroll
-        for (int u = 0; u < 8; ++u) {
+        for (int u = 0; u < kFlight; ++u) {
           const int src = min(u0 + u, cnt - 1);
           const int cl = __shfl_sync(0xffffffffu, col_l, src);
           xs[u] = __shfl_sync(0xffffffffu, xv_l, src);
@@ -133,7 +139,7 @@ __global__ void __launch_bounds__(512) k_counts_loglik(const Ctx c) {
           else lv[u][0] = __ldg(p);
         }
 #pragma unroll
-        for (int u = 0; u < 8; ++u) {
+        for (int u = 0; u < kFlight; ++u) {
           if (u0 + u < cnt) {                                  // warp-uniform
 #pragma unroll
             for (int q = 0; q < PER; ++q) a[q] = __fmaf_rn(xs[u], lv[u][q], a[q]);

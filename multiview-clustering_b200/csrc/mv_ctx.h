@@ -56,6 +56,7 @@ struct Ctx {
   const int32_t* rowptr[kMaxViews];
   const int32_t* col[kMaxViews];
   const float* val[kMaxViews];
+  const int32_t* row_order[kMaxViews];   // the rows by descending number of nonzeros (the order the likelihood kernel deals them out in)
   int32_t* cnt_t[kMaxViews];   // [vocab][cap] word counts per TABLE slot (rebuilt after every finalize)
   int32_t* cnt_d[kMaxViews];   // [vocab][cap] word counts of the DISH each table slot serves
   float* l2t[kMaxViews];       // [vocab][cap] log2 theta of that dish: log2((beta + cnt_d) / (W beta + total))
