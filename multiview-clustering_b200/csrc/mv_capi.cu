@@ -102,6 +102,7 @@ struct mvg_handle {
   // replays the draw of the next sweep has already run: a pure function of the state, discarded (the flag cleared) by
   // anything that changes the state other than a sweep.
   bool draw_pending = false;
+  bool counts_valid = false;         // count views: cnt_t / table_prev are consistent with table_cur (else the next rebuild starts from zero)
   bool pdl_draw = false;             // the next sweep's draw is launched as the programmatic dependent of k_finalize
   bool graphs_ok = true;
   int64_t sweeps_issued = 0;
@@ -198,6 +199,7 @@ int ensure_layout(mvg_handle* h) {
       const size_t cells = (size_t)c.vocab[v] * cap;
       A(c.cnt_t[v], cells); A(c.cnt_d[v], cells); A(c.l2t[v], cells);
       A(c.cnt_acc[v], N * cap); A(c.cnt_loo[v], N);
+      if (!c.table_prev) { A(c.table_prev, N); }
     }
 #undef A
   h->layout_done = true;
@@ -248,7 +250,8 @@ int rebuild_pipeline(mvg_handle* h, int32_t flags, cudaEvent_t* marks /* 4 event
   if (rc != MVG_OK) return rc;
   { NvtxRange r("mvg:births, hyper step, parameters"); MVG_CUDA(h, launch_finalize(h->c, flags, h->stream)); }
   if (h->c.n_count_views) {          // count views: word counts by the final seating, then the log2 theta tables
-    MVG_CUDA(h, launch_counts_rebuild(h->c, h->stream));
+    MVG_CUDA(h, launch_counts_rebuild(h->c, /*delta=*/h->counts_valid, h->stream));
+    h->counts_valid = true;            // cnt_t and table_prev now stand for the current seating
     h->launches += 2;
   }
   if (marks) MVG_CUDA(h, cudaEventRecord(marks[3], h->stream));
@@ -535,6 +538,7 @@ int mvg_get_debug_loo(mvg_handle* h, float* loo) {
 int mvg_init_state_reference(mvg_handle* h) {
   if (!h) return MVG_EINVAL;
   h->draw_pending = false;
+  h->counts_valid = false;           // the seating is replaced from outside: the word counts of count views start from zero
   MVG_CUDA(h, cudaSetDevice(h->cfg.device));
   int rc = ensure_layout(h);
   if (rc != MVG_OK) return rc;
@@ -553,6 +557,7 @@ int mvg_init_state_reference(mvg_handle* h) {
 int mvg_set_state(mvg_handle* h, const mvg_state_host* s) {
   if (!h || !s) return MVG_EINVAL;
   h->draw_pending = false;
+  h->counts_valid = false;           // the seating is replaced from outside: the word counts of count views start from zero
   MVG_CUDA(h, cudaSetDevice(h->cfg.device));
   int rc = ensure_layout(h);
   if (rc != MVG_OK) return rc;

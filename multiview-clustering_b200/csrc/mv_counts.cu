@@ -6,7 +6,8 @@
 // dish's word counts; log f_vk(x) = sum_w x_w log theta_kw, the row's own counts removed for its own dish.
 //
 //   k_rowtotals       |x| of every row, once per upload (kept in the squared-norm slot of the view)
-//   k_counts_scatter  word counts per TABLE slot: cnt_t[w][t] += x_w over the rows seated at t.  Integer
+//   k_counts_scatter  word counts per TABLE slot: cnt_t[w][t] += x_w over the rows seated at t — from scratch after a
+//                     state upload, otherwise only for the rows that changed table since the last call.  Integer
 //                     atomics: the sums are exact and independent of the order (north_star: integer counts
 //                     bit-exact)
 //   k_counts_tables   per (word, table slot): the counts of the DISH the slot serves (sum over the slots of that
@@ -31,7 +32,10 @@ __device__ __forceinline__ int nth_count_view(const Ctx& c, int nth) {
   return v;
 }
 
-__global__ void k_counts_scatter(const Ctx c) {
+// delta: cnt_t is current for the seating table_prev; only the rows that changed table since are visited — their words
+// leave the old slot and join the new one (the reference's remove_customer / add_customer bookkeeping,
+// multiview_utils.cpp:151-163, 199-206, batched).  Integer atomics either way: exact, order-independent.
+__global__ void k_counts_scatter(const Ctx c, const int delta) {
   const int v = nth_count_view(c, blockIdx.y);
   const int lane = threadIdx.x & 31;
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = (gridDim.x * blockDim.x) >> 5;
@@ -41,7 +45,13 @@ __global__ void k_counts_scatter(const Ctx c) {
   int32_t* cnt = c.cnt_t[v];
   for (int i = warp; i < c.n_rows; i += nwarps) {
     const int t = c.table_cur[i];
-    for (int j = rp[i] + lane; j < rp[i + 1]; j += 32) atomicAdd(&cnt[(size_t)col[j] * c.cap + t], (int32_t)val[j]);
+    const int p = delta ? c.table_prev[i] : -1;
+    if (delta && p == t) continue;
+    for (int j = rp[i] + lane; j < rp[i + 1]; j += 32) {
+      const int32_t x = (int32_t)val[j];
+      atomicAdd(&cnt[(size_t)col[j] * c.cap + t], x);
+      if (p >= 0) atomicAdd(&cnt[(size_t)col[j] * c.cap + p], -x);
+    }
   }
 }
 
@@ -65,6 +75,10 @@ __global__ void k_counts_tables(const Ctx c) {
     s_mask[threadIdx.x] = m;
   }
   __syncthreads();
+  // (every view's scatter has read table_prev by now — this kernel follows it in the stream: the seating the counts now
+  //  stand for is the current one)
+  if (blockIdx.y == 0)
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < c.n_rows; i += gridDim.x * blockDim.x) c.table_prev[i] = c.table_cur[i];
   const size_t total = (size_t)c.vocab[v] * cap;
   for (size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (size_t)gridDim.x * blockDim.x) {
     const int t = (int)(e % cap);
@@ -170,19 +184,21 @@ cudaError_t launch_rowtotals(const int32_t* rowptr, const float* val, float* out
   return cudaGetLastError();
 }
 
-cudaError_t launch_counts_rebuild(const Ctx& c, cudaStream_t s) {
+cudaError_t launch_counts_rebuild(const Ctx& c, bool delta, cudaStream_t s) {
   if (!c.n_count_views) return cudaSuccess;
   size_t max_cells = 0;
   for (int v = 0; v < c.V; ++v) {
     if (!c.kind[v]) continue;
     const size_t cells = (size_t)c.vocab[v] * c.cap;
     max_cells = cells > max_cells ? cells : max_cells;
-    cudaError_t e = cudaMemsetAsync(c.cnt_t[v], 0, sizeof(int32_t) * cells, s);
-    if (e != cudaSuccess) return e;
+    if (!delta) {
+      cudaError_t e = cudaMemsetAsync(c.cnt_t[v], 0, sizeof(int32_t) * cells, s);
+      if (e != cudaSuccess) return e;
+    }
   }
   int blocks = (c.n_rows + 7) / 8;                 // 8 warps per block, one row per warp per step
   if (blocks > 148 * 4) blocks = 148 * 4;
-  k_counts_scatter<<<dim3(blocks, c.n_count_views), 256, 0, s>>>(c);
+  k_counts_scatter<<<dim3(blocks, c.n_count_views), 256, 0, s>>>(c, delta ? 1 : 0);
   int tb = (int)((max_cells + 255) / 256);
   if (tb > 148 * 8) tb = 148 * 8;
   k_counts_tables<<<dim3(tb, c.n_count_views), 256, 0, s>>>(c);

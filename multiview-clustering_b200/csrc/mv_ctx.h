@@ -57,13 +57,14 @@ struct Ctx {
   const int32_t* col[kMaxViews];
   const float* val[kMaxViews];
   const int32_t* row_order[kMaxViews];   // the rows by descending number of nonzeros (the order the likelihood kernel deals them out in)
-  int32_t* cnt_t[kMaxViews];   // [vocab][cap] word counts per TABLE slot (rebuilt after every finalize)
+  int32_t* cnt_t[kMaxViews];   // [vocab][cap] word counts per TABLE slot (kept current after every finalize: the rows that changed table leave one slot and join another)
   int32_t* cnt_d[kMaxViews];   // [vocab][cap] word counts of the DISH each table slot serves
   float* l2t[kMaxViews];       // [vocab][cap] log2 theta of that dish: log2((beta + cnt_d) / (W beta + total))
   float* cnt_acc[kMaxViews];   // [N][cap] log2 f of every row under every table slot's dish (stage A of the sweep)
   float* cnt_loo[kMaxViews];   // [N] the same under the row's own dish with the row removed
   float count_beta;            // symmetric Dirichlet pseudo-count
   int32_t n_count_views;
+  int32_t* table_prev;         // [N] count views: the table every row's words are currently counted at in cnt_t
   float* xx;                // [V][xx_stride] squared norms of the rows (count views: the rows' total counts), computed once per upload
   int64_t xx_stride;        // n_rows rounded up to a multiple of 4
 
@@ -210,7 +211,7 @@ cudaError_t launch_f64_to_f32(const double* src, float* dst, int64_t n, cudaStre
 int stats_smem_bytes(const Ctx& c);
 // count views (mv_counts.cu)
 cudaError_t launch_rowtotals(const int32_t* rowptr, const float* val, float* out, int n, cudaStream_t s);
-cudaError_t launch_counts_rebuild(const Ctx& c, cudaStream_t s);   // per count view: zero, scatter, dish tables
+cudaError_t launch_counts_rebuild(const Ctx& c, bool delta, cudaStream_t s);   // per count view: word counts per table slot (from scratch, or only the rows that changed table), dish tables
 cudaError_t launch_counts_loglik(const Ctx& c, cudaStream_t s);    // per count view: log2 f of every row under every table
 // posterior summaries (mv_summary.cu)
 cudaError_t launch_labels(const Ctx& c, int32_t* out, cudaStream_t s);
