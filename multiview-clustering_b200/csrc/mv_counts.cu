@@ -59,6 +59,7 @@ __global__ void k_counts_tables(const Ctx c) {
   const int v = nth_count_view(c, blockIdx.y);
   __shared__ int32_t s_dish[64];
   __shared__ double s_den[64];
+  __shared__ float s_l2zero[64];                 // log2 theta of a word the dish has never seen: most cells of the table
   __shared__ unsigned long long s_mask[64];      // the table slots serving the same dish as slot t
   const int cap = c.cap;
   if (threadIdx.x < cap) {
@@ -66,6 +67,7 @@ __global__ void k_counts_tables(const Ctx c) {
     s_dish[threadIdx.x] = k;
     // S2k of a count view holds the token total of the dish (an exact integer)
     s_den[threadIdx.x] = (k >= 0) ? (double)c.vocab[v] * (double)c.count_beta + c.S2k[v * cap + k] : 1.0;
+    s_l2zero[threadIdx.x] = (float)log2(((double)c.count_beta + 0.0) / s_den[threadIdx.x]);   // the cell expression at cd = 0
   }
   __syncthreads();
   if (threadIdx.x < cap) {
@@ -89,7 +91,7 @@ __global__ void k_counts_tables(const Ctx c) {
       const int32_t* row = c.cnt_t[v] + w * cap;
       cd = row[t];                                              // usually the dish's only table
       for (unsigned long long m = s_mask[t] & ~(1ull << t); m; m &= m - 1ull) cd += row[__ffsll((long long)m) - 1];
-      l2 = (float)log2(((double)c.count_beta + (double)cd) / s_den[t]);
+      l2 = (cd == 0) ? s_l2zero[t] : (float)log2(((double)c.count_beta + (double)cd) / s_den[t]);
     }
     c.cnt_d[v][e] = cd;
     c.l2t[v][e] = l2;
