@@ -82,9 +82,10 @@ __global__ void k_counts_tables(const Ctx c) {
   if (blockIdx.y == 0)
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < c.n_rows; i += gridDim.x * blockDim.x) c.table_prev[i] = c.table_cur[i];
   const size_t total = (size_t)c.vocab[v] * cap;
+  const int shift = (cap == 64) ? 6 : 5;
   for (size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (size_t)gridDim.x * blockDim.x) {
-    const int t = (int)(e % cap);
-    const size_t w = e / cap;
+    const int t = (int)(e & (size_t)(cap - 1));             // cap is 32 or 64 (mvg_create): no 64-bit division per cell
+    const size_t w = e >> shift;
     int32_t cd = 0;
     float l2 = 0.0f;
     if (s_dish[t] >= 0) {
