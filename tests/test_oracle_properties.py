@@ -45,6 +45,47 @@ def test_fp32_mirror_agrees_with_fp64_restatement(oracle, dims, cap):
     assert worst < 1e-5                                    # the stated FP32 tolerance
 
 
+@pytest.mark.parametrize("shared_dishes", [False, True])
+def test_tensor_core_mirror_agrees_with_fp64_restatement(oracle, shared_dishes):
+    """The CPU mirror of the tensor-core engine's epilogue (mvo_stageB_tc: pre-scaled means b = 2 A m, scalar
+    leave-one-out corrections, new-table log-weight taken as an input) against the FP64 restatement, on the CPU alone:
+    fed FP32 dot products x.b and the FP64 new-table log-weight it must reproduce the log-weights to the stated 1e-5 and
+    the draws but for CDF edges.  With the FP64 restatement pinned to the compiled reference at D = 1
+    (test_oracle_vs_reference.py) this closes the chain  GPU kernel == mirror (bit-exact, GPU tests)  ~  restatement
+    (here)  ==  reference  without a GPU.  Free table slots (the new-table option has weight) and, in the second case,
+    tables that share dishes (the leave-one-out correction reaches several tables)."""
+    n, dims, cap, k_true = 400, [64, 64, 64], 64, 6
+    views, z = make_mixture(n, dims, k_true, seed=17)
+    rng = np.random.default_rng(3)
+    n_tab = 12 if shared_dishes else k_true
+    tab = np.where(rng.random(n) < 0.15, rng.integers(0, n_tab, n), z + (k_true * (rng.random(n) < 0.5) if shared_dishes else 0))
+    tab = tab.astype(np.int32)
+    dish = np.full((len(dims), cap), -1, np.int32)
+    dish[:, :n_tab] = np.arange(n_tab) % k_true              # shared: tables t and t + 6 serve the same dish
+    s = oracle.OracleState(views, cap, seed=7)
+    s.set_assignment(tab, dish)
+    s.tau_v[:] = 0.9
+    P = s.make_params()
+    ps = oracle.params_struct(P)
+    ch64 = s.draw_rows()
+    L = oracle.lib()
+    agree, worst = 0, 0.0
+    for i in range(n):
+        acc = np.stack([(views[v][i].astype(np.float64) @ oracle.scaled_means(P["A"][v], P["m"][v]).astype(np.float64).T)
+                        .astype(np.float32) for v in range(len(dims))])
+        xx = np.array([float((views[v][i].astype(np.float64) ** 2).sum()) for v in range(len(dims))], np.float32)
+        lw64 = s.row_logweights(i) / np.log(2.0)
+        lnew = np.float32(lw64[cap]) if np.isfinite(lw64[cap]) else np.float32(-1e30)
+        u = L.mvo_uf(7, 0, 0, 0, s.sweep, i)
+        ch, lw32 = oracle.stageB_tc(ps, acc, xx, tab[i], u, lnew, want_lw=True)
+        agree += int(ch == ch64[i])
+        ok = np.isfinite(lw64)
+        assert np.all(lw32[~ok] < -1e29)
+        worst = max(worst, np.max(np.abs(lw32[ok] - lw64[ok]) / np.maximum(1.0, np.abs(lw64[ok]))))
+    assert worst < 1e-5, worst
+    assert agree / n > 0.99, agree
+
+
 def test_leave_one_out_equals_explicit_removal(oracle):
     """Row weights must equal what one gets by really deleting the row and rebuilding the state."""
     views, z = make_mixture(80, [3, 2], 4, seed=2)
