@@ -57,16 +57,6 @@ struct Waiter {          // bounded polling: the clock is read every 256 polls
     return true;
   }
 };
-__device__ __forceinline__ bool ll_load_unit(const void* src, uint32_t seq, unsigned long long* payload, Waiter& w) {
-  uint32_t a, fa, b, fb;
-  for (;;) {
-    asm volatile("ld.volatile.global.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(a), "=r"(fa), "=r"(b), "=r"(fb) : "l"(src) : "memory");
-    if (fa == seq && fb == seq) break;
-    if (!w.keep_waiting()) return false;
-  }
-  *payload = (unsigned long long)a | ((unsigned long long)b << 32);
-  return true;
-}
 __device__ __forceinline__ bool ll_load_word(const void* src, uint32_t seq, uint32_t* payload, Waiter& w) {
   uint32_t a, fa;
   for (;;) {
