@@ -772,7 +772,7 @@ def _main(args, out):
     # ---------------- e2e: one chain through the C ABI with HOST buffers ---------------------------------------------------
     e2e = None
     if not args.no_e2e:
-        k_e2e = max(args.steps, 200)
+        k_e2e = max(args.steps, 1000)            # a chain, not an upload: the reference's own script runs M = 10 000 sweeps per call (New_Simulation.R:123-132)
         thin = max(1, k_e2e // 4)
         s2 = make_sampler(W, attach=False)       # handle (+ borrowed communicator): set-up, not part of a chain's run
         barrier()
