@@ -86,6 +86,43 @@ def test_tensor_core_mirror_agrees_with_fp64_restatement(oracle, shared_dishes):
     assert agree / n > 0.99, agree
 
 
+def test_dominant_option_shortcut_holds_in_the_mirror_arithmetic(oracle):
+    """The tensor-core kernel skips exponentials, totals and the scan when one option dominates: every other table at
+    least 31 below it in log2 and the new-table option at least 27 (csrc/mv_draw_tc.cu).  The claim behind it — the
+    full FP32 computation then returns the dominant option for EVERY uniform the stream can produce — is checked here
+    against the mirror that always runs the full computation, at the worst case the thresholds admit: all 63 other
+    tables exactly 31 below, the new table exactly 27 below, the smallest and the largest uniform.  (Parameters chosen
+    so that the log-weights are the inputs themselves: one view, A = C = 0, so lw[t] = acc[t] and lw[t0] = 0.)"""
+    cap, t0 = 64, 17
+    z = np.zeros((1, cap), np.float32)
+    P = {"dish": np.arange(cap, dtype=np.int32)[None, :].copy(), "A": z.copy(), "C": z.copy(), "A1": z.copy(), "C1": z.copy(),
+         "W": z.copy(), "W1": z.copy(), "lone": np.ones((1, cap), np.int32), "AN": np.zeros(1, np.float32),
+         "CN": np.zeros(1, np.float32), "WN": np.zeros(2, np.float32), "LD": np.zeros(2, np.float32),
+         "LM": np.zeros(cap, np.float32), "LM1": np.zeros(cap, np.float32), "single": np.zeros(cap, np.int32),
+         "LMN": np.zeros(2, np.float32)}
+    ps = oracle.params_struct(P)
+    xx = np.zeros(1, np.float32)
+    u_lo, u_hi = np.float32(2.0 ** -24), np.float32(1.0 - 2.0 ** -24)
+    for winner in ("own", "other-low", "other-high", "new"):
+        acc = np.full((1, cap), -31.0, np.float32)            # lw[t] = acc[t]; lw[t0] = 0 whatever acc[t0] is
+        lnew, want, shift = np.float32(-27.0), t0, 0.0
+        if winner.startswith("other"):
+            want, shift = (3 if winner == "other-low" else 60), 40.0   # a table before / after the own one in the scan
+            acc[:] = shift - 31.0
+            acc[0, want] = shift
+            lnew = np.float32(shift - 27.0)                    # (the own table, lw = 0, is 40 below: far)
+        if winner == "new":
+            want, lnew = -1, np.float32(40.0)
+            acc[:] = 40.0 - 31.0                               # every table (the own one, lw = 0, too) at least 31 below
+        for u in (u_lo, np.float32(0.5), u_hi):
+            ch, lw = oracle.stageB_tc(ps, acc, xx, t0, u, lnew, want_lw=True)
+            assert lw[t0] == 0.0
+            assert ch == want, (winner, float(u), ch)
+    # control: with the other tables only 20 below, the smallest uniform does land on one of them
+    acc = np.full((1, cap), -20.0, np.float32)
+    assert oracle.stageB_tc(ps, acc, xx, t0, u_lo, np.float32(-27.0)) != t0
+
+
 def test_leave_one_out_equals_explicit_removal(oracle):
     """Row weights must equal what one gets by really deleting the row and rebuilding the state."""
     views, z = make_mixture(80, [3, 2], 4, seed=2)
