@@ -118,6 +118,22 @@ def test_dominant_option_shortcut_holds_in_the_mirror_arithmetic(oracle):
             ch, lw = oracle.stageB_tc(ps, acc, xx, t0, u, lnew, want_lw=True)
             assert lw[t0] == 0.0
             assert ch == want, (winner, float(u), ch)
+    # random admissible configurations: any winner, the others anywhere at or below the thresholds
+    rng = np.random.default_rng(12)
+    for _ in range(300):
+        top = np.float32(rng.uniform(32.0, 60.0))             # (the own table sits at 0: keep it far as well)
+        acc = (top - 31.0 - rng.exponential(8.0, (1, cap))).astype(np.float32)
+        want = int(rng.integers(-1, cap))
+        lnew = np.float32(top - 27.0 - rng.exponential(8.0))
+        if want == -1:
+            lnew = top
+        elif want == t0:
+            acc = (-31.0 - rng.exponential(8.0, (1, cap))).astype(np.float32)
+            lnew = np.float32(-27.0 - rng.exponential(8.0))
+        else:
+            acc[0, want] = top
+        for u in (u_lo, u_hi, np.float32(rng.uniform(0.0, 1.0))):
+            assert oracle.stageB_tc(ps, acc, xx, t0, u, lnew) == want
     # control: with the other tables only 20 below, the smallest uniform does land on one of them
     acc = np.full((1, cap), -20.0, np.float32)
     assert oracle.stageB_tc(ps, acc, xx, t0, u_lo, np.float32(-27.0)) != t0
